@@ -1,0 +1,30 @@
+// dumphfdl_b200/csrc/common.cuh -- shared definitions for the sm_100a kernels and their host driver.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#ifdef HFDL_CUSIM
+#include "cusim.h"     // tests/cusim: host emulation for logic tests only (never part of the product build)
+#define HFDL_LAUNCH(kernel, grid, block, smem, stream, ...) cusim::launch(grid, block, smem, [&] { kernel(__VA_ARGS__); })
+#define HFDL_DYN_SMEM(type, name) CUSIM_DYN_SMEM(type, name)
+#else
+#include <cuda_runtime.h>
+#define HFDL_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define HFDL_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; type *name = reinterpret_cast<type *>(name##_raw_)
+#endif
+
+#define HFDL_CHECK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { \
+	fprintf(stderr, "hfdl_b200: CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, __LINE__, #call); return -1; } } while(0)
+
+typedef float2 cf;
+
+__host__ __device__ __forceinline__ cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__host__ __device__ __forceinline__ cf cmulc(cf a, cf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a*conj(b)
+__host__ __device__ __forceinline__ cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cf cscale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
+
+// sample formats (src/input-common.h sample_format)
+enum { HFDL_SFMT_CU8 = 1, HFDL_SFMT_CS16 = 2, HFDL_SFMT_CF32 = 3 };
+
+static inline int hfdl_ilog2(int64_t x) { int l = 0; while(((int64_t)1 << l) < x) l++; return l; }

@@ -1,0 +1,288 @@
+// dumphfdl_b200/csrc/ddc_kernels.cuh -- sm_100a kernels for the overlap-save channeliser:
+//   K0+K1  ingest (CU8/CS16/CF32 -> CF32, input-helpers.c:10-78) fused into the first pass of the
+//          forward FFT of the overlap-save window (fft.c:49-59, fft_fftw.c:22-41)
+//   K2+K3+K4  per-(channel, block) pass-band slice x tap spectrum, inverse FFT(M), 1/N, scrap,
+//          phase rotation and post-decimation (fastddc.c:152-215, libcsdr_gpl.c:41-74)
+//   K5     arbitrary resampler to 5400 Hz (msresamp_crcf, hfdl.c:472,676)
+//
+// Forward FFT layout.  N = L1*L2(*L3).  Pass p transforms axis p of the row-major view
+// [L1][L2][L3] in place, so the spectrum ends up "digit-scrambled": natural bin
+// k = k1 + L1*(k2 + L2*k3) lives at address (k1*L2 + k2)*L3 + k3.  No transposing pass is run:
+// the only consumers are the channel extractor (gathers M bins per channel through
+// fft_bin_addr()) and debug read-back.  fft_swap_sides (fastddc.c:102-112) is likewise folded
+// into that gather.  Every global access of the passes is a >=128-byte contiguous run.
+#pragma once
+#include "common.cuh"
+
+#define HFDL_TWN 4096          // twiddle table size: exp(-2*pi*i*k/4096); sub-FFT lengths <= 4096
+#define HFDL_FFT_THREADS 256
+#define HFDL_RS_TAPS 14        // resamp_crcf sub-filter length (2*m, m = 7)
+#define HFDL_RS_NPFB 256
+#define HFDL_RS_HIST (HFDL_RS_TAPS - 1)
+
+struct FftPlan {
+	int N, lgN, P;
+	int lgL[3];
+};
+
+__host__ __device__ __forceinline__ int fft_bin_addr(const FftPlan &pl, int k) {
+	if(pl.P == 1) return k;
+	int k1 = k & ((1 << pl.lgL[0]) - 1);
+	int r = k >> pl.lgL[0];
+	if(pl.P == 2) return (k1 << pl.lgL[1]) | r;
+	int k2 = r & ((1 << pl.lgL[1]) - 1);
+	int k3 = r >> pl.lgL[1];
+	return (((k1 << pl.lgL[1]) | k2) << pl.lgL[2]) | k3;
+}
+
+__device__ __forceinline__ int brev_n(int x, int bits) { return (int)(__brev((unsigned)x) >> (32 - bits)); }
+
+// In-place radix-2^2 DIT FFT over shared memory.  Element e of transform f lives at s[e*TP + f]
+// and must have been stored in bit-reversed element order.  nf transforms of length L = 1<<lgL.
+// dirsign = +1: forward (e^-j), -1: inverse (e^+j, unnormalised) -- FFTW_FORWARD/BACKWARD, fft_fftw.c:25.
+__device__ __forceinline__ void smem_fft(cf *s, int lgL, int nf, int TP, const cf *__restrict__ tw, int inverse) {
+	const int L = 1 << lgL;
+	const int tid = threadIdx.x, nth = blockDim.x;
+	int st = 0;
+	for(; st + 1 < lgL; st += 2) {
+		const int h = 1 << st;
+		const int items = nf * (L >> 2);
+		for(int w = tid; w < items; w += nth) {
+			int f = w % nf, q = w / nf;
+			int j = q & (h - 1);
+			int i0 = ((q >> st) << (st + 2)) + j;
+			cf w1 = __ldg(&tw[j * (HFDL_TWN >> (st + 1))]);
+			cf w2 = __ldg(&tw[j * (HFDL_TWN >> (st + 2))]);
+			if(inverse) { w1.y = -w1.y; w2.y = -w2.y; }
+			cf *p = s + i0 * TP + f;
+			const int hs = h * TP;
+			cf x0 = p[0], x1 = p[hs], x2 = p[2 * hs], x3 = p[3 * hs];
+			cf t1 = cmul(w1, x1), t3 = cmul(w1, x3);
+			cf a = cadd(x0, t1), b = csub(x0, t1), c = cadd(x2, t3), d = csub(x2, t3);
+			cf u = cmul(w2, c);
+			cf wd = cmul(w2, d);
+			// W_{4h}^{j+h} = -i * W_{4h}^j (forward), +i (inverse)
+			cf v = inverse ? make_float2(-wd.y, wd.x) : make_float2(wd.y, -wd.x);
+			p[0] = cadd(a, u);
+			p[hs] = cadd(b, v);
+			p[2 * hs] = csub(a, u);
+			p[3 * hs] = csub(b, v);
+		}
+		__syncthreads();
+	}
+	if(st < lgL) {      // odd log2: one radix-2 stage, h = L/2
+		const int h = 1 << st;
+		const int items = nf * (L >> 1);
+		for(int w = tid; w < items; w += nth) {
+			int f = w % nf, q = w / nf;
+			int j = q & (h - 1);
+			int i0 = ((q >> st) << (st + 1)) + j;
+			cf w1 = __ldg(&tw[j * (HFDL_TWN >> (st + 1))]);
+			if(inverse) w1.y = -w1.y;
+			cf *p = s + i0 * TP + f;
+			cf x0 = p[0], x1 = p[h * TP];
+			cf t = cmul(w1, x1);
+			p[0] = cadd(x0, t);
+			p[h * TP] = csub(x0, t);
+		}
+		__syncthreads();
+	}
+}
+
+// Source of the wideband stream for the first pass: a cyclic device buffer of raw samples.
+// Window b starts at stream position pos0 + b*block_stride; positions < 0 read as zero (the
+// reference's first window has a zeroed overlap, fft.c:79), others wrap modulo ring_len.
+struct RawSource {
+	const void *base;
+	long long ring_len;        // samples
+	long long pos0;            // stream position of window 0, element 0 (may be negative)
+	long long ring_origin;     // ring index that holds stream position 0 (mod ring_len)
+	long long block_stride;    // input_size
+	int sfmt;
+};
+
+__device__ __forceinline__ cf load_raw(const RawSource &src, long long pos) {
+	if(pos < 0) return make_float2(0.f, 0.f);
+	long long r = (pos + src.ring_origin) % src.ring_len;
+	if(src.sfmt == HFDL_SFMT_CF32) {
+		return reinterpret_cast<const cf *>(src.base)[r];                 // full_scale 1.0
+	} else if(src.sfmt == HFDL_SFMT_CS16) {
+		short2 v = reinterpret_cast<const short2 *>(src.base)[r];
+		const float fs = 32767.5f;                                        // SHRT_MAX + 0.5 (input-helpers.c:116)
+		return make_float2((float)v.x / fs, (float)v.y / fs);
+	} else {
+		uchar2 v = reinterpret_cast<const uchar2 *>(src.base)[r];
+		const float fs = 127.0f, shift = 63.5f;                           // input-helpers.c:54,110
+		return make_float2(((float)v.x - shift) / fs, ((float)v.y - shift) / fs);
+	}
+}
+
+// Column pass: FFT along an axis of stride 'inner' for T adjacent inner positions, then twiddle
+// W_{L*inner}^{k*n_rest}.  grid = (outer*inner/T, B).  FIRST: read the raw stream instead of 'work'.
+struct ColPassArgs {
+	RawSource src;
+	cf *work;
+	const cf *tw;
+	int N, lgL, inner, lgInner, T, first;
+};
+
+__global__ void __launch_bounds__(HFDL_FFT_THREADS) fft_col_pass(ColPassArgs a) {
+	HFDL_DYN_SMEM(cf, s);
+	const int L = 1 << a.lgL;
+	const int tiles_per_row = a.inner / a.T;
+	const int o = blockIdx.x / tiles_per_row;
+	const int n0 = (blockIdx.x % tiles_per_row) * a.T;
+	const int b = blockIdx.y;
+	const long long base = (long long)o * L * a.inner + n0;
+	const int total = L * a.T;
+	for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+		int t = idx % a.T, e = idx / a.T;
+		long long n = base + (long long)e * a.inner + t;
+		cf v;
+		if(a.first) v = load_raw(a.src, a.src.pos0 + (long long)b * a.src.block_stride + n);
+		else v = a.work[(long long)b * a.N + n];
+		s[brev_n(e, a.lgL) * a.T + t] = v;
+	}
+	__syncthreads();
+	smem_fft(s, a.lgL, a.T, a.T, a.tw, 0);
+	const float inv_np = 1.0f / (float)(L * a.inner);    // power of two: exact
+	for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+		int t = idx % a.T, k = idx / a.T;
+		float sn, cs;
+		// k*(n0+t) < L*inner <= 2^23: exact in fp32, so the twiddle angle is exact before sincospi
+		sincospif(-2.0f * (float)(k * (n0 + t)) * inv_np, &sn, &cs);
+		cf v = cmul(s[k * a.T + t], make_float2(cs, sn));
+		a.work[(long long)b * a.N + base + (long long)k * a.inner + t] = v;
+	}
+}
+
+// Row pass (last pass): R adjacent contiguous rows of length L.  grid = (N/L/R, B).
+struct RowPassArgs {
+	RawSource src;
+	cf *work;
+	const cf *tw;
+	int N, lgL, R, first;
+};
+
+__global__ void __launch_bounds__(HFDL_FFT_THREADS) fft_row_pass(RowPassArgs a) {
+	HFDL_DYN_SMEM(cf, s);
+	const int L = 1 << a.lgL;
+	const int TP = a.R + 1;
+	const int b = blockIdx.y;
+	const long long row0 = (long long)blockIdx.x * a.R;
+	const int total = L * a.R;
+	for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+		int e = idx & (L - 1), rr = idx >> a.lgL;
+		long long n = (row0 + rr) * L + e;
+		cf v;
+		if(a.first) v = load_raw(a.src, a.src.pos0 + (long long)b * a.src.block_stride + n);
+		else v = a.work[(long long)b * a.N + n];
+		s[brev_n(e, a.lgL) * TP + rr] = v;
+	}
+	__syncthreads();
+	smem_fft(s, a.lgL, a.R, TP, a.tw, 0);
+	for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+		int e = idx & (L - 1), rr = idx >> a.lgL;
+		a.work[(long long)b * a.N + (row0 + rr) * L + e] = s[e * TP + rr];
+	}
+}
+
+// Debug / init helper: gather natural-order bins [k0, k0+n) of window b out of the scrambled layout.
+__global__ void fft_gather_bins(const cf *work, FftPlan pl, int b, int k0, int n, cf *out) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if(i < n) out[i] = work[(long long)b * pl.N + fft_bin_addr(pl, (k0 + i) & (pl.N - 1))];
+}
+
+// Tap-slice extraction at init: tapslice[c][i'] = H_c[natural bin offsetbin_c + sgn(i')], i' in IFFT input order
+// (fastddc.c:229-230 computes the full N-bin tap spectrum; only the M bins the slice fold uses are kept).
+__global__ void tapslice_gather(const cf *work, FftPlan pl, int M, const int *offsetbin, int c0, cf *tapslice) {
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	int cl = blockIdx.y;      // window index within this FFT batch
+	if(i < M) {
+		int sg = i < M / 2 ? i : i - M;
+		int k = (offsetbin[c0 + cl] + sg) & (pl.N - 1);
+		tapslice[(long long)(c0 + cl) * M + i] = work[(long long)cl * pl.N + fft_bin_addr(pl, k)];
+	}
+}
+
+// K2+K3+K4.  grid = (C, B), block = HFDL_FFT_THREADS, smem = M*8.
+struct ChanArgs {
+	const cf *work;            // [B][N] scrambled spectra
+	const cf *tapslice;        // [C][M]
+	const int *offsetbin;      // [C]
+	const float *dsa_rate;     // [C] phase increment per output sample / pi (libcsdr_gpl.c:26-39)
+	cf *bb;                    // [C][bb_stride] baseband stream, HFDL_RS_HIST history samples first
+	const cf *tw;
+	FftPlan pl;
+	int M, lgM, scrap, post_dec, out_per_block;
+	long long bb_stride;
+	long long out_index0;      // global output-sample index of (block 0, output 0)
+	float inv_norm;            // 1/(pre_decimation*M) = 1/N (fastddc.c:193)
+};
+
+__global__ void __launch_bounds__(HFDL_FFT_THREADS) chan_extract(ChanArgs a) {
+	HFDL_DYN_SMEM(cf, s);
+	const int c = blockIdx.x, b = blockIdx.y;
+	const int off = a.offsetbin[c];
+	const cf *W = a.work + (long long)b * a.pl.N;
+	const cf *H = a.tapslice + (long long)c * a.M;
+	for(int i = threadIdx.x; i < a.M; i += blockDim.x) {
+		int sg = i < a.M / 2 ? i : i - a.M;
+		int k = (off + sg) & (a.pl.N - 1);
+		cf v = cmul(__ldg(&H[i]), W[fft_bin_addr(a.pl, k)]);
+		s[brev_n(i, a.lgM)] = v;
+	}
+	__syncthreads();
+	smem_fft(s, a.lgM, 1, 1, a.tw, 1);
+	const double cyc = 0.5 * (double)a.dsa_rate[c];     // cycles of phase per output sample
+	cf *out = a.bb + (long long)c * a.bb_stride + HFDL_RS_HIST + (long long)b * a.out_per_block;
+	for(int j = threadIdx.x; j < a.out_per_block; j += blockDim.x) {
+		long long g = a.out_index0 + (long long)b * a.out_per_block + j;
+		double fr = cyc * (double)g;
+		fr -= floor(fr);
+		float sn, cs;
+		sincospif((float)(2.0 * fr), &sn, &cs);
+		cf v = cscale(s[a.scrap + j * a.post_dec], a.inv_norm);
+		out[j] = make_float2(cs * v.x - sn * v.y, sn * v.x + cs * v.y);
+	}
+}
+
+// moves the last HFDL_RS_HIST baseband samples of a batch in front of the next one
+__global__ void bb_carry(cf *bb, long long bb_stride, long long n_new) {
+	int c = blockIdx.x, t = threadIdx.x;
+	cf v = make_float2(0.f, 0.f);
+	cf *row = bb + (long long)c * bb_stride;
+	if(t < HFDL_RS_HIST) v = row[n_new + t];
+	__syncthreads();
+	if(t < HFDL_RS_HIST) row[t] = v;
+}
+
+// K5: resamp_crcf with 24-bit fixed-point phase.  Output m of this batch is taken at
+// tau = phi0 + m*step (2^-24 input samples): input index tau>>24, filter (tau & 0xFFFFFF)>>16.
+struct ResampArgs {
+	const cf *bb; long long bb_stride;
+	cf *rs; long long rs_stride;
+	const float *h;            // [256][14]
+	unsigned long long phi0; unsigned step;
+	int n_out;
+};
+
+__global__ void resamp_kernel(ResampArgs a) {
+	int m = blockIdx.x * blockDim.x + threadIdx.x;
+	int c = blockIdx.y;
+	if(m >= a.n_out) return;
+	unsigned long long tau = a.phi0 + (unsigned long long)m * a.step;
+	long long i = (long long)(tau >> 24);
+	int idx = (int)((tau & 0xFFFFFFull) >> 16);
+	const cf *x = a.bb + (long long)c * a.bb_stride + HFDL_RS_HIST + i;
+	const float *h = a.h + idx * HFDL_RS_TAPS;
+	float re = 0.f, im = 0.f;
+#pragma unroll
+	for(int k = HFDL_RS_TAPS - 1; k >= 0; k--) {      // oldest sample first
+		cf v = x[-k];
+		float hk = __ldg(&h[k]);
+		re += hk * v.x;
+		im += hk * v.y;
+	}
+	a.rs[(long long)c * a.rs_stride + m] = make_float2(re, im);
+}

@@ -1,0 +1,587 @@
+// dumphfdl_b200/csrc/demod_kernels.cuh -- per-channel HFDL demodulator + framer (K6-K11) and
+// FEC (K12-K14) kernels for sm_100a.
+//
+// demod_kernel follows the per-sample / per-symbol loop of hfdl_decoder_thread (hfdl.c:685-893):
+// AGC -> 19-tap matched filter -> noise-floor tick -> symsync (16-arm Kaiser PFB, 2 outputs/symbol)
+// -> Costas -> T/2 LMS equaliser -> M-PSK slicer -> sampler -> framer FSM (A1/A2/M1/M2/T/data).
+// The feedback loops make this a strictly sequential recurrence per channel, so round 1 maps one
+// channel to one thread (channels are the only parallel axis the algorithm offers here) and keeps
+// the whole loop state in a per-channel struct in HBM between batches.
+// fec_kernel is decode_user_data (hfdl.c:993-1056): descramble + soft demod, 40-row deinterleaver
+// as a closed-form scatter/gather, chip averaging for r=1/4, K=7 Viterbi bit-exact with
+// libfec/viterbi27_port.c (one warp: 32 butterflies in 32 lanes, metrics exchanged by shuffles),
+// byte reversal and the frame check (pdu.c:68-79, mpdu.c:56-85, spdu.c:55-64).
+#pragma once
+#include "common.cuh"
+
+#define HFDL_MF_TAPS 19
+#define HFDL_SS_NPFB 16
+#define HFDL_SS_SUB 18
+#define HFDL_EQ_LEN 15
+#define HFDL_T_LEN 15
+#define HFDL_A_LEN 127
+#define HFDL_DATA_SYMS_MAX 5040
+#define HFDL_MAX_PDU 945
+#define HFDL_SINGLE_SLOT_FRAME_LEN 4219     // hfdl.c:41
+#define HFDL_FRAME_SLOTS 4                  // data-symbol buffers per channel (frames in flight per batch)
+
+enum { HS_EMIT_BITS = 1, HS_EMIT_SYMBOLS = 2, HS_SKIP = 3 };
+enum { HF_A1 = 1, HF_A2, HF_M1, HF_M2_SKIP, HF_EQ_TRAIN, HF_DATA_1, HF_DATA_2 };
+
+// constants shared by all channels (designed on the host at create time, see design.hpp)
+struct DemodTables {
+	float mf[HFDL_MF_TAPS];                          // hfdl.c:148-154
+	float ss_mf[HFDL_SS_NPFB][HFDL_SS_SUB];          // symsync matched-filter bank
+	float ss_dmf[HFDL_SS_NPFB][HFDL_SS_SUB];         // derivative bank
+	float ss_b0, ss_a1, ss_a2, ss_rate_adj;          // timing loop filter (lf_bw 0.001, hfdl.c:504)
+	cf eq_h0[HFDL_EQ_LEN];                           // eqlms lowpass initial weights (hfdl.c:495)
+	unsigned A_bits[4];                              // 127-bit templates, bit 0 of word 0 = newest
+	unsigned M1_bits[8][4];
+	cf psk[4][8];                                    // [arity][symbol] constellation (liquid modem PSK, gray coded)
+	unsigned char scr[120];                          // scrambler bits (hfdl.c:333-345)
+	int mode_arity[8], mode_segments[8], mode_code_rate[8], mode_col_shift[8];   // hfdl.c:81-138
+};
+
+struct DemodState {
+	float agc_g, agc_y2;
+	cf mf_win[HFDL_MF_TAPS];                 // [0] newest
+	cf ss_win_mf[HFDL_SS_SUB], ss_win_dmf[HFDL_SS_SUB];
+	unsigned ss_decim_counter;
+	float ss_rate, ss_del, ss_tau, ss_bf, ss_q, ss_q_hat;
+	int ss_b;
+	float ss_v[3];
+	float c_phi, c_dphi;
+	cf eq_w[HFDL_EQ_LEN], eq_win[HFDL_EQ_LEN];      // eq_win[0] oldest
+	float eq_x2[HFDL_EQ_LEN], eq_x2_sum;
+	unsigned eq_count; int eq_buf_full;
+	unsigned bits[4];                                // 127-bit shift register
+	cf training[HFDL_T_LEN]; int training_n;
+	int data_n, cur_buf, slot;
+	unsigned long long symbol_cnt, sample_cnt, a2_sample_cnt;
+	int s_state, fr_state, data_arity, cur_arity;
+	int symbols_wanted, search_retries, eq_train_seq_cnt, data_segment_cnt;
+	int train_bits_total, train_bits_bad, T_idx, M1;
+	unsigned bitmask, symsync_out_idx;
+	float freq_err_hz, signal_level, noise_floor;
+	unsigned nf_clk; float frame_symbol_cnt;
+	int st_a1, st_a2, st_m1, st_frames;
+};
+
+struct FrameRec {          // one completed frame handed from demod_kernel to fec_kernel
+	int channel, slot, M1;
+	unsigned bitmask;
+	float freq_err_hz, signal_level, noise_floor;
+	unsigned long long sample_cnt_a2, sample_cnt_end;
+	int train_bits_bad, train_bits_total;
+};
+
+struct PduRec {            // what the host turns into hfdl_pdu_metadata + octet_string (hfdl.c:1058-1080)
+	int channel, M1, len, crc_good;
+	float freq_err_hz, signal_level, noise_floor;
+	unsigned long long sample_cnt_a2, sample_cnt_end;
+	int train_bits_bad, train_bits_total;
+	unsigned char octets[HFDL_MAX_PDU + 3];
+};
+
+struct DemodArgs {
+	const cf *rs; long long rs_stride; int n_samples;
+	DemodState *state;
+	const DemodTables *tab;
+	cf *datasym;               // [C][HFDL_FRAME_SLOTS][HFDL_DATA_SYMS_MAX]
+	FrameRec *frames; int *nframes; int max_frames;
+	int C;
+	// optional capture of one channel's checkpoints (the reference's DATADUMPS taps, hfdl.c:616-655)
+	int cap_channel; cf *cap_agc, *cap_mf, *cap_eq; int *cap_cnt; int cap_max;
+};
+
+__device__ __forceinline__ void bits_push(unsigned *b, unsigned bit) {
+	b[3] = ((b[3] << 1) | (b[2] >> 31)) & 0x7FFFFFFFu;
+	b[2] = (b[2] << 1) | (b[1] >> 31);
+	b[1] = (b[1] << 1) | (b[0] >> 31);
+	b[0] = (b[0] << 1) | (bit & 1u);
+}
+__device__ __forceinline__ int bits_corr(const unsigned *a, const unsigned *b) {   // equal positions of 127
+	return 127 - (__popc(a[0] ^ b[0]) + __popc(a[1] ^ b[1]) + __popc(a[2] ^ b[2]) + __popc((a[3] ^ b[3]) & 0x7FFFFFFFu));
+}
+
+__device__ __forceinline__ void ss_reset(DemodState &S) {     // symsync_crcf_reset: mf window, timing state, loop filter
+	for(int i = 0; i < HFDL_SS_SUB; i++) S.ss_win_mf[i] = make_float2(0.f, 0.f);
+	S.ss_rate = 1.5f; S.ss_del = 1.5f;                       // k / k_out = 3/2
+	S.ss_b = 0; S.ss_bf = 0.f; S.ss_tau = 0.f; S.ss_q = 0.f; S.ss_q_hat = 0.f; S.ss_decim_counter = 0;
+	S.ss_v[0] = S.ss_v[1] = S.ss_v[2] = 0.f;
+}
+__device__ __forceinline__ void eq_reset(DemodState &S, const DemodTables &T) {
+	for(int i = 0; i < HFDL_EQ_LEN; i++) { S.eq_w[i] = T.eq_h0[i]; S.eq_win[i] = make_float2(0.f, 0.f); S.eq_x2[i] = 0.f; }
+	S.eq_count = 0; S.eq_buf_full = 0; S.eq_x2_sum = 0.f;
+}
+__device__ __forceinline__ void framer_reset(DemodState &S, const DemodTables &T) {   // hfdl.c:968-991
+	S.fr_state = HF_A1; S.symbols_wanted = 1; S.search_retries = 0; S.cur_arity = 1;
+	S.train_bits_total = S.train_bits_bad = 0; S.T_idx = 0; S.cur_buf = 0;
+	eq_reset(S, T);
+	S.data_n = 0; S.training_n = 0;
+	ss_reset(S);
+	S.s_state = HS_EMIT_BITS; S.bitmask = 0;
+}
+
+// hard decision + phase error: liquid modem_demodulate / get_demodulator_phase_error for BPSK, PSK4, PSK8
+__device__ __forceinline__ unsigned modem_demod(int m, cf x, const DemodTables &T, cf *x_hat) {
+	unsigned sym;
+	if(m == 1) {
+		sym = (x.x > 0.f) ? 0u : 1u;
+		*x_hat = make_float2(sym ? -1.0f : 1.0f, 0.f);
+	} else {
+		const int M = 1 << m;
+		const float alpha = (float)(M_PI / (float)M);
+		const float d_phi = (float)(M_PI * (1.0f - 1.0f / (float)M));
+		float theta = atan2f(x.y, x.x);
+		theta -= d_phi;
+		if(theta < -(float)M_PI) theta += (float)(2 * M_PI);
+		unsigned s = 0;
+		float v = theta;
+		for(int i = 0; i < m; i++) {
+			float ref = (float)(1 << (m - i - 1)) * alpha;
+			s <<= 1;
+			if(v > 0.f) { s |= 1u; v -= ref; } else { v += ref; }
+		}
+		sym = s ^ (s >> 1);
+		*x_hat = T.psk[m][sym];
+	}
+	return sym;
+}
+
+__global__ void demod_kernel(DemodArgs a) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if(c >= a.C) return;
+	const DemodTables &T = *a.tab;
+	DemodState S = a.state[c];
+	const cf *x = a.rs + (long long)c * a.rs_stride;
+	const bool cap = (c == a.cap_channel);
+	int cap_n_agc = 0, cap_n_eq = 0;
+	if(cap) { cap_n_agc = a.cap_cnt[0]; cap_n_eq = a.cap_cnt[1]; }
+	cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+
+	for(int k = 0; k < a.n_samples; k++, S.sample_cnt++) {
+		// ---- agc_crcf_execute (bandwidth 0.01, hfdl.c:485-487,686)
+		cf r = cscale(x[k], S.agc_g);
+		float y2 = r.x * r.x + r.y * r.y;
+		S.agc_y2 = (float)((1.0 - (double)0.01f) * (double)S.agc_y2 + (double)(0.01f * y2));
+		if(S.agc_y2 > 1e-6f) S.agc_g *= expf(-0.5f * 0.01f * logf(S.agc_y2));
+		if(S.agc_g > 1e6f) S.agc_g = 1e6f;
+		// ---- matched filter (firfilt_crcf, hfdl.c:694-695)
+		for(int i = HFDL_MF_TAPS - 1; i > 0; i--) S.mf_win[i] = S.mf_win[i - 1];
+		S.mf_win[0] = r;
+		cf s = make_float2(0.f, 0.f);
+		for(int i = HFDL_MF_TAPS - 1; i >= 0; i--) { s.x += T.mf[i] * S.mf_win[i].x; s.y += T.mf[i] * S.mf_win[i].y; }
+		if(cap && cap_n_agc < a.cap_max) { a.cap_agc[cap_n_agc] = r; a.cap_mf[cap_n_agc] = s; }
+		if(cap) cap_n_agc++;
+		// ---- noise floor (hfdl.c:700-706)
+		if(S.fr_state == HF_A1 && (++S.nf_clk & 0xFFu) == 0xFFu)
+			S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, 1.0f / S.agc_g) + 1e-6f;
+		// ---- symsync_crcf_execute (hfdl.c:707)
+		for(int i = HFDL_SS_SUB - 1; i > 0; i--) { S.ss_win_mf[i] = S.ss_win_mf[i - 1]; S.ss_win_dmf[i] = S.ss_win_dmf[i - 1]; }
+		S.ss_win_mf[0] = s; S.ss_win_dmf[0] = s;
+		cf symbols[4];
+		int produced = 0;
+		while(S.ss_b < HFDL_SS_NPFB) {
+			cf mf = make_float2(0.f, 0.f);
+			const float *h = T.ss_mf[S.ss_b];
+			for(int i = HFDL_SS_SUB - 1; i >= 0; i--) { mf.x += h[i] * S.ss_win_mf[i].x; mf.y += h[i] * S.ss_win_mf[i].y; }
+			if(produced < 4) symbols[produced] = make_float2(mf.x / 3.0f, mf.y / 3.0f);
+			if(S.ss_decim_counter == 2u) {
+				S.ss_decim_counter = 0;
+				cf dmf = make_float2(0.f, 0.f);
+				const float *dh = T.ss_dmf[S.ss_b];
+				for(int i = HFDL_SS_SUB - 1; i >= 0; i--) { dmf.x += dh[i] * S.ss_win_dmf[i].x; dmf.y += dh[i] * S.ss_win_dmf[i].y; }
+				float q = mf.x * dmf.x + mf.y * dmf.y;           // Re(conj(mf)*dmf)
+				q = fminf(fmaxf(q, -1.0f), 1.0f);
+				S.ss_q = q;
+				S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0];
+				S.ss_v[0] = q - T.ss_a1 * S.ss_v[1] - T.ss_a2 * S.ss_v[2];
+				S.ss_q_hat = T.ss_b0 * S.ss_v[0];
+				S.ss_rate += T.ss_rate_adj * S.ss_q_hat;
+				S.ss_del = S.ss_rate + S.ss_q_hat;
+			}
+			S.ss_decim_counter++;
+			S.ss_tau += S.ss_del;
+			S.ss_bf = S.ss_tau * (float)HFDL_SS_NPFB;
+			S.ss_b = (int)roundf(S.ss_bf);
+			produced++;
+		}
+		S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
+		if(produced > 4) produced = 4;
+
+		for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
+			// ---- Costas step + rotate (hfdl.c:250-294,709-715)
+			S.c_phi += S.c_dphi;
+			if((double)S.c_phi > M_PI) S.c_phi = (float)((double)S.c_phi - 2.0 * M_PI);
+			else if((double)S.c_phi < -M_PI) S.c_phi = (float)((double)S.c_phi + 2.0 * M_PI);
+			float sn, cs;
+			sincosf(S.c_phi, &sn, &cs);
+			r = make_float2(symbols[i].x * cs + symbols[i].y * sn, symbols[i].y * cs - symbols[i].x * sn);
+			if(fabsf(S.c_dphi) > 0.25f && S.fr_state == HF_A1) {
+				S.c_phi = S.c_dphi = 0.f;
+				ss_reset(S);
+			}
+			// ---- eqlms_cccf_push
+			for(int j = 0; j < HFDL_EQ_LEN - 1; j++) { S.eq_win[j] = S.eq_win[j + 1]; }
+			S.eq_win[HFDL_EQ_LEN - 1] = r;
+			{
+				float x2n = r.x * r.x + r.y * r.y, x20 = S.eq_x2[0];
+				for(int j = 0; j < HFDL_EQ_LEN - 1; j++) S.eq_x2[j] = S.eq_x2[j + 1];
+				S.eq_x2[HFDL_EQ_LEN - 1] = x2n;
+				S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
+				S.eq_count++;
+			}
+			if(!(S.symsync_out_idx & 1u)) continue;
+			// ---- eqlms_cccf_execute: y = sum conj(w[i]) * x[i]
+			s = make_float2(0.f, 0.f);
+			for(int j = 0; j < HFDL_EQ_LEN; j++) {
+				cf w = S.eq_w[j], v = S.eq_win[j];
+				s.x += w.x * v.x + w.y * v.y;
+				s.y += w.x * v.y - w.y * v.x;
+			}
+			if(S.fr_state == HF_EQ_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
+				float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
+				if(S.bitmask & 1u) d = -d;
+				bool run = true;
+				if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
+				if(run) {
+					cf al = make_float2(d - s.x, -s.y);                  // alpha = d - d_hat
+					float g = 0.1f;                                      // mu (hfdl.c:496)
+					for(int j = 0; j < HFDL_EQ_LEN; j++) {
+						cf v = S.eq_win[j];
+						// mu * conj(alpha) * x[j] / x2_sum
+						cf t = make_float2(g * al.x, -g * al.y);
+						cf u = cmul(t, v);
+						S.eq_w[j].x += u.x / S.eq_x2_sum;
+						S.eq_w[j].y += u.y / S.eq_x2_sum;
+					}
+				}
+				S.T_idx++;
+			}
+			if(cap && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s;
+			if(cap) cap_n_eq++;
+			cf x_hat;
+			unsigned bits = modem_demod(S.cur_arity, s, T, &x_hat);
+			// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
+			float err = s.y * x_hat.x - s.x * x_hat.y;
+			err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
+			S.c_phi += 0.1f * err;
+			S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
+
+			S.symbol_cnt++;
+			if(S.symbol_cnt >= 13ull * HFDL_SINGLE_SLOT_FRAME_LEN && S.fr_state == HF_A1) {
+				S.symbol_cnt = 0;
+				S.c_phi = S.c_dphi = 0.f;
+				ss_reset(S);
+			}
+			if(S.s_state == HS_EMIT_BITS) {
+				bits ^= S.bitmask;
+				for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
+			} else if(S.s_state == HS_EMIT_SYMBOLS) {
+				if(S.cur_buf == 0) { if(S.training_n < HFDL_T_LEN) S.training[S.training_n++] = s; }
+				else { if(S.data_n < HFDL_DATA_SYMS_MAX) dsym[S.data_n++] = s; }
+			}
+			if(S.fr_state > HF_A1) {
+				S.signal_level = (S.signal_level * S.frame_symbol_cnt + 1.0f / S.agc_g) / (S.frame_symbol_cnt + 1.0f);
+				S.frame_symbol_cnt += 1.0f;
+			}
+			if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }
+
+			switch(S.fr_state) {
+			case HF_A1: {
+				float corr = 2.0f * (float)bits_corr(T.A_bits, S.bits) / 127.0f - 1.0f;
+				if(fabsf(corr) > 0.36f) {
+					S.st_a1++;
+					S.bitmask = corr > 0.f ? 0u : ~0u;
+					S.signal_level = 1.0f / S.agc_g;
+					S.frame_symbol_cnt = 1.0f;
+					S.symbols_wanted = HFDL_A_LEN;
+					S.search_retries = 0;
+					S.fr_state = HF_A2;
+				}
+				break; }
+			case HF_A2: {
+				float corr = 2.0f * (float)bits_corr(T.A_bits, S.bits) / 127.0f - 1.0f;
+				if(fabsf(corr) > 0.3f) {
+					S.a2_sample_cnt = S.sample_cnt;
+					S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
+					S.st_a2++;
+					S.symbols_wanted = 127;
+					S.search_retries = 0;
+					S.fr_state = HF_M1;
+				} else if(++S.search_retries >= 3) {
+					framer_reset(S, T);
+				}
+				break; }
+			case HF_M1: {
+				float max_corr = 0.f; int max_idx = -1;
+				for(int idx = 0; idx < 8; idx++) {
+					float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
+					if(corr > max_corr) { max_corr = corr; max_idx = idx; }
+				}
+				if(max_corr > 0.3f) {
+					S.st_m1++;
+					S.data_segment_cnt = T.mode_segments[max_idx];
+					S.data_arity = T.mode_arity[max_idx];
+					S.M1 = max_idx;
+					S.symbols_wanted = 15;
+					S.search_retries = 0;
+					S.fr_state = HF_M2_SKIP;
+					S.s_state = HS_SKIP;
+				} else {
+					framer_reset(S, T);
+				}
+				break; }
+			case HF_M2_SKIP:
+				S.training_n = 0;
+				S.symbols_wanted = HFDL_T_LEN;
+				S.eq_train_seq_cnt = 9;
+				S.fr_state = HF_EQ_TRAIN;
+				S.s_state = HS_EMIT_SYMBOLS;
+				break;
+			case HF_EQ_TRAIN: {
+				unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
+				for(int j = 0; j < HFDL_T_LEN; j++) {
+					unsigned bit = (S.training[j].x > 0.f) ? 0u : 1u;
+					bit ^= (S.bitmask & 1u);
+					tseq = (tseq << 1) | bit;
+				}
+				S.train_bits_total += HFDL_T_LEN;
+				S.train_bits_bad += __popc(0x9AFu ^ tseq);
+				S.training_n = 0;
+				if(S.eq_train_seq_cnt > 1) {
+					S.eq_train_seq_cnt--;
+					S.symbols_wanted = HFDL_T_LEN;
+					S.T_idx = 0;
+				} else if(S.data_segment_cnt > 0) {
+					S.symbols_wanted = 15;
+					S.fr_state = HF_DATA_1;
+					S.cur_arity = S.data_arity;
+					S.cur_buf = 1;
+				} else {                                 // end of frame: hand the symbols to fec_kernel
+					int q = atomicAdd(a.nframes, 1);
+					if(q < a.max_frames) {
+						FrameRec fr;
+						fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
+						fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
+						fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = S.sample_cnt;
+						fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
+						a.frames[q] = fr;
+					}
+					S.st_frames++;
+					S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
+					dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+					framer_reset(S, T);
+					S.symbol_cnt = 0;
+				}
+				break; }
+			case HF_DATA_1:
+				S.symbols_wanted = 15;
+				S.fr_state = HF_DATA_2;
+				break;
+			case HF_DATA_2:
+				S.data_segment_cnt--;
+				S.cur_arity = 1;
+				S.cur_buf = 0;
+				S.fr_state = HF_EQ_TRAIN;
+				S.eq_train_seq_cnt = 1;
+				S.symbols_wanted = HFDL_T_LEN;
+				S.T_idx = 0;
+				break;
+			}
+		}
+	}
+	a.state[c] = S;
+	if(cap) { a.cap_cnt[0] = cap_n_agc; a.cap_cnt[1] = cap_n_eq; }
+}
+
+// ======================================================================================
+// FEC: one warp per completed frame.
+// ======================================================================================
+struct FecArgs {
+	const FrameRec *frames; const int *nframes; int max_frames;
+	const cf *datasym;                 // [C][SLOTS][5040]; or a bare symbol array when frames[].channel/slot are 0
+	const DemodTables *tab;
+	PduRec *pdus;                      // [max_frames]
+	unsigned char *soft_out;           // optional [max_frames][15120] soft bits in push order (debug/parity)
+	const unsigned char *vin_direct;   // stage entry hfdl_b200_viterbi27: [max_frames][2*vin_nbits] soft bytes, skips demod/deinterleave
+	int vin_nbits;
+};
+
+#define HFDL_FEC_VIN_MAX 15120
+#define HFDL_FEC_SMEM (HFDL_FEC_VIN_MAX + 7566 * 8)
+
+__device__ __forceinline__ unsigned crc16_x25_update(unsigned crc, unsigned byte) {    // crc.c:4-47, bitwise form
+	crc ^= byte;
+	for(int b = 0; b < 8; b++) crc = (crc & 1u) ? ((crc >> 1) ^ 0x8408u) : (crc >> 1);
+	return crc;
+}
+__device__ __forceinline__ int fcs_check(const unsigned char *buf, unsigned hdr_len) {  // pdu.c:68-79
+	unsigned crc = 0xFFFFu;
+	for(unsigned i = 0; i < hdr_len; i++) crc = crc16_x25_update(crc, buf[i]);
+	crc ^= 0xFFFFu;
+	unsigned rx = (unsigned)buf[hdr_len] | ((unsigned)buf[hdr_len + 1] << 8);
+	return rx == crc;
+}
+__device__ __forceinline__ int pdu_crc_good(const unsigned char *buf, unsigned len) {   // pdu.c:104, mpdu.c:56-85, spdu.c:55-64
+	if(len < 1) return 0;
+	if(buf[0] & 1u) {
+		unsigned hdr_len;
+		if(buf[0] & 0x2u) hdr_len = 6 + ((buf[0] >> 2) & 0xFu);
+		else {
+			unsigned ac = ((buf[0] & 0x70u) >> 4) + 1;
+			hdr_len = 2;
+			for(unsigned i = 0; i < ac; i++) {
+				if(len < hdr_len + 2) return 0;
+				hdr_len += 2 + (buf[hdr_len + 1] >> 4);
+			}
+		}
+		if(len < hdr_len + 2) return 0;
+		return fcs_check(buf, hdr_len);
+	}
+	if(len < 66) return 0;
+	return fcs_check(buf, 64u);
+}
+
+__global__ void __launch_bounds__(32) fec_kernel(FecArgs a) {
+	HFDL_DYN_SMEM(unsigned char, sm);
+	const int q = blockIdx.x;
+	int nfr = *a.nframes;
+	if(nfr > a.max_frames) nfr = a.max_frames;
+	if(q >= nfr) return;
+	const int lane = threadIdx.x;
+	const DemodTables &T = *a.tab;
+	const FrameRec fr = a.frames[q];
+	const int M1 = fr.M1;
+	const int arity = T.mode_arity[M1], code_rate = T.mode_code_rate[M1], shift = T.mode_col_shift[M1];
+	const int nsym = T.mode_segments[M1] * 30;
+	const int nenc = nsym * arity;
+	const int ncol = nenc / 40;
+	const cf *sym = a.datasym + ((long long)fr.channel * HFDL_FRAME_SLOTS + fr.slot) * HFDL_DATA_SYMS_MAX;
+	unsigned char *vin = sm;                                  // [<=15120] Viterbi input
+	unsigned char *table = sm + HFDL_FEC_VIN_MAX;             // [40][ncol], later overlaid by the decisions
+	uint2 *dec = reinterpret_cast<uint2 *>(sm + HFDL_FEC_VIN_MAX);   // [nbits+6] (.x even states, .y odd states)
+	const float pol = (fr.bitmask & 1u) ? -1.0f : 1.0f;
+	int vin_len = (code_rate == 4) ? nenc / 2 : nenc;
+
+	if(a.vin_direct) {
+		vin_len = 2 * a.vin_nbits;
+		for(int i = lane; i < vin_len; i += 32) vin[i] = a.vin_direct[(long long)q * vin_len + i];
+	} else {
+	// ---- descramble + soft demod + deinterleaver push (hfdl.c:1008-1018,387-399): closed form of the push
+	// sequence: soft bit i lands in row i%40, column (i/40 - shift*i) mod ncol
+	for(int i = lane; i < nsym; i += 32) {
+		float flip = (T.scr[i % 120] ? -1.0f : 1.0f) * pol;
+		cf x = make_float2(sym[i].x * flip, sym[i].y * flip);
+		unsigned char soft[3];
+		if(arity == 1) {
+			float LLR = -2.0f * x.x * 4.0f;
+			int sb = (int)__fadd_rn(__fmul_rn(LLR, 16.0f), 127.0f);
+			sb = sb > 255 ? 255 : (sb < 0 ? 0 : sb);
+			soft[0] = (unsigned char)sb;
+		} else {
+			cf xh;
+			unsigned s = modem_demod(arity, x, T, &xh);
+			if(arity == 2) {
+				soft[0] = (s & 2u) ? 255 : 0; soft[1] = (s & 1u) ? 255 : 0;
+			} else {
+				// liquid modem_demodulate_soft_table, p = 2 nearest neighbours (the adjacent PSK8 points)
+				const float gamma = 1.2f * 8.0f;
+				float dmin0[3], dmin1[3];
+				for(int k = 0; k < 3; k++) dmin0[k] = dmin1[k] = 4.0f;
+				float ex = __fsub_rn(x.x, xh.x), ey = __fsub_rn(x.y, xh.y);
+				float d = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+				for(int k = 0; k < 3; k++) { if((s >> (2 - k)) & 1u) dmin1[k] = d; else dmin0[k] = d; }
+				unsigned g = s; { unsigned mm = g >> 1; while(mm) { g ^= mm; mm >>= 1; } }   // gray decode
+				for(int n = 0; n < 2; n++) {
+					unsigned gg = (g + (n == 0 ? 1u : 7u)) & 7u;
+					unsigned nb = gg ^ (gg >> 1);
+					cf p = T.psk[3][nb];
+					ex = __fsub_rn(x.x, p.x); ey = __fsub_rn(x.y, p.y);
+					d = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+					for(int k = 0; k < 3; k++) {
+						if((nb >> (2 - k)) & 1u) { if(d < dmin1[k]) dmin1[k] = d; }
+						else { if(d < dmin0[k]) dmin0[k] = d; }
+					}
+				}
+				for(int k = 0; k < 3; k++) {
+					int sb = (int)__fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(dmin0[k], dmin1[k]), gamma), 16.0f), 127.0f);
+					sb = sb > 255 ? 255 : (sb < 0 ? 0 : sb);
+					soft[k] = (unsigned char)sb;
+				}
+			}
+		}
+		for(int j = 0; j < arity; j++) {
+			int p = i * arity + j;
+			int row = p % 40;
+			int col = (int)(((long long)(p / 40) - (long long)shift * p) % ncol);
+			if(col < 0) col += ncol;
+			table[row * ncol + col] = soft[j];
+			if(a.soft_out) a.soft_out[(long long)q * HFDL_FEC_VIN_MAX + p] = soft[j];
+		}
+	}
+	__syncwarp();
+	// ---- deinterleaver pop (hfdl.c:401-409): pop j reads row 9j%40, column j/40; r=1/4 averages chip pairs
+	for(int i = lane; i < vin_len; i += 32) {
+		if(code_rate == 4) {
+			int j0 = 2 * i, j1 = 2 * i + 1;
+			unsigned A = table[((9 * j0) % 40) * ncol + j0 / 40], B = table[((9 * j1) % 40) * ncol + j1 / 40];
+			vin[i] = (unsigned char)((A & B) + ((A ^ B) >> 1));
+		} else {
+			vin[i] = table[((9 * i) % 40) * ncol + i / 40];
+		}
+	}
+	}   // !vin_direct
+	__syncwarp();
+	// ---- Viterbi K=7 (viterbi27_port.c:147-221): lane i owns butterfly i -> new states 2i, 2i+1
+	const int nbits = vin_len / 2;
+	const unsigned bt0 = (__popc((2u * lane) & 0x6du) & 1) ? 255u : 0u;    // set_viterbi27_polynomial, :81-89
+	const unsigned bt1 = (__popc((2u * lane) & 0x4fu) & 1) ? 255u : 0u;
+	unsigned m_even = 63u, m_odd = 63u;                  // metrics of states 2*lane, 2*lane+1 (init_viterbi27 :65-79)
+	if(lane == 0) m_even = 0u;
+	for(int t = 0; t < nbits; t++) {
+		unsigned s0 = vin[2 * t], s1 = vin[2 * t + 1];
+		// old[i] and old[i+32] for butterfly i=lane: state i is held by lane i>>1 (even/odd slot i&1)
+		unsigned src_lo = (unsigned)lane >> 1, src_hi = 16u + ((unsigned)lane >> 1);
+		unsigned lo_e = __shfl_sync(0xffffffffu, m_even, src_lo), lo_o = __shfl_sync(0xffffffffu, m_odd, src_lo);
+		unsigned hi_e = __shfl_sync(0xffffffffu, m_even, src_hi), hi_o = __shfl_sync(0xffffffffu, m_odd, src_hi);
+		unsigned old_i = (lane & 1) ? lo_o : lo_e;
+		unsigned old_i32 = (lane & 1) ? hi_o : hi_e;
+		unsigned metric = (bt0 ^ s0) + (bt1 ^ s1);
+		unsigned a0 = old_i + metric, b0 = old_i32 + (510u - metric);
+		unsigned d0 = ((int)(a0 - b0) > 0) ? 1u : 0u;
+		m_even = d0 ? b0 : a0;
+		unsigned a1 = old_i + (510u - metric), b1 = old_i32 + metric;
+		unsigned d1 = ((int)(a1 - b1) > 0) ? 1u : 0u;
+		m_odd = d1 ? b1 : a1;
+		unsigned de = __ballot_sync(0xffffffffu, d0), dod = __ballot_sync(0xffffffffu, d1);
+		if(lane == 0) dec[t] = make_uint2(de, dod);
+	}
+	__syncwarp();
+	// ---- chainback from state 0, reading 6 steps ahead; the 6 steps past the end were never written
+	// by the reference (calloc'd zero) -> zeros here (viterbi27_port.c:105-134)
+	PduRec *out = &a.pdus[q];
+	const int out_octets = nbits / 8 + ((nbits % 8) ? 1 : 0);
+	if(lane == 0) {
+		unsigned endstate = 0;
+		for(int i = 0; i < out_octets; i++) out->octets[i] = 0;
+		for(int n = nbits - 1; n >= 0; n--) {
+			unsigned st = endstate >> 2;
+			unsigned k = 0;
+			if(n + 6 < nbits) {
+				uint2 d = dec[n + 6];
+				k = (((st & 1u) ? d.y : d.x) >> (st >> 1)) & 1u;
+			}
+			endstate = ((endstate >> 1) | (k << 7)) & 0xFFu;
+			out->octets[n >> 3] = (unsigned char)endstate;
+		}
+		if(!a.vin_direct) for(int i = 0; i < out_octets; i++)  // REVERSE_BYTE (util.h:109, hfdl.c:1051-1053)
+			out->octets[i] = (unsigned char)(__brev((unsigned)out->octets[i]) >> 24);
+		out->channel = fr.channel; out->M1 = M1; out->len = out_octets;
+		out->freq_err_hz = fr.freq_err_hz; out->signal_level = fr.signal_level; out->noise_floor = fr.noise_floor;
+		out->sample_cnt_a2 = fr.sample_cnt_a2; out->sample_cnt_end = fr.sample_cnt_end;
+		out->train_bits_bad = fr.train_bits_bad; out->train_bits_total = fr.train_bits_total;
+		out->crc_good = pdu_crc_good(out->octets, (unsigned)out_octets);
+	}
+}

@@ -1,0 +1,711 @@
+// dumphfdl_b200/csrc/frontend.cu -- host driver + C ABI (include/hfdl_b200.h) of the B200 front-end.
+// Owns the CUDA stream, the HBM layout and the batch schedule; all arithmetic on the sample path runs
+// in the kernels of ddc_kernels.cuh / demod_kernels.cuh.  There is no CPU implementation of the path
+// in this library: without a CUDA device hfdl_b200_create() fails.
+#include <vector>
+#include <deque>
+#include <string>
+#include <thread>
+#include <algorithm>
+#include <string.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "ddc_kernels.cuh"
+#include "demod_kernels.cuh"
+#include "design.hpp"
+#include "../../include/hfdl_b200.h"
+
+#define CK(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { \
+	fprintf(stderr, "hfdl_b200: CUDA error '%s' at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -1; } } while(0)
+
+namespace {
+
+enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_DEMOD, KC_FEC, KC_COUNT };
+const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "demod", "fec" };
+
+struct ProfRec { int cls; cudaEvent_t e0, e1; };
+
+FftPlan make_plan(int N) {
+	FftPlan p;
+	memset(&p, 0, sizeof(p));
+	p.N = N; p.lgN = hfdl_ilog2(N);
+	int lg = p.lgN;
+	if(lg <= 12) { p.P = 1; p.lgL[0] = lg; }
+	else if(lg <= 18) { p.P = 2; p.lgL[0] = lg / 2; p.lgL[1] = lg - p.lgL[0]; }
+	else { p.P = 3; p.lgL[0] = lg / 3; p.lgL[1] = (lg - p.lgL[0]) / 2; p.lgL[2] = lg - p.lgL[0] - p.lgL[1]; }
+	return p;
+}
+
+int tile_for(int lgL) {          // columns (or rows) per CTA: keep the tile <= 64 KiB
+	int t = 8192 >> lgL;
+	if(t > 16) t = 16;
+	if(t < 1) t = 1;
+	return t;
+}
+
+struct FftEngine {
+	cf *d_tw = nullptr;
+	bool attrs_set = false;
+	int init() {
+		std::vector<cf> tw(HFDL_TWN);
+		for(int i = 0; i < HFDL_TWN; i++) {
+			double a = -2.0 * M_PI * (double)i / (double)HFDL_TWN;
+			tw[i] = make_float2((float)cos(a), (float)sin(a));
+		}
+		CK(cudaMalloc((void **)&d_tw, sizeof(cf) * HFDL_TWN));
+		CK(cudaMemcpy(d_tw, tw.data(), sizeof(cf) * HFDL_TWN, cudaMemcpyHostToDevice));
+		CK(cudaFuncSetAttribute(fft_col_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(chan_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+		CK(cudaFuncSetAttribute(fec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_FEC_SMEM));
+		return 0;
+	}
+	void destroy() { if(d_tw) cudaFree(d_tw); d_tw = nullptr; }
+};
+
+}  // namespace
+
+struct hfdl_b200_frontend {
+	hfdl_b200_config_t cfg;
+	std::vector<int32_t> freqs;
+	hfdl_design::Geometry g;
+	std::vector<hfdl_design::ChannelGeom> chg;
+	FftPlan plan;
+	int C = 0, Bmax = 0, sfmt = 0, bps = 0, out_per_block = 0;
+	float resamp_rate = 0;
+	cudaStream_t stream = nullptr;
+	FftEngine fft;
+	// device memory
+	cf *d_work = nullptr; void *d_ring = nullptr; long long ring_len = 0;
+	cf *d_tapslice = nullptr; int *d_offsetbin = nullptr; float *d_dsa_rate = nullptr;
+	cf *d_bb = nullptr; long long bb_stride = 0;
+	cf *d_rs = nullptr; long long rs_stride = 0; float *d_rs_h = nullptr;
+	DemodTables *d_tab = nullptr; DemodState *d_state = nullptr; cf *d_datasym = nullptr;
+	FrameRec *d_frames = nullptr; int *d_nframes = nullptr; PduRec *d_pdus = nullptr; int max_frames = 0;
+	cf *d_cap_agc = nullptr, *d_cap_mf = nullptr, *d_cap_eq = nullptr; int *d_cap_cnt = nullptr;
+	cf *d_tmp = nullptr; long long tmp_len = 0;
+	// host state
+	PduRec *h_pdus = nullptr; int *h_nframes = nullptr;
+	long long fed = 0;              // samples pushed so far (host-fed path)
+	long long blocks_done = 0;      // overlap-save blocks processed
+	unsigned long long rs_phi0 = 0; unsigned rs_step = 0;
+	int last_nblocks = 0, last_nout = 0;
+	std::deque<hfdl_b200_pdu_t> pduq;
+	long long launches = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	bool profiling = false;
+	std::vector<ProfRec> prof;
+	float prof_ms[KC_COUNT] = { 0 }; int prof_n[KC_COUNT] = { 0 };
+};
+
+namespace {
+
+inline void prof_begin(hfdl_b200_frontend *fe, int cls, ProfRec &r) {
+	r.cls = -1;
+	if(!fe || !fe->profiling) return;
+	r.cls = cls;
+	cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+	cudaEventRecord(r.e0, fe->stream);
+}
+inline void prof_end(hfdl_b200_frontend *fe, ProfRec &r) {
+	if(r.cls < 0) return;
+	cudaEventRecord(r.e1, fe->stream);
+	fe->prof.push_back(r);
+}
+
+// forward FFT of nb windows described by src into work (scrambled layout)
+int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, const RawSource &src, cf *work, int nb, cudaStream_t st) {
+	int inner = pl.N;
+	int outer = 1;
+	for(int p = 0; p < pl.P; p++) {
+		int lgL = pl.lgL[p], L = 1 << lgL;
+		inner /= L;
+		ProfRec pr;
+		prof_begin(fe, KC_FFT1 + p, pr);
+		if(p < pl.P - 1) {
+			ColPassArgs a;
+			a.src = src; a.work = work; a.tw = eng.d_tw; a.N = pl.N; a.lgL = lgL; a.inner = inner; a.lgInner = hfdl_ilog2(inner);
+			a.T = tile_for(lgL); if(a.T > inner) a.T = inner;
+			a.first = (p == 0);
+			dim3 grid((unsigned)(outer * (inner / a.T)), (unsigned)nb);
+			size_t smem = sizeof(cf) * (size_t)L * a.T;
+			HFDL_LAUNCH(fft_col_pass, grid, dim3(HFDL_FFT_THREADS), smem, st, a);
+		} else {
+			RowPassArgs a;
+			a.src = src; a.work = work; a.tw = eng.d_tw; a.N = pl.N; a.lgL = lgL; a.R = tile_for(lgL);
+			int rows = pl.N / L;
+			if(a.R > rows) a.R = rows;
+			a.first = (p == 0);
+			dim3 grid((unsigned)(rows / a.R), (unsigned)nb);
+			size_t smem = sizeof(cf) * (size_t)L * (a.R + 1);
+			HFDL_LAUNCH(fft_row_pass, grid, dim3(HFDL_FFT_THREADS), smem, st, a);
+		}
+		prof_end(fe, pr);
+		if(fe) fe->launches++;
+		outer *= L;
+	}
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int bytes_per_sample(int sfmt) { return sfmt == HFDL_SFMT_CF32 ? 8 : (sfmt == HFDL_SFMT_CS16 ? 4 : 2); }
+
+void to_pdu(const hfdl_b200_frontend *fe, const PduRec &r, hfdl_b200_pdu_t &p) {    // dispatch_pdu, hfdl.c:1058-1080
+	static const int ar[8] = { 1, 1, 2, 3, 1, 1, 2, 3 }, cr[8] = { 4, 2, 2, 2, 4, 2, 2, 2 };
+	memset(&p, 0, sizeof(p));
+	p.version = 1;
+	p.freq = fe->freqs[r.channel];
+	p.bit_rate = 1800 * ar[r.M1] / cr[r.M1] * 30 / (30 + 15);
+	p.freq_err_hz = r.freq_err_hz;
+	p.rssi = 20.0f * log10f(r.signal_level);
+	p.noise_floor = 20.0f * log10f(r.noise_floor);
+	p.slot = r.M1 < 4 ? 'S' : 'D';
+	p.M1 = r.M1; p.crc_good = r.crc_good;
+	p.train_bits_bad = r.train_bits_bad; p.train_bits_total = r.train_bits_total;
+	p.sample_cnt_a2 = r.sample_cnt_a2; p.sample_cnt_end = r.sample_cnt_end;
+	p.rx_time_s = (double)r.sample_cnt_a2 / 5400.0 - (448.0 + 2 * 127.0) / 1800.0;
+	p.signal_level = r.signal_level; p.noise_floor_lin = r.noise_floor;
+	p.len = r.len;
+	memcpy(p.octets, r.octets, (size_t)r.len);
+}
+
+// one group of nb <= Bmax blocks: FFT -> channel extract -> resample -> demod -> FEC -> PDUs to host
+int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
+	cudaStream_t st = fe->stream;
+	const auto &g = fe->g;
+	CK(cudaMemsetAsync(fe->d_nframes, 0, sizeof(int), st));
+	if(run_fft(fe, fe->fft, fe->plan, src, fe->d_work, nb, st)) return -1;
+	ProfRec pr;
+	{
+		ChanArgs a;
+		a.work = fe->d_work; a.tapslice = fe->d_tapslice; a.offsetbin = fe->d_offsetbin; a.dsa_rate = fe->d_dsa_rate;
+		a.bb = fe->d_bb; a.tw = fe->fft.d_tw; a.pl = fe->plan;
+		a.M = g.fft_inv_size; a.lgM = hfdl_ilog2(g.fft_inv_size); a.scrap = g.scrap; a.post_dec = g.post_decimation;
+		a.out_per_block = fe->out_per_block; a.bb_stride = fe->bb_stride;
+		a.out_index0 = fe->blocks_done * (long long)fe->out_per_block;
+		a.inv_norm = 1.0f / (float)(g.pre_decimation * g.fft_inv_size);
+		prof_begin(fe, KC_CHAN, pr);
+		HFDL_LAUNCH(chan_extract, dim3((unsigned)fe->C, (unsigned)nb), dim3(HFDL_FFT_THREADS), sizeof(cf) * (size_t)a.M, st, a);
+		prof_end(fe, pr);
+		fe->launches++;
+	}
+	const long long n_in = (long long)nb * fe->out_per_block;
+	int n_out = 0;
+	{
+		unsigned long long span = (unsigned long long)n_in << 24;
+		if(fe->rs_phi0 < span) n_out = (int)((span - fe->rs_phi0 + fe->rs_step - 1) / fe->rs_step);
+		ResampArgs a;
+		a.bb = fe->d_bb; a.bb_stride = fe->bb_stride; a.rs = fe->d_rs; a.rs_stride = fe->rs_stride; a.h = fe->d_rs_h;
+		a.phi0 = fe->rs_phi0; a.step = fe->rs_step; a.n_out = n_out;
+		if(n_out > 0) {
+			prof_begin(fe, KC_RESAMP, pr);
+			HFDL_LAUNCH(resamp_kernel, dim3((unsigned)((n_out + 255) / 256), (unsigned)fe->C), dim3(256), 0, st, a);
+			prof_end(fe, pr);
+			fe->launches++;
+		}
+		fe->rs_phi0 = fe->rs_phi0 + (unsigned long long)n_out * fe->rs_step - span;
+		HFDL_LAUNCH(bb_carry, dim3((unsigned)fe->C), dim3(32), 0, st, fe->d_bb, fe->bb_stride, n_in);
+		fe->launches++;
+	}
+	{
+		DemodArgs a;
+		a.rs = fe->d_rs; a.rs_stride = fe->rs_stride; a.n_samples = n_out;
+		a.state = fe->d_state; a.tab = fe->d_tab; a.datasym = fe->d_datasym;
+		a.frames = fe->d_frames; a.nframes = fe->d_nframes; a.max_frames = fe->max_frames; a.C = fe->C;
+		a.cap_channel = fe->cfg.capture_channel; a.cap_agc = fe->d_cap_agc; a.cap_mf = fe->d_cap_mf; a.cap_eq = fe->d_cap_eq;
+		a.cap_cnt = fe->d_cap_cnt; a.cap_max = fe->cfg.capture_max;
+		prof_begin(fe, KC_DEMOD, pr);
+		HFDL_LAUNCH(demod_kernel, dim3((unsigned)((fe->C + 31) / 32)), dim3(32), 0, st, a);
+		prof_end(fe, pr);
+		fe->launches++;
+	}
+	{
+		FecArgs a;
+		a.frames = fe->d_frames; a.nframes = fe->d_nframes; a.max_frames = fe->max_frames; a.datasym = fe->d_datasym;
+		a.tab = fe->d_tab; a.pdus = fe->d_pdus; a.soft_out = nullptr; a.vin_direct = nullptr; a.vin_nbits = 0;
+		prof_begin(fe, KC_FEC, pr);
+		HFDL_LAUNCH(fec_kernel, dim3((unsigned)fe->max_frames), dim3(32), HFDL_FEC_SMEM, st, a);
+		prof_end(fe, pr);
+		fe->launches++;
+	}
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(fe->h_nframes, fe->d_nframes, sizeof(int), cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	int nfr = *fe->h_nframes;
+	if(nfr > fe->max_frames) {
+		fprintf(stderr, "hfdl_b200: frame queue overflow (%d > %d), frames dropped\n", nfr, fe->max_frames);
+		nfr = fe->max_frames;
+	}
+	if(nfr > 0) {
+		CK(cudaMemcpyAsync(fe->h_pdus, fe->d_pdus, sizeof(PduRec) * (size_t)nfr, cudaMemcpyDeviceToHost, st));
+		CK(cudaStreamSynchronize(st));
+		// canonical order within a batch: (end sample, channel) -- the reference emits in thread-race order
+		std::vector<int> order((size_t)nfr);
+		for(int i = 0; i < nfr; i++) order[(size_t)i] = i;
+		std::sort(order.begin(), order.end(), [&](int x, int y) {
+			const PduRec &a = fe->h_pdus[x], &b = fe->h_pdus[y];
+			if(a.sample_cnt_end != b.sample_cnt_end) return a.sample_cnt_end < b.sample_cnt_end;
+			return a.channel < b.channel;
+		});
+		for(int i : order) { hfdl_b200_pdu_t p; to_pdu(fe, fe->h_pdus[i], p); fe->pduq.push_back(p); }
+	}
+	fe->blocks_done += nb;
+	fe->last_nblocks = nb; fe->last_nout = n_out;
+	return 0;
+}
+
+int compute_tapslices(hfdl_b200_frontend *fe) {
+	// fft_channelizer_create (fastddc.c:217-252): taps -> N-point forward FFT; keep the M bins of the slice
+	const auto &g = fe->g;
+	const int N = g.fft_size, M = g.fft_inv_size, C = fe->C;
+	int chunk = std::min(fe->Bmax, C);
+	cf *d_in = nullptr;
+	CK(cudaMalloc((void **)&d_in, sizeof(cf) * (size_t)N * chunk));
+	std::vector<std::vector<std::complex<float>>> taps((size_t)chunk);
+	for(int c0 = 0; c0 < C; c0 += chunk) {
+		int nc = std::min(chunk, C - c0);
+		std::vector<std::thread> th;
+		for(int i = 0; i < nc; i++) th.emplace_back([&, i] {
+			float fs = fe->chg[(size_t)(c0 + i)].freq_shift;
+			float half = 0.5f / g.decimation;
+			hfdl_design::bandpass_taps(taps[(size_t)i], g.taps_length, (-fs) - half, (-fs) + half);
+		});
+		for(auto &t : th) t.join();
+		CK(cudaMemsetAsync(d_in, 0, sizeof(cf) * (size_t)N * nc, fe->stream));
+		for(int i = 0; i < nc; i++)
+			CK(cudaMemcpyAsync(d_in + (size_t)i * N, taps[(size_t)i].data(), sizeof(cf) * (size_t)g.taps_length, cudaMemcpyHostToDevice, fe->stream));
+		RawSource src;
+		src.base = d_in; src.ring_len = (long long)N * nc; src.pos0 = 0; src.ring_origin = 0; src.block_stride = N; src.sfmt = HFDL_SFMT_CF32;
+		if(run_fft(nullptr, fe->fft, fe->plan, src, fe->d_work, nc, fe->stream)) return -1;
+		HFDL_LAUNCH(tapslice_gather, dim3((unsigned)((M + 255) / 256), (unsigned)nc), dim3(256), 0, fe->stream,
+			fe->d_work, fe->plan, M, fe->d_offsetbin, c0, fe->d_tapslice);
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(fe->stream));
+	}
+	cudaFree(d_in);
+	return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t hfdl_b200_device_count(void) {
+	int n = 0;
+	if(cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+int32_t hfdl_b200_pdu_len(int32_t M1) { return (M1 < 0 || M1 > 7) ? -1 : hfdl_design::pdu_len(M1); }
+
+int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *cfg) {
+	if(!out || !cfg || cfg->nfreq < 1 || !cfg->freqs_hz) { fprintf(stderr, "hfdl_b200_create: bad arguments\n"); return -1; }
+	if(hfdl_b200_device_count() < 1) { fprintf(stderr, "hfdl_b200_create: no CUDA device -- this library has no CPU path\n"); return -1; }
+	if(cfg->sample_format < HFDL_SFMT_CU8 || cfg->sample_format > HFDL_SFMT_CF32) { fprintf(stderr, "hfdl_b200_create: bad sample format\n"); return -1; }
+	hfdl_b200_frontend *fe = new hfdl_b200_frontend();
+	fe->cfg = *cfg;
+	fe->freqs.assign(cfg->freqs_hz, cfg->freqs_hz + cfg->nfreq);
+	fe->cfg.freqs_hz = fe->freqs.data();
+	fe->C = cfg->nfreq;
+	fe->sfmt = cfg->sample_format;
+	fe->bps = bytes_per_sample(fe->sfmt);
+	if(!hfdl_design::geometry_init(fe->g, cfg->sample_rate)) { fprintf(stderr, "hfdl_b200_create: unsupported sample rate %d\n", cfg->sample_rate); delete fe; return -1; }
+	const auto &g = fe->g;
+	// check_frequency_span (main.c:214-226)
+	for(int i = 0; i < fe->C; i++) {
+		if(abs(cfg->centerfreq_hz - fe->freqs[(size_t)i]) >= cfg->sample_rate / 2) {
+			fprintf(stderr, "hfdl_b200_create: channel %d Hz too far from the centre frequency %d Hz\n", fe->freqs[(size_t)i], cfg->centerfreq_hz);
+			delete fe; return -1;
+		}
+		fe->chg.push_back(hfdl_design::channel_geom(g, cfg->sample_rate, cfg->centerfreq_hz, fe->freqs[(size_t)i]));
+	}
+	fe->out_per_block = g.post_input_size / g.post_decimation;
+	if(g.post_input_size % g.post_decimation != 0 || hfdl_ilog2(g.fft_inv_size) > 12 || g.fft_size > (1 << 27)) {
+		fprintf(stderr, "hfdl_b200_create: geometry outside the supported range\n"); delete fe; return -1;
+	}
+	fe->resamp_rate = (float)(1800 * 3) / ((float)cfg->sample_rate / (float)g.decimation);     // hfdl.c:471
+	if(!(fe->resamp_rate >= 0.5f && fe->resamp_rate <= 1.0f)) { fprintf(stderr, "hfdl_b200_create: resampling rate %f outside [0.5,1]\n", fe->resamp_rate); delete fe; return -1; }
+	fe->plan = make_plan(g.fft_size);
+	fe->Bmax = cfg->max_blocks_per_batch > 0 ? cfg->max_blocks_per_batch : std::max(1, std::min(64, (int)((256ll << 20) / ((long long)g.fft_size * 8))));
+	if(cfg->capture_channel >= fe->C) fe->cfg.capture_channel = -1;
+	if(fe->cfg.capture_max < 0) fe->cfg.capture_max = 0;
+
+#define CKD(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { fprintf(stderr, "hfdl_b200_create: CUDA error '%s' (%s)\n", cudaGetErrorString(e_), #call); hfdl_b200_destroy(fe); return -1; } } while(0)
+	CKD(cudaSetDevice(cfg->device));
+	CKD(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
+	if(fe->fft.init()) { hfdl_b200_destroy(fe); return -1; }
+	const int C = fe->C, N = g.fft_size, M = g.fft_inv_size, B = fe->Bmax;
+	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * B));
+	fe->ring_len = (long long)g.overlap_length + (long long)(B + 1) * g.input_size;
+	CKD(cudaMalloc(&fe->d_ring, (size_t)fe->ring_len * fe->bps));
+	CKD(cudaMemset(fe->d_ring, 0, (size_t)fe->ring_len * fe->bps));
+	CKD(cudaMalloc((void **)&fe->d_tapslice, sizeof(cf) * (size_t)C * M));
+	CKD(cudaMalloc((void **)&fe->d_offsetbin, sizeof(int) * (size_t)C));
+	CKD(cudaMalloc((void **)&fe->d_dsa_rate, sizeof(float) * (size_t)C));
+	{
+		std::vector<int> ob((size_t)C); std::vector<float> dr((size_t)C);
+		for(int i = 0; i < C; i++) { ob[(size_t)i] = fe->chg[(size_t)i].offsetbin; dr[(size_t)i] = fe->chg[(size_t)i].dsa_rate; }
+		CKD(cudaMemcpy(fe->d_offsetbin, ob.data(), sizeof(int) * (size_t)C, cudaMemcpyHostToDevice));
+		CKD(cudaMemcpy(fe->d_dsa_rate, dr.data(), sizeof(float) * (size_t)C, cudaMemcpyHostToDevice));
+	}
+	fe->bb_stride = HFDL_RS_HIST + (long long)B * fe->out_per_block + 16;
+	CKD(cudaMalloc((void **)&fe->d_bb, sizeof(cf) * (size_t)C * fe->bb_stride));
+	CKD(cudaMemset(fe->d_bb, 0, sizeof(cf) * (size_t)C * fe->bb_stride));
+	fe->rs_stride = (long long)B * fe->out_per_block + 16;
+	CKD(cudaMalloc((void **)&fe->d_rs, sizeof(cf) * (size_t)C * fe->rs_stride));
+	{
+		std::vector<float> h((size_t)HFDL_RS_NPFB * HFDL_RS_TAPS);
+		hfdl_design::resamp_design(fe->resamp_rate, h.data(), &fe->rs_step);
+		CKD(cudaMalloc((void **)&fe->d_rs_h, sizeof(float) * h.size()));
+		CKD(cudaMemcpy(fe->d_rs_h, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice));
+	}
+	{
+		DemodTables *T = new DemodTables();
+		hfdl_design::demod_tables(*T);
+		CKD(cudaMalloc((void **)&fe->d_tab, sizeof(DemodTables)));
+		CKD(cudaMemcpy(fe->d_tab, T, sizeof(DemodTables), cudaMemcpyHostToDevice));
+		std::vector<DemodState> st((size_t)C);
+		for(int i = 0; i < C; i++) hfdl_design::demod_state_init(st[(size_t)i], *T);
+		CKD(cudaMalloc((void **)&fe->d_state, sizeof(DemodState) * (size_t)C));
+		CKD(cudaMemcpy(fe->d_state, st.data(), sizeof(DemodState) * (size_t)C, cudaMemcpyHostToDevice));
+		delete T;
+	}
+	CKD(cudaMalloc((void **)&fe->d_datasym, sizeof(cf) * (size_t)C * HFDL_FRAME_SLOTS * HFDL_DATA_SYMS_MAX));
+	fe->max_frames = C * HFDL_FRAME_SLOTS;
+	CKD(cudaMalloc((void **)&fe->d_frames, sizeof(FrameRec) * (size_t)fe->max_frames));
+	CKD(cudaMalloc((void **)&fe->d_nframes, sizeof(int)));
+	CKD(cudaMemset(fe->d_nframes, 0, sizeof(int)));
+	CKD(cudaMalloc((void **)&fe->d_pdus, sizeof(PduRec) * (size_t)fe->max_frames));
+	CKD(cudaMallocHost((void **)&fe->h_pdus, sizeof(PduRec) * (size_t)fe->max_frames));
+	CKD(cudaMallocHost((void **)&fe->h_nframes, sizeof(int)));
+	if(fe->cfg.capture_channel >= 0 && fe->cfg.capture_max > 0) {
+		size_t n = (size_t)fe->cfg.capture_max;
+		CKD(cudaMalloc((void **)&fe->d_cap_agc, sizeof(cf) * n));
+		CKD(cudaMalloc((void **)&fe->d_cap_mf, sizeof(cf) * n));
+		CKD(cudaMalloc((void **)&fe->d_cap_eq, sizeof(cf) * n));
+	} else fe->cfg.capture_channel = -1;
+	CKD(cudaMalloc((void **)&fe->d_cap_cnt, sizeof(int) * 2));
+	CKD(cudaMemset(fe->d_cap_cnt, 0, sizeof(int) * 2));
+	fe->tmp_len = std::max((long long)N, (long long)B * fe->out_per_block + 64);
+	CKD(cudaMalloc((void **)&fe->d_tmp, sizeof(cf) * (size_t)fe->tmp_len));
+	CKD(cudaEventCreate(&fe->ev0));
+	CKD(cudaEventCreate(&fe->ev1));
+	if(compute_tapslices(fe)) { hfdl_b200_destroy(fe); return -1; }
+#undef CKD
+	*out = fe;
+	return 0;
+}
+
+void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
+	if(!fe) return;
+	if(fe->stream) cudaStreamSynchronize(fe->stream);
+	cudaFree(fe->d_work); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
+	cudaFree(fe->d_bb); cudaFree(fe->d_rs); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
+	cudaFree(fe->d_frames); cudaFree(fe->d_nframes); cudaFree(fe->d_pdus); cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf);
+	cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp);
+	if(fe->h_pdus) cudaFreeHost(fe->h_pdus);
+	if(fe->h_nframes) cudaFreeHost(fe->h_nframes);
+	for(auto &r : fe->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+	if(fe->ev0) cudaEventDestroy(fe->ev0);
+	if(fe->ev1) cudaEventDestroy(fe->ev1);
+	fe->fft.destroy();
+	if(fe->stream) cudaStreamDestroy(fe->stream);
+	delete fe;
+}
+
+int32_t hfdl_b200_get_geometry(const hfdl_b200_frontend_t *fe, hfdl_b200_geometry_t *o) {
+	if(!fe || !o) return -1;
+	const auto &g = fe->g;
+	memset(o, 0, sizeof(*o));
+	o->decimation = g.decimation; o->pre_decimation = g.pre_decimation; o->post_decimation = g.post_decimation;
+	o->taps_length = g.taps_length; o->overlap_length = g.overlap_length; o->fft_size = g.fft_size; o->fft_inv_size = g.fft_inv_size;
+	o->input_size = g.input_size; o->post_input_size = g.post_input_size; o->scrap = g.scrap; o->out_per_block = fe->out_per_block;
+	o->transition_bw = g.transition_bw; o->resamp_rate = fe->resamp_rate;
+	o->fft_passes = fe->plan.P;
+	for(int i = 0; i < fe->plan.P; i++) o->fft_len[i] = 1 << fe->plan.lgL[i];
+	return 0;
+}
+
+static int process_pending(hfdl_b200_frontend *fe, bool all) {
+	const auto &g = fe->g;
+	int done = 0;
+	for(;;) {
+		long long pending = fe->fed - fe->blocks_done * (long long)g.input_size;
+		int nb = (int)(pending / g.input_size);
+		if(nb < 1 || (!all && nb < fe->Bmax)) break;
+		if(nb > fe->Bmax) nb = fe->Bmax;
+		RawSource src;
+		src.base = fe->d_ring; src.ring_len = fe->ring_len; src.ring_origin = 0; src.block_stride = g.input_size; src.sfmt = fe->sfmt;
+		src.pos0 = fe->blocks_done * (long long)g.input_size - g.overlap_length;
+		if(run_batch(fe, src, nb)) return -1;
+		done += nb;
+	}
+	return done;
+}
+
+int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples) {
+	if(!fe || (!samples && nsamples > 0) || nsamples < 0) return -1;
+	const auto &g = fe->g;
+	const unsigned char *p = (const unsigned char *)samples;
+	int blocks = 0;
+	while(nsamples > 0) {
+		// oldest sample still needed: start of the overlap of the next unprocessed block
+		long long keep_from = fe->blocks_done * (long long)g.input_size - g.overlap_length;
+		long long space = fe->ring_len - (fe->fed - keep_from);
+		if(space <= 0) {
+			int r = process_pending(fe, true);
+			if(r < 0) return -1;
+			blocks += r;
+			continue;
+		}
+		long long n = std::min<long long>(nsamples, space);
+		long long idx = fe->fed % fe->ring_len;
+		long long first = std::min(n, fe->ring_len - idx);
+		CK(cudaMemcpyAsync((unsigned char *)fe->d_ring + idx * fe->bps, p, (size_t)(first * fe->bps), cudaMemcpyHostToDevice, fe->stream));
+		if(n > first)
+			CK(cudaMemcpyAsync(fe->d_ring, p + first * fe->bps, (size_t)((n - first) * fe->bps), cudaMemcpyHostToDevice, fe->stream));
+		fe->fed += n; p += n * fe->bps; nsamples -= n;
+		int r = process_pending(fe, false);
+		if(r < 0) return -1;
+		blocks += r;
+	}
+	return blocks;
+}
+
+int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe) {
+	if(!fe) return -1;
+	return process_pending(fe, true);
+}
+
+int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t ring_samples, int64_t start_sample, int32_t nblocks) {
+	if(!fe || !d_samples || ring_samples < fe->g.fft_size || nblocks < 0) return -1;
+	const auto &g = fe->g;
+	int done = 0;
+	while(done < nblocks) {
+		int nb = std::min(fe->Bmax, nblocks - done);
+		RawSource src;
+		src.base = d_samples; src.ring_len = ring_samples; src.ring_origin = 0; src.block_stride = g.input_size; src.sfmt = fe->sfmt;
+		src.pos0 = start_sample + (long long)done * g.input_size - g.overlap_length;
+		if(run_batch(fe, src, nb)) return -1;
+		done += nb;
+	}
+	// keep the host-fed bookkeeping consistent if the two paths are mixed
+	fe->fed = fe->blocks_done * (long long)g.input_size;
+	return done;
+}
+
+int32_t hfdl_b200_sync(hfdl_b200_frontend_t *fe) {
+	if(!fe) return -1;
+	CK(cudaStreamSynchronize(fe->stream));
+	return 0;
+}
+
+int32_t hfdl_b200_pdu_count(hfdl_b200_frontend_t *fe) { return fe ? (int32_t)fe->pduq.size() : -1; }
+
+int32_t hfdl_b200_pop_pdu(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdu) {
+	if(!fe || !pdu) return -1;
+	if(fe->pduq.empty()) return 0;
+	*pdu = fe->pduq.front();
+	fe->pduq.pop_front();
+	return 1;
+}
+
+static int read_state(hfdl_b200_frontend *fe, int ch, DemodState *S) {
+	if(!fe || ch < 0 || ch >= fe->C) return -1;
+	CK(cudaStreamSynchronize(fe->stream));
+	CK(cudaMemcpy(S, fe->d_state + ch, sizeof(DemodState), cudaMemcpyDeviceToHost));
+	return 0;
+}
+
+int32_t hfdl_b200_channel_noise_floor(hfdl_b200_frontend_t *fe, int32_t channel, float *level) {
+	DemodState S;
+	if(!level || read_state(fe, channel, &S)) return -1;
+	*level = S.noise_floor;
+	return 0;
+}
+
+int32_t hfdl_b200_channel_stats(hfdl_b200_frontend_t *fe, int32_t channel, int32_t out[4]) {
+	DemodState S;
+	if(!out || read_state(fe, channel, &S)) return -1;
+	out[0] = S.st_a1; out[1] = S.st_a2; out[2] = S.st_m1; out[3] = S.st_frames;
+	return 0;
+}
+
+void hfdl_b200_print_summary(hfdl_b200_frontend_t *fe) {
+	if(!fe) return;
+	long long t[4] = { 0, 0, 0, 0 };
+	for(int c = 0; c < fe->C; c++) { int32_t s[4]; if(hfdl_b200_channel_stats(fe, c, s) == 0) for(int i = 0; i < 4; i++) t[i] += s[i]; }
+	fprintf(stderr, "A1_found:\t\t%lld\nA2_found:\t\t%lld\nM1_found:\t\t%lld\nframes:\t\t\t%lld\n", t[0], t[1], t[2], t[3]);
+}
+
+int32_t hfdl_b200_timer_start(hfdl_b200_frontend_t *fe) {
+	if(!fe) return -1;
+	CK(cudaEventRecord(fe->ev0, fe->stream));
+	return 0;
+}
+int32_t hfdl_b200_timer_stop(hfdl_b200_frontend_t *fe, float *ms) {
+	if(!fe || !ms) return -1;
+	CK(cudaEventRecord(fe->ev1, fe->stream));
+	CK(cudaEventSynchronize(fe->ev1));
+	CK(cudaEventElapsedTime(ms, fe->ev0, fe->ev1));
+	return 0;
+}
+int32_t hfdl_b200_profile_enable(hfdl_b200_frontend_t *fe, int32_t on) {
+	if(!fe) return -1;
+	fe->profiling = on != 0;
+	return 0;
+}
+int32_t hfdl_b200_profile_read(hfdl_b200_frontend_t *fe, int32_t max, char names[][32], float *ms, int32_t *launches) {
+	if(!fe) return -1;
+	CK(cudaStreamSynchronize(fe->stream));
+	for(auto &r : fe->prof) {
+		float t = 0;
+		if(cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { fe->prof_ms[r.cls] += t; fe->prof_n[r.cls]++; }
+		cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+	}
+	fe->prof.clear();
+	int n = std::min<int>(max, KC_COUNT);
+	for(int i = 0; i < n; i++) {
+		strncpy(names[i], kc_names[i], 31); names[i][31] = 0;
+		ms[i] = fe->prof_ms[i]; launches[i] = fe->prof_n[i];
+		fe->prof_ms[i] = 0; fe->prof_n[i] = 0;
+	}
+	return n;
+}
+int64_t hfdl_b200_kernel_launches(hfdl_b200_frontend_t *fe) { return fe ? fe->launches : -1; }
+
+int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_t index, void *dst, int64_t max) {
+	if(!fe || max < 0) return -1;
+	CK(cudaStreamSynchronize(fe->stream));
+	const auto &g = fe->g;
+	long long avail = 0;
+	const cf *srcp = nullptr;
+	switch(what) {
+	case HFDL_B200_CP_SPECTRUM: {
+		if(index < 0 || index >= fe->last_nblocks) return -1;
+		avail = g.fft_size;
+		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((g.fft_size + 255) / 256)), dim3(256), 0, fe->stream, fe->d_work, fe->plan, index, 0, g.fft_size, fe->d_tmp);
+		CK(cudaGetLastError());
+		CK(cudaStreamSynchronize(fe->stream));
+		srcp = fe->d_tmp;
+		break; }
+	case HFDL_B200_CP_DDC:
+		if(index < 0 || index >= fe->C) return -1;
+		avail = (long long)fe->last_nblocks * fe->out_per_block;
+		srcp = fe->d_bb + (long long)index * fe->bb_stride + HFDL_RS_HIST;
+		break;
+	case HFDL_B200_CP_CHAN:
+		if(index < 0 || index >= fe->C) return -1;
+		avail = fe->last_nout;
+		srcp = fe->d_rs + (long long)index * fe->rs_stride;
+		break;
+	case HFDL_B200_CP_AGC: case HFDL_B200_CP_MF: case HFDL_B200_CP_EQ: {
+		if(fe->cfg.capture_channel < 0) return -1;
+		int cnt[2];
+		CK(cudaMemcpy(cnt, fe->d_cap_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
+		avail = std::min<long long>(what == HFDL_B200_CP_EQ ? cnt[1] : cnt[0], fe->cfg.capture_max);
+		srcp = what == HFDL_B200_CP_AGC ? fe->d_cap_agc : (what == HFDL_B200_CP_MF ? fe->d_cap_mf : fe->d_cap_eq);
+		break; }
+	case HFDL_B200_CP_TAPSLICE:
+		if(index < 0 || index >= fe->C) return -1;
+		avail = g.fft_inv_size;
+		srcp = fe->d_tapslice + (long long)index * g.fft_inv_size;
+		break;
+	default: return -1;
+	}
+	long long n = std::min<long long>(avail, max);
+	if(dst && n > 0) CK(cudaMemcpy(dst, srcp, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToHost));
+	return avail;
+}
+
+// ---------------- stage entry points ----------------
+int32_t hfdl_b200_fft_forward(int32_t device, const void *in, void *outp, int32_t n, int32_t batch) {
+	if(!in || !outp || n < 2 || (n & (n - 1)) || batch < 1 || hfdl_b200_device_count() < 1) return -1;
+	CK(cudaSetDevice(device));
+	FftEngine eng;
+	if(eng.init()) return -1;
+	FftPlan pl = make_plan(n);
+	cf *d_in = nullptr, *d_work = nullptr, *d_out = nullptr;
+	size_t bytes = sizeof(cf) * (size_t)n * (size_t)batch;
+	CK(cudaMalloc((void **)&d_in, bytes)); CK(cudaMalloc((void **)&d_work, bytes)); CK(cudaMalloc((void **)&d_out, sizeof(cf) * (size_t)n));
+	CK(cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice));
+	RawSource src;
+	src.base = d_in; src.ring_len = (long long)n * batch; src.pos0 = 0; src.ring_origin = 0; src.block_stride = n; src.sfmt = HFDL_SFMT_CF32;
+	cudaStream_t st = nullptr;
+	CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	int rc = run_fft(nullptr, eng, pl, src, d_work, batch, st);
+	for(int b = 0; b < batch && rc == 0; b++) {
+		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, d_work, pl, b, 0, n, d_out);
+		if(cudaStreamSynchronize(st) != cudaSuccess) { rc = -1; break; }
+		if(cudaMemcpy((cf *)outp + (size_t)b * n, d_out, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
+	}
+	if(cudaGetLastError() != cudaSuccess) rc = -1;
+	cudaStreamDestroy(st);
+	cudaFree(d_in); cudaFree(d_work); cudaFree(d_out);
+	eng.destroy();
+	return rc;
+}
+
+static int fec_run(int device, const void *symbols, const uint8_t *vin, int nframes, int M1, uint32_t bitmask, int nbits,
+		uint8_t *pdu_out, int stride_out, uint8_t *soft_out, int32_t *crc_out) {
+	if(nframes < 1 || hfdl_b200_device_count() < 1) return -1;
+	CK(cudaSetDevice(device));
+	CK(cudaFuncSetAttribute(fec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_FEC_SMEM));
+	DemodTables *T = new DemodTables();
+	hfdl_design::demod_tables(*T);
+	DemodTables *d_tab = nullptr; FrameRec *d_fr = nullptr; int *d_n = nullptr; PduRec *d_p = nullptr; cf *d_sym = nullptr;
+	unsigned char *d_soft = nullptr, *d_vin = nullptr;
+	CK(cudaMalloc((void **)&d_tab, sizeof(DemodTables)));
+	CK(cudaMemcpy(d_tab, T, sizeof(DemodTables), cudaMemcpyHostToDevice));
+	std::vector<FrameRec> fr((size_t)nframes);
+	for(int q = 0; q < nframes; q++) {
+		memset(&fr[(size_t)q], 0, sizeof(FrameRec));
+		fr[(size_t)q].channel = q / HFDL_FRAME_SLOTS; fr[(size_t)q].slot = q % HFDL_FRAME_SLOTS; fr[(size_t)q].M1 = M1; fr[(size_t)q].bitmask = bitmask;
+	}
+	CK(cudaMalloc((void **)&d_fr, sizeof(FrameRec) * (size_t)nframes));
+	CK(cudaMemcpy(d_fr, fr.data(), sizeof(FrameRec) * (size_t)nframes, cudaMemcpyHostToDevice));
+	CK(cudaMalloc((void **)&d_n, sizeof(int)));
+	CK(cudaMemcpy(d_n, &nframes, sizeof(int), cudaMemcpyHostToDevice));
+	CK(cudaMalloc((void **)&d_p, sizeof(PduRec) * (size_t)nframes));
+	int nsym = T->mode_segments[M1] * 30;
+	if(symbols) {
+		CK(cudaMalloc((void **)&d_sym, sizeof(cf) * (size_t)nframes * HFDL_DATA_SYMS_MAX));
+		for(int q = 0; q < nframes; q++)
+			CK(cudaMemcpy(d_sym + (size_t)q * HFDL_DATA_SYMS_MAX, (const cf *)symbols + (size_t)q * nsym, sizeof(cf) * (size_t)nsym, cudaMemcpyHostToDevice));
+	}
+	if(vin) {
+		CK(cudaMalloc((void **)&d_vin, (size_t)nframes * 2 * nbits));
+		CK(cudaMemcpy(d_vin, vin, (size_t)nframes * 2 * nbits, cudaMemcpyHostToDevice));
+	}
+	if(soft_out) CK(cudaMalloc((void **)&d_soft, (size_t)nframes * HFDL_FEC_VIN_MAX));
+	FecArgs a;
+	a.frames = d_fr; a.nframes = d_n; a.max_frames = nframes; a.datasym = d_sym; a.tab = d_tab; a.pdus = d_p; a.soft_out = d_soft;
+	a.vin_direct = d_vin; a.vin_nbits = nbits;
+	HFDL_LAUNCH(fec_kernel, dim3((unsigned)nframes), dim3(32), HFDL_FEC_SMEM, 0, a);
+	CK(cudaGetLastError());
+	CK(cudaDeviceSynchronize());
+	std::vector<PduRec> out((size_t)nframes);
+	CK(cudaMemcpy(out.data(), d_p, sizeof(PduRec) * (size_t)nframes, cudaMemcpyDeviceToHost));
+	for(int q = 0; q < nframes; q++) {
+		int len = out[(size_t)q].len;
+		memcpy(pdu_out + (size_t)q * stride_out, out[(size_t)q].octets, (size_t)std::min(len, stride_out));
+		if(crc_out) crc_out[q] = out[(size_t)q].crc_good;
+	}
+	if(soft_out) CK(cudaMemcpy(soft_out, d_soft, (size_t)nframes * HFDL_FEC_VIN_MAX, cudaMemcpyDeviceToHost));
+	cudaFree(d_tab); cudaFree(d_fr); cudaFree(d_n); cudaFree(d_p); cudaFree(d_sym); cudaFree(d_soft); cudaFree(d_vin);
+	delete T;
+	return 0;
+}
+
+int32_t hfdl_b200_fec_decode(int32_t device, const void *symbols, int32_t nframes, int32_t M1, uint32_t bitmask,
+		uint8_t *pdu_out, int32_t stride_out, uint8_t *soft_out, int32_t *crc_good_out) {
+	if(!symbols || !pdu_out || M1 < 0 || M1 > 7 || stride_out < hfdl_design::pdu_len(M1)) return -1;
+	return fec_run(device, symbols, nullptr, nframes, M1, bitmask, 0, pdu_out, stride_out, soft_out, crc_good_out);
+}
+
+int32_t hfdl_b200_viterbi27(int32_t device, const uint8_t *syms, int32_t nframes, int32_t nbits, uint8_t *out) {
+	if(!syms || !out || nbits < 8 || nbits > 7560) return -1;
+	return fec_run(device, nullptr, syms, nframes, 1, 0, nbits, out, (nbits + 7) / 8, nullptr, nullptr);
+}
+
+}  // extern "C"

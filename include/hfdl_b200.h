@@ -1,0 +1,146 @@
+/*
+ * include/hfdl_b200.h -- C ABI of libhfdl_b200.so, the B200 (sm_100a) replacement for dumphfdl's
+ * multichannel front-end hot path:  fft.c (overlap-save forward FFT)  ->  fastddc.c/libcsdr*.c
+ * (channeliser)  ->  hfdl.c (demodulator, framer, FEC driver)  ->  libfec/viterbi27_port.c.
+ *
+ * Plain C, plain pointers and sizes; every entry point returns 0 on success and -1 on error
+ * (message on stderr, like the reference).  There is NO CPU implementation behind this ABI:
+ * creation fails when no CUDA device is present.
+ *
+ * Reference interfaces replaced (paths relative to dumphfdl's src/):
+ *   hfdl_b200_create            <- csdr_fft_init (main.c:697, fft.h:23), compute_fft_decimation_rate /
+ *                                  compute_filter_relative_transition_bw (main.c:699-704), fft_create (fft.h:31),
+ *                                  hfdl_init_globals + hfdl_channel_create x C (hfdl.h:10-12, main.c:739-750),
+ *                                  block_connect_one2many (main.c:752-755)
+ *   hfdl_b200_destroy           <- fft_destroy (fft.h:32), hfdl_channel_destroy (hfdl.h:13), csdr_fft_destroy
+ *   hfdl_b200_push_samples      <- the consumer side of fft_thread (fft.c:38-61) fed by
+ *                                  complex_samples_produce (input-helpers.c:80-92), plus the sample conversion
+ *                                  of input-helpers.c:10-78 when raw CU8/CS16 is pushed
+ *   hfdl_b200_process_device    <- same, for a capture already resident in HBM (replay / multi-GPU broadcast)
+ *   hfdl_b200_flush             <- the drain-then-exit rule of fft.c:38-47 (only whole blocks are processed)
+ *   hfdl_b200_pop_pdu           <- dispatch_pdu -> pdu_decoder_queue_push (hfdl.c:1058-1080, pdu.h:39)
+ *   hfdl_b200_channel_noise_floor <- the c->noise_floor read of noise_floor_stats_thread (hfdl.c:1082-1105)
+ *   hfdl_b200_print_summary     <- hfdl_print_summary (hfdl.h:14)
+ *   hfdl_b200_fft_forward       <- csdr_make_fft_c2c + csdr_fft_execute (fft.h:25-28) [stage entry for parity tests]
+ *   hfdl_b200_fec_decode        <- decode_user_data (hfdl.c:993-1056)              [stage entry for parity tests]
+ *   hfdl_b200_viterbi27         <- init/update_blk/chainback_viterbi27 (libfec/fec.h:18-21) [stage entry]
+ * The block.c-facing wrapper (struct block with a thread routine, hfdl_gpu_frontend_create) is declared in
+ * include/hfdl_b200_block.h.
+ */
+#ifndef HFDL_B200_H
+#define HFDL_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hfdl_b200_frontend hfdl_b200_frontend_t;
+
+/* sample formats: values of the reference's enum sample_format (input-common.h) */
+#define HFDL_B200_SFMT_CU8  1
+#define HFDL_B200_SFMT_CS16 2
+#define HFDL_B200_SFMT_CF32 3
+
+#define HFDL_B200_MAX_PDU_OCTETS 945
+
+typedef struct {
+	int32_t sample_rate;
+	int32_t centerfreq_hz;
+	const int32_t *freqs_hz;      /* dial frequencies, one channel each (carrier = dial + 1440 Hz, hfdl.c:46) */
+	int32_t nfreq;
+	int32_t sample_format;        /* HFDL_B200_SFMT_* of the samples that will be pushed */
+	int32_t device;               /* CUDA device ordinal */
+	int32_t max_blocks_per_batch; /* overlap-save blocks processed per launch group (0 = default) */
+	int32_t capture_channel;      /* >=0: keep DATADUMPS-style checkpoints of this channel (debug/parity); -1 off */
+	int32_t capture_max;          /* samples kept per checkpoint */
+} hfdl_b200_config_t;
+
+/* block geometry = fastddc_t of the reference (fastddc.h:8-27) + the resampler rate (hfdl.c:471) */
+typedef struct {
+	int32_t decimation, pre_decimation, post_decimation;
+	int32_t taps_length, overlap_length, fft_size, fft_inv_size, input_size, post_input_size, scrap;
+	int32_t out_per_block;        /* post_input_size / post_decimation */
+	float   transition_bw, resamp_rate;
+	int32_t fft_passes, fft_len[3];
+} hfdl_b200_geometry_t;
+
+/* one decoded frame = struct hfdl_pdu_metadata (pdu.h:8-17) + the octet string (hfdl.c:1077-1079) */
+typedef struct {
+	int32_t version;              /* 1 (hfdl.c:1061) */
+	int32_t freq;                 /* channel dial frequency, Hz */
+	int32_t bit_rate;             /* hfdl.c:1072-1073 */
+	float   freq_err_hz;          /* hfdl.c:812 */
+	float   rssi;                 /* 20*log10(signal_level), hfdl.c:1064 */
+	float   noise_floor;          /* 20*log10(noise_floor), hfdl.c:1065 */
+	char    slot;                 /* 'S' / 'D' */
+	int32_t M1;                   /* mode index 0..7 (hfdl.c:81-138) */
+	int32_t crc_good;             /* 1 when the MPDU header / SPDU FCS is good (mpdu.c:83, spdu.c:62) */
+	int32_t train_bits_bad, train_bits_total;
+	uint64_t sample_cnt_a2;       /* 5400 Hz sample clock at A2 detection (stands in for the wall clock of hfdl.c:808) */
+	uint64_t sample_cnt_end;      /* ... at the end of the frame */
+	double  rx_time_s;            /* stream time of the frame start: (sample_cnt_a2/5400) - (448+254)/1800, hfdl.c:657-660 */
+	float   signal_level, noise_floor_lin;
+	int32_t len;
+	uint8_t octets[HFDL_B200_MAX_PDU_OCTETS + 3];
+} hfdl_b200_pdu_t;
+
+int32_t hfdl_b200_device_count(void);
+int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *cfg);
+void    hfdl_b200_destroy(hfdl_b200_frontend_t *fe);
+int32_t hfdl_b200_get_geometry(const hfdl_b200_frontend_t *fe, hfdl_b200_geometry_t *g);
+
+/* Host samples in the configured sample format.  Whole batches are processed as they fill; the call
+ * returns the number of overlap-save blocks processed (>=0) or -1. */
+int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples);
+/* Process every whole block still buffered (a final partial block is dropped, as in fft.c:41-46). */
+int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe);
+/* Device-resident cyclic capture: 'd_samples' holds ring_samples samples of the configured format in
+ * HBM; processes nblocks blocks starting at stream position start_sample (stream position p lives at
+ * ring index p % ring_samples; positions < 0 read as zeros).  Consecutive calls must continue the stream. */
+int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t ring_samples,
+		int64_t start_sample, int32_t nblocks);
+/* Blocks until all queued GPU work of this frontend is complete and PDUs are collected. */
+int32_t hfdl_b200_sync(hfdl_b200_frontend_t *fe);
+
+int32_t hfdl_b200_pdu_count(hfdl_b200_frontend_t *fe);
+/* returns 1 and fills *pdu when one is available, 0 when the queue is empty */
+int32_t hfdl_b200_pop_pdu(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdu);
+int32_t hfdl_b200_channel_noise_floor(hfdl_b200_frontend_t *fe, int32_t channel, float *level_linear);
+/* counters: A1 found, A2 found, M1 found, frames (hfdl.c:162-179) */
+int32_t hfdl_b200_channel_stats(hfdl_b200_frontend_t *fe, int32_t channel, int32_t out[4]);
+void    hfdl_b200_print_summary(hfdl_b200_frontend_t *fe);
+
+/* timing of the device work issued since the previous call (CUDA events on the frontend's stream) */
+int32_t hfdl_b200_timer_start(hfdl_b200_frontend_t *fe);
+int32_t hfdl_b200_timer_stop(hfdl_b200_frontend_t *fe, float *ms);
+/* per-kernel-class device time accumulated while profiling is on: fills names/ms/launches for up to max classes */
+int32_t hfdl_b200_profile_enable(hfdl_b200_frontend_t *fe, int32_t on);
+int32_t hfdl_b200_profile_read(hfdl_b200_frontend_t *fe, int32_t max, char names[][32], float *ms, int32_t *launches);
+int64_t hfdl_b200_kernel_launches(hfdl_b200_frontend_t *fe);
+
+/* ---- checkpoints for parity tests (the reference's DATADUMPS taps, hfdl.c:616-655) ---- */
+#define HFDL_B200_CP_SPECTRUM 0   /* last batch: forward spectrum of block 'index', natural FFTW order, fft_size bins */
+#define HFDL_B200_CP_DDC      1   /* last batch: channel 'index' fastddc_inv_cc output, out_per_block*blocks samples */
+#define HFDL_B200_CP_CHAN     2   /* last batch: channel 'index' resampler output (f_chan_out) */
+#define HFDL_B200_CP_AGC      3   /* capture channel: AGC output since create (f_agc_out) */
+#define HFDL_B200_CP_MF       4   /* capture channel: matched filter output (f_mf_out) */
+#define HFDL_B200_CP_EQ       5   /* capture channel: equaliser output per symbol (f_eq_out) */
+#define HFDL_B200_CP_TAPSLICE 6   /* channel 'index': M tap-spectrum bins in inverse-FFT input order */
+/* copies up to max complex64 values into dst (host); returns the number available or -1 */
+int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_t index, void *dst, int64_t max);
+
+/* ---- stage entry points (host buffers in, host buffers out; run on the device) ---- */
+/* forward unnormalised DFT of 'batch' windows of n complex64 each, FFTW_FORWARD sign, natural order out */
+int32_t hfdl_b200_fft_forward(int32_t device, const void *in_cf32, void *out_cf32, int32_t n, int32_t batch);
+/* decode_user_data for 'nframes' frames of mode M1: symbols [nframes][nsym(M1)] complex64, bitmask per call;
+ * pdu_out [nframes][stride_out] octets (stride_out >= pdu length), soft_out optional [nframes][15120] */
+int32_t hfdl_b200_fec_decode(int32_t device, const void *symbols_cf32, int32_t nframes, int32_t M1, uint32_t bitmask,
+		uint8_t *pdu_out, int32_t stride_out, uint8_t *soft_out, int32_t *crc_good_out);
+/* Viterbi only: syms [nframes][2*nbits] soft bytes -> out [nframes][(nbits+7)/8]; nbits must be one of the HFDL sizes */
+int32_t hfdl_b200_viterbi27(int32_t device, const uint8_t *syms, int32_t nframes, int32_t nbits, uint8_t *out);
+int32_t hfdl_b200_pdu_len(int32_t M1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
