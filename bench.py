@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric on BASELINE config 2 (2 Msps CF32, 8 HFDL channels) per GPU.
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (libhfdl_b200.so, sm_100a kernels)
+  python bench.py --impl reference --gpus N ...            the reference's CPU path on the host cores
+                                                           (oracle/_ref is only partial -> restated CPU reference,
+                                                            oracle/liboracle_fast.so built -O3 -ffast-math like the
+                                                            reference, all host threads, full-N fold as fastddc.c)
+
+A "step" is one pass of the hot path over one synthetic slab: SLOTS*22 overlap-save blocks of a looped
+multichannel capture (frames placed cyclically so the stream is seamless across steps).
+  value : I/Q Msamples/s ingested with the slab resident in HBM (device timed, CUDA events)
+  e2e   : same metric through hfdl_b200_push_samples() with pinned HOST buffers: H2D of the slab and D2H of the
+          PDUs inside the timed region
+N>1: one process per GPU (torchrun); every GPU owns an independent 2 Msps capture and its 8 channels end to end
+(weak scaling, no data-path collective); --shared-spectrum broadcasts one capture over NCCL instead and shards
+the channels."""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SR = 2000000
+NCH = 8
+CF = 100000000            # centre 100 000 kHz (only differences matter)
+BLOCKS_PER_SLOT = 22      # 22 * 229376 / 2e6 = 2.523 s >= one 2.344 s single-slot frame
+SLOTS = 4                 # slab = 88 blocks = 20.2 Msamples = 161 MB CF32 (> 126 MB L2)
+ESN0_DB = 20.0
+SEED = 635002             # 635000 + cfg_index
+METRIC = "I/Q Msamples/s & CRC-good PDUs/s at 1/2/4/8 B200 vs fftw CPU ref"
+
+
+def channel_freqs(nch=NCH):
+    delta = int(0.85 * SR / nch / 1000) * 1000
+    return [int(round((CF + (k - (nch - 1) / 2) * delta) / 1000.0)) * 1000 for k in range(nch)]
+
+
+def build_slab(O, seed, nthreads):
+    """Cyclic slab: per channel, back-to-back frames of random modes filling SLOTS slots."""
+    d = O.geometry(SR)[2]
+    isz = d.input_size
+    nblocks = BLOCKS_PER_SLOT * SLOTS
+    nsamp = nblocks * isz
+    slot_s = BLOCKS_PER_SLOT * isz / SR
+    rng = np.random.default_rng(seed)
+    amp = 0.25 / np.sqrt(NCH) / np.sqrt(0.947)
+    frames, truth = [], []
+    for k, f in enumerate(channel_freqs()):
+        slot = 0
+        phase = float(rng.uniform(0, slot_s))            # random start offset of this channel's slot grid
+        while slot < SLOTS:
+            m = int(rng.integers(0, 8))
+            need = 2 if m >= 4 else 1
+            if slot + need > SLOTS:
+                m -= 4
+                need = 1
+            flen = (448 + 531 + (168 if m >= 4 else 72) * 45) / 1800.0 + 0.02
+            start = (phase + slot * slot_s + float(rng.uniform(0, need * slot_s - flen))) % (nsamp / SR)
+            pdu = O.make_pdu(m, int(rng.integers(0, 2)), seed=int(rng.integers(1, 1 << 30)))
+            frames.append(O.tx_frame(f, m, start, pdu, cfo_hz=float(rng.uniform(-20, 20)), phase0=float(rng.uniform(0, 2 * np.pi)), amplitude=amp))
+            truth.append((f, pdu))
+            slot += need
+    x = O.render(nsamp, SR, CF, frames, noise_sigma=O.noise_sigma(amp, SR, ESN0_DB), seed=seed, cyclic=True, nthreads=nthreads)
+    return x, truth, nblocks, isz
+
+
+class ClockSampler:
+    def __init__(self, gpu):
+        self.rows = []
+        self.p = None
+        self.gpu = gpu
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([s.strip() for s in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(O, x, isz, nblocks_avail, target_s=12.0):
+    """The reference's own algorithm on the host cores: restated CPU reference (oracle built -O3 -ffast-math),
+    full-N fold exactly as fastddc.c:123-150, FFT + channels threaded like fft_fftw.c / block.c."""
+    cores = os.cpu_count() or 1
+    freqs = channel_freqs()
+    p = O.Pipeline(SR, CF, freqs, fold_mode=O.FOLD_FULL, nthreads=cores, fast=True)
+    probe = min(4, nblocks_avail)
+    t0 = time.perf_counter()
+    p.feed(x[: probe * isz])
+    dt = time.perf_counter() - t0
+    nb = int(max(probe, min(nblocks_avail - probe, target_s / max(dt / probe, 1e-6))))
+    t0 = time.perf_counter()
+    p.feed(x[probe * isz:(probe + nb) * isz])
+    dt = time.perf_counter() - t0
+    good = sum(1 for q in p.pdus() if q.crc_good)
+    p.close()
+    return {"value": nb * isz / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": "port",
+            "sample": "%d overlap-save blocks (%.1f Msamples) of the cfg-2 slab, restated CPU reference (fftw3/liquid-dsp not installed): "
+                      "oracle/liboracle_fast.so -O3 -ffast-math, full-N fold, %d threads; %d CRC-good PDUs" % (nb, nb * isz / 1e6, cores, good),
+            "seconds": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--shared-spectrum", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import orclib as O
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        x, truth, nblocks, isz = build_slab(O, SEED, os.cpu_count() or 1)
+        per = max(4, min(nblocks, 8))
+        vals = []
+        cores = os.cpu_count() or 1
+        p = O.Pipeline(SR, CF, channel_freqs(), fold_mode=O.FOLD_FULL, nthreads=cores, fast=True)
+        pos = 0
+        for s in range(a.warmup + a.steps):
+            seg = np.concatenate([x[(pos + i * isz) % x.size:(pos + i * isz) % x.size + isz] for i in range(per)])
+            t0 = time.perf_counter()
+            p.feed(seg)
+            dt = time.perf_counter() - t0
+            pos += per * isz
+            if s >= a.warmup:
+                vals.append(dt)
+        tot = sum(vals)
+        v = a.steps * per * isz / tot / 1e6
+        good = sum(1 for q in p.pdus() if q.crc_good)
+        line = {"metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "impl": "reference",
+                "config": {"workload": "cfg2: 2 Msps CF32, 8 HFDL channels, synthetic looped slab; each step = %d blocks (%.2f Msamples)" % (per, per * isz / 1e6)},
+                "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                                 "sample": "restated CPU reference (oracle/liboracle_fast.so, -O3 -ffast-math, full-N fold, %d threads); fftw3f/liquid-dsp absent so dumphfdl itself cannot be built" % cores},
+                "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "pdus_crc_good": good}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import dumphfdl_b200 as hb
+    hb.load()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ncpu = max(1, (os.cpu_count() or 1) // max(world, 1))
+    shared = a.shared_spectrum and world > 1
+    seed = SEED if shared else SEED + 1000 * rank
+    x, truth, nblocks, isz = build_slab(O, seed, ncpu)
+    freqs = channel_freqs()
+    if shared:
+        my = list(range(rank, NCH, world))
+        freqs = [freqs[i] for i in my]
+        truth = [t for t in truth if t[0] in freqs]
+    nsamp = x.size
+    xf = torch.from_numpy(x.view(np.float32))
+    h_pin = xf.pin_memory()
+    d_slab = torch.empty_like(xf, device="cuda")
+    d_slab.copy_(h_pin)
+    torch.cuda.synchronize()
+    fe = hb.Frontend(SR, CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    truth_set = set(truth)
+    stream_pos = [0]
+
+    def step_device():
+        if shared:
+            dist.broadcast(d_slab, src=0)
+            torch.cuda.synchronize()
+        fe.process_device(d_slab.data_ptr(), nsamp, stream_pos[0], nblocks)
+        stream_pos[0] += nsamp
+
+    def count(pdus):
+        good = sum(1 for q in pdus if q.crc_good)
+        exact = sum(1 for q in pdus if (q.freq, q.data()) in truth_set)
+        return good, exact
+
+    # ---- value: slab resident in HBM
+    for _ in range(a.warmup):
+        step_device()
+    fe.pdus()
+    clk = ClockSampler(local)
+    clk.start()
+    fe.profile(True)
+    l0 = fe.launches()
+    barrier()
+    fe.timer_start()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_device()
+    ms_dev = fe.timer_stop()
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = clk.stop()
+    launches = fe.launches() - l0
+    prof = fe.profile_read()
+    fe.profile(False)
+    good, exact = count(fe.pdus())
+    ms = max(ms_dev, 0.0)
+    # ---- e2e: host buffers through the C ABI (H2D + D2H inside)
+    fe2 = hb.Frontend(SR, CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
+    for _ in range(max(1, a.warmup - 1)):
+        fe2.push_ptr(h_pin.data_ptr(), nsamp)
+        fe2.flush()
+    fe2.pdus()
+    barrier()
+    t0 = time.perf_counter()
+    e_good = 0
+    for _ in range(a.steps):
+        fe2.push_ptr(h_pin.data_ptr(), nsamp)
+        fe2.flush()
+        e_good += count(fe2.pdus())[0]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1e3, float(good), float(exact), float(e_good), float(len(truth))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, e2e_ms = float(tmax[0]), float(tmax[1])
+        good, exact, e_good, ntruth = float(tsum[2]), float(tsum[3]), float(tsum[4]), float(tsum[5])
+    else:
+        ms, e2e_ms, ntruth = float(t[0]), float(t[1]), float(t[5])
+    streams = 1 if shared else world
+    total_samples = a.steps * nsamp * streams
+    value = total_samples / (ms / 1e3) / 1e6
+    e2e = total_samples / (e2e_ms / 1e3) / 1e6
+    if rank == 0:
+        g = fe.geom
+        N, M, out = g.fft_size, g.fft_inv_size, g.out_per_block
+        Cn = len(freqs)
+        # algorithmic (compulsory) bytes per block, SURVEY 8(d) / BASELINE.md section 3
+        b_blk = isz * 8 + N * 8 + Cn * M * 8 + Cn * M * 8 + Cn * out * 16
+        alg = {"fft_pass1": isz * 8, "fft_pass2": N * 8 if g.fft_passes == 2 else 0, "fft_pass3": N * 8 if g.fft_passes == 3 else 0,
+               "chan_extract": Cn * M * 16 + Cn * out * 8, "resamp": Cn * out * 8 * (1 + g.resamp_rate), "demod": Cn * out * g.resamp_rate * 8, "fec": 0}
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        kern = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": (v[0] / v[1] if v[1] else 0.0)} for k, v in prof.items()}
+        dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+        roof = None
+        if dom and prof[dom][1]:
+            per_launch_bytes = alg.get(dom, 0) * nblocks
+            dur = prof[dom][0] / prof[dom][1] / 1e3
+            ach = per_launch_bytes / dur / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dur * 1e3}
+        pipe_ach = b_blk * nblocks * a.steps / (ms / 1e3) / 1e9
+        line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak" if not shared else "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "cfg2: 2 Msps CF32, %d HFDL channels per GPU, looped slab of %d overlap-save blocks (%.1f Msamples, %.0f MB; "
+                                       "slab + %.0f MB spectrum workspace exceed the 126 MB L2, no explicit flush)" % (Cn, nblocks, nsamp / 1e6, nsamp * 8 / 1e6, nblocks * N * 8 / 1e6),
+                           "sample_rate": SR, "channels_per_gpu": Cn, "blocks_per_step": nblocks, "fft_size": N, "esn0_db": ESN0_DB,
+                           "sharding": ("one capture broadcast over NCCL each step, channels sharded" if shared else "one independent capture + its channels per GPU, no collective")},
+                "pdus_per_s": good / (ms / 1e3), "pdus_crc_good": good, "pdus_exact": exact, "pdus_expected_per_step": ntruth,
+                "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": nsamp * 8, "d2h_bytes_per_step": int(e_good / max(a.steps, 1) * 1024) + 4,
+                        "pdus_per_s": e_good / (e2e_ms / 1e3)},
+                "gpu_launches": int(launches), "clocks": clocks, "kernels": kern, "roofline": roof,
+                "roofline_pipeline": {"bound": "hbm", "achieved": pipe_ach, "peak": peak, "unit": "GB/s", "frac": pipe_ach / peak,
+                                      "algorithmic_bytes_per_block": b_blk},
+                "wall_ms_per_step": 1e3 * wall / a.steps}
+        if not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference(O, x, isz, nblocks)
+        print(json.dumps(line))
+    fe.close()
+    fe2.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -582,6 +582,7 @@ int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_
 	const cf *srcp = nullptr;
 	switch(what) {
 	case HFDL_B200_CP_SPECTRUM: {
+		if(index < 0) index = fe->last_nblocks - 1;       // -1: last block processed
 		if(index < 0 || index >= fe->last_nblocks) return -1;
 		avail = g.fft_size;
 		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((g.fft_size + 255) / 256)), dim3(256), 0, fe->stream, fe->d_work, fe->plan, index, 0, g.fft_size, fe->d_tmp);

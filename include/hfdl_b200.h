@@ -119,7 +119,7 @@ int32_t hfdl_b200_profile_read(hfdl_b200_frontend_t *fe, int32_t max, char names
 int64_t hfdl_b200_kernel_launches(hfdl_b200_frontend_t *fe);
 
 /* ---- checkpoints for parity tests (the reference's DATADUMPS taps, hfdl.c:616-655) ---- */
-#define HFDL_B200_CP_SPECTRUM 0   /* last batch: forward spectrum of block 'index', natural FFTW order, fft_size bins */
+#define HFDL_B200_CP_SPECTRUM 0   /* last batch: forward spectrum of block 'index' (-1 = last), natural FFTW order */
 #define HFDL_B200_CP_DDC      1   /* last batch: channel 'index' fastddc_inv_cc output, out_per_block*blocks samples */
 #define HFDL_B200_CP_CHAN     2   /* last batch: channel 'index' resampler output (f_chan_out) */
 #define HFDL_B200_CP_AGC      3   /* capture channel: AGC output since create (f_agc_out) */

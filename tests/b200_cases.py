@@ -1,0 +1,165 @@
+"""Parity cases shared by the GPU tests (real libhfdl_b200.so, -m gpu) and the CPU logic tests
+(same kernels compiled for host emulation, tests/cusim).  Every case drives the C ABI of
+include/hfdl_b200.h and compares with the CPU oracle on the same seeded input."""
+import numpy as np
+
+import orclib as O
+import dumphfdl_b200.api as A
+
+# float tolerances (relative L2).  The reference itself is built -ffast-math, so float I/Q is
+# compared within tolerance and only PDU octets / integer stages bit-exactly.
+TOL_FFT = 2e-6          # forward spectrum vs float64 FFT
+TOL_DDC = 2e-5          # channeliser output vs oracle (slice fold); closed-form phase vs the reference's recursion
+TOL_DEMOD = 5e-4        # AGC / MF / EQ checkpoints (feedback loops amplify 1-ulp libm differences)
+
+CF = 10000000
+
+
+def rel(a, b):
+    n = min(a.size, b.size)
+    return float(np.linalg.norm(a[:n] - b[:n]) / max(np.linalg.norm(b[:n]), 1e-30))
+
+
+def case_fft(lib, sizes, batch=2, seed=1):
+    rng = np.random.default_rng(seed)
+    for n in sizes:
+        x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+        y = A.fft_forward(x, lib=lib)
+        ref = np.fft.fft(x.astype(np.complex128), axis=1)
+        assert rel(y.ravel(), ref.ravel()) < TOL_FFT, n
+        o = np.zeros(n, np.complex64)
+        O.lib().orc_fft(x[0].copy(), o, n, 1)
+        assert rel(y[0], o) < TOL_FFT
+    # linearity + a pure tone lands in one bin (size-independent properties)
+    n = sizes[-1]
+    k = 5 * n // 16 + 3
+    t = np.exp(2j * np.pi * k * np.arange(n) / n).astype(np.complex64)
+    y = A.fft_forward(t, lib=lib)[0] if False else A.fft_forward(t, lib=lib).ravel()
+    assert abs(abs(y[k]) - n) / n < 1e-4
+    y[k] = 0
+    assert np.abs(y).max() / n < 1e-4
+
+
+def case_viterbi(lib, sizes, seed=4, frames=3):
+    rng = np.random.default_rng(seed)
+    L = O.lib()
+    for nbits in sizes:
+        syms = rng.integers(0, 256, (frames, 2 * nbits), dtype=np.uint8)
+        bits = rng.integers(0, 2, nbits, dtype=np.uint8)
+        chips = np.zeros(2 * nbits, np.uint8)
+        L.orc_conv_encode27(bits, nbits, chips)
+        syms[0] = np.clip(chips.astype(np.int32) * 255 + rng.normal(0, 70, 2 * nbits), 0, 255).astype(np.uint8)
+        got = A.viterbi27(syms, nbits, lib=lib)
+        for i in range(frames):
+            want = np.zeros((nbits + 7) // 8, np.uint8)
+            L.orc_viterbi27(syms[i].copy(), nbits, want)
+            assert np.array_equal(got[i], want), (nbits, i)      # bit-exact
+
+
+def case_fec(lib, modes, seed=2, noise=0.25):
+    rng = np.random.default_rng(seed)
+    L = O.lib()
+    for M1 in modes:
+        pdus = [O.make_pdu(M1, k % 2, seed=seed * 100 + M1 * 10 + k) for k in range(3)]
+        nsym = [2160, 5040][M1 // 4]
+        S = np.zeros((3, nsym), np.complex64)
+        for k, p in enumerate(pdus):
+            sym = np.zeros(5040, np.complex64)
+            n = L.orc_encode_user_data(np.frombuffer(p, np.uint8).copy(), M1, sym)
+            assert n == nsym
+            nz = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) * (noise if k < 2 else 0.7)
+            S[k] = ((sym[:n] + nz) * np.exp(1j * 0.05)).astype(np.complex64)
+        for bm in (0, 0xFFFFFFFF):
+            X = (S * (-1 if bm else 1)).astype(np.complex64)
+            out, crc, soft = A.fec_decode(X, M1, bm, want_soft=True, lib=lib)
+            nenc = nsym * [1, 1, 2, 3][M1 % 4]
+            for k in range(3):
+                ro = np.zeros(948, np.uint8)
+                rs = np.zeros(15120, np.uint8)
+                ln = L.orc_decode_user_data(X[k].copy(), M1, bm, ro, rs.ctypes.data)
+                assert np.array_equal(soft[k][:nenc], rs[:nenc]), (M1, k)       # soft bits bit-exact
+                assert np.array_equal(out[k], ro[:ln]), (M1, k)                  # PDU octets bit-exact
+                assert crc[k] == L.orc_pdu_crc_good(ro, ln)
+            assert bytes(out[0]) == pdus[0] and crc[0] == 1                      # and equal to what was sent
+
+
+def make_capture(sr, freqs, modes, dur, esn0=20.0, seed=3, amp=None, starts=None):
+    amp = amp or 0.5 / max(2.0, np.sqrt(len(freqs)) * 2)
+    rng = np.random.default_rng(seed)
+    frames, truth = [], []
+    for i, (f, m) in enumerate(zip(freqs, modes)):
+        pdu = O.make_pdu(m, (i + m) % 2, seed=seed * 1000 + i)
+        st = starts[i] if starts else 0.15 + 0.03 * i
+        frames.append(O.tx_frame(f, m, st, pdu, cfo_hz=float(rng.uniform(-15, 15)), phase0=float(rng.uniform(0, 6.28)), amplitude=amp))
+        truth.append((f, pdu))
+    x = O.render(int(sr * dur), sr, CF, frames, noise_sigma=O.noise_sigma(amp, sr, esn0), seed=seed)
+    return x, truth
+
+
+def run_oracle(sr, freqs, raw, sfmt, capture_ch=None, taps=()):
+    p = O.Pipeline(sr, CF, freqs, fold_mode=O.FOLD_SLICE, nthreads=8)
+    if capture_ch is not None:
+        p.set_capture(capture_ch, list(taps), 1 << 22)
+    p.feed(raw, sfmt)
+    return p
+
+
+def compare_pdus(got, ref, truth=None):
+    g = sorted((q.freq, q.sample_cnt_end, q.data(), q.M1, q.crc_good, q.sample_cnt_a2) for q in got)
+    r = sorted((q.freq, q.sample_cnt_end, q.data(), q.M1, q.crc_good, q.sample_cnt_a2) for q in ref)
+    assert g == r, "PDU list differs from the oracle's"
+    if truth is not None:
+        assert sorted((f, d) for f, _, d, _, _, _ in g) == sorted(truth)
+
+
+def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_floats=True, ragged=False, seed=3):
+    x, truth = make_capture(sr, freqs, modes, dur, seed=seed)
+    if sfmt == A.SFMT_CS16:
+        raw = np.zeros(2 * x.size, np.int16)
+        O.lib().orc_quantize_cs16(x, x.size, raw)
+    elif sfmt == A.SFMT_CU8:
+        raw = np.zeros(2 * x.size, np.uint8)
+        O.lib().orc_quantize_cu8((x * 0.9).astype(np.complex64), x.size, raw)
+    else:
+        raw = x
+    p = run_oracle(sr, freqs, raw, sfmt, 0, ["ddc", "agc", "mf", "eq"])
+    ref = p.pdus()
+    fe = A.Frontend(sr, CF, freqs, sample_format=sfmt, max_blocks_per_batch=batch, capture_channel=0, capture_max=1 << 18, lib=lib)
+    g = fe.geom
+    assert (g.fft_size, g.input_size, g.fft_inv_size, g.scrap) == (p.ddc.fft_size, p.ddc.input_size, p.ddc.fft_inv_size, p.ddc.scrap)
+    if ragged:
+        rng = np.random.default_rng(9)
+        per = raw.size // x.size
+        i = 0
+        while i < x.size:
+            k = int(rng.integers(1, 3 * g.input_size))
+            fe.push(raw[i * per:(i + k) * per])
+            i += k
+        fe.push(raw[:0])
+    else:
+        fe.push(raw)
+    fe.flush()
+    got = fe.pdus()
+    compare_pdus(got, ref, truth if sfmt != A.SFMT_CU8 else None)
+    for c in range(len(freqs)):
+        assert fe.stats(c) == p.stats(c)
+    if check_floats:
+        # spectrum of the last processed block vs the oracle's last spectrum (oracle holds the swapped one)
+        spec = fe.checkpoint("spectrum", -1)
+        osp = np.fft.ifftshift(p.last_spectrum())
+        assert rel(spec, osp) < TOL_FFT * 2
+        ddc = fe.checkpoint("ddc", 0)
+        od = p.capture(0, "ddc")
+        assert rel(ddc, od[-ddc.size:]) < TOL_DDC
+        for name in ("agc", "mf", "eq"):
+            a, b = fe.checkpoint(name), p.capture(0, name)
+            assert a.size == b.size and rel(a, b) < TOL_DEMOD, name
+        # metadata that goes into hfdl_pdu_metadata (hfdl.c:1061-1067)
+        for q, r in zip(sorted(got, key=lambda z: (z.sample_cnt_end, z.freq)), sorted(ref, key=lambda z: (z.sample_cnt_end, z.freq))):
+            assert abs(q.freq_err_hz - r.freq_err_hz) < 1e-2
+            assert abs(q.signal_level - r.signal_level) / r.signal_level < 1e-3
+            assert abs(q.noise_floor_lin - r.noise_floor) / r.noise_floor < 1e-3
+            assert q.bit_rate == r.bit_rate and q.slot == r.slot
+            assert (q.train_bits_bad, q.train_bits_total) == (r.train_bits_bad, r.train_bits_total)
+    fe.close()
+    return len(got)

@@ -1,0 +1,40 @@
+"""CPU logic tests of the CUDA kernels: dumphfdl_b200/csrc compiled for host emulation (tests/cusim) and run
+through the same C ABI and the same parity cases as the GPU tests, at small sizes.  This is test
+infrastructure (there is no GPU in the development container); the product never loads this library."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+import b200_cases as K
+import dumphfdl_b200.api as A
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "cusim")], check=True)
+    return A.bind(C.CDLL(os.path.join(HERE, "cusim", "libhfdl_cusim.so")))
+
+
+def test_fft_one_and_two_pass(sim):
+    K.case_fft(sim, [64, 2048, 8192, 32768])
+
+
+def test_viterbi_bitexact(sim):
+    K.case_viterbi(sim, [540, 1080], frames=2)
+
+
+def test_fec_bitexact(sim):
+    K.case_fec(sim, [0, 3, 6])
+
+
+def test_frontend_cfg1_cs16(sim):
+    # BASELINE config 1: 250 ksps CS16, one channel
+    assert K.case_frontend(sim, 250000, [10063000], [1], 3.2, sfmt=A.SFMT_CS16, batch=4) == 1
+
+
+def test_frontend_two_channels_ragged_cf32(sim):
+    assert K.case_frontend(sim, 250000, [10063000, 9952000], [3, 0], 3.2, batch=3, ragged=True, seed=5) == 2

@@ -1,0 +1,124 @@
+"""GPU parity tests (-m gpu): libhfdl_b200.so on a real B200 through the C ABI vs the CPU oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import b200_cases as K
+import dumphfdl_b200 as hb
+import dumphfdl_b200.api as A
+import orclib as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = hb.load()
+    assert L.hfdl_b200_device_count() >= 1
+    return L
+
+
+def test_fft_all_plans(lib):
+    # 1-, 2- and 3-pass plans incl. the BASELINE sizes 2^15 (cfg1), 2^18 (cfg2), 2^22 (cfg3/4), 2^23 (cfg5)
+    K.case_fft(lib, [256, 4096, 8192, 32768, 262144, 524288], batch=3)
+    K.case_fft(lib, [1 << 22], batch=2, seed=2)
+    K.case_fft(lib, [1 << 23], batch=1, seed=3)
+
+
+def test_viterbi_bitexact_all_sizes(lib):
+    K.case_viterbi(lib, [540, 1080, 1260, 2160, 2520, 3240, 5040, 7560], frames=5)
+
+
+def test_fec_bitexact_all_modes(lib):
+    K.case_fec(lib, range(8))
+
+
+def test_fec_roundtrip_at_scale(lib):
+    # encode -> decode of 512 frames in one launch: every PDU comes back, FCS good (size-independent property)
+    L = O.lib()
+    for M1 in (1, 7):
+        nsym = [2160, 5040][M1 // 4]
+        pd = [O.make_pdu(M1, k % 2, seed=7000 + k) for k in range(512)]
+        S = np.zeros((512, nsym), np.complex64)
+        sym = np.zeros(5040, np.complex64)
+        for k, p in enumerate(pd):
+            L.orc_encode_user_data(np.frombuffer(p, np.uint8).copy(), M1, sym)
+            S[k] = sym[:nsym]
+        out, crc, _ = A.fec_decode(S, M1, 0, lib=lib)
+        assert all(bytes(out[k]) == pd[k] for k in range(512)) and crc.all()
+
+
+def test_frontend_cfg1_cs16(lib):
+    assert K.case_frontend(lib, 250000, [10063000], [1], 3.2, sfmt=A.SFMT_CS16, batch=8) == 1
+
+
+def test_frontend_cu8(lib):
+    assert K.case_frontend(lib, 250000, [10063000], [2], 3.2, sfmt=A.SFMT_CU8, batch=5, check_floats=False) == 1
+
+
+def test_frontend_cfg2_8ch_all_modes(lib):
+    # BASELINE config 2: 2 Msps CF32, 8 channels (one frame of every M1 mode)
+    sr = 2000000
+    freqs = [K.CF + int((k - 3.5) * 212000) // 1000 * 1000 for k in range(8)]
+    assert K.case_frontend(lib, sr, freqs, list(range(8)), 5.8, batch=16, seed=11) == 8
+
+
+def test_frontend_ragged_push_and_batch_size_invariance(lib):
+    n1 = K.case_frontend(lib, 250000, [10063000, 9952000, 10101000], [3, 0, 5], 5.6, batch=3, ragged=True, seed=5)
+    n2 = K.case_frontend(lib, 250000, [10063000, 9952000, 10101000], [3, 0, 5], 5.6, batch=64, seed=5)
+    assert n1 == n2 == 3
+
+
+def test_device_resident_path_equals_host_path(lib):
+    import torch
+    sr, freqs = 250000, [10063000, 9952000]
+    x, truth = K.make_capture(sr, freqs, [1, 2], 3.3, seed=21)
+    fe1 = A.Frontend(sr, K.CF, freqs, max_blocks_per_batch=8, lib=lib)
+    fe1.push(x)
+    fe1.flush()
+    a = fe1.pdus()
+    fe2 = A.Frontend(sr, K.CF, freqs, max_blocks_per_batch=8, lib=lib)
+    isz = fe2.geom.input_size
+    nb = x.size // isz
+    d = torch.from_numpy(x.view(np.float32).copy()).cuda()
+    torch.cuda.synchronize()
+    done = 0
+    while done < nb:
+        k = min(5, nb - done)
+        fe2.process_device(d.data_ptr(), x.size, done * isz, k)
+        done += k
+    b = fe2.pdus()
+    K.compare_pdus(b, [O_pdu(q) for q in a], truth)
+
+
+class O_pdu:
+    def __init__(self, q):
+        self.freq, self.sample_cnt_end, self._d, self.M1, self.crc_good, self.sample_cnt_a2 = q.freq, q.sample_cnt_end, q.data(), q.M1, q.crc_good, q.sample_cnt_a2
+
+    def data(self):
+        return self._d
+
+
+def test_golden_fixture(lib):
+    """PDUs / frame positions recorded from the oracle in the development container (tests/golden/make_golden.py)."""
+    with open(os.path.join(HERE, "golden", "cfg1_pdus.json")) as f:
+        G = json.load(f)
+    x, _ = K.make_capture(G["sample_rate"], G["freqs"], G["modes"], G["dur"], seed=G["seed"])
+    raw = np.zeros(2 * x.size, np.int16)
+    O.lib().orc_quantize_cs16(x, x.size, raw)
+    fe = A.Frontend(G["sample_rate"], K.CF, G["freqs"], sample_format=A.SFMT_CS16, max_blocks_per_batch=7, lib=lib)
+    fe.push(raw)
+    fe.flush()
+    got = sorted((q.freq, q.sample_cnt_a2, q.sample_cnt_end, q.M1, q.data().hex()) for q in fe.pdus())
+    want = sorted((p["freq"], p["a2"], p["end"], p["M1"], p["octets"]) for p in G["pdus"])
+    assert got == want
+
+
+def test_no_cpu_fallback_symbols(lib):
+    # the product library must not export anything of the oracle
+    import subprocess
+    out = subprocess.run(["nm", "-D", hb.LIB_PATH], capture_output=True, text=True).stdout
+    assert "orc_" not in out and "hfdl_b200_create" in out
