@@ -1,16 +1,23 @@
 // dumphfdl_b200/csrc/demod_kernels.cuh -- per-channel HFDL demodulator + framer (K6-K11) and
 // FEC (K12-K14) kernels for sm_100a.
 //
-// demod_kernel follows the per-sample / per-symbol loop of hfdl_decoder_thread (hfdl.c:685-893):
-// AGC -> 19-tap matched filter -> noise-floor tick -> symsync (16-arm Kaiser PFB, 2 outputs/symbol)
-// -> Costas -> T/2 LMS equaliser -> M-PSK slicer -> sampler -> framer FSM (A1/A2/M1/M2/T/data).
-// The feedback loops make this a strictly sequential recurrence per channel, so round 1 maps one
-// channel to one thread (channels are the only parallel axis the algorithm offers here) and keeps
-// the whole loop state in a per-channel struct in HBM between batches.
+// The reference runs the whole per-sample chain of hfdl_decoder_thread (hfdl.c:685-893) in one loop.
+// Its data dependencies split it into a feed-forward pipeline of three kernels:
+//   agc_kernel   K6      AGC (agc_crcf_execute, hfdl.c:686): a strictly sequential 2-state nonlinear
+//                        recurrence per channel, nothing downstream feeds back into it -> one thread per
+//                        channel runs the bare recurrence and writes gain-controlled samples + 1/g.
+//   bank_kernel  K7+K8a  matched filter (firfilt_crcf, hfdl.c:694-695) and the symbol synchroniser's 16-arm
+//                        polyphase matched / derivative filter banks (symsync_crcf, hfdl.c:503,707) evaluated
+//                        for EVERY sample and EVERY arm: pure FIR work, parallel over samples x arms.
+//   loop_kernel  K8b-K11 the feedback part: timing loop picks an arm per output, Costas rotation, T/2 LMS
+//                        equaliser, M-PSK slicer, sampler and the framer FSM (hfdl.c:708-891).  One warp
+//                        per channel; lanes hold a prefetched ring of bank rows (lane = arm), the arm the
+//                        loop selects is fetched with one warp shuffle, so the sequential critical path has
+//                        no dependent global load.
 // fec_kernel is decode_user_data (hfdl.c:993-1056): descramble + soft demod, 40-row deinterleaver
 // as a closed-form scatter/gather, chip averaging for r=1/4, K=7 Viterbi bit-exact with
-// libfec/viterbi27_port.c (one warp: 32 butterflies in 32 lanes, metrics exchanged by shuffles),
-// byte reversal and the frame check (pdu.c:68-79, mpdu.c:56-85, spdu.c:55-64).
+// libfec/viterbi27_port.c (one warp: 32 butterflies in 32 lanes), byte reversal and the frame check
+// (pdu.c:68-79, mpdu.c:56-85, spdu.c:55-64).
 #pragma once
 #include "common.cuh"
 
@@ -24,6 +31,10 @@
 #define HFDL_MAX_PDU 945
 #define HFDL_SINGLE_SLOT_FRAME_LEN 4219     // hfdl.c:41
 #define HFDL_FRAME_SLOTS 4                  // data-symbol buffers per channel (frames in flight per batch)
+#define HFDL_AGC_HIST (HFDL_MF_TAPS - 1 + HFDL_SS_SUB - 1)   // AGC-output samples kept in front of a batch (35)
+#define HFDL_MFO_HIST (HFDL_SS_SUB - 1)                     // matched-filter outputs kept in front of a batch (17)
+#define HFDL_BANK_TILE 64
+#define HFDL_PF 8                           // bank rows prefetched ahead by loop_kernel
 
 enum { HS_EMIT_BITS = 1, HS_EMIT_SYMBOLS = 2, HS_SKIP = 3 };
 enum { HF_A1 = 1, HF_A2, HF_M1, HF_M2_SKIP, HF_EQ_TRAIN, HF_DATA_1, HF_DATA_2 };
@@ -42,10 +53,10 @@ struct DemodTables {
 	int mode_arity[8], mode_segments[8], mode_code_rate[8], mode_col_shift[8];   // hfdl.c:81-138
 };
 
-struct DemodState {
-	float agc_g, agc_y2;
-	cf mf_win[HFDL_MF_TAPS];                 // [0] newest
-	cf ss_win_mf[HFDL_SS_SUB], ss_win_dmf[HFDL_SS_SUB];
+struct AgcState { float g, y2; };
+
+struct DemodState {                                  // loop_kernel state carried between batches
+	unsigned ss_since_reset;                         // pushes since the last symsync reset (saturates at 18)
 	unsigned ss_decim_counter;
 	float ss_rate, ss_del, ss_tau, ss_bf, ss_q, ss_q_hat;
 	int ss_b;
@@ -67,7 +78,7 @@ struct DemodState {
 	int st_a1, st_a2, st_m1, st_frames;
 };
 
-struct FrameRec {          // one completed frame handed from demod_kernel to fec_kernel
+struct FrameRec {          // one completed frame handed from loop_kernel to fec_kernel
 	int channel, slot, M1;
 	unsigned bitmask;
 	float freq_err_hz, signal_level, noise_floor;
@@ -83,15 +94,124 @@ struct PduRec {            // what the host turns into hfdl_pdu_metadata + octet
 	unsigned char octets[HFDL_MAX_PDU + 3];
 };
 
-struct DemodArgs {
+// ======================================================================================
+// K6: AGC.  grid = C blocks of 32 threads, lane 0 runs the recurrence of channel blockIdx.x.
+//   y = x*g;  y2' = (1-a)*y2' + a*|y|^2;  if(y2' > 1e-6) g *= exp(-0.5*a*ln y2');  g = min(g, 1e6)   (a = 0.01)
+// ======================================================================================
+struct AgcArgs {
 	const cf *rs; long long rs_stride; int n_samples;
+	AgcState *state;
+	cf *agc_out; long long agc_stride;       // [C][HFDL_AGC_HIST + n]
+	float *lvl; long long lvl_stride;        // [C][n]  1/g after the update (agc_crcf_get_signal_level)
+};
+
+__global__ void __launch_bounds__(32) agc_kernel(AgcArgs a) {
+	const int c = blockIdx.x;
+	if(threadIdx.x != 0) return;
+	const cf *x = a.rs + (long long)c * a.rs_stride;
+	cf *out = a.agc_out + (long long)c * a.agc_stride + HFDL_AGC_HIST;
+	float *lvl = a.lvl + (long long)c * a.lvl_stride;
+	float g = a.state[c].g, y2 = a.state[c].y2;
+	const float alpha = 0.01f;
+	for(int k0 = 0; k0 < a.n_samples; k0 += 8) {
+		cf xv[8];
+#pragma unroll
+		for(int u = 0; u < 8; u++) xv[u] = (k0 + u < a.n_samples) ? x[k0 + u] : make_float2(0.f, 0.f);
+#pragma unroll
+		for(int u = 0; u < 8; u++) {
+			if(k0 + u < a.n_samples) {
+				cf r = make_float2(xv[u].x * g, xv[u].y * g);
+				float p = r.x * r.x + r.y * r.y;
+				// (1.0 - alpha)*y2 + alpha*p with the product term kept exact: y2 - alpha*y2
+				y2 = fmaf(alpha, p, fmaf(-alpha, y2, y2));
+				if(y2 > 1e-6f) g *= expf(-0.5f * alpha * logf(y2));
+				g = fminf(g, 1e6f);
+				out[k0 + u] = r;
+				lvl[k0 + u] = 1.0f / g;
+			}
+		}
+	}
+	a.state[c].g = g; a.state[c].y2 = y2;
+}
+
+// ======================================================================================
+// K7+K8a: matched filter + symsync filter banks.  grid = (ceil(n/TILE), C), 256 threads.
+// bank[c][n][arm]: arm 0..15 = matched-filter arm output (before the 1/k scaling), 16..31 = derivative arm.
+// ======================================================================================
+struct BankArgs {
+	const cf *agc_out; long long agc_stride; int n_samples;
+	cf *mfo; long long mfo_stride;           // [C][HFDL_MFO_HIST + n]   matched filter output (f_mf_out)
+	cf *bank; long long bank_stride;         // [C][n][32]
+	const DemodTables *tab;
+};
+
+__global__ void __launch_bounds__(256) bank_kernel(BankArgs a) {
+	__shared__ cf s_agc[HFDL_BANK_TILE + HFDL_AGC_HIST];
+	__shared__ cf s_mfo[HFDL_BANK_TILE + HFDL_MFO_HIST];
+	__shared__ float s_mf[HFDL_MF_TAPS];
+	const int c = blockIdx.y;
+	const int n0 = blockIdx.x * HFDL_BANK_TILE;
+	const int tid = threadIdx.x;
+	const DemodTables &T = *a.tab;
+	const cf *ag = a.agc_out + (long long)c * a.agc_stride + HFDL_AGC_HIST;     // ag[n], n >= -35 valid
+	for(int i = tid; i < HFDL_BANK_TILE + HFDL_AGC_HIST; i += blockDim.x) {
+		int n = n0 - HFDL_AGC_HIST + i;
+		s_agc[i] = (n < a.n_samples) ? ag[n] : make_float2(0.f, 0.f);
+	}
+	if(tid < HFDL_MF_TAPS) s_mf[tid] = T.mf[tid];
+	__syncthreads();
+	// matched filter for samples n0-17 .. n0+TILE-1 (the 17 extra ones re-create the bank's input history)
+	for(int i = tid; i < HFDL_BANK_TILE + HFDL_MFO_HIST; i += blockDim.x) {
+		const cf *w = s_agc + i + (HFDL_AGC_HIST - HFDL_MFO_HIST);     // sample n = n0-17+i  <->  s_agc[i+18]
+		float re = 0.f, im = 0.f;
+#pragma unroll
+		for(int k = HFDL_MF_TAPS - 1; k >= 0; k--) { re += s_mf[k] * w[-k].x; im += s_mf[k] * w[-k].y; }   // oldest first
+		s_mfo[i] = make_float2(re, im);
+		int n = n0 - HFDL_MFO_HIST + i;
+		if(i >= HFDL_MFO_HIST && n < a.n_samples) a.mfo[(long long)c * a.mfo_stride + HFDL_MFO_HIST + n] = make_float2(re, im);
+	}
+	__syncthreads();
+	const int lane = tid & 31, warp = tid >> 5;
+	float h[HFDL_SS_SUB];
+#pragma unroll
+	for(int j = 0; j < HFDL_SS_SUB; j++) h[j] = (lane < 16) ? T.ss_mf[lane][j] : T.ss_dmf[lane - 16][j];
+	for(int s = warp; s < HFDL_BANK_TILE; s += 8) {
+		int n = n0 + s;
+		if(n >= a.n_samples) break;
+		const cf *w = s_mfo + s + HFDL_MFO_HIST;
+		float re = 0.f, im = 0.f;
+#pragma unroll
+		for(int j = HFDL_SS_SUB - 1; j >= 0; j--) { re += h[j] * w[-j].x; im += h[j] * w[-j].y; }
+		a.bank[((long long)c * a.bank_stride + n) * 32 + lane] = make_float2(re, im);
+	}
+}
+
+// carries the tails of the per-channel work streams in front of the next batch
+__global__ void demod_carry(cf *agc_out, long long agc_stride, cf *mfo, long long mfo_stride, long long n_new) {
+	int c = blockIdx.x, t = threadIdx.x;
+	cf *ra = agc_out + (long long)c * agc_stride, *rm = mfo + (long long)c * mfo_stride;
+	cf va = make_float2(0.f, 0.f), vm = va;
+	if(t < HFDL_AGC_HIST) va = ra[n_new + t];
+	if(t < HFDL_MFO_HIST) vm = rm[n_new + t];
+	__syncthreads();
+	if(t < HFDL_AGC_HIST) ra[t] = va;
+	if(t < HFDL_MFO_HIST) rm[t] = vm;
+}
+
+// ======================================================================================
+// K8b-K11: timing loop, Costas, equaliser, slicer, framer.  One warp per channel; every lane runs the
+// same (warp-uniform) scalar state machine, lanes differ only in the bank arm they prefetch.
+// ======================================================================================
+struct LoopArgs {
+	const cf *bank; long long bank_stride;
+	const cf *mfo; long long mfo_stride;
+	const float *lvl; long long lvl_stride;
+	int n_samples;
 	DemodState *state;
 	const DemodTables *tab;
 	cf *datasym;               // [C][HFDL_FRAME_SLOTS][HFDL_DATA_SYMS_MAX]
 	FrameRec *frames; int *nframes; int max_frames;
-	int C;
-	// optional capture of one channel's checkpoints (the reference's DATADUMPS taps, hfdl.c:616-655)
-	int cap_channel; cf *cap_agc, *cap_mf, *cap_eq; int *cap_cnt; int cap_max;
+	int cap_channel; cf *cap_eq; int *cap_cnt; int cap_max;      // f_eq_out checkpoint of one channel
 };
 
 __device__ __forceinline__ void bits_push(unsigned *b, unsigned bit) {
@@ -105,12 +225,13 @@ __device__ __forceinline__ int bits_corr(const unsigned *a, const unsigned *b) {
 }
 
 __device__ __forceinline__ void ss_reset(DemodState &S) {     // symsync_crcf_reset: mf window, timing state, loop filter
-	for(int i = 0; i < HFDL_SS_SUB; i++) S.ss_win_mf[i] = make_float2(0.f, 0.f);
-	S.ss_rate = 1.5f; S.ss_del = 1.5f;                       // k / k_out = 3/2
+	S.ss_since_reset = 0;                                     // the mf-arm window is cleared, the dmf one is not
+	S.ss_rate = 1.5f; S.ss_del = 1.5f;                        // k / k_out = 3/2
 	S.ss_b = 0; S.ss_bf = 0.f; S.ss_tau = 0.f; S.ss_q = 0.f; S.ss_q_hat = 0.f; S.ss_decim_counter = 0;
 	S.ss_v[0] = S.ss_v[1] = S.ss_v[2] = 0.f;
 }
 __device__ __forceinline__ void eq_reset(DemodState &S, const DemodTables &T) {
+#pragma unroll
 	for(int i = 0; i < HFDL_EQ_LEN; i++) { S.eq_w[i] = T.eq_h0[i]; S.eq_win[i] = make_float2(0.f, 0.f); S.eq_x2[i] = 0.f; }
 	S.eq_count = 0; S.eq_buf_full = 0; S.eq_x2_sum = 0.f;
 }
@@ -123,7 +244,7 @@ __device__ __forceinline__ void framer_reset(DemodState &S, const DemodTables &T
 	S.s_state = HS_EMIT_BITS; S.bitmask = 0;
 }
 
-// hard decision + phase error: liquid modem_demodulate / get_demodulator_phase_error for BPSK, PSK4, PSK8
+// hard decision of liquid's modem_demodulate for BPSK / PSK4 / PSK8 (gray-coded symbol) + re-modulated point
 __device__ __forceinline__ unsigned modem_demod(int m, cf x, const DemodTables &T, cf *x_hat) {
 	unsigned sym;
 	if(m == 1) {
@@ -149,251 +270,271 @@ __device__ __forceinline__ unsigned modem_demod(int m, cf x, const DemodTables &
 	return sym;
 }
 
-__global__ void demod_kernel(DemodArgs a) {
-	const int c = blockIdx.x * blockDim.x + threadIdx.x;
-	if(c >= a.C) return;
+__global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
+	const int c = blockIdx.x;
+	const int lane = threadIdx.x;
 	const DemodTables &T = *a.tab;
 	DemodState S = a.state[c];
-	const cf *x = a.rs + (long long)c * a.rs_stride;
+	const cf *bank = a.bank + (long long)c * a.bank_stride * 32;
+	const cf *mfo = a.mfo + (long long)c * a.mfo_stride + HFDL_MFO_HIST;
+	const float *lvl = a.lvl + (long long)c * a.lvl_stride;
 	const bool cap = (c == a.cap_channel);
-	int cap_n_agc = 0, cap_n_eq = 0;
-	if(cap) { cap_n_agc = a.cap_cnt[0]; cap_n_eq = a.cap_cnt[1]; }
+	int cap_n_eq = cap ? a.cap_cnt[1] : 0;
 	cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+	const float ss_a1 = T.ss_a1, ss_a2 = T.ss_a2, ss_b0 = T.ss_b0, ss_radj = T.ss_rate_adj;
 
-	for(int k = 0; k < a.n_samples; k++, S.sample_cnt++) {
-		// ---- agc_crcf_execute (bandwidth 0.01, hfdl.c:485-487,686)
-		cf r = cscale(x[k], S.agc_g);
-		float y2 = r.x * r.x + r.y * r.y;
-		S.agc_y2 = (float)((1.0 - (double)0.01f) * (double)S.agc_y2 + (double)(0.01f * y2));
-		if(S.agc_y2 > 1e-6f) S.agc_g *= expf(-0.5f * 0.01f * logf(S.agc_y2));
-		if(S.agc_g > 1e6f) S.agc_g = 1e6f;
-		// ---- matched filter (firfilt_crcf, hfdl.c:694-695)
-		for(int i = HFDL_MF_TAPS - 1; i > 0; i--) S.mf_win[i] = S.mf_win[i - 1];
-		S.mf_win[0] = r;
-		cf s = make_float2(0.f, 0.f);
-		for(int i = HFDL_MF_TAPS - 1; i >= 0; i--) { s.x += T.mf[i] * S.mf_win[i].x; s.y += T.mf[i] * S.mf_win[i].y; }
-		if(cap && cap_n_agc < a.cap_max) { a.cap_agc[cap_n_agc] = r; a.cap_mf[cap_n_agc] = s; }
-		if(cap) cap_n_agc++;
-		// ---- noise floor (hfdl.c:700-706)
-		if(S.fr_state == HF_A1 && (++S.nf_clk & 0xFFu) == 0xFFu)
-			S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, 1.0f / S.agc_g) + 1e-6f;
-		// ---- symsync_crcf_execute (hfdl.c:707)
-		for(int i = HFDL_SS_SUB - 1; i > 0; i--) { S.ss_win_mf[i] = S.ss_win_mf[i - 1]; S.ss_win_dmf[i] = S.ss_win_dmf[i - 1]; }
-		S.ss_win_mf[0] = s; S.ss_win_dmf[0] = s;
-		cf symbols[4];
-		int produced = 0;
-		while(S.ss_b < HFDL_SS_NPFB) {
-			cf mf = make_float2(0.f, 0.f);
-			const float *h = T.ss_mf[S.ss_b];
-			for(int i = HFDL_SS_SUB - 1; i >= 0; i--) { mf.x += h[i] * S.ss_win_mf[i].x; mf.y += h[i] * S.ss_win_mf[i].y; }
-			if(produced < 4) symbols[produced] = make_float2(mf.x / 3.0f, mf.y / 3.0f);
-			if(S.ss_decim_counter == 2u) {
-				S.ss_decim_counter = 0;
-				cf dmf = make_float2(0.f, 0.f);
-				const float *dh = T.ss_dmf[S.ss_b];
-				for(int i = HFDL_SS_SUB - 1; i >= 0; i--) { dmf.x += dh[i] * S.ss_win_dmf[i].x; dmf.y += dh[i] * S.ss_win_dmf[i].y; }
-				float q = mf.x * dmf.x + mf.y * dmf.y;           // Re(conj(mf)*dmf)
-				q = fminf(fmaxf(q, -1.0f), 1.0f);
-				S.ss_q = q;
-				S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0];
-				S.ss_v[0] = q - T.ss_a1 * S.ss_v[1] - T.ss_a2 * S.ss_v[2];
-				S.ss_q_hat = T.ss_b0 * S.ss_v[0];
-				S.ss_rate += T.ss_rate_adj * S.ss_q_hat;
-				S.ss_del = S.ss_rate + S.ss_q_hat;
-			}
-			S.ss_decim_counter++;
-			S.ss_tau += S.ss_del;
-			S.ss_bf = S.ss_tau * (float)HFDL_SS_NPFB;
-			S.ss_b = (int)roundf(S.ss_bf);
-			produced++;
-		}
-		S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
-		if(produced > 4) produced = 4;
+	cf ring[HFDL_PF];
+#pragma unroll
+	for(int u = 0; u < HFDL_PF; u++) ring[u] = (u < a.n_samples) ? bank[(long long)u * 32 + lane] : make_float2(0.f, 0.f);
 
-		for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
-			// ---- Costas step + rotate (hfdl.c:250-294,709-715)
-			S.c_phi += S.c_dphi;
-			if((double)S.c_phi > M_PI) S.c_phi = (float)((double)S.c_phi - 2.0 * M_PI);
-			else if((double)S.c_phi < -M_PI) S.c_phi = (float)((double)S.c_phi + 2.0 * M_PI);
-			float sn, cs;
-			sincosf(S.c_phi, &sn, &cs);
-			r = make_float2(symbols[i].x * cs + symbols[i].y * sn, symbols[i].y * cs - symbols[i].x * sn);
-			if(fabsf(S.c_dphi) > 0.25f && S.fr_state == HF_A1) {
-				S.c_phi = S.c_dphi = 0.f;
-				ss_reset(S);
-			}
-			// ---- eqlms_cccf_push
-			for(int j = 0; j < HFDL_EQ_LEN - 1; j++) { S.eq_win[j] = S.eq_win[j + 1]; }
-			S.eq_win[HFDL_EQ_LEN - 1] = r;
-			{
-				float x2n = r.x * r.x + r.y * r.y, x20 = S.eq_x2[0];
-				for(int j = 0; j < HFDL_EQ_LEN - 1; j++) S.eq_x2[j] = S.eq_x2[j + 1];
-				S.eq_x2[HFDL_EQ_LEN - 1] = x2n;
-				S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
-				S.eq_count++;
-			}
-			if(!(S.symsync_out_idx & 1u)) continue;
-			// ---- eqlms_cccf_execute: y = sum conj(w[i]) * x[i]
-			s = make_float2(0.f, 0.f);
-			for(int j = 0; j < HFDL_EQ_LEN; j++) {
-				cf w = S.eq_w[j], v = S.eq_win[j];
-				s.x += w.x * v.x + w.y * v.y;
-				s.y += w.x * v.y - w.y * v.x;
-			}
-			if(S.fr_state == HF_EQ_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
-				float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
-				if(S.bitmask & 1u) d = -d;
-				bool run = true;
-				if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
-				if(run) {
-					cf al = make_float2(d - s.x, -s.y);                  // alpha = d - d_hat
-					float g = 0.1f;                                      // mu (hfdl.c:496)
+	for(int k0 = 0; k0 < a.n_samples; k0 += HFDL_PF) {
+#pragma unroll
+		for(int u = 0; u < HFDL_PF; u++) {
+			const int k = k0 + u;
+			if(k < a.n_samples) {
+				const cf row = ring[u];
+				ring[u] = (k + HFDL_PF < a.n_samples) ? bank[(long long)(k + HFDL_PF) * 32 + lane] : make_float2(0.f, 0.f);
+				const float level = lvl[k];                      // 1/g after this sample's AGC update
+				// ---- noise floor (hfdl.c:700-706)
+				if(S.fr_state == HF_A1 && (++S.nf_clk & 0xFFu) == 0xFFu)
+					S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, level) + 1e-6f;
+				// ---- symsync_crcf_step (push happened in bank_kernel; the reset only clears the mf-arm window)
+				if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
+				cf symbols[4];
+				int produced = 0;
+				while(S.ss_b < HFDL_SS_NPFB) {
+					cf mf;
+					mf.x = __shfl_sync(0xffffffffu, row.x, S.ss_b);
+					mf.y = __shfl_sync(0xffffffffu, row.y, S.ss_b);
+					if(S.ss_since_reset < HFDL_SS_SUB) {
+						// window still filling after a reset: only the samples pushed since then contribute
+						mf = make_float2(0.f, 0.f);
+						const float *h = T.ss_mf[S.ss_b];
+						for(int j = (int)S.ss_since_reset - 1; j >= 0; j--) { cf v = mfo[k - j]; mf.x += h[j] * v.x; mf.y += h[j] * v.y; }
+					}
+					if(produced < 4) symbols[produced] = make_float2(mf.x / 3.0f, mf.y / 3.0f);
+					if(S.ss_decim_counter == 2u) {
+						S.ss_decim_counter = 0;
+						cf dmf;
+						dmf.x = __shfl_sync(0xffffffffu, row.x, 16 + S.ss_b);
+						dmf.y = __shfl_sync(0xffffffffu, row.y, 16 + S.ss_b);
+						float q = mf.x * dmf.x + mf.y * dmf.y;           // Re(conj(mf)*dmf)
+						q = fminf(fmaxf(q, -1.0f), 1.0f);
+						S.ss_q = q;
+						S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0];
+						S.ss_v[0] = q - ss_a1 * S.ss_v[1] - ss_a2 * S.ss_v[2];
+						S.ss_q_hat = ss_b0 * S.ss_v[0];
+						S.ss_rate += ss_radj * S.ss_q_hat;
+						S.ss_del = S.ss_rate + S.ss_q_hat;
+					}
+					S.ss_decim_counter++;
+					S.ss_tau += S.ss_del;
+					S.ss_bf = S.ss_tau * (float)HFDL_SS_NPFB;
+					S.ss_b = (int)roundf(S.ss_bf);
+					produced++;
+				}
+				S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
+				if(produced > 4) produced = 4;
+
+				for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
+					// ---- Costas step + rotate (hfdl.c:250-294,709-715)
+					S.c_phi += S.c_dphi;
+					if((double)S.c_phi > M_PI) S.c_phi = (float)((double)S.c_phi - 2.0 * M_PI);
+					else if((double)S.c_phi < -M_PI) S.c_phi = (float)((double)S.c_phi + 2.0 * M_PI);
+					float sn, cs;
+					sincosf(S.c_phi, &sn, &cs);
+					cf r = make_float2(symbols[i].x * cs + symbols[i].y * sn, symbols[i].y * cs - symbols[i].x * sn);
+					if(fabsf(S.c_dphi) > 0.25f && S.fr_state == HF_A1) {
+						S.c_phi = S.c_dphi = 0.f;
+						ss_reset(S);
+					}
+					// ---- eqlms_cccf_push
+#pragma unroll
+					for(int j = 0; j < HFDL_EQ_LEN - 1; j++) { S.eq_win[j] = S.eq_win[j + 1]; }
+					S.eq_win[HFDL_EQ_LEN - 1] = r;
+					{
+						float x2n = r.x * r.x + r.y * r.y, x20 = S.eq_x2[0];
+#pragma unroll
+						for(int j = 0; j < HFDL_EQ_LEN - 1; j++) S.eq_x2[j] = S.eq_x2[j + 1];
+						S.eq_x2[HFDL_EQ_LEN - 1] = x2n;
+						S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
+						S.eq_count++;
+					}
+					if(!(S.symsync_out_idx & 1u)) continue;
+					// ---- eqlms_cccf_execute: y = sum conj(w[i]) * x[i]
+					cf s = make_float2(0.f, 0.f);
+#pragma unroll
 					for(int j = 0; j < HFDL_EQ_LEN; j++) {
-						cf v = S.eq_win[j];
-						// mu * conj(alpha) * x[j] / x2_sum
-						cf t = make_float2(g * al.x, -g * al.y);
-						cf u = cmul(t, v);
-						S.eq_w[j].x += u.x / S.eq_x2_sum;
-						S.eq_w[j].y += u.y / S.eq_x2_sum;
+						cf w = S.eq_w[j], v = S.eq_win[j];
+						s.x += w.x * v.x + w.y * v.y;
+						s.y += w.x * v.y - w.y * v.x;
+					}
+					if(S.fr_state == HF_EQ_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
+						float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
+						if(S.bitmask & 1u) d = -d;
+						bool run = true;
+						if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
+						if(run) {
+							cf t = make_float2(0.1f * (d - s.x), 0.1f * s.y);      // mu * conj(d - d_hat), mu = 0.1 (hfdl.c:496)
+#pragma unroll
+							for(int j = 0; j < HFDL_EQ_LEN; j++) {
+								cf uu = cmul(t, S.eq_win[j]);
+								S.eq_w[j].x += uu.x / S.eq_x2_sum;
+								S.eq_w[j].y += uu.y / S.eq_x2_sum;
+							}
+						}
+						S.T_idx++;
+					}
+					if(cap && lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s;
+					if(cap) cap_n_eq++;
+					cf x_hat;
+					unsigned bits = modem_demod(S.cur_arity, s, T, &x_hat);
+					// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
+					float err = s.y * x_hat.x - s.x * x_hat.y;
+					err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
+					S.c_phi += 0.1f * err;
+					S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
+
+					S.symbol_cnt++;
+					if(S.symbol_cnt >= 13ull * HFDL_SINGLE_SLOT_FRAME_LEN && S.fr_state == HF_A1) {
+						S.symbol_cnt = 0;
+						S.c_phi = S.c_dphi = 0.f;
+						ss_reset(S);
+					}
+					if(S.s_state == HS_EMIT_BITS) {
+						bits ^= S.bitmask;
+						for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
+					} else if(S.s_state == HS_EMIT_SYMBOLS) {
+						if(S.cur_buf == 0) {
+							if(S.training_n < HFDL_T_LEN) {
+#pragma unroll
+								for(int j = 0; j < HFDL_T_LEN; j++) if(j == S.training_n) S.training[j] = s;
+								S.training_n++;
+							}
+						} else {
+							if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
+						}
+					}
+					if(S.fr_state > HF_A1) {
+						S.signal_level = (S.signal_level * S.frame_symbol_cnt + level) / (S.frame_symbol_cnt + 1.0f);
+						S.frame_symbol_cnt += 1.0f;
+					}
+					if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }
+
+					switch(S.fr_state) {
+					case HF_A1: {
+						float corr = 2.0f * (float)bits_corr(T.A_bits, S.bits) / 127.0f - 1.0f;
+						if(fabsf(corr) > 0.36f) {
+							S.st_a1++;
+							S.bitmask = corr > 0.f ? 0u : ~0u;
+							S.signal_level = level;
+							S.frame_symbol_cnt = 1.0f;
+							S.symbols_wanted = HFDL_A_LEN;
+							S.search_retries = 0;
+							S.fr_state = HF_A2;
+						}
+						break; }
+					case HF_A2: {
+						float corr = 2.0f * (float)bits_corr(T.A_bits, S.bits) / 127.0f - 1.0f;
+						if(fabsf(corr) > 0.3f) {
+							S.a2_sample_cnt = S.sample_cnt;
+							S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
+							S.st_a2++;
+							S.symbols_wanted = 127;
+							S.search_retries = 0;
+							S.fr_state = HF_M1;
+						} else if(++S.search_retries >= 3) {
+							framer_reset(S, T);
+						}
+						break; }
+					case HF_M1: {
+						float max_corr = 0.f; int max_idx = -1;
+						for(int idx = 0; idx < 8; idx++) {
+							float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
+							if(corr > max_corr) { max_corr = corr; max_idx = idx; }
+						}
+						if(max_corr > 0.3f) {
+							S.st_m1++;
+							S.data_segment_cnt = T.mode_segments[max_idx];
+							S.data_arity = T.mode_arity[max_idx];
+							S.M1 = max_idx;
+							S.symbols_wanted = 15;
+							S.search_retries = 0;
+							S.fr_state = HF_M2_SKIP;
+							S.s_state = HS_SKIP;
+						} else {
+							framer_reset(S, T);
+						}
+						break; }
+					case HF_M2_SKIP:
+						S.training_n = 0;
+						S.symbols_wanted = HFDL_T_LEN;
+						S.eq_train_seq_cnt = 9;
+						S.fr_state = HF_EQ_TRAIN;
+						S.s_state = HS_EMIT_SYMBOLS;
+						break;
+					case HF_EQ_TRAIN: {
+						unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
+#pragma unroll
+						for(int j = 0; j < HFDL_T_LEN; j++) {
+							unsigned bit = (S.training[j].x > 0.f) ? 0u : 1u;
+							bit ^= (S.bitmask & 1u);
+							tseq = (tseq << 1) | bit;
+						}
+						S.train_bits_total += HFDL_T_LEN;
+						S.train_bits_bad += __popc(0x9AFu ^ tseq);
+						S.training_n = 0;
+						if(S.eq_train_seq_cnt > 1) {
+							S.eq_train_seq_cnt--;
+							S.symbols_wanted = HFDL_T_LEN;
+							S.T_idx = 0;
+						} else if(S.data_segment_cnt > 0) {
+							S.symbols_wanted = 15;
+							S.fr_state = HF_DATA_1;
+							S.cur_arity = S.data_arity;
+							S.cur_buf = 1;
+						} else {                                 // end of frame: hand the symbols to fec_kernel
+							int q = 0;
+							if(lane == 0) q = atomicAdd(a.nframes, 1);
+							q = __shfl_sync(0xffffffffu, q, 0);
+							if(q < a.max_frames && lane == 0) {
+								FrameRec fr;
+								fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
+								fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
+								fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = S.sample_cnt;
+								fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
+								a.frames[q] = fr;
+							}
+							S.st_frames++;
+							S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
+							dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+							framer_reset(S, T);
+							S.symbol_cnt = 0;
+						}
+						break; }
+					case HF_DATA_1:
+						S.symbols_wanted = 15;
+						S.fr_state = HF_DATA_2;
+						break;
+					case HF_DATA_2:
+						S.data_segment_cnt--;
+						S.cur_arity = 1;
+						S.cur_buf = 0;
+						S.fr_state = HF_EQ_TRAIN;
+						S.eq_train_seq_cnt = 1;
+						S.symbols_wanted = HFDL_T_LEN;
+						S.T_idx = 0;
+						break;
 					}
 				}
-				S.T_idx++;
-			}
-			if(cap && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s;
-			if(cap) cap_n_eq++;
-			cf x_hat;
-			unsigned bits = modem_demod(S.cur_arity, s, T, &x_hat);
-			// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
-			float err = s.y * x_hat.x - s.x * x_hat.y;
-			err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
-			S.c_phi += 0.1f * err;
-			S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
-
-			S.symbol_cnt++;
-			if(S.symbol_cnt >= 13ull * HFDL_SINGLE_SLOT_FRAME_LEN && S.fr_state == HF_A1) {
-				S.symbol_cnt = 0;
-				S.c_phi = S.c_dphi = 0.f;
-				ss_reset(S);
-			}
-			if(S.s_state == HS_EMIT_BITS) {
-				bits ^= S.bitmask;
-				for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
-			} else if(S.s_state == HS_EMIT_SYMBOLS) {
-				if(S.cur_buf == 0) { if(S.training_n < HFDL_T_LEN) S.training[S.training_n++] = s; }
-				else { if(S.data_n < HFDL_DATA_SYMS_MAX) dsym[S.data_n++] = s; }
-			}
-			if(S.fr_state > HF_A1) {
-				S.signal_level = (S.signal_level * S.frame_symbol_cnt + 1.0f / S.agc_g) / (S.frame_symbol_cnt + 1.0f);
-				S.frame_symbol_cnt += 1.0f;
-			}
-			if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }
-
-			switch(S.fr_state) {
-			case HF_A1: {
-				float corr = 2.0f * (float)bits_corr(T.A_bits, S.bits) / 127.0f - 1.0f;
-				if(fabsf(corr) > 0.36f) {
-					S.st_a1++;
-					S.bitmask = corr > 0.f ? 0u : ~0u;
-					S.signal_level = 1.0f / S.agc_g;
-					S.frame_symbol_cnt = 1.0f;
-					S.symbols_wanted = HFDL_A_LEN;
-					S.search_retries = 0;
-					S.fr_state = HF_A2;
-				}
-				break; }
-			case HF_A2: {
-				float corr = 2.0f * (float)bits_corr(T.A_bits, S.bits) / 127.0f - 1.0f;
-				if(fabsf(corr) > 0.3f) {
-					S.a2_sample_cnt = S.sample_cnt;
-					S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
-					S.st_a2++;
-					S.symbols_wanted = 127;
-					S.search_retries = 0;
-					S.fr_state = HF_M1;
-				} else if(++S.search_retries >= 3) {
-					framer_reset(S, T);
-				}
-				break; }
-			case HF_M1: {
-				float max_corr = 0.f; int max_idx = -1;
-				for(int idx = 0; idx < 8; idx++) {
-					float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
-					if(corr > max_corr) { max_corr = corr; max_idx = idx; }
-				}
-				if(max_corr > 0.3f) {
-					S.st_m1++;
-					S.data_segment_cnt = T.mode_segments[max_idx];
-					S.data_arity = T.mode_arity[max_idx];
-					S.M1 = max_idx;
-					S.symbols_wanted = 15;
-					S.search_retries = 0;
-					S.fr_state = HF_M2_SKIP;
-					S.s_state = HS_SKIP;
-				} else {
-					framer_reset(S, T);
-				}
-				break; }
-			case HF_M2_SKIP:
-				S.training_n = 0;
-				S.symbols_wanted = HFDL_T_LEN;
-				S.eq_train_seq_cnt = 9;
-				S.fr_state = HF_EQ_TRAIN;
-				S.s_state = HS_EMIT_SYMBOLS;
-				break;
-			case HF_EQ_TRAIN: {
-				unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
-				for(int j = 0; j < HFDL_T_LEN; j++) {
-					unsigned bit = (S.training[j].x > 0.f) ? 0u : 1u;
-					bit ^= (S.bitmask & 1u);
-					tseq = (tseq << 1) | bit;
-				}
-				S.train_bits_total += HFDL_T_LEN;
-				S.train_bits_bad += __popc(0x9AFu ^ tseq);
-				S.training_n = 0;
-				if(S.eq_train_seq_cnt > 1) {
-					S.eq_train_seq_cnt--;
-					S.symbols_wanted = HFDL_T_LEN;
-					S.T_idx = 0;
-				} else if(S.data_segment_cnt > 0) {
-					S.symbols_wanted = 15;
-					S.fr_state = HF_DATA_1;
-					S.cur_arity = S.data_arity;
-					S.cur_buf = 1;
-				} else {                                 // end of frame: hand the symbols to fec_kernel
-					int q = atomicAdd(a.nframes, 1);
-					if(q < a.max_frames) {
-						FrameRec fr;
-						fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
-						fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
-						fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = S.sample_cnt;
-						fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
-						a.frames[q] = fr;
-					}
-					S.st_frames++;
-					S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
-					dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
-					framer_reset(S, T);
-					S.symbol_cnt = 0;
-				}
-				break; }
-			case HF_DATA_1:
-				S.symbols_wanted = 15;
-				S.fr_state = HF_DATA_2;
-				break;
-			case HF_DATA_2:
-				S.data_segment_cnt--;
-				S.cur_arity = 1;
-				S.cur_buf = 0;
-				S.fr_state = HF_EQ_TRAIN;
-				S.eq_train_seq_cnt = 1;
-				S.symbols_wanted = HFDL_T_LEN;
-				S.T_idx = 0;
-				break;
+				S.sample_cnt++;
 			}
 		}
 	}
-	a.state[c] = S;
-	if(cap) { a.cap_cnt[0] = cap_n_agc; a.cap_cnt[1] = cap_n_eq; }
+	if(lane == 0) {
+		a.state[c] = S;
+		if(cap) a.cap_cnt[1] = cap_n_eq;
+	}
 }
 
 // ======================================================================================

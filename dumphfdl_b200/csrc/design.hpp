@@ -212,8 +212,8 @@ inline int pdu_len(int M1) {
 
 inline void demod_state_init(DemodState &S, const DemodTables &T) {      // hfdl_channel_create, hfdl.c:485-521
 	memset(&S, 0, sizeof(S));
-	S.agc_g = 1.0f; S.agc_y2 = 1.0f;
-	S.noise_floor = 1.0f;
+	S.noise_floor = 1.0f;                               // hfdl.c:490
+	S.ss_since_reset = 0;
 	// symsync created (reset), then k_out = 2
 	S.ss_rate = 1.5f; S.ss_del = 1.5f;
 	for(int i = 0; i < HFDL_EQ_LEN; i++) S.eq_w[i] = T.eq_h0[i];

@@ -20,8 +20,8 @@
 
 namespace {
 
-enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_DEMOD, KC_FEC, KC_COUNT };
-const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "demod", "fec" };
+enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_AGC, KC_BANK, KC_LOOP, KC_FEC, KC_COUNT };
+const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "agc", "bank", "loop", "fec" };
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
 
@@ -80,7 +80,9 @@ struct hfdl_b200_frontend {
 	cf *d_tapslice = nullptr; int *d_offsetbin = nullptr; float *d_dsa_rate = nullptr;
 	cf *d_bb = nullptr; long long bb_stride = 0;
 	cf *d_rs = nullptr; long long rs_stride = 0; float *d_rs_h = nullptr;
-	DemodTables *d_tab = nullptr; DemodState *d_state = nullptr; cf *d_datasym = nullptr;
+	DemodTables *d_tab = nullptr; DemodState *d_state = nullptr; AgcState *d_agc_state = nullptr; cf *d_datasym = nullptr;
+	cf *d_agc = nullptr, *d_mfo = nullptr, *d_bank = nullptr; float *d_lvl = nullptr; long long agc_stride = 0, mfo_stride = 0;
+	long long cap_n = 0;            // AGC/MF checkpoint samples captured so far
 	FrameRec *d_frames = nullptr; int *d_nframes = nullptr; PduRec *d_pdus = nullptr; int max_frames = 0;
 	cf *d_cap_agc = nullptr, *d_cap_mf = nullptr, *d_cap_eq = nullptr; int *d_cap_cnt = nullptr;
 	cf *d_tmp = nullptr; long long tmp_len = 0;
@@ -207,16 +209,37 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 		HFDL_LAUNCH(bb_carry, dim3((unsigned)fe->C), dim3(32), 0, st, fe->d_bb, fe->bb_stride, n_in);
 		fe->launches++;
 	}
-	{
-		DemodArgs a;
-		a.rs = fe->d_rs; a.rs_stride = fe->rs_stride; a.n_samples = n_out;
-		a.state = fe->d_state; a.tab = fe->d_tab; a.datasym = fe->d_datasym;
-		a.frames = fe->d_frames; a.nframes = fe->d_nframes; a.max_frames = fe->max_frames; a.C = fe->C;
-		a.cap_channel = fe->cfg.capture_channel; a.cap_agc = fe->d_cap_agc; a.cap_mf = fe->d_cap_mf; a.cap_eq = fe->d_cap_eq;
-		a.cap_cnt = fe->d_cap_cnt; a.cap_max = fe->cfg.capture_max;
-		prof_begin(fe, KC_DEMOD, pr);
-		HFDL_LAUNCH(demod_kernel, dim3((unsigned)((fe->C + 31) / 32)), dim3(32), 0, st, a);
+	if(n_out > 0) {
+		AgcArgs a;
+		a.rs = fe->d_rs; a.rs_stride = fe->rs_stride; a.n_samples = n_out; a.state = fe->d_agc_state;
+		a.agc_out = fe->d_agc; a.agc_stride = fe->agc_stride; a.lvl = fe->d_lvl; a.lvl_stride = fe->rs_stride;
+		prof_begin(fe, KC_AGC, pr);
+		HFDL_LAUNCH(agc_kernel, dim3((unsigned)fe->C), dim3(32), 0, st, a);
 		prof_end(fe, pr);
+		BankArgs b;
+		b.agc_out = fe->d_agc; b.agc_stride = fe->agc_stride; b.n_samples = n_out; b.mfo = fe->d_mfo; b.mfo_stride = fe->mfo_stride;
+		b.bank = fe->d_bank; b.bank_stride = fe->rs_stride; b.tab = fe->d_tab;
+		prof_begin(fe, KC_BANK, pr);
+		HFDL_LAUNCH(bank_kernel, dim3((unsigned)((n_out + HFDL_BANK_TILE - 1) / HFDL_BANK_TILE), (unsigned)fe->C), dim3(256), 0, st, b);
+		prof_end(fe, pr);
+		LoopArgs l;
+		l.bank = fe->d_bank; l.bank_stride = fe->rs_stride; l.mfo = fe->d_mfo; l.mfo_stride = fe->mfo_stride;
+		l.lvl = fe->d_lvl; l.lvl_stride = fe->rs_stride; l.n_samples = n_out;
+		l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym;
+		l.frames = fe->d_frames; l.nframes = fe->d_nframes; l.max_frames = fe->max_frames;
+		l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
+		prof_begin(fe, KC_LOOP, pr);
+		HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(32), 0, st, l);
+		prof_end(fe, pr);
+		fe->launches += 3;
+		if(fe->cfg.capture_channel >= 0 && fe->cap_n < fe->cfg.capture_max) {       // f_agc_out / f_mf_out checkpoints
+			long long n = std::min<long long>(n_out, fe->cfg.capture_max - fe->cap_n);
+			int cc = fe->cfg.capture_channel;
+			CK(cudaMemcpyAsync(fe->d_cap_agc + fe->cap_n, fe->d_agc + (long long)cc * fe->agc_stride + HFDL_AGC_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(fe->d_cap_mf + fe->cap_n, fe->d_mfo + (long long)cc * fe->mfo_stride + HFDL_MFO_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+		}
+		if(fe->cfg.capture_channel >= 0) fe->cap_n += n_out;
+		HFDL_LAUNCH(demod_carry, dim3((unsigned)fe->C), dim3(64), 0, st, fe->d_agc, fe->agc_stride, fe->d_mfo, fe->mfo_stride, (long long)n_out);
 		fe->launches++;
 	}
 	{
@@ -368,6 +391,17 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 		for(int i = 0; i < C; i++) hfdl_design::demod_state_init(st[(size_t)i], *T);
 		CKD(cudaMalloc((void **)&fe->d_state, sizeof(DemodState) * (size_t)C));
 		CKD(cudaMemcpy(fe->d_state, st.data(), sizeof(DemodState) * (size_t)C, cudaMemcpyHostToDevice));
+		std::vector<AgcState> ag((size_t)C);
+		for(int i = 0; i < C; i++) { ag[(size_t)i].g = 1.0f; ag[(size_t)i].y2 = 1.0f; }      // agc_crcf_create / reset
+		CKD(cudaMalloc((void **)&fe->d_agc_state, sizeof(AgcState) * (size_t)C));
+		CKD(cudaMemcpy(fe->d_agc_state, ag.data(), sizeof(AgcState) * (size_t)C, cudaMemcpyHostToDevice));
+		fe->agc_stride = HFDL_AGC_HIST + fe->rs_stride; fe->mfo_stride = HFDL_MFO_HIST + fe->rs_stride;
+		CKD(cudaMalloc((void **)&fe->d_agc, sizeof(cf) * (size_t)C * fe->agc_stride));
+		CKD(cudaMemset(fe->d_agc, 0, sizeof(cf) * (size_t)C * fe->agc_stride));
+		CKD(cudaMalloc((void **)&fe->d_mfo, sizeof(cf) * (size_t)C * fe->mfo_stride));
+		CKD(cudaMemset(fe->d_mfo, 0, sizeof(cf) * (size_t)C * fe->mfo_stride));
+		CKD(cudaMalloc((void **)&fe->d_lvl, sizeof(float) * (size_t)C * fe->rs_stride));
+		CKD(cudaMalloc((void **)&fe->d_bank, sizeof(cf) * (size_t)C * fe->rs_stride * 32));
 		delete T;
 	}
 	CKD(cudaMalloc((void **)&fe->d_datasym, sizeof(cf) * (size_t)C * HFDL_FRAME_SLOTS * HFDL_DATA_SYMS_MAX));
@@ -403,6 +437,7 @@ void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	cudaFree(fe->d_bb); cudaFree(fe->d_rs); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
 	cudaFree(fe->d_frames); cudaFree(fe->d_nframes); cudaFree(fe->d_pdus); cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf);
 	cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp);
+	cudaFree(fe->d_agc_state); cudaFree(fe->d_agc); cudaFree(fe->d_mfo); cudaFree(fe->d_lvl); cudaFree(fe->d_bank);
 	if(fe->h_pdus) cudaFreeHost(fe->h_pdus);
 	if(fe->h_nframes) cudaFreeHost(fe->h_nframes);
 	for(auto &r : fe->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
@@ -604,7 +639,7 @@ int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_
 		if(fe->cfg.capture_channel < 0) return -1;
 		int cnt[2];
 		CK(cudaMemcpy(cnt, fe->d_cap_cnt, sizeof(cnt), cudaMemcpyDeviceToHost));
-		avail = std::min<long long>(what == HFDL_B200_CP_EQ ? cnt[1] : cnt[0], fe->cfg.capture_max);
+		avail = std::min<long long>(what == HFDL_B200_CP_EQ ? cnt[1] : fe->cap_n, fe->cfg.capture_max);
 		srcp = what == HFDL_B200_CP_AGC ? fe->d_cap_agc : (what == HFDL_B200_CP_MF ? fe->d_cap_mf : fe->d_cap_eq);
 		break; }
 	case HFDL_B200_CP_TAPSLICE:
