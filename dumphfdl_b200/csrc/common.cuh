@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <string.h>
 #ifdef HFDL_CUSIM
 #include "cusim.h"     // tests/cusim: host emulation for logic tests only (never part of the product build)
 #define HFDL_LAUNCH(kernel, grid, block, smem, stream, ...) cusim::launch(grid, block, smem, [&] { kernel(__VA_ARGS__); })
@@ -18,11 +19,43 @@
 
 typedef float2 cf;
 
+// fast transcendental wrappers: MUFU-based intrinsics on the device, libm under host emulation
+#ifdef HFDL_CUSIM
+static inline float hfdl_log2_fast(float x) { return log2f(x); }
+static inline float hfdl_exp2_fast(float x) { return exp2f(x); }
+static inline int hfdl_round_pos(float x) { return (int)floorf(x + 0.5f); }
+static inline void hfdl_sincos_fast(float x, float *s, float *c) { sincosf(x, s, c); }
+#else
+__device__ __forceinline__ float hfdl_log2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float hfdl_exp2_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ int hfdl_round_pos(float x) { return __float2int_rd(x + 0.5f); }      // == roundf for 0 <= x < 2^22
+__device__ __forceinline__ void hfdl_sincos_fast(float x, float *s, float *c) { __sincosf(x, s, c); }
+#endif
+
 __host__ __device__ __forceinline__ cf cmul(cf a, cf b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __host__ __device__ __forceinline__ cf cmulc(cf a, cf b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a*conj(b)
 __host__ __device__ __forceinline__ cf cadd(cf a, cf b) { return make_float2(a.x + b.x, a.y + b.y); }
 __host__ __device__ __forceinline__ cf csub(cf a, cf b) { return make_float2(a.x - b.x, a.y - b.y); }
 __host__ __device__ __forceinline__ cf cscale(cf a, float s) { return make_float2(a.x * s, a.y * s); }
+
+// cp.async (LDGSTS) global->shared prefetch; immediate copies under host emulation
+#ifdef HFDL_CUSIM
+static inline void hfdl_cp_async8(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 8); }
+static inline void hfdl_cp_async4(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 4); }
+static inline void hfdl_cp_async_commit() {}
+template <int N> static inline void hfdl_cp_async_wait() {}
+#else
+__device__ __forceinline__ void hfdl_cp_async8(void *sdst, const void *gsrc) {
+	unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void hfdl_cp_async4(void *sdst, const void *gsrc) {
+	unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void hfdl_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void hfdl_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 // sample formats (src/input-common.h sample_format)
 enum { HFDL_SFMT_CU8 = 1, HFDL_SFMT_CS16 = 2, HFDL_SFMT_CF32 = 3 };

@@ -34,7 +34,7 @@
 #define HFDL_AGC_HIST (HFDL_MF_TAPS - 1 + HFDL_SS_SUB - 1)   // AGC-output samples kept in front of a batch (35)
 #define HFDL_MFO_HIST (HFDL_SS_SUB - 1)                     // matched-filter outputs kept in front of a batch (17)
 #define HFDL_BANK_TILE 64
-#define HFDL_PF 8                           // bank rows prefetched ahead by loop_kernel
+#define HFDL_LOOP_CH 32                     // samples per shared-memory prefetch chunk of loop_kernel
 
 enum { HS_EMIT_BITS = 1, HS_EMIT_SYMBOLS = 2, HS_SKIP = 3 };
 enum { HF_A1 = 1, HF_A2, HF_M1, HF_M2_SKIP, HF_EQ_TRAIN, HF_DATA_1, HF_DATA_2 };
@@ -105,33 +105,55 @@ struct AgcArgs {
 	float *lvl; long long lvl_stride;        // [C][n]  1/g after the update (agc_crcf_get_signal_level)
 };
 
+#define HFDL_AGC_CH 64
 __global__ void __launch_bounds__(32) agc_kernel(AgcArgs a) {
-	const int c = blockIdx.x;
-	if(threadIdx.x != 0) return;
+	__shared__ cf s_in[2][HFDL_AGC_CH];
+	__shared__ cf s_out[HFDL_AGC_CH];
+	__shared__ float s_lvl[HFDL_AGC_CH];
+	const int c = blockIdx.x, lane = threadIdx.x;
 	const cf *x = a.rs + (long long)c * a.rs_stride;
 	cf *out = a.agc_out + (long long)c * a.agc_stride + HFDL_AGC_HIST;
 	float *lvl = a.lvl + (long long)c * a.lvl_stride;
 	float g = a.state[c].g, y2 = a.state[c].y2;
 	const float alpha = 0.01f;
-	for(int k0 = 0; k0 < a.n_samples; k0 += 8) {
-		cf xv[8];
-#pragma unroll
-		for(int u = 0; u < 8; u++) xv[u] = (k0 + u < a.n_samples) ? x[k0 + u] : make_float2(0.f, 0.f);
-#pragma unroll
-		for(int u = 0; u < 8; u++) {
-			if(k0 + u < a.n_samples) {
-				cf r = make_float2(xv[u].x * g, xv[u].y * g);
+	const int N = a.n_samples;
+	const int nchunks = (N + HFDL_AGC_CH - 1) / HFDL_AGC_CH;
+	for(int pre = 0; pre < 2; pre++) {
+		for(int i = lane; i < HFDL_AGC_CH; i += 32) { int n = pre * HFDL_AGC_CH + i; if(n < N) hfdl_cp_async8(&s_in[pre][i], &x[n]); }
+		hfdl_cp_async_commit();
+	}
+	for(int j = 0; j < nchunks; j++) {
+		hfdl_cp_async_wait<1>();
+		__syncwarp();
+		const int n0 = j * HFDL_AGC_CH;
+		const int cnt = (N - n0 < HFDL_AGC_CH) ? (N - n0) : HFDL_AGC_CH;
+		if(lane == 0) {
+			const cf *in = s_in[j & 1];
+#pragma unroll 4
+			for(int i = 0; i < cnt; i++) {
+				cf xv = in[i];
+				cf r = make_float2(xv.x * g, xv.y * g);
 				float p = r.x * r.x + r.y * r.y;
 				// (1.0 - alpha)*y2 + alpha*p with the product term kept exact: y2 - alpha*y2
 				y2 = fmaf(alpha, p, fmaf(-alpha, y2, y2));
-				if(y2 > 1e-6f) g *= expf(-0.5f * alpha * logf(y2));
-				g = fminf(g, 1e6f);
-				out[k0 + u] = r;
-				lvl[k0 + u] = 1.0f / g;
+				// g *= exp(-0.5*alpha*ln(y2)) == 2^(-0.5*alpha*log2(y2)): MUFU.LG2 + MUFU.EX2 on the critical chain
+				const float e = hfdl_exp2_fast(-0.5f * alpha * hfdl_log2_fast(y2));
+				g = fminf((y2 > 1e-6f) ? g * e : g, 1e6f);
+				s_out[i] = r;
+				s_lvl[i] = __fdividef(1.0f, g);
 			}
 		}
+		__syncwarp();
+		for(int i = lane; i < cnt; i += 32) { out[n0 + i] = s_out[i]; lvl[n0 + i] = s_lvl[i]; }
+		__syncwarp();
+		{
+			const int nn0 = (j + 2) * HFDL_AGC_CH;
+			for(int i = lane; i < HFDL_AGC_CH; i += 32) { int n = nn0 + i; if(n < N) hfdl_cp_async8(&s_in[j & 1][i], &x[n]); }
+			hfdl_cp_async_commit();
+		}
 	}
-	a.state[c].g = g; a.state[c].y2 = y2;
+	hfdl_cp_async_wait<0>();
+	if(lane == 0) { a.state[c].g = g; a.state[c].y2 = y2; }
 }
 
 // ======================================================================================
@@ -230,15 +252,22 @@ __device__ __forceinline__ void ss_reset(DemodState &S) {     // symsync_crcf_re
 	S.ss_b = 0; S.ss_bf = 0.f; S.ss_tau = 0.f; S.ss_q = 0.f; S.ss_q_hat = 0.f; S.ss_decim_counter = 0;
 	S.ss_v[0] = S.ss_v[1] = S.ss_v[2] = 0.f;
 }
-__device__ __forceinline__ void eq_reset(DemodState &S, const DemodTables &T) {
+// equaliser window / |x|^2 delay line live in a 16-slot shared-memory ring while the kernel runs (ep = oldest slot).
+// Every lane owns a private column (slot*32 + lane): lanes run the same state machine but need not stay in lockstep.
+struct EqRing { cf *win; float *x2; int ep; };
+#define EQS(i) ((i) * 32)
+__device__ __forceinline__ void eq_reset(DemodState &S, const DemodTables &T, EqRing &E) {
 #pragma unroll
-	for(int i = 0; i < HFDL_EQ_LEN; i++) { S.eq_w[i] = T.eq_h0[i]; S.eq_win[i] = make_float2(0.f, 0.f); S.eq_x2[i] = 0.f; }
+	for(int i = 0; i < HFDL_EQ_LEN; i++) S.eq_w[i] = T.eq_h0[i];
+#pragma unroll
+	for(int i = 0; i < 16; i++) { E.win[EQS(i)] = make_float2(0.f, 0.f); E.x2[EQS(i)] = 0.f; }
+	E.ep = 0;
 	S.eq_count = 0; S.eq_buf_full = 0; S.eq_x2_sum = 0.f;
 }
-__device__ __forceinline__ void framer_reset(DemodState &S, const DemodTables &T) {   // hfdl.c:968-991
+__device__ __forceinline__ void framer_reset(DemodState &S, const DemodTables &T, EqRing &E) {   // hfdl.c:968-991
 	S.fr_state = HF_A1; S.symbols_wanted = 1; S.search_retries = 0; S.cur_arity = 1;
 	S.train_bits_total = S.train_bits_bad = 0; S.T_idx = 0; S.cur_buf = 0;
-	eq_reset(S, T);
+	eq_reset(S, T, E);
 	S.data_n = 0; S.training_n = 0;
 	ss_reset(S);
 	S.s_state = HS_EMIT_BITS; S.bitmask = 0;
@@ -251,20 +280,18 @@ __device__ __forceinline__ unsigned modem_demod(int m, cf x, const DemodTables &
 		sym = (x.x > 0.f) ? 0u : 1u;
 		*x_hat = make_float2(sym ? -1.0f : 1.0f, 0.f);
 	} else {
-		const int M = 1 << m;
-		const float alpha = (float)(M_PI / (float)M);
-		const float d_phi = (float)(M_PI * (1.0f - 1.0f / (float)M));
-		float theta = atan2f(x.y, x.x);
-		theta -= d_phi;
-		if(theta < -(float)M_PI) theta += (float)(2 * M_PI);
-		unsigned s = 0;
-		float v = theta;
-		for(int i = 0; i < m; i++) {
-			float ref = (float)(1 << (m - i - 1)) * alpha;
-			s <<= 1;
-			if(v > 0.f) { s |= 1u; v -= ref; } else { v += ref; }
+		// nearest constellation angle k*2pi/M: the same decision regions as liquid's atan2 + linear search
+		unsigned k;
+		const float ax = fabsf(x.x), ay = fabsf(x.y);
+		if(m == 2) {
+			k = (ax >= ay) ? (x.x > 0.f ? 0u : 2u) : (x.y > 0.f ? 1u : 3u);
+		} else {
+			const float t8 = 0.41421356237f;                 // tan(pi/8)
+			if(ay < t8 * ax) k = x.x > 0.f ? 0u : 4u;
+			else if(ax < t8 * ay) k = x.y > 0.f ? 2u : 6u;
+			else k = x.x > 0.f ? (x.y > 0.f ? 1u : 7u) : (x.y > 0.f ? 3u : 5u);
 		}
-		sym = s ^ (s >> 1);
+		sym = k ^ (k >> 1);
 		*x_hat = T.psk[m][sym];
 	}
 	return sym;
@@ -283,41 +310,63 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 	cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
 	const float ss_a1 = T.ss_a1, ss_a2 = T.ss_a2, ss_b0 = T.ss_b0, ss_radj = T.ss_rate_adj;
 
-	cf ring[HFDL_PF];
+	unsigned A_bits[4];
 #pragma unroll
-	for(int u = 0; u < HFDL_PF; u++) ring[u] = (u < a.n_samples) ? bank[(long long)u * 32 + lane] : make_float2(0.f, 0.f);
+	for(int i = 0; i < 4; i++) A_bits[i] = T.A_bits[i];
+	// bank rows (lane = arm) and AGC levels are staged through shared memory two chunks ahead with cp.async,
+	// so the arm the timing loop selects is a shared-memory read, never a dependent global load
+	__shared__ cf s_bank[2][HFDL_LOOP_CH][32];
+	__shared__ float s_lvl[2][HFDL_LOOP_CH];
+	__shared__ cf s_eqwin[16 * 32];
+	__shared__ float s_eqx2[16 * 32];
+	__shared__ cf s_train_all[16 * 32];
+	EqRing E;
+	E.win = s_eqwin + lane; E.x2 = s_eqx2 + lane; E.ep = 0;
+	cf *s_train = s_train_all + lane;
+	for(int j = 0; j < 16; j++) {
+		E.win[EQS(j)] = j < HFDL_EQ_LEN ? a.state[c].eq_win[j] : make_float2(0.f, 0.f);
+		E.x2[EQS(j)] = j < HFDL_EQ_LEN ? a.state[c].eq_x2[j] : 0.f;
+		s_train[EQS(j)] = j < HFDL_T_LEN ? a.state[c].training[j] : make_float2(0.f, 0.f);
+	}
+	const int N = a.n_samples;
+	const int nchunks = (N + HFDL_LOOP_CH - 1) / HFDL_LOOP_CH;
+	for(int pre = 0; pre < 2; pre++) {
+		for(int i = 0; i < HFDL_LOOP_CH; i++) { int n = pre * HFDL_LOOP_CH + i; if(n < N) hfdl_cp_async8(&s_bank[pre][i][lane], &bank[(long long)n * 32 + lane]); }
+		{ int n = pre * HFDL_LOOP_CH + lane; if(lane < HFDL_LOOP_CH && n < N) hfdl_cp_async4(&s_lvl[pre][lane], &lvl[n]); }
+		hfdl_cp_async_commit();
+	}
 
-	for(int k0 = 0; k0 < a.n_samples; k0 += HFDL_PF) {
-#pragma unroll
-		for(int u = 0; u < HFDL_PF; u++) {
-			const int k = k0 + u;
-			if(k < a.n_samples) {
-				const cf row = ring[u];
-				ring[u] = (k + HFDL_PF < a.n_samples) ? bank[(long long)(k + HFDL_PF) * 32 + lane] : make_float2(0.f, 0.f);
-				const float level = lvl[k];                      // 1/g after this sample's AGC update
+	for(int jc = 0; jc < nchunks; jc++) {
+		hfdl_cp_async_wait<1>();
+		__syncwarp();
+		const int cnt = (N - jc * HFDL_LOOP_CH < HFDL_LOOP_CH) ? (N - jc * HFDL_LOOP_CH) : HFDL_LOOP_CH;
+		for(int ii = 0; ii < cnt; ii++) {
+			{
+				const int k = jc * HFDL_LOOP_CH + ii;
+				const cf *row = s_bank[jc & 1][ii];
+				const float level = s_lvl[jc & 1][ii];           // 1/g after this sample's AGC update
 				// ---- noise floor (hfdl.c:700-706)
 				if(S.fr_state == HF_A1 && (++S.nf_clk & 0xFFu) == 0xFFu)
 					S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, level) + 1e-6f;
 				// ---- symsync_crcf_step (push happened in bank_kernel; the reset only clears the mf-arm window)
 				if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
-				cf symbols[4];
+				cf sym0 = make_float2(0.f, 0.f), sym1 = sym0;     // symsync outputs of this input sample (at most 2: del ~ 1.5)
 				int produced = 0;
 				while(S.ss_b < HFDL_SS_NPFB) {
-					cf mf;
-					mf.x = __shfl_sync(0xffffffffu, row.x, S.ss_b);
-					mf.y = __shfl_sync(0xffffffffu, row.y, S.ss_b);
+					cf mf = row[S.ss_b];
 					if(S.ss_since_reset < HFDL_SS_SUB) {
 						// window still filling after a reset: only the samples pushed since then contribute
 						mf = make_float2(0.f, 0.f);
 						const float *h = T.ss_mf[S.ss_b];
 						for(int j = (int)S.ss_since_reset - 1; j >= 0; j--) { cf v = mfo[k - j]; mf.x += h[j] * v.x; mf.y += h[j] * v.y; }
 					}
-					if(produced < 4) symbols[produced] = make_float2(mf.x / 3.0f, mf.y / 3.0f);
+					{   // output scaled by 1/k (k = 3 samples per symbol)
+						cf o = make_float2(mf.x * 0.33333334f, mf.y * 0.33333334f);
+						if(produced == 0) sym0 = o; else if(produced == 1) sym1 = o;
+					}
 					if(S.ss_decim_counter == 2u) {
 						S.ss_decim_counter = 0;
-						cf dmf;
-						dmf.x = __shfl_sync(0xffffffffu, row.x, 16 + S.ss_b);
-						dmf.y = __shfl_sync(0xffffffffu, row.y, 16 + S.ss_b);
+						cf dmf = row[16 + S.ss_b];
 						float q = mf.x * dmf.x + mf.y * dmf.y;           // Re(conj(mf)*dmf)
 						q = fminf(fmaxf(q, -1.0f), 1.0f);
 						S.ss_q = q;
@@ -330,42 +379,46 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 					S.ss_decim_counter++;
 					S.ss_tau += S.ss_del;
 					S.ss_bf = S.ss_tau * (float)HFDL_SS_NPFB;
-					S.ss_b = (int)roundf(S.ss_bf);
+					S.ss_b = hfdl_round_pos(S.ss_bf);                 // bf > 0 here, == (int)roundf(bf)
 					produced++;
 				}
 				S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
-				if(produced > 4) produced = 4;
+				if(produced > 2) produced = 2;
 
 				for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
 					// ---- Costas step + rotate (hfdl.c:250-294,709-715)
 					S.c_phi += S.c_dphi;
-					if((double)S.c_phi > M_PI) S.c_phi = (float)((double)S.c_phi - 2.0 * M_PI);
-					else if((double)S.c_phi < -M_PI) S.c_phi = (float)((double)S.c_phi + 2.0 * M_PI);
+					// (double)phi > M_PI  <=>  phi > 3.1415925f (largest float below pi); 2*pi split hi+lo
+					if(S.c_phi > 3.1415925f) S.c_phi = (S.c_phi - 6.2831855f) + 1.7484555e-7f;
+					else if(S.c_phi < -3.1415925f) S.c_phi = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
 					float sn, cs;
-					sincosf(S.c_phi, &sn, &cs);
-					cf r = make_float2(symbols[i].x * cs + symbols[i].y * sn, symbols[i].y * cs - symbols[i].x * sn);
+					hfdl_sincos_fast(S.c_phi, &sn, &cs);
+					const cf so = (i == 0) ? sym0 : sym1;
+					cf r = make_float2(so.x * cs + so.y * sn, so.y * cs - so.x * sn);
 					if(fabsf(S.c_dphi) > 0.25f && S.fr_state == HF_A1) {
 						S.c_phi = S.c_dphi = 0.f;
 						ss_reset(S);
 					}
-					// ---- eqlms_cccf_push
-#pragma unroll
-					for(int j = 0; j < HFDL_EQ_LEN - 1; j++) { S.eq_win[j] = S.eq_win[j + 1]; }
-					S.eq_win[HFDL_EQ_LEN - 1] = r;
+					// ---- eqlms_cccf_push (ring: oldest at ep, new element goes to ep+15, then ep advances)
 					{
-						float x2n = r.x * r.x + r.y * r.y, x20 = S.eq_x2[0];
-#pragma unroll
-						for(int j = 0; j < HFDL_EQ_LEN - 1; j++) S.eq_x2[j] = S.eq_x2[j + 1];
-						S.eq_x2[HFDL_EQ_LEN - 1] = x2n;
+						const int wp = (E.ep + 15) & 15;
+						float x2n = r.x * r.x + r.y * r.y, x20 = E.x2[EQS(E.ep)];
+						E.win[EQS(wp)] = r;
+						E.x2[EQS(wp)] = x2n;
+						E.ep = (E.ep + 1) & 15;
 						S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
 						S.eq_count++;
 					}
 					if(!(S.symsync_out_idx & 1u)) continue;
 					// ---- eqlms_cccf_execute: y = sum conj(w[i]) * x[i]
 					cf s = make_float2(0.f, 0.f);
+					cf wv[HFDL_EQ_LEN];
+#pragma unroll
+					for(int j = 0; j < HFDL_EQ_LEN - 1; j++) wv[j] = E.win[EQS((E.ep + j) & 15)];
+					wv[HFDL_EQ_LEN - 1] = r;
 #pragma unroll
 					for(int j = 0; j < HFDL_EQ_LEN; j++) {
-						cf w = S.eq_w[j], v = S.eq_win[j];
+						cf w = S.eq_w[j], v = wv[j];
 						s.x += w.x * v.x + w.y * v.y;
 						s.y += w.x * v.y - w.y * v.x;
 					}
@@ -375,12 +428,13 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 						bool run = true;
 						if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
 						if(run) {
-							cf t = make_float2(0.1f * (d - s.x), 0.1f * s.y);      // mu * conj(d - d_hat), mu = 0.1 (hfdl.c:496)
+							const float inv = 1.0f / S.eq_x2_sum;
+							cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);      // mu * conj(d - d_hat) / sum|x|^2, mu = 0.1 (hfdl.c:496)
 #pragma unroll
 							for(int j = 0; j < HFDL_EQ_LEN; j++) {
-								cf uu = cmul(t, S.eq_win[j]);
-								S.eq_w[j].x += uu.x / S.eq_x2_sum;
-								S.eq_w[j].y += uu.y / S.eq_x2_sum;
+								cf uu = cmul(t, wv[j]);
+								S.eq_w[j].x += uu.x;
+								S.eq_w[j].y += uu.y;
 							}
 						}
 						S.T_idx++;
@@ -406,11 +460,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 						for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
 					} else if(S.s_state == HS_EMIT_SYMBOLS) {
 						if(S.cur_buf == 0) {
-							if(S.training_n < HFDL_T_LEN) {
-#pragma unroll
-								for(int j = 0; j < HFDL_T_LEN; j++) if(j == S.training_n) S.training[j] = s;
-								S.training_n++;
-							}
+							if(S.training_n < HFDL_T_LEN) { s_train[EQS(S.training_n)] = s; S.training_n++; }
 						} else {
 							if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
 						}
@@ -423,7 +473,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 
 					switch(S.fr_state) {
 					case HF_A1: {
-						float corr = 2.0f * (float)bits_corr(T.A_bits, S.bits) / 127.0f - 1.0f;
+						float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
 						if(fabsf(corr) > 0.36f) {
 							S.st_a1++;
 							S.bitmask = corr > 0.f ? 0u : ~0u;
@@ -435,7 +485,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 						}
 						break; }
 					case HF_A2: {
-						float corr = 2.0f * (float)bits_corr(T.A_bits, S.bits) / 127.0f - 1.0f;
+						float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
 						if(fabsf(corr) > 0.3f) {
 							S.a2_sample_cnt = S.sample_cnt;
 							S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
@@ -444,7 +494,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 							S.search_retries = 0;
 							S.fr_state = HF_M1;
 						} else if(++S.search_retries >= 3) {
-							framer_reset(S, T);
+							framer_reset(S, T, E);
 						}
 						break; }
 					case HF_M1: {
@@ -463,7 +513,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 							S.fr_state = HF_M2_SKIP;
 							S.s_state = HS_SKIP;
 						} else {
-							framer_reset(S, T);
+							framer_reset(S, T, E);
 						}
 						break; }
 					case HF_M2_SKIP:
@@ -477,7 +527,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 						unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
 #pragma unroll
 						for(int j = 0; j < HFDL_T_LEN; j++) {
-							unsigned bit = (S.training[j].x > 0.f) ? 0u : 1u;
+							unsigned bit = (s_train[EQS(j)].x > 0.f) ? 0u : 1u;
 							bit ^= (S.bitmask & 1u);
 							tseq = (tseq << 1) | bit;
 						}
@@ -508,7 +558,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 							S.st_frames++;
 							S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
 							dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
-							framer_reset(S, T);
+							framer_reset(S, T, E);
 							S.symbol_cnt = 0;
 						}
 						break; }
@@ -530,8 +580,19 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 				S.sample_cnt++;
 			}
 		}
+		__syncwarp();
+		{
+			const int nn0 = (jc + 2) * HFDL_LOOP_CH;
+			for(int i = 0; i < HFDL_LOOP_CH; i++) { int n = nn0 + i; if(n < N) hfdl_cp_async8(&s_bank[jc & 1][i][lane], &bank[(long long)n * 32 + lane]); }
+			{ int n = nn0 + lane; if(lane < HFDL_LOOP_CH && n < N) hfdl_cp_async4(&s_lvl[jc & 1][lane], &lvl[n]); }
+			hfdl_cp_async_commit();
+		}
 	}
+	hfdl_cp_async_wait<0>();
+	__syncwarp();
 	if(lane == 0) {
+		for(int j = 0; j < HFDL_EQ_LEN; j++) { S.eq_win[j] = E.win[EQS((E.ep + j) & 15)]; S.eq_x2[j] = E.x2[EQS((E.ep + j) & 15)]; }
+		for(int j = 0; j < HFDL_T_LEN; j++) S.training[j] = s_train[EQS(j)];
 		a.state[c] = S;
 		if(cap) a.cap_cnt[1] = cap_n_eq;
 	}
