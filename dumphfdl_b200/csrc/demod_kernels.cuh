@@ -260,7 +260,7 @@ __device__ __forceinline__ void eq_reset(DemodState &S, const DemodTables &T, Eq
 #pragma unroll
 	for(int i = 0; i < HFDL_EQ_LEN; i++) S.eq_w[i] = T.eq_h0[i];
 #pragma unroll
-	for(int i = 0; i < 16; i++) { E.win[EQS(i)] = make_float2(0.f, 0.f); E.x2[EQS(i)] = 0.f; }
+	for(int i = 0; i < 16; i++) { E.win[EQS(i)] = make_float2(0.f, 0.f); E.win[EQS(i + 16)] = make_float2(0.f, 0.f); E.x2[EQS(i)] = 0.f; }
 	E.ep = 0;
 	S.eq_count = 0; S.eq_buf_full = 0; S.eq_x2_sum = 0.f;
 }
@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 	int cap_n_eq = cap ? a.cap_cnt[1] : 0;
 	cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
 	const float ss_a1 = T.ss_a1, ss_a2 = T.ss_a2, ss_b0 = T.ss_b0, ss_radj = T.ss_rate_adj;
+	const unsigned long long cnt_base = S.sample_cnt;
 
 	unsigned A_bits[4];
 #pragma unroll
@@ -317,281 +318,307 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 	// so the arm the timing loop selects is a shared-memory read, never a dependent global load
 	__shared__ cf s_bank[2][HFDL_LOOP_CH][32];
 	__shared__ float s_lvl[2][HFDL_LOOP_CH];
-	__shared__ cf s_eqwin[16 * 32];
+	__shared__ cf s_eqwin[32 * 32];
 	__shared__ float s_eqx2[16 * 32];
 	__shared__ cf s_train_all[16 * 32];
 	EqRing E;
 	E.win = s_eqwin + lane; E.x2 = s_eqx2 + lane; E.ep = 0;
 	cf *s_train = s_train_all + lane;
 	for(int j = 0; j < 16; j++) {
-		E.win[EQS(j)] = j < HFDL_EQ_LEN ? a.state[c].eq_win[j] : make_float2(0.f, 0.f);
+		cf v = j < HFDL_EQ_LEN ? a.state[c].eq_win[j] : make_float2(0.f, 0.f);
+		E.win[EQS(j)] = v; E.win[EQS(j + 16)] = v;
 		E.x2[EQS(j)] = j < HFDL_EQ_LEN ? a.state[c].eq_x2[j] : 0.f;
 		s_train[EQS(j)] = j < HFDL_T_LEN ? a.state[c].training[j] : make_float2(0.f, 0.f);
 	}
 	const int N = a.n_samples;
-	const int nchunks = (N + HFDL_LOOP_CH - 1) / HFDL_LOOP_CH;
 	for(int pre = 0; pre < 2; pre++) {
 		for(int i = 0; i < HFDL_LOOP_CH; i++) { int n = pre * HFDL_LOOP_CH + i; if(n < N) hfdl_cp_async8(&s_bank[pre][i][lane], &bank[(long long)n * 32 + lane]); }
 		{ int n = pre * HFDL_LOOP_CH + lane; if(lane < HFDL_LOOP_CH && n < N) hfdl_cp_async4(&s_lvl[pre][lane], &lvl[n]); }
 		hfdl_cp_async_commit();
 	}
-
-	for(int jc = 0; jc < nchunks; jc++) {
-		hfdl_cp_async_wait<1>();
-		__syncwarp();
-		const int cnt = (N - jc * HFDL_LOOP_CH < HFDL_LOOP_CH) ? (N - jc * HFDL_LOOP_CH) : HFDL_LOOP_CH;
-		for(int ii = 0; ii < cnt; ii++) {
-			{
-				const int k = jc * HFDL_LOOP_CH + ii;
-				const cf *row = s_bank[jc & 1][ii];
-				const float level = s_lvl[jc & 1][ii];           // 1/g after this sample's AGC update
-				// ---- noise floor (hfdl.c:700-706)
-				if(S.fr_state == HF_A1 && (++S.nf_clk & 0xFFu) == 0xFFu)
-					S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, level) + 1e-6f;
-				// ---- symsync_crcf_step (push happened in bank_kernel; the reset only clears the mf-arm window)
+	hfdl_cp_async_wait<1>();
+	__syncwarp();
+	int chunk = 0;                 // chunk currently readable in s_bank[chunk & 1]
+	int k = -1;                    // last input sample consumed
+	// The loop is driven by symsync OUTPUTS (2 per 3 input samples): input samples that produce no output only
+	// tick the noise-floor clock and step the timing phase (symsync_crcf_step: tau -= 1, b -= npfb).
+#define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1 && (++S.nf_clk & 0xFFu) == 0xFFu) \
+		S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } while(0)     /* hfdl.c:700-706 */
+	for(;;) {
+		const int skip = (S.ss_b >= HFDL_SS_NPFB) ? (S.ss_b >> 4) : 0;
+		const int kn = k + 1 + skip;
+		if(kn >= N) {              // the rest of the batch yields no output
+			for(int sidx = k + 1; sidx < N; sidx++) {
+				HFDL_NF_TICK(sidx);
 				if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
-				cf sym0 = make_float2(0.f, 0.f), sym1 = sym0;     // symsync outputs of this input sample (at most 2: del ~ 1.5)
-				int produced = 0;
-				while(S.ss_b < HFDL_SS_NPFB) {
-					cf mf = row[S.ss_b];
-					if(S.ss_since_reset < HFDL_SS_SUB) {
-						// window still filling after a reset: only the samples pushed since then contribute
-						mf = make_float2(0.f, 0.f);
-						const float *h = T.ss_mf[S.ss_b];
-						for(int j = (int)S.ss_since_reset - 1; j >= 0; j--) { cf v = mfo[k - j]; mf.x += h[j] * v.x; mf.y += h[j] * v.y; }
-					}
-					{   // output scaled by 1/k (k = 3 samples per symbol)
-						cf o = make_float2(mf.x * 0.33333334f, mf.y * 0.33333334f);
-						if(produced == 0) sym0 = o; else if(produced == 1) sym1 = o;
-					}
-					if(S.ss_decim_counter == 2u) {
-						S.ss_decim_counter = 0;
-						cf dmf = row[16 + S.ss_b];
-						float q = mf.x * dmf.x + mf.y * dmf.y;           // Re(conj(mf)*dmf)
-						q = fminf(fmaxf(q, -1.0f), 1.0f);
-						S.ss_q = q;
-						S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0];
-						S.ss_v[0] = q - ss_a1 * S.ss_v[1] - ss_a2 * S.ss_v[2];
-						S.ss_q_hat = ss_b0 * S.ss_v[0];
-						S.ss_rate += ss_radj * S.ss_q_hat;
-						S.ss_del = S.ss_rate + S.ss_q_hat;
-					}
-					S.ss_decim_counter++;
-					S.ss_tau += S.ss_del;
-					S.ss_bf = S.ss_tau * (float)HFDL_SS_NPFB;
-					S.ss_b = hfdl_round_pos(S.ss_bf);                 // bf > 0 here, == (int)roundf(bf)
-					produced++;
-				}
 				S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
-				if(produced > 2) produced = 2;
+			}
+			break;
+		}
+		for(int sidx = k + 1; sidx < kn; sidx++) {
+			HFDL_NF_TICK(sidx);
+			if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
+			S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
+		}
+		k = kn;
+		while(k >= (chunk + 1) * HFDL_LOOP_CH) {       // move to the next staged chunk, refill the one just left
+			__syncwarp();
+			const int nn0 = (chunk + 2) * HFDL_LOOP_CH;
+			for(int i = 0; i < HFDL_LOOP_CH; i++) { int n = nn0 + i; if(n < N) hfdl_cp_async8(&s_bank[chunk & 1][i][lane], &bank[(long long)n * 32 + lane]); }
+			{ int n = nn0 + lane; if(lane < HFDL_LOOP_CH && n < N) hfdl_cp_async4(&s_lvl[chunk & 1][lane], &lvl[n]); }
+			hfdl_cp_async_commit();
+			hfdl_cp_async_wait<1>();
+			__syncwarp();
+			chunk++;
+		}
+		const int ii = k - chunk * HFDL_LOOP_CH;
+		const cf *row = s_bank[chunk & 1][ii];
+		const float level = s_lvl[chunk & 1][ii];           // 1/g after this sample's AGC update
+		S.sample_cnt = cnt_base + (unsigned long long)k;
+		HFDL_NF_TICK(k);
+		// ---- symsync_crcf_step (push happened in bank_kernel; the reset only clears the mf-arm window)
+		if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
+		cf sym0 = make_float2(0.f, 0.f), sym1 = sym0;     // symsync outputs of this input sample (at most 2: del ~ 1.5)
+		int produced = 0;
+		while(S.ss_b < HFDL_SS_NPFB) {
+			cf mf = row[S.ss_b];
+			if(S.ss_since_reset < HFDL_SS_SUB) {
+				// window still filling after a reset: only the samples pushed since then contribute
+				mf = make_float2(0.f, 0.f);
+				const float *h = T.ss_mf[S.ss_b];
+				for(int j = (int)S.ss_since_reset - 1; j >= 0; j--) { cf v = mfo[k - j]; mf.x += h[j] * v.x; mf.y += h[j] * v.y; }
+			}
+			{   // output scaled by 1/k (k = 3 samples per symbol)
+				cf o = make_float2(mf.x * 0.33333334f, mf.y * 0.33333334f);
+				if(produced == 0) sym0 = o; else if(produced == 1) sym1 = o;
+			}
+			if(S.ss_decim_counter == 2u) {
+				S.ss_decim_counter = 0;
+				cf dmf = row[16 + S.ss_b];
+				float q = mf.x * dmf.x + mf.y * dmf.y;           // Re(conj(mf)*dmf)
+				q = fminf(fmaxf(q, -1.0f), 1.0f);
+				S.ss_q = q;
+				S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0];
+				S.ss_v[0] = q - ss_a1 * S.ss_v[1] - ss_a2 * S.ss_v[2];
+				S.ss_q_hat = ss_b0 * S.ss_v[0];
+				S.ss_rate += ss_radj * S.ss_q_hat;
+				S.ss_del = S.ss_rate + S.ss_q_hat;
+			}
+			S.ss_decim_counter++;
+			S.ss_tau += S.ss_del;
+			S.ss_bf = S.ss_tau * (float)HFDL_SS_NPFB;
+			S.ss_b = hfdl_round_pos(S.ss_bf);                 // bf > 0 here, == (int)roundf(bf)
+			produced++;
+		}
+		S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
+		if(produced > 2) produced = 2;
 
-				for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
-					// ---- Costas step + rotate (hfdl.c:250-294,709-715)
-					S.c_phi += S.c_dphi;
-					// (double)phi > M_PI  <=>  phi > 3.1415925f (largest float below pi); 2*pi split hi+lo
-					if(S.c_phi > 3.1415925f) S.c_phi = (S.c_phi - 6.2831855f) + 1.7484555e-7f;
-					else if(S.c_phi < -3.1415925f) S.c_phi = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
-					float sn, cs;
-					hfdl_sincos_fast(S.c_phi, &sn, &cs);
-					const cf so = (i == 0) ? sym0 : sym1;
-					cf r = make_float2(so.x * cs + so.y * sn, so.y * cs - so.x * sn);
-					if(fabsf(S.c_dphi) > 0.25f && S.fr_state == HF_A1) {
-						S.c_phi = S.c_dphi = 0.f;
-						ss_reset(S);
-					}
-					// ---- eqlms_cccf_push (ring: oldest at ep, new element goes to ep+15, then ep advances)
-					{
-						const int wp = (E.ep + 15) & 15;
-						float x2n = r.x * r.x + r.y * r.y, x20 = E.x2[EQS(E.ep)];
-						E.win[EQS(wp)] = r;
-						E.x2[EQS(wp)] = x2n;
-						E.ep = (E.ep + 1) & 15;
-						S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
-						S.eq_count++;
-					}
-					if(!(S.symsync_out_idx & 1u)) continue;
-					// ---- eqlms_cccf_execute: y = sum conj(w[i]) * x[i]
-					cf s = make_float2(0.f, 0.f);
-					cf wv[HFDL_EQ_LEN];
+		for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
+			// ---- Costas step + rotate (hfdl.c:250-294,709-715)
+			S.c_phi += S.c_dphi;
+			// (double)phi > M_PI  <=>  phi > 3.1415925f (largest float below pi); 2*pi split hi+lo
+			if(S.c_phi > 3.1415925f) S.c_phi = (S.c_phi - 6.2831855f) + 1.7484555e-7f;
+			else if(S.c_phi < -3.1415925f) S.c_phi = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
+			float sn, cs;
+			hfdl_sincos_fast(S.c_phi, &sn, &cs);
+			const cf so = (i == 0) ? sym0 : sym1;
+			cf r = make_float2(so.x * cs + so.y * sn, so.y * cs - so.x * sn);
+			if(fabsf(S.c_dphi) > 0.25f && S.fr_state == HF_A1) {
+				S.c_phi = S.c_dphi = 0.f;
+				ss_reset(S);
+			}
+			// ---- eqlms_cccf_push (mirrored ring: slot w and w+16 hold the same element, so the 15-element
+			//      window is always the contiguous run [ep, ep+14])
+			{
+				const int wp = (E.ep + 15) & 15;
+				float x2n = r.x * r.x + r.y * r.y, x20 = E.x2[EQS(E.ep)];
+				E.win[EQS(wp)] = r;
+				E.win[EQS(wp + 16)] = r;
+				E.x2[EQS(wp)] = x2n;
+				E.ep = (E.ep + 1) & 15;
+				S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
+				S.eq_count++;
+			}
+			if(!(S.symsync_out_idx & 1u)) continue;
+			// ---- eqlms_cccf_execute: y = sum conj(w[i]) * x[i]
+			cf s = make_float2(0.f, 0.f);
+			cf wv[HFDL_EQ_LEN];
+			{
+				const cf *wb = E.win + EQS(E.ep);
 #pragma unroll
-					for(int j = 0; j < HFDL_EQ_LEN - 1; j++) wv[j] = E.win[EQS((E.ep + j) & 15)];
-					wv[HFDL_EQ_LEN - 1] = r;
+				for(int j = 0; j < HFDL_EQ_LEN - 1; j++) wv[j] = wb[EQS(j)];
+				wv[HFDL_EQ_LEN - 1] = r;
+				cf s2 = make_float2(0.f, 0.f);          // two accumulator pairs shorten the dependent FMA chain
+#pragma unroll
+				for(int j = 0; j < HFDL_EQ_LEN; j++) {
+					cf w = S.eq_w[j], v = wv[j];
+					if(j & 1) { s2.x = fmaf(w.x, v.x, fmaf(w.y, v.y, s2.x)); s2.y = fmaf(w.x, v.y, fmaf(-w.y, v.x, s2.y)); }
+					else { s.x = fmaf(w.x, v.x, fmaf(w.y, v.y, s.x)); s.y = fmaf(w.x, v.y, fmaf(-w.y, v.x, s.y)); }
+				}
+				s.x += s2.x; s.y += s2.y;
+			}
+			if(S.fr_state == HF_EQ_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
+				float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
+				if(S.bitmask & 1u) d = -d;
+				bool run = true;
+				if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
+				if(run) {
+					const float inv = 1.0f / S.eq_x2_sum;
+					cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);      // mu * conj(d - d_hat) / sum|x|^2, mu = 0.1 (hfdl.c:496)
 #pragma unroll
 					for(int j = 0; j < HFDL_EQ_LEN; j++) {
-						cf w = S.eq_w[j], v = wv[j];
-						s.x += w.x * v.x + w.y * v.y;
-						s.y += w.x * v.y - w.y * v.x;
-					}
-					if(S.fr_state == HF_EQ_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
-						float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
-						if(S.bitmask & 1u) d = -d;
-						bool run = true;
-						if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
-						if(run) {
-							const float inv = 1.0f / S.eq_x2_sum;
-							cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);      // mu * conj(d - d_hat) / sum|x|^2, mu = 0.1 (hfdl.c:496)
-#pragma unroll
-							for(int j = 0; j < HFDL_EQ_LEN; j++) {
-								cf uu = cmul(t, wv[j]);
-								S.eq_w[j].x += uu.x;
-								S.eq_w[j].y += uu.y;
-							}
-						}
-						S.T_idx++;
-					}
-					if(cap && lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s;
-					if(cap) cap_n_eq++;
-					cf x_hat;
-					unsigned bits = modem_demod(S.cur_arity, s, T, &x_hat);
-					// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
-					float err = s.y * x_hat.x - s.x * x_hat.y;
-					err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
-					S.c_phi += 0.1f * err;
-					S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
-
-					S.symbol_cnt++;
-					if(S.symbol_cnt >= 13ull * HFDL_SINGLE_SLOT_FRAME_LEN && S.fr_state == HF_A1) {
-						S.symbol_cnt = 0;
-						S.c_phi = S.c_dphi = 0.f;
-						ss_reset(S);
-					}
-					if(S.s_state == HS_EMIT_BITS) {
-						bits ^= S.bitmask;
-						for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
-					} else if(S.s_state == HS_EMIT_SYMBOLS) {
-						if(S.cur_buf == 0) {
-							if(S.training_n < HFDL_T_LEN) { s_train[EQS(S.training_n)] = s; S.training_n++; }
-						} else {
-							if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
-						}
-					}
-					if(S.fr_state > HF_A1) {
-						S.signal_level = (S.signal_level * S.frame_symbol_cnt + level) / (S.frame_symbol_cnt + 1.0f);
-						S.frame_symbol_cnt += 1.0f;
-					}
-					if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }
-
-					switch(S.fr_state) {
-					case HF_A1: {
-						float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
-						if(fabsf(corr) > 0.36f) {
-							S.st_a1++;
-							S.bitmask = corr > 0.f ? 0u : ~0u;
-							S.signal_level = level;
-							S.frame_symbol_cnt = 1.0f;
-							S.symbols_wanted = HFDL_A_LEN;
-							S.search_retries = 0;
-							S.fr_state = HF_A2;
-						}
-						break; }
-					case HF_A2: {
-						float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
-						if(fabsf(corr) > 0.3f) {
-							S.a2_sample_cnt = S.sample_cnt;
-							S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
-							S.st_a2++;
-							S.symbols_wanted = 127;
-							S.search_retries = 0;
-							S.fr_state = HF_M1;
-						} else if(++S.search_retries >= 3) {
-							framer_reset(S, T, E);
-						}
-						break; }
-					case HF_M1: {
-						float max_corr = 0.f; int max_idx = -1;
-						for(int idx = 0; idx < 8; idx++) {
-							float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
-							if(corr > max_corr) { max_corr = corr; max_idx = idx; }
-						}
-						if(max_corr > 0.3f) {
-							S.st_m1++;
-							S.data_segment_cnt = T.mode_segments[max_idx];
-							S.data_arity = T.mode_arity[max_idx];
-							S.M1 = max_idx;
-							S.symbols_wanted = 15;
-							S.search_retries = 0;
-							S.fr_state = HF_M2_SKIP;
-							S.s_state = HS_SKIP;
-						} else {
-							framer_reset(S, T, E);
-						}
-						break; }
-					case HF_M2_SKIP:
-						S.training_n = 0;
-						S.symbols_wanted = HFDL_T_LEN;
-						S.eq_train_seq_cnt = 9;
-						S.fr_state = HF_EQ_TRAIN;
-						S.s_state = HS_EMIT_SYMBOLS;
-						break;
-					case HF_EQ_TRAIN: {
-						unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
-#pragma unroll
-						for(int j = 0; j < HFDL_T_LEN; j++) {
-							unsigned bit = (s_train[EQS(j)].x > 0.f) ? 0u : 1u;
-							bit ^= (S.bitmask & 1u);
-							tseq = (tseq << 1) | bit;
-						}
-						S.train_bits_total += HFDL_T_LEN;
-						S.train_bits_bad += __popc(0x9AFu ^ tseq);
-						S.training_n = 0;
-						if(S.eq_train_seq_cnt > 1) {
-							S.eq_train_seq_cnt--;
-							S.symbols_wanted = HFDL_T_LEN;
-							S.T_idx = 0;
-						} else if(S.data_segment_cnt > 0) {
-							S.symbols_wanted = 15;
-							S.fr_state = HF_DATA_1;
-							S.cur_arity = S.data_arity;
-							S.cur_buf = 1;
-						} else {                                 // end of frame: hand the symbols to fec_kernel
-							int q = 0;
-							if(lane == 0) q = atomicAdd(a.nframes, 1);
-							q = __shfl_sync(0xffffffffu, q, 0);
-							if(q < a.max_frames && lane == 0) {
-								FrameRec fr;
-								fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
-								fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
-								fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = S.sample_cnt;
-								fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
-								a.frames[q] = fr;
-							}
-							S.st_frames++;
-							S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
-							dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
-							framer_reset(S, T, E);
-							S.symbol_cnt = 0;
-						}
-						break; }
-					case HF_DATA_1:
-						S.symbols_wanted = 15;
-						S.fr_state = HF_DATA_2;
-						break;
-					case HF_DATA_2:
-						S.data_segment_cnt--;
-						S.cur_arity = 1;
-						S.cur_buf = 0;
-						S.fr_state = HF_EQ_TRAIN;
-						S.eq_train_seq_cnt = 1;
-						S.symbols_wanted = HFDL_T_LEN;
-						S.T_idx = 0;
-						break;
+						cf uu = cmul(t, wv[j]);
+						S.eq_w[j].x += uu.x;
+						S.eq_w[j].y += uu.y;
 					}
 				}
-				S.sample_cnt++;
+				S.T_idx++;
+			}
+			if(cap && lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s;
+			if(cap) cap_n_eq++;
+			cf x_hat;
+			unsigned bits = modem_demod(S.cur_arity, s, T, &x_hat);
+			// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
+			float err = s.y * x_hat.x - s.x * x_hat.y;
+			err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
+			S.c_phi += 0.1f * err;
+			S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
+
+			S.symbol_cnt++;
+			if(S.symbol_cnt >= 13ull * HFDL_SINGLE_SLOT_FRAME_LEN && S.fr_state == HF_A1) {
+				S.symbol_cnt = 0;
+				S.c_phi = S.c_dphi = 0.f;
+				ss_reset(S);
+			}
+			if(S.s_state == HS_EMIT_BITS) {
+				bits ^= S.bitmask;
+				for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
+			} else if(S.s_state == HS_EMIT_SYMBOLS) {
+				if(S.cur_buf == 0) {
+					if(S.training_n < HFDL_T_LEN) { s_train[EQS(S.training_n)] = s; S.training_n++; }
+				} else {
+					if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
+				}
+			}
+			if(S.fr_state > HF_A1) {
+				S.signal_level = (S.signal_level * S.frame_symbol_cnt + level) / (S.frame_symbol_cnt + 1.0f);
+				S.frame_symbol_cnt += 1.0f;
+			}
+			if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }
+
+			switch(S.fr_state) {
+			case HF_A1: {
+				float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+				if(fabsf(corr) > 0.36f) {
+					S.st_a1++;
+					S.bitmask = corr > 0.f ? 0u : ~0u;
+					S.signal_level = level;
+					S.frame_symbol_cnt = 1.0f;
+					S.symbols_wanted = HFDL_A_LEN;
+					S.search_retries = 0;
+					S.fr_state = HF_A2;
+				}
+				break; }
+			case HF_A2: {
+				float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+				if(fabsf(corr) > 0.3f) {
+					S.a2_sample_cnt = S.sample_cnt;
+					S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
+					S.st_a2++;
+					S.symbols_wanted = 127;
+					S.search_retries = 0;
+					S.fr_state = HF_M1;
+				} else if(++S.search_retries >= 3) {
+					framer_reset(S, T, E);
+				}
+				break; }
+			case HF_M1: {
+				float max_corr = 0.f; int max_idx = -1;
+				for(int idx = 0; idx < 8; idx++) {
+					float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
+					if(corr > max_corr) { max_corr = corr; max_idx = idx; }
+				}
+				if(max_corr > 0.3f) {
+					S.st_m1++;
+					S.data_segment_cnt = T.mode_segments[max_idx];
+					S.data_arity = T.mode_arity[max_idx];
+					S.M1 = max_idx;
+					S.symbols_wanted = 15;
+					S.search_retries = 0;
+					S.fr_state = HF_M2_SKIP;
+					S.s_state = HS_SKIP;
+				} else {
+					framer_reset(S, T, E);
+				}
+				break; }
+			case HF_M2_SKIP:
+				S.training_n = 0;
+				S.symbols_wanted = HFDL_T_LEN;
+				S.eq_train_seq_cnt = 9;
+				S.fr_state = HF_EQ_TRAIN;
+				S.s_state = HS_EMIT_SYMBOLS;
+				break;
+			case HF_EQ_TRAIN: {
+				unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
+#pragma unroll
+				for(int j = 0; j < HFDL_T_LEN; j++) {
+					unsigned bit = (s_train[EQS(j)].x > 0.f) ? 0u : 1u;
+					bit ^= (S.bitmask & 1u);
+					tseq = (tseq << 1) | bit;
+				}
+				S.train_bits_total += HFDL_T_LEN;
+				S.train_bits_bad += __popc(0x9AFu ^ tseq);
+				S.training_n = 0;
+				if(S.eq_train_seq_cnt > 1) {
+					S.eq_train_seq_cnt--;
+					S.symbols_wanted = HFDL_T_LEN;
+					S.T_idx = 0;
+				} else if(S.data_segment_cnt > 0) {
+					S.symbols_wanted = 15;
+					S.fr_state = HF_DATA_1;
+					S.cur_arity = S.data_arity;
+					S.cur_buf = 1;
+				} else {                                 // end of frame: hand the symbols to fec_kernel
+					int q = 0;
+					if(lane == 0) q = atomicAdd(a.nframes, 1);
+					q = __shfl_sync(0xffffffffu, q, 0);
+					if(q < a.max_frames && lane == 0) {
+						FrameRec fr;
+						fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
+						fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
+						fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = S.sample_cnt;
+						fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
+						a.frames[q] = fr;
+					}
+					S.st_frames++;
+					S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
+					dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+					framer_reset(S, T, E);
+					S.symbol_cnt = 0;
+				}
+				break; }
+			case HF_DATA_1:
+				S.symbols_wanted = 15;
+				S.fr_state = HF_DATA_2;
+				break;
+			case HF_DATA_2:
+				S.data_segment_cnt--;
+				S.cur_arity = 1;
+				S.cur_buf = 0;
+				S.fr_state = HF_EQ_TRAIN;
+				S.eq_train_seq_cnt = 1;
+				S.symbols_wanted = HFDL_T_LEN;
+				S.T_idx = 0;
+				break;
 			}
 		}
-		__syncwarp();
-		{
-			const int nn0 = (jc + 2) * HFDL_LOOP_CH;
-			for(int i = 0; i < HFDL_LOOP_CH; i++) { int n = nn0 + i; if(n < N) hfdl_cp_async8(&s_bank[jc & 1][i][lane], &bank[(long long)n * 32 + lane]); }
-			{ int n = nn0 + lane; if(lane < HFDL_LOOP_CH && n < N) hfdl_cp_async4(&s_lvl[jc & 1][lane], &lvl[n]); }
-			hfdl_cp_async_commit();
-		}
 	}
+#undef HFDL_NF_TICK
+	S.sample_cnt = cnt_base + (unsigned long long)N;
 	hfdl_cp_async_wait<0>();
 	__syncwarp();
 	if(lane == 0) {
-		for(int j = 0; j < HFDL_EQ_LEN; j++) { S.eq_win[j] = E.win[EQS((E.ep + j) & 15)]; S.eq_x2[j] = E.x2[EQS((E.ep + j) & 15)]; }
+		for(int j = 0; j < HFDL_EQ_LEN; j++) { S.eq_win[j] = E.win[EQS(E.ep + j)]; S.eq_x2[j] = E.x2[EQS((E.ep + j) & 15)]; }
 		for(int j = 0; j < HFDL_T_LEN; j++) S.training[j] = s_train[EQS(j)];
 		a.state[c] = S;
 		if(cap) a.cap_cnt[1] = cap_n_eq;
