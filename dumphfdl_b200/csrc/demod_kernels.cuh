@@ -249,7 +249,7 @@ __device__ __forceinline__ int bits_corr(const unsigned *a, const unsigned *b) {
 __device__ __forceinline__ void ss_reset(DemodState &S) {     // symsync_crcf_reset: mf window, timing state, loop filter
 	S.ss_since_reset = 0;                                     // the mf-arm window is cleared, the dmf one is not
 	S.ss_rate = 1.5f; S.ss_del = 1.5f;                        // k / k_out = 3/2
-	S.ss_b = 0; S.ss_bf = 0.f; S.ss_tau = 0.f; S.ss_q = 0.f; S.ss_q_hat = 0.f; S.ss_decim_counter = 0;
+	S.ss_b = 0; S.ss_tau = 0.f; S.ss_q = 0.f; S.ss_q_hat = 0.f; S.ss_decim_counter = 0;
 	S.ss_v[0] = S.ss_v[1] = S.ss_v[2] = 0.f;
 }
 // equaliser window / |x|^2 delay line live in a 16-slot shared-memory ring while the kernel runs (ep = oldest slot).
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 	}
 	hfdl_cp_async_wait<1>();
 	__syncwarp();
-	int chunk = 0;                 // chunk currently readable in s_bank[chunk & 1]
+	int chunk = 0, chunk_end = HFDL_LOOP_CH;   // chunk currently readable in s_bank[chunk & 1]
 	int k = -1;                    // last input sample consumed
 	// The loop is driven by symsync OUTPUTS (2 per 3 input samples): input samples that produce no output only
 	// tick the noise-floor clock and step the timing phase (symsync_crcf_step: tau -= 1, b -= npfb).
@@ -351,17 +351,17 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 			for(int sidx = k + 1; sidx < N; sidx++) {
 				HFDL_NF_TICK(sidx);
 				if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
-				S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
+				S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
 			}
 			break;
 		}
 		for(int sidx = k + 1; sidx < kn; sidx++) {
 			HFDL_NF_TICK(sidx);
 			if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
-			S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
+			S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
 		}
 		k = kn;
-		while(k >= (chunk + 1) * HFDL_LOOP_CH) {       // move to the next staged chunk, refill the one just left
+		while(k >= chunk_end) {       // move to the next staged chunk, refill the one just left
 			__syncwarp();
 			const int nn0 = (chunk + 2) * HFDL_LOOP_CH;
 			for(int i = 0; i < HFDL_LOOP_CH; i++) { int n = nn0 + i; if(n < N) hfdl_cp_async8(&s_bank[chunk & 1][i][lane], &bank[(long long)n * 32 + lane]); }
@@ -369,9 +369,9 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 			hfdl_cp_async_commit();
 			hfdl_cp_async_wait<1>();
 			__syncwarp();
-			chunk++;
+			chunk++; chunk_end += HFDL_LOOP_CH;
 		}
-		const int ii = k - chunk * HFDL_LOOP_CH;
+		const int ii = k - (chunk_end - HFDL_LOOP_CH);
 		const cf *row = s_bank[chunk & 1][ii];
 		const float level = s_lvl[chunk & 1][ii];           // 1/g after this sample's AGC update
 		S.sample_cnt = cnt_base + (unsigned long long)k;
@@ -406,11 +406,10 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 			}
 			S.ss_decim_counter++;
 			S.ss_tau += S.ss_del;
-			S.ss_bf = S.ss_tau * (float)HFDL_SS_NPFB;
-			S.ss_b = hfdl_round_pos(S.ss_bf);                 // bf > 0 here, == (int)roundf(bf)
+			S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);     // bf = tau*npfb > 0 here: == (int)roundf(bf)
 			produced++;
 		}
-		S.ss_tau -= 1.0f; S.ss_bf -= (float)HFDL_SS_NPFB; S.ss_b -= HFDL_SS_NPFB;
+		S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
 		if(produced > 2) produced = 2;
 
 		for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
@@ -501,7 +500,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 				}
 			}
 			if(S.fr_state > HF_A1) {
-				S.signal_level = (S.signal_level * S.frame_symbol_cnt + level) / (S.frame_symbol_cnt + 1.0f);
+				S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + level, S.frame_symbol_cnt + 1.0f);
 				S.frame_symbol_cnt += 1.0f;
 			}
 			if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }

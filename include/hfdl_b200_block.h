@@ -1,0 +1,80 @@
+/*
+ * include/hfdl_b200_block.h -- the block.c-facing side of libhfdl_b200.so: one `struct block` that replaces
+ * the reference's fft block and all of its hfdl channel blocks, so that input-file.c / input-soapysdr.c keep
+ * producing into the same ring and pdu.c / fmtr-*.c / output-*.c keep consuming PDUs, untouched.
+ *
+ * Replaces (dumphfdl src/):
+ *   hfdl_gpu_frontend_create   <- fft_create (fft.h:31) + hfdl_init_globals / hfdl_channel_create x C (hfdl.h:10-12)
+ *                                 + block_connect_one2many(fft, channels) (main.c:752-755) + csdr_fft_init (main.c:697)
+ *   hfdl_gpu_frontend_destroy  <- fft_destroy (fft.h:32) + hfdl_channel_destroy x C (hfdl.h:13) + block_disconnect_one2many
+ *   block->thread_routine      <- fft_thread (fft.c:22-68) + hfdl_decoder_thread x C (hfdl.c:593-935); started by the
+ *                                 reference's own block_start() (block.c:157-166) after block_connect_one2one(input, this)
+ *   PDU delivery               <- dispatch_pdu (hfdl.c:1058-1080): hfdl_pdu_metadata_create + octet_string_new +
+ *                                 pdu_decoder_queue_push (pdu.h:39-40), resolved against the host program at load time
+ *   hfdl_gpu_frontend_print_summary <- hfdl_print_summary (hfdl.h:14)
+ *   cbuffercf_*                <- liquid-dsp's cbuffercf as used by block.c:20,28, fft.c:41-54, input-helpers.c:83-89,
+ *                                 input-file.c:55 (only needed when dumphfdl is linked without liquid-dsp, e.g. the tests)
+ *
+ * The struct layouts below restate the ABI of src/block.h:27-68 (field order and types are the interface).
+ */
+#ifndef HFDL_B200_BLOCK_H
+#define HFDL_B200_BLOCK_H
+#include <stdint.h>
+#include <stdbool.h>
+#include <stddef.h>
+#include <pthread.h>
+#include "hfdl_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef HFDL_B200_NO_BLOCK_STRUCTS      /* define when compiling inside dumphfdl, which has its own block.h */
+enum producer_type { PRODUCER_NONE = 0, PRODUCER_SINGLE, PRODUCER_MULTI, PRODUCER_MAX };
+enum consumer_type { CONSUMER_NONE = 0, CONSUMER_SINGLE, CONSUMER_MULTI, CONSUMER_MAX };
+typedef struct hfdl_cbuffercf_s *cbuffercf;
+struct circ_buffer { cbuffercf buf; pthread_cond_t *cond; pthread_mutex_t *mutex; };
+struct shared_buffer { void *buf; pthread_barrier_t *data_ready; pthread_barrier_t *consumers_ready; };
+struct block_connection {
+	union { struct circ_buffer circ_buffer; struct shared_buffer shared_buffer; };
+	uint32_t flags;
+};
+#define BLOCK_CONNECTION_SHUTDOWN (1 << 0)
+struct block;
+struct producer { struct block_connection *out; size_t max_tu; enum producer_type type; };
+struct consumer { struct block_connection *in; size_t min_ru; enum consumer_type type; };
+struct block {
+	struct consumer consumer;
+	struct producer producer;
+	pthread_t thread;
+	void *(*thread_routine)(void *);
+	bool running;
+};
+#endif
+
+/* Returns &obj->block with consumer = { CONSUMER_SINGLE, min_ru = fft_size }, producer = { PRODUCER_NONE } and
+ * thread_routine set; NULL on error.  The ring carries CF32 (what complex_samples_produce writes). */
+struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_hz, const int32_t *freqs_hz,
+		int32_t nfreq, int32_t device);
+void hfdl_gpu_frontend_destroy(struct block *frontend_block);
+void hfdl_gpu_frontend_print_summary(struct block *frontend_block);
+/* channel noise floor in dBFS, as noise_floor_stats_thread reports it (hfdl.c:1093) */
+int32_t hfdl_gpu_frontend_noise_floor_db(struct block *frontend_block, int32_t channel, float *db);
+/* When the host program does not export pdu_decoder_queue_push (e.g. the tests), PDUs go to this callback. */
+typedef void (*hfdl_gpu_pdu_callback)(const hfdl_b200_pdu_t *pdu, void *user);
+void hfdl_gpu_frontend_set_pdu_callback(struct block *frontend_block, hfdl_gpu_pdu_callback cb, void *user);
+
+/* ---- cbuffercf stand-in (liquid-dsp API subset), elements are C99 float complex = 2 floats ---- */
+cbuffercf cbuffercf_create(unsigned int max_size);
+void cbuffercf_destroy(cbuffercf q);
+void cbuffercf_reset(cbuffercf q);
+unsigned int cbuffercf_size(cbuffercf q);
+unsigned int cbuffercf_max_size(cbuffercf q);
+unsigned int cbuffercf_space_available(cbuffercf q);
+int cbuffercf_write(cbuffercf q, void *v /* float complex* */, unsigned int n);
+int cbuffercf_read(cbuffercf q, unsigned int n, void **v /* float complex** */, unsigned int *num_read);
+int cbuffercf_release(cbuffercf q, unsigned int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

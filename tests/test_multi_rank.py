@@ -1,0 +1,71 @@
+"""world_size-2 test of the N>1 path on CPU (gloo): rank 0's capture is broadcast, each rank runs its channel
+shard through the front-end (host-emulation build of the kernels), PDUs are gathered and must equal the
+oracle's for the full channel set."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+import b200_cases as K
+import orclib as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FREQS = [10063000, 9952000, 10101000]
+MODES = [1, 2, 0]
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import dumphfdl_b200.api as A
+    from dumphfdl_b200 import sharding
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sim = A.bind(C.CDLL(os.path.join(HERE, "cusim", "libhfdl_cusim.so")))
+    n = int(250000 * 3.3)
+    if rank == 0:
+        x, _ = K.make_capture(250000, FREQS, MODES, 3.3, seed=41)
+        t = torch.from_numpy(x.view(np.float32).copy())
+    else:
+        t = torch.zeros(2 * n, dtype=torch.float32)
+    sharding.broadcast_capture(t, 0)
+    idx, mine = sharding.shard_channels(FREQS, rank, world)
+    fe = A.Frontend(250000, K.CF, mine, max_blocks_per_batch=8, lib=sim)
+    fe.push(t.numpy())
+    fe.flush()
+    merged = sharding.gather_pdus(fe.pdus())
+    if rank == 0:
+        q.put(merged)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_channel_sharding_gloo():
+    import torch.multiprocessing as mp
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "cusim"), "all"], check=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    x, truth = K.make_capture(250000, FREQS, MODES, 3.3, seed=41)
+    ref = K.run_oracle(250000, FREQS, x, O.SFMT_CF32).pdus()
+    want = sorted((int(r.sample_cnt_end), int(r.freq), r.data(), int(r.M1), int(r.crc_good)) for r in ref)
+    assert merged == want and len(merged) == 3
+
+
+def test_shard_map_is_a_partition():
+    from dumphfdl_b200 import sharding
+    f = list(range(1000, 1013))
+    for world in (1, 2, 4, 8):
+        parts = [sharding.shard_channels(f, r, world) for r in range(world)]
+        assert sorted(i for idx, _ in parts for i in idx) == list(range(len(f)))
+        assert all(fr == [f[i] for i in idx] for idx, fr in parts)
