@@ -24,6 +24,7 @@ enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_AGC, KC_BANK, KC_LO
 const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "agc", "bank", "loop", "fec" };
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
+#define HFDL_NSUB 8        // sub-ranges per batch for the agc/bank || loop overlap
 
 FftPlan make_plan(int N) {
 	FftPlan p;
@@ -73,7 +74,8 @@ struct hfdl_b200_frontend {
 	FftPlan plan;
 	int C = 0, Bmax = 0, sfmt = 0, bps = 0, out_per_block = 0;
 	float resamp_rate = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, stream2 = nullptr;
+	cudaEvent_t ev_rs = nullptr, ev_sub[HFDL_NSUB] = { nullptr };
 	FftEngine fft;
 	// device memory
 	cf *d_work = nullptr; void *d_ring = nullptr; long long ring_len = 0;
@@ -112,6 +114,18 @@ inline void prof_begin(hfdl_b200_frontend *fe, int cls, ProfRec &r) {
 inline void prof_end(hfdl_b200_frontend *fe, ProfRec &r) {
 	if(r.cls < 0) return;
 	cudaEventRecord(r.e1, fe->stream);
+	fe->prof.push_back(r);
+}
+inline void prof_begin2(hfdl_b200_frontend *fe, int cls, ProfRec &r, cudaStream_t st) {
+	r.cls = -1;
+	if(!fe || !fe->profiling) return;
+	r.cls = cls;
+	cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+	cudaEventRecord(r.e0, st);
+}
+inline void prof_end2(hfdl_b200_frontend *fe, ProfRec &r, cudaStream_t st) {
+	if(r.cls < 0) return;
+	cudaEventRecord(r.e1, st);
 	fe->prof.push_back(r);
 }
 
@@ -210,28 +224,42 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 		fe->launches++;
 	}
 	if(n_out > 0) {
-		AgcArgs a;
-		a.rs = fe->d_rs; a.rs_stride = fe->rs_stride; a.n_samples = n_out; a.state = fe->d_agc_state;
-		a.agc_out = fe->d_agc; a.agc_stride = fe->agc_stride; a.lvl = fe->d_lvl; a.lvl_stride = fe->rs_stride;
-		prof_begin(fe, KC_AGC, pr);
-		HFDL_LAUNCH(agc_kernel, dim3((unsigned)fe->C), dim3(32), 0, st, a);
-		prof_end(fe, pr);
-		BankArgs b;
-		b.agc_out = fe->d_agc; b.agc_stride = fe->agc_stride; b.n_samples = n_out; b.mfo = fe->d_mfo; b.mfo_stride = fe->mfo_stride;
-		b.bank = fe->d_bank; b.bank_stride = fe->rs_stride; b.tab = fe->d_tab;
-		prof_begin(fe, KC_BANK, pr);
-		HFDL_LAUNCH(bank_kernel, dim3((unsigned)((n_out + HFDL_BANK_TILE - 1) / HFDL_BANK_TILE), (unsigned)fe->C), dim3(256), 0, st, b);
-		prof_end(fe, pr);
-		LoopArgs l;
-		l.bank = fe->d_bank; l.bank_stride = fe->rs_stride; l.mfo = fe->d_mfo; l.mfo_stride = fe->mfo_stride;
-		l.lvl = fe->d_lvl; l.lvl_stride = fe->rs_stride; l.n_samples = n_out;
-		l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym;
-		l.frames = fe->d_frames; l.nframes = fe->d_nframes; l.max_frames = fe->max_frames;
-		l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
-		prof_begin(fe, KC_LOOP, pr);
-		HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(32), 0, st, l);
-		prof_end(fe, pr);
-		fe->launches += 3;
+		// The demodulator is a feed-forward chain agc -> bank -> loop whose first and last stage are latency-bound
+		// single-warp recurrences: split the batch into sub-ranges and run agc/bank of sub-range i+1 on a second
+		// stream while loop works on sub-range i (both recurrences keep their state in HBM between launches).
+		const int nsub = (n_out >= 8 * 2048) ? HFDL_NSUB : 1;
+		CK(cudaEventRecord(fe->ev_rs, st));
+		CK(cudaStreamWaitEvent(fe->stream2, fe->ev_rs, 0));
+		cudaStream_t st2 = fe->stream2;
+		for(int i = 0; i < nsub; i++) {
+			const long long s0 = (long long)n_out * i / nsub, s1 = (long long)n_out * (i + 1) / nsub;
+			const int ns = (int)(s1 - s0);
+			if(ns <= 0) continue;
+			AgcArgs a;
+			a.rs = fe->d_rs + s0; a.rs_stride = fe->rs_stride; a.n_samples = ns; a.state = fe->d_agc_state;
+			a.agc_out = fe->d_agc + s0; a.agc_stride = fe->agc_stride; a.lvl = fe->d_lvl + s0; a.lvl_stride = fe->rs_stride;
+			prof_begin2(fe, KC_AGC, pr, st2);
+			HFDL_LAUNCH(agc_kernel, dim3((unsigned)fe->C), dim3(32), 0, st2, a);
+			prof_end2(fe, pr, st2);
+			BankArgs b;
+			b.agc_out = fe->d_agc + s0; b.agc_stride = fe->agc_stride; b.n_samples = ns; b.mfo = fe->d_mfo + s0; b.mfo_stride = fe->mfo_stride;
+			b.bank = fe->d_bank + s0 * 32; b.bank_stride = fe->rs_stride; b.tab = fe->d_tab;
+			prof_begin2(fe, KC_BANK, pr, st2);
+			HFDL_LAUNCH(bank_kernel, dim3((unsigned)((ns + HFDL_BANK_TILE - 1) / HFDL_BANK_TILE), (unsigned)fe->C), dim3(256), 0, st2, b);
+			prof_end2(fe, pr, st2);
+			CK(cudaEventRecord(fe->ev_sub[i], st2));
+			CK(cudaStreamWaitEvent(st, fe->ev_sub[i], 0));
+			LoopArgs l;
+			l.bank = fe->d_bank + s0 * 32; l.bank_stride = fe->rs_stride; l.mfo = fe->d_mfo + s0; l.mfo_stride = fe->mfo_stride;
+			l.lvl = fe->d_lvl + s0; l.lvl_stride = fe->rs_stride; l.n_samples = ns;
+			l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym;
+			l.frames = fe->d_frames; l.nframes = fe->d_nframes; l.max_frames = fe->max_frames;
+			l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
+			prof_begin(fe, KC_LOOP, pr);
+			HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(32), 0, st, l);
+			prof_end(fe, pr);
+			fe->launches += 3;
+		}
 		if(fe->cfg.capture_channel >= 0 && fe->cap_n < fe->cfg.capture_max) {       // f_agc_out / f_mf_out checkpoints
 			long long n = std::min<long long>(n_out, fe->cfg.capture_max - fe->cap_n);
 			int cc = fe->cfg.capture_channel;
@@ -356,6 +384,9 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 #define CKD(call) do { cudaError_t e_ = (call); if(e_ != cudaSuccess) { fprintf(stderr, "hfdl_b200_create: CUDA error '%s' (%s)\n", cudaGetErrorString(e_), #call); hfdl_b200_destroy(fe); return -1; } } while(0)
 	CKD(cudaSetDevice(cfg->device));
 	CKD(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
+	CKD(cudaStreamCreateWithFlags(&fe->stream2, cudaStreamNonBlocking));
+	CKD(cudaEventCreateWithFlags(&fe->ev_rs, cudaEventDisableTiming));
+	for(int i = 0; i < HFDL_NSUB; i++) CKD(cudaEventCreateWithFlags(&fe->ev_sub[i], cudaEventDisableTiming));
 	if(fe->fft.init()) { hfdl_b200_destroy(fe); return -1; }
 	const int C = fe->C, N = g.fft_size, M = g.fft_inv_size, B = fe->Bmax;
 	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * B));
@@ -444,6 +475,9 @@ void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	if(fe->ev0) cudaEventDestroy(fe->ev0);
 	if(fe->ev1) cudaEventDestroy(fe->ev1);
 	fe->fft.destroy();
+	if(fe->stream2) { cudaStreamSynchronize(fe->stream2); cudaStreamDestroy(fe->stream2); }
+	if(fe->ev_rs) cudaEventDestroy(fe->ev_rs);
+	for(int i = 0; i < HFDL_NSUB; i++) if(fe->ev_sub[i]) cudaEventDestroy(fe->ev_sub[i]);
 	if(fe->stream) cudaStreamDestroy(fe->stream);
 	delete fe;
 }

@@ -38,3 +38,8 @@ def test_frontend_cfg1_cs16(sim):
 
 def test_frontend_two_channels_ragged_cf32(sim):
     assert K.case_frontend(sim, 250000, [10063000, 9952000], [3, 0], 3.2, batch=3, ragged=True, seed=5) == 2
+
+
+def test_frontend_large_batch_uses_subranges(sim):
+    # one 48-block batch: n_out > 16384 -> the agc/bank || loop sub-range schedule (HFDL_NSUB) is exercised
+    assert K.case_frontend(sim, 250000, [10063000, 9952000], [5, 1], 5.6, batch=64, seed=8) == 2
