@@ -310,6 +310,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 	cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
 	const float ss_a1 = T.ss_a1, ss_a2 = T.ss_a2, ss_b0 = T.ss_b0, ss_radj = T.ss_rate_adj;
 	const unsigned long long cnt_base = S.sample_cnt;
+	unsigned symcnt = (unsigned)S.symbol_cnt;
 
 	unsigned A_bits[4];
 #pragma unroll
@@ -342,24 +343,47 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 	int k = -1;                    // last input sample consumed
 	// The loop is driven by symsync OUTPUTS (2 per 3 input samples): input samples that produce no output only
 	// tick the noise-floor clock and step the timing phase (symsync_crcf_step: tau -= 1, b -= npfb).
-#define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1 && (++S.nf_clk & 0xFFu) == 0xFFu) \
-		S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } while(0)     /* hfdl.c:700-706 */
+	// The hot path is kept branch-poor: one output per input sample is the rule (del ~ 1.5), everything else is
+	// handled by generic, rarely taken code.
+#define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1) { if((++S.nf_clk & 0xFFu) == 0xFFu) \
+		S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } } while(0)     /* hfdl.c:700-706 */
+#define HFDL_SS_CONSUME() do { if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++; } while(0)
+	// one symsync output at input sample k from arm b: value (scaled by 1/k_sps) and, on "ideal timing" outputs,
+	// the timing-error detector + loop filter (symsync_crcf_step / advance_internal_loop)
+#define HFDL_SS_OUTPUT(dst) do { \
+		const int bb_ = S.ss_b < 0 ? 0 : S.ss_b; \
+		cf mf_ = row[bb_]; \
+		if(S.ss_since_reset < HFDL_SS_SUB) { /* window still filling after a reset: only samples pushed since then count */ \
+			mf_ = make_float2(0.f, 0.f); \
+			const float *h_ = T.ss_mf[bb_]; \
+			for(int j_ = (int)S.ss_since_reset - 1; j_ >= 0; j_--) { cf v_ = mfo[k - j_]; mf_.x += h_[j_] * v_.x; mf_.y += h_[j_] * v_.y; } \
+		} \
+		dst = make_float2(mf_.x * 0.33333334f, mf_.y * 0.33333334f); \
+		if(S.ss_decim_counter == 2u) { \
+			S.ss_decim_counter = 0; \
+			const cf dmf_ = row[16 + bb_]; \
+			float q_ = fminf(fmaxf(mf_.x * dmf_.x + mf_.y * dmf_.y, -1.0f), 1.0f);     /* Re(conj(mf)*dmf), clipped */ \
+			S.ss_q = q_; \
+			S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0]; \
+			S.ss_v[0] = q_ - ss_a1 * S.ss_v[1] - ss_a2 * S.ss_v[2]; \
+			S.ss_q_hat = ss_b0 * S.ss_v[0]; \
+			S.ss_rate += ss_radj * S.ss_q_hat; \
+			S.ss_del = S.ss_rate + S.ss_q_hat; \
+		} \
+		S.ss_decim_counter++; \
+		S.ss_tau += S.ss_del; \
+		S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);     /* bf = tau*npfb > 0 here: == (int)roundf(bf) */ \
+	} while(0)
 	for(;;) {
-		const int skip = (S.ss_b >= HFDL_SS_NPFB) ? (S.ss_b >> 4) : 0;
-		const int kn = k + 1 + skip;
-		if(kn >= N) {              // the rest of the batch yields no output
-			for(int sidx = k + 1; sidx < N; sidx++) {
-				HFDL_NF_TICK(sidx);
-				if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
-				S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
+		int kn = k + 1;
+		if(S.ss_b >= HFDL_SS_NPFB) {               // input sample(s) without output: usually exactly one
+			int skip = S.ss_b >> 4;
+			if(kn + skip >= N) {                   // the rest of the batch yields no output
+				for(; kn < N; kn++) { HFDL_NF_TICK(kn); HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; }
+				break;
 			}
-			break;
-		}
-		for(int sidx = k + 1; sidx < kn; sidx++) {
-			HFDL_NF_TICK(sidx);
-			if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
-			S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
-		}
+			do { HFDL_NF_TICK(kn); HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; kn++; } while(--skip);
+		} else if(kn >= N) break;
 		k = kn;
 		while(k >= chunk_end) {       // move to the next staged chunk, refill the one just left
 			__syncwarp();
@@ -374,55 +398,32 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 		const int ii = k - (chunk_end - HFDL_LOOP_CH);
 		const cf *row = s_bank[chunk & 1][ii];
 		const float level = s_lvl[chunk & 1][ii];           // 1/g after this sample's AGC update
-		S.sample_cnt = cnt_base + (unsigned long long)k;
 		HFDL_NF_TICK(k);
 		// ---- symsync_crcf_step (push happened in bank_kernel; the reset only clears the mf-arm window)
-		if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;
-		cf sym0 = make_float2(0.f, 0.f), sym1 = sym0;     // symsync outputs of this input sample (at most 2: del ~ 1.5)
-		int produced = 0;
-		while(S.ss_b < HFDL_SS_NPFB) {
-			cf mf = row[S.ss_b];
-			if(S.ss_since_reset < HFDL_SS_SUB) {
-				// window still filling after a reset: only the samples pushed since then contribute
-				mf = make_float2(0.f, 0.f);
-				const float *h = T.ss_mf[S.ss_b];
-				for(int j = (int)S.ss_since_reset - 1; j >= 0; j--) { cf v = mfo[k - j]; mf.x += h[j] * v.x; mf.y += h[j] * v.y; }
-			}
-			{   // output scaled by 1/k (k = 3 samples per symbol)
-				cf o = make_float2(mf.x * 0.33333334f, mf.y * 0.33333334f);
-				if(produced == 0) sym0 = o; else if(produced == 1) sym1 = o;
-			}
-			if(S.ss_decim_counter == 2u) {
-				S.ss_decim_counter = 0;
-				cf dmf = row[16 + S.ss_b];
-				float q = mf.x * dmf.x + mf.y * dmf.y;           // Re(conj(mf)*dmf)
-				q = fminf(fmaxf(q, -1.0f), 1.0f);
-				S.ss_q = q;
-				S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0];
-				S.ss_v[0] = q - ss_a1 * S.ss_v[1] - ss_a2 * S.ss_v[2];
-				S.ss_q_hat = ss_b0 * S.ss_v[0];
-				S.ss_rate += ss_radj * S.ss_q_hat;
-				S.ss_del = S.ss_rate + S.ss_q_hat;
-			}
-			S.ss_decim_counter++;
-			S.ss_tau += S.ss_del;
-			S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);     // bf = tau*npfb > 0 here: == (int)roundf(bf)
-			produced++;
+		HFDL_SS_CONSUME();
+		cf sym0, sym1 = make_float2(0.f, 0.f);
+		int produced = 1;
+		HFDL_SS_OUTPUT(sym0);
+		if(S.ss_b < HFDL_SS_NPFB) {                // a second (third, ...) output of the same input sample: del < 1, rare
+			HFDL_SS_OUTPUT(sym1);
+			produced = 2;
+			while(S.ss_b < HFDL_SS_NPFB) { cf drop; HFDL_SS_OUTPUT(drop); (void)drop; }
 		}
 		S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
-		if(produced > 2) produced = 2;
 
 		for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
 			// ---- Costas step + rotate (hfdl.c:250-294,709-715)
 			S.c_phi += S.c_dphi;
 			// (double)phi > M_PI  <=>  phi > 3.1415925f (largest float below pi); 2*pi split hi+lo
-			if(S.c_phi > 3.1415925f) S.c_phi = (S.c_phi - 6.2831855f) + 1.7484555e-7f;
-			else if(S.c_phi < -3.1415925f) S.c_phi = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
+			{
+				const float dn = (S.c_phi - 6.2831855f) + 1.7484555e-7f, up = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
+				S.c_phi = S.c_phi > 3.1415925f ? dn : (S.c_phi < -3.1415925f ? up : S.c_phi);
+			}
 			float sn, cs;
 			hfdl_sincos_fast(S.c_phi, &sn, &cs);
 			const cf so = (i == 0) ? sym0 : sym1;
 			cf r = make_float2(so.x * cs + so.y * sn, so.y * cs - so.x * sn);
-			if(fabsf(S.c_dphi) > 0.25f && S.fr_state == HF_A1) {
+			if(S.fr_state == HF_A1 && fabsf(S.c_dphi) > 0.25f) {
 				S.c_phi = S.c_dphi = 0.f;
 				ss_reset(S);
 			}
@@ -483,9 +484,9 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 			S.c_phi += 0.1f * err;
 			S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
 
-			S.symbol_cnt++;
-			if(S.symbol_cnt >= 13ull * HFDL_SINGLE_SLOT_FRAME_LEN && S.fr_state == HF_A1) {
-				S.symbol_cnt = 0;
+			symcnt++;
+			if(S.fr_state == HF_A1 && symcnt >= 13u * HFDL_SINGLE_SLOT_FRAME_LEN) {
+				symcnt = 0;
 				S.c_phi = S.c_dphi = 0.f;
 				ss_reset(S);
 			}
@@ -521,7 +522,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 			case HF_A2: {
 				float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
 				if(fabsf(corr) > 0.3f) {
-					S.a2_sample_cnt = S.sample_cnt;
+					S.a2_sample_cnt = cnt_base + (unsigned long long)k;
 					S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
 					S.st_a2++;
 					S.symbols_wanted = 127;
@@ -585,7 +586,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 						FrameRec fr;
 						fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
 						fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
-						fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = S.sample_cnt;
+						fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = cnt_base + (unsigned long long)k;
 						fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
 						a.frames[q] = fr;
 					}
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 					S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
 					dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
 					framer_reset(S, T, E);
-					S.symbol_cnt = 0;
+					symcnt = 0;
 				}
 				break; }
 			case HF_DATA_1:
@@ -613,7 +614,10 @@ __global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
 		}
 	}
 #undef HFDL_NF_TICK
+#undef HFDL_SS_CONSUME
+#undef HFDL_SS_OUTPUT
 	S.sample_cnt = cnt_base + (unsigned long long)N;
+	S.symbol_cnt = symcnt;
 	hfdl_cp_async_wait<0>();
 	__syncwarp();
 	if(lane == 0) {
