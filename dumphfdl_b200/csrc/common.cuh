@@ -57,6 +57,13 @@ __device__ __forceinline__ void hfdl_cp_async_commit() { asm volatile("cp.async.
 template <int N> __device__ __forceinline__ void hfdl_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
+// polite spinning while one warp waits for another
+#ifdef HFDL_CUSIM
+#define HFDL_SPIN_PAUSE() std::this_thread::yield()
+#else
+#define HFDL_SPIN_PAUSE() __nanosleep(20)
+#endif
+
 // sample formats (src/input-common.h sample_format)
 enum { HFDL_SFMT_CU8 = 1, HFDL_SFMT_CS16 = 2, HFDL_SFMT_CF32 = 3 };
 

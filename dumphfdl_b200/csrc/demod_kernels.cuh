@@ -297,334 +297,431 @@ __device__ __forceinline__ unsigned modem_demod(int m, cf x, const DemodTables &
 	return sym;
 }
 
-__global__ void __launch_bounds__(32) loop_kernel(LoopArgs a) {
+#define HFDL_RING 64           // symsync outputs the timing warp may run ahead of the demodulator warp
+// a value polled from shared memory is made warp-uniform (lane 0's view) so that every lane takes the same branch
+#define HFDL_UNI(v) __shfl_sync(0xffffffffu, (int)(v), 0)
+// loop_kernel: 2 warps per channel.
+//   warp 1 ("timing")  runs the symbol-timing recursion (symsync_crcf_step: arm selection, timing-error detector,
+//                      loop filter) AHEAD of the demodulator and publishes its outputs into a shared-memory ring.
+//                      That recursion does not depend on Costas/equaliser/framer -- except when they reset it
+//                      (symsync_crcf_reset from framer_reset, Costas blow-up, 13-frame timeout: hfdl.c:711-715,
+//                      746-752, 968-991).  Resets are rare (about once per frame): the demodulator warp posts
+//                      (sample, sequence) of the reset and the timing warp rolls back to that point.
+//   warp 0 ("demod")   consumes the outputs in order: Costas, equaliser, slicer, sampler, framer.
+// Inside a warp every lane runs the same scalar program (warp-uniform); lane 0 publishes ring indices.
+__global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 	const int c = blockIdx.x;
-	const int lane = threadIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const DemodTables &T = *a.tab;
 	DemodState S = a.state[c];
-	const cf *bank = a.bank + (long long)c * a.bank_stride * 32;
-	const cf *mfo = a.mfo + (long long)c * a.mfo_stride + HFDL_MFO_HIST;
 	const float *lvl = a.lvl + (long long)c * a.lvl_stride;
-	const bool cap = (c == a.cap_channel);
-	int cap_n_eq = cap ? a.cap_cnt[1] : 0;
-	cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
-	const float ss_a1 = T.ss_a1, ss_a2 = T.ss_a2, ss_b0 = T.ss_b0, ss_radj = T.ss_rate_adj;
-	const unsigned long long cnt_base = S.sample_cnt;
-	unsigned symcnt = (unsigned)S.symbol_cnt;
-
-	unsigned A_bits[4];
-#pragma unroll
-	for(int i = 0; i < 4; i++) A_bits[i] = T.A_bits[i];
-	// bank rows (lane = arm) and AGC levels are staged through shared memory two chunks ahead with cp.async,
-	// so the arm the timing loop selects is a shared-memory read, never a dependent global load
+	const int N = a.n_samples;
+	__shared__ float4 s_ring[HFDL_RING];            // {sym.re, sym.im, AGC level, input sample index (int bits)}
+	__shared__ volatile int s_head, s_tail, s_end_seq, s_done;
+	__shared__ volatile int s_reset_gen, s_reset_k, s_reset_seq, s_ack_gen;
 	__shared__ cf s_bank[2][HFDL_LOOP_CH][32];
 	__shared__ float s_lvl[2][HFDL_LOOP_CH];
 	__shared__ cf s_eqwin[32 * 32];
 	__shared__ float s_eqx2[16 * 32];
 	__shared__ cf s_train_all[16 * 32];
-	EqRing E;
-	E.win = s_eqwin + lane; E.x2 = s_eqx2 + lane; E.ep = 0;
-	cf *s_train = s_train_all + lane;
-	for(int j = 0; j < 16; j++) {
-		cf v = j < HFDL_EQ_LEN ? a.state[c].eq_win[j] : make_float2(0.f, 0.f);
-		E.win[EQS(j)] = v; E.win[EQS(j + 16)] = v;
-		E.x2[EQS(j)] = j < HFDL_EQ_LEN ? a.state[c].eq_x2[j] : 0.f;
-		s_train[EQS(j)] = j < HFDL_T_LEN ? a.state[c].training[j] : make_float2(0.f, 0.f);
-	}
-	const int N = a.n_samples;
-	for(int pre = 0; pre < 2; pre++) {
-		for(int i = 0; i < HFDL_LOOP_CH; i++) { int n = pre * HFDL_LOOP_CH + i; if(n < N) hfdl_cp_async8(&s_bank[pre][i][lane], &bank[(long long)n * 32 + lane]); }
-		{ int n = pre * HFDL_LOOP_CH + lane; if(lane < HFDL_LOOP_CH && n < N) hfdl_cp_async4(&s_lvl[pre][lane], &lvl[n]); }
-		hfdl_cp_async_commit();
-	}
-	hfdl_cp_async_wait<1>();
-	__syncwarp();
-	int chunk = 0, chunk_end = HFDL_LOOP_CH;   // chunk currently readable in s_bank[chunk & 1]
-	int k = -1;                    // last input sample consumed
-	// The loop is driven by symsync OUTPUTS (2 per 3 input samples): input samples that produce no output only
-	// tick the noise-floor clock and step the timing phase (symsync_crcf_step: tau -= 1, b -= npfb).
-	// The hot path is kept branch-poor: one output per input sample is the rule (del ~ 1.5), everything else is
-	// handled by generic, rarely taken code.
-#define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1) { if((++S.nf_clk & 0xFFu) == 0xFFu) \
-		S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } } while(0)     /* hfdl.c:700-706 */
+	if(threadIdx.x == 0) { s_head = 0; s_tail = 0; s_end_seq = 0x7fffffff; s_done = 0; s_reset_gen = 0; s_reset_k = 0; s_reset_seq = 0; s_ack_gen = 0; }
+	__syncthreads();
+
+	if(warp == 1) {
+		// =========================== timing warp (producer) ===========================
+		const cf *bank = a.bank + (long long)c * a.bank_stride * 32;
+		const cf *mfo = a.mfo + (long long)c * a.mfo_stride + HFDL_MFO_HIST;
+		const float ss_a1 = T.ss_a1, ss_a2 = T.ss_a2, ss_b0 = T.ss_b0, ss_radj = T.ss_rate_adj;
+		int chunk = 0, chunk_end = 0;       // chunk readable in s_bank[chunk & 1]; (re)primed by HFDL_STAGE
+		int k = -1;                         // last input sample consumed
+		int seq = 0;                        // sequence number of the next output
+		int my_gen = 0;
+		bool finished = false, need_stage = true;
+#define HFDL_STAGE_CHUNK(ch_, buf_) do { \
+			const int nn0_ = (ch_) * HFDL_LOOP_CH; \
+			for(int i_ = 0; i_ < HFDL_LOOP_CH; i_++) { int n_ = nn0_ + i_; if(n_ < N) hfdl_cp_async8(&s_bank[buf_][i_][lane], &bank[(long long)n_ * 32 + lane]); } \
+			{ int n_ = nn0_ + lane; if(lane < HFDL_LOOP_CH && n_ < N) hfdl_cp_async4(&s_lvl[buf_][lane], &lvl[n_]); } \
+			hfdl_cp_async_commit(); } while(0)
 #define HFDL_SS_CONSUME() do { if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++; } while(0)
-	// one symsync output at input sample k from arm b: value (scaled by 1/k_sps) and, on "ideal timing" outputs,
-	// the timing-error detector + loop filter (symsync_crcf_step / advance_internal_loop)
 #define HFDL_SS_OUTPUT(dst) do { \
-		const int bb_ = S.ss_b < 0 ? 0 : S.ss_b; \
-		cf mf_ = row[bb_]; \
-		if(S.ss_since_reset < HFDL_SS_SUB) { /* window still filling after a reset: only samples pushed since then count */ \
-			mf_ = make_float2(0.f, 0.f); \
-			const float *h_ = T.ss_mf[bb_]; \
-			for(int j_ = (int)S.ss_since_reset - 1; j_ >= 0; j_--) { cf v_ = mfo[k - j_]; mf_.x += h_[j_] * v_.x; mf_.y += h_[j_] * v_.y; } \
-		} \
-		dst = make_float2(mf_.x * 0.33333334f, mf_.y * 0.33333334f); \
-		if(S.ss_decim_counter == 2u) { \
-			S.ss_decim_counter = 0; \
-			const cf dmf_ = row[16 + bb_]; \
-			float q_ = fminf(fmaxf(mf_.x * dmf_.x + mf_.y * dmf_.y, -1.0f), 1.0f);     /* Re(conj(mf)*dmf), clipped */ \
-			S.ss_q = q_; \
-			S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0]; \
-			S.ss_v[0] = q_ - ss_a1 * S.ss_v[1] - ss_a2 * S.ss_v[2]; \
-			S.ss_q_hat = ss_b0 * S.ss_v[0]; \
-			S.ss_rate += ss_radj * S.ss_q_hat; \
-			S.ss_del = S.ss_rate + S.ss_q_hat; \
-		} \
-		S.ss_decim_counter++; \
-		S.ss_tau += S.ss_del; \
-		S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);     /* bf = tau*npfb > 0 here: == (int)roundf(bf) */ \
-	} while(0)
-	for(;;) {
-		int kn = k + 1;
-		if(S.ss_b >= HFDL_SS_NPFB) {               // input sample(s) without output: usually exactly one
-			int skip = S.ss_b >> 4;
-			if(kn + skip >= N) {                   // the rest of the batch yields no output
-				for(; kn < N; kn++) { HFDL_NF_TICK(kn); HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; }
-				break;
-			}
-			do { HFDL_NF_TICK(kn); HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; kn++; } while(--skip);
-		} else if(kn >= N) break;
-		k = kn;
-		while(k >= chunk_end) {       // move to the next staged chunk, refill the one just left
-			__syncwarp();
-			const int nn0 = (chunk + 2) * HFDL_LOOP_CH;
-			for(int i = 0; i < HFDL_LOOP_CH; i++) { int n = nn0 + i; if(n < N) hfdl_cp_async8(&s_bank[chunk & 1][i][lane], &bank[(long long)n * 32 + lane]); }
-			{ int n = nn0 + lane; if(lane < HFDL_LOOP_CH && n < N) hfdl_cp_async4(&s_lvl[chunk & 1][lane], &lvl[n]); }
-			hfdl_cp_async_commit();
-			hfdl_cp_async_wait<1>();
-			__syncwarp();
-			chunk++; chunk_end += HFDL_LOOP_CH;
-		}
-		const int ii = k - (chunk_end - HFDL_LOOP_CH);
-		const cf *row = s_bank[chunk & 1][ii];
-		const float level = s_lvl[chunk & 1][ii];           // 1/g after this sample's AGC update
-		HFDL_NF_TICK(k);
-		// ---- symsync_crcf_step (push happened in bank_kernel; the reset only clears the mf-arm window)
-		HFDL_SS_CONSUME();
-		cf sym0, sym1 = make_float2(0.f, 0.f);
-		int produced = 1;
-		HFDL_SS_OUTPUT(sym0);
-		if(S.ss_b < HFDL_SS_NPFB) {                // a second (third, ...) output of the same input sample: del < 1, rare
-			HFDL_SS_OUTPUT(sym1);
-			produced = 2;
-			while(S.ss_b < HFDL_SS_NPFB) { cf drop; HFDL_SS_OUTPUT(drop); (void)drop; }
-		}
-		S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
-
-		for(int i = 0; i < produced; i++, S.symsync_out_idx++) {
-			// ---- Costas step + rotate (hfdl.c:250-294,709-715)
-			S.c_phi += S.c_dphi;
-			// (double)phi > M_PI  <=>  phi > 3.1415925f (largest float below pi); 2*pi split hi+lo
-			{
-				const float dn = (S.c_phi - 6.2831855f) + 1.7484555e-7f, up = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
-				S.c_phi = S.c_phi > 3.1415925f ? dn : (S.c_phi < -3.1415925f ? up : S.c_phi);
-			}
-			float sn, cs;
-			hfdl_sincos_fast(S.c_phi, &sn, &cs);
-			const cf so = (i == 0) ? sym0 : sym1;
-			cf r = make_float2(so.x * cs + so.y * sn, so.y * cs - so.x * sn);
-			if(S.fr_state == HF_A1 && fabsf(S.c_dphi) > 0.25f) {
-				S.c_phi = S.c_dphi = 0.f;
+			const int bb_ = S.ss_b < 0 ? 0 : S.ss_b; \
+			cf mf_ = row[bb_]; \
+			if(S.ss_since_reset < HFDL_SS_SUB) { /* window still filling after a reset: only samples pushed since then count */ \
+				mf_ = make_float2(0.f, 0.f); \
+				const float *h_ = T.ss_mf[bb_]; \
+				for(int j_ = (int)S.ss_since_reset - 1; j_ >= 0; j_--) { cf v_ = mfo[k - j_]; mf_.x += h_[j_] * v_.x; mf_.y += h_[j_] * v_.y; } \
+			} \
+			dst = make_float2(mf_.x * 0.33333334f, mf_.y * 0.33333334f);      /* output scaled by 1/k, k = 3 samples/symbol */ \
+			if(S.ss_decim_counter == 2u) { \
+				S.ss_decim_counter = 0; \
+				const cf dmf_ = row[16 + bb_]; \
+				float q_ = fminf(fmaxf(mf_.x * dmf_.x + mf_.y * dmf_.y, -1.0f), 1.0f);     /* Re(conj(mf)*dmf), clipped */ \
+				S.ss_q = q_; \
+				S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0]; \
+				S.ss_v[0] = q_ - ss_a1 * S.ss_v[1] - ss_a2 * S.ss_v[2]; \
+				S.ss_q_hat = ss_b0 * S.ss_v[0]; \
+				S.ss_rate += ss_radj * S.ss_q_hat; \
+				S.ss_del = S.ss_rate + S.ss_q_hat; \
+			} \
+			S.ss_decim_counter++; \
+			S.ss_tau += S.ss_del; \
+			S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);     /* bf = tau*npfb > 0 here: == (int)roundf(bf) */ \
+		} while(0)
+		for(;;) {
+			const int p_gen = HFDL_UNI(s_reset_gen), p_tail = HFDL_UNI(s_tail), p_done = HFDL_UNI(s_done);
+			if(p_gen != my_gen) {            // symsync_crcf_reset posted by the demodulator warp: roll back
+				my_gen = p_gen;
+				__threadfence_block();
+				k = HFDL_UNI(s_reset_k); seq = HFDL_UNI(s_reset_seq);
 				ss_reset(S);
+				finished = false; need_stage = true;
+				__syncwarp();
+				if(lane == 0) { s_end_seq = 0x7fffffff; s_head = seq; __threadfence_block(); s_ack_gen = my_gen; }
+				continue;
 			}
-			// ---- eqlms_cccf_push (mirrored ring: slot w and w+16 hold the same element, so the 15-element
-			//      window is always the contiguous run [ep, ep+14])
-			{
-				const int wp = (E.ep + 15) & 15;
-				float x2n = r.x * r.x + r.y * r.y, x20 = E.x2[EQS(E.ep)];
-				E.win[EQS(wp)] = r;
-				E.win[EQS(wp + 16)] = r;
-				E.x2[EQS(wp)] = x2n;
-				E.ep = (E.ep + 1) & 15;
-				S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
-				S.eq_count++;
+			if(finished) { if(p_done) break; HFDL_SPIN_PAUSE(); continue; }
+			if(seq - p_tail >= HFDL_RING - 2) { HFDL_SPIN_PAUSE(); continue; }      // ring full: wait (keeps polling for resets)
+			int kn = k + 1;
+			if(S.ss_b >= HFDL_SS_NPFB) {               // input sample(s) without output: usually exactly one
+				int skip = S.ss_b >> 4;
+				if(kn + skip >= N) {                   // the rest of the batch yields no output
+					for(; kn < N; kn++) { HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; }
+					k = N - 1; finished = true;
+					__syncwarp();
+					if(lane == 0) { __threadfence_block(); s_end_seq = seq; }
+					continue;
+				}
+				do { HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; kn++; } while(--skip);
+			} else if(kn >= N) {
+				finished = true;
+				__syncwarp();
+				if(lane == 0) { __threadfence_block(); s_end_seq = seq; }
+				continue;
 			}
-			if(!(S.symsync_out_idx & 1u)) continue;
-			// ---- eqlms_cccf_execute: y = sum conj(w[i]) * x[i]
-			cf s = make_float2(0.f, 0.f);
-			cf wv[HFDL_EQ_LEN];
-			{
-				const cf *wb = E.win + EQS(E.ep);
-#pragma unroll
-				for(int j = 0; j < HFDL_EQ_LEN - 1; j++) wv[j] = wb[EQS(j)];
-				wv[HFDL_EQ_LEN - 1] = r;
-				cf s2 = make_float2(0.f, 0.f);          // two accumulator pairs shorten the dependent FMA chain
-#pragma unroll
-				for(int j = 0; j < HFDL_EQ_LEN; j++) {
-					cf w = S.eq_w[j], v = wv[j];
-					if(j & 1) { s2.x = fmaf(w.x, v.x, fmaf(w.y, v.y, s2.x)); s2.y = fmaf(w.x, v.y, fmaf(-w.y, v.x, s2.y)); }
-					else { s.x = fmaf(w.x, v.x, fmaf(w.y, v.y, s.x)); s.y = fmaf(w.x, v.y, fmaf(-w.y, v.x, s.y)); }
-				}
-				s.x += s2.x; s.y += s2.y;
+			k = kn;
+			if(need_stage) {                           // (re)prime the two staging buffers at the chunk of sample k
+				hfdl_cp_async_wait<0>();
+				__syncwarp();
+				chunk = k / HFDL_LOOP_CH; chunk_end = (chunk + 1) * HFDL_LOOP_CH;
+				HFDL_STAGE_CHUNK(chunk, chunk & 1);
+				HFDL_STAGE_CHUNK(chunk + 1, (chunk + 1) & 1);
+				hfdl_cp_async_wait<1>();
+				__syncwarp();
+				need_stage = false;
 			}
-			if(S.fr_state == HF_EQ_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
-				float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
-				if(S.bitmask & 1u) d = -d;
-				bool run = true;
-				if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
-				if(run) {
-					const float inv = 1.0f / S.eq_x2_sum;
-					cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);      // mu * conj(d - d_hat) / sum|x|^2, mu = 0.1 (hfdl.c:496)
-#pragma unroll
-					for(int j = 0; j < HFDL_EQ_LEN; j++) {
-						cf uu = cmul(t, wv[j]);
-						S.eq_w[j].x += uu.x;
-						S.eq_w[j].y += uu.y;
-					}
-				}
-				S.T_idx++;
+			while(k >= chunk_end) {                    // move to the next staged chunk, refill the one just left
+				__syncwarp();
+				HFDL_STAGE_CHUNK(chunk + 2, chunk & 1);
+				hfdl_cp_async_wait<1>();
+				__syncwarp();
+				chunk++; chunk_end += HFDL_LOOP_CH;
 			}
-			if(cap && lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s;
-			if(cap) cap_n_eq++;
-			cf x_hat;
-			unsigned bits = modem_demod(S.cur_arity, s, T, &x_hat);
-			// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
-			float err = s.y * x_hat.x - s.x * x_hat.y;
-			err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
-			S.c_phi += 0.1f * err;
-			S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
-
-			symcnt++;
-			if(S.fr_state == HF_A1 && symcnt >= 13u * HFDL_SINGLE_SLOT_FRAME_LEN) {
-				symcnt = 0;
-				S.c_phi = S.c_dphi = 0.f;
-				ss_reset(S);
+			const int ii = k - (chunk_end - HFDL_LOOP_CH);
+			const cf *row = s_bank[chunk & 1][ii];
+			const float level = s_lvl[chunk & 1][ii];           // 1/g after this sample's AGC update
+			HFDL_SS_CONSUME();                       // the push itself happened in bank_kernel
+			cf sym0, sym1 = make_float2(0.f, 0.f);
+			int produced = 1;
+			HFDL_SS_OUTPUT(sym0);
+			if(S.ss_b < HFDL_SS_NPFB) {                // further outputs of the same input sample: del < 1, rare
+				HFDL_SS_OUTPUT(sym1);
+				produced = 2;
+				while(S.ss_b < HFDL_SS_NPFB) { cf drop; HFDL_SS_OUTPUT(drop); (void)drop; }
 			}
-			if(S.s_state == HS_EMIT_BITS) {
-				bits ^= S.bitmask;
-				for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
-			} else if(S.s_state == HS_EMIT_SYMBOLS) {
-				if(S.cur_buf == 0) {
-					if(S.training_n < HFDL_T_LEN) { s_train[EQS(S.training_n)] = s; S.training_n++; }
-				} else {
-					if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
-				}
-			}
-			if(S.fr_state > HF_A1) {
-				S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + level, S.frame_symbol_cnt + 1.0f);
-				S.frame_symbol_cnt += 1.0f;
-			}
-			if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }
-
-			switch(S.fr_state) {
-			case HF_A1: {
-				float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
-				if(fabsf(corr) > 0.36f) {
-					S.st_a1++;
-					S.bitmask = corr > 0.f ? 0u : ~0u;
-					S.signal_level = level;
-					S.frame_symbol_cnt = 1.0f;
-					S.symbols_wanted = HFDL_A_LEN;
-					S.search_retries = 0;
-					S.fr_state = HF_A2;
-				}
-				break; }
-			case HF_A2: {
-				float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
-				if(fabsf(corr) > 0.3f) {
-					S.a2_sample_cnt = cnt_base + (unsigned long long)k;
-					S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
-					S.st_a2++;
-					S.symbols_wanted = 127;
-					S.search_retries = 0;
-					S.fr_state = HF_M1;
-				} else if(++S.search_retries >= 3) {
-					framer_reset(S, T, E);
-				}
-				break; }
-			case HF_M1: {
-				float max_corr = 0.f; int max_idx = -1;
-				for(int idx = 0; idx < 8; idx++) {
-					float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
-					if(corr > max_corr) { max_corr = corr; max_idx = idx; }
-				}
-				if(max_corr > 0.3f) {
-					S.st_m1++;
-					S.data_segment_cnt = T.mode_segments[max_idx];
-					S.data_arity = T.mode_arity[max_idx];
-					S.M1 = max_idx;
-					S.symbols_wanted = 15;
-					S.search_retries = 0;
-					S.fr_state = HF_M2_SKIP;
-					S.s_state = HS_SKIP;
-				} else {
-					framer_reset(S, T, E);
-				}
-				break; }
-			case HF_M2_SKIP:
-				S.training_n = 0;
-				S.symbols_wanted = HFDL_T_LEN;
-				S.eq_train_seq_cnt = 9;
-				S.fr_state = HF_EQ_TRAIN;
-				S.s_state = HS_EMIT_SYMBOLS;
-				break;
-			case HF_EQ_TRAIN: {
-				unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
-#pragma unroll
-				for(int j = 0; j < HFDL_T_LEN; j++) {
-					unsigned bit = (s_train[EQS(j)].x > 0.f) ? 0u : 1u;
-					bit ^= (S.bitmask & 1u);
-					tseq = (tseq << 1) | bit;
-				}
-				S.train_bits_total += HFDL_T_LEN;
-				S.train_bits_bad += __popc(0x9AFu ^ tseq);
-				S.training_n = 0;
-				if(S.eq_train_seq_cnt > 1) {
-					S.eq_train_seq_cnt--;
-					S.symbols_wanted = HFDL_T_LEN;
-					S.T_idx = 0;
-				} else if(S.data_segment_cnt > 0) {
-					S.symbols_wanted = 15;
-					S.fr_state = HF_DATA_1;
-					S.cur_arity = S.data_arity;
-					S.cur_buf = 1;
-				} else {                                 // end of frame: hand the symbols to fec_kernel
-					int q = 0;
-					if(lane == 0) q = atomicAdd(a.nframes, 1);
-					q = __shfl_sync(0xffffffffu, q, 0);
-					if(q < a.max_frames && lane == 0) {
-						FrameRec fr;
-						fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
-						fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
-						fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = cnt_base + (unsigned long long)k;
-						fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
-						a.frames[q] = fr;
-					}
-					S.st_frames++;
-					S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
-					dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
-					framer_reset(S, T, E);
-					symcnt = 0;
-				}
-				break; }
-			case HF_DATA_1:
-				S.symbols_wanted = 15;
-				S.fr_state = HF_DATA_2;
-				break;
-			case HF_DATA_2:
-				S.data_segment_cnt--;
-				S.cur_arity = 1;
-				S.cur_buf = 0;
-				S.fr_state = HF_EQ_TRAIN;
-				S.eq_train_seq_cnt = 1;
-				S.symbols_wanted = HFDL_T_LEN;
-				S.T_idx = 0;
-				break;
-			}
+			S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
+			// all outputs of one input sample are published together
+			s_ring[seq & (HFDL_RING - 1)] = make_float4(sym0.x, sym0.y, level, __int_as_float(k));
+			if(produced == 2) s_ring[(seq + 1) & (HFDL_RING - 1)] = make_float4(sym1.x, sym1.y, level, __int_as_float(k));
+			seq += produced;
+			__threadfence_block();
+			__syncwarp();
+			if(lane == 0) s_head = seq;
 		}
-	}
-#undef HFDL_NF_TICK
+#undef HFDL_STAGE_CHUNK
 #undef HFDL_SS_CONSUME
 #undef HFDL_SS_OUTPUT
-	S.sample_cnt = cnt_base + (unsigned long long)N;
-	S.symbol_cnt = symcnt;
-	hfdl_cp_async_wait<0>();
-	__syncwarp();
-	if(lane == 0) {
-		for(int j = 0; j < HFDL_EQ_LEN; j++) { S.eq_win[j] = E.win[EQS(E.ep + j)]; S.eq_x2[j] = E.x2[EQS((E.ep + j) & 15)]; }
-		for(int j = 0; j < HFDL_T_LEN; j++) S.training[j] = s_train[EQS(j)];
-		a.state[c] = S;
-		if(cap) a.cap_cnt[1] = cap_n_eq;
+		hfdl_cp_async_wait<0>();
+	} else {
+		// =========================== demodulator warp (consumer) ===========================
+		const bool cap = (c == a.cap_channel);
+		int cap_n_eq = cap ? a.cap_cnt[1] : 0;
+		cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+		const unsigned long long cnt_base = S.sample_cnt;
+		unsigned symcnt = (unsigned)S.symbol_cnt;
+		unsigned A_bits[4];
+#pragma unroll
+		for(int i = 0; i < 4; i++) A_bits[i] = T.A_bits[i];
+		EqRing E;
+		E.win = s_eqwin + lane; E.x2 = s_eqx2 + lane; E.ep = 0;
+		cf *s_train = s_train_all + lane;
+		for(int j = 0; j < 16; j++) {
+			cf v = j < HFDL_EQ_LEN ? a.state[c].eq_win[j] : make_float2(0.f, 0.f);
+			E.win[EQS(j)] = v; E.win[EQS(j + 16)] = v;
+			E.x2[EQS(j)] = j < HFDL_EQ_LEN ? a.state[c].eq_x2[j] : 0.f;
+			s_train[EQS(j)] = j < HFDL_T_LEN ? a.state[c].training[j] : make_float2(0.f, 0.f);
+		}
+#define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1) { if((++S.nf_clk & 0xFFu) == 0xFFu) \
+			S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } } while(0)     /* hfdl.c:700-706 */
+		int seq = 0, k_prev = -1, gen = 0, wait_seq = 0x7fffffff;
+		for(;;) {
+			if(seq >= wait_seq) {                      // outputs from here on must come from the re-started timing loop
+				while(HFDL_UNI(s_ack_gen) != gen) { HFDL_SPIN_PAUSE(); }
+				__threadfence_block();
+				wait_seq = 0x7fffffff;
+			}
+			int c_head = HFDL_UNI(s_head);
+			while(c_head <= seq && seq < HFDL_UNI(s_end_seq)) { HFDL_SPIN_PAUSE(); c_head = HFDL_UNI(s_head); }
+			__threadfence_block();
+			if(c_head <= seq) break;                   // end of batch: every output consumed
+			const float4 ent = s_ring[seq & (HFDL_RING - 1)];
+			const int k = __float_as_int(ent.w);
+			const float level = ent.z;
+			// noise-floor clock ticks once per input sample, before that sample's outputs (hfdl.c:700)
+			for(int sidx = k_prev + 1; sidx <= k; sidx++) HFDL_NF_TICK(sidx);
+			k_prev = k;
+			bool reset_req = false;
+			for(int i = 0; i < 1; i++, S.symsync_out_idx++) {
+				// ---- Costas step + rotate (hfdl.c:250-294,709-715)
+				S.c_phi += S.c_dphi;
+				// (double)phi > M_PI  <=>  phi > 3.1415925f (largest float below pi); 2*pi split hi+lo
+				{
+					const float dn = (S.c_phi - 6.2831855f) + 1.7484555e-7f, up = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
+					S.c_phi = S.c_phi > 3.1415925f ? dn : (S.c_phi < -3.1415925f ? up : S.c_phi);
+				}
+				float sn, cs;
+				hfdl_sincos_fast(S.c_phi, &sn, &cs);
+				const cf so = make_float2(ent.x, ent.y);
+				cf r = make_float2(so.x * cs + so.y * sn, so.y * cs - so.x * sn);
+				if(S.fr_state == HF_A1 && fabsf(S.c_dphi) > 0.25f) {
+					S.c_phi = S.c_dphi = 0.f;
+					{ ss_reset(S); reset_req = true; }
+				}
+				// ---- eqlms_cccf_push (mirrored ring: slot w and w+16 hold the same element, so the 15-element
+				//      window is always the contiguous run [ep, ep+14])
+				{
+					const int wp = (E.ep + 15) & 15;
+					float x2n = r.x * r.x + r.y * r.y, x20 = E.x2[EQS(E.ep)];
+					E.win[EQS(wp)] = r;
+					E.win[EQS(wp + 16)] = r;
+					E.x2[EQS(wp)] = x2n;
+					E.ep = (E.ep + 1) & 15;
+					S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
+					S.eq_count++;
+				}
+				if(!(S.symsync_out_idx & 1u)) continue;
+				// ---- eqlms_cccf_execute: y = sum conj(w[i]) * x[i]
+				cf s = make_float2(0.f, 0.f);
+				cf wv[HFDL_EQ_LEN];
+				{
+					const cf *wb = E.win + EQS(E.ep);
+	#pragma unroll
+					for(int j = 0; j < HFDL_EQ_LEN - 1; j++) wv[j] = wb[EQS(j)];
+					wv[HFDL_EQ_LEN - 1] = r;
+					cf s2 = make_float2(0.f, 0.f);          // two accumulator pairs shorten the dependent FMA chain
+	#pragma unroll
+					for(int j = 0; j < HFDL_EQ_LEN; j++) {
+						cf w = S.eq_w[j], v = wv[j];
+						if(j & 1) { s2.x = fmaf(w.x, v.x, fmaf(w.y, v.y, s2.x)); s2.y = fmaf(w.x, v.y, fmaf(-w.y, v.x, s2.y)); }
+						else { s.x = fmaf(w.x, v.x, fmaf(w.y, v.y, s.x)); s.y = fmaf(w.x, v.y, fmaf(-w.y, v.x, s.y)); }
+					}
+					s.x += s2.x; s.y += s2.y;
+				}
+				if(S.fr_state == HF_EQ_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
+					float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
+					if(S.bitmask & 1u) d = -d;
+					bool run = true;
+					if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
+					if(run) {
+						const float inv = 1.0f / S.eq_x2_sum;
+						cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);      // mu * conj(d - d_hat) / sum|x|^2, mu = 0.1 (hfdl.c:496)
+	#pragma unroll
+						for(int j = 0; j < HFDL_EQ_LEN; j++) {
+							cf uu = cmul(t, wv[j]);
+							S.eq_w[j].x += uu.x;
+							S.eq_w[j].y += uu.y;
+						}
+					}
+					S.T_idx++;
+				}
+				if(cap && lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s;
+				if(cap) cap_n_eq++;
+				cf x_hat;
+				unsigned bits = modem_demod(S.cur_arity, s, T, &x_hat);
+				// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
+				float err = s.y * x_hat.x - s.x * x_hat.y;
+				err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
+				S.c_phi += 0.1f * err;
+				S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
+
+				symcnt++;
+				if(S.fr_state == HF_A1 && symcnt >= 13u * HFDL_SINGLE_SLOT_FRAME_LEN) {
+					symcnt = 0;
+					S.c_phi = S.c_dphi = 0.f;
+					{ ss_reset(S); reset_req = true; }
+				}
+				if(S.s_state == HS_EMIT_BITS) {
+					bits ^= S.bitmask;
+					for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
+				} else if(S.s_state == HS_EMIT_SYMBOLS) {
+					if(S.cur_buf == 0) {
+						if(S.training_n < HFDL_T_LEN) { s_train[EQS(S.training_n)] = s; S.training_n++; }
+					} else {
+						if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
+					}
+				}
+				if(S.fr_state > HF_A1) {
+					S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + level, S.frame_symbol_cnt + 1.0f);
+					S.frame_symbol_cnt += 1.0f;
+				}
+				if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }
+
+				switch(S.fr_state) {
+				case HF_A1: {
+					float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+					if(fabsf(corr) > 0.36f) {
+						S.st_a1++;
+						S.bitmask = corr > 0.f ? 0u : ~0u;
+						S.signal_level = level;
+						S.frame_symbol_cnt = 1.0f;
+						S.symbols_wanted = HFDL_A_LEN;
+						S.search_retries = 0;
+						S.fr_state = HF_A2;
+					}
+					break; }
+				case HF_A2: {
+					float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+					if(fabsf(corr) > 0.3f) {
+						S.a2_sample_cnt = cnt_base + (unsigned long long)k;
+						S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
+						S.st_a2++;
+						S.symbols_wanted = 127;
+						S.search_retries = 0;
+						S.fr_state = HF_M1;
+					} else if(++S.search_retries >= 3) {
+						{ framer_reset(S, T, E); reset_req = true; }
+					}
+					break; }
+				case HF_M1: {
+					float max_corr = 0.f; int max_idx = -1;
+					for(int idx = 0; idx < 8; idx++) {
+						float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
+						if(corr > max_corr) { max_corr = corr; max_idx = idx; }
+					}
+					if(max_corr > 0.3f) {
+						S.st_m1++;
+						S.data_segment_cnt = T.mode_segments[max_idx];
+						S.data_arity = T.mode_arity[max_idx];
+						S.M1 = max_idx;
+						S.symbols_wanted = 15;
+						S.search_retries = 0;
+						S.fr_state = HF_M2_SKIP;
+						S.s_state = HS_SKIP;
+					} else {
+						{ framer_reset(S, T, E); reset_req = true; }
+					}
+					break; }
+				case HF_M2_SKIP:
+					S.training_n = 0;
+					S.symbols_wanted = HFDL_T_LEN;
+					S.eq_train_seq_cnt = 9;
+					S.fr_state = HF_EQ_TRAIN;
+					S.s_state = HS_EMIT_SYMBOLS;
+					break;
+				case HF_EQ_TRAIN: {
+					unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
+	#pragma unroll
+					for(int j = 0; j < HFDL_T_LEN; j++) {
+						unsigned bit = (s_train[EQS(j)].x > 0.f) ? 0u : 1u;
+						bit ^= (S.bitmask & 1u);
+						tseq = (tseq << 1) | bit;
+					}
+					S.train_bits_total += HFDL_T_LEN;
+					S.train_bits_bad += __popc(0x9AFu ^ tseq);
+					S.training_n = 0;
+					if(S.eq_train_seq_cnt > 1) {
+						S.eq_train_seq_cnt--;
+						S.symbols_wanted = HFDL_T_LEN;
+						S.T_idx = 0;
+					} else if(S.data_segment_cnt > 0) {
+						S.symbols_wanted = 15;
+						S.fr_state = HF_DATA_1;
+						S.cur_arity = S.data_arity;
+						S.cur_buf = 1;
+					} else {                                 // end of frame: hand the symbols to fec_kernel
+						int q = 0;
+						if(lane == 0) q = atomicAdd(a.nframes, 1);
+						q = __shfl_sync(0xffffffffu, q, 0);
+						if(q < a.max_frames && lane == 0) {
+							FrameRec fr;
+							fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
+							fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
+							fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = cnt_base + (unsigned long long)k;
+							fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
+							a.frames[q] = fr;
+						}
+						S.st_frames++;
+						S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
+						dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+						{ framer_reset(S, T, E); reset_req = true; }
+						symcnt = 0;
+					}
+					break; }
+				case HF_DATA_1:
+					S.symbols_wanted = 15;
+					S.fr_state = HF_DATA_2;
+					break;
+				case HF_DATA_2:
+					S.data_segment_cnt--;
+					S.cur_arity = 1;
+					S.cur_buf = 0;
+					S.fr_state = HF_EQ_TRAIN;
+					S.eq_train_seq_cnt = 1;
+					S.symbols_wanted = HFDL_T_LEN;
+					S.T_idx = 0;
+					break;
+				}
+			}
+
+			if(reset_req) {
+				// symsync_crcf_reset happened while processing output seq (input sample k): outputs of the same
+				// input sample already produced keep their (old-state) value, the timing warp restarts after them
+				int e2 = seq;
+				while(e2 + 1 < c_head && __float_as_int(s_ring[(e2 + 1) & (HFDL_RING - 1)].w) == k) e2++;
+				__syncwarp();
+				gen++;
+				if(lane == 0) { s_reset_k = k; s_reset_seq = e2 + 1; __threadfence_block(); s_reset_gen = gen; }
+				wait_seq = e2 + 1;
+			}
+			seq++;
+			__syncwarp();
+			if(lane == 0) s_tail = seq;
+		}
+		for(int sidx = k_prev + 1; sidx < N; sidx++) HFDL_NF_TICK(sidx);      // input samples after the last output
+#undef HFDL_NF_TICK
+		S.sample_cnt = cnt_base + (unsigned long long)N;
+		S.symbol_cnt = symcnt;
+		__syncwarp();
+		if(lane == 0) {
+			for(int j = 0; j < HFDL_EQ_LEN; j++) { S.eq_win[j] = E.win[EQS(E.ep + j)]; S.eq_x2[j] = E.x2[EQS((E.ep + j) & 15)]; }
+			for(int j = 0; j < HFDL_T_LEN; j++) S.training[j] = s_train[EQS(j)];
+			// everything except the timing-loop fields, which the timing warp owns
+			DemodState *G = &a.state[c];
+			DemodState O = *G;
+			S.ss_since_reset = O.ss_since_reset; S.ss_decim_counter = O.ss_decim_counter; S.ss_rate = O.ss_rate; S.ss_del = O.ss_del;
+			S.ss_tau = O.ss_tau; S.ss_bf = O.ss_bf; S.ss_q = O.ss_q; S.ss_q_hat = O.ss_q_hat; S.ss_b = O.ss_b;
+			S.ss_v[0] = O.ss_v[0]; S.ss_v[1] = O.ss_v[1]; S.ss_v[2] = O.ss_v[2];
+			*G = S;
+			if(cap) a.cap_cnt[1] = cap_n_eq;
+			__threadfence_block();
+			s_done = 1;
+		}
+	}
+	__syncthreads();
+	if(warp == 1 && lane == 0) {       // timing-loop state after the last input sample of the batch
+		DemodState *G = &a.state[c];
+		G->ss_since_reset = S.ss_since_reset; G->ss_decim_counter = S.ss_decim_counter; G->ss_rate = S.ss_rate; G->ss_del = S.ss_del;
+		G->ss_tau = S.ss_tau; G->ss_bf = 0.f; G->ss_q = S.ss_q; G->ss_q_hat = S.ss_q_hat; G->ss_b = S.ss_b;
+		G->ss_v[0] = S.ss_v[0]; G->ss_v[1] = S.ss_v[1]; G->ss_v[2] = S.ss_v[2];
 	}
 }
 
