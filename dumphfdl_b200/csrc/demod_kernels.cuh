@@ -297,6 +297,119 @@ __device__ __forceinline__ unsigned modem_demod(int m, cf x, const DemodTables &
 	return sym;
 }
 
+// branch layout hints: on a lone warp every TAKEN branch costs a fetch bubble, so rare paths go out of line
+#define HFDL_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define HFDL_LIKELY(x) __builtin_expect(!!(x), 1)
+
+// ---- fast in-frame runs -------------------------------------------------------------------------------------
+// Between two framer events the framer only counts symbols down (hfdl.c:774-777) and, inside a frame, neither the
+// noise-floor clock nor any loop reset can fire (both need FRAMER_A1_SEARCH).  demod_run() therefore processes
+// `nsym` whole symbols (an even + an odd symsync output each) as straight-line code specialised on the sampler
+// mode and the modulation, and hands control back to the generic per-output path for the symbol that triggers
+// the next framer event.  Arithmetic is expression-for-expression the same as in the generic path.
+enum { RUN_BITS = 0, RUN_TRAIN = 1, RUN_DATA = 2, RUN_SKIP = 3 };
+
+__device__ __forceinline__ cf costas_rotate_push(DemodState &S, EqRing &E, cf so) {
+	S.c_phi += S.c_dphi;
+	{
+		const float dn = (S.c_phi - 6.2831855f) + 1.7484555e-7f, up = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
+		S.c_phi = S.c_phi > 3.1415925f ? dn : (S.c_phi < -3.1415925f ? up : S.c_phi);
+	}
+	float sn, cs;
+	hfdl_sincos_fast(S.c_phi, &sn, &cs);
+	cf r = make_float2(so.x * cs + so.y * sn, so.y * cs - so.x * sn);
+	const int wp = (E.ep + 15) & 15;
+	float x2n = r.x * r.x + r.y * r.y, x20 = E.x2[EQS(E.ep)];
+	E.win[EQS(wp)] = r;
+	E.win[EQS(wp + 16)] = r;
+	E.x2[EQS(wp)] = x2n;
+	E.ep = (E.ep + 1) & 15;
+	S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
+	S.eq_count++;
+	return r;
+}
+
+template <int MODE, int ARITY>
+__device__ __forceinline__ int demod_run(DemodState &S, EqRing &E, const DemodTables &T, const float4 *ring,
+		volatile int *p_head, volatile int *p_end, volatile int *p_tail, int &seq, int &k_prev, int nsym,
+		cf *s_train, cf *dsym, int lane, unsigned &symcnt) {
+	int done = 0;
+	int c_head = __shfl_sync(0xffffffffu, (int)*p_head, 0);
+	while(done < nsym) {
+		if(HFDL_UNLIKELY(c_head - seq < 2)) {
+			c_head = __shfl_sync(0xffffffffu, (int)*p_head, 0);
+			if(c_head - seq < 2) {
+				if(seq + 1 >= __shfl_sync(0xffffffffu, (int)*p_end, 0)) break;     // the batch ends inside this run
+				HFDL_SPIN_PAUSE();
+				continue;
+			}
+			__threadfence_block();
+		}
+		const float4 e0 = ring[seq & 63], e1 = ring[(seq + 1) & 63];
+		(void)costas_rotate_push(S, E, make_float2(e0.x, e0.y));
+		const cf r = costas_rotate_push(S, E, make_float2(e1.x, e1.y));
+		// ---- eqlms_cccf_execute
+		cf s = make_float2(0.f, 0.f);
+		cf wv[HFDL_EQ_LEN];
+		{
+			const cf *wb = E.win + EQS(E.ep);
+#pragma unroll
+			for(int j = 0; j < HFDL_EQ_LEN - 1; j++) wv[j] = wb[EQS(j)];
+			wv[HFDL_EQ_LEN - 1] = r;
+			cf s2 = make_float2(0.f, 0.f);
+#pragma unroll
+			for(int j = 0; j < HFDL_EQ_LEN; j++) {
+				cf w = S.eq_w[j], v = wv[j];
+				if(j & 1) { s2.x = fmaf(w.x, v.x, fmaf(w.y, v.y, s2.x)); s2.y = fmaf(w.x, v.y, fmaf(-w.y, v.x, s2.y)); }
+				else { s.x = fmaf(w.x, v.x, fmaf(w.y, v.y, s.x)); s.y = fmaf(w.x, v.y, fmaf(-w.y, v.x, s.y)); }
+			}
+			s.x += s2.x; s.y += s2.y;
+		}
+		if(MODE == RUN_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
+			float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
+			if(S.bitmask & 1u) d = -d;
+			bool run = true;
+			if(HFDL_UNLIKELY(!S.eq_buf_full)) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
+			if(run) {
+				const float inv = 1.0f / S.eq_x2_sum;
+				cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);
+#pragma unroll
+				for(int j = 0; j < HFDL_EQ_LEN; j++) {
+					cf uu = cmul(t, wv[j]);
+					S.eq_w[j].x += uu.x;
+					S.eq_w[j].y += uu.y;
+				}
+			}
+			S.T_idx++;
+		}
+		cf x_hat;
+		unsigned bits = modem_demod(ARITY, s, T, &x_hat);
+		float err = s.y * x_hat.x - s.x * x_hat.y;
+		err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));
+		S.c_phi += 0.1f * err;
+		S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
+		symcnt++;
+		if(MODE == RUN_BITS) {
+			bits ^= S.bitmask;
+			bits_push(S.bits, bits);
+		} else if(MODE == RUN_TRAIN) {
+			if(S.training_n < HFDL_T_LEN) { s_train[EQS(S.training_n)] = s; S.training_n++; }
+		} else if(MODE == RUN_DATA) {
+			if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
+		}
+		S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + e1.z, S.frame_symbol_cnt + 1.0f);
+		S.frame_symbol_cnt += 1.0f;
+		k_prev = __float_as_int(e1.w);
+		seq += 2;
+		S.symsync_out_idx += 2;
+		done++;
+		__syncwarp();
+		if(lane == 0) *p_tail = seq;
+	}
+	S.symbols_wanted -= done;
+	return done;
+}
+
 #define HFDL_RING 64           // symsync outputs the timing warp may run ahead of the demodulator warp
 // a value polled from shared memory is made warp-uniform (lane 0's view) so that every lane takes the same branch
 #define HFDL_UNI(v) __shfl_sync(0xffffffffu, (int)(v), 0)
@@ -346,7 +459,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 #define HFDL_SS_OUTPUT(dst) do { \
 			const int bb_ = S.ss_b < 0 ? 0 : S.ss_b; \
 			cf mf_ = row[bb_]; \
-			if(S.ss_since_reset < HFDL_SS_SUB) { /* window still filling after a reset: only samples pushed since then count */ \
+			if(HFDL_UNLIKELY(S.ss_since_reset < HFDL_SS_SUB)) { /* window still filling after a reset: only samples pushed since then count */ \
 				mf_ = make_float2(0.f, 0.f); \
 				const float *h_ = T.ss_mf[bb_]; \
 				for(int j_ = (int)S.ss_since_reset - 1; j_ >= 0; j_--) { cf v_ = mfo[k - j_]; mf_.x += h_[j_] * v_.x; mf_.y += h_[j_] * v_.y; } \
@@ -369,7 +482,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 		} while(0)
 		for(;;) {
 			const int p_gen = HFDL_UNI(s_reset_gen), p_tail = HFDL_UNI(s_tail), p_done = HFDL_UNI(s_done);
-			if(p_gen != my_gen) {            // symsync_crcf_reset posted by the demodulator warp: roll back
+			if(HFDL_UNLIKELY(p_gen != my_gen)) {            // symsync_crcf_reset posted by the demodulator warp: roll back
 				my_gen = p_gen;
 				__threadfence_block();
 				k = HFDL_UNI(s_reset_k); seq = HFDL_UNI(s_reset_seq);
@@ -379,12 +492,12 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				if(lane == 0) { s_end_seq = 0x7fffffff; s_head = seq; __threadfence_block(); s_ack_gen = my_gen; }
 				continue;
 			}
-			if(finished) { if(p_done) break; HFDL_SPIN_PAUSE(); continue; }
+			if(HFDL_UNLIKELY(finished)) { if(p_done) break; HFDL_SPIN_PAUSE(); continue; }
 			if(seq - p_tail >= HFDL_RING - 2) { HFDL_SPIN_PAUSE(); continue; }      // ring full: wait (keeps polling for resets)
 			int kn = k + 1;
 			if(S.ss_b >= HFDL_SS_NPFB) {               // input sample(s) without output: usually exactly one
 				int skip = S.ss_b >> 4;
-				if(kn + skip >= N) {                   // the rest of the batch yields no output
+				if(HFDL_UNLIKELY(kn + skip >= N)) {                   // the rest of the batch yields no output
 					for(; kn < N; kn++) { HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; }
 					k = N - 1; finished = true;
 					__syncwarp();
@@ -392,14 +505,14 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 					continue;
 				}
 				do { HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; kn++; } while(--skip);
-			} else if(kn >= N) {
+			} else if(HFDL_UNLIKELY(kn >= N)) {
 				finished = true;
 				__syncwarp();
 				if(lane == 0) { __threadfence_block(); s_end_seq = seq; }
 				continue;
 			}
 			k = kn;
-			if(need_stage) {                           // (re)prime the two staging buffers at the chunk of sample k
+			if(HFDL_UNLIKELY(need_stage)) {                           // (re)prime the two staging buffers at the chunk of sample k
 				hfdl_cp_async_wait<0>();
 				__syncwarp();
 				chunk = k / HFDL_LOOP_CH; chunk_end = (chunk + 1) * HFDL_LOOP_CH;
@@ -409,7 +522,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				__syncwarp();
 				need_stage = false;
 			}
-			while(k >= chunk_end) {                    // move to the next staged chunk, refill the one just left
+			while(HFDL_UNLIKELY(k >= chunk_end)) {                    // move to the next staged chunk, refill the one just left
 				__syncwarp();
 				HFDL_STAGE_CHUNK(chunk + 2, chunk & 1);
 				hfdl_cp_async_wait<1>();
@@ -423,7 +536,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 			cf sym0, sym1 = make_float2(0.f, 0.f);
 			int produced = 1;
 			HFDL_SS_OUTPUT(sym0);
-			if(S.ss_b < HFDL_SS_NPFB) {                // further outputs of the same input sample: del < 1, rare
+			if(HFDL_UNLIKELY(S.ss_b < HFDL_SS_NPFB)) {                // further outputs of the same input sample: del < 1, rare
 				HFDL_SS_OUTPUT(sym1);
 				produced = 2;
 				while(S.ss_b < HFDL_SS_NPFB) { cf drop; HFDL_SS_OUTPUT(drop); (void)drop; }
@@ -464,20 +577,33 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 			S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } } while(0)     /* hfdl.c:700-706 */
 		int seq = 0, k_prev = -1, gen = 0, wait_seq = 0x7fffffff;
 		for(;;) {
-			if(seq >= wait_seq) {                      // outputs from here on must come from the re-started timing loop
+			if(HFDL_UNLIKELY(seq >= wait_seq)) {                      // outputs from here on must come from the re-started timing loop
 				while(HFDL_UNI(s_ack_gen) != gen) { HFDL_SPIN_PAUSE(); }
 				__threadfence_block();
 				wait_seq = 0x7fffffff;
 			}
+			// fast path: a run of whole symbols up to (not including) the symbol of the next framer event
+			if(!cap && S.fr_state > HF_A1 && S.symbols_wanted > 1 && !(S.symsync_out_idx & 1u) && wait_seq == 0x7fffffff) {
+				const int nsym = S.symbols_wanted - 1;
+				int did;
+				const float4 *rg = s_ring;
+				if(S.s_state == HS_EMIT_BITS) did = demod_run<RUN_BITS, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
+				else if(S.s_state == HS_SKIP) did = demod_run<RUN_SKIP, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
+				else if(S.cur_buf == 0) did = demod_run<RUN_TRAIN, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
+				else if(S.cur_arity == 1) did = demod_run<RUN_DATA, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
+				else if(S.cur_arity == 2) did = demod_run<RUN_DATA, 2>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
+				else did = demod_run<RUN_DATA, 3>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
+				if(did > 0) continue;
+			}
 			int c_head = HFDL_UNI(s_head);
-			while(c_head <= seq && seq < HFDL_UNI(s_end_seq)) { HFDL_SPIN_PAUSE(); c_head = HFDL_UNI(s_head); }
+			while(HFDL_UNLIKELY(c_head <= seq) && seq < HFDL_UNI(s_end_seq)) { HFDL_SPIN_PAUSE(); c_head = HFDL_UNI(s_head); }
 			__threadfence_block();
-			if(c_head <= seq) break;                   // end of batch: every output consumed
+			if(HFDL_UNLIKELY(c_head <= seq)) break;                   // end of batch: every output consumed
 			const float4 ent = s_ring[seq & (HFDL_RING - 1)];
 			const int k = __float_as_int(ent.w);
 			const float level = ent.z;
 			// noise-floor clock ticks once per input sample, before that sample's outputs (hfdl.c:700)
-			for(int sidx = k_prev + 1; sidx <= k; sidx++) HFDL_NF_TICK(sidx);
+			if(HFDL_UNLIKELY(S.fr_state == HF_A1)) { for(int sidx = k_prev + 1; sidx <= k; sidx++) HFDL_NF_TICK(sidx); }
 			k_prev = k;
 			bool reset_req = false;
 			for(int i = 0; i < 1; i++, S.symsync_out_idx++) {
@@ -492,7 +618,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				hfdl_sincos_fast(S.c_phi, &sn, &cs);
 				const cf so = make_float2(ent.x, ent.y);
 				cf r = make_float2(so.x * cs + so.y * sn, so.y * cs - so.x * sn);
-				if(S.fr_state == HF_A1 && fabsf(S.c_dphi) > 0.25f) {
+				if(HFDL_UNLIKELY(S.fr_state == HF_A1 && fabsf(S.c_dphi) > 0.25f)) {
 					S.c_phi = S.c_dphi = 0.f;
 					{ ss_reset(S); reset_req = true; }
 				}
@@ -530,7 +656,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 					float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
 					if(S.bitmask & 1u) d = -d;
 					bool run = true;
-					if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
+					if(HFDL_UNLIKELY(!S.eq_buf_full)) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
 					if(run) {
 						const float inv = 1.0f / S.eq_x2_sum;
 						cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);      // mu * conj(d - d_hat) / sum|x|^2, mu = 0.1 (hfdl.c:496)
@@ -543,8 +669,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 					}
 					S.T_idx++;
 				}
-				if(cap && lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s;
-				if(cap) cap_n_eq++;
+				if(HFDL_UNLIKELY(cap)) { if(lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s; cap_n_eq++; }
 				cf x_hat;
 				unsigned bits = modem_demod(S.cur_arity, s, T, &x_hat);
 				// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
@@ -554,12 +679,12 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
 
 				symcnt++;
-				if(S.fr_state == HF_A1 && symcnt >= 13u * HFDL_SINGLE_SLOT_FRAME_LEN) {
+				if(HFDL_UNLIKELY(S.fr_state == HF_A1 && symcnt >= 13u * HFDL_SINGLE_SLOT_FRAME_LEN)) {
 					symcnt = 0;
 					S.c_phi = S.c_dphi = 0.f;
 					{ ss_reset(S); reset_req = true; }
 				}
-				if(S.s_state == HS_EMIT_BITS) {
+				if(HFDL_UNLIKELY(S.s_state == HS_EMIT_BITS)) {
 					bits ^= S.bitmask;
 					for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
 				} else if(S.s_state == HS_EMIT_SYMBOLS) {
@@ -569,11 +694,11 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 						if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
 					}
 				}
-				if(S.fr_state > HF_A1) {
+				if(HFDL_LIKELY(S.fr_state > HF_A1)) {
 					S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + level, S.frame_symbol_cnt + 1.0f);
 					S.frame_symbol_cnt += 1.0f;
 				}
-				if(S.symbols_wanted > 1) { S.symbols_wanted--; continue; }
+				if(HFDL_LIKELY(S.symbols_wanted > 1)) { S.symbols_wanted--; continue; }
 
 				switch(S.fr_state) {
 				case HF_A1: {
@@ -682,7 +807,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				}
 			}
 
-			if(reset_req) {
+			if(HFDL_UNLIKELY(reset_req)) {
 				// symsync_crcf_reset happened while processing output seq (input sample k): outputs of the same
 				// input sample already produced keep their (old-state) value, the timing warp restarts after them
 				int e2 = seq;
