@@ -234,6 +234,7 @@ struct LoopArgs {
 	cf *datasym;               // [C][HFDL_FRAME_SLOTS][HFDL_DATA_SYMS_MAX]
 	FrameRec *frames; int *nframes; int max_frames;
 	int cap_channel; cf *cap_eq; int *cap_cnt; int cap_max;      // f_eq_out checkpoint of one channel
+	int debug_mode;            // diagnostics only (HFDL_B200_DEBUG): 1 = demodulator warp drains the ring without processing
 };
 
 __device__ __forceinline__ void bits_push(unsigned *b, unsigned bit) {
@@ -403,13 +404,15 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqRing &E, const DemodTa
 		seq += 2;
 		S.symsync_out_idx += 2;
 		done++;
-		__syncwarp();
-		if(lane == 0) *p_tail = seq;
+		if((done & 3) == 0) { __syncwarp(); if(lane == 0) *p_tail = seq; }
 	}
+	__syncwarp();
+	if(lane == 0) *p_tail = seq;
 	S.symbols_wanted -= done;
 	return done;
 }
 
+#define HFDL_PBATCH 12          // input samples the timing warp handles between two polls of the ring indices
 #define HFDL_RING 64           // symsync outputs the timing warp may run ahead of the demodulator warp
 // a value polled from shared memory is made warp-uniform (lane 0's view) so that every lane takes the same branch
 #define HFDL_UNI(v) __shfl_sync(0xffffffffu, (int)(v), 0)
@@ -493,62 +496,52 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				continue;
 			}
 			if(HFDL_UNLIKELY(finished)) { if(p_done) break; HFDL_SPIN_PAUSE(); continue; }
-			if(seq - p_tail >= HFDL_RING - 2) { HFDL_SPIN_PAUSE(); continue; }      // ring full: wait (keeps polling for resets)
-			int kn = k + 1;
-			if(S.ss_b >= HFDL_SS_NPFB) {               // input sample(s) without output: usually exactly one
-				int skip = S.ss_b >> 4;
-				if(HFDL_UNLIKELY(kn + skip >= N)) {                   // the rest of the batch yields no output
-					for(; kn < N; kn++) { HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; }
-					k = N - 1; finished = true;
+			if(seq - p_tail > HFDL_RING - HFDL_PBATCH - 4) { HFDL_SPIN_PAUSE(); continue; }      // not enough room: wait (keeps polling for resets)
+			// several input samples are processed between polls / publications (the demodulator warp is behind anyway)
+			for(int pb = 0; pb < HFDL_PBATCH; pb++) {      // one input sample per iteration (2 of 3 yield an output)
+				const int kn = k + 1;
+				if(HFDL_UNLIKELY(kn >= N)) { finished = true; break; }
+				k = kn;
+				if(HFDL_UNLIKELY(need_stage)) {                           // (re)prime the two staging buffers at the chunk of sample k
+					hfdl_cp_async_wait<0>();
 					__syncwarp();
-					if(lane == 0) { __threadfence_block(); s_end_seq = seq; }
-					continue;
+					chunk = k / HFDL_LOOP_CH; chunk_end = (chunk + 1) * HFDL_LOOP_CH;
+					HFDL_STAGE_CHUNK(chunk, chunk & 1);
+					HFDL_STAGE_CHUNK(chunk + 1, (chunk + 1) & 1);
+					hfdl_cp_async_wait<1>();
+					__syncwarp();
+					need_stage = false;
 				}
-				do { HFDL_SS_CONSUME(); S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB; kn++; } while(--skip);
-			} else if(HFDL_UNLIKELY(kn >= N)) {
-				finished = true;
-				__syncwarp();
-				if(lane == 0) { __threadfence_block(); s_end_seq = seq; }
-				continue;
-			}
-			k = kn;
-			if(HFDL_UNLIKELY(need_stage)) {                           // (re)prime the two staging buffers at the chunk of sample k
-				hfdl_cp_async_wait<0>();
-				__syncwarp();
-				chunk = k / HFDL_LOOP_CH; chunk_end = (chunk + 1) * HFDL_LOOP_CH;
-				HFDL_STAGE_CHUNK(chunk, chunk & 1);
-				HFDL_STAGE_CHUNK(chunk + 1, (chunk + 1) & 1);
-				hfdl_cp_async_wait<1>();
-				__syncwarp();
-				need_stage = false;
-			}
-			while(HFDL_UNLIKELY(k >= chunk_end)) {                    // move to the next staged chunk, refill the one just left
-				__syncwarp();
-				HFDL_STAGE_CHUNK(chunk + 2, chunk & 1);
-				hfdl_cp_async_wait<1>();
-				__syncwarp();
-				chunk++; chunk_end += HFDL_LOOP_CH;
-			}
-			const int ii = k - (chunk_end - HFDL_LOOP_CH);
-			const cf *row = s_bank[chunk & 1][ii];
-			const float level = s_lvl[chunk & 1][ii];           // 1/g after this sample's AGC update
-			HFDL_SS_CONSUME();                       // the push itself happened in bank_kernel
-			cf sym0, sym1 = make_float2(0.f, 0.f);
-			int produced = 1;
-			HFDL_SS_OUTPUT(sym0);
-			if(HFDL_UNLIKELY(S.ss_b < HFDL_SS_NPFB)) {                // further outputs of the same input sample: del < 1, rare
-				HFDL_SS_OUTPUT(sym1);
-				produced = 2;
-				while(S.ss_b < HFDL_SS_NPFB) { cf drop; HFDL_SS_OUTPUT(drop); (void)drop; }
-			}
-			S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;
-			// all outputs of one input sample are published together
-			s_ring[seq & (HFDL_RING - 1)] = make_float4(sym0.x, sym0.y, level, __int_as_float(k));
-			if(produced == 2) s_ring[(seq + 1) & (HFDL_RING - 1)] = make_float4(sym1.x, sym1.y, level, __int_as_float(k));
-			seq += produced;
+				while(HFDL_UNLIKELY(k >= chunk_end)) {                    // move to the next staged chunk, refill the one just left
+					__syncwarp();
+					HFDL_STAGE_CHUNK(chunk + 2, chunk & 1);
+					hfdl_cp_async_wait<1>();
+					__syncwarp();
+					chunk++; chunk_end += HFDL_LOOP_CH;
+				}
+				HFDL_SS_CONSUME();                       // the push itself happened in bank_kernel
+				if(S.ss_b < HFDL_SS_NPFB) {              // symsync_crcf_step: while(b < npfb) { output ... }
+					const int ii = k - (chunk_end - HFDL_LOOP_CH);
+					const cf *row = s_bank[chunk & 1][ii];
+					const float level = s_lvl[chunk & 1][ii];           // 1/g after this sample's AGC update
+					cf sym0, sym1 = make_float2(0.f, 0.f);
+					int produced = 1;
+					HFDL_SS_OUTPUT(sym0);
+					if(HFDL_UNLIKELY(S.ss_b < HFDL_SS_NPFB)) {                // further outputs of the same input sample: del < 1, rare
+						HFDL_SS_OUTPUT(sym1);
+						produced = 2;
+						while(S.ss_b < HFDL_SS_NPFB) { cf drop; HFDL_SS_OUTPUT(drop); (void)drop; }
+					}
+					// all outputs of one input sample are published together
+					s_ring[seq & (HFDL_RING - 1)] = make_float4(sym0.x, sym0.y, level, __int_as_float(k));
+					if(HFDL_UNLIKELY(produced == 2)) s_ring[(seq + 1) & (HFDL_RING - 1)] = make_float4(sym1.x, sym1.y, level, __int_as_float(k));
+					seq += produced;
+				}
+				S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;      // ... then tau -= 1, b -= npfb
+			}   // pb
 			__threadfence_block();
 			__syncwarp();
-			if(lane == 0) s_head = seq;
+			if(lane == 0) { s_head = seq; if(finished) { __threadfence_block(); s_end_seq = seq; } }
 		}
 #undef HFDL_STAGE_CHUNK
 #undef HFDL_SS_CONSUME
@@ -583,7 +576,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				wait_seq = 0x7fffffff;
 			}
 			// fast path: a run of whole symbols up to (not including) the symbol of the next framer event
-			if(!cap && S.fr_state > HF_A1 && S.symbols_wanted > 1 && !(S.symsync_out_idx & 1u) && wait_seq == 0x7fffffff) {
+			if(!cap && a.debug_mode != 1 && a.debug_mode != 2 && S.fr_state > HF_A1 && S.symbols_wanted > 1 && !(S.symsync_out_idx & 1u) && wait_seq == 0x7fffffff) {
 				const int nsym = S.symbols_wanted - 1;
 				int did;
 				const float4 *rg = s_ring;
@@ -600,6 +593,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 			__threadfence_block();
 			if(HFDL_UNLIKELY(c_head <= seq)) break;                   // end of batch: every output consumed
 			const float4 ent = s_ring[seq & (HFDL_RING - 1)];
+			if(a.debug_mode == 1) { seq++; __syncwarp(); if(lane == 0) s_tail = seq; continue; }
 			const int k = __float_as_int(ent.w);
 			const float level = ent.z;
 			// noise-floor clock ticks once per input sample, before that sample's outputs (hfdl.c:700)

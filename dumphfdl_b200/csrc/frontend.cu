@@ -255,6 +255,7 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 			l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym;
 			l.frames = fe->d_frames; l.nframes = fe->d_nframes; l.max_frames = fe->max_frames;
 			l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
+			{ const char *dbg = getenv("HFDL_B200_DEBUG"); l.debug_mode = dbg ? atoi(dbg) : 0; }
 			prof_begin(fe, KC_LOOP, pr);
 			HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(64), 0, st, l);
 			prof_end(fe, pr);
