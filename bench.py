@@ -350,6 +350,8 @@ def main():
         if not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference(O, x, isz, nblocks)
         print(json.dumps(line))
+    if os.environ.get("HFDL_B200_DEBUG"):
+        fe.L.hfdl_b200_print_summary(fe.h)
     fe.close()
     fe2.close()
     if world > 1:

@@ -57,6 +57,11 @@ __device__ __forceinline__ void hfdl_cp_async_commit() { asm volatile("cp.async.
 template <int N> __device__ __forceinline__ void hfdl_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
+#ifdef HFDL_CUSIM
+static inline long long hfdl_clock() { return 0; }
+#else
+__device__ __forceinline__ long long hfdl_clock() { return clock64(); }
+#endif
 // polite spinning while one warp waits for another
 #ifdef HFDL_CUSIM
 #define HFDL_SPIN_PAUSE() std::this_thread::yield()

@@ -234,6 +234,7 @@ struct LoopArgs {
 	cf *datasym;               // [C][HFDL_FRAME_SLOTS][HFDL_DATA_SYMS_MAX]
 	FrameRec *frames; int *nframes; int max_frames;
 	int cap_channel; cf *cap_eq; int *cap_cnt; int cap_max;      // f_eq_out checkpoint of one channel
+	long long *dbg_cycles;     // diagnostics only: [C][4] = timing-warp total / waiting-for-room, demod-warp total / waiting-for-outputs
 	int debug_mode;            // diagnostics only (HFDL_B200_DEBUG): 1 = demodulator warp drains the ring without processing
 };
 
@@ -333,7 +334,7 @@ __device__ __forceinline__ cf costas_rotate_push(DemodState &S, EqRing &E, cf so
 template <int MODE, int ARITY>
 __device__ __forceinline__ int demod_run(DemodState &S, EqRing &E, const DemodTables &T, const float4 *ring,
 		volatile int *p_head, volatile int *p_end, volatile int *p_tail, int &seq, int &k_prev, int nsym,
-		cf *s_train, cf *dsym, int lane, unsigned &symcnt) {
+		cf *s_train, cf *dsym, int lane, unsigned &symcnt, long long *p_twait) {
 	int done = 0;
 	int c_head = __shfl_sync(0xffffffffu, (int)*p_head, 0);
 	while(done < nsym) {
@@ -341,7 +342,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqRing &E, const DemodTa
 			c_head = __shfl_sync(0xffffffffu, (int)*p_head, 0);
 			if(c_head - seq < 2) {
 				if(seq + 1 >= __shfl_sync(0xffffffffu, (int)*p_end, 0)) break;     // the batch ends inside this run
-				HFDL_SPIN_PAUSE();
+				{ long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); *p_twait += hfdl_clock() - t0; }
 				continue;
 			}
 			__threadfence_block();
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 		int seq = 0;                        // sequence number of the next output
 		int my_gen = 0;
 		bool finished = false, need_stage = true;
+		long long t_begin = hfdl_clock(), t_wait = 0;
 #define HFDL_STAGE_CHUNK(ch_, buf_) do { \
 			const int nn0_ = (ch_) * HFDL_LOOP_CH; \
 			for(int i_ = 0; i_ < HFDL_LOOP_CH; i_++) { int n_ = nn0_ + i_; if(n_ < N) hfdl_cp_async8(&s_bank[buf_][i_][lane], &bank[(long long)n_ * 32 + lane]); } \
@@ -495,8 +497,8 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				if(lane == 0) { s_end_seq = 0x7fffffff; s_head = seq; __threadfence_block(); s_ack_gen = my_gen; }
 				continue;
 			}
-			if(HFDL_UNLIKELY(finished)) { if(p_done) break; HFDL_SPIN_PAUSE(); continue; }
-			if(seq - p_tail > HFDL_RING - HFDL_PBATCH - 4) { HFDL_SPIN_PAUSE(); continue; }      // not enough room: wait (keeps polling for resets)
+			if(HFDL_UNLIKELY(finished)) { if(p_done) break; long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); t_wait += hfdl_clock() - t0; continue; }
+			if(seq - p_tail > HFDL_RING - HFDL_PBATCH - 4) { long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); t_wait += hfdl_clock() - t0; continue; }      // not enough room: wait (keeps polling for resets)
 			// several input samples are processed between polls / publications (the demodulator warp is behind anyway)
 			for(int pb = 0; pb < HFDL_PBATCH; pb++) {      // one input sample per iteration (2 of 3 yield an output)
 				const int kn = k + 1;
@@ -547,6 +549,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 #undef HFDL_SS_CONSUME
 #undef HFDL_SS_OUTPUT
 		hfdl_cp_async_wait<0>();
+		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 4 + 0] += hfdl_clock() - t_begin; a.dbg_cycles[c * 4 + 1] += t_wait; }
 	} else {
 		// =========================== demodulator warp (consumer) ===========================
 		const bool cap = (c == a.cap_channel);
@@ -569,6 +572,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 #define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1) { if((++S.nf_clk & 0xFFu) == 0xFFu) \
 			S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } } while(0)     /* hfdl.c:700-706 */
 		int seq = 0, k_prev = -1, gen = 0, wait_seq = 0x7fffffff;
+		long long t_begin = hfdl_clock(), t_wait = 0;
 		for(;;) {
 			if(HFDL_UNLIKELY(seq >= wait_seq)) {                      // outputs from here on must come from the re-started timing loop
 				while(HFDL_UNI(s_ack_gen) != gen) { HFDL_SPIN_PAUSE(); }
@@ -580,16 +584,16 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 				const int nsym = S.symbols_wanted - 1;
 				int did;
 				const float4 *rg = s_ring;
-				if(S.s_state == HS_EMIT_BITS) did = demod_run<RUN_BITS, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
-				else if(S.s_state == HS_SKIP) did = demod_run<RUN_SKIP, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
-				else if(S.cur_buf == 0) did = demod_run<RUN_TRAIN, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
-				else if(S.cur_arity == 1) did = demod_run<RUN_DATA, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
-				else if(S.cur_arity == 2) did = demod_run<RUN_DATA, 2>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
-				else did = demod_run<RUN_DATA, 3>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt);
+				if(S.s_state == HS_EMIT_BITS) did = demod_run<RUN_BITS, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt, &t_wait);
+				else if(S.s_state == HS_SKIP) did = demod_run<RUN_SKIP, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt, &t_wait);
+				else if(S.cur_buf == 0) did = demod_run<RUN_TRAIN, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt, &t_wait);
+				else if(S.cur_arity == 1) did = demod_run<RUN_DATA, 1>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt, &t_wait);
+				else if(S.cur_arity == 2) did = demod_run<RUN_DATA, 2>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt, &t_wait);
+				else did = demod_run<RUN_DATA, 3>(S, E, T, rg, &s_head, &s_end_seq, &s_tail, seq, k_prev, nsym, s_train, dsym, lane, symcnt, &t_wait);
 				if(did > 0) continue;
 			}
 			int c_head = HFDL_UNI(s_head);
-			while(HFDL_UNLIKELY(c_head <= seq) && seq < HFDL_UNI(s_end_seq)) { HFDL_SPIN_PAUSE(); c_head = HFDL_UNI(s_head); }
+			while(HFDL_UNLIKELY(c_head <= seq) && seq < HFDL_UNI(s_end_seq)) { long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); c_head = HFDL_UNI(s_head); t_wait += hfdl_clock() - t0; }
 			__threadfence_block();
 			if(HFDL_UNLIKELY(c_head <= seq)) break;                   // end of batch: every output consumed
 			const float4 ent = s_ring[seq & (HFDL_RING - 1)];
@@ -815,6 +819,7 @@ __global__ void __launch_bounds__(64) loop_kernel(LoopArgs a) {
 			__syncwarp();
 			if(lane == 0) s_tail = seq;
 		}
+		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 4 + 2] += hfdl_clock() - t_begin; a.dbg_cycles[c * 4 + 3] += t_wait; }
 		for(int sidx = k_prev + 1; sidx < N; sidx++) HFDL_NF_TICK(sidx);      // input samples after the last output
 #undef HFDL_NF_TICK
 		S.sample_cnt = cnt_base + (unsigned long long)N;

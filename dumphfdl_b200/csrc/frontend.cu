@@ -88,6 +88,7 @@ struct hfdl_b200_frontend {
 	FrameRec *d_frames = nullptr; int *d_nframes = nullptr; PduRec *d_pdus = nullptr; int max_frames = 0;
 	cf *d_cap_agc = nullptr, *d_cap_mf = nullptr, *d_cap_eq = nullptr; int *d_cap_cnt = nullptr;
 	cf *d_tmp = nullptr; long long tmp_len = 0;
+	long long *d_dbg = nullptr;
 	// host state
 	PduRec *h_pdus = nullptr; int *h_nframes = nullptr;
 	long long fed = 0;              // samples pushed so far (host-fed path)
@@ -256,6 +257,7 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 			l.frames = fe->d_frames; l.nframes = fe->d_nframes; l.max_frames = fe->max_frames;
 			l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
 			{ const char *dbg = getenv("HFDL_B200_DEBUG"); l.debug_mode = dbg ? atoi(dbg) : 0; }
+			l.dbg_cycles = fe->d_dbg;
 			prof_begin(fe, KC_LOOP, pr);
 			HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(64), 0, st, l);
 			prof_end(fe, pr);
@@ -454,6 +456,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaMemset(fe->d_cap_cnt, 0, sizeof(int) * 2));
 	fe->tmp_len = std::max((long long)N, (long long)B * fe->out_per_block + 64);
 	CKD(cudaMalloc((void **)&fe->d_tmp, sizeof(cf) * (size_t)fe->tmp_len));
+	if(getenv("HFDL_B200_DEBUG")) { CKD(cudaMalloc((void **)&fe->d_dbg, sizeof(long long) * 4 * (size_t)C)); CKD(cudaMemset(fe->d_dbg, 0, sizeof(long long) * 4 * (size_t)C)); }
 	CKD(cudaEventCreate(&fe->ev0));
 	CKD(cudaEventCreate(&fe->ev1));
 	if(compute_tapslices(fe)) { hfdl_b200_destroy(fe); return -1; }
@@ -603,6 +606,12 @@ int32_t hfdl_b200_channel_stats(hfdl_b200_frontend_t *fe, int32_t channel, int32
 
 void hfdl_b200_print_summary(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
+	if(fe->d_dbg) {
+		std::vector<long long> v((size_t)fe->C * 4);
+		cudaStreamSynchronize(fe->stream);
+		cudaMemcpy(v.data(), fe->d_dbg, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
+		for(int c = 0; c < fe->C && c < 4; c++) fprintf(stderr, "loop_kernel ch%d cycles: timing warp %lld (waiting %lld)  demod warp %lld (waiting %lld)\n", c, v[(size_t)c * 4], v[(size_t)c * 4 + 1], v[(size_t)c * 4 + 2], v[(size_t)c * 4 + 3]);
+	}
 	long long t[4] = { 0, 0, 0, 0 };
 	for(int c = 0; c < fe->C; c++) { int32_t s[4]; if(hfdl_b200_channel_stats(fe, c, s) == 0) for(int i = 0; i < 4; i++) t[i] += s[i]; }
 	fprintf(stderr, "A1_found:\t\t%lld\nA2_found:\t\t%lld\nM1_found:\t\t%lld\nframes:\t\t\t%lld\n", t[0], t[1], t[2], t[3]);
