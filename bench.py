@@ -50,7 +50,8 @@ SEED = 635002             # 635000 + cfg_index
 METRIC = "I/Q Msamples/s & CRC-good PDUs/s at 1/2/4/8 B200 vs fftw CPU ref"
 
 
-def channel_freqs(nch=NCH):
+def channel_freqs(nch=None):
+    nch = nch or NCH
     delta = int(0.85 * SR / nch / 1000) * 1000
     return [int(round((CF + (k - (nch - 1) / 2) * delta) / 1000.0)) * 1000 for k in range(nch)]
 

@@ -89,6 +89,60 @@ __device__ __forceinline__ void smem_fft(cf *s, int lgL, int nf, int TP, const c
 	}
 }
 
+// Forward sub-FFT for the passes: radix-2^2 DIF over a shared-memory tile of `nf` = 1<<lgT transforms.
+// Element e of transform f lives at s[tile_idx(e, f)], a row-major [L][nf] tile whose column is XOR-swizzled
+// with the row so that natural-order rows, bit-reversed rows and whole-row accesses are all bank-conflict free.
+// Input in natural order, output in bit-reversed order (callers read row brev(k) to get bin k).
+__device__ __forceinline__ int tile_idx(int row, int col, int lgT) {
+	const int mask = (1 << lgT) - 1;
+	return (row << lgT) + ((col ^ row ^ (row >> 4)) & mask);
+}
+
+__device__ __forceinline__ void smem_fft_dif(cf *s, int lgL, int lgT, const cf *__restrict__ tw) {
+	const int L = 1 << lgL, nf = 1 << lgT;
+	const int tid = threadIdx.x, nth = blockDim.x;
+	int st = lgL;                       // current sub-transform size is 1 << st
+	if(lgL & 1) {                       // odd log2: one radix-2 stage of size L first
+		const int h = L >> 1;
+		const int items = nf * h;
+		for(int w = tid; w < items; w += nth) {
+			const int f = w & (nf - 1), j = w >> lgT;
+			const cf w1 = __ldg(&tw[j * (HFDL_TWN >> lgL)]);
+			cf *p0 = s + tile_idx(j, f, lgT), *p1 = s + tile_idx(j + h, f, lgT);
+			const cf x0 = *p0, x1 = *p1;
+			*p0 = cadd(x0, x1);
+			*p1 = cmul(w1, csub(x0, x1));
+		}
+		__syncthreads();
+		st--;
+	}
+	for(; st >= 2; st -= 2) {           // sizes 4h = 1<<st
+		const int lgh = st - 2, h = 1 << lgh;
+		const int items = nf * (L >> 2);
+		for(int w = tid; w < items; w += nth) {
+			const int f = w & (nf - 1), q = w >> lgT;
+			const int j = q & (h - 1);
+			const int i0 = ((q >> lgh) << st) + j;
+			const cf wa = __ldg(&tw[j * (HFDL_TWN >> st)]);            // W_{4h}^j
+			const cf wb = __ldg(&tw[j * (HFDL_TWN >> (st - 1))]);      // W_{2h}^j
+			cf *p0 = s + tile_idx(i0, f, lgT), *p1 = s + tile_idx(i0 + h, f, lgT);
+			cf *p2 = s + tile_idx(i0 + 2 * h, f, lgT), *p3 = s + tile_idx(i0 + 3 * h, f, lgT);
+			const cf x0 = *p0, x1 = *p1, x2 = *p2, x3 = *p3;
+			// size-4h stage: (x0,x2) with W^j, (x1,x3) with W^(j+h) = -i W^j
+			const cf a0 = cadd(x0, x2), d02 = csub(x0, x2), a1 = cadd(x1, x3), d13 = csub(x1, x3);
+			const cf a2 = cmul(wa, d02);
+			const cf t13 = cmul(wa, d13);
+			const cf a3 = make_float2(t13.y, -t13.x);
+			// size-2h stage: (a0,a1) and (a2,a3) with W_{2h}^j
+			*p0 = cadd(a0, a1);
+			*p1 = cmul(wb, csub(a0, a1));
+			*p2 = cadd(a2, a3);
+			*p3 = cmul(wb, csub(a2, a3));
+		}
+		__syncthreads();
+	}
+}
+
 // Source of the wideband stream for the first pass: a cyclic device buffer of raw samples.
 // Window b starts at stream position pos0 + b*block_stride; positions < 0 read as zero (the
 // reference's first window has a zeroed overlap, fft.c:79), others wrap modulo ring_len.
@@ -101,19 +155,33 @@ struct RawSource {
 	int sfmt;
 };
 
-__device__ __forceinline__ cf load_raw(const RawSource &src, long long pos) {
-	if(pos < 0) return make_float2(0.f, 0.f);
+// per-CTA view of one window: ring index of its element 0 (64-bit modulo once per CTA, not per sample)
+struct WindowView { long long start_ring; long long first_valid; long long ring_len; const void *base; int sfmt; };
+
+__device__ __forceinline__ WindowView window_view(const RawSource &src, int b) {
+	WindowView v;
+	const long long pos = src.pos0 + (long long)b * src.block_stride;      // stream position of element 0
+	v.first_valid = pos < 0 ? -pos : 0;                                     // elements before this index read as zero
 	long long r = (pos + src.ring_origin) % src.ring_len;
-	if(src.sfmt == HFDL_SFMT_CF32) {
-		return reinterpret_cast<const cf *>(src.base)[r];                 // full_scale 1.0
-	} else if(src.sfmt == HFDL_SFMT_CS16) {
-		short2 v = reinterpret_cast<const short2 *>(src.base)[r];
+	if(r < 0) r += src.ring_len;
+	v.start_ring = r; v.ring_len = src.ring_len; v.base = src.base; v.sfmt = src.sfmt;
+	return v;
+}
+
+__device__ __forceinline__ cf load_window(const WindowView &v, long long n) {      // n in [0, N), N <= ring_len
+	if(n < v.first_valid) return make_float2(0.f, 0.f);
+	long long r = v.start_ring + n;
+	if(r >= v.ring_len) r -= v.ring_len;
+	if(v.sfmt == HFDL_SFMT_CF32) {
+		return reinterpret_cast<const cf *>(v.base)[r];                   // full_scale 1.0
+	} else if(v.sfmt == HFDL_SFMT_CS16) {
+		short2 q = reinterpret_cast<const short2 *>(v.base)[r];
 		const float fs = 32767.5f;                                        // SHRT_MAX + 0.5 (input-helpers.c:116)
-		return make_float2((float)v.x / fs, (float)v.y / fs);
+		return make_float2((float)q.x / fs, (float)q.y / fs);
 	} else {
-		uchar2 v = reinterpret_cast<const uchar2 *>(src.base)[r];
+		uchar2 q = reinterpret_cast<const uchar2 *>(v.base)[r];
 		const float fs = 127.0f, shift = 63.5f;                           // input-helpers.c:54,110
-		return make_float2(((float)v.x - shift) / fs, ((float)v.y - shift) / fs);
+		return make_float2(((float)q.x - shift) / fs, ((float)q.y - shift) / fs);
 	}
 }
 
@@ -123,36 +191,53 @@ struct ColPassArgs {
 	RawSource src;
 	cf *work;
 	const cf *tw;
-	int N, lgL, inner, lgInner, T, first;
+	int N, lgL, inner, lgInner, T, lgT, first;
 };
 
 __global__ void __launch_bounds__(HFDL_FFT_THREADS) fft_col_pass(ColPassArgs a) {
 	HFDL_DYN_SMEM(cf, s);
-	const int L = 1 << a.lgL;
-	const int tiles_per_row = a.inner / a.T;
+	const int L = 1 << a.lgL, lgT = a.lgT, T = 1 << lgT;
+	const int tiles_per_row = a.inner >> lgT;
 	const int o = blockIdx.x / tiles_per_row;
-	const int n0 = (blockIdx.x % tiles_per_row) * a.T;
+	const int n0 = (blockIdx.x - o * tiles_per_row) << lgT;
 	const int b = blockIdx.y;
 	const long long base = (long long)o * L * a.inner + n0;
-	const int total = L * a.T;
-	for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-		int t = idx % a.T, e = idx / a.T;
-		long long n = base + (long long)e * a.inner + t;
-		cf v;
-		if(a.first) v = load_raw(a.src, a.src.pos0 + (long long)b * a.src.block_stride + n);
-		else v = a.work[(long long)b * a.N + n];
-		s[brev_n(e, a.lgL) * a.T + t] = v;
+	const int total = L << lgT;
+	cf *wk = a.work + (long long)b * a.N + base;
+	if(a.first) {
+		const WindowView wv = window_view(a.src, b);
+		for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+			const int t = idx & (T - 1), e = idx >> lgT;
+			s[tile_idx(e, t, lgT)] = load_window(wv, base + (long long)e * a.inner + t);
+		}
+	} else {
+		for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+			const int t = idx & (T - 1), e = idx >> lgT;
+			s[tile_idx(e, t, lgT)] = wk[(long long)e * a.inner + t];
+		}
 	}
 	__syncthreads();
-	smem_fft(s, a.lgL, a.T, a.T, a.tw, 0);
+	smem_fft_dif(s, a.lgL, lgT, a.tw);
+	// bin k sits in row brev(k); each thread walks k with a constant stride, so its inter-pass twiddle
+	// W_{L*inner}^{k*(n0+t)} advances by a constant rotation (re-seeded from sincospif every 8 steps)
 	const float inv_np = 1.0f / (float)(L * a.inner);    // power of two: exact
-	for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-		int t = idx % a.T, k = idx / a.T;
-		float sn, cs;
-		// k*(n0+t) < L*inner <= 2^23: exact in fp32, so the twiddle angle is exact before sincospi
-		sincospif(-2.0f * (float)(k * (n0 + t)) * inv_np, &sn, &cs);
-		cf v = cmul(s[k * a.T + t], make_float2(cs, sn));
-		a.work[(long long)b * a.N + base + (long long)k * a.inner + t] = v;
+	const int t = threadIdx.x & (T - 1);
+	const int kstep = blockDim.x >> lgT;
+	const float c = (float)(n0 + t);
+	float ssn, scs;
+	sincospif(-2.0f * (float)kstep * c * inv_np, &ssn, &scs);          // kstep*c < L*inner <= 2^23: exact argument
+	const cf rot = make_float2(scs, ssn);
+	cf twd = make_float2(1.f, 0.f);
+	int it = 0;
+	for(int k = threadIdx.x >> lgT; k < L; k += kstep, it++) {
+		if((it & 7) == 0) {
+			float sn, cs;
+			sincospif(-2.0f * (float)k * c * inv_np, &sn, &cs);
+			twd = make_float2(cs, sn);
+		}
+		const cf v = cmul(s[tile_idx(brev_n(k, a.lgL), t, lgT)], twd);
+		wk[(long long)k * a.inner + t] = v;
+		twd = cmul(twd, rot);
 	}
 }
 
@@ -161,29 +246,33 @@ struct RowPassArgs {
 	RawSource src;
 	cf *work;
 	const cf *tw;
-	int N, lgL, R, first;
+	int N, lgL, R, lgR, first;
 };
 
 __global__ void __launch_bounds__(HFDL_FFT_THREADS) fft_row_pass(RowPassArgs a) {
 	HFDL_DYN_SMEM(cf, s);
-	const int L = 1 << a.lgL;
-	const int TP = a.R + 1;
+	const int L = 1 << a.lgL, lgR = a.lgR;
 	const int b = blockIdx.y;
-	const long long row0 = (long long)blockIdx.x * a.R;
-	const int total = L * a.R;
-	for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-		int e = idx & (L - 1), rr = idx >> a.lgL;
-		long long n = (row0 + rr) * L + e;
-		cf v;
-		if(a.first) v = load_raw(a.src, a.src.pos0 + (long long)b * a.src.block_stride + n);
-		else v = a.work[(long long)b * a.N + n];
-		s[brev_n(e, a.lgL) * TP + rr] = v;
+	const long long row0 = (long long)blockIdx.x << lgR;
+	const int total = L << lgR;
+	cf *wk = a.work + (long long)b * a.N + row0 * L;
+	if(a.first) {
+		const WindowView wv = window_view(a.src, b);
+		for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+			const int e = idx & (L - 1), rr = idx >> a.lgL;
+			s[tile_idx(e, rr, lgR)] = load_window(wv, row0 * L + idx);
+		}
+	} else {
+		for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+			const int e = idx & (L - 1), rr = idx >> a.lgL;
+			s[tile_idx(e, rr, lgR)] = wk[idx];
+		}
 	}
 	__syncthreads();
-	smem_fft(s, a.lgL, a.R, TP, a.tw, 0);
+	smem_fft_dif(s, a.lgL, lgR, a.tw);
 	for(int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-		int e = idx & (L - 1), rr = idx >> a.lgL;
-		a.work[(long long)b * a.N + (row0 + rr) * L + e] = s[e * TP + rr];
+		const int k = idx & (L - 1), rr = idx >> a.lgL;
+		wk[idx] = s[tile_idx(brev_n(k, a.lgL), rr, lgR)];
 	}
 }
 

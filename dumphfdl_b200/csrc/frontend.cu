@@ -143,6 +143,7 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 			ColPassArgs a;
 			a.src = src; a.work = work; a.tw = eng.d_tw; a.N = pl.N; a.lgL = lgL; a.inner = inner; a.lgInner = hfdl_ilog2(inner);
 			a.T = tile_for(lgL); if(a.T > inner) a.T = inner;
+			a.lgT = hfdl_ilog2(a.T);
 			a.first = (p == 0);
 			dim3 grid((unsigned)(outer * (inner / a.T)), (unsigned)nb);
 			size_t smem = sizeof(cf) * (size_t)L * a.T;
@@ -152,9 +153,10 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 			a.src = src; a.work = work; a.tw = eng.d_tw; a.N = pl.N; a.lgL = lgL; a.R = tile_for(lgL);
 			int rows = pl.N / L;
 			if(a.R > rows) a.R = rows;
+			a.lgR = hfdl_ilog2(a.R);
 			a.first = (p == 0);
 			dim3 grid((unsigned)(rows / a.R), (unsigned)nb);
-			size_t smem = sizeof(cf) * (size_t)L * (a.R + 1);
+			size_t smem = sizeof(cf) * (size_t)L * a.R;
 			HFDL_LAUNCH(fft_row_pass, grid, dim3(HFDL_FFT_THREADS), smem, st, a);
 		}
 		prof_end(fe, pr);
