@@ -42,6 +42,7 @@ __host__ __device__ __forceinline__ cf cscale(cf a, float s) { return make_float
 #ifdef HFDL_CUSIM
 static inline void hfdl_cp_async8(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 8); }
 static inline void hfdl_cp_async4(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 4); }
+static inline void hfdl_cp_async16(void *sdst, const void *gsrc) { memcpy(sdst, gsrc, 16); }
 static inline void hfdl_cp_async_commit() {}
 template <int N> static inline void hfdl_cp_async_wait() {}
 #else
@@ -52,6 +53,10 @@ __device__ __forceinline__ void hfdl_cp_async8(void *sdst, const void *gsrc) {
 __device__ __forceinline__ void hfdl_cp_async4(void *sdst, const void *gsrc) {
 	unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void hfdl_cp_async16(void *sdst, const void *gsrc) {
+	unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void hfdl_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void hfdl_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -64,9 +69,14 @@ __device__ __forceinline__ long long hfdl_clock() { return clock64(); }
 #endif
 // polite spinning while one warp waits for another
 #ifdef HFDL_CUSIM
-#define HFDL_SPIN_PAUSE() std::this_thread::yield()
+static inline void hfdl_cusim_spin(int line) {      // test build only: yield + a watchdog that names a stuck spin loop
+	static thread_local unsigned long long n = 0;
+	std::this_thread::yield();
+	if((++n % 50000000ull) == 0 && getenv("HFDL_CUSIM_WATCHDOG")) fprintf(stderr, "cusim: thread %u block %u still spinning at line %d\n", threadIdx.x, blockIdx.x, line);
+}
+#define HFDL_SPIN_PAUSE() hfdl_cusim_spin(__LINE__)
 #else
-#define HFDL_SPIN_PAUSE() __nanosleep(20)
+#define HFDL_SPIN_PAUSE() asm volatile("nanosleep.u32 20;" ::: "memory")
 #endif
 
 // sample formats (src/input-common.h sample_format)

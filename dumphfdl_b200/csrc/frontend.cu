@@ -59,6 +59,7 @@ struct FftEngine {
 		CK(cudaFuncSetAttribute(fft_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(chan_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 		CK(cudaFuncSetAttribute(fec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_FEC_SMEM));
+		CK(cudaFuncSetAttribute(loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_LK_SMEM));
 		return 0;
 	}
 	void destroy() { if(d_tw) cudaFree(d_tw); d_tw = nullptr; }
@@ -261,7 +262,7 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 			{ const char *dbg = getenv("HFDL_B200_DEBUG"); l.debug_mode = dbg ? atoi(dbg) : 0; }
 			l.dbg_cycles = fe->d_dbg;
 			prof_begin(fe, KC_LOOP, pr);
-			HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(64), 0, st, l);
+			HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(HFDL_LK_THREADS), HFDL_LK_SMEM, st, l);
 			prof_end(fe, pr);
 			fe->launches += 3;
 		}

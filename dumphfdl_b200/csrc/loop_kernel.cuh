@@ -1,0 +1,773 @@
+// dumphfdl_b200/csrc/loop_kernel.cuh -- K8b-K11: the feedback part of the per-channel HFDL demodulator
+// (hfdl.c:707-891): symbol-timing recursion, Costas loop, T/2 LMS equaliser, M-PSK slicer, sampler and framer.
+//
+// One CTA per channel, three specialised warps that talk through shared-memory rings.  Every feedback loop of the
+// reference is a strictly sequential float recurrence, so the design goal is the SHORTEST DEPENDENT CHAIN and the
+// FEWEST INSTRUCTIONS on each sequential warp; everything that is not on a chain is moved to another warp or to
+// other lanes:
+//   warp 2 "loader"  streams the precomputed filter-bank rows (bank_kernel) and AGC levels of the channel from HBM
+//                    into a 256-sample shared-memory ring (16-byte cp.async, 3 chunks in flight).
+//   warp 1 "timing"  symsync_crcf_step: iterates per OUTPUT (not per input sample): arm lookup in the ring, timing
+//                    error detector + loop filter on every second output, tau/arm update, skip to the input sample
+//                    of the next output.  Publishes {symbol, AGC level, tag} entries into a 64-entry output ring.
+//                    It runs ahead of the demodulator; symsync_crcf_reset requests (framer reset, Costas blow-up,
+//                    13-frame timeout: hfdl.c:711-715,746-752,968-991) roll it back to the reset point.
+//   warp 0 "demod"   consumes the entries in order: Costas rotation, equaliser, slicer, sampler, framer.  The 15
+//                    equaliser taps live one per lane (both half-warps hold a copy): the partial sum over the 13
+//                    window elements that are already known is reduced with shuffles OFF the critical chain, only
+//                    the two newest taps are applied after the rotation.
+// Ring entries are self-validating (generation + lap + input-sample index in one word), so neither side needs a
+// fence or a head counter on its fast path.
+#pragma once
+#include "common.cuh"
+
+#define HFDL_LK_WARPS 3
+#define HFDL_LK_THREADS (32 * HFDL_LK_WARPS)
+#define HFDL_LK_RING 64                  // output entries the timing warp may run ahead of the demodulator warp
+#define HFDL_LK_BR 256                   // bank ring, input samples (power of two)
+#define HFDL_LK_CH 32                    // input samples per loader chunk
+#define HFDL_LK_INFLIGHT 3               // loader chunks in flight
+#define HFDL_LK_SMEM (HFDL_LK_BR * 32 * 8)   // dynamic shared memory: the bank ring
+#define HFDL_LK_MAXN (1 << 20)           // input samples per launch (tag layout)
+
+struct LoopArgs {
+	const cf *bank; long long bank_stride;
+	const cf *mfo; long long mfo_stride;
+	const float *lvl; long long lvl_stride;
+	int n_samples;
+	DemodState *state;
+	const DemodTables *tab;
+	cf *datasym;               // [C][HFDL_FRAME_SLOTS][HFDL_DATA_SYMS_MAX]
+	FrameRec *frames; int *nframes; int max_frames;
+	int cap_channel; cf *cap_eq; int *cap_cnt; int cap_max;      // f_eq_out checkpoint of one channel
+	long long *dbg_cycles;     // diagnostics only: [C][4] = timing-warp total / waiting, demod-warp total / waiting
+	int debug_mode;
+};
+
+__device__ __forceinline__ void bits_push(unsigned *b, unsigned bit) {
+	b[3] = ((b[3] << 1) | (b[2] >> 31)) & 0x7FFFFFFFu;
+	b[2] = (b[2] << 1) | (b[1] >> 31);
+	b[1] = (b[1] << 1) | (b[0] >> 31);
+	b[0] = (b[0] << 1) | (bit & 1u);
+}
+__device__ __forceinline__ int bits_corr(const unsigned *a, const unsigned *b) {   // equal positions of 127
+	return 127 - (__popc(a[0] ^ b[0]) + __popc(a[1] ^ b[1]) + __popc(a[2] ^ b[2]) + __popc((a[3] ^ b[3]) & 0x7FFFFFFFu));
+}
+
+__device__ __forceinline__ void ss_reset(DemodState &S) {     // symsync_crcf_reset: mf window, timing state, loop filter
+	S.ss_since_reset = 0;                                     // the mf-arm window is cleared, the dmf one is not
+	S.ss_rate = 1.5f; S.ss_del = 1.5f;                        // k / k_out = 3/2
+	S.ss_b = 0; S.ss_tau = 0.f; S.ss_q = 0.f; S.ss_q_hat = 0.f; S.ss_decim_counter = 0;
+	S.ss_v[0] = S.ss_v[1] = S.ss_v[2] = 0.f;
+}
+
+// Equaliser state of the demodulator warp.  Lane l (and lane l+16) owns tap l & 15: its weight, its window element
+// (x[0] oldest .. x[14] newest) and |x|^2.  w13 / w14 are warp-uniform copies of the weights of the two newest taps.
+struct EqL { cf w, x; float x2; cf w13, w14; };
+
+__device__ __forceinline__ cf conj_mul(cf w, cf v) {          // conj(w) * v
+	return make_float2(fmaf(w.x, v.x, w.y * v.y), fmaf(w.x, v.y, -(w.y * v.x)));
+}
+__device__ __forceinline__ cf half_warp_sum(cf p) {           // sum over the 16 lanes of a half-warp, result in every lane
+#pragma unroll
+	for(int m = 8; m >= 1; m >>= 1) {
+		p.x += __shfl_xor_sync(0xffffffffu, p.x, m);
+		p.y += __shfl_xor_sync(0xffffffffu, p.y, m);
+	}
+	return p;
+}
+__device__ __forceinline__ void eq_reset(DemodState &S, const DemodTables &T, EqL &E, int l16) {    // eqlms_cccf_reset
+	E.w = l16 < HFDL_EQ_LEN ? T.eq_h0[l16] : make_float2(0.f, 0.f);
+	E.w13 = T.eq_h0[13]; E.w14 = T.eq_h0[14];
+	E.x = make_float2(0.f, 0.f); E.x2 = 0.f;
+	S.eq_count = 0; S.eq_buf_full = 0; S.eq_x2_sum = 0.f;
+}
+__device__ __forceinline__ void eq_push(DemodState &S, EqL &E, cf r, int l16) {                     // eqlms_cccf_push
+	const float x2n = r.x * r.x + r.y * r.y;
+	const float x20 = __shfl_sync(0xffffffffu, E.x2, 0, 16);
+	const float xsx = __shfl_down_sync(0xffffffffu, E.x.x, 1, 16), xsy = __shfl_down_sync(0xffffffffu, E.x.y, 1, 16);
+	const float x2s = __shfl_down_sync(0xffffffffu, E.x2, 1, 16);
+	E.x = l16 == 14 ? r : make_float2(xsx, xsy);
+	E.x2 = l16 == 14 ? x2n : x2s;
+	S.eq_x2_sum = S.eq_x2_sum + x2n - x20;
+	S.eq_count++;
+}
+__device__ __forceinline__ cf eq_execute(const EqL &E, int l16) {                                   // eqlms_cccf_execute
+	cf p = conj_mul(E.w, E.x);
+	if(l16 >= HFDL_EQ_LEN) p = make_float2(0.f, 0.f);
+	return half_warp_sum(p);
+}
+// eqlms_cccf_step(d, d_hat = s): w += mu * conj(d - d_hat) * x / sum|x|^2, mu = 0.1 (hfdl.c:496,730-733)
+__device__ __forceinline__ void eq_step(DemodState &S, EqL &E, float d, cf s, cf x13, cf x14) {
+	bool run = true;
+	if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
+	if(run) {
+		const float inv = 1.0f / S.eq_x2_sum;
+		const cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);
+		const cf u = cmul(t, E.x), u13 = cmul(t, x13), u14 = cmul(t, x14);
+		E.w.x += u.x; E.w.y += u.y;
+		E.w13.x += u13.x; E.w13.y += u13.y;
+		E.w14.x += u14.x; E.w14.y += u14.y;
+	}
+}
+__device__ __forceinline__ void framer_reset(DemodState &S, const DemodTables &T, EqL &E, int l16) {   // hfdl.c:968-991
+	S.fr_state = HF_A1; S.symbols_wanted = 1; S.search_retries = 0; S.cur_arity = 1;
+	S.train_bits_total = S.train_bits_bad = 0; S.T_idx = 0; S.cur_buf = 0;
+	eq_reset(S, T, E, l16);
+	S.data_n = 0; S.training_n = 0;
+	ss_reset(S);
+	S.s_state = HS_EMIT_BITS; S.bitmask = 0;
+}
+
+// hard decision of liquid's modem_demodulate for BPSK / PSK4 / PSK8 (gray-coded symbol) + re-modulated point
+__device__ __forceinline__ unsigned modem_demod(int m, cf x, const cf (*psk)[8], cf *x_hat) {
+	unsigned sym;
+	if(m == 1) {
+		sym = (x.x > 0.f) ? 0u : 1u;
+		*x_hat = make_float2(sym ? -1.0f : 1.0f, 0.f);
+	} else {
+		// nearest constellation angle k*2pi/M: the same decision regions as liquid's atan2 + linear search
+		unsigned k;
+		const float ax = fabsf(x.x), ay = fabsf(x.y);
+		if(m == 2) {
+			k = (ax >= ay) ? (x.x > 0.f ? 0u : 2u) : (x.y > 0.f ? 1u : 3u);
+		} else {
+			const float t8 = 0.41421356237f;                 // tan(pi/8)
+			if(ay < t8 * ax) k = x.x > 0.f ? 0u : 4u;
+			else if(ax < t8 * ay) k = x.y > 0.f ? 2u : 6u;
+			else k = x.x > 0.f ? (x.y > 0.f ? 1u : 7u) : (x.y > 0.f ? 3u : 5u);
+		}
+		sym = k ^ (k >> 1);
+		*x_hat = psk[m][sym];
+	}
+	return sym;
+}
+
+#define HFDL_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#define HFDL_LIKELY(x) __builtin_expect(!!(x), 1)
+// a value polled from shared memory is made warp-uniform (lane 0's view) so that every lane takes the same branch
+#define HFDL_UNI(v) __shfl_sync(0xffffffffu, (int)(v), 0)
+
+// ---- output-ring entry tags ----------------------------------------------------------------------------------
+// w = gen[31:25] | more[24] | lap[23:20] | k[19:0]: reset generation of the timing warp, "another output of the same
+// input sample follows", (sequence number / ring size) mod 16, input-sample index of the output.
+__device__ __forceinline__ unsigned lk_tag(int gen, int more, int seq, int k) {
+	return ((unsigned)(gen & 0x7F) << 25) | ((unsigned)(more & 1) << 24) | ((unsigned)((seq >> 6) & 0xF) << 20) | (unsigned)k;
+}
+__device__ __forceinline__ bool lk_tag_ok(unsigned tag, int gen, int seq) {
+	return ((tag >> 20) & 0xFEFu) == ((((unsigned)gen & 0x7Fu) << 5) | (((unsigned)seq >> 6) & 0xFu));
+}
+
+// Costas step + rotation of one symsync output (hfdl.c:250-267,709-710)
+__device__ __forceinline__ cf costas_rotate(DemodState &S, float re, float im) {
+	S.c_phi += S.c_dphi;
+	{	// (double)phi > M_PI  <=>  phi > 3.1415925f (largest float below pi); 2*pi split hi+lo
+		const float dn = (S.c_phi - 6.2831855f) + 1.7484555e-7f, up = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
+		float w_ = S.c_phi;
+		w_ = S.c_phi > 3.1415925f ? dn : w_;
+		w_ = S.c_phi < -3.1415925f ? up : w_;
+		S.c_phi = w_;
+	}
+	float sn, cs;
+	hfdl_sincos_fast(S.c_phi, &sn, &cs);
+	return make_float2(re * cs + im * sn, im * cs - re * sn);
+}
+
+// ---- shared memory of one channel CTA (file scope: every access is a direct shared-window address) ----------
+__shared__ float4 lk_ring[HFDL_LK_RING];        // output ring: {sym.re, sym.im, AGC level, tag}
+__shared__ float lk_lvl[HFDL_LK_BR];            // AGC level ring (1/g after the sample's update)
+__shared__ cf lk_psk[4][8];
+__shared__ cf lk_train[16];
+__shared__ volatile int lk_loaded, lk_tail, lk_tail_k, lk_end_seq, lk_done;
+__shared__ volatile int lk_reset_gen, lk_reset_k, lk_reset_seq, lk_ack_gen;
+
+// Output-ring accessors.  An entry is written and read as ONE 16-byte shared-memory access and validated by its tag;
+// all accesses are volatile (the other warp changes the ring behind the compiler's back).
+#ifdef HFDL_CUSIM
+static inline void lk_ring_store(int i, float x, float y, float z, unsigned tag) {
+	volatile float *p = reinterpret_cast<volatile float *>(&lk_ring[i]);
+	p[0] = x; p[1] = y; p[2] = z;
+	__atomic_thread_fence(__ATOMIC_RELEASE);
+	reinterpret_cast<volatile unsigned *>(p)[3] = tag;
+}
+static inline float4 lk_ring_load(int i) {
+	// On the GPU the warp's 16-byte load is ONE converged access: every lane sees the same entry.  Host threads are
+	// not in lockstep, so the emulation reads through lane 0 and broadcasts (called by all 32 lanes of the warp).
+	volatile float *p = reinterpret_cast<volatile float *>(&lk_ring[i]);
+	float4 r;
+	unsigned t = reinterpret_cast<volatile unsigned *>(p)[3];
+	__atomic_thread_fence(__ATOMIC_ACQUIRE);
+	r.x = p[0]; r.y = p[1]; r.z = p[2];
+	r.x = __shfl_sync(0xffffffffu, r.x, 0); r.y = __shfl_sync(0xffffffffu, r.y, 0); r.z = __shfl_sync(0xffffffffu, r.z, 0);
+	r.w = __uint_as_float(__shfl_sync(0xffffffffu, t, 0));
+	return r;
+}
+static inline unsigned lk_ring_tag(int i) { return reinterpret_cast<volatile unsigned *>(&lk_ring[i])[3]; }
+#else
+__device__ __forceinline__ void lk_ring_store(int i, float x, float y, float z, unsigned tag) {
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]);
+	asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "f"(x), "f"(y), "f"(z), "f"(__uint_as_float(tag)) : "memory");
+}
+__device__ __forceinline__ float4 lk_ring_load(int i) {
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]);
+	float4 r;
+	asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sa) : "memory");
+	return r;
+}
+__device__ __forceinline__ unsigned lk_ring_tag(int i) {
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]) + 12u;
+	unsigned t;
+	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(sa) : "memory");
+	return t;
+}
+#endif
+
+// ---- fast runs -------------------------------------------------------------------------------------------------
+// Between two framer events the framer only counts symbols down (hfdl.c:774-777) and, inside a frame, neither the
+// noise-floor clock nor any loop reset can fire (both need FRAMER_A1_SEARCH).  demod_run() therefore processes
+// up to `nsym` whole symbols (an even + an odd symsync output each) as straight-line code specialised on the sampler
+// mode and the modulation, and hands control back to the generic per-output path for the symbol that triggers
+// the next framer event.  RUN_A1 is the preamble search (hfdl.c:779-793): every symbol is correlated against the A
+// sequence, the noise-floor clock ticks per input sample, and the run ends when A1 is found or a loop reset is due.
+enum { RUN_BITS = 0, RUN_TRAIN = 1, RUN_DATA = 2, RUN_SKIP = 3, RUN_A1 = 4 };
+
+template <int MODE, int ARITY>
+__device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k_prev, const int gen, const int nsym,
+		cf *dsym, const int lane, unsigned &symcnt, long long *p_twait, const bool cap, cf *cap_eq, int &cap_n, const int cap_max,
+		const float *lvl, const unsigned *A_bits) {
+	const int l16 = lane & 15;
+	int done = 0;
+	unsigned bacc = 0; int nacc = 0;             // RUN_BITS: bits collected since the last merge into S.bits
+	// E.x stays the canonical 15-element window; xs is the window of the NEXT symbol, already shifted by two:
+	// its lanes 0..12 hold the 13 elements that are known before that symbol's two outputs arrive
+	float drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16), drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16);
+	cf xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
+	float x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
+	cf P;
+	{ cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f); P = half_warp_sum(p); }
+	float4 e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)), e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+	for(;;) {
+		// warp vote: the lanes are not guaranteed to be converged at the prefetch, so the decision must not depend on
+		// one lane's view (a lane that saw a not-yet-valid entry sends the whole warp through the reload below)
+		if(HFDL_UNLIKELY(__ballot_sync(0xffffffffu, lk_tag_ok(__float_as_uint(e0.w), gen, seq) & lk_tag_ok(__float_as_uint(e1.w), gen, seq + 1)) != 0xffffffffu)) {
+			// both outputs of the symbol are not there yet: wait, or leave when the batch ends before them
+			bool ok = false;
+			for(;;) {
+				const long long t0 = hfdl_clock();
+				const int ack = HFDL_UNI(lk_ack_gen), end_seq = HFDL_UNI(lk_end_seq);
+				const unsigned t0w = (unsigned)HFDL_UNI(lk_ring_tag(seq & (HFDL_LK_RING - 1)));
+				const unsigned t1w = (unsigned)HFDL_UNI(lk_ring_tag((seq + 1) & (HFDL_LK_RING - 1)));
+				if(lk_tag_ok(t0w, gen, seq) && lk_tag_ok(t1w, gen, seq + 1)) { ok = true; break; }
+				if(ack == gen && seq + 1 >= end_seq) break;
+				HFDL_SPIN_PAUSE();
+				*p_twait += hfdl_clock() - t0;
+			}
+			if(!ok) break;
+			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+		}
+		const cf r0 = costas_rotate(S, e0.x, e0.y);
+		const cf r1 = costas_rotate(S, e1.x, e1.y);
+		const float lvl1 = e1.z;
+		const int k1 = (int)(__float_as_uint(e1.w) & 0xFFFFFu);
+		// ---- eqlms_cccf_push x2 + execute: the 13 older taps are already summed in P
+		const float x2a = r0.x * r0.x + r0.y * r0.y, x2b = r1.x * r1.x + r1.y * r1.y;
+		S.eq_x2_sum = S.eq_x2_sum + x2a - drop0;
+		S.eq_x2_sum = S.eq_x2_sum + x2b - drop1;
+		S.eq_count += 2;
+		cf s;
+		{
+			const cf a = conj_mul(E.w13, r0), b = conj_mul(E.w14, r1);
+			s = make_float2((P.x + a.x) + b.x, (P.y + a.y) + b.y);
+		}
+		E.x = l16 == 13 ? r0 : (l16 == 14 ? r1 : xs);
+		E.x2 = l16 == 13 ? x2a : (l16 == 14 ? x2b : x2s);
+		if(MODE == RUN_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
+			float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
+			if(S.bitmask & 1u) d = -d;
+			eq_step(S, E, d, s, r0, r1);
+			S.T_idx++;
+		}
+		seq += 2;
+		done++;
+		const bool last = (done == nsym);
+		// ---- prefetch the next symbol's entries, pre-shift the window for it and reduce its 13 known taps:
+		//      all of this is independent of the decision / phase-error chain below and overlaps with it
+		e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+		drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16); drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16);
+		xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
+		x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
+		{ cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f); P = half_warp_sum(p); }
+		// ---- slicer, Costas adjust
+		if(HFDL_UNLIKELY(cap)) { if(lane == 0 && cap_n < cap_max) cap_eq[cap_n] = s; cap_n++; }
+		cf x_hat;
+		unsigned bits = modem_demod(ARITY, s, lk_psk, &x_hat);
+		float err = s.y * x_hat.x - s.x * x_hat.y;
+		err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));
+		S.c_phi += 0.1f * err;
+		S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
+		symcnt++;
+		bool stop = last;
+		if(MODE == RUN_BITS) {
+			bacc = (bacc << 1) | ((bits ^ S.bitmask) & 1u);
+			if(++nacc == 32) {         // merge 32 bits at once: a whole-word shift of the 127-bit register
+				S.bits[3] = S.bits[2] & 0x7FFFFFFFu; S.bits[2] = S.bits[1]; S.bits[1] = S.bits[0]; S.bits[0] = bacc;
+				nacc = 0; bacc = 0;
+			}
+		} else if(MODE == RUN_TRAIN) {
+			if(S.training_n < HFDL_T_LEN) { if(lane == 0) lk_train[S.training_n] = s; S.training_n++; }
+		} else if(MODE == RUN_DATA) {
+			if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
+		} else if(MODE == RUN_A1) {
+			// noise-floor clock: one tick per input sample (k_prev, k1], update on every 256th (hfdl.c:700-706)
+			const int d = k1 - k_prev;
+			unsigned j = (0xFFu - (S.nf_clk & 0xFFu)) & 0xFFu;
+			if(j == 0u) j = 256u;
+			for(; HFDL_UNLIKELY((int)j <= d); j += 256u)
+				S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[k_prev + (int)j]) + 1e-6f;
+			S.nf_clk += (unsigned)d;
+			bits_push(S.bits, bits ^ S.bitmask);
+			const float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+			if(HFDL_UNLIKELY(fabsf(corr) > 0.36f)) {          // A1 found (hfdl.c:779-793)
+				S.st_a1++;
+				S.bitmask = corr > 0.f ? 0u : ~0u;
+				S.signal_level = lvl1;
+				S.frame_symbol_cnt = 1.0f;
+				S.symbols_wanted = HFDL_A_LEN;
+				S.search_retries = 0;
+				S.fr_state = HF_A2;
+				stop = true;
+			}
+			if(HFDL_UNLIKELY(fabsf(S.c_dphi) > 0.25f)) stop = true;      // Costas blow-up: the generic path resets the loops
+		}
+		if(MODE != RUN_A1) {
+			S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + lvl1, S.frame_symbol_cnt + 1.0f);
+			S.frame_symbol_cnt += 1.0f;
+		}
+		k_prev = k1;
+		S.symsync_out_idx += 2;
+		if(lane == 0) { lk_tail = seq; lk_tail_k = k_prev; }
+		if(stop) break;
+	}
+	if(MODE == RUN_BITS) {             // merge the remaining nacc < 32 bits
+		for(int i = nacc - 1; i >= 0; i--) bits_push(S.bits, bacc >> i);
+	}
+	if(MODE != RUN_A1) S.symbols_wanted -= done;
+	return done;
+}
+
+// loop_kernel: grid = C, block = 96 threads (warp 0 demodulator, warp 1 timing, warp 2 loader), dynamic smem = bank ring.
+__global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
+	HFDL_DYN_SMEM(cf, s_bank);                      // [HFDL_LK_BR][32]: arms 0..15 matched, 16..31 derivative
+	const int c = blockIdx.x;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const DemodTables &T = *a.tab;
+	const float *lvl = a.lvl + (long long)c * a.lvl_stride;
+	const int N = a.n_samples;
+	if(threadIdx.x < HFDL_LK_RING) lk_ring[threadIdx.x] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
+	if(threadIdx.x < 32) lk_psk[threadIdx.x >> 3][threadIdx.x & 7] = T.psk[threadIdx.x >> 3][threadIdx.x & 7];
+	if(threadIdx.x == 0) {
+		lk_loaded = 0; lk_tail = 0; lk_tail_k = -1; lk_end_seq = 0x7fffffff; lk_done = 0;
+		lk_reset_gen = 0; lk_reset_k = 0; lk_reset_seq = 0; lk_ack_gen = 0;
+	}
+	__syncthreads();
+
+	if(warp == 2) {
+		// =========================== loader warp ===========================
+		const cf *bank = a.bank + (long long)c * a.bank_stride * 32;
+		const int nchunks = (N + HFDL_LK_CH - 1) / HFDL_LK_CH;
+		for(int ch = 0; ch < nchunks + HFDL_LK_INFLIGHT; ch++) {
+			if(ch < nchunks) {
+				const int n0 = ch * HFDL_LK_CH;
+				// ring space: samples the demodulator warp has not passed yet must stay (the timing warp may be rolled back to them)
+				while(n0 + HFDL_LK_CH > HFDL_UNI(lk_tail_k) + 1 + HFDL_LK_BR - HFDL_LK_CH) {
+					if(HFDL_UNI(lk_done)) break;
+					HFDL_SPIN_PAUSE();
+				}
+				const int cnt = (N - n0 < HFDL_LK_CH) ? (N - n0) : HFDL_LK_CH;
+				const char *src = reinterpret_cast<const char *>(bank + (long long)n0 * 32);
+				char *dst = reinterpret_cast<char *>(s_bank + (n0 & (HFDL_LK_BR - 1)) * 32);
+				for(int i = lane; i < cnt * 16; i += 32) hfdl_cp_async16(dst + i * 16, src + (long long)i * 16);
+				if(lane < cnt) hfdl_cp_async4(&lk_lvl[(n0 + lane) & (HFDL_LK_BR - 1)], &lvl[n0 + lane]);
+			}
+			hfdl_cp_async_commit();
+			if(ch >= HFDL_LK_INFLIGHT - 1) {             // chunk ch-(INFLIGHT-1) has landed
+				hfdl_cp_async_wait<HFDL_LK_INFLIGHT - 1>();
+				__syncwarp();
+				__threadfence_block();
+				const int ready = (ch - (HFDL_LK_INFLIGHT - 1) + 1) * HFDL_LK_CH;
+				if(lane == 0) lk_loaded = ready < N ? ready : N;
+			}
+		}
+		hfdl_cp_async_wait<0>();
+	} else if(warp == 1) {
+		// =========================== timing warp (producer) ===========================
+		DemodState S = a.state[c];
+		const cf *mfo = a.mfo + (long long)c * a.mfo_stride + HFDL_MFO_HIST;
+		const float ss_a1 = T.ss_a1, ss_a2 = T.ss_a2, ss_b0 = T.ss_b0, ss_radj = T.ss_rate_adj;
+		int kn = 0;                         // next input sample (generic stepping), or the sample of the next output (fast loop)
+		bool mid = false;                   // generic stepping: sample kn has been consumed, its outputs are being produced
+		int seq = 0;                        // sequence number of the next output
+		int my_gen = 0;
+		bool finished = false;
+		long long t_begin = hfdl_clock(), t_wait = 0;
+		// one symsync output at input sample k_, arm index b_ (symsync_crcf_step body); TED_ = timing-error detector runs
+#define HFDL_SS_TED(mf_, row_, bb_) do { \
+			const cf dmf_ = (row_)[16 + (bb_)]; \
+			const float q_ = fminf(fmaxf(mf_.x * dmf_.x + mf_.y * dmf_.y, -1.0f), 1.0f);     /* Re(conj(mf)*dmf), clipped */ \
+			S.ss_q = q_; \
+			S.ss_v[2] = S.ss_v[1]; S.ss_v[1] = S.ss_v[0]; \
+			S.ss_v[0] = q_ - ss_a1 * S.ss_v[1] - ss_a2 * S.ss_v[2]; \
+			S.ss_q_hat = ss_b0 * S.ss_v[0]; \
+			S.ss_rate += ss_radj * S.ss_q_hat; \
+			S.ss_del = S.ss_rate + S.ss_q_hat; \
+		} while(0)
+		for(;;) {
+			// ---------------- control: resets, ring room, loader progress, end of batch ----------------
+			const int p_gen = HFDL_UNI(lk_reset_gen);
+			if(HFDL_UNLIKELY(p_gen != my_gen)) {            // symsync_crcf_reset posted by the demodulator warp: roll back
+				my_gen = p_gen;
+				__threadfence_block();
+				kn = HFDL_UNI(lk_reset_k) + 1; seq = HFDL_UNI(lk_reset_seq); mid = false;
+				ss_reset(S);
+				finished = false;
+				__syncwarp();
+				if(lane == 0) { lk_end_seq = 0x7fffffff; __threadfence_block(); lk_ack_gen = my_gen; }
+				continue;
+			}
+			if(HFDL_UNLIKELY(finished)) {
+				if(HFDL_UNI(lk_done)) break;
+				const long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); t_wait += hfdl_clock() - t0;
+				continue;
+			}
+			if(!mid && kn >= N) {                           // every input sample of the batch has been processed
+				finished = true;
+				__syncwarp();
+				if(lane == 0) { __threadfence_block(); lk_end_seq = seq; }
+				continue;
+			}
+			const int seq_lim = HFDL_UNI(lk_tail) + HFDL_LK_RING - 2;       // entries [tail, seq) are unread
+			int k_lim = HFDL_UNI(lk_loaded);
+			if(seq >= seq_lim || (!mid && kn >= k_lim)) { const long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); t_wait += hfdl_clock() - t0; continue; }
+			__threadfence_block();
+
+			if(S.ss_since_reset >= HFDL_SS_SUB && S.ss_decim_counter == 1u && S.ss_b >= 0) {
+				// ---------------- fast loop: per output, two outputs (one symbol) per iteration ----------------
+				float tau = S.ss_tau;
+				int k = kn + (S.ss_b >> 4), b = S.ss_b & 15;
+				tau -= (float)(S.ss_b >> 4);
+				int odd = 0;                     // 0: the next output is the non-TED one of the pair
+				int rare = 0;
+				while(k < k_lim && seq < seq_lim) {
+					const cf *row = s_bank + (k & (HFDL_LK_BR - 1)) * 32;
+					const cf mf = row[b];
+					const float level = lk_lvl[k & (HFDL_LK_BR - 1)];
+					if(odd) HFDL_SS_TED(mf, row, b);
+					tau += S.ss_del;
+					const int bi = hfdl_round_pos(tau * (float)HFDL_SS_NPFB);
+					if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_tag(my_gen, bi < HFDL_SS_NPFB, seq, k));
+					seq++;
+					odd ^= 1;
+					if(HFDL_UNLIKELY(bi < HFDL_SS_NPFB)) { b = bi; rare = 1; break; }     // del < 1: another output of the same sample
+					const int m = bi >> 4;
+					k += m; tau -= (float)m; b = bi & 15;
+				}
+				// back to the generic representation
+				S.ss_tau = tau; S.ss_b = b; S.ss_decim_counter = odd ? 2u : 1u;
+				kn = k; mid = rare != 0;
+				continue;
+			}
+			// ---------------- generic stepping (after a reset, odd alignment, rare cases) ----------------
+			if(!mid) {
+				if(S.ss_since_reset < HFDL_SS_SUB) S.ss_since_reset++;      // the push itself happened in bank_kernel
+				mid = true;
+			}
+			if(S.ss_b < HFDL_SS_NPFB) {                                     // while(b < npfb) { output ... }
+				const int bb = S.ss_b < 0 ? 0 : S.ss_b;
+				const cf *row = s_bank + (kn & (HFDL_LK_BR - 1)) * 32;
+				cf mf = row[bb];
+				if(S.ss_since_reset < HFDL_SS_SUB) {        // window still filling after a reset: only samples pushed since then count
+					mf = make_float2(0.f, 0.f);
+					const float *h = T.ss_mf[bb];
+					for(int j = (int)S.ss_since_reset - 1; j >= 0; j--) { const cf v = mfo[kn - j]; mf.x += h[j] * v.x; mf.y += h[j] * v.y; }
+				}
+				if(S.ss_decim_counter == 2u) { S.ss_decim_counter = 0; HFDL_SS_TED(mf, row, bb); }
+				S.ss_decim_counter++;
+				S.ss_tau += S.ss_del;
+				S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);
+				if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, lk_lvl[kn & (HFDL_LK_BR - 1)], lk_tag(my_gen, S.ss_b < HFDL_SS_NPFB, seq, kn));
+				seq++;
+			} else {
+				S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;                   // ... then tau -= 1, b -= npfb
+				kn++; mid = false;
+			}
+		}
+#undef HFDL_SS_TED
+		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 4 + 0] += hfdl_clock() - t_begin; a.dbg_cycles[c * 4 + 1] += t_wait; }
+		// timing-loop state after the last input sample of the batch (kn may lie beyond it: undo the skipped samples)
+		__syncwarp();
+		if(lane == 0) {
+			const int over = kn - N;
+			DemodState *G = &a.state[c];
+			G->ss_since_reset = S.ss_since_reset; G->ss_decim_counter = S.ss_decim_counter; G->ss_rate = S.ss_rate; G->ss_del = S.ss_del;
+			G->ss_tau = S.ss_tau + (float)over; G->ss_bf = 0.f; G->ss_q = S.ss_q; G->ss_q_hat = S.ss_q_hat; G->ss_b = S.ss_b + HFDL_SS_NPFB * over;
+			G->ss_v[0] = S.ss_v[0]; G->ss_v[1] = S.ss_v[1]; G->ss_v[2] = S.ss_v[2];
+		}
+	} else {
+		// =========================== demodulator warp (consumer) ===========================
+		DemodState S = a.state[c];
+		const int l16 = lane & 15;
+		const bool cap = (c == a.cap_channel);
+		int cap_n_eq = cap ? a.cap_cnt[1] : 0;
+		cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+		const unsigned long long cnt_base = S.sample_cnt;
+		unsigned symcnt = (unsigned)S.symbol_cnt;
+		unsigned A_bits[4];
+#pragma unroll
+		for(int i = 0; i < 4; i++) A_bits[i] = T.A_bits[i];
+		EqL E;
+		E.w = l16 < HFDL_EQ_LEN ? a.state[c].eq_w[l16] : make_float2(0.f, 0.f);
+		E.x = l16 < HFDL_EQ_LEN ? a.state[c].eq_win[l16] : make_float2(0.f, 0.f);
+		E.x2 = l16 < HFDL_EQ_LEN ? a.state[c].eq_x2[l16] : 0.f;
+		E.w13 = a.state[c].eq_w[13]; E.w14 = a.state[c].eq_w[14];
+		if(lane < 16) lk_train[lane] = lane < HFDL_T_LEN ? a.state[c].training[lane] : make_float2(0.f, 0.f);
+		__syncwarp();
+#define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1) { if((++S.nf_clk & 0xFFu) == 0xFFu) \
+			S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } } while(0)     /* hfdl.c:700-706 */
+		int seq = 0, k_prev = -1, gen = 0;
+		bool reset_pending = false;
+		long long t_begin = hfdl_clock(), t_wait = 0;
+		for(;;) {
+			// fast path: a run of whole symbols up to (not including) the symbol of the next framer event
+#define HFDL_RUN(MODE, AR) demod_run<MODE, AR>(S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, &t_wait, cap, a.cap_eq, cap_n_eq, a.cap_max, lvl, A_bits)
+			if(S.fr_state == HF_A1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode != 2
+					&& fabsf(S.c_dphi) <= 0.25f && symcnt + 1u < 13u * HFDL_SINGLE_SLOT_FRAME_LEN) {
+				const int nsym = (int)(13u * HFDL_SINGLE_SLOT_FRAME_LEN - 1u - symcnt);     // the symbol of the 13-frame timeout goes the generic way
+				if(HFDL_RUN(RUN_A1, 1) > 0) continue;
+			} else if(S.fr_state > HF_A1 && S.symbols_wanted > 1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode != 2) {
+				const int nsym = S.symbols_wanted - 1;
+				int did;
+				if(S.s_state == HS_EMIT_BITS) did = HFDL_RUN(RUN_BITS, 1);
+				else if(S.s_state == HS_SKIP) did = HFDL_RUN(RUN_SKIP, 1);
+				else if(S.cur_buf == 0) did = HFDL_RUN(RUN_TRAIN, 1);
+				else if(S.cur_arity == 1) did = HFDL_RUN(RUN_DATA, 1);
+				else if(S.cur_arity == 2) did = HFDL_RUN(RUN_DATA, 2);
+				else did = HFDL_RUN(RUN_DATA, 3);
+				if(did > 0) continue;
+			}
+#undef HFDL_RUN
+			// ---- generic path: one symsync output
+			unsigned tagw;
+			bool have = false;
+			for(;;) {
+				tagw = (unsigned)HFDL_UNI(lk_ring_tag(seq & (HFDL_LK_RING - 1)));
+				if(lk_tag_ok(tagw, gen, seq)) { have = true; break; }
+				if(HFDL_UNI(lk_ack_gen) == gen && seq >= HFDL_UNI(lk_end_seq)) break;
+				const long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); t_wait += hfdl_clock() - t0;
+			}
+			if(!have) break;                                          // end of batch: every output consumed
+			const float4 ent = lk_ring_load(seq & (HFDL_LK_RING - 1));
+			tagw = __float_as_uint(ent.w);
+			const int k = (int)(tagw & 0xFFFFFu);
+			const bool more = (tagw >> 24) & 1u;
+			const float level = ent.z;
+			// noise-floor clock ticks once per input sample, before that sample's outputs (hfdl.c:700)
+			if(HFDL_UNLIKELY(S.fr_state == HF_A1)) { for(int sidx = k_prev + 1; sidx <= k; sidx++) HFDL_NF_TICK(sidx); }
+			k_prev = k;
+			do {
+				// ---- Costas step + rotate (hfdl.c:250-294,709-715)
+				const cf r = costas_rotate(S, ent.x, ent.y);
+				if(HFDL_UNLIKELY(S.fr_state == HF_A1 && fabsf(S.c_dphi) > 0.25f)) {
+					S.c_phi = S.c_dphi = 0.f;
+					reset_pending = true;                              // symsync_crcf_reset
+				}
+				eq_push(S, E, r, l16);
+				if(!(S.symsync_out_idx & 1u)) break;
+				const cf s = eq_execute(E, l16);
+				if(S.fr_state == HF_EQ_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
+					float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
+					if(S.bitmask & 1u) d = -d;
+					const cf x13 = make_float2(__shfl_sync(0xffffffffu, E.x.x, 13, 16), __shfl_sync(0xffffffffu, E.x.y, 13, 16));
+					eq_step(S, E, d, s, x13, r);
+					S.T_idx++;
+				}
+				if(HFDL_UNLIKELY(cap)) { if(lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s; cap_n_eq++; }
+				cf x_hat;
+				unsigned bits = modem_demod(S.cur_arity, s, lk_psk, &x_hat);
+				// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
+				float err = s.y * x_hat.x - s.x * x_hat.y;
+				err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
+				S.c_phi += 0.1f * err;
+				S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
+
+				symcnt++;
+				if(HFDL_UNLIKELY(S.fr_state == HF_A1 && symcnt >= 13u * HFDL_SINGLE_SLOT_FRAME_LEN)) {
+					symcnt = 0;
+					S.c_phi = S.c_dphi = 0.f;
+					reset_pending = true;
+				}
+				if(S.s_state == HS_EMIT_BITS) {
+					bits ^= S.bitmask;
+					for(int bb = 0; bb < S.cur_arity; bb++, bits >>= 1) bits_push(S.bits, bits);
+				} else if(S.s_state == HS_EMIT_SYMBOLS) {
+					if(S.cur_buf == 0) {
+						if(S.training_n < HFDL_T_LEN) { if(lane == 0) lk_train[S.training_n] = s; S.training_n++; }
+					} else {
+						if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
+					}
+				}
+				if(S.fr_state > HF_A1) {
+					S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + level, S.frame_symbol_cnt + 1.0f);
+					S.frame_symbol_cnt += 1.0f;
+				}
+				if(S.symbols_wanted > 1) { S.symbols_wanted--; break; }
+
+				switch(S.fr_state) {
+				case HF_A1: {
+					float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+					if(fabsf(corr) > 0.36f) {
+						S.st_a1++;
+						S.bitmask = corr > 0.f ? 0u : ~0u;
+						S.signal_level = level;
+						S.frame_symbol_cnt = 1.0f;
+						S.symbols_wanted = HFDL_A_LEN;
+						S.search_retries = 0;
+						S.fr_state = HF_A2;
+					}
+					break; }
+				case HF_A2: {
+					float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+					if(fabsf(corr) > 0.3f) {
+						S.a2_sample_cnt = cnt_base + (unsigned long long)k;
+						S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
+						S.st_a2++;
+						S.symbols_wanted = 127;
+						S.search_retries = 0;
+						S.fr_state = HF_M1;
+					} else if(++S.search_retries >= 3) {
+						framer_reset(S, T, E, l16); reset_pending = true;
+					}
+					break; }
+				case HF_M1: {
+					float max_corr = 0.f; int max_idx = -1;
+					for(int idx = 0; idx < 8; idx++) {
+						float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
+						if(corr > max_corr) { max_corr = corr; max_idx = idx; }
+					}
+					if(max_corr > 0.3f) {
+						S.st_m1++;
+						S.data_segment_cnt = T.mode_segments[max_idx];
+						S.data_arity = T.mode_arity[max_idx];
+						S.M1 = max_idx;
+						S.symbols_wanted = 15;
+						S.search_retries = 0;
+						S.fr_state = HF_M2_SKIP;
+						S.s_state = HS_SKIP;
+					} else {
+						framer_reset(S, T, E, l16); reset_pending = true;
+					}
+					break; }
+				case HF_M2_SKIP:
+					S.training_n = 0;
+					S.symbols_wanted = HFDL_T_LEN;
+					S.eq_train_seq_cnt = 9;
+					S.fr_state = HF_EQ_TRAIN;
+					S.s_state = HS_EMIT_SYMBOLS;
+					break;
+				case HF_EQ_TRAIN: {
+					__syncwarp();
+					unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
+#pragma unroll
+					for(int j = 0; j < HFDL_T_LEN; j++) {
+						unsigned bit = (lk_train[j].x > 0.f) ? 0u : 1u;
+						bit ^= (S.bitmask & 1u);
+						tseq = (tseq << 1) | bit;
+					}
+					__syncwarp();
+					S.train_bits_total += HFDL_T_LEN;
+					S.train_bits_bad += __popc(0x9AFu ^ tseq);
+					S.training_n = 0;
+					if(S.eq_train_seq_cnt > 1) {
+						S.eq_train_seq_cnt--;
+						S.symbols_wanted = HFDL_T_LEN;
+						S.T_idx = 0;
+					} else if(S.data_segment_cnt > 0) {
+						S.symbols_wanted = 15;
+						S.fr_state = HF_DATA_1;
+						S.cur_arity = S.data_arity;
+						S.cur_buf = 1;
+					} else {                                 // end of frame: hand the symbols to fec_kernel
+						int q = 0;
+						if(lane == 0) q = atomicAdd(a.nframes, 1);
+						q = __shfl_sync(0xffffffffu, q, 0);
+						if(q < a.max_frames && lane == 0) {
+							FrameRec fr;
+							fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
+							fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
+							fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = cnt_base + (unsigned long long)k;
+							fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
+							a.frames[q] = fr;
+						}
+						S.st_frames++;
+						S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
+						dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+						framer_reset(S, T, E, l16); reset_pending = true;
+						symcnt = 0;
+					}
+					break; }
+				case HF_DATA_1:
+					S.symbols_wanted = 15;
+					S.fr_state = HF_DATA_2;
+					break;
+				case HF_DATA_2:
+					S.data_segment_cnt--;
+					S.cur_arity = 1;
+					S.cur_buf = 0;
+					S.fr_state = HF_EQ_TRAIN;
+					S.eq_train_seq_cnt = 1;
+					S.symbols_wanted = HFDL_T_LEN;
+					S.T_idx = 0;
+					break;
+				}
+			} while(0);
+			S.symsync_out_idx++;
+			seq++;
+			__syncwarp();
+			if(lane == 0) { lk_tail = seq; lk_tail_k = k; }
+			if(HFDL_UNLIKELY(reset_pending) && !more) {
+				// symsync_crcf_reset happened while processing the outputs of input sample k: outputs of that sample that
+				// were already produced kept their (old-state) value; the timing warp restarts with sample k+1
+				gen = (gen + 1) & 0x7F;
+				__syncwarp();
+				if(lane == 0) { lk_reset_k = k; lk_reset_seq = seq; __threadfence_block(); lk_reset_gen = gen; }
+				reset_pending = false;
+			}
+		}
+		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 4 + 2] += hfdl_clock() - t_begin; a.dbg_cycles[c * 4 + 3] += t_wait; }
+		for(int sidx = k_prev + 1; sidx < N; sidx++) HFDL_NF_TICK(sidx);      // input samples after the last output
+#undef HFDL_NF_TICK
+		S.sample_cnt = cnt_base + (unsigned long long)N;
+		S.symbol_cnt = symcnt;
+		__syncwarp();
+		DemodState *G = &a.state[c];
+		if(lane < HFDL_EQ_LEN) { G->eq_w[lane] = E.w; G->eq_win[lane] = E.x; G->eq_x2[lane] = E.x2; G->training[lane] = lk_train[lane]; }
+		__syncwarp();
+		if(lane == 0) {
+			// everything except the timing-loop fields (owned by the timing warp) and the per-lane equaliser arrays (written above)
+			G->eq_x2_sum = S.eq_x2_sum; G->eq_count = S.eq_count; G->eq_buf_full = S.eq_buf_full;
+			G->c_phi = S.c_phi; G->c_dphi = S.c_dphi;
+			for(int i = 0; i < 4; i++) G->bits[i] = S.bits[i];
+			G->training_n = S.training_n; G->data_n = S.data_n; G->cur_buf = S.cur_buf; G->slot = S.slot;
+			G->symbol_cnt = S.symbol_cnt; G->sample_cnt = S.sample_cnt; G->a2_sample_cnt = S.a2_sample_cnt;
+			G->s_state = S.s_state; G->fr_state = S.fr_state; G->data_arity = S.data_arity; G->cur_arity = S.cur_arity;
+			G->symbols_wanted = S.symbols_wanted; G->search_retries = S.search_retries; G->eq_train_seq_cnt = S.eq_train_seq_cnt;
+			G->data_segment_cnt = S.data_segment_cnt; G->train_bits_total = S.train_bits_total; G->train_bits_bad = S.train_bits_bad;
+			G->T_idx = S.T_idx; G->M1 = S.M1; G->bitmask = S.bitmask; G->symsync_out_idx = S.symsync_out_idx;
+			G->freq_err_hz = S.freq_err_hz; G->signal_level = S.signal_level; G->noise_floor = S.noise_floor;
+			G->nf_clk = S.nf_clk; G->frame_symbol_cnt = S.frame_symbol_cnt;
+			G->st_a1 = S.st_a1; G->st_a2 = S.st_a2; G->st_m1 = S.st_m1; G->st_frames = S.st_frames;
+			if(cap) a.cap_cnt[1] = cap_n_eq;
+			__threadfence_block();
+			lk_done = 1;
+		}
+	}
+}

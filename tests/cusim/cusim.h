@@ -121,9 +121,9 @@ template <typename T> static inline T shfl_any(T v, int src) {
 #define __shared__ static
 static inline void __syncthreads() { cusim::t_ctx->bar->wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { cusim::t_warp->bar.wait(); }
-template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return cusim::shfl_any(v, src); }
+template <typename T> static inline T __shfl_sync(unsigned, T v, int src, int w = 32) { int base = (int)cusim::t_lane & ~(w - 1); return cusim::shfl_any(v, base + (src & (w - 1))); }
 template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return cusim::shfl_any(v, (int)cusim::t_lane ^ m); }
-template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d, int = 32) { int s = (int)cusim::t_lane + d; return cusim::shfl_any(v, s > 31 ? (int)cusim::t_lane : s); }
+template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d, int w = 32) { int l = (int)cusim::t_lane, s = l + d; return cusim::shfl_any(v, (s & ~(w - 1)) != (l & ~(w - 1)) ? l : s); }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d, int = 32) { int s = (int)cusim::t_lane - d; return cusim::shfl_any(v, s < 0 ? (int)cusim::t_lane : s); }
 static inline unsigned __ballot_sync(unsigned, int pred) {
 	cusim::t_warp->xch[cusim::t_lane] = pred ? 1u : 0u;
@@ -151,6 +151,8 @@ static inline void __threadfence_block() { __atomic_thread_fence(__ATOMIC_SEQ_CS
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline unsigned __float_as_uint(float f) { unsigned i; memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); return f; }
 #define CUSIM_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(cusim::t_ctx->dyn_smem)
 
 /* ---------------- minimal CUDA runtime stand-in for the host code ---------------- */
