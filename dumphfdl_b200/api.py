@@ -60,6 +60,8 @@ def bind(L):
     L.hfdl_b200_profile_read.argtypes = [vp, C.c_int32, vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
     L.hfdl_b200_kernel_launches.argtypes = [vp]
     L.hfdl_b200_kernel_launches.restype = C.c_int64
+    L.hfdl_b200_result_bytes_per_batch.argtypes = [vp]
+    L.hfdl_b200_result_bytes_per_batch.restype = C.c_int64
     L.hfdl_b200_read_checkpoint.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int64]
     L.hfdl_b200_read_checkpoint.restype = C.c_int64
     L.hfdl_b200_fft_forward.argtypes = [C.c_int32, vp, vp, C.c_int32, C.c_int32]
@@ -223,6 +225,9 @@ class Frontend:
 
     def launches(self):
         return self.L.hfdl_b200_kernel_launches(self.h)
+
+    def result_bytes_per_batch(self):
+        return self.L.hfdl_b200_result_bytes_per_batch(self.h)
 
     def close(self):
         if self.h:

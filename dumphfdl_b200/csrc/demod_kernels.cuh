@@ -30,7 +30,7 @@
 #define HFDL_DATA_SYMS_MAX 5040
 #define HFDL_MAX_PDU 945
 #define HFDL_SINGLE_SLOT_FRAME_LEN 4219     // hfdl.c:41
-#define HFDL_FRAME_SLOTS 4                  // data-symbol buffers per channel (frames in flight per batch)
+#define HFDL_FRAME_SLOTS_MIN 4              // data-symbol buffers per channel: run-time value, >= 2 x (frames a batch can end per channel)
 #define HFDL_AGC_HIST (HFDL_MF_TAPS - 1 + HFDL_SS_SUB - 1)   // AGC-output samples kept in front of a batch (35)
 #define HFDL_MFO_HIST (HFDL_SS_SUB - 1)                     // matched-filter outputs kept in front of a batch (17)
 #define HFDL_BANK_TILE 64
@@ -227,7 +227,7 @@ __global__ void demod_carry(cf *agc_out, long long agc_stride, cf *mfo, long lon
 // ======================================================================================
 struct FecArgs {
 	const FrameRec *frames; const int *nframes; int max_frames;
-	const cf *datasym;                 // [C][SLOTS][5040]; or a bare symbol array when frames[].channel/slot are 0
+	const cf *datasym; int nslots;     // [C][nslots][5040]; or a bare symbol array when frames[].channel/slot are 0
 	const DemodTables *tab;
 	PduRec *pdus;                      // [max_frames]
 	unsigned char *soft_out;           // optional [max_frames][15120] soft bits in push order (debug/parity)
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(32) fec_kernel(FecArgs a) {
 	const int nsym = T.mode_segments[M1] * 30;
 	const int nenc = nsym * arity;
 	const int ncol = nenc / 40;
-	const cf *sym = a.datasym + ((long long)fr.channel * HFDL_FRAME_SLOTS + fr.slot) * HFDL_DATA_SYMS_MAX;
+	const cf *sym = a.datasym + ((long long)fr.channel * a.nslots + fr.slot) * HFDL_DATA_SYMS_MAX;
 	unsigned char *vin = sm;                                  // [<=15120] Viterbi input
 	unsigned char *table = sm + HFDL_FEC_VIN_MAX;             // [40][ncol], later overlaid by the decisions
 	uint2 *dec = reinterpret_cast<uint2 *>(sm + HFDL_FEC_VIN_MAX);   // [nbits+6] (.x even states, .y odd states)

@@ -1,5 +1,6 @@
 // dumphfdl_b200/csrc/frontend.cu -- host driver + C ABI (include/hfdl_b200.h) of the B200 front-end.
-// Owns the CUDA stream, the HBM layout and the batch schedule; all arithmetic on the sample path runs
+// Owns the CUDA streams, the HBM layout and the batch schedule (a four-stream software pipeline across batches,
+// see enqueue_batch); all arithmetic on the sample path runs
 // in the kernels of ddc_kernels.cuh / demod_kernels.cuh.  There is no CPU implementation of the path
 // in this library: without a CUDA device hfdl_b200_create() fails.
 #include <vector>
@@ -75,23 +76,29 @@ struct hfdl_b200_frontend {
 	FftPlan plan;
 	int C = 0, Bmax = 0, sfmt = 0, bps = 0, out_per_block = 0;
 	float resamp_rate = 0;
-	cudaStream_t stream = nullptr, stream2 = nullptr;
-	cudaEvent_t ev_rs = nullptr, ev_sub[HFDL_NSUB] = { nullptr };
+	// streams: front (H2D, FFT, channeliser, resampler) | agc/bank | loop | fec + D2H.  Batch i+1's front, agc and
+	// bank stages run while batch i is still in the loop kernels; fec of batch i runs beside loop of batch i+1.
+	cudaStream_t stream = nullptr, stream2 = nullptr, st_loop = nullptr, st_fec = nullptr;
+	cudaEvent_t ev_front[2] = { nullptr, nullptr }, ev_agc_done[2] = { nullptr, nullptr }, ev_fec_done[2] = { nullptr, nullptr };
+	cudaEvent_t ev_sub[2][HFDL_NSUB] = { { nullptr } }, ev_loop[2][HFDL_NSUB] = { { nullptr } }, ev_h2d = nullptr;
+	struct Flight { bool busy = false; int nsub = 0; long long s0[HFDL_NSUB], s1[HFDL_NSUB]; } flight[2];
+	long long batch_seq = 0;        // batches enqueued so far; set p = batch_seq & 1
+	int nslots = HFDL_FRAME_SLOTS_MIN;
 	FftEngine fft;
 	// device memory
 	cf *d_work = nullptr; void *d_ring = nullptr; long long ring_len = 0;
 	cf *d_tapslice = nullptr; int *d_offsetbin = nullptr; float *d_dsa_rate = nullptr;
 	cf *d_bb = nullptr; long long bb_stride = 0;
-	cf *d_rs = nullptr; long long rs_stride = 0; float *d_rs_h = nullptr;
+	cf *d_rs[2] = { nullptr, nullptr }; long long rs_stride = 0; float *d_rs_h = nullptr;
 	DemodTables *d_tab = nullptr; DemodState *d_state = nullptr; AgcState *d_agc_state = nullptr; cf *d_datasym = nullptr;
 	cf *d_agc = nullptr, *d_mfo = nullptr, *d_bank = nullptr; float *d_lvl = nullptr; long long agc_stride = 0, mfo_stride = 0;
 	long long cap_n = 0;            // AGC/MF checkpoint samples captured so far
-	FrameRec *d_frames = nullptr; int *d_nframes = nullptr; PduRec *d_pdus = nullptr; int max_frames = 0;
+	FrameRec *d_frames[2] = { nullptr, nullptr }; int *d_nframes[2] = { nullptr, nullptr }; PduRec *d_pdus[2] = { nullptr, nullptr }; int max_frames = 0;
 	cf *d_cap_agc = nullptr, *d_cap_mf = nullptr, *d_cap_eq = nullptr; int *d_cap_cnt = nullptr;
 	cf *d_tmp = nullptr; long long tmp_len = 0;
 	long long *d_dbg = nullptr;
 	// host state
-	PduRec *h_pdus = nullptr; int *h_nframes = nullptr;
+	PduRec *h_pdus[2] = { nullptr, nullptr }; int *h_nframes[2] = { nullptr, nullptr };
 	long long fed = 0;              // samples pushed so far (host-fed path)
 	long long blocks_done = 0;      // overlap-save blocks processed
 	unsigned long long rs_phi0 = 0; unsigned rs_step = 0;
@@ -190,10 +197,59 @@ void to_pdu(const hfdl_b200_frontend *fe, const PduRec &r, hfdl_b200_pdu_t &p) {
 }
 
 // one group of nb <= Bmax blocks: FFT -> channel extract -> resample -> demod -> FEC -> PDUs to host
+// Results of one finished batch: PDU records of set q -> host queue.
+int collect_batch(hfdl_b200_frontend *fe, int q) {
+	if(!fe->flight[q].busy) return 0;
+	CK(cudaEventSynchronize(fe->ev_fec_done[q]));
+	fe->flight[q].busy = false;
+	int nfr = *fe->h_nframes[q];
+	if(nfr > fe->max_frames) {
+		fprintf(stderr, "hfdl_b200: frame queue overflow (%d > %d), frames dropped\n", nfr, fe->max_frames);
+		nfr = fe->max_frames;
+	}
+	if(nfr > 0) {
+		const PduRec *hp = fe->h_pdus[q];
+		// canonical order within a batch: (end sample, channel) -- the reference emits in thread-race order
+		std::vector<int> order((size_t)nfr);
+		for(int i = 0; i < nfr; i++) order[(size_t)i] = i;
+		std::sort(order.begin(), order.end(), [&](int x, int y) {
+			const PduRec &a = hp[x], &b = hp[y];
+			if(a.sample_cnt_end != b.sample_cnt_end) return a.sample_cnt_end < b.sample_cnt_end;
+			return a.channel < b.channel;
+		});
+		for(int i : order) { hfdl_b200_pdu_t p; to_pdu(fe, hp[i], p); fe->pduq.push_back(p); }
+	}
+	return 0;
+}
+
+// Everything enqueued so far has finished and its PDUs are in the host queue (oldest batch first).
+int drain(hfdl_b200_frontend *fe) {
+	const int p = (int)(fe->batch_seq & 1);
+	if(collect_batch(fe, p)) return -1;          // set p holds the older of the two batches in flight
+	if(collect_batch(fe, p ^ 1)) return -1;
+	CK(cudaStreamSynchronize(fe->stream));
+	CK(cudaStreamSynchronize(fe->stream2));
+	CK(cudaStreamSynchronize(fe->st_loop));
+	CK(cudaStreamSynchronize(fe->st_fec));
+	return 0;
+}
+
+// One batch of nb overlap-save blocks, fully asynchronous.  Stages and the stream each runs on:
+//   front  (stream)   FFT passes, chan_extract, resamp -> d_rs[p]
+//   agc    (stream2)  per sub-range: agc_kernel, bank_kernel            (work arrays shared by consecutive batches)
+//   loop   (st_loop)  per sub-range: loop_kernel                        (the latency-bound stage: sets the pace)
+//   fec    (st_fec)   fec_kernel, D2H of the PDU records of set p
+// Hazards between batch i and i+1 are ordered with events: the agc stage of a sub-range waits for the loop launches
+// of the previous batch that still read those samples; the resampler waits until the agc stage of batch i-2 has
+// read d_rs[p]; the first loop launch waits until fec of batch i-2 has released the frame records of set p.
+// The host collects the PDUs of batch i-1 after it has enqueued batch i.
 int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
-	cudaStream_t st = fe->stream;
+	const int p = (int)(fe->batch_seq & 1);
+	if(collect_batch(fe, p)) return -1;          // batch i-2 (normally collected long ago)
+	cudaStream_t st = fe->stream, st2 = fe->stream2, stl = fe->st_loop, stf = fe->st_fec;
 	const auto &g = fe->g;
-	CK(cudaMemsetAsync(fe->d_nframes, 0, sizeof(int), st));
+	hfdl_b200_frontend::Flight &prev = fe->flight[p ^ 1];
+	hfdl_b200_frontend::Flight &cur = fe->flight[p];
 	if(run_fft(fe, fe->fft, fe->plan, src, fe->d_work, nb, st)) return -1;
 	ProfRec pr;
 	{
@@ -215,9 +271,10 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 		unsigned long long span = (unsigned long long)n_in << 24;
 		if(fe->rs_phi0 < span) n_out = (int)((span - fe->rs_phi0 + fe->rs_step - 1) / fe->rs_step);
 		ResampArgs a;
-		a.bb = fe->d_bb; a.bb_stride = fe->bb_stride; a.rs = fe->d_rs; a.rs_stride = fe->rs_stride; a.h = fe->d_rs_h;
+		a.bb = fe->d_bb; a.bb_stride = fe->bb_stride; a.rs = fe->d_rs[p]; a.rs_stride = fe->rs_stride; a.h = fe->d_rs_h;
 		a.phi0 = fe->rs_phi0; a.step = fe->rs_step; a.n_out = n_out;
 		if(n_out > 0) {
+			CK(cudaStreamWaitEvent(st, fe->ev_agc_done[p], 0));          // agc of batch i-2 has read d_rs[p]
 			prof_begin(fe, KC_RESAMP, pr);
 			HFDL_LAUNCH(resamp_kernel, dim3((unsigned)((n_out + 255) / 256), (unsigned)fe->C), dim3(256), 0, st, a);
 			prof_end(fe, pr);
@@ -227,20 +284,33 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 		HFDL_LAUNCH(bb_carry, dim3((unsigned)fe->C), dim3(32), 0, st, fe->d_bb, fe->bb_stride, n_in);
 		fe->launches++;
 	}
+	CK(cudaEventRecord(fe->ev_front[p], st));
+	// frame records of set p: free once fec of batch i-2 is done
+	CK(cudaStreamWaitEvent(stl, fe->ev_fec_done[p], 0));
+	CK(cudaMemsetAsync(fe->d_nframes[p], 0, sizeof(int), stl));
+	cur.nsub = 0;
 	if(n_out > 0) {
 		// The demodulator is a feed-forward chain agc -> bank -> loop whose first and last stage are latency-bound
-		// single-warp recurrences: split the batch into sub-ranges and run agc/bank of sub-range i+1 on a second
-		// stream while loop works on sub-range i (both recurrences keep their state in HBM between launches).
+		// recurrences: the batch is split into sub-ranges so that agc/bank of later sub-ranges (and of the next batch)
+		// run while loop_kernel works on earlier ones (both recurrences keep their state in HBM between launches).
 		const int nsub = (n_out >= 8 * 2048) ? HFDL_NSUB : 1;
-		CK(cudaEventRecord(fe->ev_rs, st));
-		CK(cudaStreamWaitEvent(fe->stream2, fe->ev_rs, 0));
-		cudaStream_t st2 = fe->stream2;
+		CK(cudaStreamWaitEvent(st2, fe->ev_front[p], 0));
+		int first_loop = -1, last_loop = -1;
 		for(int i = 0; i < nsub; i++) {
 			const long long s0 = (long long)n_out * i / nsub, s1 = (long long)n_out * (i + 1) / nsub;
 			const int ns = (int)(s1 - s0);
 			if(ns <= 0) continue;
+			// samples [s0, s1) of the shared work arrays (and the HIST samples in front of the arrays, written by
+			// demod_carry) are still read by the previous batch's loop launches that cover [s0 - HIST, s1)
+			if(prev.busy) {
+				int need = -1;
+				for(int j = 0; j < prev.nsub; j++)
+					if(prev.s0[j] - HFDL_AGC_HIST < s1 + HFDL_AGC_HIST && prev.s1[j] > s0 - HFDL_AGC_HIST) need = j;
+				if(i == 0 && prev.nsub > 0 && need < 0) need = 0;
+				if(need >= 0) CK(cudaStreamWaitEvent(st2, fe->ev_loop[p ^ 1][need], 0));
+			}
 			AgcArgs a;
-			a.rs = fe->d_rs + s0; a.rs_stride = fe->rs_stride; a.n_samples = ns; a.state = fe->d_agc_state;
+			a.rs = fe->d_rs[p] + s0; a.rs_stride = fe->rs_stride; a.n_samples = ns; a.state = fe->d_agc_state;
 			a.agc_out = fe->d_agc + s0; a.agc_stride = fe->agc_stride; a.lvl = fe->d_lvl + s0; a.lvl_stride = fe->rs_stride;
 			prof_begin2(fe, KC_AGC, pr, st2);
 			HFDL_LAUNCH(agc_kernel, dim3((unsigned)fe->C), dim3(32), 0, st2, a);
@@ -251,64 +321,63 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 			prof_begin2(fe, KC_BANK, pr, st2);
 			HFDL_LAUNCH(bank_kernel, dim3((unsigned)((ns + HFDL_BANK_TILE - 1) / HFDL_BANK_TILE), (unsigned)fe->C), dim3(256), 0, st2, b);
 			prof_end2(fe, pr, st2);
-			CK(cudaEventRecord(fe->ev_sub[i], st2));
-			CK(cudaStreamWaitEvent(st, fe->ev_sub[i], 0));
+			CK(cudaEventRecord(fe->ev_sub[p][i], st2));
+			CK(cudaStreamWaitEvent(stl, fe->ev_sub[p][i], 0));
 			LoopArgs l;
 			l.bank = fe->d_bank + s0 * 32; l.bank_stride = fe->rs_stride; l.mfo = fe->d_mfo + s0; l.mfo_stride = fe->mfo_stride;
 			l.lvl = fe->d_lvl + s0; l.lvl_stride = fe->rs_stride; l.n_samples = ns;
-			l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym;
-			l.frames = fe->d_frames; l.nframes = fe->d_nframes; l.max_frames = fe->max_frames;
+			l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym; l.nslots = fe->nslots;
+			l.frames = fe->d_frames[p]; l.nframes = fe->d_nframes[p]; l.max_frames = fe->max_frames;
 			l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
 			{ const char *dbg = getenv("HFDL_B200_DEBUG"); l.debug_mode = dbg ? atoi(dbg) : 0; }
 			l.dbg_cycles = fe->d_dbg;
-			prof_begin(fe, KC_LOOP, pr);
-			HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(HFDL_LK_THREADS), HFDL_LK_SMEM, st, l);
-			prof_end(fe, pr);
+			prof_begin2(fe, KC_LOOP, pr, stl);
+			HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(HFDL_LK_THREADS), HFDL_LK_SMEM, stl, l);
+			prof_end2(fe, pr, stl);
+			CK(cudaEventRecord(fe->ev_loop[p][cur.nsub], stl));
+			cur.s0[cur.nsub] = s0; cur.s1[cur.nsub] = s1; cur.nsub++;
+			if(first_loop < 0) first_loop = cur.nsub - 1;
+			last_loop = cur.nsub - 1;
 			fe->launches += 3;
 		}
 		if(fe->cfg.capture_channel >= 0 && fe->cap_n < fe->cfg.capture_max) {       // f_agc_out / f_mf_out checkpoints
 			long long n = std::min<long long>(n_out, fe->cfg.capture_max - fe->cap_n);
 			int cc = fe->cfg.capture_channel;
-			CK(cudaMemcpyAsync(fe->d_cap_agc + fe->cap_n, fe->d_agc + (long long)cc * fe->agc_stride + HFDL_AGC_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st));
-			CK(cudaMemcpyAsync(fe->d_cap_mf + fe->cap_n, fe->d_mfo + (long long)cc * fe->mfo_stride + HFDL_MFO_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+			CK(cudaMemcpyAsync(fe->d_cap_agc + fe->cap_n, fe->d_agc + (long long)cc * fe->agc_stride + HFDL_AGC_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st2));
+			CK(cudaMemcpyAsync(fe->d_cap_mf + fe->cap_n, fe->d_mfo + (long long)cc * fe->mfo_stride + HFDL_MFO_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st2));
 		}
 		if(fe->cfg.capture_channel >= 0) fe->cap_n += n_out;
-		HFDL_LAUNCH(demod_carry, dim3((unsigned)fe->C), dim3(64), 0, st, fe->d_agc, fe->agc_stride, fe->d_mfo, fe->mfo_stride, (long long)n_out);
+		// the tails move in front of the arrays for the next batch once the first loop launch (which may still read
+		// the old matched-filter history after a symsync reset) is done
+		if(first_loop >= 0) CK(cudaStreamWaitEvent(st2, fe->ev_loop[p][first_loop], 0));
+		HFDL_LAUNCH(demod_carry, dim3((unsigned)fe->C), dim3(64), 0, st2, fe->d_agc, fe->agc_stride, fe->d_mfo, fe->mfo_stride, (long long)n_out);
 		fe->launches++;
+		(void)last_loop;
 	}
+	CK(cudaEventRecord(fe->ev_agc_done[p], st2));
 	{
+		// st_fec: after the last loop launch of this batch (stream order on st_loop -> one event)
+		cudaEvent_t ev_all = fe->ev_loop[p][HFDL_NSUB - 1];
+		if(cur.nsub < HFDL_NSUB) CK(cudaEventRecord(ev_all, stl));     // (when nsub == HFDL_NSUB it was recorded above)
+		CK(cudaStreamWaitEvent(stf, ev_all, 0));
 		FecArgs a;
-		a.frames = fe->d_frames; a.nframes = fe->d_nframes; a.max_frames = fe->max_frames; a.datasym = fe->d_datasym;
-		a.tab = fe->d_tab; a.pdus = fe->d_pdus; a.soft_out = nullptr; a.vin_direct = nullptr; a.vin_nbits = 0;
-		prof_begin(fe, KC_FEC, pr);
-		HFDL_LAUNCH(fec_kernel, dim3((unsigned)fe->max_frames), dim3(32), HFDL_FEC_SMEM, st, a);
-		prof_end(fe, pr);
+		a.frames = fe->d_frames[p]; a.nframes = fe->d_nframes[p]; a.max_frames = fe->max_frames; a.datasym = fe->d_datasym; a.nslots = fe->nslots;
+		a.tab = fe->d_tab; a.pdus = fe->d_pdus[p]; a.soft_out = nullptr; a.vin_direct = nullptr; a.vin_nbits = 0;
+		prof_begin2(fe, KC_FEC, pr, stf);
+		HFDL_LAUNCH(fec_kernel, dim3((unsigned)fe->max_frames), dim3(32), HFDL_FEC_SMEM, stf, a);
+		prof_end2(fe, pr, stf);
 		fe->launches++;
+		CK(cudaGetLastError());
+		CK(cudaMemcpyAsync(fe->h_nframes[p], fe->d_nframes[p], sizeof(int), cudaMemcpyDeviceToHost, stf));
+		CK(cudaMemcpyAsync(fe->h_pdus[p], fe->d_pdus[p], sizeof(PduRec) * (size_t)fe->max_frames, cudaMemcpyDeviceToHost, stf));
+		CK(cudaEventRecord(fe->ev_fec_done[p], stf));
 	}
-	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(fe->h_nframes, fe->d_nframes, sizeof(int), cudaMemcpyDeviceToHost, st));
-	CK(cudaStreamSynchronize(st));
-	int nfr = *fe->h_nframes;
-	if(nfr > fe->max_frames) {
-		fprintf(stderr, "hfdl_b200: frame queue overflow (%d > %d), frames dropped\n", nfr, fe->max_frames);
-		nfr = fe->max_frames;
-	}
-	if(nfr > 0) {
-		CK(cudaMemcpyAsync(fe->h_pdus, fe->d_pdus, sizeof(PduRec) * (size_t)nfr, cudaMemcpyDeviceToHost, st));
-		CK(cudaStreamSynchronize(st));
-		// canonical order within a batch: (end sample, channel) -- the reference emits in thread-race order
-		std::vector<int> order((size_t)nfr);
-		for(int i = 0; i < nfr; i++) order[(size_t)i] = i;
-		std::sort(order.begin(), order.end(), [&](int x, int y) {
-			const PduRec &a = fe->h_pdus[x], &b = fe->h_pdus[y];
-			if(a.sample_cnt_end != b.sample_cnt_end) return a.sample_cnt_end < b.sample_cnt_end;
-			return a.channel < b.channel;
-		});
-		for(int i : order) { hfdl_b200_pdu_t p; to_pdu(fe, fe->h_pdus[i], p); fe->pduq.push_back(p); }
-	}
+	cur.busy = true;
+	fe->batch_seq++;
 	fe->blocks_done += nb;
 	fe->last_nblocks = nb; fe->last_nout = n_out;
-	return 0;
+	// while this batch runs, pick up the previous one
+	return collect_batch(fe, p ^ 1);
 }
 
 int compute_tapslices(hfdl_b200_frontend *fe) {
@@ -391,8 +460,18 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaSetDevice(cfg->device));
 	CKD(cudaStreamCreateWithFlags(&fe->stream, cudaStreamNonBlocking));
 	CKD(cudaStreamCreateWithFlags(&fe->stream2, cudaStreamNonBlocking));
-	CKD(cudaEventCreateWithFlags(&fe->ev_rs, cudaEventDisableTiming));
-	for(int i = 0; i < HFDL_NSUB; i++) CKD(cudaEventCreateWithFlags(&fe->ev_sub[i], cudaEventDisableTiming));
+	CKD(cudaStreamCreateWithFlags(&fe->st_loop, cudaStreamNonBlocking));
+	CKD(cudaStreamCreateWithFlags(&fe->st_fec, cudaStreamNonBlocking));
+	CKD(cudaEventCreateWithFlags(&fe->ev_h2d, cudaEventDisableTiming));
+	for(int q = 0; q < 2; q++) {
+		CKD(cudaEventCreateWithFlags(&fe->ev_front[q], cudaEventDisableTiming));
+		CKD(cudaEventCreateWithFlags(&fe->ev_agc_done[q], cudaEventDisableTiming));
+		CKD(cudaEventCreateWithFlags(&fe->ev_fec_done[q], cudaEventDisableTiming));
+		for(int i = 0; i < HFDL_NSUB; i++) {
+			CKD(cudaEventCreateWithFlags(&fe->ev_sub[q][i], cudaEventDisableTiming));
+			CKD(cudaEventCreateWithFlags(&fe->ev_loop[q][i], cudaEventDisableTiming));
+		}
+	}
 	if(fe->fft.init()) { hfdl_b200_destroy(fe); return -1; }
 	const int C = fe->C, N = g.fft_size, M = g.fft_inv_size, B = fe->Bmax;
 	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * B));
@@ -412,7 +491,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaMalloc((void **)&fe->d_bb, sizeof(cf) * (size_t)C * fe->bb_stride));
 	CKD(cudaMemset(fe->d_bb, 0, sizeof(cf) * (size_t)C * fe->bb_stride));
 	fe->rs_stride = (long long)B * fe->out_per_block + 16;
-	CKD(cudaMalloc((void **)&fe->d_rs, sizeof(cf) * (size_t)C * fe->rs_stride));
+	for(int q = 0; q < 2; q++) CKD(cudaMalloc((void **)&fe->d_rs[q], sizeof(cf) * (size_t)C * fe->rs_stride));
 	{
 		std::vector<float> h((size_t)HFDL_RS_NPFB * HFDL_RS_TAPS);
 		hfdl_design::resamp_design(fe->resamp_rate, h.data(), &fe->rs_step);
@@ -441,14 +520,24 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 		CKD(cudaMalloc((void **)&fe->d_bank, sizeof(cf) * (size_t)C * fe->rs_stride * 32));
 		delete T;
 	}
-	CKD(cudaMalloc((void **)&fe->d_datasym, sizeof(cf) * (size_t)C * HFDL_FRAME_SLOTS * HFDL_DATA_SYMS_MAX));
-	fe->max_frames = C * HFDL_FRAME_SLOTS;
-	CKD(cudaMalloc((void **)&fe->d_frames, sizeof(FrameRec) * (size_t)fe->max_frames));
-	CKD(cudaMalloc((void **)&fe->d_nframes, sizeof(int)));
-	CKD(cudaMemset(fe->d_nframes, 0, sizeof(int)));
-	CKD(cudaMalloc((void **)&fe->d_pdus, sizeof(PduRec) * (size_t)fe->max_frames));
-	CKD(cudaMallocHost((void **)&fe->h_pdus, sizeof(PduRec) * (size_t)fe->max_frames));
-	CKD(cudaMallocHost((void **)&fe->h_nframes, sizeof(int)));
+	{
+		// A frame lasts >= 2.34 s of signal (448 + 531 + 72 * 45 symbols at 1800 baud): a batch can end at most
+		// fpb frames per channel.  The data symbols of a frame stay in their slot until fec of that batch has run,
+		// which overlaps with the loop stage of the next batch -> twice as many slots.
+		const double batch_s = (double)B * g.input_size / (double)cfg->sample_rate;
+		const int fpb = (int)(batch_s / 2.3) + 2;
+		fe->nslots = std::max(HFDL_FRAME_SLOTS_MIN, 2 * fpb);
+		fe->max_frames = C * fpb;
+	}
+	CKD(cudaMalloc((void **)&fe->d_datasym, sizeof(cf) * (size_t)C * fe->nslots * HFDL_DATA_SYMS_MAX));
+	for(int q = 0; q < 2; q++) {
+		CKD(cudaMalloc((void **)&fe->d_frames[q], sizeof(FrameRec) * (size_t)fe->max_frames));
+		CKD(cudaMalloc((void **)&fe->d_nframes[q], sizeof(int)));
+		CKD(cudaMemset(fe->d_nframes[q], 0, sizeof(int)));
+		CKD(cudaMalloc((void **)&fe->d_pdus[q], sizeof(PduRec) * (size_t)fe->max_frames));
+		CKD(cudaMallocHost((void **)&fe->h_pdus[q], sizeof(PduRec) * (size_t)fe->max_frames));
+		CKD(cudaMallocHost((void **)&fe->h_nframes[q], sizeof(int)));
+	}
 	if(fe->cfg.capture_channel >= 0 && fe->cfg.capture_max > 0) {
 		size_t n = (size_t)fe->cfg.capture_max;
 		CKD(cudaMalloc((void **)&fe->d_cap_agc, sizeof(cf) * n));
@@ -470,22 +559,30 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 
 void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
-	if(fe->stream) cudaStreamSynchronize(fe->stream);
+	cudaStream_t sts[4] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec };
+	for(cudaStream_t q : sts) if(q) cudaStreamSynchronize(q);
 	cudaFree(fe->d_work); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
-	cudaFree(fe->d_bb); cudaFree(fe->d_rs); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
-	cudaFree(fe->d_frames); cudaFree(fe->d_nframes); cudaFree(fe->d_pdus); cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf);
-	cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp);
+	cudaFree(fe->d_bb); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
+	cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf); cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp); cudaFree(fe->d_dbg);
 	cudaFree(fe->d_agc_state); cudaFree(fe->d_agc); cudaFree(fe->d_mfo); cudaFree(fe->d_lvl); cudaFree(fe->d_bank);
-	if(fe->h_pdus) cudaFreeHost(fe->h_pdus);
-	if(fe->h_nframes) cudaFreeHost(fe->h_nframes);
+	for(int q = 0; q < 2; q++) {
+		cudaFree(fe->d_rs[q]); cudaFree(fe->d_frames[q]); cudaFree(fe->d_nframes[q]); cudaFree(fe->d_pdus[q]);
+		if(fe->h_pdus[q]) cudaFreeHost(fe->h_pdus[q]);
+		if(fe->h_nframes[q]) cudaFreeHost(fe->h_nframes[q]);
+		if(fe->ev_front[q]) cudaEventDestroy(fe->ev_front[q]);
+		if(fe->ev_agc_done[q]) cudaEventDestroy(fe->ev_agc_done[q]);
+		if(fe->ev_fec_done[q]) cudaEventDestroy(fe->ev_fec_done[q]);
+		for(int i = 0; i < HFDL_NSUB; i++) {
+			if(fe->ev_sub[q][i]) cudaEventDestroy(fe->ev_sub[q][i]);
+			if(fe->ev_loop[q][i]) cudaEventDestroy(fe->ev_loop[q][i]);
+		}
+	}
 	for(auto &r : fe->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
 	if(fe->ev0) cudaEventDestroy(fe->ev0);
 	if(fe->ev1) cudaEventDestroy(fe->ev1);
+	if(fe->ev_h2d) cudaEventDestroy(fe->ev_h2d);
 	fe->fft.destroy();
-	if(fe->stream2) { cudaStreamSynchronize(fe->stream2); cudaStreamDestroy(fe->stream2); }
-	if(fe->ev_rs) cudaEventDestroy(fe->ev_rs);
-	for(int i = 0; i < HFDL_NSUB; i++) if(fe->ev_sub[i]) cudaEventDestroy(fe->ev_sub[i]);
-	if(fe->stream) cudaStreamDestroy(fe->stream);
+	for(cudaStream_t q : sts) if(q) cudaStreamDestroy(q);
 	delete fe;
 }
 
@@ -541,16 +638,21 @@ int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, in
 		if(n > first)
 			CK(cudaMemcpyAsync(fe->d_ring, p + first * fe->bps, (size_t)((n - first) * fe->bps), cudaMemcpyHostToDevice, fe->stream));
 		fe->fed += n; p += n * fe->bps; nsamples -= n;
+		CK(cudaEventRecord(fe->ev_h2d, fe->stream));
 		int r = process_pending(fe, false);
 		if(r < 0) return -1;
 		blocks += r;
 	}
+	// the caller may reuse its buffer when this returns: wait for the last H2D copy (not for the processing)
+	if(fe->ev_h2d && blocks >= 0) CK(cudaEventSynchronize(fe->ev_h2d));
 	return blocks;
 }
 
 int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe) {
 	if(!fe) return -1;
-	return process_pending(fe, true);
+	int r = process_pending(fe, true);
+	if(r < 0 || drain(fe)) return -1;
+	return r;
 }
 
 int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t ring_samples, int64_t start_sample, int32_t nblocks) {
@@ -572,8 +674,7 @@ int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples
 
 int32_t hfdl_b200_sync(hfdl_b200_frontend_t *fe) {
 	if(!fe) return -1;
-	CK(cudaStreamSynchronize(fe->stream));
-	return 0;
+	return drain(fe);
 }
 
 int32_t hfdl_b200_pdu_count(hfdl_b200_frontend_t *fe) { return fe ? (int32_t)fe->pduq.size() : -1; }
@@ -588,7 +689,7 @@ int32_t hfdl_b200_pop_pdu(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdu) {
 
 static int read_state(hfdl_b200_frontend *fe, int ch, DemodState *S) {
 	if(!fe || ch < 0 || ch >= fe->C) return -1;
-	CK(cudaStreamSynchronize(fe->stream));
+	if(drain(fe)) return -1;
 	CK(cudaMemcpy(S, fe->d_state + ch, sizeof(DemodState), cudaMemcpyDeviceToHost));
 	return 0;
 }
@@ -611,7 +712,7 @@ void hfdl_b200_print_summary(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
 	if(fe->d_dbg) {
 		std::vector<long long> v((size_t)fe->C * 4);
-		cudaStreamSynchronize(fe->stream);
+		drain(fe);
 		cudaMemcpy(v.data(), fe->d_dbg, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
 		for(int c = 0; c < fe->C && c < 4; c++) fprintf(stderr, "loop_kernel ch%d cycles: timing warp %lld (waiting %lld)  demod warp %lld (waiting %lld)\n", c, v[(size_t)c * 4], v[(size_t)c * 4 + 1], v[(size_t)c * 4 + 2], v[(size_t)c * 4 + 3]);
 	}
@@ -622,11 +723,13 @@ void hfdl_b200_print_summary(hfdl_b200_frontend_t *fe) {
 
 int32_t hfdl_b200_timer_start(hfdl_b200_frontend_t *fe) {
 	if(!fe) return -1;
+	if(drain(fe)) return -1;
 	CK(cudaEventRecord(fe->ev0, fe->stream));
 	return 0;
 }
 int32_t hfdl_b200_timer_stop(hfdl_b200_frontend_t *fe, float *ms) {
 	if(!fe || !ms) return -1;
+	if(drain(fe)) return -1;                      // every batch of the timed region has finished on all four streams
 	CK(cudaEventRecord(fe->ev1, fe->stream));
 	CK(cudaEventSynchronize(fe->ev1));
 	CK(cudaEventElapsedTime(ms, fe->ev0, fe->ev1));
@@ -639,7 +742,7 @@ int32_t hfdl_b200_profile_enable(hfdl_b200_frontend_t *fe, int32_t on) {
 }
 int32_t hfdl_b200_profile_read(hfdl_b200_frontend_t *fe, int32_t max, char names[][32], float *ms, int32_t *launches) {
 	if(!fe) return -1;
-	CK(cudaStreamSynchronize(fe->stream));
+	if(drain(fe)) return -1;
 	for(auto &r : fe->prof) {
 		float t = 0;
 		if(cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { fe->prof_ms[r.cls] += t; fe->prof_n[r.cls]++; }
@@ -655,10 +758,11 @@ int32_t hfdl_b200_profile_read(hfdl_b200_frontend_t *fe, int32_t max, char names
 	return n;
 }
 int64_t hfdl_b200_kernel_launches(hfdl_b200_frontend_t *fe) { return fe ? fe->launches : -1; }
+int64_t hfdl_b200_result_bytes_per_batch(hfdl_b200_frontend_t *fe) { return fe ? (int64_t)(sizeof(int) + sizeof(PduRec) * (size_t)fe->max_frames) : -1; }
 
 int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_t index, void *dst, int64_t max) {
 	if(!fe || max < 0) return -1;
-	CK(cudaStreamSynchronize(fe->stream));
+	if(drain(fe)) return -1;
 	const auto &g = fe->g;
 	long long avail = 0;
 	const cf *srcp = nullptr;
@@ -680,7 +784,7 @@ int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_
 	case HFDL_B200_CP_CHAN:
 		if(index < 0 || index >= fe->C) return -1;
 		avail = fe->last_nout;
-		srcp = fe->d_rs + (long long)index * fe->rs_stride;
+		srcp = fe->d_rs[(fe->batch_seq + 1) & 1] + (long long)index * fe->rs_stride;      // set of the last batch
 		break;
 	case HFDL_B200_CP_AGC: case HFDL_B200_CP_MF: case HFDL_B200_CP_EQ: {
 		if(fe->cfg.capture_channel < 0) return -1;
@@ -743,7 +847,7 @@ static int fec_run(int device, const void *symbols, const uint8_t *vin, int nfra
 	std::vector<FrameRec> fr((size_t)nframes);
 	for(int q = 0; q < nframes; q++) {
 		memset(&fr[(size_t)q], 0, sizeof(FrameRec));
-		fr[(size_t)q].channel = q / HFDL_FRAME_SLOTS; fr[(size_t)q].slot = q % HFDL_FRAME_SLOTS; fr[(size_t)q].M1 = M1; fr[(size_t)q].bitmask = bitmask;
+		fr[(size_t)q].channel = q / HFDL_FRAME_SLOTS_MIN; fr[(size_t)q].slot = q % HFDL_FRAME_SLOTS_MIN; fr[(size_t)q].M1 = M1; fr[(size_t)q].bitmask = bitmask;
 	}
 	CK(cudaMalloc((void **)&d_fr, sizeof(FrameRec) * (size_t)nframes));
 	CK(cudaMemcpy(d_fr, fr.data(), sizeof(FrameRec) * (size_t)nframes, cudaMemcpyHostToDevice));
@@ -762,7 +866,7 @@ static int fec_run(int device, const void *symbols, const uint8_t *vin, int nfra
 	}
 	if(soft_out) CK(cudaMalloc((void **)&d_soft, (size_t)nframes * HFDL_FEC_VIN_MAX));
 	FecArgs a;
-	a.frames = d_fr; a.nframes = d_n; a.max_frames = nframes; a.datasym = d_sym; a.tab = d_tab; a.pdus = d_p; a.soft_out = d_soft;
+	a.frames = d_fr; a.nframes = d_n; a.max_frames = nframes; a.datasym = d_sym; a.nslots = HFDL_FRAME_SLOTS_MIN; a.tab = d_tab; a.pdus = d_p; a.soft_out = d_soft;
 	a.vin_direct = d_vin; a.vin_nbits = nbits;
 	HFDL_LAUNCH(fec_kernel, dim3((unsigned)nframes), dim3(32), HFDL_FEC_SMEM, 0, a);
 	CK(cudaGetLastError());

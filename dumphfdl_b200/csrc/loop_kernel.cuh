@@ -37,7 +37,7 @@ struct LoopArgs {
 	int n_samples;
 	DemodState *state;
 	const DemodTables *tab;
-	cf *datasym;               // [C][HFDL_FRAME_SLOTS][HFDL_DATA_SYMS_MAX]
+	cf *datasym; int nslots;   // [C][nslots][HFDL_DATA_SYMS_MAX]
 	FrameRec *frames; int *nframes; int max_frames;
 	int cap_channel; cf *cap_eq; int *cap_cnt; int cap_max;      // f_eq_out checkpoint of one channel
 	long long *dbg_cycles;     // diagnostics only: [C][4] = timing-warp total / waiting, demod-warp total / waiting
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		const int l16 = lane & 15;
 		const bool cap = (c == a.cap_channel);
 		int cap_n_eq = cap ? a.cap_cnt[1] : 0;
-		cf *dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+		cf *dsym = a.datasym + ((long long)c * a.nslots + S.slot) * HFDL_DATA_SYMS_MAX;
 		const unsigned long long cnt_base = S.sample_cnt;
 		unsigned symcnt = (unsigned)S.symbol_cnt;
 		unsigned A_bits[4];
@@ -708,8 +708,8 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 							a.frames[q] = fr;
 						}
 						S.st_frames++;
-						S.slot = (S.slot + 1) % HFDL_FRAME_SLOTS;
-						dsym = a.datasym + ((long long)c * HFDL_FRAME_SLOTS + S.slot) * HFDL_DATA_SYMS_MAX;
+						S.slot = (S.slot + 1) % a.nslots;
+						dsym = a.datasym + ((long long)c * a.nslots + S.slot) * HFDL_DATA_SYMS_MAX;
 						framer_reset(S, T, E, l16); reset_pending = true;
 						symcnt = 0;
 					}

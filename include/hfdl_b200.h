@@ -89,10 +89,14 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 void    hfdl_b200_destroy(hfdl_b200_frontend_t *fe);
 int32_t hfdl_b200_get_geometry(const hfdl_b200_frontend_t *fe, hfdl_b200_geometry_t *g);
 
-/* Host samples in the configured sample format.  Whole batches are processed as they fill; the call
- * returns the number of overlap-save blocks processed (>=0) or -1. */
+/* Host samples in the configured sample format.  Whole batches are queued on the GPU as they fill; the call
+ * returns the number of overlap-save blocks queued (>=0) or -1.  Batches are pipelined: when the call returns,
+ * the samples have been copied to the device (the caller's buffer is free), the newest batch may still be
+ * running and its PDUs appear in the queue with the next push / flush / sync (the reference's fft and channel
+ * threads hand over through a barrier per block, block.c:90-120; the order of PDUs per channel is the same). */
 int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples);
-/* Process every whole block still buffered (a final partial block is dropped, as in fft.c:41-46). */
+/* Process every whole block still buffered (a final partial block is dropped, as in fft.c:41-46) and wait
+ * until all PDUs are in the queue. */
 int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe);
 /* Device-resident cyclic capture: 'd_samples' holds ring_samples samples of the configured format in
  * HBM; processes nblocks blocks starting at stream position start_sample (stream position p lives at
@@ -117,6 +121,8 @@ int32_t hfdl_b200_timer_stop(hfdl_b200_frontend_t *fe, float *ms);
 int32_t hfdl_b200_profile_enable(hfdl_b200_frontend_t *fe, int32_t on);
 int32_t hfdl_b200_profile_read(hfdl_b200_frontend_t *fe, int32_t max, char names[][32], float *ms, int32_t *launches);
 int64_t hfdl_b200_kernel_launches(hfdl_b200_frontend_t *fe);
+/* bytes copied device -> host per batch for the results (frame counter + PDU records) */
+int64_t hfdl_b200_result_bytes_per_batch(hfdl_b200_frontend_t *fe);
 
 /* ---- checkpoints for parity tests (the reference's DATADUMPS taps, hfdl.c:616-655) ---- */
 #define HFDL_B200_CP_SPECTRUM 0   /* last batch: forward spectrum of block 'index' (-1 = last), natural FFTW order */
