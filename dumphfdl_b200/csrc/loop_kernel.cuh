@@ -149,14 +149,13 @@ __device__ __forceinline__ unsigned modem_demod(int m, cf x, const cf (*psk)[8],
 #define HFDL_UNI(v) __shfl_sync(0xffffffffu, (int)(v), 0)
 
 // ---- output-ring entry tags ----------------------------------------------------------------------------------
-// w = gen[31:25] | more[24] | lap[23:20] | k[19:0]: reset generation of the timing warp, "another output of the same
-// input sample follows", (sequence number / ring size) mod 16, input-sample index of the output.
+// w = gen[31:25] | lap[24:21] | more[20] | k[19:0]: reset generation of the timing warp, (sequence number / ring
+// size) mod 16, "another output of the same input sample follows", input-sample index of the output.
 __device__ __forceinline__ unsigned lk_tag(int gen, int more, int seq, int k) {
-	return ((unsigned)(gen & 0x7F) << 25) | ((unsigned)(more & 1) << 24) | ((unsigned)((seq >> 6) & 0xF) << 20) | (unsigned)k;
+	return ((unsigned)(gen & 0x7F) << 25) | ((unsigned)((seq >> 6) & 0xF) << 21) | ((unsigned)(more & 1) << 20) | (unsigned)k;
 }
-__device__ __forceinline__ bool lk_tag_ok(unsigned tag, int gen, int seq) {
-	return ((tag >> 20) & 0xFEFu) == ((((unsigned)gen & 0x7Fu) << 5) | (((unsigned)seq >> 6) & 0xFu));
-}
+__device__ __forceinline__ unsigned lk_tag_hi(int gen, int seq) { return (((unsigned)gen & 0x7Fu) << 4) | (((unsigned)seq >> 6) & 0xFu); }
+__device__ __forceinline__ bool lk_tag_ok(unsigned tag, int gen, int seq) { return (tag >> 21) == lk_tag_hi(gen, seq); }
 
 // Costas step + rotation of one symsync output (hfdl.c:250-267,709-710)
 __device__ __forceinline__ cf costas_rotate(DemodState &S, float re, float im) {
@@ -249,7 +248,8 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 	for(;;) {
 		// warp vote: the lanes are not guaranteed to be converged at the prefetch, so the decision must not depend on
 		// one lane's view (a lane that saw a not-yet-valid entry sends the whole warp through the reload below)
-		if(HFDL_UNLIKELY(__ballot_sync(0xffffffffu, lk_tag_ok(__float_as_uint(e0.w), gen, seq) & lk_tag_ok(__float_as_uint(e1.w), gen, seq + 1)) != 0xffffffffu)) {
+		const unsigned hi = lk_tag_hi(gen, seq);      // seq is even here: seq and seq + 1 lie in the same lap
+		if(HFDL_UNLIKELY(!__all_sync(0xffffffffu, ((__float_as_uint(e0.w) >> 21) == hi) & ((__float_as_uint(e1.w) >> 21) == hi)))) {
 			// both outputs of the symbol are not there yet: wait, or leave when the batch ends before them
 			bool ok = false;
 			for(;;) {
@@ -279,8 +279,11 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			const cf a = conj_mul(E.w13, r0), b = conj_mul(E.w14, r1);
 			s = make_float2((P.x + a.x) + b.x, (P.y + a.y) + b.y);
 		}
-		E.x = l16 == 13 ? r0 : (l16 == 14 ? r1 : xs);
-		E.x2 = l16 == 13 ? x2a : (l16 == 14 ? x2b : x2s);
+		{	// window update without branches: lanes 13 / 14 take the two new elements
+			const bool is13 = (l16 == 13), is14 = (l16 == 14);
+			E.x.x = is13 ? r0.x : xs.x; E.x.y = is13 ? r0.y : xs.y; E.x2 = is13 ? x2a : x2s;
+			E.x.x = is14 ? r1.x : E.x.x; E.x.y = is14 ? r1.y : E.x.y; E.x2 = is14 ? x2b : E.x2;
+		}
 		if(MODE == RUN_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
 			float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
 			if(S.bitmask & 1u) d = -d;
@@ -314,9 +317,13 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 				nacc = 0; bacc = 0;
 			}
 		} else if(MODE == RUN_TRAIN) {
-			if(S.training_n < HFDL_T_LEN) { if(lane == 0) lk_train[S.training_n] = s; S.training_n++; }
+			const bool room = S.training_n < HFDL_T_LEN;
+			if(room & (lane == 0)) lk_train[S.training_n] = s;
+			S.training_n += room ? 1 : 0;
 		} else if(MODE == RUN_DATA) {
-			if(S.data_n < HFDL_DATA_SYMS_MAX) { if(lane == 0) dsym[S.data_n] = s; S.data_n++; }
+			const bool room = S.data_n < HFDL_DATA_SYMS_MAX;
+			if(room & (lane == 0)) dsym[S.data_n] = s;
+			S.data_n += room ? 1 : 0;
 		} else if(MODE == RUN_A1) {
 			// noise-floor clock: one tick per input sample (k_prev, k1], update on every 256th (hfdl.c:700-706)
 			const int d = k1 - k_prev;
@@ -340,7 +347,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			if(HFDL_UNLIKELY(fabsf(S.c_dphi) > 0.25f)) stop = true;      // Costas blow-up: the generic path resets the loops
 		}
 		if(MODE != RUN_A1) {
-			S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + lvl1, S.frame_symbol_cnt + 1.0f);
+			S.signal_level += lvl1;                   // in-frame: the SUM of the AGC levels (the mean is taken at the frame end)
 			S.frame_symbol_cnt += 1.0f;
 		}
 		k_prev = k1;
@@ -568,7 +575,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			const float4 ent = lk_ring_load(seq & (HFDL_LK_RING - 1));
 			tagw = __float_as_uint(ent.w);
 			const int k = (int)(tagw & 0xFFFFFu);
-			const bool more = (tagw >> 24) & 1u;
+			const bool more = (tagw >> 20) & 1u;
 			const float level = ent.z;
 			// noise-floor clock ticks once per input sample, before that sample's outputs (hfdl.c:700)
 			if(HFDL_UNLIKELY(S.fr_state == HF_A1)) { for(int sidx = k_prev + 1; sidx <= k; sidx++) HFDL_NF_TICK(sidx); }
@@ -616,7 +623,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 					}
 				}
 				if(S.fr_state > HF_A1) {
-					S.signal_level = __fdividef(S.signal_level * S.frame_symbol_cnt + level, S.frame_symbol_cnt + 1.0f);
+					S.signal_level += level;               // running mean of hfdl.c:768 kept as sum / count
 					S.frame_symbol_cnt += 1.0f;
 				}
 				if(S.symbols_wanted > 1) { S.symbols_wanted--; break; }
@@ -702,7 +709,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 						if(q < a.max_frames && lane == 0) {
 							FrameRec fr;
 							fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
-							fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level; fr.noise_floor = S.noise_floor;
+							fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level / S.frame_symbol_cnt; fr.noise_floor = S.noise_floor;
 							fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = cnt_base + (unsigned long long)k;
 							fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
 							a.frames[q] = fr;
@@ -736,7 +743,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			if(HFDL_UNLIKELY(reset_pending) && !more) {
 				// symsync_crcf_reset happened while processing the outputs of input sample k: outputs of that sample that
 				// were already produced kept their (old-state) value; the timing warp restarts with sample k+1
-				gen = (gen + 1) & 0x7F;
+				gen = (gen + 1) % 127;                  // 127 is never used: the ring is initialised with all-ones tags
 				__syncwarp();
 				if(lane == 0) { lk_reset_k = k; lk_reset_seq = seq; __threadfence_block(); lk_reset_gen = gen; }
 				reset_pending = false;

@@ -133,6 +133,8 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
 	cusim::t_warp->bar.wait();
 	return r;
 }
+static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+static inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }

@@ -43,3 +43,9 @@ def test_frontend_two_channels_ragged_cf32(sim):
 def test_frontend_large_batch_uses_subranges(sim):
     # one 48-block batch: n_out > 16384 -> the agc/bank || loop sub-range schedule (HFDL_NSUB) is exercised
     assert K.case_frontend(sim, 250000, [10063000, 9952000], [5, 1], 5.6, batch=64, seed=8) == 2
+
+
+def test_stream_small_batches_pickup(sim):
+    # host-emulation run of the streaming case (pipeline bookkeeping: set alternation, deferred collection, frame slots)
+    plan = [(0, 0, 0.2), (0, 1, 3.2)]
+    assert K.case_frontend_stream(sim, 250000, [10063000], plan, 6.2, batch=2, push_blocks=3, seed=33) == 2
