@@ -53,7 +53,7 @@ struct DemodTables {
 	int mode_arity[8], mode_segments[8], mode_code_rate[8], mode_col_shift[8];   // hfdl.c:81-138
 };
 
-struct AgcState { float g, y2; };
+struct AgcState { float g, y2; };      // g: POWER gain g^2 of agc_crcf (see agc_kernel), y2: its energy estimate
 
 struct DemodState {                                  // loop_kernel state carried between batches
 	unsigned ss_since_reset;                         // pushes since the last symsync reset (saturates at 18)
@@ -95,8 +95,13 @@ struct PduRec {            // what the host turns into hfdl_pdu_metadata + octet
 };
 
 // ======================================================================================
-// K6: AGC.  grid = C blocks of 32 threads, lane 0 runs the recurrence of channel blockIdx.x.
+// K6: AGC (liquid agc_crcf_execute, hfdl.c:686).  grid = C blocks of one warp.
 //   y = x*g;  y2' = (1-a)*y2' + a*|y|^2;  if(y2' > 1e-6) g *= exp(-0.5*a*ln y2');  g = min(g, 1e6)   (a = 0.01)
+// The recurrence is strictly sequential, so only its dependent chain stays on lane 0, restated in the power gain
+// G = g^2 so that the sample itself is off the chain:
+//   y2' = (a*|x|^2)*G + (1-a)*y2';   G *= 2^(-a*log2 y2');   G = min(G, 1e12)
+// (FFMA -> MUFU.LG2 -> FMUL -> MUFU.EX2 -> FMUL -> FMNMX per sample).  |x|^2 before and sqrt(G), x*g, 1/g after the
+// chain are computed by all 32 lanes per chunk.
 // ======================================================================================
 struct AgcArgs {
 	const cf *rs; long long rs_stride; int n_samples;
@@ -105,16 +110,16 @@ struct AgcArgs {
 	float *lvl; long long lvl_stride;        // [C][n]  1/g after the update (agc_crcf_get_signal_level)
 };
 
-#define HFDL_AGC_CH 64
+#define HFDL_AGC_CH 128
 __global__ void __launch_bounds__(32) agc_kernel(AgcArgs a) {
 	__shared__ cf s_in[2][HFDL_AGC_CH];
-	__shared__ cf s_out[HFDL_AGC_CH];
-	__shared__ float s_lvl[HFDL_AGC_CH];
+	__shared__ float s_px[HFDL_AGC_CH];
+	__shared__ float s_G[HFDL_AGC_CH + 1];       // s_G[i + 1] = G after sample i; s_G[0] = G before the chunk
 	const int c = blockIdx.x, lane = threadIdx.x;
 	const cf *x = a.rs + (long long)c * a.rs_stride;
 	cf *out = a.agc_out + (long long)c * a.agc_stride + HFDL_AGC_HIST;
 	float *lvl = a.lvl + (long long)c * a.lvl_stride;
-	float g = a.state[c].g, y2 = a.state[c].y2;
+	float G = a.state[c].g, y2 = a.state[c].y2;  // AgcState.g holds the power gain g^2
 	const float alpha = 0.01f;
 	const int N = a.n_samples;
 	const int nchunks = (N + HFDL_AGC_CH - 1) / HFDL_AGC_CH;
@@ -127,24 +132,27 @@ __global__ void __launch_bounds__(32) agc_kernel(AgcArgs a) {
 		__syncwarp();
 		const int n0 = j * HFDL_AGC_CH;
 		const int cnt = (N - n0 < HFDL_AGC_CH) ? (N - n0) : HFDL_AGC_CH;
+		const cf *in = s_in[j & 1];
+		for(int i = lane; i < cnt; i += 32) { const cf xv = in[i]; s_px[i] = alpha * (xv.x * xv.x + xv.y * xv.y); }
+		__syncwarp();
 		if(lane == 0) {
-			const cf *in = s_in[j & 1];
+			s_G[0] = G;
 #pragma unroll 4
 			for(int i = 0; i < cnt; i++) {
-				cf xv = in[i];
-				cf r = make_float2(xv.x * g, xv.y * g);
-				float p = r.x * r.x + r.y * r.y;
-				// (1.0 - alpha)*y2 + alpha*p with the product term kept exact: y2 - alpha*y2
-				y2 = fmaf(alpha, p, fmaf(-alpha, y2, y2));
-				// g *= exp(-0.5*alpha*ln(y2)) == 2^(-0.5*alpha*log2(y2)): MUFU.LG2 + MUFU.EX2 on the critical chain
-				const float e = hfdl_exp2_fast(-0.5f * alpha * hfdl_log2_fast(y2));
-				g = fminf((y2 > 1e-6f) ? g * e : g, 1e6f);
-				s_out[i] = r;
-				s_lvl[i] = __fdividef(1.0f, g);
+				// (1.0 - alpha)*y2 with the product term kept exact: y2 - alpha*y2
+				y2 = fmaf(s_px[i], G, fmaf(-alpha, y2, y2));
+				const float e = hfdl_exp2_fast(-alpha * hfdl_log2_fast(y2));
+				G = fminf((y2 > 1e-6f) ? G * e : G, 1e12f);
+				s_G[i + 1] = G;
 			}
 		}
 		__syncwarp();
-		for(int i = lane; i < cnt; i += 32) { out[n0 + i] = s_out[i]; lvl[n0 + i] = s_lvl[i]; }
+		for(int i = lane; i < cnt; i += 32) {
+			const float gb = sqrtf(s_G[i]);              // gain applied to sample i (before its update)
+			const cf xv = in[i];
+			out[n0 + i] = make_float2(xv.x * gb, xv.y * gb);
+			lvl[n0 + i] = 1.0f / sqrtf(s_G[i + 1]);
+		}
 		__syncwarp();
 		{
 			const int nn0 = (j + 2) * HFDL_AGC_CH;
@@ -153,7 +161,7 @@ __global__ void __launch_bounds__(32) agc_kernel(AgcArgs a) {
 		}
 	}
 	hfdl_cp_async_wait<0>();
-	if(lane == 0) { a.state[c].g = g; a.state[c].y2 = y2; }
+	if(lane == 0) { a.state[c].g = G; a.state[c].y2 = y2; }
 }
 
 // ======================================================================================

@@ -293,7 +293,7 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 		// The demodulator is a feed-forward chain agc -> bank -> loop whose first and last stage are latency-bound
 		// recurrences: the batch is split into sub-ranges so that agc/bank of later sub-ranges (and of the next batch)
 		// run while loop_kernel works on earlier ones (both recurrences keep their state in HBM between launches).
-		const int nsub = (n_out >= 8 * 2048) ? HFDL_NSUB : 1;
+		const int nsub = std::max(1, std::min(HFDL_NSUB, n_out / 1024));     // sub-ranges of >= 1024 samples
 		CK(cudaStreamWaitEvent(st2, fe->ev_front[p], 0));
 		int first_loop = -1, last_loop = -1;
 		for(int i = 0; i < nsub; i++) {
@@ -548,7 +548,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaMemset(fe->d_cap_cnt, 0, sizeof(int) * 2));
 	fe->tmp_len = std::max((long long)N, (long long)B * fe->out_per_block + 64);
 	CKD(cudaMalloc((void **)&fe->d_tmp, sizeof(cf) * (size_t)fe->tmp_len));
-	if(getenv("HFDL_B200_DEBUG")) { CKD(cudaMalloc((void **)&fe->d_dbg, sizeof(long long) * 4 * (size_t)C)); CKD(cudaMemset(fe->d_dbg, 0, sizeof(long long) * 4 * (size_t)C)); }
+	if(getenv("HFDL_B200_DEBUG")) { CKD(cudaMalloc((void **)&fe->d_dbg, sizeof(long long) * 12 * (size_t)C)); CKD(cudaMemset(fe->d_dbg, 0, sizeof(long long) * 12 * (size_t)C)); }
 	CKD(cudaEventCreate(&fe->ev0));
 	CKD(cudaEventCreate(&fe->ev1));
 	if(compute_tapslices(fe)) { hfdl_b200_destroy(fe); return -1; }
@@ -711,10 +711,14 @@ int32_t hfdl_b200_channel_stats(hfdl_b200_frontend_t *fe, int32_t channel, int32
 void hfdl_b200_print_summary(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
 	if(fe->d_dbg) {
-		std::vector<long long> v((size_t)fe->C * 4);
+		std::vector<long long> v((size_t)fe->C * 12);
 		drain(fe);
 		cudaMemcpy(v.data(), fe->d_dbg, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
-		for(int c = 0; c < fe->C && c < 4; c++) fprintf(stderr, "loop_kernel ch%d cycles: timing warp %lld (waiting %lld)  demod warp %lld (waiting %lld)\n", c, v[(size_t)c * 4], v[(size_t)c * 4 + 1], v[(size_t)c * 4 + 2], v[(size_t)c * 4 + 3]);
+		for(int c = 0; c < fe->C && c < 4; c++) {
+			const long long *q = &v[(size_t)c * 12];
+			fprintf(stderr, "loop_kernel ch%d cycles: timing warp %lld (blocked %lld; polls: ring full %lld, loader %lld; outputs %lld, of them generic %lld; fast-loop entries %lld, left at loader limit %lld, at ring limit %lld)  demod warp %lld (waiting %lld)\n",
+				c, q[0], q[1], q[4], q[5], q[6], q[8], q[7], q[9], q[10], q[2], q[3]);
+		}
 	}
 	long long t[4] = { 0, 0, 0, 0 };
 	for(int c = 0; c < fe->C; c++) { int32_t s[4]; if(hfdl_b200_channel_stats(fe, c, s) == 0) for(int i = 0; i < 4; i++) t[i] += s[i]; }

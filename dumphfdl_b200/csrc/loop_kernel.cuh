@@ -40,7 +40,7 @@ struct LoopArgs {
 	cf *datasym; int nslots;   // [C][nslots][HFDL_DATA_SYMS_MAX]
 	FrameRec *frames; int *nframes; int max_frames;
 	int cap_channel; cf *cap_eq; int *cap_cnt; int cap_max;      // f_eq_out checkpoint of one channel
-	long long *dbg_cycles;     // diagnostics only: [C][4] = timing-warp total / waiting, demod-warp total / waiting
+	long long *dbg_cycles;     // diagnostics only: [C][8] = timing-warp total / blocked, demod-warp total / waiting, polls (ring full / loader), outputs
 	int debug_mode;
 };
 
@@ -237,13 +237,24 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 	const int l16 = lane & 15;
 	int done = 0;
 	unsigned bacc = 0; int nacc = 0;             // RUN_BITS: bits collected since the last merge into S.bits
-	// E.x stays the canonical 15-element window; xs is the window of the NEXT symbol, already shifted by two:
-	// its lanes 0..12 hold the 13 elements that are known before that symbol's two outputs arrive
-	float drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16), drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16);
+	// E.x stays the canonical 15-element window (lane l16 = element l16).  The equaliser output of a symbol is
+	//   s = sum_{i<13} conj(w_i) x_{i+2}  +  conj(w_13) r0 + conj(w_14) r1          (r0, r1: the symbol's two rotated inputs)
+	// and only the last two terms depend on the current Costas phase.  P = the first sum is prepared ahead:
+	//  * LMS runs (weights change every symbol): after the update, from the window shifted by two (xs);
+	//  * all other runs (weights frozen): P = Q + conj(w_11) r0' + conj(w_12) r1' with r0', r1' the previous symbol's
+	//    inputs and Q = sum_{i<11} conj(w_i) x_{i+2} -- the latter is known a whole symbol earlier, so its shuffle
+	//    reduction is off the phase -> decision -> phase chain.  wq = the weights moved up by four lanes, so that Q of
+	//    the NEXT symbol is a plain lane-wise product with the current window.
+	constexpr bool LMS = (MODE == RUN_TRAIN);
+	float drop0 = 0.f, drop1 = 0.f, x2s = 0.f;
+	if(LMS) { drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16); drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16); x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16); }
 	cf xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
-	float x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
 	cf P;
 	{ cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f); P = half_warp_sum(p); }
+	cf wq = make_float2(__shfl_up_sync(0xffffffffu, E.w.x, 4, 16), __shfl_up_sync(0xffffffffu, E.w.y, 4, 16));
+	if(l16 < 4 || l16 >= HFDL_EQ_LEN) wq = make_float2(0.f, 0.f);
+	const cf w11 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 11, 16), __shfl_sync(0xffffffffu, E.w.y, 11, 16));
+	const cf w12 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 12, 16), __shfl_sync(0xffffffffu, E.w.y, 12, 16));
 	float4 e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)), e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
 	for(;;) {
 		// warp vote: the lanes are not guaranteed to be converged at the prefetch, so the decision must not depend on
@@ -252,54 +263,64 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 		if(HFDL_UNLIKELY(!__all_sync(0xffffffffu, ((__float_as_uint(e0.w) >> 21) == hi) & ((__float_as_uint(e1.w) >> 21) == hi)))) {
 			// both outputs of the symbol are not there yet: wait, or leave when the batch ends before them
 			bool ok = false;
+			const long long t0 = hfdl_clock();
 			for(;;) {
-				const long long t0 = hfdl_clock();
 				const int ack = HFDL_UNI(lk_ack_gen), end_seq = HFDL_UNI(lk_end_seq);
 				const unsigned t0w = (unsigned)HFDL_UNI(lk_ring_tag(seq & (HFDL_LK_RING - 1)));
 				const unsigned t1w = (unsigned)HFDL_UNI(lk_ring_tag((seq + 1) & (HFDL_LK_RING - 1)));
 				if(lk_tag_ok(t0w, gen, seq) && lk_tag_ok(t1w, gen, seq + 1)) { ok = true; break; }
 				if(ack == gen && seq + 1 >= end_seq) break;
 				HFDL_SPIN_PAUSE();
-				*p_twait += hfdl_clock() - t0;
 			}
+			*p_twait += hfdl_clock() - t0;
 			if(!ok) break;
 			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+		}
+		cf Qn = make_float2(0.f, 0.f);
+		if(!LMS) {	// Q of the next symbol from the current window: independent of everything below
+			Qn = half_warp_sum(conj_mul(wq, E.x));
+			xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
 		}
 		const cf r0 = costas_rotate(S, e0.x, e0.y);
 		const cf r1 = costas_rotate(S, e1.x, e1.y);
 		const float lvl1 = e1.z;
 		const int k1 = (int)(__float_as_uint(e1.w) & 0xFFFFFu);
 		// ---- eqlms_cccf_push x2 + execute: the 13 older taps are already summed in P
-		const float x2a = r0.x * r0.x + r0.y * r0.y, x2b = r1.x * r1.x + r1.y * r1.y;
-		S.eq_x2_sum = S.eq_x2_sum + x2a - drop0;
-		S.eq_x2_sum = S.eq_x2_sum + x2b - drop1;
-		S.eq_count += 2;
 		cf s;
 		{
 			const cf a = conj_mul(E.w13, r0), b = conj_mul(E.w14, r1);
 			s = make_float2((P.x + a.x) + b.x, (P.y + a.y) + b.y);
 		}
-		{	// window update without branches: lanes 13 / 14 take the two new elements
-			const bool is13 = (l16 == 13), is14 = (l16 == 14);
+		S.eq_count += 2;
+		const bool is13 = (l16 == 13), is14 = (l16 == 14);
+		seq += 2;
+		done++;
+		const bool last = (done == nsym);
+		if(LMS) {
+			const float x2a = r0.x * r0.x + r0.y * r0.y, x2b = r1.x * r1.x + r1.y * r1.y;
+			S.eq_x2_sum = S.eq_x2_sum + x2a - drop0;
+			S.eq_x2_sum = S.eq_x2_sum + x2b - drop1;
+			// window update without branches: lanes 13 / 14 take the two new elements
 			E.x.x = is13 ? r0.x : xs.x; E.x.y = is13 ? r0.y : xs.y; E.x2 = is13 ? x2a : x2s;
 			E.x.x = is14 ? r1.x : E.x.x; E.x.y = is14 ? r1.y : E.x.y; E.x2 = is14 ? x2b : E.x2;
-		}
-		if(MODE == RUN_TRAIN) {        // eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
+			// eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
 			float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
 			if(S.bitmask & 1u) d = -d;
 			eq_step(S, E, d, s, r0, r1);
 			S.T_idx++;
+			// prefetch the next symbol's entries, pre-shift the window for it and reduce its 13 known taps
+			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+			drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16); drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16);
+			xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
+			x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
+			{ cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f); P = half_warp_sum(p); }
+		} else {
+			const cf a = conj_mul(w11, r0), b = conj_mul(w12, r1);
+			P = make_float2((Qn.x + a.x) + b.x, (Qn.y + a.y) + b.y);
+			E.x.x = is13 ? r0.x : xs.x; E.x.y = is13 ? r0.y : xs.y;
+			E.x.x = is14 ? r1.x : E.x.x; E.x.y = is14 ? r1.y : E.x.y;
+			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
 		}
-		seq += 2;
-		done++;
-		const bool last = (done == nsym);
-		// ---- prefetch the next symbol's entries, pre-shift the window for it and reduce its 13 known taps:
-		//      all of this is independent of the decision / phase-error chain below and overlaps with it
-		e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
-		drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16); drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16);
-		xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
-		x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
-		{ cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f); P = half_warp_sum(p); }
 		// ---- slicer, Costas adjust
 		if(HFDL_UNLIKELY(cap)) { if(lane == 0 && cap_n < cap_max) cap_eq[cap_n] = s; cap_n++; }
 		cf x_hat;
@@ -354,6 +375,13 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 		S.symsync_out_idx += 2;
 		if(lane == 0) { lk_tail = seq; lk_tail_k = k_prev; }
 		if(stop) break;
+	}
+	if(!LMS && done > 0) {             // the |x|^2 bookkeeping of eqlms_cccf_push was skipped: rebuild it from the window
+		E.x2 = E.x.x * E.x.x + E.x.y * E.x.y;
+		float t = l16 < HFDL_EQ_LEN ? E.x2 : 0.f;
+#pragma unroll
+		for(int m = 8; m >= 1; m >>= 1) t += __shfl_xor_sync(0xffffffffu, t, m);
+		S.eq_x2_sum = t;
 	}
 	if(MODE == RUN_BITS) {             // merge the remaining nacc < 32 bits
 		for(int i = nacc - 1; i >= 0; i--) bits_push(S.bits, bacc >> i);
@@ -416,7 +444,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		int seq = 0;                        // sequence number of the next output
 		int my_gen = 0;
 		bool finished = false;
-		long long t_begin = hfdl_clock(), t_wait = 0;
+		long long t_begin = hfdl_clock(), t_wait = 0, t_blocked = 0, n_full = 0, n_starved = 0, n_fast = 0, n_gen_out = 0, n_exit_k = 0, n_exit_seq = 0;
 		// one symsync output at input sample k_, arm index b_ (symsync_crcf_step body); TED_ = timing-error detector runs
 #define HFDL_SS_TED(mf_, row_, bb_) do { \
 			const cf dmf_ = (row_)[16 + (bb_)]; \
@@ -454,7 +482,13 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			}
 			const int seq_lim = HFDL_UNI(lk_tail) + HFDL_LK_RING - 2;       // entries [tail, seq) are unread
 			int k_lim = HFDL_UNI(lk_loaded);
-			if(seq >= seq_lim || (!mid && kn >= k_lim)) { const long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); t_wait += hfdl_clock() - t0; continue; }
+			if(seq >= seq_lim || (!mid && kn >= k_lim)) {
+				if(!t_blocked) t_blocked = hfdl_clock();
+				if(seq >= seq_lim) n_full++; else n_starved++;
+				HFDL_SPIN_PAUSE();
+				continue;
+			}
+			if(t_blocked) { t_wait += hfdl_clock() - t_blocked; t_blocked = 0; }
 			__threadfence_block();
 
 			if(S.ss_since_reset >= HFDL_SS_SUB && S.ss_decim_counter == 1u && S.ss_b >= 0) {
@@ -478,6 +512,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 					const int m = bi >> 4;
 					k += m; tau -= (float)m; b = bi & 15;
 				}
+				n_fast++; if(k >= k_lim) n_exit_k++; else if(seq >= seq_lim) n_exit_seq++;
 				// back to the generic representation
 				S.ss_tau = tau; S.ss_b = b; S.ss_decim_counter = odd ? 2u : 1u;
 				kn = k; mid = rare != 0;
@@ -502,14 +537,18 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				S.ss_tau += S.ss_del;
 				S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);
 				if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, lk_lvl[kn & (HFDL_LK_BR - 1)], lk_tag(my_gen, S.ss_b < HFDL_SS_NPFB, seq, kn));
-				seq++;
+				seq++; n_gen_out++;
 			} else {
 				S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;                   // ... then tau -= 1, b -= npfb
 				kn++; mid = false;
 			}
 		}
 #undef HFDL_SS_TED
-		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 4 + 0] += hfdl_clock() - t_begin; a.dbg_cycles[c * 4 + 1] += t_wait; }
+		if(a.dbg_cycles && lane == 0) {
+			a.dbg_cycles[c * 12 + 0] += hfdl_clock() - t_begin; a.dbg_cycles[c * 12 + 1] += t_wait;
+			a.dbg_cycles[c * 12 + 4] += n_full; a.dbg_cycles[c * 12 + 5] += n_starved; a.dbg_cycles[c * 12 + 6] += seq;
+			a.dbg_cycles[c * 12 + 7] += n_fast; a.dbg_cycles[c * 12 + 8] += n_gen_out; a.dbg_cycles[c * 12 + 9] += n_exit_k; a.dbg_cycles[c * 12 + 10] += n_exit_seq;
+		}
 		// timing-loop state after the last input sample of the batch (kn may lie beyond it: undo the skipped samples)
 		__syncwarp();
 		if(lane == 0) {
@@ -546,11 +585,11 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		for(;;) {
 			// fast path: a run of whole symbols up to (not including) the symbol of the next framer event
 #define HFDL_RUN(MODE, AR) demod_run<MODE, AR>(S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, &t_wait, cap, a.cap_eq, cap_n_eq, a.cap_max, lvl, A_bits)
-			if(S.fr_state == HF_A1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode != 2
+			if(S.fr_state == HF_A1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode < 2
 					&& fabsf(S.c_dphi) <= 0.25f && symcnt + 1u < 13u * HFDL_SINGLE_SLOT_FRAME_LEN) {
 				const int nsym = (int)(13u * HFDL_SINGLE_SLOT_FRAME_LEN - 1u - symcnt);     // the symbol of the 13-frame timeout goes the generic way
 				if(HFDL_RUN(RUN_A1, 1) > 0) continue;
-			} else if(S.fr_state > HF_A1 && S.symbols_wanted > 1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode != 2) {
+			} else if(S.fr_state > HF_A1 && S.symbols_wanted > 1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode < 2) {
 				const int nsym = S.symbols_wanted - 1;
 				int did;
 				if(S.s_state == HS_EMIT_BITS) did = HFDL_RUN(RUN_BITS, 1);
@@ -577,6 +616,11 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			const int k = (int)(tagw & 0xFFFFFu);
 			const bool more = (tagw >> 20) & 1u;
 			const float level = ent.z;
+			if(HFDL_UNLIKELY(a.debug_mode == 3)) {      // diagnostics: drain the ring without demodulating (speed of the timing warp alone)
+				k_prev = k; seq++;
+				if(lane == 0) { lk_tail = seq; lk_tail_k = k; }
+				continue;
+			}
 			// noise-floor clock ticks once per input sample, before that sample's outputs (hfdl.c:700)
 			if(HFDL_UNLIKELY(S.fr_state == HF_A1)) { for(int sidx = k_prev + 1; sidx <= k; sidx++) HFDL_NF_TICK(sidx); }
 			k_prev = k;
@@ -749,7 +793,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				reset_pending = false;
 			}
 		}
-		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 4 + 2] += hfdl_clock() - t_begin; a.dbg_cycles[c * 4 + 3] += t_wait; }
+		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 12 + 2] += hfdl_clock() - t_begin; a.dbg_cycles[c * 12 + 3] += t_wait; }
 		for(int sidx = k_prev + 1; sidx < N; sidx++) HFDL_NF_TICK(sidx);      // input samples after the last output
 #undef HFDL_NF_TICK
 		S.sample_cnt = cnt_base + (unsigned long long)N;

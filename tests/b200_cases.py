@@ -104,11 +104,15 @@ def run_oracle(sr, freqs, raw, sfmt, capture_ch=None, taps=()):
     return p
 
 
-def compare_pdus(got, ref, truth=None):
+def compare_pdus(got, ref, truth=None, subset=False):
     g = sorted((q.freq, q.sample_cnt_end, q.data(), q.M1, q.crc_good, q.sample_cnt_a2) for q in got)
     r = sorted((q.freq, q.sample_cnt_end, q.data(), q.M1, q.crc_good, q.sample_cnt_a2) for q in ref)
     assert g == r, "PDU list differs from the oracle's"
-    if truth is not None:
+    if truth is not None and subset:
+        # the demodulator (reference and oracle alike) may miss a frame that follows another one closely; what it
+        # does deliver with a good FCS must be a transmitted PDU
+        assert all((f, d) in set(truth) for f, _, d, _, crc, _ in g if crc)
+    elif truth is not None:
         assert sorted((f, d) for f, _, d, _, _, _ in g) == sorted(truth)
 
 
@@ -190,7 +194,7 @@ def case_frontend_stream(lib, sr, freqs, plan, dur, batch, esn0=20.0, seed=31, p
         fe.push(x)
     fe.flush()
     got += fe.pdus()
-    compare_pdus(got, ref, truth)
+    compare_pdus(got, ref, truth, subset=True)
     for c in range(len(freqs)):
         assert fe.stats(c) == p.stats(c)
     for name in ("agc", "mf", "eq"):
