@@ -157,20 +157,30 @@ __device__ __forceinline__ unsigned lk_tag(int gen, int more, int seq, int k) {
 __device__ __forceinline__ unsigned lk_tag_hi(int gen, int seq) { return (((unsigned)gen & 0x7Fu) << 4) | (((unsigned)seq >> 6) & 0xFu); }
 __device__ __forceinline__ bool lk_tag_ok(unsigned tag, int gen, int seq) { return (tag >> 21) == lk_tag_hi(gen, seq); }
 
+__device__ __forceinline__ float costas_wrap_fwd(float phi) {      // (double)phi > M_PI  <=>  phi > 3.1415925f; 2*pi split hi+lo
+	const float dn = (phi - 6.2831855f) + 1.7484555e-7f, up = (phi + 6.2831855f) - 1.7484555e-7f;
+	float w_ = phi;
+	w_ = phi > 3.1415925f ? dn : w_;
+	w_ = phi < -3.1415925f ? up : w_;
+	return w_;
+}
 // Costas step + rotation of one symsync output (hfdl.c:250-267,709-710)
 __device__ __forceinline__ cf costas_rotate(DemodState &S, float re, float im) {
-	S.c_phi += S.c_dphi;
-	{	// (double)phi > M_PI  <=>  phi > 3.1415925f (largest float below pi); 2*pi split hi+lo
-		const float dn = (S.c_phi - 6.2831855f) + 1.7484555e-7f, up = (S.c_phi + 6.2831855f) - 1.7484555e-7f;
-		float w_ = S.c_phi;
-		w_ = S.c_phi > 3.1415925f ? dn : w_;
-		w_ = S.c_phi < -3.1415925f ? up : w_;
-		S.c_phi = w_;
-	}
+	S.c_phi = costas_wrap_fwd(S.c_phi + S.c_dphi);
 	float sn, cs;
 	hfdl_sincos_fast(S.c_phi, &sn, &cs);
 	return make_float2(re * cs + im * sn, im * cs - re * sn);
 }
+
+// Scheduling fence for the single sequential warp: both values are complete before anything that is derived from
+// them afterwards is issued.  Used to keep the shuffle stages of a reduction apart from their consumers so that
+// the shuffle latency overlaps with an independent dependent chain (ptxas otherwise packs producer and consumer
+// together and the in-order warp eats the full latency of every stage).
+#ifdef HFDL_CUSIM
+#define HFDL_ORDER2(a, b) do { } while(0)
+#else
+#define HFDL_ORDER2(a, b) asm volatile("" : "+f"(a), "+f"(b))
+#endif
 
 // ---- shared memory of one channel CTA (file scope: every access is a direct shared-window address) ----------
 __shared__ float4 lk_ring[HFDL_LK_RING];        // output ring: {sym.re, sym.im, AGC level, tag}
@@ -221,6 +231,24 @@ __device__ __forceinline__ unsigned lk_ring_tag(int i) {
 }
 #endif
 
+// Cold path of the demodulator warp: both outputs of the next symbol are not in the ring yet.  Polls until they are
+// (returns true) or until the timing warp has declared the end of the batch before them (false).  Kept out of line
+// so that the hot loop is straight fall-through code.
+__device__ __noinline__ bool lk_wait_pair(int gen, int seq, long long *p_twait) {
+	bool ok = false;
+	const long long t0 = hfdl_clock();
+	for(;;) {
+		const int ack = HFDL_UNI(lk_ack_gen), end_seq = HFDL_UNI(lk_end_seq);
+		const unsigned t0w = (unsigned)HFDL_UNI(lk_ring_tag(seq & (HFDL_LK_RING - 1)));
+		const unsigned t1w = (unsigned)HFDL_UNI(lk_ring_tag((seq + 1) & (HFDL_LK_RING - 1)));
+		if(lk_tag_ok(t0w, gen, seq) && lk_tag_ok(t1w, gen, seq + 1)) { ok = true; break; }
+		if(ack == gen && seq + 1 >= end_seq) break;
+		HFDL_SPIN_PAUSE();
+	}
+	*p_twait += hfdl_clock() - t0;
+	return ok;
+}
+
 // ---- fast runs -------------------------------------------------------------------------------------------------
 // Between two framer events the framer only counts symbols down (hfdl.c:774-777) and, inside a frame, neither the
 // noise-floor clock nor any loop reset can fire (both need FRAMER_A1_SEARCH).  demod_run() therefore processes
@@ -256,33 +284,53 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 	const cf w11 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 11, 16), __shfl_sync(0xffffffffu, E.w.y, 11, 16));
 	const cf w12 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 12, 16), __shfl_sync(0xffffffffu, E.w.y, 12, 16));
 	float4 e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)), e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+	// Validity of the two prefetched entries is a warp vote: the lanes are not guaranteed to be converged at the
+	// prefetch, so the decision must not depend on one lane's view (a lane that saw a not-yet-valid entry sends the
+	// whole warp through the reload).  seq is even here: seq and seq + 1 lie in the same lap of the ring.
+#define HFDL_PAIR_VALID() __all_sync(0xffffffffu, ((__float_as_uint(e0.w) >> 21) == lk_tag_hi(gen, seq)) & ((__float_as_uint(e1.w) >> 21) == lk_tag_hi(gen, seq)))
+	bool stop = false;
 	for(;;) {
-		// warp vote: the lanes are not guaranteed to be converged at the prefetch, so the decision must not depend on
-		// one lane's view (a lane that saw a not-yet-valid entry sends the whole warp through the reload below)
-		const unsigned hi = lk_tag_hi(gen, seq);      // seq is even here: seq and seq + 1 lie in the same lap
-		if(HFDL_UNLIKELY(!__all_sync(0xffffffffu, ((__float_as_uint(e0.w) >> 21) == hi) & ((__float_as_uint(e1.w) >> 21) == hi)))) {
+		if(!HFDL_PAIR_VALID()) {
 			// both outputs of the symbol are not there yet: wait, or leave when the batch ends before them
-			bool ok = false;
-			const long long t0 = hfdl_clock();
-			for(;;) {
-				const int ack = HFDL_UNI(lk_ack_gen), end_seq = HFDL_UNI(lk_end_seq);
-				const unsigned t0w = (unsigned)HFDL_UNI(lk_ring_tag(seq & (HFDL_LK_RING - 1)));
-				const unsigned t1w = (unsigned)HFDL_UNI(lk_ring_tag((seq + 1) & (HFDL_LK_RING - 1)));
-				if(lk_tag_ok(t0w, gen, seq) && lk_tag_ok(t1w, gen, seq + 1)) { ok = true; break; }
-				if(ack == gen && seq + 1 >= end_seq) break;
-				HFDL_SPIN_PAUSE();
-			}
-			*p_twait += hfdl_clock() - t0;
-			if(!ok) break;
+			if(!lk_wait_pair(gen, seq, p_twait)) break;
 			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
 		}
-		cf Qn = make_float2(0.f, 0.f);
-		if(!LMS) {	// Q of the next symbol from the current window: independent of everything below
-			Qn = half_warp_sum(conj_mul(wq, E.x));
+	  // hot loop: one symbol per iteration, left only at the end of the run or when the ring runs dry (the back edge is
+	  // its only taken branch)
+	  for(;;) {
+		// Costas step of both outputs, rotation, and -- in frozen-weight runs -- Q of the NEXT symbol from the current
+		// window.  Q is independent of everything else in this iteration; its four shuffle stages are spread over the
+		// phase -> sincos -> rotation -> decision chain (HFDL_ORDER2) so that their latency is hidden by that chain.
+		cf q = make_float2(0.f, 0.f);
+		float qa = 0.f, qb = 0.f;
+		if(!LMS) {
+			q = conj_mul(wq, E.x);
+			qa = __shfl_xor_sync(0xffffffffu, q.x, 8); qb = __shfl_xor_sync(0xffffffffu, q.y, 8);
 			xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
 		}
-		const cf r0 = costas_rotate(S, e0.x, e0.y);
-		const cf r1 = costas_rotate(S, e1.x, e1.y);
+		const float phi0 = costas_wrap_fwd(S.c_phi + S.c_dphi);
+		float phi1 = costas_wrap_fwd(phi0 + S.c_dphi);
+		if(!LMS) {
+			HFDL_ORDER2(qa, phi1);
+			q.x += qa; q.y += qb;
+			qa = __shfl_xor_sync(0xffffffffu, q.x, 4); qb = __shfl_xor_sync(0xffffffffu, q.y, 4);
+		}
+		float sn0, cs0, sn1, cs1;
+		hfdl_sincos_fast(phi0, &sn0, &cs0);
+		hfdl_sincos_fast(phi1, &sn1, &cs1);
+		if(!LMS) {
+			HFDL_ORDER2(qa, sn1);
+			q.x += qa; q.y += qb;
+			qa = __shfl_xor_sync(0xffffffffu, q.x, 2); qb = __shfl_xor_sync(0xffffffffu, q.y, 2);
+		}
+		S.c_phi = phi1;
+		const cf r0 = make_float2(e0.x * cs0 + e0.y * sn0, e0.y * cs0 - e0.x * sn0);
+		cf r1 = make_float2(e1.x * cs1 + e1.y * sn1, e1.y * cs1 - e1.x * sn1);
+		if(!LMS) {
+			HFDL_ORDER2(qa, r1.x);
+			q.x += qa; q.y += qb;
+			qa = __shfl_xor_sync(0xffffffffu, q.x, 1); qb = __shfl_xor_sync(0xffffffffu, q.y, 1);
+		}
 		const float lvl1 = e1.z;
 		const int k1 = (int)(__float_as_uint(e1.w) & 0xFFFFFu);
 		// ---- eqlms_cccf_push x2 + execute: the 13 older taps are already summed in P
@@ -315,6 +363,8 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
 			{ cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f); P = half_warp_sum(p); }
 		} else {
+			HFDL_ORDER2(qa, s.x);
+			const cf Qn = make_float2(q.x + qa, q.y + qb);
 			const cf a = conj_mul(w11, r0), b = conj_mul(w12, r1);
 			P = make_float2((Qn.x + a.x) + b.x, (Qn.y + a.y) + b.y);
 			E.x.x = is13 ? r0.x : xs.x; E.x.y = is13 ? r0.y : xs.y;
@@ -322,7 +372,8 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
 		}
 		// ---- slicer, Costas adjust
-		if(HFDL_UNLIKELY(cap)) { if(lane == 0 && cap_n < cap_max) cap_eq[cap_n] = s; cap_n++; }
+		if(cap & (lane == 0) & (cap_n < cap_max)) cap_eq[cap_n] = s;
+		cap_n += cap ? 1 : 0;
 		cf x_hat;
 		unsigned bits = modem_demod(ARITY, s, lk_psk, &x_hat);
 		float err = s.y * x_hat.x - s.x * x_hat.y;
@@ -330,7 +381,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 		S.c_phi += 0.1f * err;
 		S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
 		symcnt++;
-		bool stop = last;
+		stop = last;
 		if(MODE == RUN_BITS) {
 			bacc = (bacc << 1) | ((bits ^ S.bitmask) & 1u);
 			if(++nacc == 32) {         // merge 32 bits at once: a whole-word shift of the 127-bit register
@@ -374,8 +425,11 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 		k_prev = k1;
 		S.symsync_out_idx += 2;
 		if(lane == 0) { lk_tail = seq; lk_tail_k = k_prev; }
+		if(stop | !HFDL_PAIR_VALID()) break;
+	  }
 		if(stop) break;
 	}
+#undef HFDL_PAIR_VALID
 	if(!LMS && done > 0) {             // the |x|^2 bookkeeping of eqlms_cccf_push was skipped: rebuild it from the window
 		E.x2 = E.x.x * E.x.x + E.x.y * E.x.y;
 		float t = l16 < HFDL_EQ_LEN ? E.x2 : 0.f;
