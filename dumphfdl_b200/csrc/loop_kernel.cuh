@@ -148,14 +148,18 @@ __device__ __forceinline__ unsigned modem_demod(int m, cf x, const cf (*psk)[8],
 // a value polled from shared memory is made warp-uniform (lane 0's view) so that every lane takes the same branch
 #define HFDL_UNI(v) __shfl_sync(0xffffffffu, (int)(v), 0)
 
-// ---- output-ring entry tags ----------------------------------------------------------------------------------
-// w = gen[31:25] | lap[24:21] | more[20] | k[19:0]: reset generation of the timing warp, (sequence number / ring
-// size) mod 16, "another output of the same input sample follows", input-sample index of the output.
-__device__ __forceinline__ unsigned lk_tag(int gen, int more, int seq, int k) {
-	return ((unsigned)(gen & 0x7F) << 25) | ((unsigned)((seq >> 6) & 0xF) << 21) | ((unsigned)(more & 1) << 20) | (unsigned)k;
-}
+// ---- output ring ---------------------------------------------------------------------------------------------
+// Entry i of the ring is 16 bytes of data {sym.re, sym.im, AGC level, info} in lk_ring[i] plus a validity tag in
+// lk_tags[i].  info = more[20] | k[19:0]: "another output of the same input sample follows", input-sample index of
+// the output.  tag = gen[10:4] | lap[3:0]: reset generation of the timing warp, (sequence number / ring size) mod 16.
+// The producer writes the data, then (after a fence) the tag; a consumer reads the tag first and the data with a
+// load whose ADDRESS depends on the tag value, so "tag valid" implies "data complete" without assuming that a
+// 16-byte shared-memory access is single-copy atomic between warps (it is not: a combined {data, tag} vector was
+// observed torn when the consumer runs right behind the producer).
+#define HFDL_LK_TAG_INVALID 0x7FFFFFFFu          // bit 31 clear like every real tag (see lk_pair_load)
+__device__ __forceinline__ unsigned lk_info(int more, int k) { return ((unsigned)(more & 1) << 20) | (unsigned)k; }
 __device__ __forceinline__ unsigned lk_tag_hi(int gen, int seq) { return (((unsigned)gen & 0x7Fu) << 4) | (((unsigned)seq >> 6) & 0xFu); }
-__device__ __forceinline__ bool lk_tag_ok(unsigned tag, int gen, int seq) { return (tag >> 21) == lk_tag_hi(gen, seq); }
+__device__ __forceinline__ bool lk_tag_ok(unsigned tag, int gen, int seq) { return tag == lk_tag_hi(gen, seq); }
 
 __device__ __forceinline__ float costas_wrap_fwd(float phi) {      // (double)phi > M_PI  <=>  phi > 3.1415925f; 2*pi split hi+lo
 	const float dn = (phi - 6.2831855f) + 1.7484555e-7f, up = (phi + 6.2831855f) - 1.7484555e-7f;
@@ -176,65 +180,89 @@ __device__ __forceinline__ cf costas_rotate(DemodState &S, float re, float im) {
 // them afterwards is issued.  Used to keep the shuffle stages of a reduction apart from their consumers so that
 // the shuffle latency overlaps with an independent dependent chain (ptxas otherwise packs producer and consumer
 // together and the in-order warp eats the full latency of every stage).
-#ifdef HFDL_CUSIM
+#if defined(HFDL_CUSIM) || defined(HFDL_NO_ORDER)
 #define HFDL_ORDER2(a, b) do { } while(0)
 #else
 #define HFDL_ORDER2(a, b) asm volatile("" : "+f"(a), "+f"(b))
 #endif
 
 // ---- shared memory of one channel CTA (file scope: every access is a direct shared-window address) ----------
-__shared__ float4 lk_ring[HFDL_LK_RING];        // output ring: {sym.re, sym.im, AGC level, tag}
+__shared__ float4 lk_ring[HFDL_LK_RING];        // output ring data: {sym.re, sym.im, AGC level, info}
+__shared__ unsigned lk_tags[HFDL_LK_RING];      // output ring validity tags
 __shared__ float lk_lvl[HFDL_LK_BR];            // AGC level ring (1/g after the sample's update)
 __shared__ cf lk_psk[4][8];
 __shared__ cf lk_train[16];
 __shared__ volatile int lk_loaded, lk_tail, lk_tail_k, lk_end_seq, lk_done;
 __shared__ volatile int lk_reset_gen, lk_reset_k, lk_reset_seq, lk_ack_gen;
 
-// Output-ring accessors.  An entry is written and read as ONE 16-byte shared-memory access and validated by its tag;
-// all accesses are volatile (the other warp changes the ring behind the compiler's back).
+// Output-ring accessors; all accesses are volatile (the other warp changes the ring behind the compiler's back).
 #ifdef HFDL_CUSIM
-static inline void lk_ring_store(int i, float x, float y, float z, unsigned tag) {
+static inline void lk_ring_store(int i, float x, float y, float z, unsigned info, unsigned tag) {
 	volatile float *p = reinterpret_cast<volatile float *>(&lk_ring[i]);
-	p[0] = x; p[1] = y; p[2] = z;
+	p[0] = x; p[1] = y; p[2] = z; reinterpret_cast<volatile unsigned *>(p)[3] = info;
 	__atomic_thread_fence(__ATOMIC_RELEASE);
-	reinterpret_cast<volatile unsigned *>(p)[3] = tag;
+	reinterpret_cast<volatile unsigned *>(lk_tags)[i] = tag;
 }
-static inline float4 lk_ring_load(int i) {
-	// On the GPU the warp's 16-byte load is ONE converged access: every lane sees the same entry.  Host threads are
-	// not in lockstep, so the emulation reads through lane 0 and broadcasts (called by all 32 lanes of the warp).
+// Host threads are not in lockstep, so the emulation reads through lane 0 and broadcasts (called by all 32 lanes).
+static inline unsigned lk_ring_tag(int i) {
+	unsigned t = reinterpret_cast<volatile unsigned *>(lk_tags)[i];
+	__atomic_thread_fence(__ATOMIC_ACQUIRE);
+	return __shfl_sync(0xffffffffu, t, 0);
+}
+static inline float4 lk_ring_load(int i, unsigned = 0u) {
 	volatile float *p = reinterpret_cast<volatile float *>(&lk_ring[i]);
 	float4 r;
-	unsigned t = reinterpret_cast<volatile unsigned *>(p)[3];
-	__atomic_thread_fence(__ATOMIC_ACQUIRE);
-	r.x = p[0]; r.y = p[1]; r.z = p[2];
+	r.x = p[0]; r.y = p[1]; r.z = p[2]; r.w = p[3];
 	r.x = __shfl_sync(0xffffffffu, r.x, 0); r.y = __shfl_sync(0xffffffffu, r.y, 0); r.z = __shfl_sync(0xffffffffu, r.z, 0);
-	r.w = __uint_as_float(__shfl_sync(0xffffffffu, t, 0));
+	r.w = __shfl_sync(0xffffffffu, r.w, 0);
 	return r;
 }
-static inline unsigned lk_ring_tag(int i) { return reinterpret_cast<volatile unsigned *>(&lk_ring[i])[3]; }
-#else
-__device__ __forceinline__ void lk_ring_store(int i, float x, float y, float z, unsigned tag) {
-	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]);
-	asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "f"(x), "f"(y), "f"(z), "f"(__uint_as_float(tag)) : "memory");
+static inline void lk_pair_load(int seq, float4 &e0, float4 &e1, unsigned &t0, unsigned &t1) {
+	const int i = seq & (HFDL_LK_RING - 1);
+	t0 = lk_ring_tag(i); t1 = lk_ring_tag(i + 1);
+	e0 = lk_ring_load(i); e1 = lk_ring_load(i + 1);
 }
-__device__ __forceinline__ float4 lk_ring_load(int i) {
+#else
+__device__ __forceinline__ void lk_ring_store(int i, float x, float y, float z, unsigned info, unsigned tag) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]);
+	const unsigned ta = (unsigned)__cvta_generic_to_shared(&lk_tags[i]);
+	asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "f"(x), "f"(y), "f"(z), "f"(__uint_as_float(info)) : "memory");
+	__threadfence_block();
+	asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ta), "r"(tag) : "memory");
+}
+__device__ __forceinline__ unsigned lk_ring_tag(int i) {
+	const unsigned ta = (unsigned)__cvta_generic_to_shared(&lk_tags[i]);
+	unsigned t;
+	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(ta) : "memory");
+	return t;
+}
+// data of entry i; `dep` is a value that is 0 (bit 31 of a tag) but only known at run time: it makes the load
+// address -- and with it the load -- depend on the tag that was read before
+__device__ __forceinline__ float4 lk_ring_load(int i, unsigned dep = 0u) {
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]) + (dep << 4);
 	float4 r;
 	asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sa) : "memory");
 	return r;
 }
-__device__ __forceinline__ unsigned lk_ring_tag(int i) {
-	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]) + 12u;
-	unsigned t;
-	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(sa) : "memory");
-	return t;
+// tags and data of the pair (seq, seq + 1), seq even: one 8-byte tag load, then the two data loads behind it
+__device__ __forceinline__ void lk_pair_load(int seq, float4 &e0, float4 &e1, unsigned &t0, unsigned &t1) {
+	const int i = seq & (HFDL_LK_RING - 1);
+	const unsigned ta = (unsigned)__cvta_generic_to_shared(&lk_tags[i]);
+	asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t0), "=r"(t1) : "r"(ta) : "memory");
+	e0 = lk_ring_load(i, t0 >> 31);
+	e1 = lk_ring_load(i + 1, t1 >> 31);
 }
 #endif
 
 // Cold path of the demodulator warp: both outputs of the next symbol are not in the ring yet.  Polls until they are
 // (returns true) or until the timing warp has declared the end of the batch before them (false).  Kept out of line
 // so that the hot loop is straight fall-through code.
-__device__ __noinline__ bool lk_wait_pair(int gen, int seq, long long *p_twait) {
+#ifdef HFDL_INLINE_WAIT
+#define HFDL_WAIT_ATTR __forceinline__
+#else
+#define HFDL_WAIT_ATTR __noinline__
+#endif
+__device__ HFDL_WAIT_ATTR bool lk_wait_pair(int gen, int seq, long long *p_twait) {
 	bool ok = false;
 	const long long t0 = hfdl_clock();
 	for(;;) {
@@ -283,17 +311,18 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 	if(l16 < 4 || l16 >= HFDL_EQ_LEN) wq = make_float2(0.f, 0.f);
 	const cf w11 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 11, 16), __shfl_sync(0xffffffffu, E.w.y, 11, 16));
 	const cf w12 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 12, 16), __shfl_sync(0xffffffffu, E.w.y, 12, 16));
-	float4 e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)), e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+	float4 e0, e1; unsigned t0, t1;
+	lk_pair_load(seq, e0, e1, t0, t1);
 	// Validity of the two prefetched entries is a warp vote: the lanes are not guaranteed to be converged at the
 	// prefetch, so the decision must not depend on one lane's view (a lane that saw a not-yet-valid entry sends the
 	// whole warp through the reload).  seq is even here: seq and seq + 1 lie in the same lap of the ring.
-#define HFDL_PAIR_VALID() __all_sync(0xffffffffu, ((__float_as_uint(e0.w) >> 21) == lk_tag_hi(gen, seq)) & ((__float_as_uint(e1.w) >> 21) == lk_tag_hi(gen, seq)))
+#define HFDL_PAIR_VALID() __all_sync(0xffffffffu, (t0 == lk_tag_hi(gen, seq)) & (t1 == lk_tag_hi(gen, seq)))
 	bool stop = false;
 	for(;;) {
 		if(!HFDL_PAIR_VALID()) {
 			// both outputs of the symbol are not there yet: wait, or leave when the batch ends before them
 			if(!lk_wait_pair(gen, seq, p_twait)) break;
-			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+			lk_pair_load(seq, e0, e1, t0, t1);
 		}
 	  // hot loop: one symbol per iteration, left only at the end of the run or when the ring runs dry (the back edge is
 	  // its only taken branch)
@@ -357,7 +386,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			eq_step(S, E, d, s, r0, r1);
 			S.T_idx++;
 			// prefetch the next symbol's entries, pre-shift the window for it and reduce its 13 known taps
-			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+			lk_pair_load(seq, e0, e1, t0, t1);
 			drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16); drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16);
 			xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
 			x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
@@ -369,7 +398,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			P = make_float2((Qn.x + a.x) + b.x, (Qn.y + a.y) + b.y);
 			E.x.x = is13 ? r0.x : xs.x; E.x.y = is13 ? r0.y : xs.y;
 			E.x.x = is14 ? r1.x : E.x.x; E.x.y = is14 ? r1.y : E.x.y;
-			e0 = lk_ring_load(seq & (HFDL_LK_RING - 1)); e1 = lk_ring_load((seq + 1) & (HFDL_LK_RING - 1));
+			lk_pair_load(seq, e0, e1, t0, t1);
 		}
 		// ---- slicer, Costas adjust
 		if(cap & (lane == 0) & (cap_n < cap_max)) cap_eq[cap_n] = s;
@@ -452,10 +481,10 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 	const DemodTables &T = *a.tab;
 	const float *lvl = a.lvl + (long long)c * a.lvl_stride;
 	const int N = a.n_samples;
-	if(threadIdx.x < HFDL_LK_RING) lk_ring[threadIdx.x] = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
+	if(threadIdx.x < HFDL_LK_RING) { lk_ring[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f); lk_tags[threadIdx.x] = HFDL_LK_TAG_INVALID; }
 	if(threadIdx.x < 32) lk_psk[threadIdx.x >> 3][threadIdx.x & 7] = T.psk[threadIdx.x >> 3][threadIdx.x & 7];
 	if(threadIdx.x == 0) {
-		lk_loaded = 0; lk_tail = 0; lk_tail_k = -1; lk_end_seq = 0x7fffffff; lk_done = 0;
+		lk_loaded = 0; lk_tail = (int)(a.state[c].symsync_out_idx & 1u); lk_tail_k = -1; lk_end_seq = 0x7fffffff; lk_done = 0;
 		lk_reset_gen = 0; lk_reset_k = 0; lk_reset_seq = 0; lk_ack_gen = 0;
 	}
 	__syncthreads();
@@ -495,7 +524,9 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		const float ss_a1 = T.ss_a1, ss_a2 = T.ss_a2, ss_b0 = T.ss_b0, ss_radj = T.ss_rate_adj;
 		int kn = 0;                         // next input sample (generic stepping), or the sample of the next output (fast loop)
 		bool mid = false;                   // generic stepping: sample kn has been consumed, its outputs are being produced
-		int seq = 0;                        // sequence number of the next output
+		// sequence number of the next output.  It starts with the parity of the stream's output counter, so that the two
+		// outputs of a symbol are always the ring pair (even, odd): the demodulator warp reads them as one aligned pair
+		int seq = (int)(S.symsync_out_idx & 1u);
 		int my_gen = 0;
 		bool finished = false;
 		long long t_begin = hfdl_clock(), t_wait = 0, t_blocked = 0, n_full = 0, n_starved = 0, n_fast = 0, n_gen_out = 0, n_exit_k = 0, n_exit_seq = 0;
@@ -559,7 +590,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 					if(odd) HFDL_SS_TED(mf, row, b);
 					tau += S.ss_del;
 					const int bi = hfdl_round_pos(tau * (float)HFDL_SS_NPFB);
-					if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_tag(my_gen, bi < HFDL_SS_NPFB, seq, k));
+					if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_info(bi < HFDL_SS_NPFB, k), lk_tag_hi(my_gen, seq));
 					seq++;
 					odd ^= 1;
 					if(HFDL_UNLIKELY(bi < HFDL_SS_NPFB)) { b = bi; rare = 1; break; }     // del < 1: another output of the same sample
@@ -590,7 +621,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				S.ss_decim_counter++;
 				S.ss_tau += S.ss_del;
 				S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);
-				if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, lk_lvl[kn & (HFDL_LK_BR - 1)], lk_tag(my_gen, S.ss_b < HFDL_SS_NPFB, seq, kn));
+				if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, lk_lvl[kn & (HFDL_LK_BR - 1)], lk_info(S.ss_b < HFDL_SS_NPFB, kn), lk_tag_hi(my_gen, seq));
 				seq++; n_gen_out++;
 			} else {
 				S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;                   // ... then tau -= 1, b -= npfb
@@ -633,7 +664,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		__syncwarp();
 #define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1) { if((++S.nf_clk & 0xFFu) == 0xFFu) \
 			S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } } while(0)     /* hfdl.c:700-706 */
-		int seq = 0, k_prev = -1, gen = 0;
+		int seq = (int)(S.symsync_out_idx & 1u), k_prev = -1, gen = 0;     // same start as the timing warp (pair alignment)
 		bool reset_pending = false;
 		long long t_begin = hfdl_clock(), t_wait = 0;
 		for(;;) {
@@ -665,7 +696,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				const long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); t_wait += hfdl_clock() - t0;
 			}
 			if(!have) break;                                          // end of batch: every output consumed
-			const float4 ent = lk_ring_load(seq & (HFDL_LK_RING - 1));
+			const float4 ent = lk_ring_load(seq & (HFDL_LK_RING - 1), tagw >> 31);
 			tagw = __float_as_uint(ent.w);
 			const int k = (int)(tagw & 0xFFFFFu);
 			const bool more = (tagw >> 20) & 1u;
@@ -841,7 +872,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			if(HFDL_UNLIKELY(reset_pending) && !more) {
 				// symsync_crcf_reset happened while processing the outputs of input sample k: outputs of that sample that
 				// were already produced kept their (old-state) value; the timing warp restarts with sample k+1
-				gen = (gen + 1) % 127;                  // 127 is never used: the ring is initialised with all-ones tags
+				gen = (gen + 1) % 127;
 				__syncwarp();
 				if(lane == 0) { lk_reset_k = k; lk_reset_seq = seq; __threadfence_block(); lk_reset_gen = gen; }
 				reset_pending = false;
