@@ -188,7 +188,7 @@ __device__ __forceinline__ cf costas_rotate(DemodState &S, float re, float im) {
 
 // ---- shared memory of one channel CTA (file scope: every access is a direct shared-window address) ----------
 __shared__ float4 lk_ring[HFDL_LK_RING];        // output ring data: {sym.re, sym.im, AGC level, info}
-__shared__ unsigned lk_tags[HFDL_LK_RING];      // output ring validity tags
+__shared__ __align__(8) unsigned lk_tags[HFDL_LK_RING];      // output ring validity tags (read as aligned pairs)
 __shared__ float lk_lvl[HFDL_LK_BR];            // AGC level ring (1/g after the sample's update)
 __shared__ cf lk_psk[4][8];
 __shared__ cf lk_train[16];
