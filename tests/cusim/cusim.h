@@ -44,7 +44,7 @@ static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r; r.x = a; r.y =
 #define __host__
 #define __forceinline__ inline
 #define __noinline__
-#define __align__(n) alignas(n)
+#define __align__(n) __attribute__((aligned(n)))
 #define __launch_bounds__(...)
 #define __restrict__ __restrict
 #define __constant__ static
