@@ -242,12 +242,22 @@ def main():
     truth_set = set(truth)
     stream_pos = [0]
 
+    # shared spectrum: the capture of rank 0 is broadcast (NCCL over NVLink) into one of three slab buffers per step;
+    # only the broadcast's stream is waited for, so the frontend's batch pipeline keeps running underneath (a buffer
+    # is reused three steps later, when process_device() has already collected the batch that read it)
+    slabs = [d_slab] + ([torch.empty_like(d_slab), torch.empty_like(d_slab)] if shared else [])
+    step_no = [0]
+
     def step_device():
+        buf = slabs[step_no[0] % len(slabs)]
         if shared:
-            dist.broadcast(d_slab, src=0)
-            torch.cuda.synchronize()
-        fe.process_device(d_slab.data_ptr(), nsamp, stream_pos[0], nblocks)
+            if rank == 0 and buf is not d_slab:
+                buf.copy_(d_slab, non_blocking=True)
+            dist.broadcast(buf, src=0)
+            torch.cuda.current_stream().synchronize()
+        fe.process_device(buf.data_ptr(), nsamp, stream_pos[0], nblocks)
         stream_pos[0] += nsamp
+        step_no[0] += 1
 
     def count(pdus):
         good = sum(1 for q in pdus if q.crc_good)
