@@ -98,11 +98,22 @@ __device__ __forceinline__ int tile_idx(int row, int col, int lgT) {
 	return (row << lgT) + ((col ^ row ^ (row >> 4)) & mask);
 }
 
+__device__ __forceinline__ cf cmul_w8(cf v) {       // v * W_8^1 = v * (1 - i) / sqrt(2)
+	const float c = 0.70710678118654752f;
+	return make_float2(c * (v.x + v.y), c * (v.y - v.x));
+}
+__device__ __forceinline__ cf cmul_w83(cf v) {      // v * W_8^3 = v * (-1 - i) / sqrt(2)
+	const float c = 0.70710678118654752f;
+	return make_float2(c * (v.y - v.x), -c * (v.x + v.y));
+}
+__device__ __forceinline__ cf cmul_mi(cf v) { return make_float2(v.y, -v.x); }      // v * (-i)
+
 __device__ __forceinline__ void smem_fft_dif(cf *s, int lgL, int lgT, const cf *__restrict__ tw) {
 	const int L = 1 << lgL, nf = 1 << lgT;
 	const int tid = threadIdx.x, nth = blockDim.x;
 	int st = lgL;                       // current sub-transform size is 1 << st
-	if(lgL & 1) {                       // odd log2: one radix-2 stage of size L first
+	const int rem = lgL % 3;            // radix-8 register steps; the 1 or 2 left-over bits go first
+	if(rem == 1) {                      // one radix-2 stage of size L
 		const int h = L >> 1;
 		const int items = nf * h;
 		for(int w = tid; w < items; w += nth) {
@@ -114,9 +125,8 @@ __device__ __forceinline__ void smem_fft_dif(cf *s, int lgL, int lgT, const cf *
 			*p1 = cmul(w1, csub(x0, x1));
 		}
 		__syncthreads();
-		st--;
-	}
-	for(; st >= 2; st -= 2) {           // sizes 4h = 1<<st
+		st -= 1;
+	} else if(rem == 2) {               // one radix-2^2 stage of size L = 4h
 		const int lgh = st - 2, h = 1 << lgh;
 		const int items = nf * (L >> 2);
 		for(int w = tid; w < items; w += nth) {
@@ -138,6 +148,39 @@ __device__ __forceinline__ void smem_fft_dif(cf *s, int lgL, int lgT, const cf *
 			*p1 = cmul(wb, csub(a0, a1));
 			*p2 = cadd(a2, a3);
 			*p3 = cmul(wb, csub(a2, a3));
+		}
+		__syncthreads();
+		st -= 2;
+	}
+	// Radix-8 steps: a work item takes the 8 elements i0 + j*m (m = size/8) of one sub-transform into registers,
+	// runs the three radix-2 DIF stages there (outputs in bit-reversed order: register j holds bin brev3(j)),
+	// applies the twiddle W_size^(b*brev3(j)) and stores back in place.  One shared-memory round trip per 3 stages.
+	for(; st >= 3; st -= 3) {
+		const int lgm = st - 3, m = 1 << lgm;
+		const int items = nf * (L >> 3);
+		const int tws = HFDL_TWN >> st;
+		for(int w = tid; w < items; w += nth) {
+			const int f = w & (nf - 1), q = w >> lgT;
+			const int b = q & (m - 1);
+			const int i0 = ((q >> lgm) << st) + b;
+			cf x[8];
+#pragma unroll
+			for(int j = 0; j < 8; j++) x[j] = s[tile_idx(i0 + (j << lgm), f, lgT)];
+			const cf u0 = cadd(x[0], x[4]), u1 = cadd(x[1], x[5]), u2 = cadd(x[2], x[6]), u3 = cadd(x[3], x[7]);
+			const cf v0 = csub(x[0], x[4]), v1 = cmul_w8(csub(x[1], x[5])), v2 = cmul_mi(csub(x[2], x[6])), v3 = cmul_w83(csub(x[3], x[7]));
+			const cf p0 = cadd(u0, u2), p1 = cadd(u1, u3), p2 = csub(u0, u2), p3 = cmul_mi(csub(u1, u3));
+			const cf q0 = cadd(v0, v2), q1 = cadd(v1, v3), q2 = csub(v0, v2), q3 = cmul_mi(csub(v1, v3));
+			cf y[8];
+			y[0] = cadd(p0, p1); y[1] = csub(p0, p1); y[2] = cadd(p2, p3); y[3] = csub(p2, p3);      // bins 0 4 2 6
+			y[4] = cadd(q0, q1); y[5] = csub(q0, q1); y[6] = cadd(q2, q3); y[7] = csub(q2, q3);      // bins 1 5 3 7
+			if(lgm > 0) {
+				const int bt = b * tws;
+				y[1] = cmul(__ldg(&tw[4 * bt]), y[1]); y[2] = cmul(__ldg(&tw[2 * bt]), y[2]); y[3] = cmul(__ldg(&tw[6 * bt]), y[3]);
+				y[4] = cmul(__ldg(&tw[bt]), y[4]); y[5] = cmul(__ldg(&tw[5 * bt]), y[5]); y[6] = cmul(__ldg(&tw[3 * bt]), y[6]);
+				y[7] = cmul(__ldg(&tw[7 * bt]), y[7]);
+			}
+#pragma unroll
+			for(int j = 0; j < 8; j++) s[tile_idx(i0 + (j << lgm), f, lgT)] = y[j];
 		}
 		__syncthreads();
 	}

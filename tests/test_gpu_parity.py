@@ -66,6 +66,13 @@ def test_frontend_cfg2_8ch_all_modes(lib):
     assert K.case_frontend(lib, sr, freqs, list(range(8)), 5.8, batch=16, seed=11) == 8
 
 
+def test_frontend_three_pass_fft_plan(lib):
+    # 8 Msps: N = 2^20 -> the three-pass forward FFT plan (as at BASELINE configs 3-5) under the whole demodulator
+    sr = 8000000
+    freqs = [K.CF - 3100000, K.CF + 40000, K.CF + 2900000]
+    assert K.case_frontend(lib, sr, freqs, [1, 3, 0], 2.9, batch=5, seed=17) == 3
+
+
 def test_frontend_ragged_push_and_batch_size_invariance(lib):
     n1 = K.case_frontend(lib, 250000, [10063000, 9952000, 10101000], [3, 0, 5], 5.6, batch=3, ragged=True, seed=5)
     n2 = K.case_frontend(lib, 250000, [10063000, 9952000, 10101000], [3, 0, 5], 5.6, batch=64, seed=5)
