@@ -192,7 +192,18 @@ __shared__ __align__(8) unsigned lk_tags[HFDL_LK_RING];      // output ring vali
 __shared__ float lk_lvl[HFDL_LK_BR];            // AGC level ring (1/g after the sample's update)
 __shared__ cf lk_psk[4][8];
 __shared__ cf lk_train[16];
-__shared__ volatile int lk_loaded, lk_tail, lk_tail_k, lk_end_seq, lk_done;
+__shared__ volatile int lk_loaded, lk_end_seq, lk_done;
+__shared__ __align__(8) volatile int lk_tailv[2];      // {sequence number, input-sample index} the demodulator warp has passed
+#define lk_tail lk_tailv[0]
+#define lk_tail_k lk_tailv[1]
+__device__ __forceinline__ void lk_tail_publish(int seq, int k) {      // one 8-byte store on the hot path
+#ifdef HFDL_CUSIM
+	lk_tailv[0] = seq; lk_tailv[1] = k;
+#else
+	const unsigned sa = (unsigned)__cvta_generic_to_shared(const_cast<int *>(lk_tailv));
+	asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(seq), "r"(k) : "memory");
+#endif
+}
 __shared__ volatile int lk_reset_gen, lk_reset_k, lk_reset_seq, lk_ack_gen;
 
 // Output-ring accessors; all accesses are volatile (the other warp changes the ring behind the compiler's back).
@@ -337,8 +348,11 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			qa = __shfl_xor_sync(0xffffffffu, q.x, 8); qb = __shfl_xor_sync(0xffffffffu, q.y, 8);
 			xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
 		}
-		const float phi0 = costas_wrap_fwd(S.c_phi + S.c_dphi);
-		float phi1 = costas_wrap_fwd(phi0 + S.c_dphi);
+		float phi0 = S.c_phi + S.c_dphi, phi1 = phi0 + S.c_dphi;
+		if(HFDL_UNLIKELY(fmaxf(fabsf(phi0), fabsf(phi1)) > 3.1415925f)) {      // a wrap is due (rare): the exact sequence of hfdl.c:256-265
+			phi0 = costas_wrap_fwd(phi0);
+			phi1 = costas_wrap_fwd(phi0 + S.c_dphi);
+		}
 		if(!LMS) {
 			HFDL_ORDER2(qa, phi1);
 			q.x += qa; q.y += qb;
@@ -368,7 +382,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			const cf a = conj_mul(E.w13, r0), b = conj_mul(E.w14, r1);
 			s = make_float2((P.x + a.x) + b.x, (P.y + a.y) + b.y);
 		}
-		S.eq_count += 2;
+		if(LMS) S.eq_count += 2;                   // (frozen-weight runs: counters are advanced by `done` after the loop)
 		const bool is13 = (l16 == 13), is14 = (l16 == 14);
 		seq += 2;
 		done++;
@@ -409,7 +423,6 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 		err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));
 		S.c_phi += 0.1f * err;
 		S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
-		symcnt++;
 		stop = last;
 		if(MODE == RUN_BITS) {
 			bacc = (bacc << 1) | ((bits ^ S.bitmask) & 1u);
@@ -447,18 +460,19 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			}
 			if(HFDL_UNLIKELY(fabsf(S.c_dphi) > 0.25f)) stop = true;      // Costas blow-up: the generic path resets the loops
 		}
-		if(MODE != RUN_A1) {
-			S.signal_level += lvl1;                   // in-frame: the SUM of the AGC levels (the mean is taken at the frame end)
-			S.frame_symbol_cnt += 1.0f;
-		}
+		if(MODE != RUN_A1) S.signal_level += lvl1;    // in-frame: the SUM of the AGC levels (the mean is taken at the frame end)
 		k_prev = k1;
-		S.symsync_out_idx += 2;
-		if(lane == 0) { lk_tail = seq; lk_tail_k = k_prev; }
+		if(lane == 0) lk_tail_publish(seq, k_prev);
 		if(stop | !HFDL_PAIR_VALID()) break;
 	  }
 		if(stop) break;
 	}
 #undef HFDL_PAIR_VALID
+	// per-symbol counters of the run
+	symcnt += (unsigned)done;
+	S.symsync_out_idx += 2u * (unsigned)done;
+	if(!LMS) S.eq_count += 2 * done;
+	if(MODE != RUN_A1) S.frame_symbol_cnt += (float)done;     // exact: whole numbers far below 2^24
 	if(!LMS && done > 0) {             // the |x|^2 bookkeeping of eqlms_cccf_push was skipped: rebuild it from the window
 		E.x2 = E.x.x * E.x.x + E.x.y * E.x.y;
 		float t = l16 < HFDL_EQ_LEN ? E.x2 : 0.f;
