@@ -548,7 +548,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaMemset(fe->d_cap_cnt, 0, sizeof(int) * 2));
 	fe->tmp_len = std::max((long long)N, (long long)B * fe->out_per_block + 64);
 	CKD(cudaMalloc((void **)&fe->d_tmp, sizeof(cf) * (size_t)fe->tmp_len));
-	if(getenv("HFDL_B200_DEBUG")) { CKD(cudaMalloc((void **)&fe->d_dbg, sizeof(long long) * 12 * (size_t)C)); CKD(cudaMemset(fe->d_dbg, 0, sizeof(long long) * 12 * (size_t)C)); }
+	if(getenv("HFDL_B200_DEBUG")) { CKD(cudaMalloc((void **)&fe->d_dbg, sizeof(long long) * 32 * (size_t)C)); CKD(cudaMemset(fe->d_dbg, 0, sizeof(long long) * 32 * (size_t)C)); }
 	CKD(cudaEventCreate(&fe->ev0));
 	CKD(cudaEventCreate(&fe->ev1));
 	if(compute_tapslices(fe)) { hfdl_b200_destroy(fe); return -1; }
@@ -711,13 +711,16 @@ int32_t hfdl_b200_channel_stats(hfdl_b200_frontend_t *fe, int32_t channel, int32
 void hfdl_b200_print_summary(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
 	if(fe->d_dbg) {
-		std::vector<long long> v((size_t)fe->C * 12);
+		std::vector<long long> v((size_t)fe->C * 32);
 		drain(fe);
 		cudaMemcpy(v.data(), fe->d_dbg, sizeof(long long) * v.size(), cudaMemcpyDeviceToHost);
 		for(int c = 0; c < fe->C && c < 4; c++) {
-			const long long *q = &v[(size_t)c * 12];
+			const long long *q = &v[(size_t)c * 32];
 			fprintf(stderr, "loop_kernel ch%d cycles: timing warp %lld (blocked %lld; polls: ring full %lld, loader %lld; outputs %lld, of them generic %lld; fast-loop entries %lld, left at loader limit %lld, at ring limit %lld)  demod warp %lld (waiting %lld)\n",
 				c, q[0], q[1], q[4], q[5], q[6], q[8], q[7], q[9], q[10], q[2], q[3]);
+			const char *mn[8] = { "bits", "train", "-", "skip", "A1", "data-bpsk", "data-psk4", "data-psk8" };
+			for(int m = 0; m < 8; m++) if(q[12 + 2 * m + 1] > 0)
+				fprintf(stderr, "    demod run %-9s: %lld symbols, %.0f cycles/symbol (waiting excluded)\n", mn[m], q[12 + 2 * m + 1], (double)q[12 + 2 * m] / (double)q[12 + 2 * m + 1]);
 		}
 	}
 	long long t[4] = { 0, 0, 0, 0 };

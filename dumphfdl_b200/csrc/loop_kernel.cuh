@@ -300,7 +300,7 @@ enum { RUN_BITS = 0, RUN_TRAIN = 1, RUN_DATA = 2, RUN_SKIP = 3, RUN_A1 = 4 };
 template <int MODE, int ARITY>
 __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k_prev, const int gen, const int nsym,
 		cf *dsym, const int lane, unsigned &symcnt, long long *p_twait, const bool cap, cf *cap_eq, int &cap_n, const int cap_max,
-		const float *lvl, const unsigned *A_bits) {
+		const float *lvl, const unsigned *A_bits, float &last_lvl, unsigned &last_info) {
 	const int l16 = lane & 15;
 	int done = 0;
 	unsigned bacc = 0; int nacc = 0;             // RUN_BITS: bits collected since the last merge into S.bits
@@ -376,6 +376,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 		}
 		const float lvl1 = e1.z;
 		const int k1 = (int)(__float_as_uint(e1.w) & 0xFFFFFu);
+		last_lvl = lvl1; last_info = __float_as_uint(e1.w);
 		// ---- eqlms_cccf_push x2 + execute: the 13 older taps are already summed in P
 		cf s;
 		{
@@ -485,6 +486,22 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 	}
 	if(MODE != RUN_A1) S.symbols_wanted -= done;
 	return done;
+}
+
+// diagnostics wrapper (HFDL_B200_DEBUG): cycles and symbols per run mode, slots 12.. of the per-channel counters
+template <int MODE, int ARITY>
+__device__ __forceinline__ int demod_run_timed(long long *dbg, int c, DemodState &S, EqL &E, int &seq, int &k_prev, const int gen, const int nsym,
+		cf *dsym, const int lane, unsigned &symcnt, long long *p_twait, const bool cap, cf *cap_eq, int &cap_n, const int cap_max,
+		const float *lvl, const unsigned *A_bits, float &last_lvl, unsigned &last_info) {
+	if(!dbg) return demod_run<MODE, ARITY>(S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, p_twait, cap, cap_eq, cap_n, cap_max, lvl, A_bits, last_lvl, last_info);
+	const long long t0 = hfdl_clock(), w0 = *p_twait;
+	const int did = demod_run<MODE, ARITY>(S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, p_twait, cap, cap_eq, cap_n, cap_max, lvl, A_bits, last_lvl, last_info);
+	if(lane == 0) {
+		const int slot = 12 + 2 * (MODE == RUN_DATA ? 4 + ARITY : MODE);      // BITS 0, TRAIN 1, SKIP 3, A1 4, DATA arity 1..3 -> 5..7
+		dbg[c * 32 + slot] += (hfdl_clock() - t0) - (*p_twait - w0);
+		dbg[c * 32 + slot + 1] += did;
+	}
+	return did;
 }
 
 // loop_kernel: grid = C, block = 96 threads (warp 0 demodulator, warp 1 timing, warp 2 loader), dynamic smem = bank ring.
@@ -644,9 +661,9 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		}
 #undef HFDL_SS_TED
 		if(a.dbg_cycles && lane == 0) {
-			a.dbg_cycles[c * 12 + 0] += hfdl_clock() - t_begin; a.dbg_cycles[c * 12 + 1] += t_wait;
-			a.dbg_cycles[c * 12 + 4] += n_full; a.dbg_cycles[c * 12 + 5] += n_starved; a.dbg_cycles[c * 12 + 6] += seq;
-			a.dbg_cycles[c * 12 + 7] += n_fast; a.dbg_cycles[c * 12 + 8] += n_gen_out; a.dbg_cycles[c * 12 + 9] += n_exit_k; a.dbg_cycles[c * 12 + 10] += n_exit_seq;
+			a.dbg_cycles[c * 32 + 0] += hfdl_clock() - t_begin; a.dbg_cycles[c * 32 + 1] += t_wait;
+			a.dbg_cycles[c * 32 + 4] += n_full; a.dbg_cycles[c * 32 + 5] += n_starved; a.dbg_cycles[c * 32 + 6] += seq;
+			a.dbg_cycles[c * 32 + 7] += n_fast; a.dbg_cycles[c * 32 + 8] += n_gen_out; a.dbg_cycles[c * 32 + 9] += n_exit_k; a.dbg_cycles[c * 32 + 10] += n_exit_seq;
 		}
 		// timing-loop state after the last input sample of the batch (kn may lie beyond it: undo the skipped samples)
 		__syncwarp();
@@ -679,17 +696,137 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 #define HFDL_NF_TICK(sidx) do { if(S.fr_state == HF_A1) { if((++S.nf_clk & 0xFFu) == 0xFFu) \
 			S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[sidx]) + 1e-6f; } } while(0)     /* hfdl.c:700-706 */
 		int seq = (int)(S.symsync_out_idx & 1u), k_prev = -1, gen = 0;     // same start as the timing warp (pair alignment)
+		float last_lvl = 0.f; unsigned last_info = 0u;                     // AGC level / info word of the last output a run consumed
 		bool reset_pending = false;
 		long long t_begin = hfdl_clock(), t_wait = 0;
+		// symsync_crcf_reset happened while processing the outputs of input sample k: outputs of that sample that were
+		// already produced kept their (old-state) value; the timing warp restarts with sample k+1
+		auto post_reset = [&](int k) {
+			gen = (gen + 1) % 127;
+			__syncwarp();
+			if(lane == 0) { lk_reset_k = k; lk_reset_seq = seq; __threadfence_block(); lk_reset_gen = gen; }
+			reset_pending = false;
+		};
+		// framer FSM, entered at the symbol on which the symbols_wanted countdown expires (hfdl.c:779-891); k / level:
+		// input-sample index and AGC level of that symbol's last output
+		auto framer_event = [&](const int k, const float level) {
+			switch(S.fr_state) {
+			case HF_A1: {
+				float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+				if(fabsf(corr) > 0.36f) {
+					S.st_a1++;
+					S.bitmask = corr > 0.f ? 0u : ~0u;
+					S.signal_level = level;
+					S.frame_symbol_cnt = 1.0f;
+					S.symbols_wanted = HFDL_A_LEN;
+					S.search_retries = 0;
+					S.fr_state = HF_A2;
+				}
+				break; }
+			case HF_A2: {
+				float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
+				if(fabsf(corr) > 0.3f) {
+					S.a2_sample_cnt = cnt_base + (unsigned long long)k;
+					S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
+					S.st_a2++;
+					S.symbols_wanted = 127;
+					S.search_retries = 0;
+					S.fr_state = HF_M1;
+				} else if(++S.search_retries >= 3) {
+					framer_reset(S, T, E, l16); reset_pending = true;
+				}
+				break; }
+			case HF_M1: {
+				float max_corr = 0.f; int max_idx = -1;
+				for(int idx = 0; idx < 8; idx++) {
+					float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
+					if(corr > max_corr) { max_corr = corr; max_idx = idx; }
+				}
+				if(max_corr > 0.3f) {
+					S.st_m1++;
+					S.data_segment_cnt = T.mode_segments[max_idx];
+					S.data_arity = T.mode_arity[max_idx];
+					S.M1 = max_idx;
+					S.symbols_wanted = 15;
+					S.search_retries = 0;
+					S.fr_state = HF_M2_SKIP;
+					S.s_state = HS_SKIP;
+				} else {
+					framer_reset(S, T, E, l16); reset_pending = true;
+				}
+				break; }
+			case HF_M2_SKIP:
+				S.training_n = 0;
+				S.symbols_wanted = HFDL_T_LEN;
+				S.eq_train_seq_cnt = 9;
+				S.fr_state = HF_EQ_TRAIN;
+				S.s_state = HS_EMIT_SYMBOLS;
+				break;
+			case HF_EQ_TRAIN: {
+				__syncwarp();
+				unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
+#pragma unroll
+				for(int j = 0; j < HFDL_T_LEN; j++) {
+					unsigned bit = (lk_train[j].x > 0.f) ? 0u : 1u;
+					bit ^= (S.bitmask & 1u);
+					tseq = (tseq << 1) | bit;
+				}
+				__syncwarp();
+				S.train_bits_total += HFDL_T_LEN;
+				S.train_bits_bad += __popc(0x9AFu ^ tseq);
+				S.training_n = 0;
+				if(S.eq_train_seq_cnt > 1) {
+					S.eq_train_seq_cnt--;
+					S.symbols_wanted = HFDL_T_LEN;
+					S.T_idx = 0;
+				} else if(S.data_segment_cnt > 0) {
+					S.symbols_wanted = 15;
+					S.fr_state = HF_DATA_1;
+					S.cur_arity = S.data_arity;
+					S.cur_buf = 1;
+				} else {                                 // end of frame: hand the symbols to fec_kernel
+					int q = 0;
+					if(lane == 0) q = atomicAdd(a.nframes, 1);
+					q = __shfl_sync(0xffffffffu, q, 0);
+					if(q < a.max_frames && lane == 0) {
+						FrameRec fr;
+						fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
+						fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level / S.frame_symbol_cnt; fr.noise_floor = S.noise_floor;
+						fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = cnt_base + (unsigned long long)k;
+						fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
+						a.frames[q] = fr;
+					}
+					S.st_frames++;
+					S.slot = (S.slot + 1) % a.nslots;
+					dsym = a.datasym + ((long long)c * a.nslots + S.slot) * HFDL_DATA_SYMS_MAX;
+					framer_reset(S, T, E, l16); reset_pending = true;
+					symcnt = 0;
+				}
+				break; }
+			case HF_DATA_1:
+				S.symbols_wanted = 15;
+				S.fr_state = HF_DATA_2;
+				break;
+			case HF_DATA_2:
+				S.data_segment_cnt--;
+				S.cur_arity = 1;
+				S.cur_buf = 0;
+				S.fr_state = HF_EQ_TRAIN;
+				S.eq_train_seq_cnt = 1;
+				S.symbols_wanted = HFDL_T_LEN;
+				S.T_idx = 0;
+				break;
+			}
+		};
 		for(;;) {
-			// fast path: a run of whole symbols up to (not including) the symbol of the next framer event
-#define HFDL_RUN(MODE, AR) demod_run<MODE, AR>(S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, &t_wait, cap, a.cap_eq, cap_n_eq, a.cap_max, lvl, A_bits)
+			// fast path: a run of whole symbols up to AND including the symbol of the next framer event
+#define HFDL_RUN(MODE, AR) demod_run_timed<MODE, AR>(a.dbg_cycles, c, S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, &t_wait, cap, a.cap_eq, cap_n_eq, a.cap_max, lvl, A_bits, last_lvl, last_info)
 			if(S.fr_state == HF_A1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode < 2
 					&& fabsf(S.c_dphi) <= 0.25f && symcnt + 1u < 13u * HFDL_SINGLE_SLOT_FRAME_LEN) {
 				const int nsym = (int)(13u * HFDL_SINGLE_SLOT_FRAME_LEN - 1u - symcnt);     // the symbol of the 13-frame timeout goes the generic way
 				if(HFDL_RUN(RUN_A1, 1) > 0) continue;
-			} else if(S.fr_state > HF_A1 && S.symbols_wanted > 1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode < 2) {
-				const int nsym = S.symbols_wanted - 1;
+			} else if(S.fr_state > HF_A1 && S.symbols_wanted >= 1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode < 2) {
+				const int nsym = S.symbols_wanted;
 				int did;
 				if(S.s_state == HS_EMIT_BITS) did = HFDL_RUN(RUN_BITS, 1);
 				else if(S.s_state == HS_SKIP) did = HFDL_RUN(RUN_SKIP, 1);
@@ -697,7 +834,14 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				else if(S.cur_arity == 1) did = HFDL_RUN(RUN_DATA, 1);
 				else if(S.cur_arity == 2) did = HFDL_RUN(RUN_DATA, 2);
 				else did = HFDL_RUN(RUN_DATA, 3);
-				if(did > 0) continue;
+				if(did > 0) {
+					if(S.symbols_wanted == 0) {            // the countdown expired on the run's last symbol: framer event
+						S.symbols_wanted = 1;
+						framer_event(k_prev, last_lvl);
+						if(HFDL_UNLIKELY(reset_pending) && !((last_info >> 20) & 1u)) post_reset(k_prev);
+					}
+					continue;
+				}
 			}
 #undef HFDL_RUN
 			// ---- generic path: one symsync output
@@ -771,128 +915,15 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				}
 				if(S.symbols_wanted > 1) { S.symbols_wanted--; break; }
 
-				switch(S.fr_state) {
-				case HF_A1: {
-					float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
-					if(fabsf(corr) > 0.36f) {
-						S.st_a1++;
-						S.bitmask = corr > 0.f ? 0u : ~0u;
-						S.signal_level = level;
-						S.frame_symbol_cnt = 1.0f;
-						S.symbols_wanted = HFDL_A_LEN;
-						S.search_retries = 0;
-						S.fr_state = HF_A2;
-					}
-					break; }
-				case HF_A2: {
-					float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
-					if(fabsf(corr) > 0.3f) {
-						S.a2_sample_cnt = cnt_base + (unsigned long long)k;
-						S.freq_err_hz = (float)((double)(S.c_dphi * 1800.0f) / (2.0 * M_PI));   // hfdl.c:812
-						S.st_a2++;
-						S.symbols_wanted = 127;
-						S.search_retries = 0;
-						S.fr_state = HF_M1;
-					} else if(++S.search_retries >= 3) {
-						framer_reset(S, T, E, l16); reset_pending = true;
-					}
-					break; }
-				case HF_M1: {
-					float max_corr = 0.f; int max_idx = -1;
-					for(int idx = 0; idx < 8; idx++) {
-						float corr = fabsf(2.0f * (float)bits_corr(T.M1_bits[idx], S.bits) / 127.0f - 1.0f);
-						if(corr > max_corr) { max_corr = corr; max_idx = idx; }
-					}
-					if(max_corr > 0.3f) {
-						S.st_m1++;
-						S.data_segment_cnt = T.mode_segments[max_idx];
-						S.data_arity = T.mode_arity[max_idx];
-						S.M1 = max_idx;
-						S.symbols_wanted = 15;
-						S.search_retries = 0;
-						S.fr_state = HF_M2_SKIP;
-						S.s_state = HS_SKIP;
-					} else {
-						framer_reset(S, T, E, l16); reset_pending = true;
-					}
-					break; }
-				case HF_M2_SKIP:
-					S.training_n = 0;
-					S.symbols_wanted = HFDL_T_LEN;
-					S.eq_train_seq_cnt = 9;
-					S.fr_state = HF_EQ_TRAIN;
-					S.s_state = HS_EMIT_SYMBOLS;
-					break;
-				case HF_EQ_TRAIN: {
-					__syncwarp();
-					unsigned tseq = 0;                       // compute_train_bit_error_cnt hfdl.c:952-966
-#pragma unroll
-					for(int j = 0; j < HFDL_T_LEN; j++) {
-						unsigned bit = (lk_train[j].x > 0.f) ? 0u : 1u;
-						bit ^= (S.bitmask & 1u);
-						tseq = (tseq << 1) | bit;
-					}
-					__syncwarp();
-					S.train_bits_total += HFDL_T_LEN;
-					S.train_bits_bad += __popc(0x9AFu ^ tseq);
-					S.training_n = 0;
-					if(S.eq_train_seq_cnt > 1) {
-						S.eq_train_seq_cnt--;
-						S.symbols_wanted = HFDL_T_LEN;
-						S.T_idx = 0;
-					} else if(S.data_segment_cnt > 0) {
-						S.symbols_wanted = 15;
-						S.fr_state = HF_DATA_1;
-						S.cur_arity = S.data_arity;
-						S.cur_buf = 1;
-					} else {                                 // end of frame: hand the symbols to fec_kernel
-						int q = 0;
-						if(lane == 0) q = atomicAdd(a.nframes, 1);
-						q = __shfl_sync(0xffffffffu, q, 0);
-						if(q < a.max_frames && lane == 0) {
-							FrameRec fr;
-							fr.channel = c; fr.slot = S.slot; fr.M1 = S.M1; fr.bitmask = S.bitmask;
-							fr.freq_err_hz = S.freq_err_hz; fr.signal_level = S.signal_level / S.frame_symbol_cnt; fr.noise_floor = S.noise_floor;
-							fr.sample_cnt_a2 = S.a2_sample_cnt; fr.sample_cnt_end = cnt_base + (unsigned long long)k;
-							fr.train_bits_bad = S.train_bits_bad; fr.train_bits_total = S.train_bits_total;
-							a.frames[q] = fr;
-						}
-						S.st_frames++;
-						S.slot = (S.slot + 1) % a.nslots;
-						dsym = a.datasym + ((long long)c * a.nslots + S.slot) * HFDL_DATA_SYMS_MAX;
-						framer_reset(S, T, E, l16); reset_pending = true;
-						symcnt = 0;
-					}
-					break; }
-				case HF_DATA_1:
-					S.symbols_wanted = 15;
-					S.fr_state = HF_DATA_2;
-					break;
-				case HF_DATA_2:
-					S.data_segment_cnt--;
-					S.cur_arity = 1;
-					S.cur_buf = 0;
-					S.fr_state = HF_EQ_TRAIN;
-					S.eq_train_seq_cnt = 1;
-					S.symbols_wanted = HFDL_T_LEN;
-					S.T_idx = 0;
-					break;
-				}
+				framer_event(k, level);
 			} while(0);
 			S.symsync_out_idx++;
 			seq++;
 			__syncwarp();
 			if(lane == 0) { lk_tail = seq; lk_tail_k = k; }
-			if(HFDL_UNLIKELY(reset_pending) && !more) {
-				// symsync_crcf_reset happened while processing the outputs of input sample k: outputs of that sample that
-				// were already produced kept their (old-state) value; the timing warp restarts with sample k+1
-				gen = (gen + 1) % 127;
-				__syncwarp();
-				if(lane == 0) { lk_reset_k = k; lk_reset_seq = seq; __threadfence_block(); lk_reset_gen = gen; }
-				reset_pending = false;
-			}
+			if(HFDL_UNLIKELY(reset_pending) && !more) post_reset(k);
 		}
-		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 12 + 2] += hfdl_clock() - t_begin; a.dbg_cycles[c * 12 + 3] += t_wait; }
+		if(a.dbg_cycles && lane == 0) { a.dbg_cycles[c * 32 + 2] += hfdl_clock() - t_begin; a.dbg_cycles[c * 32 + 3] += t_wait; }
 		for(int sidx = k_prev + 1; sidx < N; sidx++) HFDL_NF_TICK(sidx);      // input samples after the last output
 #undef HFDL_NF_TICK
 		S.sample_cnt = cnt_base + (unsigned long long)N;
