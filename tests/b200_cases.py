@@ -116,7 +116,7 @@ def compare_pdus(got, ref, truth=None, subset=False):
         assert sorted((f, d) for f, _, d, _, _, _ in g) == sorted(truth)
 
 
-def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_floats=True, ragged=False, seed=3):
+def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_floats=True, ragged=False, seed=3, ragged_seed=9):
     x, truth = make_capture(sr, freqs, modes, dur, seed=seed)
     if sfmt == A.SFMT_CS16:
         raw = np.zeros(2 * x.size, np.int16)
@@ -132,7 +132,7 @@ def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_f
     g = fe.geom
     assert (g.fft_size, g.input_size, g.fft_inv_size, g.scrap) == (p.ddc.fft_size, p.ddc.input_size, p.ddc.fft_inv_size, p.ddc.scrap)
     if ragged:
-        rng = np.random.default_rng(9)
+        rng = np.random.default_rng(ragged_seed)
         per = raw.size // x.size
         i = 0
         while i < x.size:

@@ -79,6 +79,14 @@ def test_frontend_ragged_push_and_batch_size_invariance(lib):
     assert n1 == n2 == 3
 
 
+def test_ring_protocol_under_small_launches_repeated(lib):
+    """Many short loop_kernel launches (the consumer warp runs right behind the producer warp after every launch
+    start): the continuous equaliser checkpoint must stay within tolerance on every repetition.  This is the case
+    that exposed torn 16-byte ring entries."""
+    for rs in (1, 2, 3, 4):
+        assert K.case_frontend(lib, 250000, [10063000, 9952000, 10101000], [3, 0, 5], 5.6, batch=3, ragged=True, seed=5, ragged_seed=rs) == 3
+
+
 def test_pipeline_many_batches_subranges(lib):
     # 5 batches of 32 blocks (n_out > 16384: the 8 sub-range schedule) with frames in every batch, whole capture in one push
     plan = [(0, 1, 0.3), (0, 3, 3.3), (0, 0, 6.3), (0, 2, 9.3), (0, 1, 12.3), (0, 3, 15.3),
