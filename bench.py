@@ -12,6 +12,10 @@ multichannel capture (frames placed cyclically so the stream is seamless across 
   value : I/Q Msamples/s ingested with the slab resident in HBM (device timed, CUDA events)
   e2e   : same metric through hfdl_b200_push_samples() with pinned HOST buffers: H2D of the slab and D2H of the
           PDUs inside the timed region
+The synthetic capture and the list of transmitted PDUs come from the HFDL transmitter that lives with the test
+infrastructure (oracle/orc_tx.c via tests/orclib.py): input generation and the exactness check of the decoded PDUs,
+outside every timed region and never on the product path.  The only oracle code that is TIMED is the cpu_baseline /
+--impl reference leg.
 N>1: one process per GPU (torchrun); every GPU owns an independent 2 Msps capture and its 8 channels end to end
 (weak scaling, no data-path collective); --shared-spectrum broadcasts one capture over NCCL instead and shards
 the channels."""
@@ -94,7 +98,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -164,7 +168,7 @@ def cpu_reference(O, x, isz, nblocks_avail, target_s=12.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--shared-spectrum", action="store_true")
