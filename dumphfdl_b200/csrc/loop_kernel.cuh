@@ -102,7 +102,7 @@ __device__ __forceinline__ void eq_step(DemodState &S, EqL &E, float d, cf s, cf
 	bool run = true;
 	if(!S.eq_buf_full) { if(S.eq_count < HFDL_EQ_LEN) run = false; else S.eq_buf_full = 1; }
 	if(run) {
-		const float inv = 1.0f / S.eq_x2_sum;
+		const float inv = __fdividef(1.0f, S.eq_x2_sum);
 		const cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);
 		const cf u = cmul(t, E.x), u13 = cmul(t, x13), u14 = cmul(t, x14);
 		E.w.x += u.x; E.w.y += u.y;
@@ -316,8 +316,16 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 	float drop0 = 0.f, drop1 = 0.f, x2s = 0.f;
 	if(LMS) { drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16); drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16); x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16); }
 	cf xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
-	cf P;
-	{ cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f); P = half_warp_sum(p); }
+	cf P, pl;                                     // pl (LMS runs): P after the shuffle stages 8 and 4; stages 2 and 1 follow at
+	{	                                          // the top of the next symbol, overlapped with its Costas step
+		cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f);
+		p.x += __shfl_xor_sync(0xffffffffu, p.x, 8); p.y += __shfl_xor_sync(0xffffffffu, p.y, 8);
+		p.x += __shfl_xor_sync(0xffffffffu, p.x, 4); p.y += __shfl_xor_sync(0xffffffffu, p.y, 4);
+		pl = p;
+		p.x += __shfl_xor_sync(0xffffffffu, p.x, 2); p.y += __shfl_xor_sync(0xffffffffu, p.y, 2);
+		p.x += __shfl_xor_sync(0xffffffffu, p.x, 1); p.y += __shfl_xor_sync(0xffffffffu, p.y, 1);
+		P = p;
+	}
 	cf wq = make_float2(__shfl_up_sync(0xffffffffu, E.w.x, 4, 16), __shfl_up_sync(0xffffffffu, E.w.y, 4, 16));
 	if(l16 < 4 || l16 >= HFDL_EQ_LEN) wq = make_float2(0.f, 0.f);
 	const cf w11 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 11, 16), __shfl_sync(0xffffffffu, E.w.y, 11, 16));
@@ -348,15 +356,18 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			qa = __shfl_xor_sync(0xffffffffu, q.x, 8); qb = __shfl_xor_sync(0xffffffffu, q.y, 8);
 			xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
 		}
-		float phi0 = S.c_phi + S.c_dphi, phi1 = phi0 + S.c_dphi;
-		if(HFDL_UNLIKELY(fmaxf(fabsf(phi0), fabsf(phi1)) > 3.1415925f)) {      // a wrap is due (rare): the exact sequence of hfdl.c:256-265
-			phi0 = costas_wrap_fwd(phi0);
-			phi1 = costas_wrap_fwd(phi0 + S.c_dphi);
-		}
+		if(LMS) { qa = __shfl_xor_sync(0xffffffffu, pl.x, 2); qb = __shfl_xor_sync(0xffffffffu, pl.y, 2); }
+		// branch-free wrap: a rarely-taken branch here splits the block and costs more than the eight selects
+		const float phi0 = costas_wrap_fwd(S.c_phi + S.c_dphi);
+		float phi1 = costas_wrap_fwd(phi0 + S.c_dphi);
 		if(!LMS) {
 			HFDL_ORDER2(qa, phi1);
 			q.x += qa; q.y += qb;
 			qa = __shfl_xor_sync(0xffffffffu, q.x, 4); qb = __shfl_xor_sync(0xffffffffu, q.y, 4);
+		} else {
+			HFDL_ORDER2(qa, phi1);
+			pl.x += qa; pl.y += qb;
+			qa = __shfl_xor_sync(0xffffffffu, pl.x, 1); qb = __shfl_xor_sync(0xffffffffu, pl.y, 1);
 		}
 		float sn0, cs0, sn1, cs1;
 		hfdl_sincos_fast(phi0, &sn0, &cs0);
@@ -373,6 +384,9 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			HFDL_ORDER2(qa, r1.x);
 			q.x += qa; q.y += qb;
 			qa = __shfl_xor_sync(0xffffffffu, q.x, 1); qb = __shfl_xor_sync(0xffffffffu, q.y, 1);
+		} else {
+			HFDL_ORDER2(qa, r1.x);
+			P = make_float2(pl.x + qa, pl.y + qb);
 		}
 		const float lvl1 = e1.z;
 		const int k1 = (int)(__float_as_uint(e1.w) & 0xFFFFFu);
@@ -405,7 +419,8 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16); drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16);
 			xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
 			x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
-			{ cf p = conj_mul(E.w, xs); if(l16 >= 13) p = make_float2(0.f, 0.f); P = half_warp_sum(p); }
+			pl = conj_mul(E.w, xs); if(l16 >= 13) pl = make_float2(0.f, 0.f);
+			qa = __shfl_xor_sync(0xffffffffu, pl.x, 8); qb = __shfl_xor_sync(0xffffffffu, pl.y, 8);
 		} else {
 			HFDL_ORDER2(qa, s.x);
 			const cf Qn = make_float2(q.x + qa, q.y + qb);
@@ -424,6 +439,11 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 		err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));
 		S.c_phi += 0.1f * err;
 		S.c_dphi += (0.047f * 0.1f * 0.1f) * err;
+		if(LMS) {                                  // stages 8 -> 4 of the next P behind the decision chain
+			HFDL_ORDER2(qa, S.c_phi);
+			pl.x += qa; pl.y += qb;
+			qa = __shfl_xor_sync(0xffffffffu, pl.x, 4); qb = __shfl_xor_sync(0xffffffffu, pl.y, 4);
+		}
 		stop = last;
 		if(MODE == RUN_BITS) {
 			bacc = (bacc << 1) | ((bits ^ S.bitmask) & 1u);
@@ -462,6 +482,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			if(HFDL_UNLIKELY(fabsf(S.c_dphi) > 0.25f)) stop = true;      // Costas blow-up: the generic path resets the loops
 		}
 		if(MODE != RUN_A1) S.signal_level += lvl1;    // in-frame: the SUM of the AGC levels (the mean is taken at the frame end)
+		if(LMS) { HFDL_ORDER2(qa, S.signal_level); pl.x += qa; pl.y += qb; }
 		k_prev = k1;
 		if(lane == 0) lk_tail_publish(seq, k_prev);
 		if(stop | !HFDL_PAIR_VALID()) break;
