@@ -15,7 +15,11 @@
 #include "common.cuh"
 
 #define HFDL_TWN 4096          // twiddle table size: exp(-2*pi*i*k/4096); sub-FFT lengths <= 4096
+#ifdef HFDL_FFT_THREADS_OVERRIDE
+#define HFDL_FFT_THREADS HFDL_FFT_THREADS_OVERRIDE
+#else
 #define HFDL_FFT_THREADS 256
+#endif
 #define HFDL_RS_TAPS 14        // resamp_crcf sub-filter length (2*m, m = 7)
 #define HFDL_RS_NPFB 256
 #define HFDL_RS_HIST (HFDL_RS_TAPS - 1)

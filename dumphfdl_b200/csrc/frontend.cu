@@ -39,8 +39,11 @@ FftPlan make_plan(int N) {
 }
 
 int tile_for(int lgL) {          // columns (or rows) per CTA: keep the tile <= 64 KiB
-	int t = 8192 >> lgL;
-	if(t > 16) t = 16;
+#ifndef HFDL_FFT_TILE_CAP
+#define HFDL_FFT_TILE_CAP 16
+#endif
+	int t = (512 * HFDL_FFT_TILE_CAP) >> lgL;
+	if(t > HFDL_FFT_TILE_CAP) t = HFDL_FFT_TILE_CAP;
 	if(t < 1) t = 1;
 	return t;
 }
