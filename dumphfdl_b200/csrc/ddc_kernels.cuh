@@ -323,6 +323,159 @@ __global__ void __launch_bounds__(HFDL_FFT_THREADS) fft_row_pass(RowPassArgs a) 
 	}
 }
 
+// ======================================================================================
+// Register-resident passes (L = 32 * B, B = 2..16; every plan of BASELINE configs 1-5).
+// A pass transforms one axis of length L for a tile of T = 8192 / L columns (or rows).  Each of the 256 threads
+//   1. loads 32 elements x[a] = X[a*B + b] of one (column, b) straight from global memory into registers,
+//   2. runs a 32-point DIF there (five radix-2 stages with compile-time twiddles), applies W_L^(b*ka) and stores the
+//      32 results to shared memory,                                                    -- the only __syncthreads --
+//   3. reads B elements (fixed ka) back, runs the B-point DIF in registers and writes natural bin k = ka + 32*kb
+//      to global memory (column pass: times the inter-pass twiddle W^(k * column)).
+// Versus the shared-memory passes above: one barrier instead of four, ~2.5x fewer instructions per element, 32
+// independent global loads in flight per thread.
+// ======================================================================================
+__host__ __device__ __forceinline__ constexpr float w32_cos(int m) {      // cos(2*pi*m/32), m = 0..15
+	return m == 0 ? 1.0f : m == 1 ? 0.98078528040323043f : m == 2 ? 0.92387953251128674f : m == 3 ? 0.83146961230254524f :
+	       m == 4 ? 0.70710678118654752f : m == 5 ? 0.55557023301960218f : m == 6 ? 0.38268343236508978f : m == 7 ? 0.19509032201612825f :
+	       m == 8 ? 0.0f : m == 9 ? -0.19509032201612825f : m == 10 ? -0.38268343236508978f : m == 11 ? -0.55557023301960218f :
+	       m == 12 ? -0.70710678118654752f : m == 13 ? -0.83146961230254524f : m == 14 ? -0.92387953251128674f : -0.98078528040323043f;
+}
+__host__ __device__ __forceinline__ constexpr float w32_sin(int m) { return m <= 8 ? w32_cos(8 - m) : w32_cos(m - 8); }      // sin(2*pi*m/32)
+__host__ __device__ __forceinline__ constexpr int brev_ct(int x, int bits) {
+	int r = 0;
+	for(int i = 0; i < bits; i++) r |= ((x >> i) & 1) << (bits - 1 - i);
+	return r;
+}
+// d * W_32^m, W_32 = exp(-2*pi*i/32); m is a compile-time constant after unrolling
+__device__ __forceinline__ cf cmul_w32(cf d, int m) {
+	if(m == 0) return d;
+	if(m == 8) return make_float2(d.y, -d.x);
+	const float c = w32_cos(m), sn = w32_sin(m);
+	return make_float2(d.x * c + d.y * sn, d.y * c - d.x * sn);
+}
+// in-place DIF of N = 2..32 points in registers; x[j] ends up holding bin brev(j)
+template <int N> __device__ __forceinline__ void fft_reg_dif(cf *x) {
+#pragma unroll
+	for(int S = N; S >= 2; S >>= 1) {
+		const int h = S >> 1;
+#pragma unroll
+		for(int g = 0; g < N; g += S) {
+#pragma unroll
+			for(int j = 0; j < h; j++) {
+				const cf a = x[g + j], b = x[g + j + h];
+				x[g + j] = cadd(a, b);
+				x[g + j + h] = cmul_w32(csub(a, b), j * (32 / S));
+			}
+		}
+	}
+}
+
+template <int LGB>
+__global__ void __launch_bounds__(256) fft_col_pass_reg(ColPassArgs a) {
+	HFDL_DYN_SMEM(cf, s);
+	constexpr int B = 1 << LGB, L = 32 << LGB, LGT = 8 - LGB, T = 1 << LGT;
+	const int tiles_per_row = a.inner >> LGT;
+	const int o = blockIdx.x / tiles_per_row;
+	const int n0 = (blockIdx.x - o * tiles_per_row) << LGT;
+	const int blk = blockIdx.y;
+	const long long base = (long long)o * L * a.inner + n0;
+	cf *wk = a.work + (long long)blk * a.N + base;
+	const int tid = threadIdx.x;
+	{
+		const int t = tid & (T - 1), b = tid >> LGT;
+		cf x[32];
+		if(a.first) {
+			const WindowView wv = window_view(a.src, blk);
+#pragma unroll
+			for(int i = 0; i < 32; i++) x[i] = load_window(wv, base + (long long)(i * B + b) * a.inner + t);
+		} else {
+#pragma unroll
+			for(int i = 0; i < 32; i++) x[i] = wk[(long long)(i * B + b) * a.inner + t];
+		}
+		fft_reg_dif<32>(x);
+		const int bt = b * (HFDL_TWN / L);
+#pragma unroll
+		for(int j = 0; j < 32; j++) {
+			const int ka = brev_ct(j, 5);
+			cf v = x[j];
+			if(ka != 0) v = cmul(__ldg(&a.tw[ka * bt]), v);
+			s[((ka << LGB) + b) * T + t] = v;
+		}
+	}
+	__syncthreads();
+	const float inv_np = 1.0f / (float)((long long)L * a.inner);      // power of two: exact
+#pragma unroll
+	for(int i = 0; i < 32 / B; i++) {
+		const int p = tid + 256 * i;
+		const int t = p & (T - 1), ka = p >> LGT;
+		cf z[B];
+#pragma unroll
+		for(int b = 0; b < B; b++) z[b] = s[((ka << LGB) + b) * T + t];
+		fft_reg_dif<B>(z);
+		// inter-pass twiddle W^(k*c), k = ka + 32*kb, c = column: base W^(ka*c) times powers of W^(32*c)
+		const float c = (float)(n0 + t);
+		float sn, cs;
+		sincospif(-2.0f * (float)ka * c * inv_np, &sn, &cs);
+		const cf wbase = make_float2(cs, sn);
+		sincospif(-2.0f * 32.0f * c * inv_np, &sn, &cs);
+		cf pw[B];
+		pw[0] = make_float2(1.f, 0.f);
+		if(B > 1) pw[1] = make_float2(cs, sn);
+#pragma unroll
+		for(int q = 2; q < B; q++) pw[q] = cmul(pw[q >> 1], pw[q - (q >> 1)]);
+#pragma unroll
+		for(int j = 0; j < B; j++) {
+			const int kb = brev_ct(j, LGB);
+			const cf w = cmul(wbase, pw[kb]);
+			wk[(long long)(ka + 32 * kb) * a.inner + t] = cmul(z[j], w);
+		}
+	}
+}
+
+// last pass: T contiguous rows of length L per CTA; shared-memory rows are padded to 33 elements
+template <int LGB>
+__global__ void __launch_bounds__(256) fft_row_pass_reg(RowPassArgs a) {
+	HFDL_DYN_SMEM(cf, s);
+	constexpr int B = 1 << LGB, L = 32 << LGB, LGT = 8 - LGB;
+	const int blk = blockIdx.y;
+	const long long row0 = (long long)blockIdx.x << LGT;
+	cf *wk = a.work + (long long)blk * a.N + row0 * L;
+	const int tid = threadIdx.x;
+	{
+		const int b = tid & (B - 1), r = tid >> LGB;
+		cf x[32];
+		if(a.first) {
+			const WindowView wv = window_view(a.src, blk);
+#pragma unroll
+			for(int i = 0; i < 32; i++) x[i] = load_window(wv, (row0 + r) * L + i * B + b);
+		} else {
+#pragma unroll
+			for(int i = 0; i < 32; i++) x[i] = wk[(long long)r * L + i * B + b];
+		}
+		fft_reg_dif<32>(x);
+		const int bt = b * (HFDL_TWN / L);
+#pragma unroll
+		for(int j = 0; j < 32; j++) {
+			const int ka = brev_ct(j, 5);
+			cf v = x[j];
+			if(ka != 0) v = cmul(__ldg(&a.tw[ka * bt]), v);
+			s[((r << LGB) + b) * 33 + ka] = v;
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for(int i = 0; i < 32 / B; i++) {
+		const int p = tid + 256 * i;
+		const int ka = p & 31, r = p >> 5;
+		cf z[B];
+#pragma unroll
+		for(int b = 0; b < B; b++) z[b] = s[((r << LGB) + b) * 33 + ka];
+		fft_reg_dif<B>(z);
+#pragma unroll
+		for(int j = 0; j < B; j++) wk[(long long)r * L + ka + 32 * brev_ct(j, LGB)] = z[j];
+	}
+}
+
 // Debug / init helper: gather natural-order bins [k0, k0+n) of window b out of the scrambled layout.
 __global__ void fft_gather_bins(const cf *work, FftPlan pl, int b, int k0, int n, cf *out) {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;

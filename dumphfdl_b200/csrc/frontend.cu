@@ -60,6 +60,14 @@ struct FftEngine {
 		CK(cudaMalloc((void **)&d_tw, sizeof(cf) * HFDL_TWN));
 		CK(cudaMemcpy(d_tw, tw.data(), sizeof(cf) * HFDL_TWN, cudaMemcpyHostToDevice));
 		CK(cudaFuncSetAttribute(fft_col_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_col_pass_reg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_col_pass_reg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_col_pass_reg<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_col_pass_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_row_pass_reg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_row_pass_reg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_row_pass_reg<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_row_pass_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(fft_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(chan_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 		CK(cudaFuncSetAttribute(fec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_FEC_SMEM));
@@ -156,9 +164,21 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 			a.T = tile_for(lgL); if(a.T > inner) a.T = inner;
 			a.lgT = hfdl_ilog2(a.T);
 			a.first = (p == 0);
-			dim3 grid((unsigned)(outer * (inner / a.T)), (unsigned)nb);
-			size_t smem = sizeof(cf) * (size_t)L * a.T;
-			HFDL_LAUNCH(fft_col_pass, grid, dim3(HFDL_FFT_THREADS), smem, st, a);
+			const int lgb = lgL - 5;              // register-resident pass: L = 32 * B, tile of 8192 / L columns
+			if(!getenv("HFDL_B200_SMEM_FFT") && lgb >= 1 && lgb <= 4 && (256 >> lgb) <= inner) {
+				dim3 grid((unsigned)(outer * (inner / (256 >> lgb))), (unsigned)nb);
+				const size_t smem = sizeof(cf) * 8192;
+				switch(lgb) {
+				case 1: HFDL_LAUNCH(fft_col_pass_reg<1>, grid, dim3(256), smem, st, a); break;
+				case 2: HFDL_LAUNCH(fft_col_pass_reg<2>, grid, dim3(256), smem, st, a); break;
+				case 3: HFDL_LAUNCH(fft_col_pass_reg<3>, grid, dim3(256), smem, st, a); break;
+				default: HFDL_LAUNCH(fft_col_pass_reg<4>, grid, dim3(256), smem, st, a); break;
+				}
+			} else {
+				dim3 grid((unsigned)(outer * (inner / a.T)), (unsigned)nb);
+				size_t smem = sizeof(cf) * (size_t)L * a.T;
+				HFDL_LAUNCH(fft_col_pass, grid, dim3(HFDL_FFT_THREADS), smem, st, a);
+			}
 		} else {
 			RowPassArgs a;
 			a.src = src; a.work = work; a.tw = eng.d_tw; a.N = pl.N; a.lgL = lgL; a.R = tile_for(lgL);
@@ -166,9 +186,21 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 			if(a.R > rows) a.R = rows;
 			a.lgR = hfdl_ilog2(a.R);
 			a.first = (p == 0);
-			dim3 grid((unsigned)(rows / a.R), (unsigned)nb);
-			size_t smem = sizeof(cf) * (size_t)L * a.R;
-			HFDL_LAUNCH(fft_row_pass, grid, dim3(HFDL_FFT_THREADS), smem, st, a);
+			const int lgb = lgL - 5;
+			if(!getenv("HFDL_B200_SMEM_FFT") && lgb >= 1 && lgb <= 4 && (256 >> lgb) <= rows) {
+				dim3 grid((unsigned)(rows / (256 >> lgb)), (unsigned)nb);
+				const size_t smem = sizeof(cf) * 256 * 33;
+				switch(lgb) {
+				case 1: HFDL_LAUNCH(fft_row_pass_reg<1>, grid, dim3(256), smem, st, a); break;
+				case 2: HFDL_LAUNCH(fft_row_pass_reg<2>, grid, dim3(256), smem, st, a); break;
+				case 3: HFDL_LAUNCH(fft_row_pass_reg<3>, grid, dim3(256), smem, st, a); break;
+				default: HFDL_LAUNCH(fft_row_pass_reg<4>, grid, dim3(256), smem, st, a); break;
+				}
+			} else {
+				dim3 grid((unsigned)(rows / a.R), (unsigned)nb);
+				size_t smem = sizeof(cf) * (size_t)L * a.R;
+				HFDL_LAUNCH(fft_row_pass, grid, dim3(HFDL_FFT_THREADS), smem, st, a);
+			}
 		}
 		prof_end(fe, pr);
 		if(fe) fe->launches++;
