@@ -334,6 +334,9 @@ __global__ void __launch_bounds__(HFDL_FFT_THREADS) fft_row_pass(RowPassArgs a) 
 // Versus the shared-memory passes above: one barrier instead of four, ~2.5x fewer instructions per element, 32
 // independent global loads in flight per thread.
 // ======================================================================================
+#ifndef HFDL_FFT_REG_MINB
+#define HFDL_FFT_REG_MINB 3          // CTAs per SM the register-resident passes are compiled for
+#endif
 __host__ __device__ __forceinline__ constexpr float w32_cos(int m) {      // cos(2*pi*m/32), m = 0..15
 	return m == 0 ? 1.0f : m == 1 ? 0.98078528040323043f : m == 2 ? 0.92387953251128674f : m == 3 ? 0.83146961230254524f :
 	       m == 4 ? 0.70710678118654752f : m == 5 ? 0.55557023301960218f : m == 6 ? 0.38268343236508978f : m == 7 ? 0.19509032201612825f :
@@ -371,7 +374,7 @@ template <int N> __device__ __forceinline__ void fft_reg_dif(cf *x) {
 }
 
 template <int LGB>
-__global__ void __launch_bounds__(256) fft_col_pass_reg(ColPassArgs a) {
+__global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_col_pass_reg(ColPassArgs a) {
 	HFDL_DYN_SMEM(cf, s);
 	constexpr int B = 1 << LGB, L = 32 << LGB, LGT = 8 - LGB, T = 1 << LGT;
 	const int tiles_per_row = a.inner >> LGT;
@@ -434,7 +437,7 @@ __global__ void __launch_bounds__(256) fft_col_pass_reg(ColPassArgs a) {
 
 // last pass: T contiguous rows of length L per CTA; shared-memory rows are padded to 33 elements
 template <int LGB>
-__global__ void __launch_bounds__(256) fft_row_pass_reg(RowPassArgs a) {
+__global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_row_pass_reg(RowPassArgs a) {
 	HFDL_DYN_SMEM(cf, s);
 	constexpr int B = 1 << LGB, L = 32 << LGB, LGT = 8 - LGB;
 	const int blk = blockIdx.y;
