@@ -20,10 +20,10 @@ lines = ["# ncu --set full --clock-control none captures, round 1 (B200, cfg2 be
          "| kernel | grid x block | regs | duration ms | dram read MB | dram write MB | dram % of peak | sm throughput % | warps active % | warp instr |",
          "|---|---|---|---|---|---|---|---|---|---|"]
 traffic = {}
-name_map = {'loop_kernel': 'loop', 'fft_col_pass': 'fft_pass1', 'fft_row_pass': 'fft_pass2', 'chan_extract': 'chan_extract', 'agc_kernel': 'agc',
+name_map = {'loop_kernel': 'loop', 'fft_col_pass': 'fft_pass1', 'fft_row_pass': 'fft_pass2', 'fft_col_pass_reg': 'fft_pass1', 'fft_row_pass_reg': 'fft_pass2', 'chan_extract': 'chan_extract', 'agc_kernel': 'agc',
             'bank_kernel': 'bank', 'fec_kernel': 'fec', 'resamp_kernel': 'resamp'}
 for d in rows:
-    kn = d['Kernel Name'].split('(')[0]
+    kn = d['Kernel Name'].split('(')[0].replace('void ', '').strip()
     if kn in seen:
         continue
     seen[kn] = 1
@@ -34,7 +34,7 @@ for d in rows:
         kn, d['launch__grid_size'], d['launch__block_size'], d['launch__registers_per_thread'], ms, rd / 1e6, wr / 1e6,
         float(d['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']), float(d['sm__throughput.avg.pct_of_peak_sustained_elapsed']),
         float(d['sm__warps_active.avg.pct_of_peak_sustained_active']), float(d.get('smsp__inst_executed.sum', 0))))
-    traffic[name_map.get(kn, kn)] = int(rd + wr)
+    traffic[name_map.get(kn.split('<')[0], kn)] = int(rd + wr)
 open(os.path.join(HERE, 'r01_ncu_summary.md'), 'w').write("\n".join(lines) + "\n")
 json.dump({"workload": "cfg2", "blocks_per_step": 88, "channels": 8,
            "source": "ncu --set full --clock-control none, one launch per kernel class inside `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` "
