@@ -847,7 +847,10 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				const int nsym = (int)(13u * HFDL_SINGLE_SLOT_FRAME_LEN - 1u - symcnt);     // the symbol of the 13-frame timeout goes the generic way
 				if(HFDL_RUN(RUN_A1, 1) > 0) continue;
 			} else if(S.fr_state > HF_A1 && S.symbols_wanted >= 1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode < 2) {
-				const int nsym = S.symbols_wanted;
+				// DATA_1's framer event only re-arms the countdown for DATA_2 (hfdl.c:878-881): both halves of a data
+				// segment go through one run
+				const bool fuse = (S.fr_state == HF_DATA_1);
+				const int nsym = S.symbols_wanted + (fuse ? 15 : 0);
 				int did;
 				if(S.s_state == HS_EMIT_BITS) did = HFDL_RUN(RUN_BITS, 1);
 				else if(S.s_state == HS_SKIP) did = HFDL_RUN(RUN_SKIP, 1);
@@ -856,6 +859,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				else if(S.cur_arity == 2) did = HFDL_RUN(RUN_DATA, 2);
 				else did = HFDL_RUN(RUN_DATA, 3);
 				if(did > 0) {
+					if(fuse && S.symbols_wanted <= 0) { S.fr_state = HF_DATA_2; S.symbols_wanted += 15; }      // the DATA_1 event, in passing
 					if(S.symbols_wanted == 0) {            // the countdown expired on the run's last symbol: framer event
 						S.symbols_wanted = 1;
 						framer_event(k_prev, last_lvl);
