@@ -488,6 +488,8 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	if(!(fe->resamp_rate >= 0.5f && fe->resamp_rate <= 1.0f)) { fprintf(stderr, "hfdl_b200_create: resampling rate %f outside [0.5,1]\n", fe->resamp_rate); delete fe; return -1; }
 	fe->plan = make_plan(g.fft_size);
 	fe->Bmax = cfg->max_blocks_per_batch > 0 ? cfg->max_blocks_per_batch : std::max(1, std::min(64, (int)((256ll << 20) / ((long long)g.fft_size * 8))));
+	// loop_kernel addresses the samples of one launch (a sub-range = 1/8 batch) with 20 bits (HFDL_LK_MAXN)
+	if((long long)fe->Bmax * fe->out_per_block > (1ll << 22)) fe->Bmax = (int)((1ll << 22) / fe->out_per_block);
 	if(cfg->capture_channel >= fe->C) fe->cfg.capture_channel = -1;
 	if(fe->cfg.capture_max < 0) fe->cfg.capture_max = 0;
 
