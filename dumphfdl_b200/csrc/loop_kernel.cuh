@@ -631,31 +631,61 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			__threadfence_block();
 
 			if(S.ss_since_reset >= HFDL_SS_SUB && S.ss_decim_counter == 1u && S.ss_b >= 0) {
-				// ---------------- fast loop: per output, two outputs (one symbol) per iteration ----------------
+				// ---------------- fast loop: two outputs (one symbol) per iteration, straight-line ----------------
+				// A lone warp pays ~20 cycles for every branch it has to resolve, so the pair body has only rarely
+				// taken ones: limit refreshes (once per loader chunk / when the ring is full) and the del < 1 case.
+				// Every lane stores the (identical) ring entry: no lane-0 branch.
 				float tau = S.ss_tau;
 				int k = kn + (S.ss_b >> 4), b = S.ss_b & 15;
 				tau -= (float)(S.ss_b >> 4);
 				int odd = 0;                     // 0: the next output is the non-TED one of the pair
 				int rare = 0;
-				while(k < k_lim && seq < seq_lim) {
-					const cf *row = s_bank + (k & (HFDL_LK_BR - 1)) * 32;
-					const cf mf = row[b];
-					const float level = lk_lvl[k & (HFDL_LK_BR - 1)];
-					if(odd) HFDL_SS_TED(mf, row, b);
-					tau += S.ss_del;
-					const int bi = hfdl_round_pos(tau * (float)HFDL_SS_NPFB);
-					if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_info(bi < HFDL_SS_NPFB, k), lk_tag_hi(my_gen, seq));
-					seq++;
-					odd ^= 1;
-					if(HFDL_UNLIKELY(bi < HFDL_SS_NPFB)) { b = bi; rare = 1; break; }     // del < 1: another output of the same sample
-					const int m = bi >> 4;
-					k += m; tau -= (float)m; b = bi & 15;
+				int k_lim2 = k_lim, seq_lim2 = seq_lim;
+				const int seq_in = seq;
+				for(;;) {
+					if(HFDL_UNLIKELY(k + 4 > k_lim2)) {       // both outputs of the pair lie within 3 samples (del ~ 1.5)
+						k_lim2 = HFDL_UNI(lk_loaded); __threadfence_block();
+						if(k + 4 > k_lim2) break;
+					}
+					if(HFDL_UNLIKELY(seq + 2 > seq_lim2)) {
+						seq_lim2 = HFDL_UNI(lk_tail) + HFDL_LK_RING - 2;
+						if(seq + 2 > seq_lim2) break;
+					}
+					{	// first output of the symbol: no timing-error detector
+						const cf *row = s_bank + (k & (HFDL_LK_BR - 1)) * 32;
+						const cf mf = row[b];
+						const float level = lk_lvl[k & (HFDL_LK_BR - 1)];
+						tau += S.ss_del;
+						const int bi = hfdl_round_pos(tau * (float)HFDL_SS_NPFB);
+						lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_info(bi < HFDL_SS_NPFB, k), lk_tag_hi(my_gen, seq));
+						if(HFDL_UNLIKELY(bi < HFDL_SS_NPFB)) { seq++; odd = 1; b = bi; rare = 1; break; }     // del < 1: another output of the same sample
+						const int m = bi >> 4;
+						k += m; tau -= (float)m; b = bi & 15;
+						if(HFDL_UNLIKELY(k >= k_lim2)) { seq++; odd = 1; break; }      // (cannot happen while del < 3)
+					}
+					{	// second output: timing-error detector + loop filter
+						const cf *row = s_bank + (k & (HFDL_LK_BR - 1)) * 32;
+						const cf mf = row[b];
+						const float level = lk_lvl[k & (HFDL_LK_BR - 1)];
+						HFDL_SS_TED(mf, row, b);
+						tau += S.ss_del;
+						const int bi = hfdl_round_pos(tau * (float)HFDL_SS_NPFB);
+						lk_ring_store((seq + 1) & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_info(bi < HFDL_SS_NPFB, k), lk_tag_hi(my_gen, seq + 1));
+						seq += 2;
+						if(HFDL_UNLIKELY(bi < HFDL_SS_NPFB)) { b = bi; rare = 1; break; }
+						const int m = bi >> 4;
+						k += m; tau -= (float)m; b = bi & 15;
+					}
 				}
-				n_fast++; if(k >= k_lim) n_exit_k++; else if(seq >= seq_lim) n_exit_seq++;
+				const int k_lim_seen = k_lim2;
+				n_fast++; if(k + 4 > k_lim_seen) n_exit_k++; else n_exit_seq++;
 				// back to the generic representation
 				S.ss_tau = tau; S.ss_b = b; S.ss_decim_counter = odd ? 2u : 1u;
 				kn = k; mid = rare != 0;
-				continue;
+				if(seq != seq_in || rare) continue;
+				// no pair fitted: the ring is full or the loader is less than 4 samples ahead -> poll again; only the last
+				// samples of the batch (everything is loaded) go through the generic stepping below
+				if(seq + 2 > seq_lim2 || k_lim2 < N || kn >= N) { if(kn < N) HFDL_SPIN_PAUSE(); continue; }
 			}
 			// ---------------- generic stepping (after a reset, odd alignment, rare cases) ----------------
 			if(!mid) {
