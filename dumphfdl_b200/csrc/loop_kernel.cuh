@@ -412,9 +412,15 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			E.x.x = is13 ? r0.x : xs.x; E.x.y = is13 ? r0.y : xs.y; E.x2 = is13 ? x2a : x2s;
 			E.x.x = is14 ? r1.x : E.x.x; E.x.y = is14 ? r1.y : E.x.y; E.x2 = is14 ? x2b : E.x2;
 			// eqlms_cccf_step(T_seq[bitmask&1][T_idx], s)  hfdl.c:730-733
-			float d = ((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) & 1u) ? -1.0f : 1.0f;
-			if(S.bitmask & 1u) d = -d;
-			eq_step(S, E, d, s, r0, r1);
+			const float d = (((0x9AFu >> (HFDL_T_LEN - 1 - S.T_idx)) ^ S.bitmask) & 1u) ? -1.0f : 1.0f;
+			{	// eqlms_cccf_step with a full window (the dispatcher guarantees S.eq_buf_full)
+				const float inv = __fdividef(1.0f, S.eq_x2_sum);
+				const cf t = make_float2(0.1f * (d - s.x) * inv, 0.1f * s.y * inv);
+				const cf u = cmul(t, E.x), u13 = cmul(t, r0), u14 = cmul(t, r1);
+				E.w.x += u.x; E.w.y += u.y;
+				E.w13.x += u13.x; E.w13.y += u13.y;
+				E.w14.x += u14.x; E.w14.y += u14.y;
+			}
 			S.T_idx++;
 			// prefetch the next symbol's entries, pre-shift the window for it and reduce its 13 known taps
 			lk_pair_load(seq, e0, e1, t0, t1);
@@ -462,18 +468,23 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			if(room & (lane == 0)) dsym[S.data_n] = s;
 			S.data_n += room ? 1 : 0;
 		} else if(MODE == RUN_A1) {
-			// noise-floor clock: one tick per input sample (k_prev, k1], update on every 256th (hfdl.c:700-706)
+			// noise-floor clock: one tick per input sample (k_prev, k1], update on every 256th (hfdl.c:700-706); the
+			// number of updates due is floor((clk_after + 1) / 256) - floor((clk_before + 1) / 256), almost always 0
 			const int d = k1 - k_prev;
-			unsigned j = (0xFFu - (S.nf_clk & 0xFFu)) & 0xFFu;
-			if(j == 0u) j = 256u;
-			for(; HFDL_UNLIKELY((int)j <= d); j += 256u)
-				S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[k_prev + (int)j]) + 1e-6f;
-			S.nf_clk += (unsigned)d;
+			const unsigned clk_after = S.nf_clk + (unsigned)d;
+			if(HFDL_UNLIKELY(((clk_after + 1u) >> 8) != ((S.nf_clk + 1u) >> 8))) {
+				unsigned j = (0xFFu - (S.nf_clk & 0xFFu)) & 0xFFu;
+				if(j == 0u) j = 256u;
+				for(; (int)j <= d; j += 256u)
+					S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[k_prev + (int)j]) + 1e-6f;
+			}
+			S.nf_clk = clk_after;
 			bits_push(S.bits, bits ^ S.bitmask);
-			const float corr = 2.0f * (float)bits_corr(A_bits, S.bits) / 127.0f - 1.0f;
-			if(HFDL_UNLIKELY(fabsf(corr) > 0.36f)) {          // A1 found (hfdl.c:779-793)
+			// |2*eq/127 - 1| > 0.36 in float arithmetic  <=>  eq <= 40 or eq >= 87 (all 128 values enumerated)
+			const int eq = bits_corr(A_bits, S.bits);
+			if(HFDL_UNLIKELY((unsigned)(eq - 41) > 45u)) {          // A1 found (hfdl.c:779-793)
 				S.st_a1++;
-				S.bitmask = corr > 0.f ? 0u : ~0u;
+				S.bitmask = eq >= 87 ? 0u : ~0u;
 				S.signal_level = lvl1;
 				S.frame_symbol_cnt = 1.0f;
 				S.symbols_wanted = HFDL_A_LEN;
@@ -886,7 +897,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				int did;
 				if(S.s_state == HS_EMIT_BITS) did = HFDL_RUN(RUN_BITS, 1);
 				else if(S.s_state == HS_SKIP) did = HFDL_RUN(RUN_SKIP, 1);
-				else if(S.cur_buf == 0) did = HFDL_RUN(RUN_TRAIN, 1);
+				else if(S.cur_buf == 0) { if(!S.eq_buf_full) goto generic_path; did = HFDL_RUN(RUN_TRAIN, 1); }
 				else if(S.cur_arity == 1) did = HFDL_RUN(RUN_DATA, 1);
 				else if(S.cur_arity == 2) did = HFDL_RUN(RUN_DATA, 2);
 				else did = HFDL_RUN(RUN_DATA, 3);
@@ -901,6 +912,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				}
 			}
 #undef HFDL_RUN
+		generic_path:
 			// ---- generic path: one symsync output
 			unsigned tagw;
 			bool have = false;
