@@ -27,10 +27,11 @@
 struct FftPlan {
 	int N, lgN, P;
 	int lgL[3];
+	int natural;       // 1: the last pass writes the spectrum out of place in natural bin order (fft_last_pass_nat)
 };
 
 __host__ __device__ __forceinline__ int fft_bin_addr(const FftPlan &pl, int k) {
-	if(pl.P == 1) return k;
+	if(pl.P == 1 || pl.natural) return k;
 	int k1 = k & ((1 << pl.lgL[0]) - 1);
 	int r = k >> pl.lgL[0];
 	if(pl.P == 2) return (k1 << pl.lgL[1]) | r;
@@ -294,6 +295,8 @@ struct RowPassArgs {
 	cf *work;
 	const cf *tw;
 	int N, lgL, R, lgR, first;
+	cf *out;           // fft_last_pass_nat: natural-order spectrum [B][N]
+	int L1, mid;       // fft_last_pass_nat: length of the first axis; product of the middle axes (1 for two-pass plans)
 };
 
 __global__ void __launch_bounds__(HFDL_FFT_THREADS) fft_row_pass(RowPassArgs a) {
@@ -476,6 +479,55 @@ __global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_row_pass_reg(RowPa
 		fft_reg_dif<B>(z);
 #pragma unroll
 		for(int j = 0; j < B; j++) wk[(long long)r * L + ka + 32 * brev_ct(j, LGB)] = z[j];
+	}
+}
+
+// Last pass, out of place, natural bin order.  The T rows of a tile are the rows of T CONSECUTIVE values of the first
+// (fastest natural) digit k1 for one value of the middle digits, so that for every output bin of the row transform
+// the tile's T results are T adjacent natural bins: each row is read as one contiguous run, each result group is
+// written as one contiguous run, and the consumers (chan_extract, tap-slice gather) read plain contiguous slices.
+// Shared memory: element (r, b, ka) at r*(33*B + 1) + 33*b + ka -- both the (b, r)-major writes of phase 1 and the
+// (r, ka)-major reads of phase 2 are bank-conflict free.
+template <int LGB>
+__global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_last_pass_nat(RowPassArgs a) {
+	HFDL_DYN_SMEM(cf, s);
+	constexpr int B = 1 << LGB, L = 32 << LGB, LGT = 8 - LGB, T = 1 << LGT, RS = 33 * B + 1;
+	const int blk = blockIdx.y;
+	const int tiles1 = a.L1 >> LGT;
+	const int kmid = blockIdx.x / tiles1;                     // value of the middle digit(s)
+	const int k10 = (blockIdx.x - kmid * tiles1) << LGT;      // first k1 of the tile
+	const cf *wk = a.work + (long long)blk * a.N;
+	cf *out = a.out + (long long)blk * a.N;
+	const int tid = threadIdx.x;
+	{
+		const int b = tid & (B - 1), r = tid >> LGB;
+		const cf *row = wk + ((long long)(k10 + r) * a.mid + kmid) * L;
+		cf x[32];
+#pragma unroll
+		for(int i = 0; i < 32; i++) x[i] = row[i * B + b];
+		fft_reg_dif<32>(x);
+		const int bt = b * (HFDL_TWN / L);
+#pragma unroll
+		for(int j = 0; j < 32; j++) {
+			const int ka = brev_ct(j, 5);
+			cf v = x[j];
+			if(ka != 0) v = cmul(__ldg(&a.tw[ka * bt]), v);
+			s[r * RS + b * 33 + ka] = v;
+		}
+	}
+	__syncthreads();
+	const long long kstride = (long long)a.L1 * a.mid;          // natural-index stride of the last digit
+#pragma unroll
+	for(int i = 0; i < 32 / B; i++) {
+		const int p = tid + 256 * i;
+		const int r = p & (T - 1), ka = p >> LGT;
+		cf z[B];
+#pragma unroll
+		for(int b = 0; b < B; b++) z[b] = s[r * RS + b * 33 + ka];
+		fft_reg_dif<B>(z);
+		cf *o = out + (k10 + r) + (long long)a.L1 * kmid;
+#pragma unroll
+		for(int j = 0; j < B; j++) o[kstride * (ka + 32 * brev_ct(j, LGB))] = z[j];
 	}
 }
 

@@ -35,6 +35,12 @@ FftPlan make_plan(int N) {
 	if(lg <= 12) { p.P = 1; p.lgL[0] = lg; }
 	else if(lg <= 18) { p.P = 2; p.lgL[0] = lg / 2; p.lgL[1] = lg - p.lgL[0]; }
 	else { p.P = 3; p.lgL[0] = lg / 3; p.lgL[1] = (lg - p.lgL[0]) / 2; p.lgL[2] = lg - p.lgL[0] - p.lgL[1]; }
+	// natural-order, out-of-place last pass (fft_last_pass_nat): needs a register-resident last pass (L = 32*B,
+	// B = 2..16) and at least one tile of 256/B consecutive k1 rows
+	if(p.P >= 2 && !getenv("HFDL_B200_SMEM_FFT")) {
+		const int lgb = p.lgL[p.P - 1] - 5;
+		if(lgb >= 1 && lgb <= 4 && p.lgL[0] >= 8 - lgb) p.natural = 1;
+	}
 	return p;
 }
 
@@ -68,6 +74,10 @@ struct FftEngine {
 		CK(cudaFuncSetAttribute(fft_row_pass_reg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(fft_row_pass_reg<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(fft_row_pass_reg<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_last_pass_nat<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_last_pass_nat<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_last_pass_nat<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+		CK(cudaFuncSetAttribute(fft_last_pass_nat<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(fft_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(chan_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 		CK(cudaFuncSetAttribute(fec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_FEC_SMEM));
@@ -97,7 +107,8 @@ struct hfdl_b200_frontend {
 	int nslots = HFDL_FRAME_SLOTS_MIN;
 	FftEngine fft;
 	// device memory
-	cf *d_work = nullptr; void *d_ring = nullptr; long long ring_len = 0;
+	cf *d_work = nullptr, *d_spec = nullptr;       // FFT workspace (passes in place) / natural-order spectra (plan.natural)
+	void *d_ring = nullptr; long long ring_len = 0;
 	cf *d_tapslice = nullptr; int *d_offsetbin = nullptr; float *d_dsa_rate = nullptr;
 	cf *d_bb = nullptr; long long bb_stride = 0;
 	cf *d_rs[2] = { nullptr, nullptr }; long long rs_stride = 0; float *d_rs_h = nullptr;
@@ -150,7 +161,9 @@ inline void prof_end2(hfdl_b200_frontend *fe, ProfRec &r, cudaStream_t st) {
 }
 
 // forward FFT of nb windows described by src into work (scrambled layout)
-int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, const RawSource &src, cf *work, int nb, cudaStream_t st) {
+// forward FFT of nb windows: passes in place in `work`; when pl.natural the last pass writes the natural-order
+// spectrum to `spec` (else the digit-scrambled spectrum stays in `work`)
+int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, const RawSource &src, cf *work, cf *spec, int nb, cudaStream_t st) {
 	int inner = pl.N;
 	int outer = 1;
 	for(int p = 0; p < pl.P; p++) {
@@ -186,8 +199,19 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 			if(a.R > rows) a.R = rows;
 			a.lgR = hfdl_ilog2(a.R);
 			a.first = (p == 0);
+			a.out = nullptr; a.L1 = 0; a.mid = 0;
 			const int lgb = lgL - 5;
-			if(!getenv("HFDL_B200_SMEM_FFT") && lgb >= 1 && lgb <= 4 && (256 >> lgb) <= rows) {
+			if(pl.natural) {
+				a.out = spec; a.L1 = 1 << pl.lgL[0]; a.mid = pl.P == 3 ? (1 << pl.lgL[1]) : 1;
+				dim3 grid((unsigned)(rows / (256 >> lgb)), (unsigned)nb);
+				const size_t smem = sizeof(cf) * (size_t)(256 >> lgb) * (size_t)(33 * (1 << lgb) + 1);
+				switch(lgb) {
+				case 1: HFDL_LAUNCH(fft_last_pass_nat<1>, grid, dim3(256), smem, st, a); break;
+				case 2: HFDL_LAUNCH(fft_last_pass_nat<2>, grid, dim3(256), smem, st, a); break;
+				case 3: HFDL_LAUNCH(fft_last_pass_nat<3>, grid, dim3(256), smem, st, a); break;
+				default: HFDL_LAUNCH(fft_last_pass_nat<4>, grid, dim3(256), smem, st, a); break;
+				}
+			} else if(!getenv("HFDL_B200_SMEM_FFT") && lgb >= 1 && lgb <= 4 && (256 >> lgb) <= rows) {
 				dim3 grid((unsigned)(rows / (256 >> lgb)), (unsigned)nb);
 				const size_t smem = sizeof(cf) * 256 * 33;
 				switch(lgb) {
@@ -285,11 +309,11 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 	const auto &g = fe->g;
 	hfdl_b200_frontend::Flight &prev = fe->flight[p ^ 1];
 	hfdl_b200_frontend::Flight &cur = fe->flight[p];
-	if(run_fft(fe, fe->fft, fe->plan, src, fe->d_work, nb, st)) return -1;
+	if(run_fft(fe, fe->fft, fe->plan, src, fe->d_work, fe->d_spec, nb, st)) return -1;
 	ProfRec pr;
 	{
 		ChanArgs a;
-		a.work = fe->d_work; a.tapslice = fe->d_tapslice; a.offsetbin = fe->d_offsetbin; a.dsa_rate = fe->d_dsa_rate;
+		a.work = fe->plan.natural ? fe->d_spec : fe->d_work; a.tapslice = fe->d_tapslice; a.offsetbin = fe->d_offsetbin; a.dsa_rate = fe->d_dsa_rate;
 		a.bb = fe->d_bb; a.tw = fe->fft.d_tw; a.pl = fe->plan;
 		a.M = g.fft_inv_size; a.lgM = hfdl_ilog2(g.fft_inv_size); a.scrap = g.scrap; a.post_dec = g.post_decimation;
 		a.out_per_block = fe->out_per_block; a.bb_stride = fe->bb_stride;
@@ -437,9 +461,9 @@ int compute_tapslices(hfdl_b200_frontend *fe) {
 			CK(cudaMemcpyAsync(d_in + (size_t)i * N, taps[(size_t)i].data(), sizeof(cf) * (size_t)g.taps_length, cudaMemcpyHostToDevice, fe->stream));
 		RawSource src;
 		src.base = d_in; src.ring_len = (long long)N * nc; src.pos0 = 0; src.ring_origin = 0; src.block_stride = N; src.sfmt = HFDL_SFMT_CF32;
-		if(run_fft(nullptr, fe->fft, fe->plan, src, fe->d_work, nc, fe->stream)) return -1;
+		if(run_fft(nullptr, fe->fft, fe->plan, src, fe->d_work, fe->d_spec, nc, fe->stream)) return -1;
 		HFDL_LAUNCH(tapslice_gather, dim3((unsigned)((M + 255) / 256), (unsigned)nc), dim3(256), 0, fe->stream,
-			fe->d_work, fe->plan, M, fe->d_offsetbin, c0, fe->d_tapslice);
+			fe->plan.natural ? fe->d_spec : fe->d_work, fe->plan, M, fe->d_offsetbin, c0, fe->d_tapslice);
 		CK(cudaGetLastError());
 		CK(cudaStreamSynchronize(fe->stream));
 	}
@@ -512,6 +536,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	if(fe->fft.init()) { hfdl_b200_destroy(fe); return -1; }
 	const int C = fe->C, N = g.fft_size, M = g.fft_inv_size, B = fe->Bmax;
 	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * B));
+	if(fe->plan.natural) CKD(cudaMalloc((void **)&fe->d_spec, sizeof(cf) * (size_t)N * B));
 	fe->ring_len = (long long)g.overlap_length + (long long)(B + 1) * g.input_size;
 	CKD(cudaMalloc(&fe->d_ring, (size_t)fe->ring_len * fe->bps));
 	CKD(cudaMemset(fe->d_ring, 0, (size_t)fe->ring_len * fe->bps));
@@ -598,7 +623,7 @@ void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
 	cudaStream_t sts[4] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec };
 	for(cudaStream_t q : sts) if(q) cudaStreamSynchronize(q);
-	cudaFree(fe->d_work); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
+	cudaFree(fe->d_work); cudaFree(fe->d_spec); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
 	cudaFree(fe->d_bb); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
 	cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf); cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp); cudaFree(fe->d_dbg);
 	cudaFree(fe->d_agc_state); cudaFree(fe->d_agc); cudaFree(fe->d_mfo); cudaFree(fe->d_lvl); cudaFree(fe->d_bank);
@@ -815,7 +840,7 @@ int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_
 		if(index < 0) index = fe->last_nblocks - 1;       // -1: last block processed
 		if(index < 0 || index >= fe->last_nblocks) return -1;
 		avail = g.fft_size;
-		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((g.fft_size + 255) / 256)), dim3(256), 0, fe->stream, fe->d_work, fe->plan, index, 0, g.fft_size, fe->d_tmp);
+		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((g.fft_size + 255) / 256)), dim3(256), 0, fe->stream, fe->plan.natural ? fe->d_spec : fe->d_work, fe->plan, index, 0, g.fft_size, fe->d_tmp);
 		CK(cudaGetLastError());
 		CK(cudaStreamSynchronize(fe->stream));
 		srcp = fe->d_tmp;
@@ -856,23 +881,24 @@ int32_t hfdl_b200_fft_forward(int32_t device, const void *in, void *outp, int32_
 	FftEngine eng;
 	if(eng.init()) return -1;
 	FftPlan pl = make_plan(n);
-	cf *d_in = nullptr, *d_work = nullptr, *d_out = nullptr;
+	cf *d_in = nullptr, *d_work = nullptr, *d_spec = nullptr, *d_out = nullptr;
 	size_t bytes = sizeof(cf) * (size_t)n * (size_t)batch;
 	CK(cudaMalloc((void **)&d_in, bytes)); CK(cudaMalloc((void **)&d_work, bytes)); CK(cudaMalloc((void **)&d_out, sizeof(cf) * (size_t)n));
+	if(pl.natural) CK(cudaMalloc((void **)&d_spec, bytes));
 	CK(cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice));
 	RawSource src;
 	src.base = d_in; src.ring_len = (long long)n * batch; src.pos0 = 0; src.ring_origin = 0; src.block_stride = n; src.sfmt = HFDL_SFMT_CF32;
 	cudaStream_t st = nullptr;
 	CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-	int rc = run_fft(nullptr, eng, pl, src, d_work, batch, st);
+	int rc = run_fft(nullptr, eng, pl, src, d_work, d_spec, batch, st);
 	for(int b = 0; b < batch && rc == 0; b++) {
-		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, d_work, pl, b, 0, n, d_out);
+		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, pl.natural ? d_spec : d_work, pl, b, 0, n, d_out);
 		if(cudaStreamSynchronize(st) != cudaSuccess) { rc = -1; break; }
 		if(cudaMemcpy((cf *)outp + (size_t)b * n, d_out, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
 	}
 	if(cudaGetLastError() != cudaSuccess) rc = -1;
 	cudaStreamDestroy(st);
-	cudaFree(d_in); cudaFree(d_work); cudaFree(d_out);
+	cudaFree(d_in); cudaFree(d_work); cudaFree(d_spec); cudaFree(d_out);
 	eng.destroy();
 	return rc;
 }
