@@ -269,12 +269,12 @@ def main():
         return good, exact
 
     # ---- value: slab resident in HBM
+    clk = ClockSampler(local)          # started before the warm-up so that nvidia-smi is already sampling when the
+    clk.start()                        # (short) timed region begins; every sample is taken under load
     for _ in range(a.warmup):
         step_device()
     fe.sync()
     fe.pdus()
-    clk = ClockSampler(local)
-    clk.start()
     fe.profile(True)
     l0 = fe.launches()
     barrier()

@@ -20,7 +20,7 @@ lines = ["# ncu --set full --clock-control none captures, round 1 (B200, cfg2 be
          "| kernel | grid x block | regs | duration ms | dram read MB | dram write MB | dram % of peak | sm throughput % | warps active % | warp instr |",
          "|---|---|---|---|---|---|---|---|---|---|"]
 traffic = {}
-name_map = {'loop_kernel': 'loop', 'fft_col_pass': 'fft_pass1', 'fft_row_pass': 'fft_pass2', 'fft_col_pass_reg': 'fft_pass1', 'fft_row_pass_reg': 'fft_pass2', 'chan_extract': 'chan_extract', 'agc_kernel': 'agc',
+name_map = {'loop_kernel': 'loop', 'fft_col_pass': 'fft_pass1', 'fft_row_pass': 'fft_pass2', 'fft_col_pass_reg': 'fft_pass1', 'fft_row_pass_reg': 'fft_pass2', 'fft_last_pass_nat': 'fft_pass2', 'chan_extract': 'chan_extract', 'agc_kernel': 'agc',
             'bank_kernel': 'bank', 'fec_kernel': 'fec', 'resamp_kernel': 'resamp'}
 for d in rows:
     kn = d['Kernel Name'].split('(')[0].replace('void ', '').strip()
