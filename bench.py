@@ -90,18 +90,50 @@ def build_slab(O, seed, nthreads):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every 10 ms
+    (nvidia_ml_py), nvidia-smi -lms as the fallback when NVML cannot be imported."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+
     def __init__(self, gpu):
-        self.rows = []
-        self.p = None
         self.gpu = gpu
+        self.sm, self.mx, self.mask = [], [], 0
+        self.stop_flag = False
+        self.t = None
+        self.p = None
+        self.rows = []
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def poll():
+                while not self.stop_flag:
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        self.mx.append(mx)
+                        try:
+                            self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                        except Exception:
+                            self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                    except Exception:
+                        pass
+                    time.sleep(0.01)
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.t = None
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self.t2 = threading.Thread(target=self._read, daemon=True)
+            self.t2.start()
         except Exception:
             self.p = None
 
@@ -110,6 +142,12 @@ class ClockSampler:
             self.rows.append([s.strip() for s in line.split(",")])
 
     def stop(self):
+        if self.t is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            reasons = [n for n, bit in self.REASONS.items() if self.mask & bit]
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                    "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -121,7 +159,7 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
 def best_threads(O, x, isz, nblocks_avail):
@@ -269,12 +307,12 @@ def main():
         return good, exact
 
     # ---- value: slab resident in HBM
-    clk = ClockSampler(local)          # started before the warm-up so that nvidia-smi is already sampling when the
-    clk.start()                        # (short) timed region begins; every sample is taken under load
     for _ in range(a.warmup):
         step_device()
     fe.sync()
     fe.pdus()
+    clk = ClockSampler(local)
+    clk.start()
     fe.profile(True)
     l0 = fe.launches()
     barrier()
