@@ -187,7 +187,7 @@ def cpu_reference(O, x, isz, nblocks_avail, target_s=12.0):
     cores = os.cpu_count() or 1
     nt, per_block = best_threads(O, x, isz, nblocks_avail)
     p = O.Pipeline(SR, CF, channel_freqs(), fold_mode=O.FOLD_FULL, nthreads=nt, fast=True)
-    nb = int(max(4, min(6 * nblocks_avail, target_s / max(per_block, 1e-6))))
+    nb = int(max(4, min(80 * nblocks_avail, target_s / max(per_block, 1e-6))))      # ~target_s seconds of CPU work over the looped slab
     t0 = time.perf_counter()
     done = 0
     while done < nb:                               # the slab is cyclic: keep feeding it until ~target_s of CPU work
