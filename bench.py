@@ -424,7 +424,7 @@ def main():
                 "roofline_pipeline": {"bound": "hbm", "achieved": pipe_ach, "peak": peak, "unit": "GB/s", "frac": pipe_ach / peak,
                                       "algorithmic_bytes_per_block": b_blk},
                 "wall_ms_per_step": 1e3 * wall / a.steps}
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:          # the CPU baseline is reported by the single-GPU run only
             line["cpu_baseline"] = cpu_reference(O, x, isz, nblocks)
         print(json.dumps(line))
     if os.environ.get("HFDL_B200_DEBUG"):
