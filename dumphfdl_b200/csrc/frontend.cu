@@ -25,7 +25,9 @@ enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_AGC, KC_BANK, KC_LO
 const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "agc", "bank", "loop", "fec" };
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
+#ifndef HFDL_NSUB
 #define HFDL_NSUB 8        // sub-ranges per batch for the agc/bank || loop overlap
+#endif
 
 FftPlan make_plan(int N) {
 	FftPlan p;
