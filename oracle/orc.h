@@ -12,15 +12,20 @@
  * /root/reference/src).
  *
  * PARITY STATUS
- *   - channeliser (fastddc/libcsdr/libcsdr_gpl), Viterbi and CRC are PINNED against the
- *     reference's own sources compiled in place into oracle/_ref/ (see oracle/Makefile,
- *     tests/test_oracle_ref.py) and against the constants/known answers in the reference text.
- *   - the liquid-dsp objects (agc, firfilt, msresamp, symsync, eqlms, modem, bsequence,
- *     msequence) are NOT in /root/reference (un-vendored dependency jgaeddert/liquid-dsp,
- *     any 1.3.0 <= v < 2.0 accepted by src/CMakeLists.txt:71-101) and the reference ships no
- *     test vectors: for those objects parity with real liquid-dsp is "parity unpinned".
- *     They restate the published liquid-dsp 1.3.2 algorithms; ground truth is the HFDL
- *     transmitter in orc_tx.c (decoded PDU octets == transmitted octets, FCS good).
+ *   - PINNED against the reference's own sources compiled where they lie into oracle/_ref/ (recipe:
+ *     oracle/Makefile): geometry, tap design, all-bin channeliser, shift/decimate (fastddc.c, libcsdr.c,
+ *     libcsdr_gpl.c), Viterbi (libfec/viterbi27_port.c), CRC (crc.c) -- tests/test_oracle_ref.py -- and the
+ *     WHOLE of hfdl.c (sample loop, Costas loop, sampler, framer FSM, descrambler, deinterleaver,
+ *     decode_user_data, dispatch_pdu, statsd hook points) plus block.c / fft.c / input-helpers.c running as
+ *     the reference's own threads: every DATADUMPS tap bit-identical, every PDU and its metadata identical --
+ *     tests/test_oracle_hfdl_ref.py.
+ *   - NOT PINNED: the inside of the liquid-dsp objects (agc, firfilt, msresamp, symsync, eqlms, modem,
+ *     bsequence, msequence; oracle/orc_liquid.c).  liquid-dsp is NOT in /root/reference (un-vendored
+ *     dependency jgaeddert/liquid-dsp, any 1.3.0 <= v < 2.0 accepted by src/CMakeLists.txt:71-101), is not
+ *     installed here and the reference ships no test vectors: in oracle/_ref/ the reference's hfdl.c is linked
+ *     against these same restated objects (ref_shim/liquid_shim.c).  They restate the published liquid-dsp
+ *     1.3.2 algorithms; ground truth for them is the HFDL transmitter in orc_tx.c (decoded PDU octets ==
+ *     transmitted octets, FCS good, all 8 modes, Es/N0 3..30 dB).  For these objects: "parity unpinned".
  */
 #ifndef ORC_H
 #define ORC_H
@@ -161,6 +166,8 @@ int  orc_channel_get_pdu(orc_channel_t *c, int idx, orc_pdu_t *out);
 const orc_ddc_t *orc_channel_ddc(orc_channel_t *c);
 float orc_channel_resamp_rate(orc_channel_t *c);
 void orc_channel_stats(orc_channel_t *c, int32_t *a1, int32_t *a2, int32_t *m1, int32_t *frames);
+int32_t orc_channel_m1_not_found(orc_channel_t *c);      /* statsd demod.preamble.errors.M1_not_found, hfdl.c:840 */
+float orc_channel_noise_floor(orc_channel_t *c);          /* c->noise_floor as noise_floor_stats_thread reads it, hfdl.c:1093 */
 
 /* ---------------- whole pipeline: fft.c thread + C channel threads ---------------- */
 typedef struct orc_pipeline orc_pipeline_t;

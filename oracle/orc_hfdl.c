@@ -10,6 +10,7 @@
 #include <string.h>
 #include <stdio.h>
 #include "orc.h"
+#include "orc_liquid.h"
 
 /* ---------------- tables from the reference text ---------------- */
 const orc_mode_t orc_modes[8] = {           /* hfdl.c:81-138 */
@@ -157,93 +158,6 @@ uint32_t orc_scrambler_bits(uint8_t *out, int n) {
 }
 
 /* ====================================================================================
- * modem (liquid modem_psk.c / modem_bpsk.c / modem_demod_soft.c), schemes BPSK, PSK4, PSK8
- * ==================================================================================== */
-typedef struct { cf32 r, x_hat; } modem_state_t;
-
-static uint32_t gray_enc(uint32_t s) { return s ^ (s >> 1); }
-static uint32_t gray_dec(uint32_t s) { uint32_t m = s >> 1; while(m) { s ^= m; m >>= 1; } return s; }
-
-static cf32 psk_point(int m, uint32_t sym) {
-	int M = 1 << m;
-	float alpha = (float)(M_PI / (float)M);
-	float ang = (float)gray_dec(sym) * 2 * alpha;
-	return cosf(ang) + I * sinf(ang);
-}
-
-static uint32_t modem_demod(int m, cf32 x, modem_state_t *st) {
-	uint32_t sym;
-	if(m == 1) {
-		sym = (crealf(x) > 0) ? 0 : 1;
-		st->x_hat = sym ? -1.0f : 1.0f;
-	} else {
-		int M = 1 << m;
-		float alpha = (float)(M_PI / (float)M);
-		float d_phi = (float)(M_PI * (1.0f - 1.0f / (float)M));
-		float theta = cargf(x);
-		theta -= d_phi;
-		if(theta < -M_PI) theta += 2 * M_PI;
-		uint32_t s = 0;
-		float v = theta;
-		for(int i = 0; i < m; i++) {
-			float ref = (float)(1 << (m - i - 1)) * alpha;
-			s <<= 1;
-			if(v > 0) { s |= 1; v -= ref; } else { v += ref; }
-		}
-		sym = gray_enc(s);
-		st->x_hat = psk_point(m, sym);
-	}
-	st->r = x;
-	return sym;
-}
-static float modem_phase_error(const modem_state_t *st) { return cimagf(st->r * conjf(st->x_hat)); }
-
-static void modem_demod_soft(int m, cf32 x, modem_state_t *st, uint8_t *soft) {
-	if(m == 1) {
-		float gamma = 4.0f;
-		float LLR = -2.0f * crealf(x) * gamma;
-		int sb = (int)(LLR * 16 + 127);
-		if(sb > 255) sb = 255;
-		if(sb < 0) sb = 0;
-		soft[0] = (uint8_t)sb;
-		modem_demod(1, x, st);
-		return;
-	}
-	uint32_t s = modem_demod(m, x, st);
-	if(m == 2) {   /* LIQUID_MODEM_PSK4: no soft table (built for m>=3 only) -> hard bits 0/255, MSB first */
-		for(int i = 0; i < m; i++) soft[i] = ((s >> (m - i - 1)) & 1) ? 255 : 0;
-		return;
-	}
-	/* PSK8: nearest-neighbour table, p = 2 (the two adjacent constellation points) */
-	int M = 1 << m;
-	float gamma = 1.2f * M;
-	float dmin0[3], dmin1[3];
-	for(int k = 0; k < m; k++) dmin0[k] = dmin1[k] = 4.0f;
-	cf32 e = x - st->x_hat;
-	float d = crealf(e * conjf(e));
-	for(int k = 0; k < m; k++) {
-		if((s >> (m - k - 1)) & 1) dmin1[k] = d; else dmin0[k] = d;
-	}
-	uint32_t g = gray_dec(s);
-	for(int i = 0; i < 2; i++) {
-		uint32_t nb = gray_enc((g + (i == 0 ? 1 : (uint32_t)(M - 1))) % (uint32_t)M);
-		cf32 xh = psk_point(m, nb);
-		cf32 ee = x - xh;
-		d = crealf(ee * conjf(ee));
-		for(int k = 0; k < m; k++) {
-			if((nb >> (m - k - 1)) & 1) { if(d < dmin1[k]) dmin1[k] = d; }
-			else { if(d < dmin0[k]) dmin0[k] = d; }
-		}
-	}
-	for(int k = 0; k < m; k++) {
-		int sb = (int)(((dmin0[k] - dmin1[k]) * gamma) * 16 + 127);
-		if(sb > 255) sb = 255;
-		if(sb < 0) sb = 0;
-		soft[k] = (uint8_t)sb;
-	}
-}
-
-/* ====================================================================================
  * decode_user_data (hfdl.c:993-1056) and its transmit-side inverse
  * ==================================================================================== */
 int orc_pdu_len_octets(int M1) {
@@ -260,13 +174,13 @@ int orc_decode_user_data(const cf32 *symbols, int M1, uint32_t bitmask, uint8_t 
 	uint8_t *table = calloc((size_t)nenc, 1);          /* [row][col], 40 rows */
 	uint8_t *scr = malloc((size_t)num_symbols);
 	orc_scrambler_bits(scr, num_symbols);
-	modem_state_t ms;
+	orc_modem_t ms;
 	int row = 0, col = 0;
 	uint8_t soft[3];
 	int si = 0;
 	for(int i = 0; i < num_symbols; i++) {
 		float flip = (scr[i] ? -1.0f : 1.0f) * ((bitmask & 1) ? -1.0f : 1.0f);
-		modem_demod_soft(p->arity, symbols[i] * flip, &ms, soft);
+		orc_modem_demod_soft(p->arity, symbols[i] * flip, &ms, soft);
 		for(int j = 0; j < p->arity; j++) {
 			if(softbits_out) softbits_out[si] = soft[j];
 			si++;
@@ -341,158 +255,11 @@ int orc_encode_user_data(const uint8_t *pdu, int M1, cf32 *symbols_out) {
 			col -= p->col_shift;
 			if(col < 0) col += column_cnt;
 		}
-		cf32 x = (p->arity == 1) ? (sym ? -1.0f : 1.0f) : psk_point(p->arity, sym);
+		cf32 x = (p->arity == 1) ? (sym ? -1.0f : 1.0f) : orc_psk_point(p->arity, sym);
 		symbols_out[i] = scr[i] ? -x : x;
 	}
 	free(bits); free(chips); free(v); free(table); free(scr);
 	return num_symbols;
-}
-
-/* ====================================================================================
- * liquid objects with state: agc_crcf, firfilt_crcf, symsync_crcf(kaiser), eqlms_cccf
- * ==================================================================================== */
-#define SS_NPFB 16
-#define SS_K 3
-#define SS_M 3
-#define SS_SUB 18                      /* (2*npfb*k*m+1)/npfb */
-typedef struct {
-	float mf[SS_NPFB][SS_SUB], dmf[SS_NPFB][SS_SUB];   /* [filter][n] = h[filter + n*npfb] */
-	cf32 win_mf[SS_SUB], win_dmf[SS_SUB];              /* [0] = newest */
-	uint32_t k, k_out, decim_counter;
-	float rate, del, tau, bf, q, q_hat;
-	int b;
-	float b0, a1, a2;                                  /* normalised loop-filter SOS */
-	float v[3];
-	float rate_adjustment;
-} symsync_t;
-
-static void symsync_reset(symsync_t *q) {              /* liquid symsync.c SYMSYNC(_reset): mf window only */
-	memset(q->win_mf, 0, sizeof(q->win_mf));
-	q->rate = (float)q->k / (float)q->k_out;
-	q->del = q->rate;
-	q->b = 0; q->bf = 0; q->tau = 0; q->q = 0; q->q_hat = 0; q->decim_counter = 0;
-	q->v[0] = q->v[1] = q->v[2] = 0;
-}
-
-static void symsync_set_lf_bw(symsync_t *q, float bt) {
-	float alpha = 1.000f - bt, beta = 0.220f * bt, a = 0.500f, b = 0.495f;
-	float B0 = beta, A0 = 1.0f - a * alpha, A1 = -b * alpha, A2 = 0;
-	q->b0 = B0 / A0; q->a1 = A1 / A0; q->a2 = A2 / A0;
-	q->rate_adjustment = 0.5 * bt;
-}
-
-static void symsync_init(symsync_t *q) {               /* create_kaiser(k=3,m=3,beta(unused),M=16) hfdl.c:503-505 */
-	memset(q, 0, sizeof(*q));
-	enum { HL = 2 * SS_NPFB * SS_K * SS_M + 1 };
-	float Hf[HL], H[HL], dH[HL];
-	float fc = 0.75f, As = 40.0f;
-	orc_firdes_kaiser(HL, fc / (float)(SS_K * SS_NPFB), As, 0.0f, Hf);
-	for(int i = 0; i < HL; i++) H[i] = Hf[i] * 2.0f * fc;
-	float hdh_max = 0;
-	for(int i = 0; i < HL; i++) {
-		if(i == 0) dH[i] = H[i + 1] - H[HL - 1];
-		else if(i == HL - 1) dH[i] = H[0] - H[i - 1];
-		else dH[i] = H[i + 1] - H[i - 1];
-		if(fabsf(H[i] * dH[i]) > hdh_max || i == 0) hdh_max = fabsf(H[i] * dH[i]);
-	}
-	for(int i = 0; i < HL; i++) dH[i] *= 0.06f / hdh_max;
-	for(int f = 0; f < SS_NPFB; f++)
-		for(int n = 0; n < SS_SUB; n++) {
-			q->mf[f][n] = H[f + n * SS_NPFB];
-			q->dmf[f][n] = dH[f + n * SS_NPFB];
-		}
-	q->k = SS_K;
-	q->k_out = 1;
-	symsync_reset(q);
-	symsync_set_lf_bw(q, 0.01f);
-	/* hfdl.c:504-505 */
-	symsync_set_lf_bw(q, 0.001f);
-	q->k_out = 2;
-	q->rate = (float)q->k / (float)q->k_out;
-	q->del = q->rate;
-}
-
-static cf32 pfb_exec(const float *h, const cf32 *win) {
-	cf32 acc = 0;
-	for(int n = SS_SUB - 1; n >= 0; n--) acc += h[n] * win[n];   /* oldest first */
-	return acc;
-}
-
-static int symsync_step(symsync_t *q, cf32 x, cf32 *y) {
-	memmove(q->win_mf + 1, q->win_mf, sizeof(cf32) * (SS_SUB - 1));
-	q->win_mf[0] = x;
-	memmove(q->win_dmf + 1, q->win_dmf, sizeof(cf32) * (SS_SUB - 1));
-	q->win_dmf[0] = x;
-	int n = 0;
-	while(q->b < SS_NPFB) {
-		cf32 mf = pfb_exec(q->mf[q->b], q->win_mf);
-		y[n] = mf / (float)q->k;
-		if(q->decim_counter == q->k_out) {
-			q->decim_counter = 0;
-			cf32 dmf = pfb_exec(q->dmf[q->b], q->win_dmf);
-			/* advance_internal_loop */
-			q->q = crealf(conjf(mf) * dmf);
-			if(q->q > 1.0f) q->q = 1.0f; else if(q->q < -1.0f) q->q = -1.0f;
-			q->v[2] = q->v[1]; q->v[1] = q->v[0];
-			q->v[0] = q->q - q->a1 * q->v[1] - q->a2 * q->v[2];
-			q->q_hat = q->b0 * q->v[0];
-			q->rate += q->rate_adjustment * q->q_hat;
-			q->del = q->rate + q->q_hat;
-		}
-		q->decim_counter++;
-		q->tau += q->del;
-		q->bf = q->tau * (float)SS_NPFB;
-		q->b = (int)roundf(q->bf);
-		n++;
-	}
-	q->tau -= 1.0f;
-	q->bf -= (float)SS_NPFB;
-	q->b -= SS_NPFB;
-	return n;
-}
-
-typedef struct {
-	cf32 h0[ORC_EQ_LEN], w[ORC_EQ_LEN], win[ORC_EQ_LEN];   /* win[0] = oldest */
-	float x2[ORC_EQ_LEN];                                   /* delay line, x2[0] = oldest */
-	float x2_sum, mu;
-	uint32_t count; int buf_full;
-} eqlms_t;
-
-static void eqlms_reset(eqlms_t *q) {
-	memcpy(q->w, q->h0, sizeof(q->w));
-	memset(q->win, 0, sizeof(q->win));
-	memset(q->x2, 0, sizeof(q->x2));
-	q->count = 0; q->buf_full = 0; q->x2_sum = 0;
-}
-static void eqlms_init(eqlms_t *q) {                   /* create_lowpass(15, 0.45), set_bw 0.1 (hfdl.c:495-496) */
-	float h[ORC_EQ_LEN];
-	orc_firdes_kaiser(ORC_EQ_LEN, 0.45f, 40.0f, 0.0f, h);
-	for(int i = 0; i < ORC_EQ_LEN; i++) q->h0[i] = conjf((cf32)(h[ORC_EQ_LEN - 1 - i] * 2 * 0.45f));
-	q->mu = 0.1f;
-	eqlms_reset(q);
-}
-static void eqlms_push(eqlms_t *q, cf32 x) {
-	memmove(q->win, q->win + 1, sizeof(cf32) * (ORC_EQ_LEN - 1));
-	q->win[ORC_EQ_LEN - 1] = x;
-	float x2n = crealf(x * conjf(x));
-	float x20 = q->x2[0];
-	memmove(q->x2, q->x2 + 1, sizeof(float) * (ORC_EQ_LEN - 1));
-	q->x2[ORC_EQ_LEN - 1] = x2n;
-	q->x2_sum = q->x2_sum + x2n - x20;
-	q->count++;
-}
-static cf32 eqlms_execute(const eqlms_t *q) {
-	cf32 y = 0;
-	for(int i = 0; i < ORC_EQ_LEN; i++) y += conjf(q->w[i]) * q->win[i];
-	return y;
-}
-static void eqlms_step(eqlms_t *q, cf32 d, cf32 d_hat) {
-	if(!q->buf_full) {
-		if(q->count < ORC_EQ_LEN) return;
-		q->buf_full = 1;
-	}
-	cf32 alpha = d - d_hat;
-	for(int i = 0; i < ORC_EQ_LEN; i++) q->w[i] = q->w[i] + q->mu * conjf(alpha) * q->win[i] / q->x2_sum;
 }
 
 /* ====================================================================================
@@ -509,13 +276,13 @@ struct orc_channel {
 	float resamp_rate;
 	int32_t freq;
 	/* agc_crcf */
-	float agc_g, agc_alpha, agc_y2;
+	orc_agc_t agc;
 	/* firfilt (matched filter) */
-	cf32 mf_win[ORC_MF_TAPS];      /* [0] = newest */
-	symsync_t ss;
+	orc_firfilt_t mf;
+	orc_symsync_t ss;
 	float c_alpha, c_beta, c_phi, c_dphi, c_err;   /* costas hfdl.c:250-294 */
-	eqlms_t eq;
-	modem_state_t modem;
+	orc_eqlms_t eq;
+	orc_modem_t modem;
 	bits128_t bits, A_bs, M1_bs[8];
 	cf32 training[ORC_T_LEN]; int training_n;
 	cf32 *data_symbols; int data_n;
@@ -531,7 +298,7 @@ struct orc_channel {
 	uint32_t nf_clk; float frame_symbol_cnt;
 	/* outputs */
 	orc_pdu_t *pdus; int npdu, cap_pdu;
-	int32_t st_a1, st_a2, st_m1, st_frames;
+	int32_t st_a1, st_a2, st_m1, st_frames, st_m1_fail;
 	/* capture */
 	uint32_t cap_mask; size_t cap_max; cf32 *cap[ORC_CAP_COUNT]; size_t cap_n[ORC_CAP_COUNT];
 	cf32 *chan_out, *resampled;
@@ -553,7 +320,7 @@ static int bits_correlate(const bits128_t *a, const bits128_t *b) {   /* number 
 }
 
 static void sampler_reset(orc_channel_t *c) {          /* hfdl.c:968-972 */
-	symsync_reset(&c->ss);
+	orc_symsync_reset(&c->ss);
 	c->s_state = S_EMIT_BITS;
 	c->bitmask = 0;
 }
@@ -566,7 +333,7 @@ static void framer_reset(orc_channel_t *c) {           /* hfdl.c:974-991 */
 	c->T_idx = 0;
 	c->cur_buf = 0;
 	/* agc_crcf_unlock: the AGC is never locked, no effect */
-	eqlms_reset(&c->eq);
+	orc_eqlms_reset(&c->eq);
 	c->data_n = 0;
 	c->training_n = 0;
 	sampler_reset(c);
@@ -580,12 +347,16 @@ orc_channel_t *orc_channel_create(int32_t sample_rate, int32_t pre_dec, float tb
 	float freq_shift = orc_channel_shift_rate(sample_rate, centerfreq, frequency);
 	c->chz = orc_channelizer_create(pre_dec, tbw, freq_shift, fold_mode);
 	if(!c->chz || !c->rs) { free(c); return NULL; }
-	c->agc_g = 1.0f; c->agc_y2 = 1.0f; c->agc_alpha = 0.01f;   /* hfdl.c:485-487 */
+	orc_agc_init(&c->agc, 0.01f);                              /* hfdl.c:485-487 */
+	orc_firfilt_init(&c->mf, orc_mf_taps, ORC_MF_TAPS);        /* hfdl.c:494 */
 	c->noise_floor = 1.0f;                                     /* hfdl.c:490 */
 	c->c_alpha = 0.1f;
 	c->c_beta = 0.047f * c->c_alpha * c->c_alpha;              /* hfdl.c:254-259 */
-	eqlms_init(&c->eq);
-	symsync_init(&c->ss);
+	orc_eqlms_init_lowpass(&c->eq, 0.45f);                     /* hfdl.c:495 */
+	c->eq.mu = 0.1f;                                           /* eqlms_cccf_set_bw, hfdl.c:496 */
+	orc_symsync_init_kaiser(&c->ss);                           /* hfdl.c:503 */
+	orc_symsync_set_lf_bw(&c->ss, 0.001f);                     /* hfdl.c:504 */
+	orc_symsync_set_output_rate(&c->ss, 2);                    /* hfdl.c:505 */
 	/* A and M1 templates, hfdl.c:438-459 (bits pushed in time order) */
 	for(int i = 0; i < ORC_A_LEN; i++) bits_push(&c->A_bs, (orc_A_octets[i >> 3] >> (7 - (i & 7))) & 1);
 	for(int s = 0; s < 8; s++)
@@ -629,6 +400,8 @@ int orc_channel_get_pdu(orc_channel_t *c, int idx, orc_pdu_t *out) {
 void orc_channel_stats(orc_channel_t *c, int32_t *a1, int32_t *a2, int32_t *m1, int32_t *frames) {
 	*a1 = c->st_a1; *a2 = c->st_a2; *m1 = c->st_m1; *frames = c->st_frames;
 }
+int32_t orc_channel_m1_not_found(orc_channel_t *c) { return c->st_m1_fail; }
+float orc_channel_noise_floor(orc_channel_t *c) { return c->noise_floor; }
 
 static void dispatch_pdu(orc_channel_t *c, const uint8_t *buf, int len) {   /* hfdl.c:1058-1080 */
 	if(c->npdu == c->cap_pdu) {
@@ -651,9 +424,9 @@ static void dispatch_pdu(orc_channel_t *c, const uint8_t *buf, int len) {   /* h
 
 static void train_bit_errors(orc_channel_t *c) {       /* hfdl.c:952-966 */
 	uint32_t T_seq = 0;
-	modem_state_t ms;
+	orc_modem_t ms;
 	for(int i = 0; i < ORC_T_LEN; i++) {
-		uint32_t bit = modem_demod(1, c->training[i], &ms);
+		uint32_t bit = orc_modem_demod(1, c->training[i], &ms);
 		bit ^= (c->bitmask & 1);
 		T_seq = (T_seq << 1) | bit;
 	}
@@ -667,23 +440,17 @@ static const float T_sym[ORC_T_LEN] = { 1, 1, 1, -1, 1, 1, -1, -1, 1, -1, 1, -1,
 /* one sample at 5400 Hz: body of the k loop, hfdl.c:685-893 */
 static void demod_sample(orc_channel_t *c, cf32 x) {
 	/* agc_crcf_execute */
-	cf32 r = x * c->agc_g;
-	float y2 = crealf(r * conjf(r));
-	c->agc_y2 = (1.0 - c->agc_alpha) * c->agc_y2 + c->agc_alpha * y2;
-	if(c->agc_y2 > 1e-6f) c->agc_g *= expf(-0.5f * c->agc_alpha * logf(c->agc_y2));
-	if(c->agc_g > 1e6f) c->agc_g = 1e6f;
+	cf32 r = orc_agc_execute(&c->agc, x);
 	cap_push(c, ORC_CAP_AGC, r);
 	/* matched filter */
-	memmove(c->mf_win + 1, c->mf_win, sizeof(cf32) * (ORC_MF_TAPS - 1));
-	c->mf_win[0] = r;
-	cf32 s = 0;
-	for(int k = ORC_MF_TAPS - 1; k >= 0; k--) s += orc_mf_taps[k] * c->mf_win[k];
+	orc_firfilt_push(&c->mf, r);
+	cf32 s = orc_firfilt_execute(&c->mf);
 	cap_push(c, ORC_CAP_MF, s);
 	/* noise floor hfdl.c:700-706 */
 	if(c->fr_state == F_A1 && (++c->nf_clk & 0xFFu) == 0xFFu)
-		c->noise_floor = 0.65f * c->noise_floor + 0.35f * fminf(c->noise_floor, 1.0f / c->agc_g) + 1e-6f;
+		c->noise_floor = 0.65f * c->noise_floor + 0.35f * fminf(c->noise_floor, orc_agc_signal_level(&c->agc)) + 1e-6f;
 	cf32 symbols[8];
-	int produced = symsync_step(&c->ss, s, symbols);
+	int produced = orc_symsync_step(&c->ss, s, symbols);
 	for(int i = 0; i < produced; i++, c->symsync_out_idx++) {
 		/* costas_cccf_step + execute */
 		c->c_phi += c->c_dphi;
@@ -692,23 +459,23 @@ static void demod_sample(orc_channel_t *c, cf32 x) {
 		r = symbols[i] * (cosf(c->c_phi) - I * sinf(c->c_phi));
 		if(fabsf(c->c_dphi) > 0.25f && c->fr_state == F_A1) {
 			c->c_phi = c->c_dphi = 0.f;
-			symsync_reset(&c->ss);
+			orc_symsync_reset(&c->ss);
 		}
-		eqlms_push(&c->eq, r);
+		orc_eqlms_push(&c->eq, r);
 		if(!(c->symsync_out_idx & 1)) continue;
 		cap_push(c, ORC_CAP_SYMSYNC, symbols[i]);
 		cap_push(c, ORC_CAP_COSTAS, r);
-		s = eqlms_execute(&c->eq);
+		s = orc_eqlms_execute(&c->eq);
 		if(c->fr_state == F_EQ_TRAIN) {
 			float d = T_sym[c->T_idx];
 			if(c->bitmask & 1) d = -d;
-			eqlms_step(&c->eq, d, s);
+			orc_eqlms_step(&c->eq, d, s);
 			c->T_idx++;
 		}
 		cap_push(c, ORC_CAP_EQ, s);
-		uint32_t bits = modem_demod(c->cur_arity, s, &c->modem);
+		uint32_t bits = orc_modem_demod(c->cur_arity, s, &c->modem);
 		/* costas_cccf_adjust */
-		float err = modem_phase_error(&c->modem);
+		float err = orc_modem_phase_error(&c->modem);
 		err = 0.5 * (fabsf(err + 1.0f) - fabsf(err - 1.0f));
 		c->c_err = err;
 		c->c_phi += c->c_alpha * err;
@@ -718,7 +485,7 @@ static void demod_sample(orc_channel_t *c, cf32 x) {
 		if(c->symbol_cnt >= 13u * ORC_SINGLE_SLOT_FRAME_LEN && c->fr_state == F_A1) {
 			c->symbol_cnt = 0;
 			c->c_phi = c->c_dphi = 0.f;
-			symsync_reset(&c->ss);
+			orc_symsync_reset(&c->ss);
 		}
 		if(c->s_state == S_EMIT_BITS) {
 			bits ^= c->bitmask;
@@ -728,7 +495,7 @@ static void demod_sample(orc_channel_t *c, cf32 x) {
 			else { if(c->data_n < ORC_DATA_SYMS_MAX) c->data_symbols[c->data_n++] = s; }
 		}
 		if(c->fr_state > F_A1) {
-			c->signal_level = (c->signal_level * c->frame_symbol_cnt + 1.0f / c->agc_g) / (c->frame_symbol_cnt + 1.0f);
+			c->signal_level = (c->signal_level * c->frame_symbol_cnt + orc_agc_signal_level(&c->agc)) / (c->frame_symbol_cnt + 1.0f);
 			c->frame_symbol_cnt += 1.0f;
 		}
 		if(c->symbols_wanted > 1) { c->symbols_wanted--; continue; }
@@ -739,7 +506,7 @@ static void demod_sample(orc_channel_t *c, cf32 x) {
 			if(fabsf(corr) > 0.36f) {
 				c->st_a1++;
 				c->bitmask = corr > 0.f ? 0 : ~0u;
-				c->signal_level = 1.0f / c->agc_g;
+				c->signal_level = orc_agc_signal_level(&c->agc);
 				c->frame_symbol_cnt = 1.0f;
 				c->symbols_wanted = ORC_A_LEN;
 				c->search_retries = 0;
@@ -775,6 +542,7 @@ static void demod_sample(orc_channel_t *c, cf32 x) {
 				c->fr_state = F_M2_SKIP;
 				c->s_state = S_SKIP;
 			} else {
+				c->st_m1_fail++;                        /* statsd demod.preamble.errors.M1_not_found, hfdl.c:840 */
 				framer_reset(c);
 			}
 			break; }

@@ -1,26 +1,74 @@
-/* oracle/ref_shim/ref_glue.c -- glue so the reference's own fastddc.c / libcsdr.c link without fftw3f:
- * the five csdr_* FFT entry points of src/fft.h:23-28 (implemented in the reference by fft_fftw.c on
- * fftw3f, which is not installed here) are served by the oracle's FFT.  Test infrastructure only. */
+/* oracle/ref_shim/ref_glue.c -- glue so the reference's own fastddc.c / libcsdr.c / fft.c link without fftw3f:
+ * the five csdr_* FFT entry points of src/fft.h:23-28 (implemented in the reference by fft_fftw.c on fftw3f).
+ * When libfftw3f.so.3 can be dlopen'ed on the machine (it is not installed in the build container) the calls go
+ * to fftwf_plan_dft_1d / fftwf_execute exactly as fft_fftw.c:8-41 makes them (FFTW_ESTIMATE, nthreads); otherwise
+ * they are served by the oracle's FFT (orc_fft, persistent worker pool).  Test infrastructure only. */
+#define _GNU_SOURCE
 #include <math.h>
 #include <complex.h>
 #include <stdlib.h>
+#include <stdio.h>
+#include <dlfcn.h>
 #include "fft.h"
 #include "fastddc.h"
 
 void orc_fft(const float complex *in, float complex *out, int n, int dir);
+void orc_fft_set_threads(int nthreads);
 
-void csdr_fft_init(int32_t thread_cnt) { (void)thread_cnt; }
+typedef void *(*fftwf_plan_dft_1d_t)(int, void *, void *, int, unsigned);
+typedef void (*fftwf_execute_t)(void *);
+typedef void (*fftwf_destroy_plan_t)(void *);
+typedef int (*fftwf_init_threads_t)(void);
+typedef void (*fftwf_plan_with_nthreads_t)(int);
+static struct {
+	int probed, ok, threads;
+	fftwf_plan_dft_1d_t plan; fftwf_execute_t exec; fftwf_destroy_plan_t destroy;
+	fftwf_init_threads_t init_threads; fftwf_plan_with_nthreads_t with_nthreads;
+} F;
+
+static void probe_fftw(void) {
+	if(F.probed) return;
+	F.probed = 1;
+	if(getenv("ORC_NO_FFTW")) return;
+	void *h = dlopen("libfftw3f.so.3", RTLD_NOW | RTLD_GLOBAL);
+	if(!h) return;
+	F.plan = (fftwf_plan_dft_1d_t)dlsym(h, "fftwf_plan_dft_1d");
+	F.exec = (fftwf_execute_t)dlsym(h, "fftwf_execute");
+	F.destroy = (fftwf_destroy_plan_t)dlsym(h, "fftwf_destroy_plan");
+	if(!F.plan || !F.exec || !F.destroy) return;
+	F.ok = 1;
+	void *ht = dlopen("libfftw3f_threads.so.3", RTLD_NOW | RTLD_GLOBAL);
+	if(ht) {
+		F.init_threads = (fftwf_init_threads_t)dlsym(ht, "fftwf_init_threads");
+		F.with_nthreads = (fftwf_plan_with_nthreads_t)dlsym(ht, "fftwf_plan_with_nthreads");
+		if(F.init_threads && F.with_nthreads) F.threads = 1;
+	}
+}
+/* 1: fftw3f (+2: with fftw3f_threads); 0: the oracle's FFT */
+int ref_fft_backend(void) { probe_fftw(); return F.ok ? (F.threads ? 3 : 1) : 0; }
+
+void csdr_fft_init(int32_t thread_cnt) {                 /* fft_fftw.c:8-14 */
+	probe_fftw();
+	if(F.ok && F.threads) { F.init_threads(); F.with_nthreads(thread_cnt); }
+	orc_fft_set_threads(thread_cnt);
+}
 void csdr_fft_destroy() {}
 FFT_PLAN_T *csdr_make_fft_c2c(int32_t size, float complex *input, float complex *output, int32_t forward, int32_t benchmark) {
 	(void)benchmark;
+	probe_fftw();
 	FFT_PLAN_T *p = calloc(1, sizeof(*p));
 	p->size = size; p->input = input; p->output = output;
-	p->plan = forward ? (void *)1 : (void *)2;
+	if(F.ok) p->plan = F.plan(size, input, output, forward ? -1 : +1, 1u << 6);      /* FFTW_FORWARD / BACKWARD, FFTW_ESTIMATE (fft_fftw.c:25) */
+	else p->plan = forward ? (void *)1 : (void *)2;
 	return p;
 }
-void csdr_destroy_fft_c2c(FFT_PLAN_T *plan) { free(plan); }
+void csdr_destroy_fft_c2c(FFT_PLAN_T *plan) {
+	if(F.ok && plan) F.destroy(plan->plan);
+	free(plan);
+}
 void csdr_fft_execute(FFT_PLAN_T *plan) {
-	orc_fft(plan->input, plan->output, plan->size, plan->plan == (void *)1 ? +1 : -1);
+	if(F.ok) F.exec(plan->plan);
+	else orc_fft(plan->input, plan->output, plan->size, plan->plan == (void *)1 ? +1 : -1);
 }
 /* fastddc.c declares is_integer as a C99 'inline' without an external definition */
 int32_t is_integer(float a) { return floorf(a) == a; }

@@ -107,6 +107,9 @@ def lib(fast=False):
     L.orc_channel_resamp_rate.restype = C.c_float
     L.orc_channel_resamp_rate.argtypes = [C.c_void_p]
     L.orc_channel_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+    L.orc_channel_m1_not_found.argtypes = [C.c_void_p]
+    L.orc_channel_noise_floor.argtypes = [C.c_void_p]
+    L.orc_channel_noise_floor.restype = C.c_float
     L.orc_pipeline_create.restype = C.c_void_p
     L.orc_pipeline_create.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int, C.c_int]
     L.orc_pipeline_destroy.argtypes = [C.c_void_p]
@@ -171,8 +174,112 @@ def reflib():
     R.ref_channelizer_ddc.argtypes = [C.c_void_p]
     R.ref_channelizer_execute.argtypes = [C.c_void_p, cfp, cfp]
     R.fft_swap_sides.argtypes = [cfp, C.c_int32]
+    _bind_ref_host(R)
     _libs["ref"] = R
     return R
+
+
+class RefPdu(C.Structure):
+    """capture record of oracle/ref_shim/ref_host.c: struct hfdl_pdu_metadata (pdu.h:8-17) + the octet string"""
+    _fields_ = [("version", C.c_int32), ("freq", C.c_int32), ("bit_rate", C.c_int32),
+                ("freq_err_hz", C.c_float), ("rssi", C.c_float), ("noise_floor", C.c_float),
+                ("slot", C.c_char), ("len", C.c_int32), ("flags", C.c_uint32), ("octets", C.c_uint8 * 948)]
+
+    def data(self):
+        return bytes(self.octets[: self.len])
+
+
+def _bind_ref_host(R):
+    if not hasattr(R, "ref_pipeline_create"):
+        return
+    R.ref_pipeline_create.restype = C.c_void_p
+    R.ref_pipeline_create.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32]
+    R.ref_pipeline_feed.restype = C.c_int64
+    R.ref_pipeline_feed.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    R.ref_pipeline_finish.argtypes = [C.c_void_p]
+    R.ref_pipeline_drain.argtypes = [C.c_void_p]
+    R.ref_pipeline_destroy.argtypes = [C.c_void_p]
+    R.ref_pipeline_input_size.argtypes = [C.c_void_p]
+    R.ref_pdu_get.argtypes = [C.c_int, C.POINTER(RefPdu)]
+    R.ref_stat_count.restype = C.c_long
+    R.ref_stat_count.argtypes = [C.c_int32, C.c_char_p]
+    R.ref_dump_read.restype = C.c_long
+    R.ref_dump_read.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_long]
+    R.ref_dumps_enable.argtypes = [C.c_int]
+    R.ref_struct_sizes.argtypes = [C.c_int]
+
+
+def reflib_fast():
+    """Timing build of the same reference sources (-O3 -ffast-math, no DATADUMPS); None if not built."""
+    if "ref_fast" in _libs:
+        return _libs["ref_fast"]
+    path = os.path.join(ODIR, "_ref", "libref_fast.so")
+    if not os.path.exists(path) and os.path.isdir("/root/reference/src"):
+        build()
+    R = C.CDLL(path) if os.path.exists(path) else None
+    if R is not None:
+        _bind_ref_host(R)
+        R.ref_fft_backend.restype = C.c_int
+    _libs["ref_fast"] = R
+    return R
+
+
+class RefPipeline:
+    """The REFERENCE's own block.c + fft.c + fastddc.c + hfdl.c + viterbi27_port.c, wired as main.c does, fed as
+    input-file.c does (oracle/ref_shim/ref_host.c).  One instance at a time (the PDU capture list is global)."""
+
+    def __init__(self, sample_rate, centerfreq, freqs, sfmt=3, fft_threads=4, fast=False, dumps=False):
+        self.R = reflib_fast() if fast else reflib()
+        assert self.R is not None, "oracle/_ref not built"
+        self.R.ref_pdu_clear()
+        self.R.ref_stat_clear()
+        self.R.ref_dumps_clear()
+        self.R.ref_dumps_enable(1 if dumps else 0)
+        fa = (C.c_int32 * len(freqs))(*freqs)
+        self.p = self.R.ref_pipeline_create(sample_rate, centerfreq, fa, len(freqs), sfmt, fft_threads)
+        assert self.p
+        self.freqs = list(freqs)
+        self.sfmt = sfmt
+        self.finished = False
+
+    def feed(self, raw):
+        raw = np.ascontiguousarray(raw)
+        n = raw.size if raw.dtype == np.complex64 else raw.size // 2
+        return self.R.ref_pipeline_feed(self.p, raw.ctypes.data, n)
+
+    def drain(self):
+        self.R.ref_pipeline_drain(self.p)
+
+    def finish(self):
+        if not self.finished:
+            self.R.ref_pipeline_finish(self.p)
+            self.finished = True
+
+    def pdus(self):
+        out = []
+        for i in range(self.R.ref_pdu_count()):
+            q = RefPdu()
+            self.R.ref_pdu_get(i, C.byref(q))
+            out.append(q)
+        return out
+
+    def stat(self, freq, name):
+        return int(self.R.ref_stat_count(freq, name.encode()))
+
+    def dump(self, name, idx=0, complex_=True):
+        n = self.R.ref_dump_read(name.encode(), idx, None, None, 0)
+        if n < 0:
+            return None, None
+        t = np.zeros(n, np.uint64)
+        v = np.zeros(n, np.complex64)
+        self.R.ref_dump_read(name.encode(), idx, t.ctypes.data, v.ctypes.data, n)
+        return t, (v if complex_ else v.real.copy())
+
+    def close(self):
+        if self.p:
+            self.finish()
+            self.R.ref_pipeline_destroy(self.p)
+            self.p = None
 
 
 # ---------------------------------------------------------------- helpers
@@ -271,6 +378,12 @@ class Pipeline:
         v = [C.c_int32() for _ in range(4)]
         self.L.orc_channel_stats(self.channel(ch), *[C.byref(x) for x in v])
         return tuple(x.value for x in v)
+
+    def m1_not_found(self, ch):
+        return int(self.L.orc_channel_m1_not_found(self.channel(ch)))
+
+    def noise_floor(self, ch):
+        return float(self.L.orc_channel_noise_floor(self.channel(ch)))
 
     def last_spectrum(self):
         out = np.zeros(self.ddc.fft_size, np.complex64)
