@@ -22,12 +22,24 @@ class Geometry(C.Structure):
                [("transition_bw", C.c_float), ("resamp_rate", C.c_float), ("fft_passes", C.c_int32), ("fft_len", C.c_int32 * 3)]
 
 
+class Counters(C.Structure):
+    """hfdl_b200_counters_t: the reference's per-channel statsd metrics (doc/STATSD_METRICS.md)"""
+    _fields_ = [("freq", C.c_int32)] + [(n, C.c_int64) for n in (
+        "A1_found", "A2_found", "M1_found", "M1_not_found", "frames_processed", "frames_good", "frames_bad_fcs", "frames_too_short",
+        "frames_air2gnd", "frames_gnd2air", "lpdus_processed", "lpdus_good", "lpdus_bad_fcs", "lpdus_too_short")] + [("noise_floor", C.c_float)]
+
+    def asdict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class Pdu(C.Structure):
     _fields_ = [("version", C.c_int32), ("freq", C.c_int32), ("bit_rate", C.c_int32), ("freq_err_hz", C.c_float),
                 ("rssi", C.c_float), ("noise_floor", C.c_float), ("slot", C.c_char), ("M1", C.c_int32), ("crc_good", C.c_int32),
                 ("train_bits_bad", C.c_int32), ("train_bits_total", C.c_int32), ("sample_cnt_a2", C.c_uint64),
                 ("sample_cnt_end", C.c_uint64), ("rx_time_s", C.c_double), ("signal_level", C.c_float),
-                ("noise_floor_lin", C.c_float), ("len", C.c_int32), ("octets", C.c_uint8 * (MAX_PDU + 3))]
+                ("noise_floor_lin", C.c_float), ("len", C.c_int32), ("octets", C.c_uint8 * (MAX_PDU + 3)),
+                ("frame_status", C.c_int32), ("direction", C.c_int32), ("lpdus_processed", C.c_int32), ("lpdus_good", C.c_int32),
+                ("lpdus_bad_fcs", C.c_int32), ("lpdus_too_short", C.c_int32), ("lpdu_good_mask", C.c_uint64)]
 
     def data(self):
         return bytes(self.octets[: self.len])
@@ -48,6 +60,11 @@ def bind(L):
     L.hfdl_b200_flush.argtypes = [vp]
     L.hfdl_b200_process_device.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int32]
     L.hfdl_b200_sync.argtypes = [vp]
+    L.hfdl_b200_submit.argtypes = [vp]
+    L.hfdl_b200_push_peer.argtypes = [vp, vp]
+    L.hfdl_b200_poll.argtypes = [vp]
+    L.hfdl_b200_busy.argtypes = [vp]
+    L.hfdl_b200_channel_counters.argtypes = [vp, C.c_int32, C.POINTER(Counters)]
     L.hfdl_b200_pdu_count.argtypes = [vp]
     L.hfdl_b200_pop_pdu.argtypes = [vp, C.POINTER(Pdu)]
     L.hfdl_b200_channel_noise_floor.argtypes = [vp, C.c_int32, C.POINTER(C.c_float)]
@@ -68,6 +85,7 @@ def bind(L):
     L.hfdl_b200_fec_decode.argtypes = [C.c_int32, vp, C.c_int32, C.c_int32, C.c_uint32, vp, C.c_int32, vp, vp]
     L.hfdl_b200_viterbi27.argtypes = [C.c_int32, vp, C.c_int32, C.c_int32, vp]
     L.hfdl_b200_pdu_len.argtypes = [C.c_int32]
+    L.hfdl_b200_pdu_front_parse.argtypes = [C.c_int32, vp, C.c_int32, vp, C.c_int32, vp]
     return L
 
 
@@ -115,6 +133,22 @@ def fec_decode(symbols, M1, bitmask=0, device=0, want_soft=False, lib=None):
     if rc != 0:
         raise RuntimeError("hfdl_b200_fec_decode failed")
     return out, crc, soft
+
+
+def pdu_front_parse(pdus, device=0, lib=None):
+    """list of bytes -> list of (frame_status, direction, lpdus processed, good, bad_fcs, too_short, good mask, crc_good)"""
+    L = lib or load()
+    n = len(pdus)
+    stride = max(len(p) for p in pdus)
+    buf = np.zeros((n, stride), np.uint8)
+    lens = np.zeros(n, np.int32)
+    for i, p in enumerate(pdus):
+        buf[i, :len(p)] = np.frombuffer(bytes(p), np.uint8)
+        lens[i] = len(p)
+    out = (Pdu * n)()
+    if L.hfdl_b200_pdu_front_parse(device, buf.ctypes.data, stride, lens.ctypes.data, n, out) != 0:
+        raise RuntimeError("hfdl_b200_pdu_front_parse failed")
+    return [(q.frame_status, q.direction, q.lpdus_processed, q.lpdus_good, q.lpdus_bad_fcs, q.lpdus_too_short, q.lpdu_good_mask, q.crc_good) for q in out]
 
 
 def viterbi27(syms, nbits, device=0, lib=None):
@@ -176,6 +210,30 @@ class Frontend:
 
     def sync(self):
         self.L.hfdl_b200_sync(self.h)
+
+    def push_peer(self, src):
+        r = self.L.hfdl_b200_push_peer(self.h, src.h)
+        if r < 0:
+            raise RuntimeError("hfdl_b200_push_peer failed")
+        return r
+
+    def submit(self):
+        r = self.L.hfdl_b200_submit(self.h)
+        if r < 0:
+            raise RuntimeError("hfdl_b200_submit failed")
+        return r
+
+    def poll(self):
+        return self.L.hfdl_b200_poll(self.h)
+
+    def busy(self):
+        return self.L.hfdl_b200_busy(self.h)
+
+    def counters(self, ch):
+        c = Counters()
+        if self.L.hfdl_b200_channel_counters(self.h, ch, C.byref(c)) != 0:
+            raise RuntimeError("hfdl_b200_channel_counters failed")
+        return c
 
     def pdus(self):
         out = []

@@ -1,10 +1,17 @@
 // dumphfdl_b200/csrc/block_shim.cu -- block.c-facing wrapper (include/hfdl_b200_block.h): a `struct block` whose
-// thread routine follows the consumer protocol of fft_thread (fft.c:38-55), feeds the GPU front-end and hands
+// thread routine follows the consumer protocol of fft_thread (fft.c:38-55), feeds the GPU front-end(s) and hands
 // decoded frames to the reference's pdu_decoder_queue_push (hfdl.c:1058-1080).  Host code only.
+//
+// Everything the wrapper needs from the host program is a WEAK reference resolved when the library is loaded into
+// dumphfdl: liquid-dsp's cbuffercf_* (the ring block_connect_one2one creates, block.c:20), hfdl_pdu_metadata_create,
+// octet_string_new, pdu_decoder_queue_push and (optional) the statsd hook statsd_counter_per_channel_increment.
+// The library itself defines none of them (it must not interpose libliquid's cbuffercf).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <errno.h>
+#include <time.h>
 #include <sys/time.h>
 #include <vector>
 #include "../../include/hfdl_b200_block.h"
@@ -28,59 +35,19 @@ struct octet_string;
 struct metadata *hfdl_pdu_metadata_create(void) __attribute__((weak));
 struct octet_string *octet_string_new(void *buf, size_t len) __attribute__((weak));
 void pdu_decoder_queue_push(struct metadata *metadata, struct octet_string *pdu, uint32_t flags) __attribute__((weak));
+void statsd_counter_per_channel_increment(int32_t freq, char *counter) __attribute__((weak));       // statsd.h:15 (WITH_STATSD builds)
+// liquid-dsp cbuffercf (liquid.h; used by block.c:20,28, fft.c:41-54, input-helpers.c:83-89): the four calls the consumer makes
+unsigned int cbuffercf_size(cbuffercf q) __attribute__((weak));
+// (liquid-dsp 1.3.x returns void from the next two, >= 1.4 an int status that is not used here)
+void cbuffercf_read(cbuffercf q, unsigned int num_requested, void **v, unsigned int *num_read) __attribute__((weak));
+void cbuffercf_release(cbuffercf q, unsigned int n) __attribute__((weak));
 }
-
-// ---- cbuffercf stand-in: mirrored storage so that any read of <= max_size elements is contiguous ---------------
-struct hfdl_cbuffercf_s {
-	unsigned int max_size, num_elements, read_index, write_index;
-	float *v;                      // 2 * max_size complex elements (re, im)
-};
-
-extern "C" {
-
-cbuffercf cbuffercf_create(unsigned int max_size) {
-	if(max_size == 0) return NULL;
-	cbuffercf q = (cbuffercf)calloc(1, sizeof(*q));
-	q->max_size = max_size;
-	q->v = (float *)calloc((size_t)max_size * 2 * 2, sizeof(float));
-	return q;
-}
-void cbuffercf_destroy(cbuffercf q) { if(q) { free(q->v); free(q); } }
-void cbuffercf_reset(cbuffercf q) { q->num_elements = q->read_index = q->write_index = 0; }
-unsigned int cbuffercf_size(cbuffercf q) { return q->num_elements; }
-unsigned int cbuffercf_max_size(cbuffercf q) { return q->max_size; }
-unsigned int cbuffercf_space_available(cbuffercf q) { return q->max_size - q->num_elements; }
-int cbuffercf_write(cbuffercf q, void *v, unsigned int n) {
-	if(n > q->max_size - q->num_elements) return -1;
-	const float *src = (const float *)v;
-	for(unsigned int i = 0; i < n; i++) {
-		unsigned int w = q->write_index;
-		q->v[2 * w] = src[2 * i]; q->v[2 * w + 1] = src[2 * i + 1];
-		q->v[2 * (w + q->max_size)] = src[2 * i]; q->v[2 * (w + q->max_size) + 1] = src[2 * i + 1];
-		q->write_index = (w + 1 == q->max_size) ? 0 : w + 1;
-	}
-	q->num_elements += n;
-	return 0;
-}
-int cbuffercf_read(cbuffercf q, unsigned int n, void **v, unsigned int *num_read) {
-	if(n > q->num_elements) n = q->num_elements;
-	*v = q->v + 2 * (size_t)q->read_index;
-	*num_read = n;
-	return 0;
-}
-int cbuffercf_release(cbuffercf q, unsigned int n) {
-	if(n > q->num_elements) return -1;
-	q->read_index = (q->read_index + n) % q->max_size;
-	q->num_elements -= n;
-	return 0;
-}
-
-}  // extern "C"
 
 // ---- the block --------------------------------------------------------------------------------------------------
 struct gpu_frontend {
 	struct block block;            // must stay first: container_of idiom of fft.c:24 / hfdl.c:596
-	hfdl_b200_frontend_t *fe;
+	int ngpus;
+	std::vector<hfdl_b200_frontend_t *> fe;        // fe[g] owns channels g, g + ngpus, g + 2*ngpus, ...
 	hfdl_b200_geometry_t geom;
 	float *staging; size_t staging_samples;
 	hfdl_gpu_pdu_callback cb; void *cb_user;
@@ -90,7 +57,8 @@ struct gpu_frontend {
 
 static void deliver(gpu_frontend *g) {
 	hfdl_b200_pdu_t p;
-	while(hfdl_b200_pop_pdu(g->fe, &p) == 1) {
+	for(int d = 0; d < g->ngpus; d++)
+	while(hfdl_b200_pop_pdu(g->fe[(size_t)d], &p) == 1) {
 		g->delivered++;
 		if(pdu_decoder_queue_push && hfdl_pdu_metadata_create && octet_string_new) {
 			struct metadata *m = hfdl_pdu_metadata_create();
@@ -110,34 +78,52 @@ static void deliver(gpu_frontend *g) {
 	}
 }
 
+// Consumer side of the one2one ring, as fft_thread runs it (fft.c:38-55) -- but nothing here waits for the GPU: the
+// blocks read from the ring are queued (hfdl_b200_submit) and the PDUs of batches that have finished meanwhile are
+// delivered (hfdl_b200_poll); the ring is drained again while the GPU works.  When the producer pauses, a timed wait
+// picks up the stragglers.  With several GPUs the samples cross PCIe once (to the first GPU) and reach the others
+// over NVLink (hfdl_b200_push_peer).
 static void *gpu_frontend_thread(void *ctx) {
 	struct block *block = (struct block *)ctx;
 	gpu_frontend *g = (gpu_frontend *)block;
 	struct circ_buffer *cb = &block->consumer.in->circ_buffer;
 	const unsigned int isz = (unsigned int)g->geom.input_size;
 	gettimeofday(&g->t_start, NULL);
-	for(;;) {
+	bool ok = true;
+	while(ok) {
 		pthread_mutex_lock(cb->mutex);
 		// the shutdown flag is honoured only when less than one block is buffered (drain, then exit: fft.c:38-47)
-		bool stop = false;
+		bool stop = false, idle = false;
 		while(cbuffercf_size(cb->buf) < isz) {
 			if(block->consumer.in->flags & BLOCK_CONNECTION_SHUTDOWN) { stop = true; break; }
-			pthread_cond_wait(cb->cond, cb->mutex);
+			struct timespec ts;
+			clock_gettime(CLOCK_REALTIME, &ts);
+			ts.tv_nsec += 20 * 1000 * 1000;
+			if(ts.tv_nsec >= 1000000000L) { ts.tv_sec++; ts.tv_nsec -= 1000000000L; }
+			if(pthread_cond_timedwait(cb->cond, cb->mutex, &ts) == ETIMEDOUT) { idle = true; break; }
 		}
 		if(stop) { pthread_mutex_unlock(cb->mutex); break; }
-		unsigned int avail = cbuffercf_size(cb->buf);
-		unsigned int take = (avail / isz) * isz;
-		if(take > g->staging_samples) take = (unsigned int)(g->staging_samples / isz) * isz;
-		void *rp; unsigned int nr;
-		cbuffercf_read(cb->buf, take, &rp, &nr);
-		memcpy(g->staging, rp, (size_t)nr * 2 * sizeof(float));
-		cbuffercf_release(cb->buf, nr);
+		unsigned int nr = 0;
+		if(!idle || cbuffercf_size(cb->buf) >= isz) {
+			unsigned int avail = cbuffercf_size(cb->buf);
+			unsigned int take = (avail / isz) * isz;
+			if(take > g->staging_samples) take = (unsigned int)(g->staging_samples / isz) * isz;
+			void *rp;
+			cbuffercf_read(cb->buf, take, &rp, &nr);
+			memcpy(g->staging, rp, (size_t)nr * 2 * sizeof(float));
+			cbuffercf_release(cb->buf, nr);
+		}
 		pthread_mutex_unlock(cb->mutex);
-		if(hfdl_b200_push_samples(g->fe, g->staging, nr) < 0) { fprintf(stderr, "hfdl_gpu_frontend: GPU processing failed\n"); break; }
-		if(hfdl_b200_flush(g->fe) < 0) break;
+		if(nr > 0) {
+			if(hfdl_b200_push_samples(g->fe[0], g->staging, nr) < 0) ok = false;
+			for(int d = 1; d < g->ngpus && ok; d++) if(hfdl_b200_push_peer(g->fe[(size_t)d], g->fe[0]) < 0) ok = false;
+			for(int d = 0; d < g->ngpus && ok; d++) if(hfdl_b200_submit(g->fe[(size_t)d]) < 0) ok = false;
+		}
+		for(int d = 0; d < g->ngpus && ok; d++) if(hfdl_b200_poll(g->fe[(size_t)d]) < 0) ok = false;
+		if(!ok) { fprintf(stderr, "hfdl_gpu_frontend: GPU processing failed\n"); break; }
 		deliver(g);
 	}
-	hfdl_b200_flush(g->fe);
+	for(int d = 0; d < g->ngpus; d++) hfdl_b200_flush(g->fe[(size_t)d]);
 	deliver(g);
 	block->running = false;
 	return NULL;
@@ -145,16 +131,44 @@ static void *gpu_frontend_thread(void *ctx) {
 
 extern "C" {
 
-struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_hz, const int32_t *freqs_hz, int32_t nfreq, int32_t device) {
-	gpu_frontend *g = (gpu_frontend *)calloc(1, sizeof(*g));
-	hfdl_b200_config_t cfg;
-	memset(&cfg, 0, sizeof(cfg));
-	cfg.sample_rate = sample_rate; cfg.centerfreq_hz = centerfreq_hz; cfg.freqs_hz = freqs_hz; cfg.nfreq = nfreq;
-	cfg.sample_format = HFDL_B200_SFMT_CF32; cfg.device = device; cfg.capture_channel = -1;
-	if(hfdl_b200_create(&g->fe, &cfg) != 0) { fprintf(stderr, "Error in hfdl_gpu_frontend_create()\n"); free(g); return NULL; }
-	hfdl_b200_get_geometry(g->fe, &g->geom);
+struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_hz, const int32_t *freqs_hz, int32_t nfreq, int32_t device, int32_t ngpus) {
+	if(!cbuffercf_size || !cbuffercf_read || !cbuffercf_release) {
+		fprintf(stderr, "hfdl_gpu_frontend_create: the host program does not export liquid-dsp's cbuffercf_size/read/release\n");
+		return NULL;
+	}
+	if(ngpus < 1) ngpus = 1;
+	if(ngpus > nfreq) ngpus = nfreq;
+	if(device < 0 || device + ngpus > hfdl_b200_device_count()) {
+		fprintf(stderr, "hfdl_gpu_frontend_create: devices %d..%d requested, %d present\n", device, device + ngpus - 1, hfdl_b200_device_count());
+		return NULL;
+	}
+	gpu_frontend *g = new gpu_frontend();
+	memset(&g->block, 0, sizeof(g->block));
+	g->ngpus = ngpus; g->staging = NULL; g->cb = NULL; g->cb_user = NULL; g->delivered = 0;
+	for(int d = 0; d < ngpus; d++) {
+		std::vector<int32_t> mine;
+		for(int k = d; k < nfreq; k += ngpus) mine.push_back(freqs_hz[k]);
+		hfdl_b200_config_t cfg;
+		memset(&cfg, 0, sizeof(cfg));
+		cfg.sample_rate = sample_rate; cfg.centerfreq_hz = centerfreq_hz; cfg.freqs_hz = mine.data(); cfg.nfreq = (int32_t)mine.size();
+		cfg.sample_format = HFDL_B200_SFMT_CF32; cfg.device = device + d; cfg.capture_channel = -1;
+		hfdl_b200_frontend_t *fe = NULL;
+		if(hfdl_b200_create(&fe, &cfg) != 0) {
+			fprintf(stderr, "Error in hfdl_gpu_frontend_create()\n");
+			for(auto q : g->fe) hfdl_b200_destroy(q);
+			delete g;
+			return NULL;
+		}
+		g->fe.push_back(fe);
+	}
+	hfdl_b200_get_geometry(g->fe[0], &g->geom);
 	g->staging_samples = (size_t)g->geom.input_size * 8;
-	if(cudaMallocHost((void **)&g->staging, g->staging_samples * 2 * sizeof(float)) != cudaSuccess) { hfdl_b200_destroy(g->fe); free(g); return NULL; }
+	cudaSetDevice(device);
+	if(cudaMallocHost((void **)&g->staging, g->staging_samples * 2 * sizeof(float)) != cudaSuccess) {
+		for(auto q : g->fe) hfdl_b200_destroy(q);
+		delete g;
+		return NULL;
+	}
 	g->block.consumer.type = CONSUMER_SINGLE;
 	g->block.consumer.min_ru = (size_t)g->geom.fft_size;
 	g->block.producer.type = PRODUCER_NONE;
@@ -165,18 +179,29 @@ struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_h
 void hfdl_gpu_frontend_destroy(struct block *b) {
 	if(!b) return;
 	gpu_frontend *g = (gpu_frontend *)b;
-	hfdl_b200_destroy(g->fe);
+	for(auto q : g->fe) hfdl_b200_destroy(q);
 	cudaFreeHost(g->staging);
-	free(g);
+	delete g;
 }
 
-void hfdl_gpu_frontend_print_summary(struct block *b) { if(b) hfdl_b200_print_summary(((gpu_frontend *)b)->fe); }
+void hfdl_gpu_frontend_print_summary(struct block *b) {
+	if(!b) return;
+	for(auto q : ((gpu_frontend *)b)->fe) hfdl_b200_print_summary(q);
+}
 
 int32_t hfdl_gpu_frontend_noise_floor_db(struct block *b, int32_t channel, float *db) {
 	float lvl;
-	if(!b || !db || hfdl_b200_channel_noise_floor(((gpu_frontend *)b)->fe, channel, &lvl)) return -1;
+	if(!b || !db || channel < 0) return -1;
+	gpu_frontend *g = (gpu_frontend *)b;
+	if(hfdl_b200_channel_noise_floor(g->fe[(size_t)(channel % g->ngpus)], channel / g->ngpus, &lvl)) return -1;
 	*db = 20.0f * log10f(lvl);
 	return 0;
+}
+
+int32_t hfdl_gpu_frontend_counters(struct block *b, int32_t channel, hfdl_b200_counters_t *out) {
+	if(!b || !out || channel < 0) return -1;
+	gpu_frontend *g = (gpu_frontend *)b;
+	return hfdl_b200_channel_counters(g->fe[(size_t)(channel % g->ngpus)], channel / g->ngpus, out);
 }
 
 void hfdl_gpu_frontend_set_pdu_callback(struct block *b, hfdl_gpu_pdu_callback cb, void *user) {

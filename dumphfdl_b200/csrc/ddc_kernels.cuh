@@ -560,7 +560,8 @@ struct ChanArgs {
 	FftPlan pl;
 	int M, lgM, scrap, post_dec, out_per_block;
 	long long bb_stride;
-	long long out_index0;      // global output-sample index of (block 0, output 0)
+	long long out_index0;      // global output-sample index of (block 0 of the batch, output 0)
+	int block0;                // first block of this launch within the batch (sub-batches)
 	float inv_norm;            // 1/(pre_decimation*M) = 1/N (fastddc.c:193)
 };
 
@@ -579,9 +580,9 @@ __global__ void __launch_bounds__(HFDL_FFT_THREADS) chan_extract(ChanArgs a) {
 	__syncthreads();
 	smem_fft(s, a.lgM, 1, 1, a.tw, 1);
 	const double cyc = 0.5 * (double)a.dsa_rate[c];     // cycles of phase per output sample
-	cf *out = a.bb + (long long)c * a.bb_stride + HFDL_RS_HIST + (long long)b * a.out_per_block;
+	cf *out = a.bb + (long long)c * a.bb_stride + HFDL_RS_HIST + (long long)(b + a.block0) * a.out_per_block;
 	for(int j = threadIdx.x; j < a.out_per_block; j += blockDim.x) {
-		long long g = a.out_index0 + (long long)b * a.out_per_block + j;
+		long long g = a.out_index0 + (long long)(b + a.block0) * a.out_per_block + j;
 		double fr = cyc * (double)g;
 		fr -= floor(fr);
 		float sn, cs;

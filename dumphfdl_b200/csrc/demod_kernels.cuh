@@ -75,7 +75,7 @@ struct DemodState {                                  // loop_kernel state carrie
 	unsigned bitmask, symsync_out_idx;
 	float freq_err_hz, signal_level, noise_floor;
 	unsigned nf_clk; float frame_symbol_cnt;
-	int st_a1, st_a2, st_m1, st_frames;
+	int st_a1, st_a2, st_m1, st_frames, st_m1_fail;      // st_m1_fail: statsd demod.preamble.errors.M1_not_found (hfdl.c:840)
 };
 
 struct FrameRec {          // one completed frame handed from loop_kernel to fec_kernel
@@ -91,6 +91,11 @@ struct PduRec {            // what the host turns into hfdl_pdu_metadata + octet
 	float freq_err_hz, signal_level, noise_floor;
 	unsigned long long sample_cnt_a2, sample_cnt_end;
 	int train_bits_bad, train_bits_total;
+	// front parser (pdu.c:104,123, mpdu.c:56-134, spdu.c:55-64, lpdu.c:124-150): what the statsd counters count
+	int frame_status;          // 0 good, 1 bad_fcs, 2 too_short
+	int direction;             // 1 air2gnd (downlink MPDU), 0 gnd2air (uplink MPDU / SPDU); valid when frame_status == 0
+	int lpdus_processed, lpdus_good, lpdus_bad_fcs, lpdus_too_short;
+	unsigned long long lpdu_good_mask;     // bit j: the j-th LPDU handed to lpdu_parse had a good FCS
 	unsigned char octets[HFDL_MAX_PDU + 3];
 };
 
@@ -216,16 +221,12 @@ __global__ void __launch_bounds__(256) bank_kernel(BankArgs a) {
 	}
 }
 
-// carries the tails of the per-channel work streams in front of the next batch
-__global__ void demod_carry(cf *agc_out, long long agc_stride, cf *mfo, long long mfo_stride, long long n_new) {
+// carries the tails of the per-channel work streams of the previous batch (set "src", n_prev samples) in front of the
+// arrays of the next batch (set "dst").  With n_prev = 0 (first batch) the zeroed history of the other set is copied.
+__global__ void demod_carry(const cf *agc_src, cf *agc_dst, long long agc_stride, const cf *mfo_src, cf *mfo_dst, long long mfo_stride, long long n_prev) {
 	int c = blockIdx.x, t = threadIdx.x;
-	cf *ra = agc_out + (long long)c * agc_stride, *rm = mfo + (long long)c * mfo_stride;
-	cf va = make_float2(0.f, 0.f), vm = va;
-	if(t < HFDL_AGC_HIST) va = ra[n_new + t];
-	if(t < HFDL_MFO_HIST) vm = rm[n_new + t];
-	__syncthreads();
-	if(t < HFDL_AGC_HIST) ra[t] = va;
-	if(t < HFDL_MFO_HIST) rm[t] = vm;
+	if(t < HFDL_AGC_HIST) agc_dst[(long long)c * agc_stride + t] = agc_src[(long long)c * agc_stride + n_prev + t];
+	if(t < HFDL_MFO_HIST) mfo_dst[(long long)c * mfo_stride + t] = mfo_src[(long long)c * mfo_stride + n_prev + t];
 }
 
 #include "loop_kernel.cuh"     // K8b-K11: timing loop, Costas, equaliser, slicer, framer
@@ -258,24 +259,89 @@ __device__ __forceinline__ int fcs_check(const unsigned char *buf, unsigned hdr_
 	unsigned rx = (unsigned)buf[hdr_len] | ((unsigned)buf[hdr_len + 1] << 8);
 	return rx == crc;
 }
-__device__ __forceinline__ int pdu_crc_good(const unsigned char *buf, unsigned len) {   // pdu.c:104, mpdu.c:56-85, spdu.c:55-64
-	if(len < 1) return 0;
-	if(buf[0] & 1u) {
-		unsigned hdr_len;
-		if(buf[0] & 0x2u) hdr_len = 6 + ((buf[0] >> 2) & 0xFu);
-		else {
-			unsigned ac = ((buf[0] & 0x70u) >> 4) + 1;
-			hdr_len = 2;
-			for(unsigned i = 0; i < ac; i++) {
-				if(len < hdr_len + 2) return 0;
-				hdr_len += 2 + (buf[hdr_len + 1] >> 4);
+// Front parser of one PDU, run by a whole warp: lane 0 walks the MPDU header exactly like mpdu_parse /
+// parse_lpdu_list (mpdu.c:56-134,136-159) and lists the LPDUs in shared memory; the lanes then check the LPDU frame
+// check sequences in parallel (lpdu_parse, lpdu.c:124-150).  SPDUs carry no LPDUs (spdu.c:55-64).
+struct LpduDesc { unsigned short off, len; };
+__device__ __forceinline__ void pdu_front_parse(const unsigned char *buf, unsigned len, PduRec *out, LpduDesc *list /* smem [64] */, int *s_n, int lane) {
+	int status = 0, dir = 0;
+	if(lane == 0) {
+		int n = 0;
+		if(len < 1) status = 2;
+		else if(buf[0] & 1u) {                                   // IS_MPDU, pdu.c:104
+			unsigned hdr_len, lpdu_cnt = 0, ac = 0;
+			if(buf[0] & 0x2u) { dir = 1; lpdu_cnt = (buf[0] >> 2) & 0xFu; hdr_len = 6 + lpdu_cnt; }
+			else {
+				ac = ((buf[0] & 0x70u) >> 4) + 1;
+				hdr_len = 2;
+				for(unsigned i = 0; i < ac && status == 0; i++) {
+					if(len < hdr_len + 2) { status = 2; break; }
+					lpdu_cnt = buf[hdr_len + 1] >> 4;
+					hdr_len += 2 + lpdu_cnt;
+				}
 			}
+			if(status == 0 && len < hdr_len + 2) status = 2;
+			if(status == 0 && !fcs_check(buf, hdr_len)) status = 1;
+			if(status == 0) {
+				unsigned dp = hdr_len + 2;                          // first data octet of the first LPDU
+				if(dir == 1) {
+					unsigned hp = 6;
+					for(unsigned j = 0; j < lpdu_cnt; j++) {
+						unsigned ll = (unsigned)buf[hp] + 1u;
+						if(dp + ll > len) break;                    // truncated: parse_lpdu_list returns -1
+						if(n < 64) { list[n].off = (unsigned short)dp; list[n].len = (unsigned short)ll; n++; }
+						dp += ll; hp++;
+					}
+				} else {
+					unsigned hp = 2;
+					bool stop = false;
+					for(unsigned i = 0; i < ac && !stop; i++) {
+						hp++;                                       // aircraft id
+						unsigned cnt = (buf[hp++] >> 4) & 0xFu;
+						for(unsigned j = 0; j < cnt; j++) {
+							unsigned ll = (unsigned)buf[hp + j] + 1u;
+							if(dp + ll > len) { stop = true; break; }
+							if(n < 64) { list[n].off = (unsigned short)dp; list[n].len = (unsigned short)ll; n++; }
+							dp += ll;
+						}
+						hp += cnt;
+					}
+				}
+			}
+		} else {
+			if(len < 66) status = 2;                              // spdu.c:12,55-59
+			else if(!fcs_check(buf, 64u)) status = 1;
 		}
-		if(len < hdr_len + 2) return 0;
-		return fcs_check(buf, hdr_len);
+		*s_n = n;
 	}
-	if(len < 66) return 0;
-	return fcs_check(buf, 64u);
+	__syncwarp();
+	const int n = *s_n;
+	unsigned long long good = 0ull; int ngood = 0, nbad = 0, nshort = 0;
+	for(int j0 = 0; j0 < n; j0 += 32) {
+		const int j = j0 + lane;
+		int st = -1;                                                // -1 none, 0 good, 1 bad fcs, 2 too short
+		if(j < n) {
+			const unsigned ll = list[j].len;
+			if(ll < 3) st = 2;                                      // lpdu.c:137-142
+			else st = fcs_check(buf + list[j].off, ll - 2) ? 0 : 1;
+		}
+		const unsigned mg = __ballot_sync(0xffffffffu, st == 0), mb = __ballot_sync(0xffffffffu, st == 1), ms = __ballot_sync(0xffffffffu, st == 2);
+		good |= (unsigned long long)mg << j0;
+		ngood += __popc(mg); nbad += __popc(mb); nshort += __popc(ms);
+	}
+	if(lane == 0) {
+		out->frame_status = status; out->direction = dir;
+		out->lpdus_processed = n; out->lpdus_good = ngood; out->lpdus_bad_fcs = nbad; out->lpdus_too_short = nshort;
+		out->lpdu_good_mask = good;
+		out->crc_good = status == 0;
+	}
+}
+
+// stage entry hfdl_b200_pdu_front_parse: one warp per PDU record (octets + len already in place)
+__global__ void __launch_bounds__(32) front_kernel(PduRec *pdus, int n) {
+	__shared__ LpduDesc list[64];
+	__shared__ int s_n;
+	if((int)blockIdx.x < n) pdu_front_parse(pdus[blockIdx.x].octets, (unsigned)pdus[blockIdx.x].len, &pdus[blockIdx.x], list, &s_n, threadIdx.x);
 }
 
 __global__ void __launch_bounds__(32) fec_kernel(FecArgs a) {
@@ -416,6 +482,13 @@ __global__ void __launch_bounds__(32) fec_kernel(FecArgs a) {
 		out->freq_err_hz = fr.freq_err_hz; out->signal_level = fr.signal_level; out->noise_floor = fr.noise_floor;
 		out->sample_cnt_a2 = fr.sample_cnt_a2; out->sample_cnt_end = fr.sample_cnt_end;
 		out->train_bits_bad = fr.train_bits_bad; out->train_bits_total = fr.train_bits_total;
-		out->crc_good = pdu_crc_good(out->octets, (unsigned)out_octets);
+	}
+	__syncwarp();
+	__threadfence_block();
+	{
+		// the decisions are dead: the front parser's LPDU list overlays them
+		LpduDesc *list = reinterpret_cast<LpduDesc *>(sm + HFDL_FEC_VIN_MAX);
+		int *s_n = reinterpret_cast<int *>(sm + HFDL_FEC_VIN_MAX + 64 * sizeof(LpduDesc));
+		pdu_front_parse(out->octets, (unsigned)out_octets, out, list, s_n, lane);
 	}
 }

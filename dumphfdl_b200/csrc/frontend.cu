@@ -7,6 +7,7 @@
 #include <deque>
 #include <string>
 #include <thread>
+#include <mutex>
 #include <algorithm>
 #include <string.h>
 #include <stdlib.h>
@@ -25,9 +26,6 @@ enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_AGC, KC_BANK, KC_LO
 const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "agc", "bank", "loop", "fec" };
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
-#ifndef HFDL_NSUB
-#define HFDL_NSUB 8        // sub-ranges per batch for the agc/bank || loop overlap
-#endif
 
 FftPlan make_plan(int N) {
 	FftPlan p;
@@ -99,12 +97,17 @@ struct hfdl_b200_frontend {
 	FftPlan plan;
 	int C = 0, Bmax = 0, sfmt = 0, bps = 0, out_per_block = 0;
 	float resamp_rate = 0;
-	// streams: front (H2D, FFT, channeliser, resampler) | agc/bank | loop | fec + D2H.  Batch i+1's front, agc and
-	// bank stages run while batch i is still in the loop kernels; fec of batch i runs beside loop of batch i+1.
-	cudaStream_t stream = nullptr, stream2 = nullptr, st_loop = nullptr, st_fec = nullptr;
-	cudaEvent_t ev_front[2] = { nullptr, nullptr }, ev_agc_done[2] = { nullptr, nullptr }, ev_fec_done[2] = { nullptr, nullptr };
-	cudaEvent_t ev_sub[2][HFDL_NSUB] = { { nullptr } }, ev_loop[2][HFDL_NSUB] = { { nullptr } }, ev_h2d = nullptr;
-	struct Flight { bool busy = false; int nsub = 0; long long s0[HFDL_NSUB], s1[HFDL_NSUB]; } flight[2];
+	// streams: front (H2D, FFT, channeliser, resampler) | agc + bank | loop | fec + D2H.  One launch per stage per batch;
+	// the stages of consecutive batches overlap (front/agc/bank of batch i+1 beside loop of batch i beside fec of i-1).
+	cudaStream_t stream = nullptr, stream2 = nullptr, st_loop = nullptr, st_fec = nullptr, st_stats = nullptr;
+	cudaEvent_t ev_front[2] = { nullptr, nullptr }, ev_bank[2] = { nullptr, nullptr }, ev_loop[2] = { nullptr, nullptr }, ev_fec_done[2] = { nullptr, nullptr };
+	cudaEvent_t ev_h2d = nullptr;
+	struct Flight { bool busy = false; } flight[2];
+	std::recursive_mutex mtx;       // every public entry point: the frontend may be driven and queried from different threads
+	bool peer_enabled = false;
+	bool failed = false;            // a CUDA call failed mid-pipeline: every later call returns -1
+	int Bsub = 1;                   // blocks per FFT sub-batch (intermediate spectra stay in L2)
+	long long n_out_prev = 0;       // resampled samples of the previous batch (carry source)
 	long long batch_seq = 0;        // batches enqueued so far; set p = batch_seq & 1
 	int nslots = HFDL_FRAME_SLOTS_MIN;
 	FftEngine fft;
@@ -115,7 +118,8 @@ struct hfdl_b200_frontend {
 	cf *d_bb = nullptr; long long bb_stride = 0;
 	cf *d_rs[2] = { nullptr, nullptr }; long long rs_stride = 0; float *d_rs_h = nullptr;
 	DemodTables *d_tab = nullptr; DemodState *d_state = nullptr; AgcState *d_agc_state = nullptr; cf *d_datasym = nullptr;
-	cf *d_agc = nullptr, *d_mfo = nullptr, *d_bank = nullptr; float *d_lvl = nullptr; long long agc_stride = 0, mfo_stride = 0;
+	cf *d_agc[2] = { nullptr, nullptr }, *d_mfo[2] = { nullptr, nullptr }, *d_bank[2] = { nullptr, nullptr }; float *d_lvl[2] = { nullptr, nullptr };
+	long long agc_stride = 0, mfo_stride = 0;      // work arrays of the demodulator stages, one set per batch parity
 	long long cap_n = 0;            // AGC/MF checkpoint samples captured so far
 	FrameRec *d_frames[2] = { nullptr, nullptr }; int *d_nframes[2] = { nullptr, nullptr }; PduRec *d_pdus[2] = { nullptr, nullptr }; int max_frames = 0;
 	cf *d_cap_agc = nullptr, *d_cap_mf = nullptr, *d_cap_eq = nullptr; int *d_cap_cnt = nullptr;
@@ -126,8 +130,10 @@ struct hfdl_b200_frontend {
 	long long fed = 0;              // samples pushed so far (host-fed path)
 	long long blocks_done = 0;      // overlap-save blocks processed
 	unsigned long long rs_phi0 = 0; unsigned rs_step = 0;
-	int last_nblocks = 0, last_nout = 0;
+	int last_nblocks = 0, last_nout = 0, last_sub_blocks = 0, debug_mode = 0;
 	std::deque<hfdl_b200_pdu_t> pduq;
+	struct ChanTally { long long processed = 0, good = 0, bad_fcs = 0, too_short = 0, air2gnd = 0, gnd2air = 0, lpdus_processed = 0, lpdus_good = 0, lpdus_bad = 0, lpdus_short = 0; };
+	std::vector<ChanTally> tally;
 	long long launches = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	bool profiling = false;
@@ -136,6 +142,22 @@ struct hfdl_b200_frontend {
 };
 
 namespace {
+
+// Entry-point guard: serialises the public calls on one frontend (the block thread pushes while a stats thread reads)
+// and makes the frontend's device current for the calling host thread (the current device is per thread), restoring
+// the caller's device afterwards.
+struct ApiGuard {
+	std::unique_lock<std::recursive_mutex> lk;
+	int prev = -1;
+	bool ok = true;
+	explicit ApiGuard(hfdl_b200_frontend *fe) : lk(fe->mtx) {
+		if(cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+		if(prev != fe->cfg.device) { if(cudaSetDevice(fe->cfg.device) != cudaSuccess) ok = false; }
+		else prev = -1;
+	}
+	~ApiGuard() { if(prev >= 0) cudaSetDevice(prev); }
+};
+#define HFDL_API(fe, errval) if(!(fe)) return errval; ApiGuard guard_(fe); if(!guard_.ok || (fe)->failed) return errval
 
 inline void prof_begin(hfdl_b200_frontend *fe, int cls, ProfRec &r) {
 	r.cls = -1;
@@ -238,7 +260,7 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 
 int bytes_per_sample(int sfmt) { return sfmt == HFDL_SFMT_CF32 ? 8 : (sfmt == HFDL_SFMT_CS16 ? 4 : 2); }
 
-void to_pdu(const hfdl_b200_frontend *fe, const PduRec &r, hfdl_b200_pdu_t &p) {    // dispatch_pdu, hfdl.c:1058-1080
+void to_pdu(hfdl_b200_frontend *fe, const PduRec &r, hfdl_b200_pdu_t &p) {    // dispatch_pdu, hfdl.c:1058-1080
 	static const int ar[8] = { 1, 1, 2, 3, 1, 1, 2, 3 }, cr[8] = { 4, 2, 2, 2, 4, 2, 2, 2 };
 	memset(&p, 0, sizeof(p));
 	p.version = 1;
@@ -255,13 +277,27 @@ void to_pdu(const hfdl_b200_frontend *fe, const PduRec &r, hfdl_b200_pdu_t &p) {
 	p.signal_level = r.signal_level; p.noise_floor_lin = r.noise_floor;
 	p.len = r.len;
 	memcpy(p.octets, r.octets, (size_t)r.len);
+	p.frame_status = r.frame_status; p.direction = r.direction;
+	p.lpdus_processed = r.lpdus_processed; p.lpdus_good = r.lpdus_good; p.lpdus_bad_fcs = r.lpdus_bad_fcs; p.lpdus_too_short = r.lpdus_too_short;
+	p.lpdu_good_mask = r.lpdu_good_mask;
+	hfdl_b200_frontend::ChanTally &t = fe->tally[(size_t)r.channel];      // the statsd counters of pdu.c / mpdu.c / spdu.c / lpdu.c
+	t.processed++;
+	if(r.frame_status == 0) { t.good++; if(r.direction) t.air2gnd++; else t.gnd2air++; }
+	else if(r.frame_status == 1) t.bad_fcs++;
+	else t.too_short++;
+	t.lpdus_processed += r.lpdus_processed; t.lpdus_good += r.lpdus_good; t.lpdus_bad += r.lpdus_bad_fcs; t.lpdus_short += r.lpdus_too_short;
 }
 
-// one group of nb <= Bmax blocks: FFT -> channel extract -> resample -> demod -> FEC -> PDUs to host
-// Results of one finished batch: PDU records of set q -> host queue.
-int collect_batch(hfdl_b200_frontend *fe, int q) {
+// Results of one finished batch: PDU records of set q -> host queue.  wait = false: only if the batch has finished.
+int collect_batch(hfdl_b200_frontend *fe, int q, bool wait = true) {
 	if(!fe->flight[q].busy) return 0;
-	CK(cudaEventSynchronize(fe->ev_fec_done[q]));
+	if(!wait) {
+		cudaError_t e = cudaEventQuery(fe->ev_fec_done[q]);
+		if(e == cudaErrorNotReady) return 0;
+		if(e != cudaSuccess) { fprintf(stderr, "hfdl_b200: CUDA error '%s' while polling\n", cudaGetErrorString(e)); return -1; }
+	} else {
+		CK(cudaEventSynchronize(fe->ev_fec_done[q]));
+	}
 	fe->flight[q].busy = false;
 	int nfr = *fe->h_nframes[q];
 	if(nfr > fe->max_frames) {
@@ -295,37 +331,42 @@ int drain(hfdl_b200_frontend *fe) {
 	return 0;
 }
 
-// One batch of nb overlap-save blocks, fully asynchronous.  Stages and the stream each runs on:
-//   front  (stream)   FFT passes, chan_extract, resamp -> d_rs[p]
-//   agc    (stream2)  per sub-range: agc_kernel, bank_kernel            (work arrays shared by consecutive batches)
-//   loop   (st_loop)  per sub-range: loop_kernel                        (the latency-bound stage: sets the pace)
+// One batch of nb overlap-save blocks, fully asynchronous; ONE launch per demodulator stage per batch.  Stages and
+// the stream each runs on:
+//   front  (stream)   per sub-batch of Bsub blocks: FFT passes + chan_extract (the intermediate spectra of a sub-batch
+//                     fit the L2: only the raw samples come from HBM); then resamp -> d_rs[p]
+//   agc    (stream2)  demod_carry (history from set p^1), agc_kernel, bank_kernel -> work set p
+//   loop   (st_loop)  loop_kernel over the whole batch                  (the latency-bound stage: sets the pace)
 //   fec    (st_fec)   fec_kernel, D2H of the PDU records of set p
-// Hazards between batch i and i+1 are ordered with events: the agc stage of a sub-range waits for the loop launches
-// of the previous batch that still read those samples; the resampler waits until the agc stage of batch i-2 has
-// read d_rs[p]; the first loop launch waits until fec of batch i-2 has released the frame records of set p.
+// Consecutive batches use alternate sets (p = batch parity) of every buffer a later stage reads, so front + agc + bank
+// of batch i+1 run beside loop of batch i and fec of batch i-1; events order the reuse of a set two batches later.
 // The host collects the PDUs of batch i-1 after it has enqueued batch i.
-int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
+int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 	const int p = (int)(fe->batch_seq & 1);
-	if(collect_batch(fe, p)) return -1;          // batch i-2 (normally collected long ago)
+	if(collect_batch(fe, p)) return -1;          // batch i-2 (normally collected long ago): every set-p buffer is free
 	cudaStream_t st = fe->stream, st2 = fe->stream2, stl = fe->st_loop, stf = fe->st_fec;
 	const auto &g = fe->g;
-	hfdl_b200_frontend::Flight &prev = fe->flight[p ^ 1];
 	hfdl_b200_frontend::Flight &cur = fe->flight[p];
-	if(run_fft(fe, fe->fft, fe->plan, src, fe->d_work, fe->d_spec, nb, st)) return -1;
 	ProfRec pr;
-	{
+	for(int b0 = 0; b0 < nb; b0 += fe->Bsub) {
+		const int nsb = std::min(fe->Bsub, nb - b0);
+		RawSource src = src0;
+		src.pos0 = src0.pos0 + (long long)b0 * src0.block_stride;
+		if(run_fft(fe, fe->fft, fe->plan, src, fe->d_work, fe->d_spec, nsb, st)) return -1;
 		ChanArgs a;
 		a.work = fe->plan.natural ? fe->d_spec : fe->d_work; a.tapslice = fe->d_tapslice; a.offsetbin = fe->d_offsetbin; a.dsa_rate = fe->d_dsa_rate;
 		a.bb = fe->d_bb; a.tw = fe->fft.d_tw; a.pl = fe->plan;
 		a.M = g.fft_inv_size; a.lgM = hfdl_ilog2(g.fft_inv_size); a.scrap = g.scrap; a.post_dec = g.post_decimation;
 		a.out_per_block = fe->out_per_block; a.bb_stride = fe->bb_stride;
 		a.out_index0 = fe->blocks_done * (long long)fe->out_per_block;
+		a.block0 = b0;
 		a.inv_norm = 1.0f / (float)(g.pre_decimation * g.fft_inv_size);
 		prof_begin(fe, KC_CHAN, pr);
-		HFDL_LAUNCH(chan_extract, dim3((unsigned)fe->C, (unsigned)nb), dim3(HFDL_FFT_THREADS), sizeof(cf) * (size_t)a.M, st, a);
+		HFDL_LAUNCH(chan_extract, dim3((unsigned)fe->C, (unsigned)nsb), dim3(HFDL_FFT_THREADS), sizeof(cf) * (size_t)a.M, st, a);
 		prof_end(fe, pr);
 		fe->launches++;
 	}
+	fe->last_sub_blocks = nb - ((nb - 1) / fe->Bsub) * fe->Bsub;      // blocks of the last sub-batch (still in d_spec)
 	const long long n_in = (long long)nb * fe->out_per_block;
 	int n_out = 0;
 	{
@@ -335,7 +376,7 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 		a.bb = fe->d_bb; a.bb_stride = fe->bb_stride; a.rs = fe->d_rs[p]; a.rs_stride = fe->rs_stride; a.h = fe->d_rs_h;
 		a.phi0 = fe->rs_phi0; a.step = fe->rs_step; a.n_out = n_out;
 		if(n_out > 0) {
-			CK(cudaStreamWaitEvent(st, fe->ev_agc_done[p], 0));          // agc of batch i-2 has read d_rs[p]
+			CK(cudaStreamWaitEvent(st, fe->ev_bank[p], 0));              // agc of batch i-2 has read d_rs[p]
 			prof_begin(fe, KC_RESAMP, pr);
 			HFDL_LAUNCH(resamp_kernel, dim3((unsigned)((n_out + 255) / 256), (unsigned)fe->C), dim3(256), 0, st, a);
 			prof_end(fe, pr);
@@ -346,81 +387,56 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 		fe->launches++;
 	}
 	CK(cudaEventRecord(fe->ev_front[p], st));
-	// frame records of set p: free once fec of batch i-2 is done
-	CK(cudaStreamWaitEvent(stl, fe->ev_fec_done[p], 0));
-	CK(cudaMemsetAsync(fe->d_nframes[p], 0, sizeof(int), stl));
-	cur.nsub = 0;
+	// ---- agc + bank: work set p (free once loop of batch i-2 is done)
+	CK(cudaStreamWaitEvent(st2, fe->ev_front[p], 0));
+	CK(cudaStreamWaitEvent(st2, fe->ev_loop[p], 0));
+	// the last HIST samples of the previous batch's AGC / matched-filter outputs (set p^1) go in front of set p
+	HFDL_LAUNCH(demod_carry, dim3((unsigned)fe->C), dim3(64), 0, st2, fe->d_agc[p ^ 1], fe->d_agc[p], fe->agc_stride, fe->d_mfo[p ^ 1], fe->d_mfo[p], fe->mfo_stride, fe->n_out_prev);
+	fe->launches++;
 	if(n_out > 0) {
-		// The demodulator is a feed-forward chain agc -> bank -> loop whose first and last stage are latency-bound
-		// recurrences: the batch is split into sub-ranges so that agc/bank of later sub-ranges (and of the next batch)
-		// run while loop_kernel works on earlier ones (both recurrences keep their state in HBM between launches).
-		const int nsub = std::max(1, std::min(HFDL_NSUB, n_out / 1024));     // sub-ranges of >= 1024 samples
-		CK(cudaStreamWaitEvent(st2, fe->ev_front[p], 0));
-		int first_loop = -1, last_loop = -1;
-		for(int i = 0; i < nsub; i++) {
-			const long long s0 = (long long)n_out * i / nsub, s1 = (long long)n_out * (i + 1) / nsub;
-			const int ns = (int)(s1 - s0);
-			if(ns <= 0) continue;
-			// samples [s0, s1) of the shared work arrays (and the HIST samples in front of the arrays, written by
-			// demod_carry) are still read by the previous batch's loop launches that cover [s0 - HIST, s1)
-			if(prev.busy) {
-				int need = -1;
-				for(int j = 0; j < prev.nsub; j++)
-					if(prev.s0[j] - HFDL_AGC_HIST < s1 + HFDL_AGC_HIST && prev.s1[j] > s0 - HFDL_AGC_HIST) need = j;
-				if(i == 0 && prev.nsub > 0 && need < 0) need = 0;
-				if(need >= 0) CK(cudaStreamWaitEvent(st2, fe->ev_loop[p ^ 1][need], 0));
-			}
-			AgcArgs a;
-			a.rs = fe->d_rs[p] + s0; a.rs_stride = fe->rs_stride; a.n_samples = ns; a.state = fe->d_agc_state;
-			a.agc_out = fe->d_agc + s0; a.agc_stride = fe->agc_stride; a.lvl = fe->d_lvl + s0; a.lvl_stride = fe->rs_stride;
-			prof_begin2(fe, KC_AGC, pr, st2);
-			HFDL_LAUNCH(agc_kernel, dim3((unsigned)fe->C), dim3(32), 0, st2, a);
-			prof_end2(fe, pr, st2);
-			BankArgs b;
-			b.agc_out = fe->d_agc + s0; b.agc_stride = fe->agc_stride; b.n_samples = ns; b.mfo = fe->d_mfo + s0; b.mfo_stride = fe->mfo_stride;
-			b.bank = fe->d_bank + s0 * 32; b.bank_stride = fe->rs_stride; b.tab = fe->d_tab;
-			prof_begin2(fe, KC_BANK, pr, st2);
-			HFDL_LAUNCH(bank_kernel, dim3((unsigned)((ns + HFDL_BANK_TILE - 1) / HFDL_BANK_TILE), (unsigned)fe->C), dim3(256), 0, st2, b);
-			prof_end2(fe, pr, st2);
-			CK(cudaEventRecord(fe->ev_sub[p][i], st2));
-			CK(cudaStreamWaitEvent(stl, fe->ev_sub[p][i], 0));
-			LoopArgs l;
-			l.bank = fe->d_bank + s0 * 32; l.bank_stride = fe->rs_stride; l.mfo = fe->d_mfo + s0; l.mfo_stride = fe->mfo_stride;
-			l.lvl = fe->d_lvl + s0; l.lvl_stride = fe->rs_stride; l.n_samples = ns;
-			l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym; l.nslots = fe->nslots;
-			l.frames = fe->d_frames[p]; l.nframes = fe->d_nframes[p]; l.max_frames = fe->max_frames;
-			l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
-			{ const char *dbg = getenv("HFDL_B200_DEBUG"); l.debug_mode = dbg ? atoi(dbg) : 0; }
-			l.dbg_cycles = fe->d_dbg;
-			prof_begin2(fe, KC_LOOP, pr, stl);
-			HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(HFDL_LK_THREADS), HFDL_LK_SMEM, stl, l);
-			prof_end2(fe, pr, stl);
-			CK(cudaEventRecord(fe->ev_loop[p][cur.nsub], stl));
-			cur.s0[cur.nsub] = s0; cur.s1[cur.nsub] = s1; cur.nsub++;
-			if(first_loop < 0) first_loop = cur.nsub - 1;
-			last_loop = cur.nsub - 1;
-			fe->launches += 3;
-		}
+		AgcArgs a;
+		a.rs = fe->d_rs[p]; a.rs_stride = fe->rs_stride; a.n_samples = n_out; a.state = fe->d_agc_state;
+		a.agc_out = fe->d_agc[p]; a.agc_stride = fe->agc_stride; a.lvl = fe->d_lvl[p]; a.lvl_stride = fe->rs_stride;
+		prof_begin2(fe, KC_AGC, pr, st2);
+		HFDL_LAUNCH(agc_kernel, dim3((unsigned)fe->C), dim3(32), 0, st2, a);
+		prof_end2(fe, pr, st2);
+		BankArgs b;
+		b.agc_out = fe->d_agc[p]; b.agc_stride = fe->agc_stride; b.n_samples = n_out; b.mfo = fe->d_mfo[p]; b.mfo_stride = fe->mfo_stride;
+		b.bank = fe->d_bank[p]; b.bank_stride = fe->rs_stride; b.tab = fe->d_tab;
+		prof_begin2(fe, KC_BANK, pr, st2);
+		HFDL_LAUNCH(bank_kernel, dim3((unsigned)((n_out + HFDL_BANK_TILE - 1) / HFDL_BANK_TILE), (unsigned)fe->C), dim3(256), 0, st2, b);
+		prof_end2(fe, pr, st2);
+		fe->launches += 2;
 		if(fe->cfg.capture_channel >= 0 && fe->cap_n < fe->cfg.capture_max) {       // f_agc_out / f_mf_out checkpoints
 			long long n = std::min<long long>(n_out, fe->cfg.capture_max - fe->cap_n);
 			int cc = fe->cfg.capture_channel;
-			CK(cudaMemcpyAsync(fe->d_cap_agc + fe->cap_n, fe->d_agc + (long long)cc * fe->agc_stride + HFDL_AGC_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st2));
-			CK(cudaMemcpyAsync(fe->d_cap_mf + fe->cap_n, fe->d_mfo + (long long)cc * fe->mfo_stride + HFDL_MFO_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st2));
+			CK(cudaMemcpyAsync(fe->d_cap_agc + fe->cap_n, fe->d_agc[p] + (long long)cc * fe->agc_stride + HFDL_AGC_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st2));
+			CK(cudaMemcpyAsync(fe->d_cap_mf + fe->cap_n, fe->d_mfo[p] + (long long)cc * fe->mfo_stride + HFDL_MFO_HIST, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToDevice, st2));
 		}
 		if(fe->cfg.capture_channel >= 0) fe->cap_n += n_out;
-		// the tails move in front of the arrays for the next batch once the first loop launch (which may still read
-		// the old matched-filter history after a symsync reset) is done
-		if(first_loop >= 0) CK(cudaStreamWaitEvent(st2, fe->ev_loop[p][first_loop], 0));
-		HFDL_LAUNCH(demod_carry, dim3((unsigned)fe->C), dim3(64), 0, st2, fe->d_agc, fe->agc_stride, fe->d_mfo, fe->mfo_stride, (long long)n_out);
-		fe->launches++;
-		(void)last_loop;
 	}
-	CK(cudaEventRecord(fe->ev_agc_done[p], st2));
+	CK(cudaEventRecord(fe->ev_bank[p], st2));
+	// ---- loop: frame records of set p are free once fec of batch i-2 is done
+	CK(cudaStreamWaitEvent(stl, fe->ev_bank[p], 0));
+	CK(cudaStreamWaitEvent(stl, fe->ev_fec_done[p], 0));
+	CK(cudaMemsetAsync(fe->d_nframes[p], 0, sizeof(int), stl));
+	if(n_out > 0) {
+		LoopArgs l;
+		l.bank = fe->d_bank[p]; l.bank_stride = fe->rs_stride; l.mfo = fe->d_mfo[p]; l.mfo_stride = fe->mfo_stride;
+		l.lvl = fe->d_lvl[p]; l.lvl_stride = fe->rs_stride; l.n_samples = n_out;
+		l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym; l.nslots = fe->nslots;
+		l.frames = fe->d_frames[p]; l.nframes = fe->d_nframes[p]; l.max_frames = fe->max_frames;
+		l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
+		l.debug_mode = fe->debug_mode;
+		l.dbg_cycles = fe->d_dbg;
+		prof_begin2(fe, KC_LOOP, pr, stl);
+		HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(HFDL_LK_THREADS), HFDL_LK_SMEM, stl, l);
+		prof_end2(fe, pr, stl);
+		fe->launches++;
+	}
+	CK(cudaEventRecord(fe->ev_loop[p], stl));
 	{
-		// st_fec: after the last loop launch of this batch (stream order on st_loop -> one event)
-		cudaEvent_t ev_all = fe->ev_loop[p][HFDL_NSUB - 1];
-		if(cur.nsub < HFDL_NSUB) CK(cudaEventRecord(ev_all, stl));     // (when nsub == HFDL_NSUB it was recorded above)
-		CK(cudaStreamWaitEvent(stf, ev_all, 0));
+		CK(cudaStreamWaitEvent(stf, fe->ev_loop[p], 0));
 		FecArgs a;
 		a.frames = fe->d_frames[p]; a.nframes = fe->d_nframes[p]; a.max_frames = fe->max_frames; a.datasym = fe->d_datasym; a.nslots = fe->nslots;
 		a.tab = fe->d_tab; a.pdus = fe->d_pdus[p]; a.soft_out = nullptr; a.vin_direct = nullptr; a.vin_nbits = 0;
@@ -436,16 +452,30 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 	cur.busy = true;
 	fe->batch_seq++;
 	fe->blocks_done += nb;
+	fe->n_out_prev = n_out;
 	fe->last_nblocks = nb; fe->last_nout = n_out;
 	// while this batch runs, pick up the previous one
 	return collect_batch(fe, p ^ 1);
+}
+
+// A failure in the middle of enqueueing leaves events unrecorded and counters half advanced: stop everything and
+// refuse further work instead of running on inconsistent pipeline state.
+int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
+	if(fe->failed) return -1;
+	if(run_batch_impl(fe, src, nb) == 0) return 0;
+	fe->failed = true;
+	cudaStream_t sts[4] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec };
+	for(cudaStream_t q : sts) if(q) cudaStreamSynchronize(q);
+	fe->flight[0].busy = fe->flight[1].busy = false;
+	fprintf(stderr, "hfdl_b200: batch failed, frontend disabled\n");
+	return -1;
 }
 
 int compute_tapslices(hfdl_b200_frontend *fe) {
 	// fft_channelizer_create (fastddc.c:217-252): taps -> N-point forward FFT; keep the M bins of the slice
 	const auto &g = fe->g;
 	const int N = g.fft_size, M = g.fft_inv_size, C = fe->C;
-	int chunk = std::min(fe->Bmax, C);
+	int chunk = std::min(fe->Bsub, C);
 	cf *d_in = nullptr;
 	CK(cudaMalloc((void **)&d_in, sizeof(cf) * (size_t)N * chunk));
 	std::vector<std::vector<std::complex<float>>> taps((size_t)chunk);
@@ -494,6 +524,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	fe->freqs.assign(cfg->freqs_hz, cfg->freqs_hz + cfg->nfreq);
 	fe->cfg.freqs_hz = fe->freqs.data();
 	fe->C = cfg->nfreq;
+	fe->tally.resize((size_t)fe->C);
 	fe->sfmt = cfg->sample_format;
 	fe->bps = bytes_per_sample(fe->sfmt);
 	if(!hfdl_design::geometry_init(fe->g, cfg->sample_rate)) { fprintf(stderr, "hfdl_b200_create: unsupported sample rate %d\n", cfg->sample_rate); delete fe; return -1; }
@@ -513,9 +544,17 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	fe->resamp_rate = (float)(1800 * 3) / ((float)cfg->sample_rate / (float)g.decimation);     // hfdl.c:471
 	if(!(fe->resamp_rate >= 0.5f && fe->resamp_rate <= 1.0f)) { fprintf(stderr, "hfdl_b200_create: resampling rate %f outside [0.5,1]\n", fe->resamp_rate); delete fe; return -1; }
 	fe->plan = make_plan(g.fft_size);
-	fe->Bmax = cfg->max_blocks_per_batch > 0 ? cfg->max_blocks_per_batch : std::max(1, std::min(64, (int)((256ll << 20) / ((long long)g.fft_size * 8))));
-	// loop_kernel addresses the samples of one launch (a sub-range = 1/8 batch) with 20 bits (HFDL_LK_MAXN)
-	if((long long)fe->Bmax * fe->out_per_block > (1ll << 22)) fe->Bmax = (int)((1ll << 22) / fe->out_per_block);
+	fe->Bmax = cfg->max_blocks_per_batch > 0 ? cfg->max_blocks_per_batch : std::max(1, std::min(64, (int)((1024ll << 20) / ((long long)g.fft_size * 8))));
+	// loop_kernel addresses the resampled samples of one launch (= one batch) with 20 bits (HFDL_LK_MAXN)
+	if((long long)fe->Bmax * fe->out_per_block >= (long long)HFDL_LK_MAXN) fe->Bmax = (int)((HFDL_LK_MAXN - 1) / fe->out_per_block);
+	// FFT sub-batches: the passes and chan_extract of Bsub blocks run back to back so that the intermediate and the
+	// final spectra (2 x Bsub x N x 8 bytes) stay in the 126 MB L2 instead of making a round trip through HBM
+	{
+		const char *e = getenv("HFDL_B200_FFT_SUB_MB");
+		const long long budget = (e ? atoll(e) : 40) << 20;                 // bytes of spectrum per sub-batch
+		fe->Bsub = (int)std::max<long long>(1, std::min<long long>(fe->Bmax, budget / ((long long)g.fft_size * 8)));
+	}
+	{ const char *dbg = getenv("HFDL_B200_DEBUG"); fe->debug_mode = dbg ? atoi(dbg) : 0; }
 	if(cfg->capture_channel >= fe->C) fe->cfg.capture_channel = -1;
 	if(fe->cfg.capture_max < 0) fe->cfg.capture_max = 0;
 
@@ -525,20 +564,18 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaStreamCreateWithFlags(&fe->stream2, cudaStreamNonBlocking));
 	CKD(cudaStreamCreateWithFlags(&fe->st_loop, cudaStreamNonBlocking));
 	CKD(cudaStreamCreateWithFlags(&fe->st_fec, cudaStreamNonBlocking));
+	CKD(cudaStreamCreateWithFlags(&fe->st_stats, cudaStreamNonBlocking));
 	CKD(cudaEventCreateWithFlags(&fe->ev_h2d, cudaEventDisableTiming));
 	for(int q = 0; q < 2; q++) {
 		CKD(cudaEventCreateWithFlags(&fe->ev_front[q], cudaEventDisableTiming));
-		CKD(cudaEventCreateWithFlags(&fe->ev_agc_done[q], cudaEventDisableTiming));
+		CKD(cudaEventCreateWithFlags(&fe->ev_bank[q], cudaEventDisableTiming));
+		CKD(cudaEventCreateWithFlags(&fe->ev_loop[q], cudaEventDisableTiming));
 		CKD(cudaEventCreateWithFlags(&fe->ev_fec_done[q], cudaEventDisableTiming));
-		for(int i = 0; i < HFDL_NSUB; i++) {
-			CKD(cudaEventCreateWithFlags(&fe->ev_sub[q][i], cudaEventDisableTiming));
-			CKD(cudaEventCreateWithFlags(&fe->ev_loop[q][i], cudaEventDisableTiming));
-		}
 	}
 	if(fe->fft.init()) { hfdl_b200_destroy(fe); return -1; }
 	const int C = fe->C, N = g.fft_size, M = g.fft_inv_size, B = fe->Bmax;
-	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * B));
-	if(fe->plan.natural) CKD(cudaMalloc((void **)&fe->d_spec, sizeof(cf) * (size_t)N * B));
+	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * std::max(fe->Bsub, 1)));
+	if(fe->plan.natural) CKD(cudaMalloc((void **)&fe->d_spec, sizeof(cf) * (size_t)N * std::max(fe->Bsub, 1)));
 	fe->ring_len = (long long)g.overlap_length + (long long)(B + 1) * g.input_size;
 	CKD(cudaMalloc(&fe->d_ring, (size_t)fe->ring_len * fe->bps));
 	CKD(cudaMemset(fe->d_ring, 0, (size_t)fe->ring_len * fe->bps));
@@ -576,12 +613,14 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 		CKD(cudaMalloc((void **)&fe->d_agc_state, sizeof(AgcState) * (size_t)C));
 		CKD(cudaMemcpy(fe->d_agc_state, ag.data(), sizeof(AgcState) * (size_t)C, cudaMemcpyHostToDevice));
 		fe->agc_stride = HFDL_AGC_HIST + fe->rs_stride; fe->mfo_stride = HFDL_MFO_HIST + fe->rs_stride;
-		CKD(cudaMalloc((void **)&fe->d_agc, sizeof(cf) * (size_t)C * fe->agc_stride));
-		CKD(cudaMemset(fe->d_agc, 0, sizeof(cf) * (size_t)C * fe->agc_stride));
-		CKD(cudaMalloc((void **)&fe->d_mfo, sizeof(cf) * (size_t)C * fe->mfo_stride));
-		CKD(cudaMemset(fe->d_mfo, 0, sizeof(cf) * (size_t)C * fe->mfo_stride));
-		CKD(cudaMalloc((void **)&fe->d_lvl, sizeof(float) * (size_t)C * fe->rs_stride));
-		CKD(cudaMalloc((void **)&fe->d_bank, sizeof(cf) * (size_t)C * fe->rs_stride * 32));
+		for(int q = 0; q < 2; q++) {
+			CKD(cudaMalloc((void **)&fe->d_agc[q], sizeof(cf) * (size_t)C * fe->agc_stride));
+			CKD(cudaMemset(fe->d_agc[q], 0, sizeof(cf) * (size_t)C * fe->agc_stride));
+			CKD(cudaMalloc((void **)&fe->d_mfo[q], sizeof(cf) * (size_t)C * fe->mfo_stride));
+			CKD(cudaMemset(fe->d_mfo[q], 0, sizeof(cf) * (size_t)C * fe->mfo_stride));
+			CKD(cudaMalloc((void **)&fe->d_lvl[q], sizeof(float) * (size_t)C * fe->rs_stride));
+			CKD(cudaMalloc((void **)&fe->d_bank[q], sizeof(cf) * (size_t)C * fe->rs_stride * 32));
+		}
 		delete T;
 	}
 	{
@@ -612,7 +651,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaMemset(fe->d_cap_cnt, 0, sizeof(int) * 2));
 	fe->tmp_len = std::max((long long)N, (long long)B * fe->out_per_block + 64);
 	CKD(cudaMalloc((void **)&fe->d_tmp, sizeof(cf) * (size_t)fe->tmp_len));
-	if(getenv("HFDL_B200_DEBUG")) { CKD(cudaMalloc((void **)&fe->d_dbg, sizeof(long long) * 32 * (size_t)C)); CKD(cudaMemset(fe->d_dbg, 0, sizeof(long long) * 32 * (size_t)C)); }
+	if(fe->debug_mode) { CKD(cudaMalloc((void **)&fe->d_dbg, sizeof(long long) * 32 * (size_t)C)); CKD(cudaMemset(fe->d_dbg, 0, sizeof(long long) * 32 * (size_t)C)); }
 	CKD(cudaEventCreate(&fe->ev0));
 	CKD(cudaEventCreate(&fe->ev1));
 	if(compute_tapslices(fe)) { hfdl_b200_destroy(fe); return -1; }
@@ -623,23 +662,22 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 
 void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
-	cudaStream_t sts[4] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec };
+	cudaSetDevice(fe->cfg.device);
+	cudaStream_t sts[5] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec, fe->st_stats };
 	for(cudaStream_t q : sts) if(q) cudaStreamSynchronize(q);
 	cudaFree(fe->d_work); cudaFree(fe->d_spec); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
 	cudaFree(fe->d_bb); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
 	cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf); cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp); cudaFree(fe->d_dbg);
-	cudaFree(fe->d_agc_state); cudaFree(fe->d_agc); cudaFree(fe->d_mfo); cudaFree(fe->d_lvl); cudaFree(fe->d_bank);
+	cudaFree(fe->d_agc_state);
 	for(int q = 0; q < 2; q++) {
+		cudaFree(fe->d_agc[q]); cudaFree(fe->d_mfo[q]); cudaFree(fe->d_lvl[q]); cudaFree(fe->d_bank[q]);
 		cudaFree(fe->d_rs[q]); cudaFree(fe->d_frames[q]); cudaFree(fe->d_nframes[q]); cudaFree(fe->d_pdus[q]);
 		if(fe->h_pdus[q]) cudaFreeHost(fe->h_pdus[q]);
 		if(fe->h_nframes[q]) cudaFreeHost(fe->h_nframes[q]);
 		if(fe->ev_front[q]) cudaEventDestroy(fe->ev_front[q]);
-		if(fe->ev_agc_done[q]) cudaEventDestroy(fe->ev_agc_done[q]);
+		if(fe->ev_bank[q]) cudaEventDestroy(fe->ev_bank[q]);
+		if(fe->ev_loop[q]) cudaEventDestroy(fe->ev_loop[q]);
 		if(fe->ev_fec_done[q]) cudaEventDestroy(fe->ev_fec_done[q]);
-		for(int i = 0; i < HFDL_NSUB; i++) {
-			if(fe->ev_sub[q][i]) cudaEventDestroy(fe->ev_sub[q][i]);
-			if(fe->ev_loop[q][i]) cudaEventDestroy(fe->ev_loop[q][i]);
-		}
 	}
 	for(auto &r : fe->prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
 	if(fe->ev0) cudaEventDestroy(fe->ev0);
@@ -682,6 +720,7 @@ static int process_pending(hfdl_b200_frontend *fe, bool all) {
 
 int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples) {
 	if(!fe || (!samples && nsamples > 0) || nsamples < 0) return -1;
+	HFDL_API(fe, -1);
 	const auto &g = fe->g;
 	const unsigned char *p = (const unsigned char *)samples;
 	int blocks = 0;
@@ -712,15 +751,83 @@ int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, in
 	return blocks;
 }
 
+// Multi-GPU: dst (another device) takes the samples src has received and dst has not, ring to ring over NVLink
+// (cudaMemcpyPeerAsync with peer access enabled); both frontends have the same geometry, so the rings are congruent.
+int32_t hfdl_b200_push_peer(hfdl_b200_frontend_t *dst, hfdl_b200_frontend_t *src) {
+	if(!dst || !src || dst == src) return -1;
+	// lock order by address: two threads pushing in opposite directions cannot deadlock
+	std::unique_lock<std::recursive_mutex> l1(dst < src ? dst->mtx : src->mtx), l2(dst < src ? src->mtx : dst->mtx);
+	if(dst->failed || src->failed || dst->ring_len != src->ring_len || dst->sfmt != src->sfmt || dst->g.input_size != src->g.input_size) return -1;
+	int prev = -1;
+	cudaGetDevice(&prev);
+	struct Restore { int d; ~Restore() { if(d >= 0) cudaSetDevice(d); } } restore{ prev };
+	CK(cudaSetDevice(dst->cfg.device));
+	if(!dst->peer_enabled) {
+		int can = 0;
+		if(dst->cfg.device != src->cfg.device && cudaDeviceCanAccessPeer(&can, dst->cfg.device, src->cfg.device) == cudaSuccess && can) {
+			cudaError_t e = cudaDeviceEnablePeerAccess(src->cfg.device, 0);
+			if(e != cudaSuccess) cudaGetLastError();            // already enabled by someone else is fine
+		}
+		dst->peer_enabled = true;
+	}
+	int blocks = 0;
+	while(dst->fed < src->fed) {
+		// same bookkeeping as hfdl_b200_push_samples, the source being the peer's ring
+		long long keep_from = dst->blocks_done * (long long)dst->g.input_size - dst->g.overlap_length;
+		long long space = dst->ring_len - (dst->fed - keep_from);
+		if(space <= 0) {
+			int r = process_pending(dst, true);
+			if(r < 0) return -1;
+			blocks += r;
+			continue;
+		}
+		if(src->fed - dst->fed > src->ring_len) { fprintf(stderr, "hfdl_b200_push_peer: the peer's ring has been overwritten\n"); return -1; }
+		long long n = std::min<long long>(src->fed - dst->fed, space);
+		long long idx = dst->fed % dst->ring_len;
+		long long first = std::min(n, dst->ring_len - idx);
+		CK(cudaStreamWaitEvent(dst->stream, src->ev_h2d, 0));     // the peer's H2D copy of these samples
+		CK(cudaMemcpyPeerAsync((unsigned char *)dst->d_ring + idx * dst->bps, dst->cfg.device, (const unsigned char *)src->d_ring + idx * src->bps, src->cfg.device, (size_t)(first * dst->bps), dst->stream));
+		if(n > first)
+			CK(cudaMemcpyPeerAsync(dst->d_ring, dst->cfg.device, src->d_ring, src->cfg.device, (size_t)((n - first) * dst->bps), dst->stream));
+		dst->fed += n;
+		CK(cudaEventRecord(dst->ev_h2d, dst->stream));
+		// the peer must not overwrite this part of its ring before the copy has read it
+		CK(cudaStreamWaitEvent(src->stream, dst->ev_h2d, 0));
+		int r = process_pending(dst, false);
+		if(r < 0) return -1;
+		blocks += r;
+	}
+	return blocks;
+}
+
 int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe) {
-	if(!fe) return -1;
+	HFDL_API(fe, -1);
 	int r = process_pending(fe, true);
 	if(r < 0 || drain(fe)) return -1;
 	return r;
 }
 
+int32_t hfdl_b200_submit(hfdl_b200_frontend_t *fe) {
+	HFDL_API(fe, -1);
+	return process_pending(fe, true);
+}
+
+int32_t hfdl_b200_poll(hfdl_b200_frontend_t *fe) {
+	HFDL_API(fe, -1);
+	const int p = (int)(fe->batch_seq & 1);
+	if(collect_batch(fe, p, false)) return -1;               // older batch first: PDU order per channel is kept
+	if(!fe->flight[p].busy && collect_batch(fe, p ^ 1, false)) return -1;
+	return (int32_t)fe->pduq.size();
+}
+
+int32_t hfdl_b200_busy(hfdl_b200_frontend_t *fe) {
+	HFDL_API(fe, -1);
+	return (fe->flight[0].busy || fe->flight[1].busy) ? 1 : 0;
+}
+
 int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t ring_samples, int64_t start_sample, int32_t nblocks) {
 	if(!fe || !d_samples || ring_samples < fe->g.fft_size || nblocks < 0) return -1;
+	HFDL_API(fe, -1);
 	const auto &g = fe->g;
 	int done = 0;
 	while(done < nblocks) {
@@ -737,43 +844,72 @@ int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples
 }
 
 int32_t hfdl_b200_sync(hfdl_b200_frontend_t *fe) {
-	if(!fe) return -1;
+	HFDL_API(fe, -1);
 	return drain(fe);
 }
 
-int32_t hfdl_b200_pdu_count(hfdl_b200_frontend_t *fe) { return fe ? (int32_t)fe->pduq.size() : -1; }
+int32_t hfdl_b200_pdu_count(hfdl_b200_frontend_t *fe) {
+	if(!fe) return -1;
+	std::lock_guard<std::recursive_mutex> lk(fe->mtx);
+	return (int32_t)fe->pduq.size();
+}
 
 int32_t hfdl_b200_pop_pdu(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdu) {
 	if(!fe || !pdu) return -1;
+	std::lock_guard<std::recursive_mutex> lk(fe->mtx);
 	if(fe->pduq.empty()) return 0;
 	*pdu = fe->pduq.front();
 	fe->pduq.pop_front();
 	return 1;
 }
 
+// Snapshot of one channel's demodulator state.  It does NOT drain the pipeline (the reference's stats thread reads
+// c->noise_floor while the channel thread runs, hfdl.c:1093): the copy goes through its own stream and sees the state
+// as the last finished loop launch left it; after hfdl_b200_flush / _sync it is the state after all pushed samples.
 static int read_state(hfdl_b200_frontend *fe, int ch, DemodState *S) {
-	if(!fe || ch < 0 || ch >= fe->C) return -1;
-	if(drain(fe)) return -1;
-	CK(cudaMemcpy(S, fe->d_state + ch, sizeof(DemodState), cudaMemcpyDeviceToHost));
+	if(ch < 0 || ch >= fe->C) return -1;
+	CK(cudaMemcpyAsync(S, fe->d_state + ch, sizeof(DemodState), cudaMemcpyDeviceToHost, fe->st_stats));
+	CK(cudaStreamSynchronize(fe->st_stats));
 	return 0;
 }
 
 int32_t hfdl_b200_channel_noise_floor(hfdl_b200_frontend_t *fe, int32_t channel, float *level) {
 	DemodState S;
-	if(!level || read_state(fe, channel, &S)) return -1;
+	if(!level) return -1;
+	HFDL_API(fe, -1);
+	if(read_state(fe, channel, &S)) return -1;
 	*level = S.noise_floor;
 	return 0;
 }
 
 int32_t hfdl_b200_channel_stats(hfdl_b200_frontend_t *fe, int32_t channel, int32_t out[4]) {
 	DemodState S;
-	if(!out || read_state(fe, channel, &S)) return -1;
+	if(!out) return -1;
+	HFDL_API(fe, -1);
+	if(read_state(fe, channel, &S)) return -1;
 	out[0] = S.st_a1; out[1] = S.st_a2; out[2] = S.st_m1; out[3] = S.st_frames;
+	return 0;
+}
+
+int32_t hfdl_b200_channel_counters(hfdl_b200_frontend_t *fe, int32_t channel, hfdl_b200_counters_t *out) {
+	DemodState S;
+	if(!out) return -1;
+	HFDL_API(fe, -1);
+	if(read_state(fe, channel, &S)) return -1;
+	memset(out, 0, sizeof(*out));
+	out->freq = fe->freqs[(size_t)channel];
+	out->A1_found = S.st_a1; out->A2_found = S.st_a2; out->M1_found = S.st_m1; out->M1_not_found = S.st_m1_fail;
+	out->noise_floor = S.noise_floor;
+	const hfdl_b200_frontend::ChanTally &t = fe->tally[(size_t)channel];
+	out->frames_processed = t.processed; out->frames_good = t.good; out->frames_bad_fcs = t.bad_fcs; out->frames_too_short = t.too_short;
+	out->frames_air2gnd = t.air2gnd; out->frames_gnd2air = t.gnd2air;
+	out->lpdus_processed = t.lpdus_processed; out->lpdus_good = t.lpdus_good; out->lpdus_bad_fcs = t.lpdus_bad; out->lpdus_too_short = t.lpdus_short;
 	return 0;
 }
 
 void hfdl_b200_print_summary(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
+	ApiGuard guard_(fe);
 	if(fe->d_dbg) {
 		std::vector<long long> v((size_t)fe->C * 32);
 		drain(fe);
@@ -793,13 +929,14 @@ void hfdl_b200_print_summary(hfdl_b200_frontend_t *fe) {
 }
 
 int32_t hfdl_b200_timer_start(hfdl_b200_frontend_t *fe) {
-	if(!fe) return -1;
+	HFDL_API(fe, -1);
 	if(drain(fe)) return -1;
 	CK(cudaEventRecord(fe->ev0, fe->stream));
 	return 0;
 }
 int32_t hfdl_b200_timer_stop(hfdl_b200_frontend_t *fe, float *ms) {
-	if(!fe || !ms) return -1;
+	if(!ms) return -1;
+	HFDL_API(fe, -1);
 	if(drain(fe)) return -1;                      // every batch of the timed region has finished on all four streams
 	CK(cudaEventRecord(fe->ev1, fe->stream));
 	CK(cudaEventSynchronize(fe->ev1));
@@ -807,12 +944,12 @@ int32_t hfdl_b200_timer_stop(hfdl_b200_frontend_t *fe, float *ms) {
 	return 0;
 }
 int32_t hfdl_b200_profile_enable(hfdl_b200_frontend_t *fe, int32_t on) {
-	if(!fe) return -1;
+	HFDL_API(fe, -1);
 	fe->profiling = on != 0;
 	return 0;
 }
 int32_t hfdl_b200_profile_read(hfdl_b200_frontend_t *fe, int32_t max, char names[][32], float *ms, int32_t *launches) {
-	if(!fe) return -1;
+	HFDL_API(fe, -1);
 	if(drain(fe)) return -1;
 	for(auto &r : fe->prof) {
 		float t = 0;
@@ -832,7 +969,8 @@ int64_t hfdl_b200_kernel_launches(hfdl_b200_frontend_t *fe) { return fe ? fe->la
 int64_t hfdl_b200_result_bytes_per_batch(hfdl_b200_frontend_t *fe) { return fe ? (int64_t)(sizeof(int) + sizeof(PduRec) * (size_t)fe->max_frames) : -1; }
 
 int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_t index, void *dst, int64_t max) {
-	if(!fe || max < 0) return -1;
+	if(max < 0) return -1;
+	HFDL_API(fe, -1);
 	if(drain(fe)) return -1;
 	const auto &g = fe->g;
 	long long avail = 0;
@@ -840,7 +978,9 @@ int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_
 	switch(what) {
 	case HFDL_B200_CP_SPECTRUM: {
 		if(index < 0) index = fe->last_nblocks - 1;       // -1: last block processed
-		if(index < 0 || index >= fe->last_nblocks) return -1;
+		// only the spectra of the last FFT sub-batch are still on the device
+		index -= fe->last_nblocks - fe->last_sub_blocks;
+		if(index < 0 || index >= fe->last_sub_blocks) return -1;
 		avail = g.fft_size;
 		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((g.fft_size + 255) / 256)), dim3(256), 0, fe->stream, fe->plan.natural ? fe->d_spec : fe->d_work, fe->plan, index, 0, g.fft_size, fe->d_tmp);
 		CK(cudaGetLastError());
@@ -960,6 +1100,38 @@ int32_t hfdl_b200_fec_decode(int32_t device, const void *symbols, int32_t nframe
 		uint8_t *pdu_out, int32_t stride_out, uint8_t *soft_out, int32_t *crc_good_out) {
 	if(!symbols || !pdu_out || M1 < 0 || M1 > 7 || stride_out < hfdl_design::pdu_len(M1)) return -1;
 	return fec_run(device, symbols, nullptr, nframes, M1, bitmask, 0, pdu_out, stride_out, soft_out, crc_good_out);
+}
+
+int32_t hfdl_b200_pdu_front_parse(int32_t device, const uint8_t *pdus, int32_t stride, const int32_t *lens, int32_t n, hfdl_b200_pdu_t *out) {
+	if(!pdus || !lens || !out || n < 1 || stride < 1 || hfdl_b200_device_count() < 1) return -1;
+	CK(cudaSetDevice(device));
+	std::vector<PduRec> recs((size_t)n);
+	for(int i = 0; i < n; i++) {
+		memset(&recs[(size_t)i], 0, sizeof(PduRec));
+		if(lens[i] < 0 || lens[i] > HFDL_MAX_PDU || lens[i] > stride) return -1;
+		recs[(size_t)i].len = lens[i];
+		memcpy(recs[(size_t)i].octets, pdus + (size_t)i * stride, (size_t)lens[i]);
+	}
+	PduRec *d = nullptr;
+	CK(cudaMalloc((void **)&d, sizeof(PduRec) * (size_t)n));
+	int rc = 0;
+	if(cudaMemcpy(d, recs.data(), sizeof(PduRec) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) rc = -1;
+	if(rc == 0) {
+		HFDL_LAUNCH(front_kernel, dim3((unsigned)n), dim3(32), 0, 0, d, n);
+		if(cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) rc = -1;
+	}
+	if(rc == 0 && cudaMemcpy(recs.data(), d, sizeof(PduRec) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
+	cudaFree(d);
+	if(rc) return -1;
+	for(int i = 0; i < n; i++) {
+		const PduRec &r = recs[(size_t)i];
+		memset(&out[i], 0, sizeof(out[i]));
+		out[i].len = r.len; memcpy(out[i].octets, r.octets, (size_t)r.len);
+		out[i].crc_good = r.crc_good; out[i].frame_status = r.frame_status; out[i].direction = r.direction;
+		out[i].lpdus_processed = r.lpdus_processed; out[i].lpdus_good = r.lpdus_good; out[i].lpdus_bad_fcs = r.lpdus_bad_fcs;
+		out[i].lpdus_too_short = r.lpdus_too_short; out[i].lpdu_good_mask = r.lpdu_good_mask;
+	}
+	return 0;
 }
 
 int32_t hfdl_b200_viterbi27(int32_t device, const uint8_t *syms, int32_t nframes, int32_t nbits, uint8_t *out) {

@@ -816,6 +816,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 					S.fr_state = HF_M2_SKIP;
 					S.s_state = HS_SKIP;
 				} else {
+					S.st_m1_fail++;                  // statsd demod.preamble.errors.M1_not_found (hfdl.c:840)
 					framer_reset(S, T, E, l16); reset_pending = true;
 				}
 				break; }
@@ -1014,7 +1015,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			G->T_idx = S.T_idx; G->M1 = S.M1; G->bitmask = S.bitmask; G->symsync_out_idx = S.symsync_out_idx;
 			G->freq_err_hz = S.freq_err_hz; G->signal_level = S.signal_level; G->noise_floor = S.noise_floor;
 			G->nf_clk = S.nf_clk; G->frame_symbol_cnt = S.frame_symbol_cnt;
-			G->st_a1 = S.st_a1; G->st_a2 = S.st_a2; G->st_m1 = S.st_m1; G->st_frames = S.st_frames;
+			G->st_a1 = S.st_a1; G->st_a2 = S.st_a2; G->st_m1 = S.st_m1; G->st_frames = S.st_frames; G->st_m1_fail = S.st_m1_fail;
 			if(cap) a.cap_cnt[1] = cap_n_eq;
 			__threadfence_block();
 			lk_done = 1;

@@ -19,7 +19,14 @@
  *   hfdl_b200_process_device    <- same, for a capture already resident in HBM (replay / multi-GPU broadcast)
  *   hfdl_b200_flush             <- the drain-then-exit rule of fft.c:38-47 (only whole blocks are processed)
  *   hfdl_b200_pop_pdu           <- dispatch_pdu -> pdu_decoder_queue_push (hfdl.c:1058-1080, pdu.h:39)
+ *   hfdl_b200_push_peer         <- block_connect_one2many's shared spectrum buffer (block.c:90-120): every GPU sees the capture
+ *   hfdl_b200_submit / _poll    <- the per-block hand-over of fft_thread / hfdl_decoder_thread (fft.c:57-61, hfdl.c:663-664)
+ *                                  without its barrier pair: work is queued, finished batches are picked up later
  *   hfdl_b200_channel_noise_floor <- the c->noise_floor read of noise_floor_stats_thread (hfdl.c:1082-1105)
+ *   hfdl_b200_channel_counters  <- the per-channel statsd metrics (doc/STATSD_METRICS.md; hook points hfdl.c:818,828,840,
+ *                                  pdu.c:123, mpdu.c:68-102, spdu.c:56-70, lpdu.c:129-150)
+ *   pdu.frame_status, lpdus_*   <- the front of pdu_decoder_thread: IS_MPDU split, header-length rule, MPDU / SPDU /
+ *                                  LPDU frame check sequences (pdu.c:104, mpdu.c:56-159, spdu.c:55-64, lpdu.c:124-150)
  *   hfdl_b200_print_summary     <- hfdl_print_summary (hfdl.h:14)
  *   hfdl_b200_fft_forward       <- csdr_make_fft_c2c + csdr_fft_execute (fft.h:25-28) [stage entry for parity tests]
  *   hfdl_b200_fec_decode        <- decode_user_data (hfdl.c:993-1056)              [stage entry for parity tests]
@@ -82,7 +89,25 @@ typedef struct {
 	float   signal_level, noise_floor_lin;
 	int32_t len;
 	uint8_t octets[HFDL_B200_MAX_PDU_OCTETS + 3];
+	/* front parser, computed on the device (what pdu_decoder_thread finds out first, pdu.c:104-123) */
+	int32_t frame_status;         /* HFDL_B200_FRAME_*: frames.good / frame.errors.bad_fcs / frame.errors.too_short */
+	int32_t direction;            /* 1 air2gnd (downlink MPDU), 0 gnd2air (uplink MPDU or SPDU); valid when frame_status == GOOD */
+	int32_t lpdus_processed, lpdus_good, lpdus_bad_fcs, lpdus_too_short;      /* lpdu.c:129-150 */
+	uint64_t lpdu_good_mask;      /* bit j: the j-th LPDU of the PDU has a good FCS */
 } hfdl_b200_pdu_t;
+#define HFDL_B200_FRAME_GOOD 0
+#define HFDL_B200_FRAME_BAD_FCS 1
+#define HFDL_B200_FRAME_TOO_SHORT 2
+
+/* per-channel counters = the reference's per-channel statsd metrics (doc/STATSD_METRICS.md:21-49) */
+typedef struct {
+	int32_t freq;
+	int64_t A1_found, A2_found, M1_found, M1_not_found;                        /* demod.preamble.* (hfdl.c:818,828,840) */
+	int64_t frames_processed, frames_good, frames_bad_fcs, frames_too_short;   /* pdu.c:123, mpdu.c:68-88, spdu.c:56-66 */
+	int64_t frames_air2gnd, frames_gnd2air;                                    /* frame.dir.* (mpdu.c:92,100, spdu.c:70) */
+	int64_t lpdus_processed, lpdus_good, lpdus_bad_fcs, lpdus_too_short;       /* lpdu.c:129-150 */
+	float noise_floor;                                                         /* linear; the gauge is 10*|20log10| (hfdl.c:1093-1099) */
+} hfdl_b200_counters_t;
 
 int32_t hfdl_b200_device_count(void);
 int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *cfg);
@@ -105,6 +130,16 @@ int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples
 		int64_t start_sample, int32_t nblocks);
 /* Blocks until all queued GPU work of this frontend is complete and PDUs are collected. */
 int32_t hfdl_b200_sync(hfdl_b200_frontend_t *fe);
+/* Streaming use: queue every whole block buffered so far on the GPU and return at once (no waiting; returns the
+ * number of blocks queued), and pick up the PDUs of batches that have finished meanwhile without blocking (returns
+ * the number of PDUs waiting in the queue).  hfdl_b200_busy: 1 while a batch is still in flight. */
+int32_t hfdl_b200_submit(hfdl_b200_frontend_t *fe);
+/* Multi-GPU, one process: 'dst' (a frontend with the same sample rate / format / batch size on ANOTHER device) takes
+ * the samples 'src' has been pushed and 'dst' has not seen yet, device ring to device ring over NVLink.  The capture
+ * crosses PCIe once; this is the broadcast of the reference's one2many connection (block.c:90-120, fft.c:60-61). */
+int32_t hfdl_b200_push_peer(hfdl_b200_frontend_t *dst, hfdl_b200_frontend_t *src);
+int32_t hfdl_b200_poll(hfdl_b200_frontend_t *fe);
+int32_t hfdl_b200_busy(hfdl_b200_frontend_t *fe);
 
 int32_t hfdl_b200_pdu_count(hfdl_b200_frontend_t *fe);
 /* returns 1 and fills *pdu when one is available, 0 when the queue is empty */
@@ -112,6 +147,9 @@ int32_t hfdl_b200_pop_pdu(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdu);
 int32_t hfdl_b200_channel_noise_floor(hfdl_b200_frontend_t *fe, int32_t channel, float *level_linear);
 /* counters: A1 found, A2 found, M1 found, frames (hfdl.c:162-179) */
 int32_t hfdl_b200_channel_stats(hfdl_b200_frontend_t *fe, int32_t channel, int32_t out[4]);
+/* The demodulator counters reflect the batches finished so far, the frame / LPDU counters the PDUs collected so far;
+ * none of the three calls waits for queued work (the reference's stats thread does not stop the channels either). */
+int32_t hfdl_b200_channel_counters(hfdl_b200_frontend_t *fe, int32_t channel, hfdl_b200_counters_t *out);
 void    hfdl_b200_print_summary(hfdl_b200_frontend_t *fe);
 
 /* timing of the device work issued since the previous call (CUDA events on the frontend's stream) */
@@ -145,6 +183,8 @@ int32_t hfdl_b200_fec_decode(int32_t device, const void *symbols_cf32, int32_t n
 /* Viterbi only: syms [nframes][2*nbits] soft bytes -> out [nframes][(nbits+7)/8]; nbits must be one of the HFDL sizes */
 int32_t hfdl_b200_viterbi27(int32_t device, const uint8_t *syms, int32_t nframes, int32_t nbits, uint8_t *out);
 int32_t hfdl_b200_pdu_len(int32_t M1);
+/* front parser only: n PDUs of lens[i] octets at pdus + i*stride -> frame_status, direction, lpdus_*, lpdu_good_mask, crc_good */
+int32_t hfdl_b200_pdu_front_parse(int32_t device, const uint8_t *pdus, int32_t stride, const int32_t *lens, int32_t n, hfdl_b200_pdu_t *out);
 
 #ifdef __cplusplus
 }

@@ -12,8 +12,8 @@
  *   PDU delivery               <- dispatch_pdu (hfdl.c:1058-1080): hfdl_pdu_metadata_create + octet_string_new +
  *                                 pdu_decoder_queue_push (pdu.h:39-40), resolved against the host program at load time
  *   hfdl_gpu_frontend_print_summary <- hfdl_print_summary (hfdl.h:14)
- *   cbuffercf_*                <- liquid-dsp's cbuffercf as used by block.c:20,28, fft.c:41-54, input-helpers.c:83-89,
- *                                 input-file.c:55 (only needed when dumphfdl is linked without liquid-dsp, e.g. the tests)
+ * The ring of block_connect_one2one is liquid-dsp's cbuffercf (block.c:20): the library CALLS the host program's
+ * cbuffercf_size / cbuffercf_read / cbuffercf_release (weak references, resolved at load time) and defines none.
  *
  * The struct layouts below restate the ABI of src/block.h:27-68 (field order and types are the interface).
  */
@@ -31,7 +31,7 @@ extern "C" {
 #ifndef HFDL_B200_NO_BLOCK_STRUCTS      /* define when compiling inside dumphfdl, which has its own block.h */
 enum producer_type { PRODUCER_NONE = 0, PRODUCER_SINGLE, PRODUCER_MULTI, PRODUCER_MAX };
 enum consumer_type { CONSUMER_NONE = 0, CONSUMER_SINGLE, CONSUMER_MULTI, CONSUMER_MAX };
-typedef struct hfdl_cbuffercf_s *cbuffercf;
+typedef struct cbuffercf_s *cbuffercf;        /* liquid.h */
 struct circ_buffer { cbuffercf buf; pthread_cond_t *cond; pthread_mutex_t *mutex; };
 struct shared_buffer { void *buf; pthread_barrier_t *data_ready; pthread_barrier_t *consumers_ready; };
 struct block_connection {
@@ -52,27 +52,20 @@ struct block {
 #endif
 
 /* Returns &obj->block with consumer = { CONSUMER_SINGLE, min_ru = fft_size }, producer = { PRODUCER_NONE } and
- * thread_routine set; NULL on error.  The ring carries CF32 (what complex_samples_produce writes). */
+ * thread_routine set; NULL on error.  The ring carries CF32 (what complex_samples_produce writes).
+ * ngpus >= 1: CUDA devices device .. device+ngpus-1 share the work; channel k runs on GPU k mod ngpus end to end, the
+ * samples cross PCIe once and reach the other GPUs over NVLink (the reference's one2many broadcast, block.c:90-120). */
 struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_hz, const int32_t *freqs_hz,
-		int32_t nfreq, int32_t device);
+		int32_t nfreq, int32_t device, int32_t ngpus);
 void hfdl_gpu_frontend_destroy(struct block *frontend_block);
 void hfdl_gpu_frontend_print_summary(struct block *frontend_block);
-/* channel noise floor in dBFS, as noise_floor_stats_thread reports it (hfdl.c:1093) */
+/* channel noise floor in dBFS, as noise_floor_stats_thread reports it (hfdl.c:1093); does not stop the processing */
 int32_t hfdl_gpu_frontend_noise_floor_db(struct block *frontend_block, int32_t channel, float *db);
+/* the per-channel statsd metrics (doc/STATSD_METRICS.md) as counters; channel = index into freqs_hz */
+int32_t hfdl_gpu_frontend_counters(struct block *frontend_block, int32_t channel, hfdl_b200_counters_t *out);
 /* When the host program does not export pdu_decoder_queue_push (e.g. the tests), PDUs go to this callback. */
 typedef void (*hfdl_gpu_pdu_callback)(const hfdl_b200_pdu_t *pdu, void *user);
 void hfdl_gpu_frontend_set_pdu_callback(struct block *frontend_block, hfdl_gpu_pdu_callback cb, void *user);
-
-/* ---- cbuffercf stand-in (liquid-dsp API subset), elements are C99 float complex = 2 floats ---- */
-cbuffercf cbuffercf_create(unsigned int max_size);
-void cbuffercf_destroy(cbuffercf q);
-void cbuffercf_reset(cbuffercf q);
-unsigned int cbuffercf_size(cbuffercf q);
-unsigned int cbuffercf_max_size(cbuffercf q);
-unsigned int cbuffercf_space_available(cbuffercf q);
-int cbuffercf_write(cbuffercf q, void *v /* float complex* */, unsigned int n);
-int cbuffercf_read(cbuffercf q, unsigned int n, void **v /* float complex** */, unsigned int *num_read);
-int cbuffercf_release(cbuffercf q, unsigned int n);
 
 #ifdef __cplusplus
 }

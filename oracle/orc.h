@@ -106,6 +106,8 @@ typedef struct {
 } orc_channelizer_t;
 orc_channelizer_t *orc_channelizer_create(int32_t decimation, float transition_bw, float freq_shift, int fold_mode);
 void orc_channelizer_destroy(orc_channelizer_t *c);
+const cf32 *orc_channelizer_taps(const orc_channelizer_t *c);      /* taps_fft: N (FULL) or M (SLICE) bins */
+const orc_ddc_t *orc_channelizer_ddc(const orc_channelizer_t *c);
 /* spectrum_swapped: N bins after fft_swap_sides (DC at N/2).  out: >= post_input_size. returns #outputs */
 int  orc_channelizer_execute(orc_channelizer_t *c, const cf32 *spectrum_swapped, cf32 *out);
 void orc_swap_sides(cf32 *io, int32_t n);                                 /* fastddc.c:102-112 */
@@ -124,6 +126,9 @@ uint16_t orc_crc16(const uint8_t *data, uint32_t len, uint16_t init);           
 int      orc_fcs_check(const uint8_t *buf, uint32_t hdr_len);                    /* pdu.c:68-79 */
 /* returns 1 if the PDU's frame check is good by the rules of pdu.c:104 + mpdu.c:56-85 / spdu.c:55-64 */
 int      orc_pdu_crc_good(const uint8_t *buf, uint32_t len);
+/* front of pdu_decoder_thread (pdu.c:104-123, mpdu.c:56-159, spdu.c:55-70, lpdu.c:129-150):
+ * out = { status 0 good / 1 bad_fcs / 2 too_short, direction 1 air2gnd, lpdus processed, good, bad_fcs, too_short } */
+void     orc_pdu_front_parse(const uint8_t *buf, uint32_t len, int32_t out[6], uint64_t *good_mask);
 /* K=7 r=1/2 Viterbi restated from libfec/viterbi27_port.c: syms 2*nbits soft bytes -> ceil(nbits/8) octets (MSB first) */
 void     orc_viterbi27(const uint8_t *syms, int nbits, uint8_t *out);
 void     orc_conv_encode27(const uint8_t *bits, int nbits, uint8_t *chips /*2*nbits, values 0/1*/);
@@ -196,7 +201,8 @@ typedef struct {
 	int32_t pdu_len;
 	uint8_t pdu[ORC_MAX_PDU_OCTETS + 3];
 } orc_tx_frame_t;
-/* builds a valid PDU of the mode's size: kind 0 = downlink MPDU with lpdu_cnt LPDUs, 1 = SPDU, 2 = raw random */
+/* builds a PDU of the mode's size: kind 0 = downlink MPDU with 2 LPDUs, 1 = SPDU, 2 = raw random, 3 = uplink MPDU for two
+ * aircraft with 3 LPDUs (one with a broken FCS), 4 = downlink MPDU with a too-short and a truncated LPDU */
 int  orc_tx_make_pdu(int M1, int kind, uint64_t seed, uint8_t *out);
 /* 3 samples/symbol complex baseband of one frame (prekey..last T), shaped with orc_mf_taps; returns sample count */
 int  orc_tx_frame_baseband(const orc_tx_frame_t *f, cf32 *out, int max);

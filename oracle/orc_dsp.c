@@ -281,6 +281,9 @@ orc_channelizer_t *orc_channelizer_create(int32_t decimation, float transition_b
 	return c;
 }
 
+const cf32 *orc_channelizer_taps(const orc_channelizer_t *c) { return c->taps_fft; }
+const orc_ddc_t *orc_channelizer_ddc(const orc_channelizer_t *c) { return &c->ddc; }
+
 void orc_channelizer_destroy(orc_channelizer_t *c) {
 	if(!c) return;
 	free(c->taps_fft); free(c->inv_in); free(c->inv_out); free(c);

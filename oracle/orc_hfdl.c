@@ -83,6 +83,67 @@ int orc_pdu_crc_good(const uint8_t *buf, uint32_t len) {
 	return orc_fcs_check(buf, 64u);
 }
 
+/* Front of pdu_decoder_thread restated: IS_MPDU split (pdu.c:104), MPDU header-length rule + FCS (mpdu.c:56-88),
+ * LPDU walk (mpdu.c:90-119,136-159), LPDU length / FCS checks (lpdu.c:129-150), SPDU (spdu.c:55-70).
+ * out: status (0 good, 1 bad_fcs, 2 too_short), direction (1 air2gnd), lpdus processed / good / bad_fcs / too_short */
+void orc_pdu_front_parse(const uint8_t *buf, uint32_t len, int32_t out[6], uint64_t *good_mask) {
+	int32_t status = 0, dir = 0, n = 0, ngood = 0, nbad = 0, nshort = 0;
+	uint64_t mask = 0;
+#define LPDU(ptr, ll) do { \
+		if((ll) < 3) nshort++; \
+		else if(orc_fcs_check((ptr), (ll) - 2)) { ngood++; if(n < 64) mask |= 1ull << n; } \
+		else nbad++; \
+		n++; } while(0)
+	if(len < 1) status = 2;
+	else if(buf[0] & 1) {
+		uint32_t hdr_len, lpdu_cnt = 0, ac = 0;
+		if(buf[0] & 0x2) { dir = 1; lpdu_cnt = (buf[0] >> 2) & 0xF; hdr_len = 6 + lpdu_cnt; }
+		else {
+			ac = ((buf[0] & 0x70) >> 4) + 1;
+			hdr_len = 2;
+			for(uint32_t i = 0; i < ac; i++) {
+				if(len < hdr_len + 2) { status = 2; break; }
+				lpdu_cnt = buf[hdr_len + 1] >> 4;
+				hdr_len += 2 + lpdu_cnt;
+			}
+		}
+		if(status == 0 && len < hdr_len + 2) status = 2;
+		if(status == 0 && !orc_fcs_check(buf, hdr_len)) status = 1;
+		if(status == 0) {
+			const uint8_t *data = buf + hdr_len + 2, *end = buf + len;
+			if(dir == 1) {
+				const uint8_t *hp = buf + 6;
+				for(uint32_t j = 0; j < lpdu_cnt; j++) {
+					uint32_t ll = (uint32_t)*hp + 1;
+					if(data + ll > end) break;
+					LPDU(data, ll);
+					data += ll; hp++;
+				}
+			} else {
+				const uint8_t *hp = buf + 2;
+				int stop = 0;
+				for(uint32_t i = 0; i < ac && !stop; i++) {
+					hp++;
+					uint32_t cnt = (*hp++ >> 4) & 0xF;
+					for(uint32_t j = 0; j < cnt; j++) {
+						uint32_t ll = (uint32_t)hp[j] + 1;
+						if(data + ll > end) { stop = 1; break; }
+						LPDU(data, ll);
+						data += ll;
+					}
+					hp += cnt;
+				}
+			}
+		}
+	} else {
+		if(len < 66) status = 2;
+		else if(!orc_fcs_check(buf, 64u)) status = 1;
+	}
+#undef LPDU
+	out[0] = status; out[1] = dir; out[2] = n; out[3] = ngood; out[4] = nbad; out[5] = nshort;
+	if(good_mask) *good_mask = mask;
+}
+
 /* ====================================================================================
  * Viterbi K=7 r=1/2 (libfec/viterbi27_port.c:65-79,92-134,147-221), polys 0x6d,0x4f (fec.h:13-14)
  * ==================================================================================== */

@@ -50,6 +50,35 @@ int orc_tx_make_pdu(int M1, int kind, uint64_t seed, uint8_t *out) {
 	} else if(kind == 1) {
 		out[0] &= (uint8_t)~1u;                        /* SPDU: bit0 clear; FCS over 64 octets (spdu.c:62) */
 		put_fcs(out, 64);
+	} else if(kind == 3) {
+		/* uplink MPDU (mpdu.c:60-75,100-119): two aircraft with 2 and 1 LPDUs; the second LPDU's FCS is broken */
+		int cnt[2] = { 2, 1 }, lens[3] = { 12, 9, 15 };
+		out[0] = (uint8_t)(0x01 | (1 << 4));           /* MPDU, uplink, aircraft_cnt - 1 = 1 */
+		int h = 2, k = 0;
+		for(int a = 0; a < 2; a++) {
+			out[h] = (uint8_t)(0x10 + a);              /* aircraft id */
+			out[h + 1] = (uint8_t)(cnt[a] << 4);
+			for(int j = 0; j < cnt[a]; j++) out[h + 2 + j] = (uint8_t)(lens[k++] - 1);
+			h += 2 + cnt[a];
+		}
+		put_fcs(out, (uint32_t)h);
+		uint8_t *d = out + h + 2;
+		for(int j = 0; j < 3; j++) {
+			d[0] = 0x0D;
+			put_fcs(d, (uint32_t)(lens[j] - 2));
+			if(j == 1) d[lens[j] - 1] ^= 0x5A;
+			d += lens[j];
+		}
+	} else if(kind == 4) {
+		/* downlink MPDU with a too-short LPDU (2 octets, lpdu.c:137) and a last LPDU that runs past the PDU (mpdu.c:152) */
+		int lpdu_cnt = 3;
+		out[0] = (uint8_t)(0x03 | (lpdu_cnt << 2));
+		int hdr_len = 6 + lpdu_cnt;
+		out[6] = 10 - 1; out[7] = 2 - 1; out[8] = 255;
+		put_fcs(out, (uint32_t)hdr_len);
+		uint8_t *d = out + hdr_len + 2;
+		d[0] = 0x0D;
+		put_fcs(d, 8);
 	}
 	/* last 6 information bits are the convolutional tail (decoder forces them to 0); bits are LSB-first */
 	for(int i = nbits - 6; i < L * 8; i++) out[i >> 3] &= (uint8_t)~(1u << (i & 7));

@@ -116,6 +116,52 @@ def compare_pdus(got, ref, truth=None, subset=False):
         assert sorted((f, d) for f, _, d, _, _, _ in g) == sorted(truth)
 
 
+def check_counters(fe, p, freqs, ref):
+    """hfdl_b200_channel_counters (the statsd metrics of doc/STATSD_METRICS.md) vs the oracle: preamble counters from the
+    demodulator, frame / LPDU counters from the front parser restated in orc_pdu_front_parse"""
+    for c, f in enumerate(freqs):
+        k = fe.counters(c)
+        a1, a2, m1, frames = p.stats(c)
+        assert (k.freq, k.A1_found, k.A2_found, k.M1_found, k.M1_not_found) == (f, a1, a2, m1, p.m1_not_found(c))
+        fr = [O.pdu_front(q.data()) for q in ref if q.freq == f]
+        assert k.frames_processed == len(fr) == frames
+        assert (k.frames_good, k.frames_bad_fcs, k.frames_too_short) == tuple(sum(1 for v in fr if v[0] == s) for s in (0, 1, 2))
+        assert (k.frames_air2gnd, k.frames_gnd2air) == (sum(1 for v in fr if v[0] == 0 and v[1] == 1), sum(1 for v in fr if v[0] == 0 and v[1] == 0))
+        assert (k.lpdus_processed, k.lpdus_good, k.lpdus_bad_fcs, k.lpdus_too_short) == tuple(sum(v[i] for v in fr) for i in (2, 3, 4, 5))
+        assert abs(k.noise_floor - p.noise_floor(c)) / p.noise_floor(c) < 1e-3
+        assert abs(fe.noise_floor(c) - p.noise_floor(c)) / p.noise_floor(c) < 1e-3
+
+
+def check_front(got):
+    for q in got:
+        w = O.pdu_front(q.data())
+        assert (q.frame_status, q.direction, q.lpdus_processed, q.lpdus_good, q.lpdus_bad_fcs, q.lpdus_too_short, q.lpdu_good_mask) == w
+        assert q.crc_good == (w[0] == 0)
+
+
+def case_front_parser(lib):
+    pd = [O.make_pdu(m, k, 7 + m) for m in range(8) for k in range(5)] + [b"\x03", b"\x00" * 10, b"\x13\x05"]
+    got = A.pdu_front_parse(pd, lib=lib)
+    for p, g in zip(pd, got):
+        w = O.pdu_front(p)
+        assert tuple(g[:7]) == w and g[7] == (w[0] == 0), (len(p), g, w)
+    # every branch is hit at least once: good / bad_fcs / too_short frames, both directions, bad and short LPDUs
+    assert {g[0] for g in got} == {0, 1, 2} and {g[1] for g in got if g[0] == 0} == {0, 1}
+    assert any(g[4] for g in got) and any(g[5] for g in got)
+
+
+def case_tapslice(lib, sr, freqs):
+    """HFDL_B200_CP_TAPSLICE (fft_channelizer_create, fastddc.c:217-252, reduced to the M bins the slice fold uses) vs the
+    oracle's tap-spectrum slice; device order = inverse-FFT input order = the oracle's slice with its halves swapped"""
+    fe = A.Frontend(sr, CF, freqs, max_blocks_per_batch=2, lib=lib)
+    for c, f in enumerate(freqs):
+        t = fe.checkpoint("tapslice", c)
+        o = np.fft.fftshift(O.slice_taps(sr, CF, f))
+        assert t.size == o.size == fe.geom.fft_inv_size
+        assert rel(t, o) < 1e-5, (f, rel(t, o))
+    fe.close()
+
+
 def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_floats=True, ragged=False, seed=3, ragged_seed=9, esn0=20.0,
                   check_truth=True):
     x, truth = make_capture(sr, freqs, modes, dur, seed=seed, esn0=esn0)
@@ -148,6 +194,8 @@ def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_f
     compare_pdus(got, ref, truth if (sfmt != A.SFMT_CU8 and check_truth) else None)
     for c in range(len(freqs)):
         assert fe.stats(c) == p.stats(c)
+    check_counters(fe, p, freqs, ref)
+    check_front(got)
     if check_floats:
         # spectrum of the last processed block vs the oracle's last spectrum (oracle holds the swapped one)
         spec = fe.checkpoint("spectrum", -1)
@@ -170,7 +218,7 @@ def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_f
     return len(got)
 
 
-def case_frontend_stream(lib, sr, freqs, plan, dur, batch, esn0=20.0, seed=31, push_blocks=None):
+def case_frontend_stream(lib, sr, freqs, plan, dur, batch, esn0=20.0, seed=31, push_blocks=None, submit_poll=False):
     """Several frames per channel over many batches: `plan` = [(channel index, M1, start second), ...].
     Exercises the cross-batch pipeline (sub-range schedule, shared work arrays, deferred PDU collection):
     PDUs, counters and the continuous AGC / matched-filter / equaliser checkpoints must equal the oracle's."""
@@ -190,6 +238,9 @@ def case_frontend_stream(lib, sr, freqs, plan, dur, batch, esn0=20.0, seed=31, p
     if push_blocks:
         for i in range(0, x.size, push_blocks * isz):
             fe.push(x[i:i + push_blocks * isz])
+            if submit_poll:                        # the block shim's use: queue what is there, pick up what has finished
+                fe.submit()
+                fe.poll()
             got += fe.pdus()                       # streaming use: PDUs are picked up as the pipeline delivers them
     else:
         fe.push(x)
@@ -198,6 +249,7 @@ def case_frontend_stream(lib, sr, freqs, plan, dur, batch, esn0=20.0, seed=31, p
     compare_pdus(got, ref, truth, subset=True)
     for c in range(len(freqs)):
         assert fe.stats(c) == p.stats(c)
+    check_counters(fe, p, freqs, ref)
     for name in ("agc", "mf", "eq"):
         a, b = fe.checkpoint(name), p.capture(0, name)
         assert a.size == b.size and rel(a, b) < TOL_DEMOD, name

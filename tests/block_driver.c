@@ -1,8 +1,13 @@
-/* tests/block_driver.c -- drives libhfdl_b200.so (or the host-emulation build) through the block.c contract the
- * way dumphfdl's main.c does (main.c:687-755,770-774): an input block produces CF32 into the one2one ring
- * (file_input_thread + complex_samples_produce, input-file.c:35-74, input-helpers.c:80-92), the GPU front-end
- * block consumes it, EOF triggers the ordered shutdown of block.c:137-143.  Prints one line per PDU.
- * usage: block_driver <lib.so> <capture.cf32> <sample_rate> <centerfreq_hz> <freq_hz>... */
+/* tests/block_driver.c -- drives libhfdl_b200.so (or the host-emulation build) through the REFERENCE'S OWN block.c
+ * the way dumphfdl's main.c does (main.c:687-755,770-774,789-802).  oracle/_ref/libref.so holds the reference's
+ * block.c and input-helpers.c compiled where they lie, a cbuffercf with liquid-dsp's API and the downstream callee
+ * pdu_decoder_queue_push as a capture list (oracle/ref_shim/ref_host.c); it is loaded RTLD_GLOBAL first, so the
+ * front-end library's weak references (cbuffercf_*, hfdl_pdu_metadata_create, octet_string_new,
+ * pdu_decoder_queue_push) bind to it exactly as they would bind to dumphfdl + libliquid.
+ *   input thread  = file_input_thread (input-file.c:35-74): read, wait for ring space, complex_samples_produce
+ *   wiring        = block_connect_one2one(input, gpu) / block_start / block_connection_one2one_shutdown / block_is_running
+ * Prints one line per PDU as the reference's decoder thread would receive it (struct hfdl_pdu_metadata, pdu.h:8-17).
+ * usage: block_driver <libref.so> <lib.so> <capture.cf32> <sample_rate> <centerfreq_hz> <ngpus> <freq_hz>... */
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -10,32 +15,37 @@
 #include <unistd.h>
 #include "../include/hfdl_b200_block.h"
 
-static pthread_mutex_t out_lock = PTHREAD_MUTEX_INITIALIZER;
-static void on_pdu(const hfdl_b200_pdu_t *p, void *user) {
-	(void)user;
-	pthread_mutex_lock(&out_lock);
-	printf("PDU %d %d %d %llu ", p->freq, p->M1, p->crc_good, (unsigned long long)p->sample_cnt_a2);
-	for(int i = 0; i < p->len; i++) printf("%02x", p->octets[i]);
-	printf("\n");
-	pthread_mutex_unlock(&out_lock);
-}
+typedef struct {       /* ref_pdu_t of oracle/ref_shim/ref_host.c */
+	int32_t version, freq, bit_rate;
+	float freq_err_hz, rssi, noise_floor;
+	char slot;
+	int32_t len;
+	uint32_t flags;
+	uint8_t octets[948];
+} ref_pdu_t;
 
-struct api {
-	struct block *(*create)(int32_t, int32_t, const int32_t *, int32_t, int32_t);
-	void (*destroy)(struct block *);
-	void (*set_cb)(struct block *, hfdl_gpu_pdu_callback, void *);
-	cbuffercf (*cb_create)(unsigned int);
-	void (*cb_destroy)(cbuffercf);
+static struct {
+	int32_t (*connect)(struct block *, struct block *);
+	void (*disconnect)(struct block *, struct block *);
+	int32_t (*start)(struct block *);
+	void (*shutdown)(struct block_connection *);
+	bool (*is_running)(struct block *);
+	void (*produce)(struct circ_buffer *, float *, size_t);
 	unsigned int (*cb_space)(cbuffercf);
-	int (*cb_write)(cbuffercf, void *, unsigned int);
+	int (*pdu_count)(void);
+	int (*pdu_get)(int, ref_pdu_t *);
+	struct block *(*create)(int32_t, int32_t, const int32_t *, int32_t, int32_t, int32_t);
+	void (*destroy)(struct block *);
+	int32_t (*counters)(struct block *, int32_t, hfdl_b200_counters_t *);
+	int32_t (*nf_db)(struct block *, int32_t, float *);
 } A;
 
 struct input { struct block block; FILE *fh; };
 
 static void *input_thread(void *ctx) {               /* file_input_thread, input-file.c:35-74 */
-	struct input *in = ctx;
+	struct input *in = (struct input *)ctx;
 	struct circ_buffer *cb = &in->block.producer.out->circ_buffer;
-	const size_t batch = 40000;                      /* 320000-byte default read buffer / 8 */
+	const size_t batch = in->block.producer.max_tu;
 	float *buf = malloc(batch * 8);
 	size_t n;
 	do {
@@ -45,65 +55,71 @@ static void *input_thread(void *ctx) {               /* file_input_thread, input
 			size_t space = A.cb_space(cb->buf);
 			pthread_mutex_unlock(cb->mutex);
 			if(space >= n) break;
-			usleep(1000);
+			usleep(500);
 		}
-		pthread_mutex_lock(cb->mutex);              /* complex_samples_produce */
-		A.cb_write(cb->buf, buf, (unsigned int)n);
-		pthread_mutex_unlock(cb->mutex);
-		pthread_cond_signal(cb->cond);
+		A.produce(cb, buf, n);                       /* complex_samples_produce, input-helpers.c:80-92 */
 	} while(n > 0);
-	pthread_mutex_lock(cb->mutex);                  /* block_connection_one2one_shutdown */
-	in->block.producer.out->flags |= BLOCK_CONNECTION_SHUTDOWN;
-	pthread_mutex_unlock(cb->mutex);
-	pthread_cond_signal(cb->cond);
+	A.shutdown(in->block.producer.out);              /* block_connection_one2one_shutdown, input-file.c:68 */
 	in->block.running = false;
 	free(buf);
 	return NULL;
 }
 
+#define SYM(h, field, name) do { *(void **)&A.field = dlsym(h, name); if(!A.field) { fprintf(stderr, "missing symbol %s\n", name); return 2; } } while(0)
+
 int main(int argc, char **argv) {
-	if(argc < 6) { fprintf(stderr, "usage\n"); return 2; }
-	void *h = dlopen(argv[1], RTLD_NOW | RTLD_GLOBAL);
+	if(argc < 8) { fprintf(stderr, "usage: block_driver libref.so lib.so capture.cf32 sample_rate centerfreq ngpus freq...\n"); return 2; }
+	void *hr = dlopen(argv[1], RTLD_NOW | RTLD_GLOBAL);
+	if(!hr) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
+	void *h = dlopen(argv[2], RTLD_NOW | RTLD_GLOBAL);
 	if(!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
-	A.create = dlsym(h, "hfdl_gpu_frontend_create"); A.destroy = dlsym(h, "hfdl_gpu_frontend_destroy");
-	A.set_cb = dlsym(h, "hfdl_gpu_frontend_set_pdu_callback");
-	A.cb_create = dlsym(h, "cbuffercf_create"); A.cb_destroy = dlsym(h, "cbuffercf_destroy");
-	A.cb_space = dlsym(h, "cbuffercf_space_available"); A.cb_write = dlsym(h, "cbuffercf_write");
-	if(!A.create || !A.destroy || !A.set_cb || !A.cb_create || !A.cb_space || !A.cb_write) { fprintf(stderr, "missing symbols\n"); return 2; }
-	int32_t sr = atoi(argv[3]), cf = atoi(argv[4]);
-	int nf = argc - 5;
+	SYM(hr, connect, "block_connect_one2one"); SYM(hr, disconnect, "block_disconnect_one2one"); SYM(hr, start, "block_start");
+	SYM(hr, shutdown, "block_connection_one2one_shutdown"); SYM(hr, is_running, "block_is_running");
+	SYM(hr, produce, "complex_samples_produce"); SYM(hr, cb_space, "cbuffercf_space_available");
+	SYM(hr, pdu_count, "ref_pdu_count"); SYM(hr, pdu_get, "ref_pdu_get");
+	SYM(h, create, "hfdl_gpu_frontend_create"); SYM(h, destroy, "hfdl_gpu_frontend_destroy");
+	SYM(h, counters, "hfdl_gpu_frontend_counters"); SYM(h, nf_db, "hfdl_gpu_frontend_noise_floor_db");
+	int32_t sr = atoi(argv[4]), cf = atoi(argv[5]), ngpus = atoi(argv[6]);
+	int nf = argc - 7;
 	int32_t freqs[512];
-	for(int i = 0; i < nf; i++) freqs[i] = atoi(argv[5 + i]);
+	for(int i = 0; i < nf; i++) freqs[i] = atoi(argv[7 + i]);
 	struct input in;
 	memset(&in, 0, sizeof(in));
-	in.fh = fopen(argv[2], "rb");
+	in.fh = fopen(argv[3], "rb");
 	if(!in.fh) { perror("capture"); return 2; }
 	in.block.producer.type = PRODUCER_SINGLE;
-	in.block.producer.max_tu = 40000;
-	struct block *fe = A.create(sr, cf, freqs, nf, 0);
+	in.block.producer.max_tu = 40000;                /* 320000-byte default read buffer / 8 (input-file.c:16,107) */
+	in.block.thread_routine = input_thread;
+	struct block *fe = A.create(sr, cf, freqs, nf, 0, ngpus);
 	if(!fe) return 1;
-	A.set_cb(fe, on_pdu, NULL);
-	/* block_connect_one2one (block.c:55-76) */
-	size_t bs = 8 * in.block.producer.max_tu;
-	if(2 * fe->consumer.min_ru > bs) bs = 2 * fe->consumer.min_ru;
-	struct block_connection *conn = calloc(1, sizeof(*conn));
-	conn->circ_buffer.buf = A.cb_create((unsigned int)bs);
-	conn->circ_buffer.cond = calloc(1, sizeof(pthread_cond_t));
-	conn->circ_buffer.mutex = calloc(1, sizeof(pthread_mutex_t));
-	pthread_cond_init(conn->circ_buffer.cond, NULL);
-	pthread_mutex_init(conn->circ_buffer.mutex, NULL);
-	in.block.producer.out = fe->consumer.in = conn;
-	/* block_start (block.c:157-166) */
-	fe->running = true;
-	pthread_create(&fe->thread, NULL, fe->thread_routine, fe);
-	in.block.running = true;
-	pthread_create(&in.block.thread, NULL, input_thread, &in);
-	while(in.block.running || fe->running) usleep(2000);     /* main.c:789-802 */
-	pthread_join(in.block.thread, NULL);
-	pthread_join(fe->thread, NULL);
+	if(A.connect(&in.block, fe) != 1) { fprintf(stderr, "block_connect_one2one failed\n"); return 1; }       /* main.c:752 */
+	if(A.start(fe) != 1 || A.start(&in.block) != 1) { fprintf(stderr, "block_start failed\n"); return 1; }   /* main.c:771-772 */
+	/* a stats thread would poll while the blocks run (noise_floor_stats_thread, hfdl.c:1082-1105): do so here */
+	int polls = 0;
+	while(A.is_running(&in.block) || A.is_running(fe)) {     /* main.c:794-802 */
+		float db; hfdl_b200_counters_t c;
+		for(int i = 0; i < nf; i++) { A.nf_db(fe, i, &db); A.counters(fe, i, &c); }
+		polls++;
+		usleep(2000);
+	}
+	for(int i = 0; i < A.pdu_count(); i++) {
+		ref_pdu_t p;
+		A.pdu_get(i, &p);
+		printf("PDU %d %d %c %d %.6g %.6g %.6g ", p.freq, p.bit_rate, p.slot, p.version, p.freq_err_hz, p.rssi, p.noise_floor);
+		for(int k = 0; k < p.len; k++) printf("%02x", p.octets[k]);
+		printf("\n");
+	}
+	for(int i = 0; i < nf; i++) {
+		hfdl_b200_counters_t c;
+		if(A.counters(fe, i, &c) == 0)
+			printf("CNT %d %lld %lld %lld %lld %lld %lld %lld %lld %lld %lld\n", c.freq, (long long)c.A2_found, (long long)c.M1_found, (long long)c.M1_not_found,
+				(long long)c.frames_processed, (long long)c.frames_good, (long long)c.frames_bad_fcs, (long long)c.frames_air2gnd, (long long)c.frames_gnd2air,
+				(long long)c.lpdus_processed, (long long)c.lpdus_good);
+	}
+	printf("POLLS %d\n", polls);
 	fflush(stdout);
+	A.disconnect(&in.block, fe);
 	A.destroy(fe);
-	A.cb_destroy(conn->circ_buffer.buf);
 	fclose(in.fh);
 	return 0;
 }

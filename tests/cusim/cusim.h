@@ -194,3 +194,9 @@ static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigne
 template <typename T> static inline cudaError_t cudaFuncSetAttribute(T, int, int) { return 0; }
 struct cudaDeviceProp { char name[256]; int major, minor, multiProcessorCount; size_t totalGlobalMem; };
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { memset(p, 0, sizeof(*p)); strcpy(p->name, "cusim"); p->major = 10; p->multiProcessorCount = 148; return 0; }
+enum { cudaErrorNotReady = 600 };
+static inline cudaError_t cudaEventQuery(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return 0; }
+static inline cudaError_t cudaMemcpyPeerAsync(void *d, int, const void *s, int, size_t n, cudaStream_t) { memmove(d, s, n); return 0; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return 0; }

@@ -73,6 +73,10 @@ def lib(fast=False):
     L.orc_channelizer_create.restype = C.c_void_p
     L.orc_channelizer_create.argtypes = [C.c_int32, C.c_float, C.c_float, C.c_int]
     L.orc_channelizer_destroy.argtypes = [C.c_void_p]
+    L.orc_channelizer_taps.restype = C.POINTER(C.c_float)
+    L.orc_channelizer_taps.argtypes = [C.c_void_p]
+    L.orc_channelizer_ddc.restype = C.POINTER(Ddc)
+    L.orc_channelizer_ddc.argtypes = [C.c_void_p]
     L.orc_channelizer_execute.argtypes = [C.c_void_p, cfp, cfp]
     L.orc_swap_sides.argtypes = [cfp, C.c_int32]
     L.orc_firdes_kaiser.argtypes = [C.c_int, C.c_float, C.c_float, C.c_float, np.ctypeslib.ndpointer(np.float32)]
@@ -86,6 +90,8 @@ def lib(fast=False):
     L.orc_crc16.argtypes = [u8p, C.c_uint32, C.c_uint16]
     L.orc_pdu_crc_good.argtypes = [u8p, C.c_uint32]
     L.orc_viterbi27.argtypes = [u8p, C.c_int, u8p]
+    L.orc_pdu_front_parse.argtypes = [u8p, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)]
+    L.orc_pdu_front_parse.restype = None
     L.orc_conv_encode27.argtypes = [u8p, C.c_int, u8p]
     L.orc_scrambler_bits.argtypes = [u8p, C.c_int]
     L.orc_scrambler_bits.restype = C.c_uint32
@@ -300,6 +306,26 @@ def geometry(sample_rate):
     tbw = L.orc_relative_transition_bw(sample_rate, 250)
     d, _ = ddc_init(tbw, dec, 0.0)
     return dec, tbw, d
+
+
+def pdu_front(buf):
+    """orc_pdu_front_parse -> (status, direction, lpdus processed, good, bad_fcs, too_short, good mask)"""
+    a = np.frombuffer(bytes(buf), np.uint8).copy()
+    out = (C.c_int32 * 6)()
+    m = C.c_uint64()
+    lib().orc_pdu_front_parse(a, a.size, out, C.byref(m))
+    return tuple(out) + (m.value,)
+
+
+def slice_taps(sample_rate, centerfreq, freq):
+    """tap-spectrum slice of one channel as the oracle's slice fold uses it: M bins, index i <-> swapped bin startbin-M/2+i"""
+    L = lib()
+    dec, tbw, _ = geometry(sample_rate)
+    c = L.orc_channelizer_create(dec, tbw, L.orc_channel_shift_rate(sample_rate, centerfreq, freq), FOLD_SLICE)
+    M = L.orc_channelizer_ddc(c).contents.fft_inv_size
+    out = np.ctypeslib.as_array(L.orc_channelizer_taps(c), shape=(2 * M,)).copy().view(np.complex64)
+    L.orc_channelizer_destroy(c)
+    return out
 
 
 def make_pdu(M1, kind=0, seed=1):

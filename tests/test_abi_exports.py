@@ -40,3 +40,19 @@ def test_no_cpu_fallback_without_a_device():
     import numpy as np
     with pytest.raises(RuntimeError):
         hb.fft_forward(np.zeros(64, np.complex64))
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="libhfdl_b200.so not built")
+def test_library_does_not_define_host_program_symbols():
+    """The ring (liquid-dsp's cbuffercf) and the PDU hand-off belong to the host program: the library only holds weak
+    references to them and must not define (and so interpose) any of them."""
+    import subprocess
+    out = subprocess.run(["nm", "-D", LIB], capture_output=True, text=True, check=True).stdout
+    rows = [l.split() for l in out.splitlines()]
+    for name in ("cbuffercf_size", "cbuffercf_read", "cbuffercf_release", "pdu_decoder_queue_push", "hfdl_pdu_metadata_create", "octet_string_new"):
+        kinds = [r[-2] for r in rows if r and r[-1] == name]
+        assert kinds and all(k in ("w", "U") for k in kinds), (name, kinds)
+    defined = [r[-1] for r in rows if len(r) == 3 and r[1] in ("T", "D", "B") and r[-1].startswith("cbuffercf")]
+    assert not defined, defined
+    # and nothing of the test-side oracle is linked in
+    assert not any("orc_" in r[-1] for r in rows if r)

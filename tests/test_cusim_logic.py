@@ -49,3 +49,17 @@ def test_stream_small_batches_pickup(sim):
     # host-emulation run of the streaming case (pipeline bookkeeping: set alternation, deferred collection, frame slots)
     plan = [(0, 0, 0.2), (0, 1, 3.2)]
     assert K.case_frontend_stream(sim, 250000, [10063000], plan, 6.2, batch=2, push_blocks=3, seed=33) == 2
+
+
+def test_stream_submit_poll(sim):
+    # the block shim's use of the C ABI: push + hfdl_b200_submit + hfdl_b200_poll, never a flush before the end
+    plan = [(0, 1, 0.2), (1, 2, 0.6)]
+    assert K.case_frontend_stream(sim, 250000, [10063000, 9952000], plan, 3.4, batch=4, push_blocks=1, seed=35, submit_poll=True) == 2
+
+
+def test_front_parser(sim):
+    K.case_front_parser(sim)
+
+
+def test_tapslice_checkpoint(sim):
+    K.case_tapslice(sim, 250000, [10063000, 9931000])

@@ -73,6 +73,108 @@ def test_frontend_three_pass_fft_plan(lib):
     assert K.case_frontend(lib, sr, freqs, [1, 3, 0], 2.9, batch=5, seed=17) == 3
 
 
+def test_frontend_cfg3_geometry_many_channels(lib):
+    """BASELINE config 3 geometry: 20 Msps -> N = 2^22 (three-pass FFT, 2 blocks per L2-sized sub-batch), M = 4096,
+    1792 outputs per block, resampler 0.55296; 40 channels spread over the band, all four single-slot modes.
+    PDUs, counters, front parser, spectrum / channeliser / AGC / MF / EQ checkpoints vs the oracle."""
+    sr = 20000000
+    nch = 40
+    delta = int(0.85 * sr / nch / 1000) * 1000
+    freqs = [int(round((K.CF + (k - (nch - 1) / 2) * delta) / 1000.0)) * 1000 for k in range(nch)]
+    fe = A.Frontend(sr, K.CF, freqs[:1], max_blocks_per_batch=1, lib=lib)
+    g = fe.geom
+    assert (g.fft_size, g.fft_inv_size, g.input_size, g.out_per_block, g.fft_passes) == (1 << 22, 4096, 3670016, 1792, 3)
+    assert abs(g.resamp_rate - 0.55296) < 1e-6
+    fe.close()
+    assert K.case_frontend(lib, sr, freqs, [k % 4 for k in range(nch)], 2.75, batch=5, seed=23) == nch
+
+
+def test_tapslice_checkpoint_vs_oracle(lib):
+    # cfg 2 and cfg 3 geometries: the tap spectrum the slice fold multiplies with (fastddc.c:217-252)
+    K.case_tapslice(lib, 2000000, [K.CF + 212000, K.CF - 777000])
+    K.case_tapslice(lib, 20000000, [K.CF + 8123000, K.CF - 40000, K.CF - 9001000])
+
+
+def test_front_parser_all_branches(lib):
+    K.case_front_parser(lib)
+
+
+def test_streaming_submit_poll(lib):
+    # the block shim's use of the C ABI: hfdl_b200_push_samples + hfdl_b200_submit + hfdl_b200_poll, no flush before the end
+    plan = [(0, 0, 0.2), (0, 2, 3.2), (1, 3, 0.5), (1, 1, 3.5), (2, 1, 1.4)]
+    assert K.case_frontend_stream(lib, 250000, [10063000, 9952000, 10101000], plan, 6.4, batch=4, push_blocks=1, seed=37, submit_poll=True) >= 4
+
+
+def test_entry_points_from_other_threads_and_devices(lib):
+    """The current CUDA device is per host thread: a frontend created here must work when it is pushed, polled and
+    queried from other threads (block.c starts the thread routine on a fresh pthread; a stats thread reads beside it).
+    With two GPUs the frontend lives on device 1 while every calling thread's current device is 0."""
+    import threading
+    dev = 1 if lib.hfdl_b200_device_count() >= 2 else 0
+    sr, freqs = 250000, [10063000, 9952000]
+    x, truth = K.make_capture(sr, freqs, [1, 2], 3.3, seed=21)
+    p = K.run_oracle(sr, freqs, x, O.SFMT_CF32)
+    fe = A.Frontend(sr, K.CF, freqs, max_blocks_per_batch=4, device=dev, lib=lib)
+    isz = fe.geom.input_size
+    err, stop = [], [False]
+
+    def pusher():
+        try:
+            for i in range(0, x.size, isz):
+                fe.push(x[i:i + isz])
+                fe.submit()
+                fe.poll()
+            fe.flush()
+        except Exception as e:       # noqa: BLE001
+            err.append(e)
+
+    def reader():
+        try:
+            while not stop[0]:
+                for c in range(len(freqs)):
+                    assert fe.noise_floor(c) > 0
+                    fe.counters(c)
+        except Exception as e:       # noqa: BLE001
+            err.append(e)
+
+    t1, t2 = threading.Thread(target=pusher), threading.Thread(target=reader)
+    t2.start()
+    t1.start()
+    t1.join()
+    stop[0] = True
+    t2.join()
+    assert not err, err
+    K.compare_pdus(fe.pdus(), p.pdus(), truth)
+    K.check_counters(fe, p, freqs, p.pdus())
+    fe.close()
+
+
+def test_two_gpus_peer_broadcast_equals_single(lib):
+    """Channels k mod 2 on two GPUs, the capture pushed to GPU 0 only and copied ring to ring over NVLink
+    (hfdl_b200_push_peer): the union of the PDUs equals the oracle's list."""
+    if lib.hfdl_b200_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sr = 2000000
+    freqs = [K.CF + 212000, K.CF - 424000, K.CF + 636000, K.CF - 100000]
+    x, truth = K.make_capture(sr, freqs, [3, 5, 0, 2], 5.8, seed=35)
+    ref = K.run_oracle(sr, freqs, x, O.SFMT_CF32).pdus()
+    fes = [A.Frontend(sr, K.CF, freqs[d::2], max_blocks_per_batch=6, device=d, lib=lib) for d in range(2)]
+    isz = fes[0].geom.input_size
+    got = []
+    for i in range(0, x.size, 3 * isz):
+        fes[0].push(x[i:i + 3 * isz])
+        fes[1].push_peer(fes[0])
+        for f in fes:
+            f.submit()
+            f.poll()
+            got += f.pdus()
+    for f in fes:
+        f.flush()
+        got += f.pdus()
+        f.close()
+    K.compare_pdus(got, ref, truth)
+
+
 def test_frontend_low_snr_equals_oracle(lib):
     """Es/N0 = 8 and 5 dB: decisions are marginal and some payloads come back with bit errors behind a good header FCS;
     the GPU path must still produce exactly the oracle's PDU list, counters and float checkpoints."""
