@@ -1,26 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json metric on BASELINE config 2 (2 Msps CF32, 8 HFDL channels) per GPU.
+"""bench.py -- BASELINE.json's metric (I/Q Msamples/s ingested, CRC-good PDUs/s) on BASELINE's own configurations.
 
   python bench.py --gpus N --steps K --warmup W            our arm  (libhfdl_b200.so, sm_100a kernels)
-  python bench.py --impl reference --gpus N ...            the reference's CPU path on the host cores
-                                                           (oracle/_ref is only partial -> restated CPU reference,
-                                                            oracle/liboracle_fast.so built -O3 -ffast-math like the
-                                                            reference, all host threads, full-N fold as fastddc.c)
+  python bench.py --impl reference --gpus N ...            the reference's CPU path on the host cores: the reference's
+                                                           own block.c / fft.c / fastddc.c / hfdl.c / viterbi27_port.c
+                                                           compiled where they lie (oracle/_ref/libref_fast.so, -O3
+                                                           -ffast-math like src/CMakeLists.txt:39-42), one thread per
+                                                           channel + FFT threads exactly as dumphfdl runs them; liquid-dsp
+                                                           and fftw3f (not installed) are served by the oracle's objects /
+                                                           FFT (fftw3f is used when the box has it)
 
-A "step" is one pass of the hot path over one synthetic slab: SLOTS*22 overlap-save blocks of a looped
-multichannel capture (frames placed cyclically so the stream is seamless across steps).
-  value : I/Q Msamples/s ingested with the slab resident in HBM (device timed, CUDA events)
-  e2e   : same metric through hfdl_b200_push_samples() with pinned HOST buffers: H2D of the slab and D2H of the
-          PDUs inside the timed region
-The synthetic capture and the list of transmitted PDUs come from the HFDL transmitter that lives with the test
-infrastructure (oracle/orc_tx.c via tests/orclib.py): input generation and the exactness check of the decoded PDUs,
-outside every timed region and never on the product path.  The only oracle code that is TIMED is the cpu_baseline /
---impl reference leg.
-N>1: one process per GPU (torchrun); every GPU owns an independent 2 Msps capture and its 8 channels end to end
-(weak scaling, no data-path collective); --shared-spectrum broadcasts one capture over NCCL instead and shards
-the channels."""
+Workload by GPU count (BASELINE.json configs): N = 1, 2 -> cfg3 (20 Msps, 128 channels: the largest single-GPU
+configuration), N = 4 -> cfg4 (30 Msps, 256 channels), N = 8 -> cfg5 (60 Msps, 512 channels); --workload overrides
+(cfg2 = 2 Msps, 8 channels is still available).  The capture is ONE looped multichannel slab (frames placed cyclically, so
+the stream is seamless across passes); a "step" is LOOPS passes of the hot path over it.
+  value : Msamples/s with the capture resident in HBM when the timed region starts (device timed, CUDA events).
+          N > 1: resident on rank 0; every pass broadcasts it over NCCL/NVLink inside the timed region, every rank runs the
+          forward FFT on the whole capture and demodulates its own channels (channel k on rank k mod N).
+  e2e   : the same metric from pinned HOST memory, copies inside the timed region.  N = 1: hfdl_b200_push_samples (H2D
+          inside the C-ABI call) + PDU records D2H.  N > 1: the host scatters the slab -- rank r uploads the r-th 1/N of
+          every pass over its own PCIe link, an NCCL all-gather over NVLink completes the capture on every GPU -- then
+          hfdl_b200_process_device; the capture crosses PCIe exactly once.
+The synthetic capture and the list of transmitted PDUs come from the HFDL transmitter of the test infrastructure
+(oracle/orc_tx.c via tests/orclib.py): input generation and the exactness check of the decoded PDUs, outside every timed
+region and never on the product path.  The only oracle/ code that is TIMED is the cpu_baseline / --impl reference leg."""
 import argparse
-import ctypes as C
 import json
 import os
 import subprocess
@@ -34,59 +38,77 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-SR = 2000000
-NCH = 8
 CF = 100000000            # centre 100 000 kHz (only differences matter)
-BLOCKS_PER_SLOT = 22      # 22 * 229376 / 2e6 = 2.523 s >= one 2.344 s single-slot frame
-SLOTS = 4                 # slab = 88 blocks = 20.2 Msamples = 161 MB CF32 (> 126 MB L2)
-WORKLOAD = "cfg2"
-
-
-def set_workload(name):
-    """cfg2 (BASELINE configs[1]) is the headline; cfg3 (20 Msps, 128 channels, configs[2]) is an extra,
-    non-headline measurement of how the path behaves with many channels."""
-    global SR, NCH, BLOCKS_PER_SLOT, SLOTS, SEED, WORKLOAD
-    WORKLOAD = name
-    if name == "cfg3":
-        SR, NCH, BLOCKS_PER_SLOT, SLOTS, SEED = 20000000, 128, 14, 1, 635003
 ESN0_DB = 20.0
-SEED = 635002             # SURVEY 8(d): 635000 + cfg_index
 METRIC = "I/Q Msamples/s & CRC-good PDUs/s at 1/2/4/8 B200 vs fftw CPU ref"
+# blocks_per_slot * input_size / sample_rate >= one 2.344 s single-slot frame; seed = 635000 + cfg index;
+# loops = passes over the slab per step (so that K = 20 steps time more than a second of device work)
+WORKLOADS = {
+    "cfg2": dict(sr=2000000, nch=8, blocks_per_slot=22, slots=4, seed=635002, loops=16, group=0),
+    "cfg3": dict(sr=20000000, nch=128, blocks_per_slot=14, slots=1, seed=635003, loops=32, group=0),
+    "cfg4": dict(sr=30000000, nch=256, blocks_per_slot=21, slots=1, seed=635004, loops=16, group=64),
+    "cfg5": dict(sr=60000000, nch=512, blocks_per_slot=21, slots=1, seed=635005, loops=16, group=64),
+}
+DEFAULT_BY_GPUS = {1: "cfg3", 2: "cfg3", 4: "cfg4", 8: "cfg5"}
 
 
-def channel_freqs(nch=None):
-    nch = nch or NCH
-    delta = int(0.85 * SR / nch / 1000) * 1000
-    return [int(round((CF + (k - (nch - 1) / 2) * delta) / 1000.0)) * 1000 for k in range(nch)]
+def channel_freqs(W):
+    nch, sr = W["nch"], W["sr"]
+    delta = int(0.85 * sr / nch / 1000) * 1000
+    return [int(np.floor((CF + (k - (nch - 1) / 2) * delta) / 1000.0 + 0.5)) * 1000 for k in range(nch)], delta
 
 
-def build_slab(O, seed, nthreads):
-    """Cyclic slab: per channel, back-to-back frames of random modes filling SLOTS slots."""
-    d = O.geometry(SR)[2]
-    isz = d.input_size
-    nblocks = BLOCKS_PER_SLOT * SLOTS
+def plan_frames(O, W, isz):
+    """Cyclic slab: per channel, back-to-back frames of random modes filling the slots.  cfg4 / cfg5 (hundreds of
+    channels at 30 / 60 Msps): frames are planned for the lowest `group` channels only; the other channels carry
+    frequency-shifted copies of that sub-band (see render_range) -- same modulation, same PDUs, different frequency."""
+    freqs, delta = channel_freqs(W)
+    nbase = W["group"] or W["nch"]
+    nblocks = W["blocks_per_slot"] * W["slots"]
     nsamp = nblocks * isz
-    slot_s = BLOCKS_PER_SLOT * isz / SR
-    rng = np.random.default_rng(seed)
-    amp = 0.25 / np.sqrt(NCH) / np.sqrt(0.947)
-    frames, truth = [], []
-    for k, f in enumerate(channel_freqs()):
+    slot_s = W["blocks_per_slot"] * isz / W["sr"]
+    rng = np.random.default_rng(W["seed"])
+    amp = 0.25 / np.sqrt(W["nch"]) / np.sqrt(0.947)
+    frames, base_truth = [], []
+    for k in range(nbase):
+        f = freqs[k]
         slot = 0
         phase = float(rng.uniform(0, slot_s))            # random start offset of this channel's slot grid
-        while slot < SLOTS:
-            m = int(rng.integers(0, 8 if SLOTS >= 2 else 4))
+        while slot < W["slots"]:
+            m = int(rng.integers(0, 8 if W["slots"] >= 2 else 4))
             need = 2 if m >= 4 else 1
-            if slot + need > SLOTS:
+            if slot + need > W["slots"]:
                 m -= 4
                 need = 1
             flen = (448 + 531 + (168 if m >= 4 else 72) * 45) / 1800.0 + 0.02
-            start = (phase + slot * slot_s + float(rng.uniform(0, need * slot_s - flen))) % (nsamp / SR)
+            start = (phase + slot * slot_s + float(rng.uniform(0, need * slot_s - flen))) % (nsamp / W["sr"])
             pdu = O.make_pdu(m, int(rng.integers(0, 2)), seed=int(rng.integers(1, 1 << 30)))
             frames.append(O.tx_frame(f, m, start, pdu, cfo_hz=float(rng.uniform(-20, 20)), phase0=float(rng.uniform(0, 2 * np.pi)), amplitude=amp))
-            truth.append((f, pdu))
+            base_truth.append((k, pdu))
             slot += need
-    x = O.render(nsamp, SR, CF, frames, noise_sigma=O.noise_sigma(amp, SR, ESN0_DB), seed=seed, cyclic=True, nthreads=nthreads)
-    return x, truth, nblocks, isz
+    ngroups = W["nch"] // nbase
+    truth = [(freqs[k + g * nbase], pdu) for g in range(ngroups) for k, pdu in base_truth]
+    return dict(freqs=freqs, delta=delta, frames=frames, truth=truth, nblocks=nblocks, nsamp=nsamp, amp=amp, nbase=nbase, ngroups=ngroups)
+
+
+def render_range(O, W, P, first, count, nthreads, noise_seed):
+    """Samples [first, first + count) of the looped slab."""
+    sr = W["sr"]
+    x = O.render_range(first, count, P["nsamp"], sr, CF, P["frames"], cyclic=True, nthreads=nthreads)
+    if P["ngroups"] > 1:
+        # sub-band copies: x(t) = sum_g base(t) * exp(j 2 pi F_g t), F_g = g * group * delta moved to the nearest multiple
+        # of 1 / T_slab (< 0.2 Hz away) so that every copy is continuous across the wrap of the cyclic slab
+        T = P["nsamp"] / sr
+        n = np.arange(first, first + count, dtype=np.float64)
+        out = x.copy()
+        for g in range(1, P["ngroups"]):
+            Fg = round(g * P["nbase"] * P["delta"] * T) / T
+            ph = (Fg / sr * n) % 1.0
+            out += x * np.exp(2j * np.pi * ph).astype(np.complex64)
+        x = out
+    sig = O.noise_sigma(P["amp"], sr, ESN0_DB)
+    O.lib().orc_tx_add_noise(x, x.size, sig, noise_seed, nthreads)
+    return x
 
 
 class ClockSampler:
@@ -162,93 +184,147 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "source": "nvidia-smi"}
 
 
-def best_threads(O, x, isz, nblocks_avail):
-    """The reference lets the user pick --fft-threads; its channel threads are one per channel.  Sweep the thread
-    count on a short probe and keep the fastest, so the CPU arm is not handicapped by oversubscription."""
+def config_of(name, W, P, world):
+    """Identical for both arms: names the workload only (arm-specific step sizes are reported under "step")."""
+    if world > 1:
+        shard = "%d GPUs: one capture, channel k on GPU k mod %d (%d channels per GPU); value: NCCL broadcast from rank 0 every pass; e2e: host scatter (1/%d of every pass per PCIe link) + NCCL all-gather" % (world, world, W["nch"] // world, world)
+    else:
+        shard = "1 GPU: all %d channels" % W["nch"]
+    return {"workload": "%s: %.0f Msps CF32, %d HFDL channels, synthetic looped slab of %d overlap-save blocks (%.1f Msamples, %.0f MB > 126 MB L2, no explicit flush), "
+                        "Es/N0 %.0f dB, seed %d" % (name, W["sr"] / 1e6, W["nch"], P["nblocks"], P["nsamp"] / 1e6, P["nsamp"] * 8 / 1e6, ESN0_DB, W["seed"]),
+            "sample_rate": W["sr"], "channels": W["nch"], "blocks_per_slab": P["nblocks"], "esn0_db": ESN0_DB, "sharding": shard}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_setup(O, W, P):
     cores = os.cpu_count() or 1
-    cands = sorted({t for t in (2, 4, 8, 16, 32, cores) if t <= cores})
-    probe = min(4, nblocks_avail)
-    best = (None, 1e30)
-    for t in cands:
-        p = O.Pipeline(SR, CF, channel_freqs(), fold_mode=O.FOLD_FULL, nthreads=t, fast=True)
-        p.feed(x[: isz])                       # warm the twiddle tables / page in
+    fast = O.reflib_fast()
+    if fast is not None:
+        kind = "reference"
+        fft_threads = max(1, min(cores, 8))          # --fft-threads (main.c:438, fft.h:15 default 4); the channel threads are one per channel
+        p = O.RefPipeline(W["sr"], CF, P["freqs"], fft_threads=fft_threads, fast=True)
+        backend = {0: "oracle FFT (persistent pool) as the fftw3f stand-in", 1: "fftw3f", 3: "fftw3f + fftw3f_threads"}[fast.ref_fft_backend()]
+        desc = ("the reference's own block.c + fft.c + fastddc.c (all-bin fold) + hfdl.c + libfec/viterbi27_port.c compiled where they lie "
+                "(oracle/_ref/libref_fast.so, -O3 -ffast-math), wired as main.c does: 1 fft thread with %d FFT workers + %d channel threads on a %d-core host; "
+                "FFT backend: %s; liquid-dsp objects served by the oracle's restatement (liquid-dsp not installed)" % (fft_threads, W["nch"], cores, backend))
+        return dict(kind=kind, p=p, cores=min(cores, W["nch"] + fft_threads), desc=desc, feed=lambda seg: (p.feed(seg), p.drain()), close=p.close,
+                    good=lambda: sum(1 for q in p.pdus() if O.pdu_front(q.data())[0] == 0))
+    nt = min(cores, 32)
+    p = O.Pipeline(W["sr"], CF, P["freqs"], fold_mode=O.FOLD_FULL, nthreads=nt, fast=True)
+    desc = "restated CPU reference (oracle/liboracle_fast.so, -O3 -ffast-math, all-bin fold, %d threads on a %d-core host): oracle/_ref not built" % (nt, cores)
+    return dict(kind="port", p=p, cores=nt, desc=desc, feed=lambda seg: p.feed(seg), close=p.close, good=lambda: sum(1 for q in p.pdus() if q.crc_good))
+
+
+def fft_share(O, W, isz, per_block_s):
+    """Share of the forward FFT in one block of the CPU arm (timed alone on the same box)."""
+    try:
+        g = O.geometry(W["sr"])[2]
+        n = g.fft_size
+        x = (np.random.default_rng(1).standard_normal(n) + 0j).astype(np.complex64)
+        o = np.zeros(n, np.complex64)
+        L = O.lib(True)
+        L.orc_fft_set_threads(max(1, min(os.cpu_count() or 1, 8)))
+        L.orc_fft(x, o, n, 1)
         t0 = time.perf_counter()
-        p.feed(x[isz: (1 + probe) * isz])
-        dt = (time.perf_counter() - t0) / probe
-        p.close()
-        if dt < best[1]:
-            best = (t, dt)
-    return best
+        for _ in range(3):
+            L.orc_fft(x, o, n, 1)
+        return (time.perf_counter() - t0) / 3 / per_block_s
+    except Exception:
+        return None
 
 
-def cpu_reference(O, x, isz, nblocks_avail, target_s=12.0):
-    """The reference's own algorithm on the host cores: restated CPU reference (oracle built -O3 -ffast-math),
-    full-N fold exactly as fastddc.c:123-150, FFT + channels threaded like fft_fftw.c / block.c."""
-    cores = os.cpu_count() or 1
-    nt, per_block = best_threads(O, x, isz, nblocks_avail)
-    p = O.Pipeline(SR, CF, channel_freqs(), fold_mode=O.FOLD_FULL, nthreads=nt, fast=True)
-    nb = int(max(4, min(80 * nblocks_avail, target_s / max(per_block, 1e-6))))      # ~target_s seconds of CPU work over the looped slab
+def cpu_reference(O, W, P, isz, x0, target_s=12.0):
+    """cpu_baseline of the N = 1 line: a bounded sample (~target_s of CPU work) of the same workload: the looped slab
+    (x0 = the whole slab) fed block by block, cyclically, the way the GPU arm loops over it."""
+    R = cpu_reference_setup(O, W, P)
+    navail = x0.size // isz
+    R["feed"](x0[: isz])                     # warm up: page in, first block
     t0 = time.perf_counter()
-    done = 0
-    while done < nb:                               # the slab is cyclic: keep feeding it until ~target_s of CPU work
-        k = min(nblocks_avail, nb - done)
-        p.feed(x[: k * isz])
-        done += k
+    R["feed"](x0[isz: 2 * isz])
+    per_block = time.perf_counter() - t0
+    nb = int(max(2, min(20 * navail, target_s / max(per_block, 1e-6))))
+    t0 = time.perf_counter()
+    for i in range(nb):
+        b = (2 + i) % navail
+        R["feed"](x0[b * isz:(b + 1) * isz])
     dt = time.perf_counter() - t0
-    good = sum(1 for q in p.pdus() if q.crc_good)
-    p.close()
-    return {"value": nb * isz / dt / 1e6, "unit": "Msamples/s", "cores": nt, "kind": "port",
-            "sample": "%d overlap-save blocks (%.1f Msamples) of the cfg-2 slab, restated CPU reference (fftw3/liquid-dsp not installed): "
-                      "oracle/liboracle_fast.so -O3 -ffast-math, full-N fold, best of a thread sweep = %d threads on a %d-core host; %d CRC-good PDUs" % (nb, nb * isz / 1e6, nt, cores, good),
-            "seconds": dt, "host_cores": cores}
+    share = fft_share(O, W, isz, dt / nb)
+    good = R["good"]()
+    R["close"]()
+    return {"value": nb * isz / dt / 1e6, "unit": "Msamples/s", "cores": R["cores"], "kind": R["kind"],
+            "sample": "%d consecutive overlap-save blocks (%.1f Msamples) of the looped slab after 2 warm-up blocks; %s; forward FFT share of a block %s; %d CRC-good PDUs in the sample"
+                      % (nb, nb * isz / 1e6, R["desc"], ("%.0f %%" % (100 * share)) if share is not None else "n/a", good),
+            "seconds": dt, "host_cores": os.cpu_count() or 1}
 
 
+def run_reference_arm(a, O, name, W, world):
+    isz = O.geometry(W["sr"])[2].input_size
+    P = plan_frames(O, W, isz)
+    ncpu = os.cpu_count() or 1
+    R = cpu_reference_setup(O, W, P)
+    # size a step: one warm-up block timed, then ~1.5 s of CPU work per step, at most the slab
+    nb_total_max = P["nblocks"]
+    x = render_range(O, W, P, 0, min(nb_total_max, 3) * isz, ncpu, W["seed"])
+    R["feed"](x[: isz])
+    t0 = time.perf_counter()
+    R["feed"](x[isz: 2 * isz])
+    per_block = time.perf_counter() - t0
+    per = int(max(1, min(8, 1.5 / max(per_block, 1e-6))))
+    need = (a.warmup + a.steps) * per
+    have = min(need + 2, nb_total_max)
+    if have * isz > x.size:
+        x = np.concatenate([x, render_range(O, W, P, x.size, have * isz - x.size, ncpu, W["seed"] + 1)])
+    pos = 2
+    vals = []
+    for s in range(a.warmup + a.steps):
+        idx = [(pos + i) % have for i in range(per)]
+        seg = np.concatenate([x[i * isz:(i + 1) * isz] for i in idx])
+        t0 = time.perf_counter()
+        R["feed"](seg)
+        dt = time.perf_counter() - t0
+        pos += per
+        if s >= a.warmup:
+            vals.append(dt)
+    tot = sum(vals)
+    v = a.steps * per * isz / tot / 1e6
+    good = R["good"]()
+    R["close"]()
+    line = {"metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference", "config": config_of(name, W, P, world),
+            "step": "%d consecutive overlap-save blocks (%.2f Msamples) of the slab per step (bounded sample of the workload)" % (per, per * isz / 1e6),
+            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": R["cores"], "kind": R["kind"], "sample": R["desc"]},
+            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "pdus_crc_good": good}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--shared-spectrum", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--loops", type=int, default=0, help="passes over the slab per step (0 = the workload's default)")
+    ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: time the device-resident leg alone")
     a = ap.parse_args()
-    set_workload(a.workload)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    name = a.workload or DEFAULT_BY_GPUS.get(max(world, a.gpus), "cfg3")
+    W = dict(WORKLOADS[name])
+    if a.loops > 0:
+        W["loops"] = a.loops
+    if a.warmup < 3:
+        a.warmup = 3                                   # timing rule: at least three warm-up steps
     import orclib as O
 
     if a.impl == "reference":
-        if rank != 0:
-            return
-        x, truth, nblocks, isz = build_slab(O, SEED, os.cpu_count() or 1)
-        nt, per_block = best_threads(O, x, isz, nblocks)
-        per = int(max(4, min(nblocks, 2.0 / max(per_block, 1e-6))))        # ~2 s of CPU work per step
-        vals = []
-        cores = nt
-        p = O.Pipeline(SR, CF, channel_freqs(), fold_mode=O.FOLD_FULL, nthreads=nt, fast=True)
-        pos = 0
-        for s in range(a.warmup + a.steps):
-            seg = np.concatenate([x[(pos + i * isz) % x.size:(pos + i * isz) % x.size + isz] for i in range(per)])
-            t0 = time.perf_counter()
-            p.feed(seg)
-            dt = time.perf_counter() - t0
-            pos += per * isz
-            if s >= a.warmup:
-                vals.append(dt)
-        tot = sum(vals)
-        v = a.steps * per * isz / tot / 1e6
-        good = sum(1 for q in p.pdus() if q.crc_good)
-        line = {"metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "impl": "reference",
-                "config": {"workload": "cfg2: 2 Msps CF32, 8 HFDL channels, synthetic looped slab; each step = %d blocks (%.2f Msamples)" % (per, per * isz / 1e6)},
-                "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port",
-                                 "sample": "restated CPU reference (oracle/liboracle_fast.so, -O3 -ffast-math, full-N fold, best of a thread sweep = %d threads on a %d-core host); fftw3f/liquid-dsp absent so dumphfdl itself cannot be built" % (cores, os.cpu_count() or 1)},
-                "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "pdus_crc_good": good}
-        print(json.dumps(line))
+        if rank == 0:
+            run_reference_arm(a, O, name, W, max(world, a.gpus))
         return
 
     import torch
@@ -259,21 +335,29 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ncpu = max(1, (os.cpu_count() or 1) // max(world, 1))
-    shared = a.shared_spectrum and world > 1
-    seed = SEED if shared else SEED + 1000 * rank
-    x, truth, nblocks, isz = build_slab(O, seed, ncpu)
-    freqs = channel_freqs()
-    if shared:
-        my = list(range(rank, NCH, world))
-        freqs = [freqs[i] for i in my]
-        truth = [t for t in truth if t[0] in freqs]
-    nsamp = x.size
-    xf = torch.from_numpy(x.view(np.float32))
-    h_pin = xf.pin_memory()
-    d_slab = torch.empty_like(xf, device="cuda")
-    d_slab.copy_(h_pin)
+    isz = O.geometry(W["sr"])[2].input_size
+    P = plan_frames(O, W, isz)
+    nsamp, nblocks, loops = P["nsamp"], P["nblocks"], W["loops"]
+    assert nsamp % world == 0
+    part = nsamp // world
+    # every rank renders its own 1/N of the slab (time slice); the whole slab is assembled over NCCL where needed
+    x_part = render_range(O, W, P, rank * part, part, ncpu, W["seed"] + 7919 * rank)
+    my_idx = list(range(rank, W["nch"], world))
+    freqs = [P["freqs"][i] for i in my_idx]
+    truth_set = set(t for t in P["truth"] if t[0] in set(freqs))
+    ntruth = len(truth_set)
+    h_part = torch.from_numpy(x_part.view(np.float32)).pin_memory()
+    d_part = torch.empty_like(h_part, device="cuda")
+    d_part.copy_(h_part)
+    nbuf = 3 if world > 1 else 1
+    bufs = [torch.empty(2 * nsamp, dtype=torch.float32, device="cuda") for _ in range(nbuf)]
+    if world > 1:
+        dist.all_gather_into_tensor(bufs[0], d_part)
+        d_slab = bufs[0].clone() if rank == 0 else None
+    else:
+        bufs[0].copy_(d_part)
+        d_slab = bufs[0]
     torch.cuda.synchronize()
-    fe = hb.Frontend(SR, CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
 
     def barrier():
         torch.cuda.synchronize()
@@ -281,45 +365,45 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    truth_set = set(truth)
-    stream_pos = [0]
-
-    # shared spectrum: the capture of rank 0 is broadcast (NCCL over NVLink) into one of three slab buffers per step;
-    # only the broadcast's stream is waited for, so the frontend's batch pipeline keeps running underneath (a buffer
-    # is reused three steps later, when process_device() has already collected the batch that read it)
-    slabs = [d_slab] + ([torch.empty_like(d_slab), torch.empty_like(d_slab)] if shared else [])
-    step_no = [0]
-
-    def step_device():
-        buf = slabs[step_no[0] % len(slabs)]
-        if shared:
-            if rank == 0 and buf is not d_slab:
-                buf.copy_(d_slab, non_blocking=True)
-            dist.broadcast(buf, src=0)
-            torch.cuda.current_stream().synchronize()
-        fe.process_device(buf.data_ptr(), nsamp, stream_pos[0], nblocks)
-        stream_pos[0] += nsamp
-        step_no[0] += 1
-
     def count(pdus):
         good = sum(1 for q in pdus if q.crc_good)
         exact = sum(1 for q in pdus if (q.freq, q.data()) in truth_set)
         return good, exact
 
-    # ---- value: slab resident in HBM
+    # ---- value: capture resident in HBM (rank 0's HBM when N > 1)
+    fe = hb.Frontend(W["sr"], CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
+    state = {"pos": 0, "i": 0}
+
+    def pass_device():
+        if world > 1:
+            buf = bufs[state["i"] % nbuf]
+            fe.wait_input()                             # the batches queued so far have read their buffers (channeliser stage only)
+            if rank == 0:
+                buf.copy_(d_slab, non_blocking=True)
+            dist.broadcast(buf, src=0)                  # NCCL over NVLink; only its stream is waited for, the batch pipeline keeps running
+            torch.cuda.current_stream().synchronize()
+        else:
+            buf = d_slab
+        fe.process_device(buf.data_ptr(), nsamp, state["pos"], nblocks)
+        state["pos"] += nsamp
+        state["i"] += 1
+
     for _ in range(a.warmup):
-        step_device()
+        for _ in range(loops):
+            pass_device()
     fe.sync()
     fe.pdus()
     clk = ClockSampler(local)
     clk.start()
     fe.profile(True)
+    fe.profile_read()
     l0 = fe.launches()
     barrier()
     fe.timer_start()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        step_device()
+        for _ in range(loops):
+            pass_device()
     ms_dev = fe.timer_stop()
     barrier()
     wall = time.perf_counter() - t0
@@ -329,50 +413,73 @@ def main():
     fe.profile(False)
     good, exact = count(fe.pdus())
     ms = max(ms_dev, 0.0)
-    # ---- e2e: host buffers through the C ABI (H2D + D2H inside)
-    fe2 = hb.Frontend(SR, CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
-    for _ in range(max(3, a.warmup)):
-        fe2.push_ptr(h_pin.data_ptr(), nsamp)
-    fe2.flush()
-    fe2.pdus()
-    barrier()
-    t0 = time.perf_counter()
-    e_good = 0
-    for _ in range(a.steps):
-        # streaming use of the C ABI: every push copies this step's slab H2D and hands back the PDU records of the
-        # batch that finished meanwhile (D2H); the final flush inside the timed region drains the pipeline
-        fe2.push_ptr(h_pin.data_ptr(), nsamp)
-        e_good += count(fe2.pdus())[0]
-    fe2.flush()
-    e_good += count(fe2.pdus())[0]
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    d2h_per_step = fe2.result_bytes_per_batch()
+    if os.environ.get("HFDL_B200_DEBUG"):
+        fe.L.hfdl_b200_print_summary(fe.h)
+    geom = fe.geom
+    fe.close()
 
-    t = torch.tensor([ms, e2e_s * 1e3, float(good), float(exact), float(e_good), float(len(truth))], dtype=torch.float64, device="cuda")
+    # ---- e2e: from pinned host memory
+    e2e_ms, e_good, d2h_per_step, h2d_per_step = float("nan"), 0, 0, 0
+    if not a.skip_e2e:
+        fe2 = hb.Frontend(W["sr"], CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
+        st2 = {"pos": 0, "i": 0}
+
+        def pass_host():
+            if world > 1:
+                buf = bufs[st2["i"] % nbuf]
+                fe2.wait_input()
+                d_part.copy_(h_part, non_blocking=True)                 # this rank's 1/N of the pass over its own PCIe link
+                dist.all_gather_into_tensor(buf, d_part)                # NVLink: every GPU ends up with the whole capture
+                torch.cuda.current_stream().synchronize()
+                fe2.process_device(buf.data_ptr(), nsamp, st2["pos"], nblocks)
+            else:
+                fe2.push_ptr(h_part.data_ptr(), nsamp)                  # H2D inside the C-ABI call
+            st2["pos"] += nsamp
+            st2["i"] += 1
+
+        for _ in range(max(1, a.warmup * loops // 4)):
+            pass_host()
+        fe2.flush()
+        fe2.pdus()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            for _ in range(loops):
+                pass_host()
+                e_good += count(fe2.pdus())[0]           # PDU records of the batches that finished meanwhile (D2H)
+        fe2.flush()                                      # the timed region ends when every PDU is on the host
+        e_good += count(fe2.pdus())[0]
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        d2h_per_step = fe2.result_bytes_per_batch() * loops
+        h2d_per_step = part * 8 * loops
+        fe2.close()
+
+    t = torch.tensor([ms, e2e_ms if e2e_ms == e2e_ms else 0.0, float(good), float(exact), float(e_good), float(ntruth), float(launches),
+                      float(h2d_per_step), float(d2h_per_step)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         ms, e2e_ms = float(tmax[0]), float(tmax[1])
-        good, exact, e_good, ntruth = float(tsum[2]), float(tsum[3]), float(tsum[4]), float(tsum[5])
+        good, exact, e_good, ntruth, launches = float(tsum[2]), float(tsum[3]), float(tsum[4]), float(tsum[5]), float(tsum[6])
+        h2d_per_step, d2h_per_step = float(tsum[7]), float(tsum[8])
     else:
         ms, e2e_ms, ntruth = float(t[0]), float(t[1]), float(t[5])
-    streams = 1 if shared else world
-    total_samples = a.steps * nsamp * streams
+    total_samples = a.steps * loops * nsamp              # slab samples: every GPU sees the whole capture, it is counted once
     value = total_samples / (ms / 1e3) / 1e6
-    e2e = total_samples / (e2e_ms / 1e3) / 1e6
+    e2e = total_samples / (e2e_ms / 1e3) / 1e6 if e2e_ms > 0 else None
     if rank == 0:
-        g = fe.geom
-        N, M, out = g.fft_size, g.fft_inv_size, g.out_per_block
+        N, M, out = geom.fft_size, geom.fft_inv_size, geom.out_per_block
         Cn = len(freqs)
-        # algorithmic (compulsory) bytes per block, SURVEY 8(d) / BASELINE.md section 3
+        # algorithmic (compulsory) HBM bytes per overlap-save block ON ONE GPU, SURVEY 8(d): ingest read + spectrum write
+        # (both unsharded) + this GPU's channels' spectrum slice read + tap slice read + baseband write + demod read
         b_blk = isz * 8 + N * 8 + Cn * M * 8 + Cn * M * 8 + Cn * out * 16
-        alg = {"fft_pass1": isz * 8, "fft_pass2": N * 8 if g.fft_passes == 2 else 0, "fft_pass3": N * 8 if g.fft_passes == 3 else 0,
-               "chan_extract": Cn * M * 16 + Cn * out * 8, "resamp": Cn * out * 8 * (1 + g.resamp_rate),
-               "agc": Cn * out * g.resamp_rate * (8 + 12), "bank": Cn * out * g.resamp_rate * (8 + 8 + 256),
-               "loop": Cn * out * g.resamp_rate * (256 + 4), "fec": 0}
+        nout = out * geom.resamp_rate
+        alg = {"fft_pass1": isz * 8, "fft_pass2": N * 8 if geom.fft_passes == 2 else 0, "fft_pass3": N * 8 if geom.fft_passes == 3 else 0,
+               "chan_extract": Cn * M * 16 + Cn * out * 8, "resamp": Cn * out * 8 * (1 + geom.resamp_rate),
+               "agc": Cn * nout * (8 + 12), "bank": Cn * nout * (8 + 8 + 256), "loop": Cn * nout * (256 + 4), "fec": 0}
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -380,58 +487,57 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         kern = {k: {"ms_total": v[0], "launches": v[1], "ms_per_launch": (v[0] / v[1] if v[1] else 0.0)} for k, v in prof.items()}
-        # dram bytes per launch from the committed ncu --set full captures (profiles/r01_traffic.json): valid for this
-        # workload and batch size only
         traffic = {}
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tj = json.load(f)
-            if tj.get("workload") == WORKLOAD and tj.get("blocks_per_step") == nblocks and tj.get("channels") == Cn:
+            if tj.get("workload") == name and tj.get("blocks_per_batch") == nblocks and tj.get("channels") == Cn:
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
+        nbatches = a.steps * loops
         roofs = {}
         for k, v in prof.items():
             if not v[1] or not alg.get(k):
                 continue
-            per_launch_bytes = alg[k] * nblocks * a.steps / v[1]        # a class may be launched several times per step (sub-ranges)
+            per_launch_bytes = alg[k] * nblocks * nbatches / v[1]
             dur = v[0] / v[1] / 1e3
             ach = per_launch_bytes / dur / 1e9
-            roofs[k] = {"kernel": k, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(k),
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                        "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": dur * 1e3, "launches_per_step": v[1] / a.steps}
+            roofs[k] = {"achieved": round(ach, 1), "frac": round(ach / peak, 4), "traffic": traffic.get(k), "algorithmic_bytes_per_launch": int(per_launch_bytes),
+                        "avg_launch_ms": round(dur * 1e3, 4), "launches_per_batch": v[1] / nbatches}
+        # the dominant kernel and the contract's roofline for it: the WHOLE path's algorithmic bytes of the blocks one launch
+        # covers (B_blk x blocks per launch) over that kernel's average launch duration
         dom = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
-        roof = roofs.get(dom)
-        if roof is not None and dom in ("loop", "agc", "fec"):
-            roof = dict(roof, note="latency-bound sequential recurrence (one warp chain per channel): HBM is not the limiter of this kernel; "
-                                   "the HBM-bound kernels of the path are listed under roofline_kernels")
-        pipe_ach = b_blk * nblocks * a.steps / (ms / 1e3) / 1e9
+        roof = None
+        if dom and prof[dom][1]:
+            blocks_per_launch = nblocks * nbatches / prof[dom][1]
+            dur = prof[dom][0] / prof[dom][1] / 1e3
+            ach = b_blk * blocks_per_launch / dur / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic.get(dom),
+                    "peak_source": peak_src, "algorithmic_bytes_per_block": b_blk, "blocks_per_launch": blocks_per_launch, "avg_launch_ms": dur * 1e3,
+                    "note": ("the step costs what its slowest pipeline stage costs; %s is that stage. It is a latency-bound sequential recurrence (one warp chain per "
+                             "channel), so this fraction says how far the whole path is from the HBM roofline, not how busy HBM is; the kernels' own bytes are under "
+                             "roofline_kernels" % dom) if dom in ("loop", "agc", "fec") else None}
+        pipe_ach = b_blk * nblocks * nbatches / (ms / 1e3) / 1e9
         line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak" if not shared else "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD + ": %.0f Msps CF32, %d HFDL channels per GPU, looped slab of %d overlap-save blocks (%.1f Msamples, %.0f MB; "
-                                       "slab + %.0f MB spectrum workspace exceed the 126 MB L2, no explicit flush)" % (SR / 1e6, Cn, nblocks, nsamp / 1e6, nsamp * 8 / 1e6, nblocks * N * 8 / 1e6),
-                           "sample_rate": SR, "channels_per_gpu": Cn, "blocks_per_step": nblocks, "fft_size": N, "esn0_db": ESN0_DB,
-                           "sharding": ("one capture broadcast over NCCL each step, channels sharded" if shared else "one independent capture + its channels per GPU, no collective")},
-                "pdus_per_s": good / (ms / 1e3), "pdus_crc_good": good, "pdus_exact": exact, "pdus_expected_per_step": ntruth,
-                "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": nsamp * 8, "d2h_bytes_per_step": int(d2h_per_step),
-                        "pdus_per_s": e_good / (e2e_ms / 1e3)},
-                "gpu_launches": int(launches), "clocks": clocks, "kernels": kern, "roofline": roof,
-                "roofline_kernels": {k: {"achieved": round(v["achieved"], 1), "frac": round(v["frac"], 4), "traffic": v["traffic"],
-                                         "algorithmic_bytes_per_launch": int(v["algorithmic_bytes_per_launch"]), "avg_launch_ms": round(v["avg_launch_ms"], 4)}
-                                     for k, v in roofs.items()},
-                "roofline_pipeline": {"bound": "hbm", "achieved": pipe_ach, "peak": peak, "unit": "GB/s", "frac": pipe_ach / peak,
-                                      "algorithmic_bytes_per_block": b_blk},
+                "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_of(name, W, P, world),
+                "step": "%d passes over the slab (%.1f Msamples, %d batches of %d blocks per GPU)" % (loops, loops * nsamp / 1e6, loops, nblocks),
+                "scaling_note": "the workload is BASELINE's configuration for the GPU count (cfg3 at 1-2, cfg4 at 4, cfg5 at 8 GPUs): capture rate and channel count grow with N; "
+                                "value counts capture samples once although every GPU transforms the whole capture",
+                "pdus_per_s": good / (ms / 1e3), "pdus_crc_good": good, "pdus_exact": exact, "pdus_expected_per_pass": ntruth,
+                "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step),
+                        "pdus_per_s": (e_good / (e2e_ms / 1e3)) if e2e_ms > 0 else None, "ms_per_step": e2e_ms / a.steps if e2e_ms > 0 else None},
+                "gpu_launches": int(launches), "clocks": clocks, "kernels": kern, "roofline": roof, "roofline_kernels": roofs,
+                "roofline_pipeline": {"bound": "hbm", "achieved": pipe_ach, "peak": peak, "unit": "GB/s", "frac": pipe_ach / peak, "algorithmic_bytes_per_block": b_blk},
                 "wall_ms_per_step": 1e3 * wall / a.steps}
         if not a.no_cpu_baseline and world == 1:          # the CPU baseline is reported by the single-GPU run only
-            line["cpu_baseline"] = cpu_reference(O, x, isz, nblocks)
+            line["cpu_baseline"] = cpu_reference(O, W, P, isz, x_part)
         print(json.dumps(line))
-    if os.environ.get("HFDL_B200_DEBUG"):
-        fe.L.hfdl_b200_print_summary(fe.h)
-    fe.close()
-    fe2.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

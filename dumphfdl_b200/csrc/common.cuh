@@ -62,6 +62,42 @@ __device__ __forceinline__ void hfdl_cp_async_commit() { asm volatile("cp.async.
 template <int N> __device__ __forceinline__ void hfdl_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #endif
 
+// TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier): one elected lane moves a whole
+// contiguous tile with a single instruction; the consumer side waits on the mbarrier's phase.  Under host emulation
+// the copy is an immediate memcpy and the barrier a generation counter.
+#ifdef HFDL_CUSIM
+typedef struct { volatile unsigned long long phase; } hfdl_mbar_t;
+static inline void hfdl_mbar_init(hfdl_mbar_t *b, unsigned) { b->phase = 0; }
+static inline void hfdl_mbar_expect_tx(hfdl_mbar_t *, unsigned) {}
+static inline void hfdl_bulk_g2s(void *sdst, const void *gsrc, unsigned bytes, hfdl_mbar_t *) { memcpy(sdst, gsrc, bytes); }
+static inline void hfdl_mbar_arrive_emul(hfdl_mbar_t *b) { __atomic_thread_fence(__ATOMIC_SEQ_CST); b->phase = b->phase + 1; }
+static inline bool hfdl_mbar_try_wait(hfdl_mbar_t *b, unsigned parity) { return ((b->phase & 1ull) != (unsigned long long)parity); }
+static inline void hfdl_fence_proxy_async() {}
+static inline void hfdl_fence_mbar_init() {}
+#else
+typedef unsigned long long hfdl_mbar_t;
+__device__ __forceinline__ void hfdl_mbar_init(hfdl_mbar_t *b, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hfdl_fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void hfdl_mbar_expect_tx(hfdl_mbar_t *b, unsigned bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void hfdl_bulk_g2s(void *sdst, const void *gsrc, unsigned bytes, hfdl_mbar_t *b) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+		::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void hfdl_mbar_arrive_emul(hfdl_mbar_t *) {}
+__device__ __forceinline__ bool hfdl_mbar_try_wait(hfdl_mbar_t *b, unsigned parity) {
+	unsigned ok;
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		: "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(b)), "r"(parity) : "memory");
+	return ok != 0;
+}
+// generic-proxy accesses to shared memory (the consumers' loads) are ordered before later async-proxy writes (the next bulk copy)
+__device__ __forceinline__ void hfdl_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
 #ifdef HFDL_CUSIM
 static inline long long hfdl_clock() { return 0; }
 #else

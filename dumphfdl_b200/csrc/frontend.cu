@@ -26,6 +26,9 @@ enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_AGC, KC_BANK, KC_LO
 const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "agc", "bank", "loop", "fec" };
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
+#ifndef HFDL_NSETS
+#define HFDL_NSETS 4        // batches in flight: sets of every buffer a later pipeline stage reads
+#endif
 
 FftPlan make_plan(int N) {
 	FftPlan p;
@@ -100,15 +103,15 @@ struct hfdl_b200_frontend {
 	// streams: front (H2D, FFT, channeliser, resampler) | agc + bank | loop | fec + D2H.  One launch per stage per batch;
 	// the stages of consecutive batches overlap (front/agc/bank of batch i+1 beside loop of batch i beside fec of i-1).
 	cudaStream_t stream = nullptr, stream2 = nullptr, st_loop = nullptr, st_fec = nullptr, st_stats = nullptr;
-	cudaEvent_t ev_front[2] = { nullptr, nullptr }, ev_bank[2] = { nullptr, nullptr }, ev_loop[2] = { nullptr, nullptr }, ev_fec_done[2] = { nullptr, nullptr };
+	cudaEvent_t ev_front[HFDL_NSETS] = { nullptr }, ev_bank[HFDL_NSETS] = { nullptr }, ev_loop[HFDL_NSETS] = { nullptr }, ev_fec_done[HFDL_NSETS] = { nullptr };
 	cudaEvent_t ev_h2d = nullptr;
-	struct Flight { bool busy = false; } flight[2];
+	struct Flight { bool busy = false; } flight[HFDL_NSETS];
 	std::recursive_mutex mtx;       // every public entry point: the frontend may be driven and queried from different threads
 	bool peer_enabled = false;
 	bool failed = false;            // a CUDA call failed mid-pipeline: every later call returns -1
 	int Bsub = 1;                   // blocks per FFT sub-batch (intermediate spectra stay in L2)
 	long long n_out_prev = 0;       // resampled samples of the previous batch (carry source)
-	long long batch_seq = 0;        // batches enqueued so far; set p = batch_seq & 1
+	long long batch_seq = 0;        // batches enqueued so far; set p = batch_seq % HFDL_NSETS
 	int nslots = HFDL_FRAME_SLOTS_MIN;
 	FftEngine fft;
 	// device memory
@@ -116,17 +119,17 @@ struct hfdl_b200_frontend {
 	void *d_ring = nullptr; long long ring_len = 0;
 	cf *d_tapslice = nullptr; int *d_offsetbin = nullptr; float *d_dsa_rate = nullptr;
 	cf *d_bb = nullptr; long long bb_stride = 0;
-	cf *d_rs[2] = { nullptr, nullptr }; long long rs_stride = 0; float *d_rs_h = nullptr;
+	cf *d_rs[HFDL_NSETS] = { nullptr }; long long rs_stride = 0; float *d_rs_h = nullptr;
 	DemodTables *d_tab = nullptr; DemodState *d_state = nullptr; AgcState *d_agc_state = nullptr; cf *d_datasym = nullptr;
-	cf *d_agc[2] = { nullptr, nullptr }, *d_mfo[2] = { nullptr, nullptr }, *d_bank[2] = { nullptr, nullptr }; float *d_lvl[2] = { nullptr, nullptr };
+	cf *d_agc[HFDL_NSETS] = { nullptr }, *d_mfo[HFDL_NSETS] = { nullptr }, *d_bank[HFDL_NSETS] = { nullptr }; float *d_lvl[HFDL_NSETS] = { nullptr };
 	long long agc_stride = 0, mfo_stride = 0;      // work arrays of the demodulator stages, one set per batch parity
 	long long cap_n = 0;            // AGC/MF checkpoint samples captured so far
-	FrameRec *d_frames[2] = { nullptr, nullptr }; int *d_nframes[2] = { nullptr, nullptr }; PduRec *d_pdus[2] = { nullptr, nullptr }; int max_frames = 0;
+	FrameRec *d_frames[HFDL_NSETS] = { nullptr }; int *d_nframes[HFDL_NSETS] = { nullptr }; PduRec *d_pdus[HFDL_NSETS] = { nullptr }; int max_frames = 0;
 	cf *d_cap_agc = nullptr, *d_cap_mf = nullptr, *d_cap_eq = nullptr; int *d_cap_cnt = nullptr;
 	cf *d_tmp = nullptr; long long tmp_len = 0;
 	long long *d_dbg = nullptr;
 	// host state
-	PduRec *h_pdus[2] = { nullptr, nullptr }; int *h_nframes[2] = { nullptr, nullptr };
+	PduRec *h_pdus[HFDL_NSETS] = { nullptr }; int *h_nframes[HFDL_NSETS] = { nullptr };
 	long long fed = 0;              // samples pushed so far (host-fed path)
 	long long blocks_done = 0;      // overlap-save blocks processed
 	unsigned long long rs_phi0 = 0; unsigned rs_step = 0;
@@ -321,9 +324,8 @@ int collect_batch(hfdl_b200_frontend *fe, int q, bool wait = true) {
 
 // Everything enqueued so far has finished and its PDUs are in the host queue (oldest batch first).
 int drain(hfdl_b200_frontend *fe) {
-	const int p = (int)(fe->batch_seq & 1);
-	if(collect_batch(fe, p)) return -1;          // set p holds the older of the two batches in flight
-	if(collect_batch(fe, p ^ 1)) return -1;
+	for(int k = 0; k < HFDL_NSETS; k++)          // oldest batch first: set (batch_seq + k) % NSETS
+		if(collect_batch(fe, (int)((fe->batch_seq + k) % HFDL_NSETS))) return -1;
 	CK(cudaStreamSynchronize(fe->stream));
 	CK(cudaStreamSynchronize(fe->stream2));
 	CK(cudaStreamSynchronize(fe->st_loop));
@@ -342,8 +344,8 @@ int drain(hfdl_b200_frontend *fe) {
 // of batch i+1 run beside loop of batch i and fec of batch i-1; events order the reuse of a set two batches later.
 // The host collects the PDUs of batch i-1 after it has enqueued batch i.
 int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
-	const int p = (int)(fe->batch_seq & 1);
-	if(collect_batch(fe, p)) return -1;          // batch i-2 (normally collected long ago): every set-p buffer is free
+	const int p = (int)(fe->batch_seq % HFDL_NSETS), pp = (p + HFDL_NSETS - 1) % HFDL_NSETS, p2 = (p + HFDL_NSETS - 2) % HFDL_NSETS;
+	if(collect_batch(fe, p)) return -1;          // batch i-NSETS (normally collected long ago): every set-p buffer is free
 	cudaStream_t st = fe->stream, st2 = fe->stream2, stl = fe->st_loop, stf = fe->st_fec;
 	const auto &g = fe->g;
 	hfdl_b200_frontend::Flight &cur = fe->flight[p];
@@ -391,7 +393,7 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 	CK(cudaStreamWaitEvent(st2, fe->ev_front[p], 0));
 	CK(cudaStreamWaitEvent(st2, fe->ev_loop[p], 0));
 	// the last HIST samples of the previous batch's AGC / matched-filter outputs (set p^1) go in front of set p
-	HFDL_LAUNCH(demod_carry, dim3((unsigned)fe->C), dim3(64), 0, st2, fe->d_agc[p ^ 1], fe->d_agc[p], fe->agc_stride, fe->d_mfo[p ^ 1], fe->d_mfo[p], fe->mfo_stride, fe->n_out_prev);
+	HFDL_LAUNCH(demod_carry, dim3((unsigned)fe->C), dim3(64), 0, st2, fe->d_agc[pp], fe->d_agc[p], fe->agc_stride, fe->d_mfo[pp], fe->d_mfo[p], fe->mfo_stride, fe->n_out_prev);
 	fe->launches++;
 	if(n_out > 0) {
 		AgcArgs a;
@@ -419,6 +421,8 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 	// ---- loop: frame records of set p are free once fec of batch i-2 is done
 	CK(cudaStreamWaitEvent(stl, fe->ev_bank[p], 0));
 	CK(cudaStreamWaitEvent(stl, fe->ev_fec_done[p], 0));
+	// data-symbol slots: a channel has room for the frames of two batches, so fec of batch i-2 must have read its frames
+	CK(cudaStreamWaitEvent(stl, fe->ev_fec_done[p2], 0));
 	CK(cudaMemsetAsync(fe->d_nframes[p], 0, sizeof(int), stl));
 	if(n_out > 0) {
 		LoopArgs l;
@@ -454,8 +458,14 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 	fe->blocks_done += nb;
 	fe->n_out_prev = n_out;
 	fe->last_nblocks = nb; fe->last_nout = n_out;
-	// while this batch runs, pick up the previous one
-	return collect_batch(fe, p ^ 1);
+	// while this batch runs, pick up what has finished (oldest first; stops at the first batch still running)
+	for(int k = 1; k < HFDL_NSETS; k++) {
+		const int q = (p + k) % HFDL_NSETS;
+		if(!fe->flight[q].busy) continue;
+		if(collect_batch(fe, q, false)) return -1;
+		if(fe->flight[q].busy) break;
+	}
+	return 0;
 }
 
 // A failure in the middle of enqueueing leaves events unrecorded and counters half advanced: stop everything and
@@ -466,7 +476,7 @@ int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
 	fe->failed = true;
 	cudaStream_t sts[4] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec };
 	for(cudaStream_t q : sts) if(q) cudaStreamSynchronize(q);
-	fe->flight[0].busy = fe->flight[1].busy = false;
+	for(int q = 0; q < HFDL_NSETS; q++) fe->flight[q].busy = false;
 	fprintf(stderr, "hfdl_b200: batch failed, frontend disabled\n");
 	return -1;
 }
@@ -566,7 +576,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaStreamCreateWithFlags(&fe->st_fec, cudaStreamNonBlocking));
 	CKD(cudaStreamCreateWithFlags(&fe->st_stats, cudaStreamNonBlocking));
 	CKD(cudaEventCreateWithFlags(&fe->ev_h2d, cudaEventDisableTiming));
-	for(int q = 0; q < 2; q++) {
+	for(int q = 0; q < HFDL_NSETS; q++) {
 		CKD(cudaEventCreateWithFlags(&fe->ev_front[q], cudaEventDisableTiming));
 		CKD(cudaEventCreateWithFlags(&fe->ev_bank[q], cudaEventDisableTiming));
 		CKD(cudaEventCreateWithFlags(&fe->ev_loop[q], cudaEventDisableTiming));
@@ -592,7 +602,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaMalloc((void **)&fe->d_bb, sizeof(cf) * (size_t)C * fe->bb_stride));
 	CKD(cudaMemset(fe->d_bb, 0, sizeof(cf) * (size_t)C * fe->bb_stride));
 	fe->rs_stride = (long long)B * fe->out_per_block + 16;
-	for(int q = 0; q < 2; q++) CKD(cudaMalloc((void **)&fe->d_rs[q], sizeof(cf) * (size_t)C * fe->rs_stride));
+	for(int q = 0; q < HFDL_NSETS; q++) CKD(cudaMalloc((void **)&fe->d_rs[q], sizeof(cf) * (size_t)C * fe->rs_stride));
 	{
 		std::vector<float> h((size_t)HFDL_RS_NPFB * HFDL_RS_TAPS);
 		hfdl_design::resamp_design(fe->resamp_rate, h.data(), &fe->rs_step);
@@ -613,7 +623,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 		CKD(cudaMalloc((void **)&fe->d_agc_state, sizeof(AgcState) * (size_t)C));
 		CKD(cudaMemcpy(fe->d_agc_state, ag.data(), sizeof(AgcState) * (size_t)C, cudaMemcpyHostToDevice));
 		fe->agc_stride = HFDL_AGC_HIST + fe->rs_stride; fe->mfo_stride = HFDL_MFO_HIST + fe->rs_stride;
-		for(int q = 0; q < 2; q++) {
+		for(int q = 0; q < HFDL_NSETS; q++) {
 			CKD(cudaMalloc((void **)&fe->d_agc[q], sizeof(cf) * (size_t)C * fe->agc_stride));
 			CKD(cudaMemset(fe->d_agc[q], 0, sizeof(cf) * (size_t)C * fe->agc_stride));
 			CKD(cudaMalloc((void **)&fe->d_mfo[q], sizeof(cf) * (size_t)C * fe->mfo_stride));
@@ -633,7 +643,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 		fe->max_frames = C * fpb;
 	}
 	CKD(cudaMalloc((void **)&fe->d_datasym, sizeof(cf) * (size_t)C * fe->nslots * HFDL_DATA_SYMS_MAX));
-	for(int q = 0; q < 2; q++) {
+	for(int q = 0; q < HFDL_NSETS; q++) {
 		CKD(cudaMalloc((void **)&fe->d_frames[q], sizeof(FrameRec) * (size_t)fe->max_frames));
 		CKD(cudaMalloc((void **)&fe->d_nframes[q], sizeof(int)));
 		CKD(cudaMemset(fe->d_nframes[q], 0, sizeof(int)));
@@ -669,7 +679,7 @@ void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	cudaFree(fe->d_bb); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
 	cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf); cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp); cudaFree(fe->d_dbg);
 	cudaFree(fe->d_agc_state);
-	for(int q = 0; q < 2; q++) {
+	for(int q = 0; q < HFDL_NSETS; q++) {
 		cudaFree(fe->d_agc[q]); cudaFree(fe->d_mfo[q]); cudaFree(fe->d_lvl[q]); cudaFree(fe->d_bank[q]);
 		cudaFree(fe->d_rs[q]); cudaFree(fe->d_frames[q]); cudaFree(fe->d_nframes[q]); cudaFree(fe->d_pdus[q]);
 		if(fe->h_pdus[q]) cudaFreeHost(fe->h_pdus[q]);
@@ -807,6 +817,13 @@ int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe) {
 	return r;
 }
 
+int32_t hfdl_b200_wait_input(hfdl_b200_frontend_t *fe) {
+	HFDL_API(fe, -1);
+	if(fe->batch_seq == 0) return 0;
+	CK(cudaEventSynchronize(fe->ev_front[(fe->batch_seq + HFDL_NSETS - 1) % HFDL_NSETS]));
+	return 0;
+}
+
 int32_t hfdl_b200_submit(hfdl_b200_frontend_t *fe) {
 	HFDL_API(fe, -1);
 	return process_pending(fe, true);
@@ -814,15 +831,19 @@ int32_t hfdl_b200_submit(hfdl_b200_frontend_t *fe) {
 
 int32_t hfdl_b200_poll(hfdl_b200_frontend_t *fe) {
 	HFDL_API(fe, -1);
-	const int p = (int)(fe->batch_seq & 1);
-	if(collect_batch(fe, p, false)) return -1;               // older batch first: PDU order per channel is kept
-	if(!fe->flight[p].busy && collect_batch(fe, p ^ 1, false)) return -1;
+	for(int k = 0; k < HFDL_NSETS; k++) {                    // oldest batch first: PDU order per channel is kept
+		const int q = (int)((fe->batch_seq + k) % HFDL_NSETS);
+		if(!fe->flight[q].busy) continue;
+		if(collect_batch(fe, q, false)) return -1;
+		if(fe->flight[q].busy) break;
+	}
 	return (int32_t)fe->pduq.size();
 }
 
 int32_t hfdl_b200_busy(hfdl_b200_frontend_t *fe) {
 	HFDL_API(fe, -1);
-	return (fe->flight[0].busy || fe->flight[1].busy) ? 1 : 0;
+	for(int q = 0; q < HFDL_NSETS; q++) if(fe->flight[q].busy) return 1;
+	return 0;
 }
 
 int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t ring_samples, int64_t start_sample, int32_t nblocks) {
@@ -995,7 +1016,7 @@ int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_
 	case HFDL_B200_CP_CHAN:
 		if(index < 0 || index >= fe->C) return -1;
 		avail = fe->last_nout;
-		srcp = fe->d_rs[(fe->batch_seq + 1) & 1] + (long long)index * fe->rs_stride;      // set of the last batch
+		srcp = fe->d_rs[(fe->batch_seq + HFDL_NSETS - 1) % HFDL_NSETS] + (long long)index * fe->rs_stride;      // set of the last batch
 		break;
 	case HFDL_B200_CP_AGC: case HFDL_B200_CP_MF: case HFDL_B200_CP_EQ: {
 		if(fe->cfg.capture_channel < 0) return -1;

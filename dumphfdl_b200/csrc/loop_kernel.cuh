@@ -6,7 +6,7 @@
 // FEWEST INSTRUCTIONS on each sequential warp; everything that is not on a chain is moved to another warp or to
 // other lanes:
 //   warp 2 "loader"  streams the precomputed filter-bank rows (bank_kernel) and AGC levels of the channel from HBM
-//                    into a 256-sample shared-memory ring (16-byte cp.async, 3 chunks in flight).
+//                    into a 256-sample shared-memory ring (one TMA bulk copy per 32-sample chunk, completion on mbarriers, 3 chunks in flight).
 //   warp 1 "timing"  symsync_crcf_step: iterates per OUTPUT (not per input sample): arm lookup in the ring, timing
 //                    error detector + loop filter on every second output, tau/arm update, skip to the input sample
 //                    of the next output.  Publishes {symbol, AGC level, tag} entries into a 64-entry output ring.
@@ -191,10 +191,11 @@ __device__ __forceinline__ cf costas_rotate(DemodState &S, float re, float im) {
 // ---- shared memory of one channel CTA (file scope: every access is a direct shared-window address) ----------
 __shared__ float4 lk_ring[HFDL_LK_RING];        // output ring data: {sym.re, sym.im, AGC level, info}
 __shared__ __align__(8) unsigned lk_tags[HFDL_LK_RING];      // output ring validity tags (read as aligned pairs)
-__shared__ float lk_lvl[HFDL_LK_BR];            // AGC level ring (1/g after the sample's update)
+__shared__ __align__(16) float lk_lvl[HFDL_LK_BR];            // AGC level ring (1/g after the sample's update)
 __shared__ cf lk_psk[4][8];
 __shared__ cf lk_train[16];
 __shared__ volatile int lk_loaded, lk_end_seq, lk_done;
+__shared__ __align__(8) hfdl_mbar_t lk_mbar[HFDL_LK_INFLIGHT];      // completion barriers of the loader's bulk copies
 __shared__ __align__(8) volatile int lk_tailv[2];      // {sequence number, input-sample index} the demodulator warp has passed
 #define lk_tail lk_tailv[0]
 #define lk_tail_k lk_tailv[1]
@@ -549,6 +550,8 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 	if(threadIdx.x < HFDL_LK_RING) { lk_ring[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f); lk_tags[threadIdx.x] = HFDL_LK_TAG_INVALID; }
 	if(threadIdx.x < 32) lk_psk[threadIdx.x >> 3][threadIdx.x & 7] = T.psk[threadIdx.x >> 3][threadIdx.x & 7];
 	if(threadIdx.x == 0) {
+		for(int i = 0; i < HFDL_LK_INFLIGHT; i++) hfdl_mbar_init(&lk_mbar[i], 1);
+		hfdl_fence_mbar_init();
 		lk_loaded = 0; lk_tail = (int)(a.state[c].symsync_out_idx & 1u); lk_tail_k = -1; lk_end_seq = 0x7fffffff; lk_done = 0;
 		lk_reset_gen = 0; lk_reset_k = 0; lk_reset_seq = 0; lk_ack_gen = 0;
 	}
@@ -556,32 +559,40 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 
 	if(warp == 2) {
 		// =========================== loader warp ===========================
+		// One TMA bulk copy (cp.async.bulk) per chunk of HFDL_LK_CH samples: 8 KiB of filter-bank rows + the chunk's AGC
+		// levels, issued by lane 0, HFDL_LK_INFLIGHT chunks in flight, each completing on its own mbarrier.
 		const cf *bank = a.bank + (long long)c * a.bank_stride * 32;
 		const int nchunks = (N + HFDL_LK_CH - 1) / HFDL_LK_CH;
-		for(int ch = 0; ch < nchunks + HFDL_LK_INFLIGHT; ch++) {
-			if(ch < nchunks) {
-				const int n0 = ch * HFDL_LK_CH;
-				// ring space: samples the demodulator warp has not passed yet must stay (the timing warp may be rolled back to them)
-				while(n0 + HFDL_LK_CH > HFDL_UNI(lk_tail_k) + 1 + HFDL_LK_BR - HFDL_LK_CH) {
-					if(HFDL_UNI(lk_done)) break;
-					HFDL_SPIN_PAUSE();
+		if(lane == 0) {
+			for(int ch = 0; ch < nchunks + HFDL_LK_INFLIGHT - 1; ch++) {
+				if(ch < nchunks) {
+					const int n0 = ch * HFDL_LK_CH;
+					// ring space: samples the demodulator warp has not passed yet must stay (the timing warp may be rolled back to them)
+					while(n0 + HFDL_LK_CH > lk_tail_k + 1 + HFDL_LK_BR - HFDL_LK_CH) {
+						if(lk_done) break;
+						HFDL_SPIN_PAUSE();
+					}
+					__threadfence_block();
+					hfdl_fence_proxy_async();                  // the consumers' reads of this ring slot come before the copy's writes
+					const int cnt = (N - n0 < HFDL_LK_CH) ? (N - n0) : HFDL_LK_CH;
+					const unsigned bank_bytes = (unsigned)cnt * 256u, lvl_bytes = (unsigned)((cnt + 3) & ~3) * 4u;
+					hfdl_mbar_t *mb = &lk_mbar[ch % HFDL_LK_INFLIGHT];
+					hfdl_mbar_expect_tx(mb, bank_bytes + lvl_bytes);
+					hfdl_bulk_g2s(s_bank + (n0 & (HFDL_LK_BR - 1)) * 32, bank + (long long)n0 * 32, bank_bytes, mb);
+					hfdl_bulk_g2s(&lk_lvl[n0 & (HFDL_LK_BR - 1)], &lvl[n0], lvl_bytes, mb);
+					hfdl_mbar_arrive_emul(mb);
 				}
-				const int cnt = (N - n0 < HFDL_LK_CH) ? (N - n0) : HFDL_LK_CH;
-				const char *src = reinterpret_cast<const char *>(bank + (long long)n0 * 32);
-				char *dst = reinterpret_cast<char *>(s_bank + (n0 & (HFDL_LK_BR - 1)) * 32);
-				for(int i = lane; i < cnt * 16; i += 32) hfdl_cp_async16(dst + i * 16, src + (long long)i * 16);
-				if(lane < cnt) hfdl_cp_async4(&lk_lvl[(n0 + lane) & (HFDL_LK_BR - 1)], &lvl[n0 + lane]);
-			}
-			hfdl_cp_async_commit();
-			if(ch >= HFDL_LK_INFLIGHT - 1) {             // chunk ch-(INFLIGHT-1) has landed
-				hfdl_cp_async_wait<HFDL_LK_INFLIGHT - 1>();
-				__syncwarp();
-				__threadfence_block();
-				const int ready = (ch - (HFDL_LK_INFLIGHT - 1) + 1) * HFDL_LK_CH;
-				if(lane == 0) lk_loaded = ready < N ? ready : N;
+				if(ch >= HFDL_LK_INFLIGHT - 1) {             // chunk ch-(INFLIGHT-1) has to land before its barrier is armed again
+					const int done_ch = ch - (HFDL_LK_INFLIGHT - 1);
+					hfdl_mbar_t *mb = &lk_mbar[done_ch % HFDL_LK_INFLIGHT];
+					const unsigned parity = (unsigned)(done_ch / HFDL_LK_INFLIGHT) & 1u;
+					while(!hfdl_mbar_try_wait(mb, parity)) { }
+					__threadfence_block();
+					const int ready = (done_ch + 1) * HFDL_LK_CH;
+					lk_loaded = ready < N ? ready : N;
+				}
 			}
 		}
-		hfdl_cp_async_wait<0>();
 	} else if(warp == 1) {
 		// =========================== timing warp (producer) ===========================
 		DemodState S = a.state[c];

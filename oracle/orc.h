@@ -210,6 +210,8 @@ int  orc_tx_frame_symbols(const orc_tx_frame_t *f, cf32 *out, int max);
 /* render frames into a wideband capture (adds to 'out').  cyclic!=0: capture is treated as periodic (looped slab) */
 void orc_tx_render(cf32 *out, int64_t nsamples, int32_t sample_rate, int32_t centerfreq,
 		const orc_tx_frame_t *frames, int nframes, int cyclic, int nthreads);
+void orc_tx_render_range(cf32 *out, int64_t first, int64_t count, int64_t nsamples, int32_t sample_rate, int32_t centerfreq,
+		const orc_tx_frame_t *frames, int nframes, int cyclic, int nthreads);
 void orc_tx_add_noise(cf32 *out, int64_t nsamples, double sigma, uint64_t seed, int nthreads);
 void orc_quantize_cs16(const cf32 *in, int64_t n, int16_t *out);
 void orc_quantize_cu8(const cf32 *in, int64_t n, uint8_t *out);

@@ -77,10 +77,35 @@ static void stage2(int n, int s, int ts, const cf32 *restrict W, int conj, const
 }
 
 struct stage_job { int radix, n, s, ts, conj, p0, p1; const cf32 *W, *x; cf32 *y; };
-static void *stage_worker(void *arg) {
-	struct stage_job *j = arg;
+static void stage_run(struct stage_job *j) {
 	if(j->radix == 4) stage4(j->n, j->s, j->ts, j->W, j->conj, j->x, j->y, j->p0, j->p1);
 	else stage2(j->n, j->s, j->ts, j->W, j->conj, j->x, j->y, j->p0, j->p1);
+}
+
+/* Persistent worker pool for the stages of large transforms (fftw3f_threads keeps its workers too): created once,
+ * woken per stage.  One transform uses it at a time; a concurrent caller (the channel threads' small inverse FFTs
+ * never get here, n*s < 2^19) simply runs its stage on its own thread. */
+#define POOL_MAX 64
+static struct {
+	pthread_mutex_t busy, m;
+	pthread_cond_t cv_go, cv_done;
+	pthread_t th[POOL_MAX];
+	int nth;                       /* workers started */
+	struct stage_job jobs[POOL_MAX + 1];
+	int njobs, next, pending;
+} P = { PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, {{0}}, 0, 0, 0 };
+
+static void *pool_worker(void *arg) {
+	(void)arg;
+	pthread_mutex_lock(&P.m);
+	for(;;) {
+		while(P.next >= P.njobs) pthread_cond_wait(&P.cv_go, &P.m);
+		struct stage_job *j = &P.jobs[P.next++];
+		pthread_mutex_unlock(&P.m);
+		stage_run(j);
+		pthread_mutex_lock(&P.m);
+		if(--P.pending == 0) pthread_cond_signal(&P.cv_done);
+	}
 	return NULL;
 }
 
@@ -88,19 +113,32 @@ static void run_stage(int radix, int n, int s, int ts, const cf32 *W, int conj, 
 	int np = n / radix;
 	int nt = g_fft_threads;
 	if(nt > np) nt = np;
-	if(nt <= 1 || (size_t)n * s < 65536) {
+	if(nt > POOL_MAX) nt = POOL_MAX;
+	if(nt <= 1 || (size_t)n * s < (1u << 19) || pthread_mutex_trylock(&P.busy) != 0) {
 		struct stage_job j = { radix, n, s, ts, conj, 0, np, W, x, y };
-		stage_worker(&j);
+		stage_run(&j);
 		return;
 	}
-	pthread_t th[64];
-	struct stage_job jobs[64];
-	if(nt > 64) nt = 64;
-	for(int t = 0; t < nt; t++) {
-		jobs[t] = (struct stage_job){ radix, n, s, ts, conj, (int)((int64_t)np * t / nt), (int)((int64_t)np * (t + 1) / nt), W, x, y };
-		pthread_create(&th[t], NULL, stage_worker, &jobs[t]);
+	pthread_mutex_lock(&P.m);
+	while(P.nth < nt - 1) {                       /* the calling thread is worker number nt */
+		pthread_create(&P.th[P.nth], NULL, pool_worker, NULL);
+		pthread_detach(P.th[P.nth]);
+		P.nth++;
 	}
-	for(int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+	for(int t = 0; t < nt; t++)
+		P.jobs[t] = (struct stage_job){ radix, n, s, ts, conj, (int)((int64_t)np * t / nt), (int)((int64_t)np * (t + 1) / nt), W, x, y };
+	P.njobs = nt; P.next = 0; P.pending = nt;
+	pthread_cond_broadcast(&P.cv_go);
+	while(P.next < P.njobs) {                     /* the caller works too */
+		struct stage_job *j = &P.jobs[P.next++];
+		pthread_mutex_unlock(&P.m);
+		stage_run(j);
+		pthread_mutex_lock(&P.m);
+		P.pending--;
+	}
+	while(P.pending > 0) pthread_cond_wait(&P.cv_done, &P.m);
+	pthread_mutex_unlock(&P.m);
+	pthread_mutex_unlock(&P.busy);
 }
 
 void orc_fft(const cf32 *in, cf32 *out, int N, int dir) {

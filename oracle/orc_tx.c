@@ -195,6 +195,12 @@ static void *render_worker(void *arg) {
 
 void orc_tx_render(cf32 *out, int64_t nsamples, int32_t sr, int32_t centerfreq,
 		const orc_tx_frame_t *frames, int nframes, int cyclic, int nthreads) {
+	orc_tx_render_range(out, 0, nsamples, nsamples, sr, centerfreq, frames, nframes, cyclic, nthreads);
+}
+
+/* samples [first, first + count) of a capture of nsamples samples; out[0] is sample 'first' */
+void orc_tx_render_range(cf32 *out, int64_t first, int64_t count, int64_t nsamples, int32_t sr, int32_t centerfreq,
+		const orc_tx_frame_t *frames, int nframes, int cyclic, int nthreads) {
 	if(!ik_ok) ik_init();
 	cf32 **bb = malloc(sizeof(cf32 *) * (size_t)nframes);
 	int *bbn = malloc(sizeof(int) * (size_t)nframes);
@@ -208,7 +214,7 @@ void orc_tx_render(cf32 *out, int64_t nsamples, int32_t sr, int32_t centerfreq,
 	pthread_t th[64];
 	struct render_job jobs[64];
 	for(int t = 0; t < nthreads; t++) {
-		jobs[t] = (struct render_job){ out, nsamples * t / nthreads, nsamples * (t + 1) / nthreads, nsamples, sr, centerfreq,
+		jobs[t] = (struct render_job){ out - first, first + count * t / nthreads, first + count * (t + 1) / nthreads, nsamples, sr, centerfreq,
 			frames, nframes, cyclic, bb, bbn };
 		pthread_create(&th[t], NULL, render_worker, &jobs[t]);
 	}

@@ -174,7 +174,7 @@ void ref_dumps_clear(void) {}
 #endif
 
 /* ---------------- the wiring of main.c:697-711,739-755,770-774 ---------------- */
-typedef struct {
+typedef struct ref_pipeline_s {
 	struct input input;            /* stands for the input block (input-common.c:43-63, input-file.c:76-110) */
 	struct input_cfg cfg;
 	struct block *fft;
@@ -185,6 +185,9 @@ typedef struct {
 } ref_pipeline_t;
 
 static int g_globals_done;
+
+struct create_job { struct ref_pipeline_s *p; int32_t sample_rate, dec; float tbw; int32_t centerfreq; const int32_t *freqs; int t, nt, fail; };
+static void *create_worker(void *arg);
 
 ref_pipeline_t *ref_pipeline_create(int32_t sample_rate, int32_t centerfreq, const int32_t *freqs, int32_t nfreq, int32_t sfmt, int32_t fft_threads) {
 	ref_pipeline_t *p = calloc(1, sizeof(*p));
@@ -197,9 +200,22 @@ ref_pipeline_t *ref_pipeline_create(int32_t sample_rate, int32_t centerfreq, con
 	if(!g_globals_done) { hfdl_init_globals(); g_globals_done = 1; }                        /* main.c:739 */
 	p->nch = nfreq;
 	p->channels = calloc((size_t)nfreq, sizeof(struct block *));
-	for(int32_t i = 0; i < nfreq; i++) {
-		p->channels[i] = hfdl_channel_create(sample_rate, dec, tbw, centerfreq, freqs[i]);   /* main.c:743-744 */
-		if(!p->channels[i]) return NULL;
+	{
+		/* main.c:741-750 creates the channels one after the other; each creation is independent (taps design + an
+		 * N-point FFT), so with hundreds of channels the set-up is spread over a few threads -- set-up only, not timed */
+		struct create_job jobs[16];
+		pthread_t th[16];
+		int nt = nfreq < 16 ? nfreq : 16;
+		long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+		if(ncpu > 0 && nt > ncpu) nt = (int)ncpu;
+		if(nt < 1) nt = 1;
+		for(int t = 0; t < nt; t++) {
+			jobs[t] = (struct create_job){ p, sample_rate, dec, tbw, centerfreq, freqs, t, nt, 0 };
+			pthread_create(&th[t], NULL, create_worker, &jobs[t]);
+		}
+		int fail = 0;
+		for(int t = 0; t < nt; t++) { pthread_join(th[t], NULL); fail |= jobs[t].fail; }
+		if(fail) return NULL;
 	}
 	/* input block as input_create + file_input_init leave it (input-common.c:55, input-file.c:98-107) */
 	p->cfg.sfmt = (sample_format)sfmt; p->cfg.sample_rate = sample_rate; p->cfg.centerfreq = centerfreq;
@@ -216,6 +232,15 @@ ref_pipeline_t *ref_pipeline_create(int32_t sample_rate, int32_t centerfreq, con
 			block_connect_one2many(p->fft, (size_t)nfreq, p->channels) != nfreq) return NULL;       /* main.c:752-753 */
 	if(block_set_start((size_t)nfreq, p->channels) != nfreq || block_start(p->fft) != 1) return NULL;   /* main.c:770-771 */
 	return p;
+}
+
+static void *create_worker(void *arg) {
+	struct create_job *j = arg;
+	for(int32_t i = j->t; i < j->p->nch; i += j->nt) {
+		j->p->channels[i] = hfdl_channel_create(j->sample_rate, j->dec, j->tbw, j->centerfreq, j->freqs[i]);   /* main.c:743-744 */
+		if(!j->p->channels[i]) j->fail = 1;
+	}
+	return NULL;
 }
 
 /* what file_input_thread does per read (input-file.c:50-63): wait for ring space, convert, produce */

@@ -132,6 +132,7 @@ def lib(fast=False):
     L.orc_tx_frame_baseband.argtypes = [C.POINTER(TxFrame), cfp, C.c_int]
     L.orc_tx_frame_symbols.argtypes = [C.POINTER(TxFrame), cfp, C.c_int]
     L.orc_tx_render.argtypes = [cfp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(TxFrame), C.c_int, C.c_int, C.c_int]
+    L.orc_tx_render_range.argtypes = [cfp, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.POINTER(TxFrame), C.c_int, C.c_int, C.c_int]
     L.orc_tx_add_noise.argtypes = [cfp, C.c_int64, C.c_double, C.c_uint64, C.c_int]
     L.orc_quantize_cs16.argtypes = [cfp, C.c_int64, np.ctypeslib.ndpointer(np.int16)]
     L.orc_quantize_cu8.argtypes = [cfp, C.c_int64, np.ctypeslib.ndpointer(np.uint8)]
@@ -358,6 +359,17 @@ def render(nsamples, sample_rate, centerfreq, frames, noise_sigma=0.0, seed=1, c
     L.orc_tx_render(out, nsamples, sample_rate, centerfreq, arr, len(frames), int(cyclic), nthreads)
     if noise_sigma > 0:
         L.orc_tx_add_noise(out, nsamples, noise_sigma, seed, nthreads)
+    return out
+
+
+def render_range(first, count, nsamples, sample_rate, centerfreq, frames, noise_sigma=0.0, seed=1, cyclic=False, nthreads=8):
+    """samples [first, first + count) of the capture render() would produce (noise stream seeded per range)"""
+    L = lib()
+    out = np.zeros(count, np.complex64)
+    arr = (TxFrame * len(frames))(*frames)
+    L.orc_tx_render_range(out, first, count, nsamples, sample_rate, centerfreq, arr, len(frames), int(cyclic), nthreads)
+    if noise_sigma > 0:
+        L.orc_tx_add_noise(out, count, noise_sigma, seed, nthreads)
     return out
 
 
