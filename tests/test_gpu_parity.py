@@ -76,7 +76,9 @@ def test_frontend_three_pass_fft_plan(lib):
 def test_frontend_cfg3_geometry_many_channels(lib):
     """BASELINE config 3 geometry: 20 Msps -> N = 2^22 (three-pass FFT, 2 blocks per L2-sized sub-batch), M = 4096,
     1792 outputs per block, resampler 0.55296; 40 channels spread over the band, all four single-slot modes.
-    PDUs, counters, front parser, spectrum / channeliser / AGC / MF / EQ checkpoints vs the oracle."""
+    PDUs, counters, front parser, spectrum / channeliser / AGC / MF / EQ checkpoints vs the oracle.  The channeliser
+    tolerance is wider than at 896 outputs per block: the oracle follows the reference's recursive phasor
+    (libcsdr_gpl.c:41-74, whose error grows along the 1792-sample block), the device uses the closed-form phase."""
     sr = 20000000
     nch = 40
     delta = int(0.85 * sr / nch / 1000) * 1000
@@ -86,7 +88,7 @@ def test_frontend_cfg3_geometry_many_channels(lib):
     assert (g.fft_size, g.fft_inv_size, g.input_size, g.out_per_block, g.fft_passes) == (1 << 22, 4096, 3670016, 1792, 3)
     assert abs(g.resamp_rate - 0.55296) < 1e-6
     fe.close()
-    assert K.case_frontend(lib, sr, freqs, [k % 4 for k in range(nch)], 2.75, batch=5, seed=23) == nch
+    assert K.case_frontend(lib, sr, freqs, [k % 4 for k in range(nch)], 2.8, batch=5, seed=23, starts=[0.05 + 0.005 * k for k in range(nch)], tol_ddc=2e-4) == nch
 
 
 def test_tapslice_checkpoint_vs_oracle(lib):
