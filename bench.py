@@ -377,7 +377,7 @@ def main():
     def pass_device():
         if world > 1:
             buf = bufs[state["i"] % nbuf]
-            fe.wait_input()                             # the batches queued so far have read their buffers (channeliser stage only)
+            fe.wait_input(nbuf - 1)                     # the batch that read this buffer nbuf passes ago is through the channeliser stage
             if rank == 0:
                 buf.copy_(d_slab, non_blocking=True)
             dist.broadcast(buf, src=0)                  # NCCL over NVLink; only its stream is waited for, the batch pipeline keeps running
@@ -430,13 +430,27 @@ def main():
         fe2 = hb.Frontend(W["sr"], CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
         st2 = {"pos": 0, "i": 0}
 
+        copy_stream = torch.cuda.Stream() if world > 1 else None
+        d_parts = [d_part, torch.empty_like(d_part)] if world > 1 else None
+        h2d_ev = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
+
+        def start_h2d(i):
+            # this rank's 1/N of pass i over its own PCIe link, on its own stream (runs beside the all-gather of pass i-1)
+            with torch.cuda.stream(copy_stream):
+                d_parts[i % 2].copy_(h_part, non_blocking=True)
+                h2d_ev[i % 2].record(copy_stream)
+
         def pass_host():
+            i = st2["i"]
             if world > 1:
-                buf = bufs[st2["i"] % nbuf]
-                fe2.wait_input()
-                d_part.copy_(h_part, non_blocking=True)                 # this rank's 1/N of the pass over its own PCIe link
-                dist.all_gather_into_tensor(buf, d_part)                # NVLink: every GPU ends up with the whole capture
+                buf = bufs[i % nbuf]
+                if i == 0:
+                    start_h2d(0)
+                fe2.wait_input(nbuf - 1)
+                torch.cuda.current_stream().wait_event(h2d_ev[i % 2])
+                dist.all_gather_into_tensor(buf, d_parts[i % 2])       # NVLink: every GPU ends up with the whole capture
                 torch.cuda.current_stream().synchronize()
+                start_h2d(i + 1)                                       # d_parts[(i+1) % 2] was read by the all-gather of pass i-1, which has completed
                 fe2.process_device(buf.data_ptr(), nsamp, st2["pos"], nblocks)
             else:
                 fe2.push_ptr(h_part.data_ptr(), nsamp)                  # H2D inside the C-ABI call

@@ -61,7 +61,7 @@ def bind(L):
     L.hfdl_b200_process_device.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int32]
     L.hfdl_b200_sync.argtypes = [vp]
     L.hfdl_b200_submit.argtypes = [vp]
-    L.hfdl_b200_wait_input.argtypes = [vp]
+    L.hfdl_b200_wait_input.argtypes = [vp, C.c_int32]
     L.hfdl_b200_push_peer.argtypes = [vp, vp]
     L.hfdl_b200_poll.argtypes = [vp]
     L.hfdl_b200_busy.argtypes = [vp]
@@ -218,8 +218,8 @@ class Frontend:
             raise RuntimeError("hfdl_b200_push_peer failed")
         return r
 
-    def wait_input(self):
-        if self.L.hfdl_b200_wait_input(self.h) != 0:
+    def wait_input(self, keep=0):
+        if self.L.hfdl_b200_wait_input(self.h, keep) != 0:
             raise RuntimeError("hfdl_b200_wait_input failed")
 
     def submit(self):

@@ -413,10 +413,10 @@ __global__ void __launch_bounds__(32) fec_kernel(FecArgs a) {
 			}
 		}
 		for(int j = 0; j < arity; j++) {
-			int p = i * arity + j;
-			int row = p % 40;
-			int col = (int)(((long long)(p / 40) - (long long)shift * p) % ncol);
-			if(col < 0) col += ncol;
+			const unsigned p = (unsigned)(i * arity + j);
+			const unsigned row = p % 40u;
+			// column (p/40 - shift*p) mod ncol in 32-bit unsigned arithmetic (shift*p < 2^19)
+			const unsigned col = ((p / 40u) % (unsigned)ncol + (unsigned)ncol - ((unsigned)shift * p) % (unsigned)ncol) % (unsigned)ncol;
 			table[row * ncol + col] = soft[j];
 			if(a.soft_out) a.soft_out[(long long)q * HFDL_FEC_VIN_MAX + p] = soft[j];
 		}
@@ -464,17 +464,30 @@ __global__ void __launch_bounds__(32) fec_kernel(FecArgs a) {
 	PduRec *out = &a.pdus[q];
 	const int out_octets = nbits / 8 + ((nbits % 8) ? 1 : 0);
 	if(lane == 0) {
+		// Sequential by nature (each step's state selects the next decision bit), so the dependent chain is kept to
+		// shift / mask / or: the decision words of eight steps are loaded ahead of the chain, and an octet is stored once,
+		// when its last bit (n % 8 == 0) has been shifted in -- the value the reference's per-step store leaves behind.
 		unsigned endstate = 0;
 		for(int i = 0; i < out_octets; i++) out->octets[i] = 0;
-		for(int n = nbits - 1; n >= 0; n--) {
-			unsigned st = endstate >> 2;
+		int n = nbits - 1;
+		for(; (n & 7) != 7 && n >= 0; n--) {                 // ragged top octet (nbits not a multiple of 8)
+			const unsigned st = endstate >> 2;
 			unsigned k = 0;
-			if(n + 6 < nbits) {
-				uint2 d = dec[n + 6];
-				k = (((st & 1u) ? d.y : d.x) >> (st >> 1)) & 1u;
-			}
+			if(n + 6 < nbits) { const uint2 d = dec[n + 6]; k = (((st & 1u) ? d.y : d.x) >> (st >> 1)) & 1u; }
 			endstate = ((endstate >> 1) | (k << 7)) & 0xFFu;
-			out->octets[n >> 3] = (unsigned char)endstate;
+			if((n & 7) == 0) out->octets[n >> 3] = (unsigned char)endstate;
+		}
+		for(; n >= 7; n -= 8) {
+			uint2 d[8];
+#pragma unroll
+			for(int q = 0; q < 8; q++) d[q] = (n - q + 6 < nbits) ? dec[n - q + 6] : make_uint2(0u, 0u);
+#pragma unroll
+			for(int q = 0; q < 8; q++) {
+				const unsigned st = endstate >> 2;
+				const unsigned k = (((st & 1u) ? d[q].y : d[q].x) >> (st >> 1)) & 1u;
+				endstate = ((endstate >> 1) | (k << 7)) & 0xFFu;
+			}
+			out->octets[(n - 7) >> 3] = (unsigned char)endstate;
 		}
 		if(!a.vin_direct) for(int i = 0; i < out_octets; i++)  // REVERSE_BYTE (util.h:109, hfdl.c:1051-1053)
 			out->octets[i] = (unsigned char)(__brev((unsigned)out->octets[i]) >> 24);

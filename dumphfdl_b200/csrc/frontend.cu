@@ -817,10 +817,13 @@ int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe) {
 	return r;
 }
 
-int32_t hfdl_b200_wait_input(hfdl_b200_frontend_t *fe) {
+int32_t hfdl_b200_wait_input(hfdl_b200_frontend_t *fe, int32_t keep) {
 	HFDL_API(fe, -1);
-	if(fe->batch_seq == 0) return 0;
-	CK(cudaEventSynchronize(fe->ev_front[(fe->batch_seq + HFDL_NSETS - 1) % HFDL_NSETS]));
+	if(keep < 0) keep = 0;
+	if(keep > HFDL_NSETS - 1) keep = HFDL_NSETS - 1;
+	const long long last = fe->batch_seq - 1 - keep;          // newest batch that must have read its input
+	if(last < 0) return 0;
+	CK(cudaEventSynchronize(fe->ev_front[last % HFDL_NSETS]));
 	return 0;
 }
 

@@ -128,10 +128,11 @@ int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe);
  * ring index p % ring_samples; positions < 0 read as zeros).  Consecutive calls must continue the stream. */
 int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t ring_samples,
 		int64_t start_sample, int32_t nblocks);
-/* hfdl_b200_process_device returns while its batches are still queued: this call blocks until every queued batch has
- * finished READING the caller's device buffer (the channeliser stage; the demodulator stages keep running), i.e. until
- * the buffer may be overwritten. */
-int32_t hfdl_b200_wait_input(hfdl_b200_frontend_t *fe);
+/* hfdl_b200_process_device returns while its batches are still queued: this call blocks until all queued batches but
+ * the newest `keep` (0..3) have finished READING the caller's device buffer (the channeliser stage; the demodulator
+ * stages keep running), i.e. until the buffers of the older batches may be overwritten.  A caller that rotates over
+ * k buffers, one process_device call (of at most max_blocks_per_batch blocks) each, passes keep = k - 1. */
+int32_t hfdl_b200_wait_input(hfdl_b200_frontend_t *fe, int32_t keep);
 /* Blocks until all queued GPU work of this frontend is complete and PDUs are collected. */
 int32_t hfdl_b200_sync(hfdl_b200_frontend_t *fe);
 /* Streaming use: queue every whole block buffered so far on the GPU and return at once (no waiting; returns the

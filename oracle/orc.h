@@ -180,6 +180,10 @@ enum { ORC_SFMT_CU8 = 1, ORC_SFMT_CS16 = 2, ORC_SFMT_CF32 = 3 };               /
 orc_pipeline_t *orc_pipeline_create(int32_t sample_rate, int32_t centerfreq, const int32_t *freqs, int32_t nfreq,
 		int fold_mode, int nthreads);
 void orc_pipeline_destroy(orc_pipeline_t *p);
+/* run on the spectrum ring (include/hfdl_b200_ring.h) instead of the reference's barrier pair: `depth` spectra in flight;
+ * must be called before the first feed.  orc_pipeline_sync waits until every fed block has been demodulated. */
+int  orc_pipeline_use_ring(orc_pipeline_t *p, int depth);
+void orc_pipeline_sync(orc_pipeline_t *p);
 orc_channel_t *orc_pipeline_channel(orc_pipeline_t *p, int idx);
 const orc_ddc_t *orc_pipeline_ddc(orc_pipeline_t *p);
 /* raw samples in 'sfmt' (input-helpers.c:10-78 scaling); whole blocks are processed, the rest is kept. returns blocks run */

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <pthread.h>
 #include "orc.h"
+#include "../include/hfdl_b200_ring.h"      /* the spectrum ring runtime under test (product host code, dumphfdl_b200/csrc/spectrum_ring.c) */
 
 struct orc_pipeline {
 	int32_t sample_rate, centerfreq, nch;
@@ -23,7 +24,10 @@ struct orc_pipeline {
 	cf32 *pending; int64_t npending, cap_pending;
 	int64_t blocks_done;
 	orc_pdu_t *sorted; int nsorted;
+	/* optional: spectrum ring instead of the reference's barrier pair: FFT of block k+1 beside the channels of block k */
+	hfdl_spectrum_ring_t *ring; int nworkers; pthread_t *workers; struct ring_worker *wctx;
 };
+struct ring_worker { orc_pipeline_t *p; int id; };
 
 void orc_convert_samples(const void *raw, int64_t n, int sfmt, cf32 *out) {
 	if(sfmt == ORC_SFMT_CF32) {                         /* full_scale 1.0 */
@@ -58,8 +62,42 @@ orc_pipeline_t *orc_pipeline_create(int32_t sample_rate, int32_t centerfreq, con
 	return p;
 }
 
+static void *ring_worker_main(void *arg) {
+	struct ring_worker *w = arg;
+	orc_pipeline_t *p = w->p;
+	for(;;) {
+		const float *spec = hfdl_spectrum_ring_consume_begin(p->ring, w->id);
+		if(!spec) break;
+		for(int c = w->id; c < p->nch; c += p->nworkers) orc_channel_process_block(p->ch[c], (const cf32 *)spec);
+		hfdl_spectrum_ring_consume_end(p->ring, w->id);
+	}
+	return NULL;
+}
+
+/* switch the pipeline to the ring runtime: `depth` spectra in flight, min(nthreads, channels) channel workers */
+int orc_pipeline_use_ring(orc_pipeline_t *p, int depth) {
+	if(p->ring || p->blocks_done > 0) return -1;
+	p->nworkers = p->nthreads < p->nch ? p->nthreads : p->nch;
+	if(p->nworkers < 1) p->nworkers = 1;
+	p->ring = hfdl_spectrum_ring_create((size_t)p->ddc.fft_size, depth, p->nworkers);
+	if(!p->ring) return -1;
+	p->workers = calloc((size_t)p->nworkers, sizeof(pthread_t));
+	p->wctx = calloc((size_t)p->nworkers, sizeof(struct ring_worker));
+	for(int i = 0; i < p->nworkers; i++) {
+		p->wctx[i] = (struct ring_worker){ p, i };
+		pthread_create(&p->workers[i], NULL, ring_worker_main, &p->wctx[i]);
+	}
+	return 0;
+}
+
 void orc_pipeline_destroy(orc_pipeline_t *p) {
 	if(!p) return;
+	if(p->ring) {
+		hfdl_spectrum_ring_shutdown(p->ring);
+		for(int i = 0; i < p->nworkers; i++) pthread_join(p->workers[i], NULL);
+		hfdl_spectrum_ring_destroy(p->ring);
+		free(p->workers); free(p->wctx);
+	}
 	for(int i = 0; i < p->nch; i++) orc_channel_destroy(p->ch[i]);
 	free(p->ch); free(p->window); free(p->spectrum); free(p->pending); free(p->sorted); free(p);
 }
@@ -79,6 +117,15 @@ static void run_block(orc_pipeline_t *p, const cf32 *newsamples) {
 	memmove(p->window, p->window + d->input_size, sizeof(cf32) * (size_t)d->overlap_length);
 	memcpy(p->window + d->overlap_length, newsamples, sizeof(cf32) * (size_t)d->input_size);
 	orc_fft_set_threads(p->nthreads);
+	if(p->ring) {
+		/* producer side of the ring: this thread is the fft thread (fft.c:49-61 without the barrier pair) */
+		cf32 *slot = (cf32 *)hfdl_spectrum_ring_produce_begin(p->ring);
+		orc_fft(p->window, slot, d->fft_size, +1);
+		orc_swap_sides(slot, d->fft_size);
+		hfdl_spectrum_ring_produce_end(p->ring);
+		p->blocks_done++;
+		return;
+	}
 	orc_fft(p->window, p->spectrum, d->fft_size, +1);
 	orc_swap_sides(p->spectrum, d->fft_size);
 	int nt = p->nthreads < p->nch ? p->nthreads : p->nch;
@@ -122,8 +169,10 @@ static int pdu_cmp(const void *a, const void *b) {
 	if(x->sample_cnt_end != y->sample_cnt_end) return x->sample_cnt_end < y->sample_cnt_end ? -1 : 1;
 	return (x->freq > y->freq) - (x->freq < y->freq);
 }
+void orc_pipeline_sync(orc_pipeline_t *p) { if(p->ring) hfdl_spectrum_ring_drain(p->ring); }
 static void collect(orc_pipeline_t *p) {
 	int n = 0;
+	orc_pipeline_sync(p);
 	for(int i = 0; i < p->nch; i++) n += orc_channel_pdu_count(p->ch[i]);
 	p->sorted = realloc(p->sorted, sizeof(orc_pdu_t) * (size_t)(n ? n : 1));
 	int k = 0;

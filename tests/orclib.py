@@ -119,6 +119,8 @@ def lib(fast=False):
     L.orc_pipeline_create.restype = C.c_void_p
     L.orc_pipeline_create.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_int, C.c_int]
     L.orc_pipeline_destroy.argtypes = [C.c_void_p]
+    L.orc_pipeline_use_ring.argtypes = [C.c_void_p, C.c_int]
+    L.orc_pipeline_sync.argtypes = [C.c_void_p]
     L.orc_pipeline_channel.restype = C.c_void_p
     L.orc_pipeline_channel.argtypes = [C.c_void_p, C.c_int]
     L.orc_pipeline_ddc.restype = C.POINTER(Ddc)
@@ -374,11 +376,13 @@ def render_range(first, count, nsamples, sample_rate, centerfreq, frames, noise_
 
 
 class Pipeline:
-    def __init__(self, sample_rate, centerfreq, freqs, fold_mode=FOLD_FULL, nthreads=8, fast=False):
+    def __init__(self, sample_rate, centerfreq, freqs, fold_mode=FOLD_FULL, nthreads=8, fast=False, ring_depth=0):
         self.L = lib(fast)
         fa = (C.c_int32 * len(freqs))(*freqs)
         self.p = self.L.orc_pipeline_create(sample_rate, centerfreq, fa, len(freqs), fold_mode, nthreads)
         assert self.p
+        if ring_depth > 0:       # spectrum ring (include/hfdl_b200_ring.h) instead of the reference's barrier pair
+            assert self.L.orc_pipeline_use_ring(self.p, ring_depth) == 0
         self.freqs = list(freqs)
         self.ddc = self.L.orc_pipeline_ddc(self.p).contents
 
@@ -386,6 +390,9 @@ class Pipeline:
         raw = np.ascontiguousarray(raw)
         n = raw.size if sfmt == SFMT_CF32 and raw.dtype == np.complex64 else raw.size // 2
         return self.L.orc_pipeline_feed(self.p, raw.ctypes.data, n, sfmt)
+
+    def sync(self):
+        self.L.orc_pipeline_sync(self.p)
 
     def pdus(self):
         n = self.L.orc_pipeline_pdu_count(self.p)

@@ -230,6 +230,7 @@ def test_device_resident_path_equals_host_path(lib):
         k = min(5, nb - done)
         fe2.process_device(d.data_ptr(), x.size, done * isz, k)
         done += k
+    fe2.sync()                  # process_device only queues the batches
     b = fe2.pdus()
     K.compare_pdus(b, [O_pdu(q) for q in a], truth)
 
