@@ -297,7 +297,11 @@ struct RowPassArgs {
 	int N, lgL, R, lgR, first;
 	cf *out;           // fft_last_pass_nat: natural-order spectrum [B][N]
 	int L1, mid;       // fft_last_pass_nat: length of the first axis; product of the middle axes (1 for two-pass plans)
+	const unsigned *mask;   // fft_last_pass_nat: one bit per granule of HFDL_SPEC_GRAN natural bins, set when some channel's
+	                        // pass-band slice reads the granule; results of other granules are not stored (nullptr: store all)
 };
+#define HFDL_SPEC_LG_GRAN 5
+#define HFDL_SPEC_GRAN (1 << HFDL_SPEC_LG_GRAN)
 
 __global__ void __launch_bounds__(HFDL_FFT_THREADS) fft_row_pass(RowPassArgs a) {
 	HFDL_DYN_SMEM(cf, s);
@@ -525,9 +529,17 @@ __global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_last_pass_nat(RowP
 #pragma unroll
 		for(int b = 0; b < B; b++) z[b] = s[r * RS + b * 33 + ka];
 		fft_reg_dif<B>(z);
-		cf *o = out + (k10 + r) + (long long)a.L1 * kmid;
+		const long long bin0 = (k10 + r) + (long long)a.L1 * kmid;
+		cf *o = out + bin0;
 #pragma unroll
-		for(int j = 0; j < B; j++) o[kstride * (ka + 32 * brev_ct(j, LGB))] = z[j];
+		for(int j = 0; j < B; j++) {
+			const long long off = kstride * (ka + 32 * brev_ct(j, LGB));
+			if(a.mask) {          // channels cover a small part of the band: only the granules some slice reads are written
+				const unsigned g = (unsigned)((bin0 + off) >> HFDL_SPEC_LG_GRAN);
+				if(!((__ldg(&a.mask[g >> 5]) >> (g & 31u)) & 1u)) continue;
+			}
+			o[off] = z[j];
+		}
 	}
 }
 

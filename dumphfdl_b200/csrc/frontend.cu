@@ -116,6 +116,7 @@ struct hfdl_b200_frontend {
 	FftEngine fft;
 	// device memory
 	cf *d_work = nullptr, *d_spec = nullptr;       // FFT workspace (passes in place) / natural-order spectra (plan.natural)
+	unsigned *d_mask = nullptr; double spec_fill = 1.0;   // spectrum granules the channels read (bit set) / their share of the band
 	void *d_ring = nullptr; long long ring_len = 0;
 	cf *d_tapslice = nullptr; int *d_offsetbin = nullptr; float *d_dsa_rate = nullptr;
 	cf *d_bb = nullptr; long long bb_stride = 0;
@@ -190,7 +191,7 @@ inline void prof_end2(hfdl_b200_frontend *fe, ProfRec &r, cudaStream_t st) {
 // forward FFT of nb windows described by src into work (scrambled layout)
 // forward FFT of nb windows: passes in place in `work`; when pl.natural the last pass writes the natural-order
 // spectrum to `spec` (else the digit-scrambled spectrum stays in `work`)
-int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, const RawSource &src, cf *work, cf *spec, int nb, cudaStream_t st) {
+int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, const RawSource &src, cf *work, cf *spec, int nb, cudaStream_t st, const unsigned *mask = nullptr) {
 	int inner = pl.N;
 	int outer = 1;
 	for(int p = 0; p < pl.P; p++) {
@@ -226,7 +227,7 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 			if(a.R > rows) a.R = rows;
 			a.lgR = hfdl_ilog2(a.R);
 			a.first = (p == 0);
-			a.out = nullptr; a.L1 = 0; a.mid = 0;
+			a.out = nullptr; a.L1 = 0; a.mid = 0; a.mask = mask;
 			const int lgb = lgL - 5;
 			if(pl.natural) {
 				a.out = spec; a.L1 = 1 << pl.lgL[0]; a.mid = pl.P == 3 ? (1 << pl.lgL[1]) : 1;
@@ -350,25 +351,31 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 	const auto &g = fe->g;
 	hfdl_b200_frontend::Flight &cur = fe->flight[p];
 	ProfRec pr;
+	// FFT passes over sub-batches of Bsub blocks (the in-place intermediate stays in L2 between the passes); the last pass
+	// writes the natural-order spectrum of block b at d_spec + b*N -- only the granules some channel's slice reads
 	for(int b0 = 0; b0 < nb; b0 += fe->Bsub) {
 		const int nsb = std::min(fe->Bsub, nb - b0);
 		RawSource src = src0;
 		src.pos0 = src0.pos0 + (long long)b0 * src0.block_stride;
-		if(run_fft(fe, fe->fft, fe->plan, src, fe->d_work, fe->d_spec, nsb, st)) return -1;
+		cf *spec = fe->plan.natural ? fe->d_spec + (long long)b0 * g.fft_size : nullptr;
+		cf *work = fe->plan.natural ? fe->d_work : fe->d_work + (long long)b0 * g.fft_size;
+		if(run_fft(fe, fe->fft, fe->plan, src, work, spec, nsb, st, fe->d_mask)) return -1;
+	}
+	{
 		ChanArgs a;
 		a.work = fe->plan.natural ? fe->d_spec : fe->d_work; a.tapslice = fe->d_tapslice; a.offsetbin = fe->d_offsetbin; a.dsa_rate = fe->d_dsa_rate;
 		a.bb = fe->d_bb; a.tw = fe->fft.d_tw; a.pl = fe->plan;
 		a.M = g.fft_inv_size; a.lgM = hfdl_ilog2(g.fft_inv_size); a.scrap = g.scrap; a.post_dec = g.post_decimation;
 		a.out_per_block = fe->out_per_block; a.bb_stride = fe->bb_stride;
 		a.out_index0 = fe->blocks_done * (long long)fe->out_per_block;
-		a.block0 = b0;
+		a.block0 = 0;
 		a.inv_norm = 1.0f / (float)(g.pre_decimation * g.fft_inv_size);
 		prof_begin(fe, KC_CHAN, pr);
-		HFDL_LAUNCH(chan_extract, dim3((unsigned)fe->C, (unsigned)nsb), dim3(HFDL_FFT_THREADS), sizeof(cf) * (size_t)a.M, st, a);
+		HFDL_LAUNCH(chan_extract, dim3((unsigned)fe->C, (unsigned)nb), dim3(HFDL_FFT_THREADS), sizeof(cf) * (size_t)a.M, st, a);
 		prof_end(fe, pr);
 		fe->launches++;
 	}
-	fe->last_sub_blocks = nb - ((nb - 1) / fe->Bsub) * fe->Bsub;      // blocks of the last sub-batch (still in d_spec)
+	fe->last_sub_blocks = nb;
 	const long long n_in = (long long)nb * fe->out_per_block;
 	int n_out = 0;
 	{
@@ -503,7 +510,7 @@ int compute_tapslices(hfdl_b200_frontend *fe) {
 			CK(cudaMemcpyAsync(d_in + (size_t)i * N, taps[(size_t)i].data(), sizeof(cf) * (size_t)g.taps_length, cudaMemcpyHostToDevice, fe->stream));
 		RawSource src;
 		src.base = d_in; src.ring_len = (long long)N * nc; src.pos0 = 0; src.ring_origin = 0; src.block_stride = N; src.sfmt = HFDL_SFMT_CF32;
-		if(run_fft(nullptr, fe->fft, fe->plan, src, fe->d_work, fe->d_spec, nc, fe->stream)) return -1;
+		if(run_fft(nullptr, fe->fft, fe->plan, src, fe->d_work, fe->d_spec, nc, fe->stream, fe->d_mask)) return -1;
 		HFDL_LAUNCH(tapslice_gather, dim3((unsigned)((M + 255) / 256), (unsigned)nc), dim3(256), 0, fe->stream,
 			fe->plan.natural ? fe->d_spec : fe->d_work, fe->plan, M, fe->d_offsetbin, c0, fe->d_tapslice);
 		CK(cudaGetLastError());
@@ -561,7 +568,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	// final spectra (2 x Bsub x N x 8 bytes) stay in the 126 MB L2 instead of making a round trip through HBM
 	{
 		const char *e = getenv("HFDL_B200_FFT_SUB_MB");
-		const long long budget = (e ? atoll(e) : 40) << 20;                 // bytes of spectrum per sub-batch
+		const long long budget = (e ? atoll(e) : 80) << 20;                 // bytes of spectrum per sub-batch
 		fe->Bsub = (int)std::max<long long>(1, std::min<long long>(fe->Bmax, budget / ((long long)g.fft_size * 8)));
 	}
 	{ const char *dbg = getenv("HFDL_B200_DEBUG"); fe->debug_mode = dbg ? atoi(dbg) : 0; }
@@ -584,8 +591,29 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	}
 	if(fe->fft.init()) { hfdl_b200_destroy(fe); return -1; }
 	const int C = fe->C, N = g.fft_size, M = g.fft_inv_size, B = fe->Bmax;
-	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * std::max(fe->Bsub, 1)));
-	if(fe->plan.natural) CKD(cudaMalloc((void **)&fe->d_spec, sizeof(cf) * (size_t)N * std::max(fe->Bsub, 1)));
+	// natural-order plans: the in-place workspace only holds one sub-batch, the spectra of the whole batch go to d_spec
+	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * (fe->plan.natural ? std::max(fe->Bsub, 1) : B)));
+	if(fe->plan.natural) CKD(cudaMalloc((void **)&fe->d_spec, sizeof(cf) * (size_t)N * B));
+	if(fe->plan.natural && fe->cfg.capture_channel < 0 && !getenv("HFDL_B200_NO_SPEC_MASK")) {
+		// granules of the spectrum some channel's pass-band slice reads (chan_extract: bins offsetbin - M/2 .. offsetbin + M/2 - 1
+		// mod N); with a capture channel (parity / debug: the CP_SPECTRUM checkpoint wants every bin) everything is stored
+		const long long ngran = (long long)N >> HFDL_SPEC_LG_GRAN;
+		std::vector<unsigned> m((size_t)((ngran + 31) / 32), 0u);
+		for(int i = 0; i < C; i++) {
+			const long long off = fe->chg[(size_t)i].offsetbin;
+			for(long long k = off - M / 2; k < off + M / 2; k += HFDL_SPEC_GRAN) {
+				const long long gidx = (((k % N) + N) % N) >> HFDL_SPEC_LG_GRAN;
+				m[(size_t)(gidx >> 5)] |= 1u << (gidx & 31);
+			}
+			const long long last = ((((off + M / 2 - 1) % N) + N) % N) >> HFDL_SPEC_LG_GRAN;
+			m[(size_t)(last >> 5)] |= 1u << (last & 31);
+		}
+		CKD(cudaMalloc((void **)&fe->d_mask, sizeof(unsigned) * m.size()));
+		CKD(cudaMemcpy(fe->d_mask, m.data(), sizeof(unsigned) * m.size(), cudaMemcpyHostToDevice));
+		long long set = 0;
+		for(unsigned w : m) set += __builtin_popcount(w);
+		fe->spec_fill = (double)set / (double)ngran;
+	}
 	fe->ring_len = (long long)g.overlap_length + (long long)(B + 1) * g.input_size;
 	CKD(cudaMalloc(&fe->d_ring, (size_t)fe->ring_len * fe->bps));
 	CKD(cudaMemset(fe->d_ring, 0, (size_t)fe->ring_len * fe->bps));
@@ -675,7 +703,7 @@ void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	cudaSetDevice(fe->cfg.device);
 	cudaStream_t sts[5] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec, fe->st_stats };
 	for(cudaStream_t q : sts) if(q) cudaStreamSynchronize(q);
-	cudaFree(fe->d_work); cudaFree(fe->d_spec); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
+	cudaFree(fe->d_work); cudaFree(fe->d_spec); cudaFree(fe->d_mask); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
 	cudaFree(fe->d_bb); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
 	cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf); cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp); cudaFree(fe->d_dbg);
 	cudaFree(fe->d_agc_state);
@@ -1002,9 +1030,8 @@ int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_
 	switch(what) {
 	case HFDL_B200_CP_SPECTRUM: {
 		if(index < 0) index = fe->last_nblocks - 1;       // -1: last block processed
-		// only the spectra of the last FFT sub-batch are still on the device
-		index -= fe->last_nblocks - fe->last_sub_blocks;
-		if(index < 0 || index >= fe->last_sub_blocks) return -1;
+		if(index < 0 || index >= fe->last_nblocks) return -1;
+		if(fe->d_mask) return -1;          // pruned spectrum: only the channels' granules exist (create with a capture channel for the full one)
 		avail = g.fft_size;
 		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((g.fft_size + 255) / 256)), dim3(256), 0, fe->stream, fe->plan.natural ? fe->d_spec : fe->d_work, fe->plan, index, 0, g.fft_size, fe->d_tmp);
 		CK(cudaGetLastError());

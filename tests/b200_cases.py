@@ -218,6 +218,26 @@ def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_f
     return len(got)
 
 
+def case_pruned_spectrum(lib, sr, freqs, modes, dur, batch, seed=61):
+    """Without a capture channel the last FFT pass stores only the spectrum granules some channel's slice reads
+    (production mode); with one it stores every bin (parity / debug mode).  Both must give the oracle's PDUs."""
+    x, truth = make_capture(sr, freqs, modes, dur, seed=seed)
+    ref = run_oracle(sr, freqs, x, A.SFMT_CF32).pdus()
+    for cap in (-1, 0):
+        fe = A.Frontend(sr, CF, freqs, max_blocks_per_batch=batch, capture_channel=cap, capture_max=1024 if cap >= 0 else 0, lib=lib)
+        fe.push(x)
+        fe.flush()
+        compare_pdus(fe.pdus(), ref, truth)
+        if cap < 0:
+            try:
+                fe.checkpoint("spectrum", -1)
+                assert False, "the pruned spectrum must not be handed out as a checkpoint"
+            except RuntimeError:
+                pass
+        fe.close()
+    return len(ref)
+
+
 def case_frontend_stream(lib, sr, freqs, plan, dur, batch, esn0=20.0, seed=31, push_blocks=None, submit_poll=False):
     """Several frames per channel over many batches: `plan` = [(channel index, M1, start second), ...].
     Exercises the cross-batch pipeline (sub-range schedule, shared work arrays, deferred PDU collection):

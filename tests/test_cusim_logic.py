@@ -63,3 +63,7 @@ def test_front_parser(sim):
 
 def test_tapslice_checkpoint(sim):
     K.case_tapslice(sim, 250000, [10063000, 9931000])
+
+
+def test_pruned_spectrum_equals_full(sim):
+    assert K.case_pruned_spectrum(sim, 250000, [10063000, 9931000, 10110000], [1, 2, 0], 3.3, batch=5) == 3

@@ -97,6 +97,12 @@ def test_tapslice_checkpoint_vs_oracle(lib):
     K.case_tapslice(lib, 20000000, [K.CF + 8123000, K.CF - 40000, K.CF - 9001000])
 
 
+def test_pruned_spectrum_equals_full(lib):
+    # production mode (only the channels' spectrum granules are stored by the last FFT pass) vs parity mode, cfg 2 and 8 Msps plans
+    assert K.case_pruned_spectrum(lib, 2000000, [K.CF + 212000, K.CF - 424000, K.CF + 636000, K.CF - 900000], [3, 1, 0, 2], 2.9, batch=7) == 4
+    assert K.case_pruned_spectrum(lib, 8000000, [K.CF - 3100000, K.CF + 40000, K.CF + 3900000], [1, 3, 0], 2.9, batch=5, seed=62) == 3
+
+
 def test_front_parser_all_branches(lib):
     K.case_front_parser(lib)
 
