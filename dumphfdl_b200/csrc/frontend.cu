@@ -102,12 +102,12 @@ struct hfdl_b200_frontend {
 	float resamp_rate = 0;
 	// streams: front (H2D, FFT, channeliser, resampler) | agc + bank | loop | fec + D2H.  One launch per stage per batch;
 	// the stages of consecutive batches overlap (front/agc/bank of batch i+1 beside loop of batch i beside fec of i-1).
-	cudaStream_t stream = nullptr, stream2 = nullptr, st_loop = nullptr, st_fec = nullptr, st_stats = nullptr;
+	cudaStream_t stream = nullptr, stream2 = nullptr, st_loop = nullptr, st_fec = nullptr, st_stats = nullptr, st_h2d = nullptr;
 	cudaEvent_t ev_front[HFDL_NSETS] = { nullptr }, ev_bank[HFDL_NSETS] = { nullptr }, ev_loop[HFDL_NSETS] = { nullptr }, ev_fec_done[HFDL_NSETS] = { nullptr };
 	cudaEvent_t ev_h2d = nullptr;
 	struct Flight { bool busy = false; } flight[HFDL_NSETS];
 	std::recursive_mutex mtx;       // every public entry point: the frontend may be driven and queried from different threads
-	bool peer_enabled = false;
+	bool peer_enabled = false, h2d_pending = false;
 	bool failed = false;            // a CUDA call failed mid-pipeline: every later call returns -1
 	int Bsub = 1;                   // blocks per FFT sub-batch (intermediate spectra stay in L2)
 	long long n_out_prev = 0;       // resampled samples of the previous batch (carry source)
@@ -582,6 +582,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaStreamCreateWithFlags(&fe->st_loop, cudaStreamNonBlocking));
 	CKD(cudaStreamCreateWithFlags(&fe->st_fec, cudaStreamNonBlocking));
 	CKD(cudaStreamCreateWithFlags(&fe->st_stats, cudaStreamNonBlocking));
+	CKD(cudaStreamCreateWithFlags(&fe->st_h2d, cudaStreamNonBlocking));
 	CKD(cudaEventCreateWithFlags(&fe->ev_h2d, cudaEventDisableTiming));
 	for(int q = 0; q < HFDL_NSETS; q++) {
 		CKD(cudaEventCreateWithFlags(&fe->ev_front[q], cudaEventDisableTiming));
@@ -614,7 +615,9 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 		for(unsigned w : m) set += __builtin_popcount(w);
 		fe->spec_fill = (double)set / (double)ngran;
 	}
-	fe->ring_len = (long long)g.overlap_length + (long long)(B + 1) * g.input_size;
+	// host-fed ring: B + 1 blocks of capacity plus one batch that may still be read by the channeliser stage while the next
+	// samples arrive (the H2D copies run on their own stream, beside the FFT of the previous batch)
+	fe->ring_len = (long long)g.overlap_length + (long long)(2 * B + 1) * g.input_size;
 	CKD(cudaMalloc(&fe->d_ring, (size_t)fe->ring_len * fe->bps));
 	CKD(cudaMemset(fe->d_ring, 0, (size_t)fe->ring_len * fe->bps));
 	CKD(cudaMalloc((void **)&fe->d_tapslice, sizeof(cf) * (size_t)C * M));
@@ -701,7 +704,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	if(!fe) return;
 	cudaSetDevice(fe->cfg.device);
-	cudaStream_t sts[5] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec, fe->st_stats };
+	cudaStream_t sts[6] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec, fe->st_stats, fe->st_h2d };
 	for(cudaStream_t q : sts) if(q) cudaStreamSynchronize(q);
 	cudaFree(fe->d_work); cudaFree(fe->d_spec); cudaFree(fe->d_mask); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
 	cudaFree(fe->d_bb); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
@@ -750,6 +753,7 @@ static int process_pending(hfdl_b200_frontend *fe, bool all) {
 		RawSource src;
 		src.base = fe->d_ring; src.ring_len = fe->ring_len; src.ring_origin = 0; src.block_stride = g.input_size; src.sfmt = fe->sfmt;
 		src.pos0 = fe->blocks_done * (long long)g.input_size - g.overlap_length;
+		if(fe->h2d_pending) { if(cudaStreamWaitEvent(fe->stream, fe->ev_h2d, 0) != cudaSuccess) return -1; fe->h2d_pending = false; }     // the samples of this batch have landed
 		if(run_batch(fe, src, nb)) return -1;
 		done += nb;
 	}
@@ -763,9 +767,10 @@ int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, in
 	const unsigned char *p = (const unsigned char *)samples;
 	int blocks = 0;
 	while(nsamples > 0) {
-		// oldest sample still needed: start of the overlap of the next unprocessed block
+		// oldest sample still needed: start of the overlap of the next unprocessed block.  One batch worth of ring below that
+		// is left alone: the channeliser stage of the newest queued batch may still be reading it
 		long long keep_from = fe->blocks_done * (long long)g.input_size - g.overlap_length;
-		long long space = fe->ring_len - (fe->fed - keep_from);
+		long long space = fe->ring_len - (long long)fe->Bmax * g.input_size - (fe->fed - keep_from);
 		if(space <= 0) {
 			int r = process_pending(fe, true);
 			if(r < 0) return -1;
@@ -775,11 +780,14 @@ int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, in
 		long long n = std::min<long long>(nsamples, space);
 		long long idx = fe->fed % fe->ring_len;
 		long long first = std::min(n, fe->ring_len - idx);
-		CK(cudaMemcpyAsync((unsigned char *)fe->d_ring + idx * fe->bps, p, (size_t)(first * fe->bps), cudaMemcpyHostToDevice, fe->stream));
+		// what this copy overwrites was read by batches up to the one before the newest: their channeliser stage must be done
+		if(fe->batch_seq >= 2) CK(cudaStreamWaitEvent(fe->st_h2d, fe->ev_front[(fe->batch_seq - 2) % HFDL_NSETS], 0));
+		CK(cudaMemcpyAsync((unsigned char *)fe->d_ring + idx * fe->bps, p, (size_t)(first * fe->bps), cudaMemcpyHostToDevice, fe->st_h2d));
 		if(n > first)
-			CK(cudaMemcpyAsync(fe->d_ring, p + first * fe->bps, (size_t)((n - first) * fe->bps), cudaMemcpyHostToDevice, fe->stream));
+			CK(cudaMemcpyAsync(fe->d_ring, p + first * fe->bps, (size_t)((n - first) * fe->bps), cudaMemcpyHostToDevice, fe->st_h2d));
 		fe->fed += n; p += n * fe->bps; nsamples -= n;
-		CK(cudaEventRecord(fe->ev_h2d, fe->stream));
+		CK(cudaEventRecord(fe->ev_h2d, fe->st_h2d));
+		fe->h2d_pending = true;
 		int r = process_pending(fe, false);
 		if(r < 0) return -1;
 		blocks += r;
@@ -812,7 +820,7 @@ int32_t hfdl_b200_push_peer(hfdl_b200_frontend_t *dst, hfdl_b200_frontend_t *src
 	while(dst->fed < src->fed) {
 		// same bookkeeping as hfdl_b200_push_samples, the source being the peer's ring
 		long long keep_from = dst->blocks_done * (long long)dst->g.input_size - dst->g.overlap_length;
-		long long space = dst->ring_len - (dst->fed - keep_from);
+		long long space = dst->ring_len - (long long)dst->Bmax * dst->g.input_size - (dst->fed - keep_from);
 		if(space <= 0) {
 			int r = process_pending(dst, true);
 			if(r < 0) return -1;
@@ -830,7 +838,7 @@ int32_t hfdl_b200_push_peer(hfdl_b200_frontend_t *dst, hfdl_b200_frontend_t *src
 		dst->fed += n;
 		CK(cudaEventRecord(dst->ev_h2d, dst->stream));
 		// the peer must not overwrite this part of its ring before the copy has read it
-		CK(cudaStreamWaitEvent(src->stream, dst->ev_h2d, 0));
+		CK(cudaStreamWaitEvent(src->st_h2d, dst->ev_h2d, 0));
 		int r = process_pending(dst, false);
 		if(r < 0) return -1;
 		blocks += r;

@@ -473,27 +473,32 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			// number of updates due is floor((clk_after + 1) / 256) - floor((clk_before + 1) / 256), almost always 0
 			const int d = k1 - k_prev;
 			const unsigned clk_after = S.nf_clk + (unsigned)d;
-			if(HFDL_UNLIKELY(((clk_after + 1u) >> 8) != ((S.nf_clk + 1u) >> 8))) {
-				unsigned j = (0xFFu - (S.nf_clk & 0xFFu)) & 0xFFu;
-				if(j == 0u) j = 256u;
-				for(; (int)j <= d; j += 256u)
-					S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[k_prev + (int)j]) + 1e-6f;
-			}
-			S.nf_clk = clk_after;
+			const bool nf_due = ((clk_after + 1u) >> 8) != ((S.nf_clk + 1u) >> 8);
 			bits_push(S.bits, bits ^ S.bitmask);
 			// |2*eq/127 - 1| > 0.36 in float arithmetic  <=>  eq <= 40 or eq >= 87 (all 128 values enumerated)
 			const int eq = bits_corr(A_bits, S.bits);
-			if(HFDL_UNLIKELY((unsigned)(eq - 41) > 45u)) {          // A1 found (hfdl.c:779-793)
-				S.st_a1++;
-				S.bitmask = eq >= 87 ? 0u : ~0u;
-				S.signal_level = lvl1;
-				S.frame_symbol_cnt = 1.0f;
-				S.symbols_wanted = HFDL_A_LEN;
-				S.search_retries = 0;
-				S.fr_state = HF_A2;
-				stop = true;
+			const bool hit = (unsigned)(eq - 41) > 45u;
+			const bool blow = fabsf(S.c_dphi) > 0.25f;
+			// one rarely taken branch for the three rare events (a lone warp pays ~20 cycles per branch it has to resolve)
+			if(HFDL_UNLIKELY(nf_due | hit | blow)) {
+				if(nf_due) {
+					unsigned j = (0xFFu - (S.nf_clk & 0xFFu)) & 0xFFu;
+					if(j == 0u) j = 256u;
+					for(; (int)j <= d; j += 256u)
+						S.noise_floor = 0.65f * S.noise_floor + 0.35f * fminf(S.noise_floor, lvl[k_prev + (int)j]) + 1e-6f;
+				}
+				if(hit) {                                     // A1 found (hfdl.c:779-793)
+					S.st_a1++;
+					S.bitmask = eq >= 87 ? 0u : ~0u;
+					S.signal_level = lvl1;
+					S.frame_symbol_cnt = 1.0f;
+					S.symbols_wanted = HFDL_A_LEN;
+					S.search_retries = 0;
+					S.fr_state = HF_A2;
+				}
+				stop = stop | hit | blow;                     // Costas blow-up: the generic path resets the loops
 			}
-			if(HFDL_UNLIKELY(fabsf(S.c_dphi) > 0.25f)) stop = true;      // Costas blow-up: the generic path resets the loops
+			S.nf_clk = clk_after;
 		}
 		if(MODE != RUN_A1) S.signal_level += lvl1;    // in-frame: the SUM of the AGC levels (the mean is taken at the frame end)
 		if(LMS) { HFDL_ORDER2(qa, S.signal_level); pl.x += qa; pl.y += qb; }
