@@ -95,7 +95,7 @@ def load(path=None):
     global _lib
     if path is None and _lib is not None:
         return _lib
-    p = path or LIB_PATH
+    p = path or os.environ.get("HFDL_B200_LIB") or LIB_PATH      # HFDL_B200_LIB: a variant build of the same CUDA library (kernel experiments)
     if not os.path.exists(p):
         raise RuntimeError("%s not found: run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback." % p)
     L = bind(C.CDLL(p))

@@ -84,7 +84,7 @@ struct FftEngine {
 		CK(cudaFuncSetAttribute(fft_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(chan_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 		CK(cudaFuncSetAttribute(fec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_FEC_SMEM));
-		CK(cudaFuncSetAttribute(loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_LK_SMEM));
+		CK(cudaFuncSetAttribute(loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
 		return 0;
 	}
 	void destroy() { if(d_tw) cudaFree(d_tw); d_tw = nullptr; }
@@ -108,6 +108,7 @@ struct hfdl_b200_frontend {
 	struct Flight { bool busy = false; } flight[HFDL_NSETS];
 	std::recursive_mutex mtx;       // every public entry point: the frontend may be driven and queried from different threads
 	bool peer_enabled = false, h2d_pending = false;
+	size_t loop_smem = HFDL_LK_SMEM;  // dynamic shared memory requested for loop_kernel (padding keeps other stages' CTAs off its SMs)
 	bool failed = false;            // a CUDA call failed mid-pipeline: every later call returns -1
 	int Bsub = 1;                   // blocks per FFT sub-batch (intermediate spectra stay in L2)
 	long long n_out_prev = 0;       // resampled samples of the previous batch (carry source)
@@ -434,14 +435,14 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 	if(n_out > 0) {
 		LoopArgs l;
 		l.bank = fe->d_bank[p]; l.bank_stride = fe->rs_stride; l.mfo = fe->d_mfo[p]; l.mfo_stride = fe->mfo_stride;
-		l.lvl = fe->d_lvl[p]; l.lvl_stride = fe->rs_stride; l.n_samples = n_out;
+		l.lvl = fe->d_lvl[p]; l.lvl_stride = fe->rs_stride; l.n_samples = n_out; l.n_channels = fe->C;
 		l.state = fe->d_state; l.tab = fe->d_tab; l.datasym = fe->d_datasym; l.nslots = fe->nslots;
 		l.frames = fe->d_frames[p]; l.nframes = fe->d_nframes[p]; l.max_frames = fe->max_frames;
 		l.cap_channel = fe->cfg.capture_channel; l.cap_eq = fe->d_cap_eq; l.cap_cnt = fe->d_cap_cnt; l.cap_max = fe->cfg.capture_max;
 		l.debug_mode = fe->debug_mode;
 		l.dbg_cycles = fe->d_dbg;
 		prof_begin2(fe, KC_LOOP, pr, stl);
-		HFDL_LAUNCH(loop_kernel, dim3((unsigned)fe->C), dim3(HFDL_LK_THREADS), HFDL_LK_SMEM, stl, l);
+		HFDL_LAUNCH(loop_kernel, dim3((unsigned)((fe->C + HFDL_LK_NCH - 1) / HFDL_LK_NCH)), dim3(HFDL_LK_THREADS), fe->loop_smem, stl, l);
 		prof_end2(fe, pr, stl);
 		fe->launches++;
 	}
@@ -572,6 +573,14 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 		fe->Bsub = (int)std::max<long long>(1, std::min<long long>(fe->Bmax, budget / ((long long)g.fft_size * 8)));
 	}
 	{ const char *dbg = getenv("HFDL_B200_DEBUG"); fe->debug_mode = dbg ? atoi(dbg) : 0; }
+	{
+		// loop_kernel's SMs: asking for more shared memory than the bank rings need keeps CTAs with a sizeable shared-memory
+		// footprint (FFT passes, chan_extract, fec) away from the latency-bound warps
+		const char *e = getenv("HFDL_B200_LOOP_SMEM_KB");
+		long kb = e ? atol(e) : 0;
+		if(kb > 216) kb = 216;
+		if((size_t)kb * 1024 > fe->loop_smem) fe->loop_smem = (size_t)kb * 1024;
+	}
 	if(cfg->capture_channel >= fe->C) fe->cfg.capture_channel = -1;
 	if(fe->cfg.capture_max < 0) fe->cfg.capture_max = 0;
 

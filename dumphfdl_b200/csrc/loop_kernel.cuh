@@ -23,20 +23,31 @@
 #pragma once
 #include "common.cuh"
 
-#define HFDL_LK_WARPS 3
-#define HFDL_LK_THREADS (32 * HFDL_LK_WARPS)
+#define HFDL_LK_WARPS 3                  // warps per channel: demodulator, timing, loader
+#ifndef HFDL_LK_NCH
+#define HFDL_LK_NCH 4                    // channels per CTA (see "channel packing" below)
+#endif
+#define HFDL_LK_CH_THREADS (32 * HFDL_LK_WARPS)
+#define HFDL_LK_THREADS (HFDL_LK_CH_THREADS * HFDL_LK_NCH)
 #define HFDL_LK_RING 64                  // output entries the timing warp may run ahead of the demodulator warp
-#define HFDL_LK_BR 256                   // bank ring, input samples (power of two)
+#ifndef HFDL_LK_BR
+#define HFDL_LK_BR 128                   // bank ring, input samples (power of two, >= 4 loader chunks)
+#endif
 #define HFDL_LK_CH 32                    // input samples per loader chunk
 #define HFDL_LK_INFLIGHT 3               // loader chunks in flight
-#define HFDL_LK_SMEM (HFDL_LK_BR * 32 * 8)   // dynamic shared memory: the bank ring
+#define HFDL_LK_SMEM (HFDL_LK_NCH * HFDL_LK_BR * 32 * 8)   // dynamic shared memory: one bank ring per channel
+// Channel packing: the sequential warps of a channel are latency-bound and leave their SM's issue slots almost empty, but
+// they are slowed by ~40 % when the schedulers they sit on also serve the FFT / filter-bank CTAs of the other pipeline
+// stages (loop_kernel alone: 1.25 ms per cfg-3 batch; beside the other stages, one channel per SM: 1.75 ms).  Four
+// channels per CTA put each kind of warp on its own scheduler (warp w: channel w / 3, role w % 3 -> scheduler w % 4), use
+// a quarter of the SMs, and fill those SMs' register file so that no FFT CTA can be co-resident there.
 #define HFDL_LK_MAXN (1 << 20)           // input samples per launch (tag layout)
 
 struct LoopArgs {
 	const cf *bank; long long bank_stride;
 	const cf *mfo; long long mfo_stride;
 	const float *lvl; long long lvl_stride;
-	int n_samples;
+	int n_samples, n_channels;
 	DemodState *state;
 	const DemodTables *tab;
 	cf *datasym; int nslots;   // [C][nslots][HFDL_DATA_SYMS_MAX]
@@ -188,18 +199,37 @@ __device__ __forceinline__ cf costas_rotate(DemodState &S, float re, float im) {
 #define HFDL_ORDER2(a, b) asm volatile("" : "+f"(a), "+f"(b))
 #endif
 
-// ---- shared memory of one channel CTA (file scope: every access is a direct shared-window address) ----------
-__shared__ float4 lk_ring[HFDL_LK_RING];        // output ring data: {sym.re, sym.im, AGC level, info}
-__shared__ __align__(8) unsigned lk_tags[HFDL_LK_RING];      // output ring validity tags (read as aligned pairs)
-__shared__ __align__(16) float lk_lvl[HFDL_LK_BR];            // AGC level ring (1/g after the sample's update)
-__shared__ cf lk_psk[4][8];
-__shared__ cf lk_train[16];
-__shared__ volatile int lk_loaded, lk_end_seq, lk_done;
-__shared__ __align__(8) hfdl_mbar_t lk_mbar[HFDL_LK_INFLIGHT];      // completion barriers of the loader's bulk copies
-__shared__ __align__(8) volatile int lk_tailv[2];      // {sequence number, input-sample index} the demodulator warp has passed
-#define lk_tail lk_tailv[0]
-#define lk_tail_k lk_tailv[1]
-__device__ __forceinline__ void lk_tail_publish(int seq, int k) {      // one 8-byte store on the hot path
+// ---- shared memory: one LkShared per channel of the CTA.  The names below resolve through the reference `sh` that every
+// function touching the rings takes (or declares) -------------------------------------------------------------------
+struct LkShared {
+	float4 ring[HFDL_LK_RING];                   // output ring data: {sym.re, sym.im, AGC level, info}
+	__align__(8) unsigned tags[HFDL_LK_RING];    // output ring validity tags (read as aligned pairs)
+	__align__(16) float lvl[HFDL_LK_BR];         // AGC level ring (1/g after the sample's update)
+	cf psk[4][8];
+	cf train[16];
+	volatile int loaded, end_seq, done;
+	__align__(8) hfdl_mbar_t mbar[HFDL_LK_INFLIGHT];      // completion barriers of the loader's bulk copies
+	__align__(8) volatile int tailv[2];          // {sequence number, input-sample index} the demodulator warp has passed
+	volatile int reset_gen, reset_k, reset_seq, ack_gen;
+};
+__shared__ __align__(16) LkShared lk_sh[HFDL_LK_NCH];
+#define lk_ring (sh.ring)
+#define lk_tags (sh.tags)
+#define lk_lvl (sh.lvl)
+#define lk_psk (sh.psk)
+#define lk_train (sh.train)
+#define lk_loaded (sh.loaded)
+#define lk_end_seq (sh.end_seq)
+#define lk_done (sh.done)
+#define lk_mbar (sh.mbar)
+#define lk_tailv (sh.tailv)
+#define lk_tail (sh.tailv[0])
+#define lk_tail_k (sh.tailv[1])
+#define lk_reset_gen (sh.reset_gen)
+#define lk_reset_k (sh.reset_k)
+#define lk_reset_seq (sh.reset_seq)
+#define lk_ack_gen (sh.ack_gen)
+__device__ __forceinline__ void lk_tail_publish(LkShared &sh, int seq, int k) {      // one 8-byte store on the hot path
 #ifdef HFDL_CUSIM
 	lk_tailv[0] = seq; lk_tailv[1] = k;
 #else
@@ -207,23 +237,22 @@ __device__ __forceinline__ void lk_tail_publish(int seq, int k) {      // one 8-
 	asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(sa), "r"(seq), "r"(k) : "memory");
 #endif
 }
-__shared__ volatile int lk_reset_gen, lk_reset_k, lk_reset_seq, lk_ack_gen;
 
 // Output-ring accessors; all accesses are volatile (the other warp changes the ring behind the compiler's back).
 #ifdef HFDL_CUSIM
-static inline void lk_ring_store(int i, float x, float y, float z, unsigned info, unsigned tag) {
+static inline void lk_ring_store(LkShared &sh, int i, float x, float y, float z, unsigned info, unsigned tag) {
 	volatile float *p = reinterpret_cast<volatile float *>(&lk_ring[i]);
 	p[0] = x; p[1] = y; p[2] = z; reinterpret_cast<volatile unsigned *>(p)[3] = info;
 	__atomic_thread_fence(__ATOMIC_RELEASE);
 	reinterpret_cast<volatile unsigned *>(lk_tags)[i] = tag;
 }
 // Host threads are not in lockstep, so the emulation reads through lane 0 and broadcasts (called by all 32 lanes).
-static inline unsigned lk_ring_tag(int i) {
+static inline unsigned lk_ring_tag(LkShared &sh, int i) {
 	unsigned t = reinterpret_cast<volatile unsigned *>(lk_tags)[i];
 	__atomic_thread_fence(__ATOMIC_ACQUIRE);
 	return __shfl_sync(0xffffffffu, t, 0);
 }
-static inline float4 lk_ring_load(int i, unsigned = 0u) {
+static inline float4 lk_ring_load(LkShared &sh, int i, unsigned = 0u) {
 	volatile float *p = reinterpret_cast<volatile float *>(&lk_ring[i]);
 	float4 r;
 	r.x = p[0]; r.y = p[1]; r.z = p[2]; r.w = p[3];
@@ -231,20 +260,20 @@ static inline float4 lk_ring_load(int i, unsigned = 0u) {
 	r.w = __shfl_sync(0xffffffffu, r.w, 0);
 	return r;
 }
-static inline void lk_pair_load(int seq, float4 &e0, float4 &e1, unsigned &t0, unsigned &t1) {
+static inline void lk_pair_load(LkShared &sh, int seq, float4 &e0, float4 &e1, unsigned &t0, unsigned &t1) {
 	const int i = seq & (HFDL_LK_RING - 1);
-	t0 = lk_ring_tag(i); t1 = lk_ring_tag(i + 1);
-	e0 = lk_ring_load(i); e1 = lk_ring_load(i + 1);
+	t0 = lk_ring_tag(sh, i); t1 = lk_ring_tag(sh, i + 1);
+	e0 = lk_ring_load(sh, i); e1 = lk_ring_load(sh, i + 1);
 }
 #else
-__device__ __forceinline__ void lk_ring_store(int i, float x, float y, float z, unsigned info, unsigned tag) {
+__device__ __forceinline__ void lk_ring_store(LkShared &sh, int i, float x, float y, float z, unsigned info, unsigned tag) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]);
 	const unsigned ta = (unsigned)__cvta_generic_to_shared(&lk_tags[i]);
 	asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "f"(x), "f"(y), "f"(z), "f"(__uint_as_float(info)) : "memory");
 	__threadfence_block();          // (measured: dropping the fence or using st.release.cta instead changes the kernel time by < 2 %)
 	asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ta), "r"(tag) : "memory");
 }
-__device__ __forceinline__ unsigned lk_ring_tag(int i) {
+__device__ __forceinline__ unsigned lk_ring_tag(LkShared &sh, int i) {
 	const unsigned ta = (unsigned)__cvta_generic_to_shared(&lk_tags[i]);
 	unsigned t;
 	asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(t) : "r"(ta) : "memory");
@@ -252,19 +281,19 @@ __device__ __forceinline__ unsigned lk_ring_tag(int i) {
 }
 // data of entry i; `dep` is a value that is 0 (bit 31 of a tag) but only known at run time: it makes the load
 // address -- and with it the load -- depend on the tag that was read before
-__device__ __forceinline__ float4 lk_ring_load(int i, unsigned dep = 0u) {
+__device__ __forceinline__ float4 lk_ring_load(LkShared &sh, int i, unsigned dep = 0u) {
 	const unsigned sa = (unsigned)__cvta_generic_to_shared(&lk_ring[i]) + (dep << 4);
 	float4 r;
 	asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(sa) : "memory");
 	return r;
 }
 // tags and data of the pair (seq, seq + 1), seq even: one 8-byte tag load, then the two data loads behind it
-__device__ __forceinline__ void lk_pair_load(int seq, float4 &e0, float4 &e1, unsigned &t0, unsigned &t1) {
+__device__ __forceinline__ void lk_pair_load(LkShared &sh, int seq, float4 &e0, float4 &e1, unsigned &t0, unsigned &t1) {
 	const int i = seq & (HFDL_LK_RING - 1);
 	const unsigned ta = (unsigned)__cvta_generic_to_shared(&lk_tags[i]);
 	asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(t0), "=r"(t1) : "r"(ta) : "memory");
-	e0 = lk_ring_load(i, t0 >> 31);
-	e1 = lk_ring_load(i + 1, t1 >> 31);
+	e0 = lk_ring_load(sh, i, t0 >> 31);
+	e1 = lk_ring_load(sh, i + 1, t1 >> 31);
 }
 #endif
 
@@ -276,13 +305,13 @@ __device__ __forceinline__ void lk_pair_load(int seq, float4 &e0, float4 &e1, un
 #else
 #define HFDL_WAIT_ATTR __noinline__
 #endif
-__device__ HFDL_WAIT_ATTR bool lk_wait_pair(int gen, int seq, long long *p_twait) {
+__device__ HFDL_WAIT_ATTR bool lk_wait_pair(LkShared &sh, int gen, int seq, long long *p_twait) {
 	bool ok = false;
 	const long long t0 = hfdl_clock();
 	for(;;) {
 		const int ack = HFDL_UNI(lk_ack_gen), end_seq = HFDL_UNI(lk_end_seq);
-		const unsigned t0w = (unsigned)HFDL_UNI(lk_ring_tag(seq & (HFDL_LK_RING - 1)));
-		const unsigned t1w = (unsigned)HFDL_UNI(lk_ring_tag((seq + 1) & (HFDL_LK_RING - 1)));
+		const unsigned t0w = (unsigned)HFDL_UNI(lk_ring_tag(sh, seq & (HFDL_LK_RING - 1)));
+		const unsigned t1w = (unsigned)HFDL_UNI(lk_ring_tag(sh, (seq + 1) & (HFDL_LK_RING - 1)));
 		if(lk_tag_ok(t0w, gen, seq) && lk_tag_ok(t1w, gen, seq + 1)) { ok = true; break; }
 		if(ack == gen && seq + 1 >= end_seq) break;
 		HFDL_SPIN_PAUSE();
@@ -301,7 +330,7 @@ __device__ HFDL_WAIT_ATTR bool lk_wait_pair(int gen, int seq, long long *p_twait
 enum { RUN_BITS = 0, RUN_TRAIN = 1, RUN_DATA = 2, RUN_SKIP = 3, RUN_A1 = 4 };
 
 template <int MODE, int ARITY>
-__device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k_prev, const int gen, const int nsym,
+__device__ __forceinline__ int demod_run(LkShared &sh, DemodState &S, EqL &E, int &seq, int &k_prev, const int gen, const int nsym,
 		cf *dsym, const int lane, unsigned &symcnt, long long *p_twait, const bool cap, cf *cap_eq, int &cap_n, const int cap_max,
 		const float *lvl, const unsigned *A_bits, float &last_lvl, unsigned &last_info) {
 	const int l16 = lane & 15;
@@ -334,7 +363,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 	const cf w11 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 11, 16), __shfl_sync(0xffffffffu, E.w.y, 11, 16));
 	const cf w12 = make_float2(__shfl_sync(0xffffffffu, E.w.x, 12, 16), __shfl_sync(0xffffffffu, E.w.y, 12, 16));
 	float4 e0, e1; unsigned t0, t1;
-	lk_pair_load(seq, e0, e1, t0, t1);
+	lk_pair_load(sh, seq, e0, e1, t0, t1);
 	// Validity of the two prefetched entries is a warp vote: the lanes are not guaranteed to be converged at the
 	// prefetch, so the decision must not depend on one lane's view (a lane that saw a not-yet-valid entry sends the
 	// whole warp through the reload).  seq is even here: seq and seq + 1 lie in the same lap of the ring.
@@ -343,8 +372,8 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 	for(;;) {
 		if(!HFDL_PAIR_VALID()) {
 			// both outputs of the symbol are not there yet: wait, or leave when the batch ends before them
-			if(!lk_wait_pair(gen, seq, p_twait)) break;
-			lk_pair_load(seq, e0, e1, t0, t1);
+			if(!lk_wait_pair(sh, gen, seq, p_twait)) break;
+			lk_pair_load(sh, seq, e0, e1, t0, t1);
 		}
 	  // hot loop: one symbol per iteration, left only at the end of the run or when the ring runs dry (the back edge is
 	  // its only taken branch)
@@ -424,7 +453,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			}
 			S.T_idx++;
 			// prefetch the next symbol's entries, pre-shift the window for it and reduce its 13 known taps
-			lk_pair_load(seq, e0, e1, t0, t1);
+			lk_pair_load(sh, seq, e0, e1, t0, t1);
 			drop0 = __shfl_sync(0xffffffffu, E.x2, 0, 16); drop1 = __shfl_sync(0xffffffffu, E.x2, 1, 16);
 			xs = make_float2(__shfl_down_sync(0xffffffffu, E.x.x, 2, 16), __shfl_down_sync(0xffffffffu, E.x.y, 2, 16));
 			x2s = __shfl_down_sync(0xffffffffu, E.x2, 2, 16);
@@ -437,13 +466,13 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 			P = make_float2((Qn.x + a.x) + b.x, (Qn.y + a.y) + b.y);
 			E.x.x = is13 ? r0.x : xs.x; E.x.y = is13 ? r0.y : xs.y;
 			E.x.x = is14 ? r1.x : E.x.x; E.x.y = is14 ? r1.y : E.x.y;
-			lk_pair_load(seq, e0, e1, t0, t1);
+			lk_pair_load(sh, seq, e0, e1, t0, t1);
 		}
 		// ---- slicer, Costas adjust
 		if(cap & (lane == 0) & (cap_n < cap_max)) cap_eq[cap_n] = s;
 		cap_n += cap ? 1 : 0;
 		cf x_hat;
-		unsigned bits = modem_demod(ARITY, s, lk_psk, &x_hat);
+		unsigned bits = modem_demod(ARITY, s, sh.psk, &x_hat);
 		float err = s.y * x_hat.x - s.x * x_hat.y;
 		err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));
 		S.c_phi += 0.1f * err;
@@ -503,7 +532,7 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 		if(MODE != RUN_A1) S.signal_level += lvl1;    // in-frame: the SUM of the AGC levels (the mean is taken at the frame end)
 		if(LMS) { HFDL_ORDER2(qa, S.signal_level); pl.x += qa; pl.y += qb; }
 		k_prev = k1;
-		if(lane == 0) lk_tail_publish(seq, k_prev);
+		if(lane == 0) lk_tail_publish(sh, seq, k_prev);
 		if(stop | !HFDL_PAIR_VALID()) break;
 	  }
 		if(stop) break;
@@ -530,12 +559,12 @@ __device__ __forceinline__ int demod_run(DemodState &S, EqL &E, int &seq, int &k
 
 // diagnostics wrapper (HFDL_B200_DEBUG): cycles and symbols per run mode, slots 12.. of the per-channel counters
 template <int MODE, int ARITY>
-__device__ __forceinline__ int demod_run_timed(long long *dbg, int c, DemodState &S, EqL &E, int &seq, int &k_prev, const int gen, const int nsym,
+__device__ __forceinline__ int demod_run_timed(LkShared &sh, long long *dbg, int c, DemodState &S, EqL &E, int &seq, int &k_prev, const int gen, const int nsym,
 		cf *dsym, const int lane, unsigned &symcnt, long long *p_twait, const bool cap, cf *cap_eq, int &cap_n, const int cap_max,
 		const float *lvl, const unsigned *A_bits, float &last_lvl, unsigned &last_info) {
-	if(!dbg) return demod_run<MODE, ARITY>(S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, p_twait, cap, cap_eq, cap_n, cap_max, lvl, A_bits, last_lvl, last_info);
+	if(!dbg) return demod_run<MODE, ARITY>(sh, S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, p_twait, cap, cap_eq, cap_n, cap_max, lvl, A_bits, last_lvl, last_info);
 	const long long t0 = hfdl_clock(), w0 = *p_twait;
-	const int did = demod_run<MODE, ARITY>(S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, p_twait, cap, cap_eq, cap_n, cap_max, lvl, A_bits, last_lvl, last_info);
+	const int did = demod_run<MODE, ARITY>(sh, S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, p_twait, cap, cap_eq, cap_n, cap_max, lvl, A_bits, last_lvl, last_info);
 	if(lane == 0) {
 		const int slot = 12 + 2 * (MODE == RUN_DATA ? 4 + ARITY : MODE);      // BITS 0, TRAIN 1, SKIP 3, A1 4, DATA arity 1..3 -> 5..7
 		dbg[c * 32 + slot] += (hfdl_clock() - t0) - (*p_twait - w0);
@@ -544,23 +573,29 @@ __device__ __forceinline__ int demod_run_timed(long long *dbg, int c, DemodState
 	return did;
 }
 
-// loop_kernel: grid = C, block = 96 threads (warp 0 demodulator, warp 1 timing, warp 2 loader), dynamic smem = bank ring.
+// loop_kernel: grid = ceil(C / HFDL_LK_NCH), block = HFDL_LK_NCH x 96 threads (per channel: warp 0 demodulator, warp 1 timing,
+// warp 2 loader), dynamic smem = one bank ring per channel.
 __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
-	HFDL_DYN_SMEM(cf, s_bank);                      // [HFDL_LK_BR][32]: arms 0..15 matched, 16..31 derivative
-	const int c = blockIdx.x;
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	HFDL_DYN_SMEM(cf, s_bank_all);                  // [HFDL_LK_NCH][HFDL_LK_BR][32]: arms 0..15 matched, 16..31 derivative
+	const int slot = threadIdx.x / HFDL_LK_CH_THREADS, tid = threadIdx.x - slot * HFDL_LK_CH_THREADS;
+	const int c = blockIdx.x * HFDL_LK_NCH + slot;
+	const bool live = c < a.n_channels;
+	const int lane = tid & 31, warp = tid >> 5;
+	LkShared &sh = lk_sh[slot];
+	cf *s_bank = s_bank_all + slot * (HFDL_LK_BR * 32);
 	const DemodTables &T = *a.tab;
-	const float *lvl = a.lvl + (long long)c * a.lvl_stride;
+	const float *lvl = a.lvl + (long long)(live ? c : 0) * a.lvl_stride;
 	const int N = a.n_samples;
-	if(threadIdx.x < HFDL_LK_RING) { lk_ring[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f); lk_tags[threadIdx.x] = HFDL_LK_TAG_INVALID; }
-	if(threadIdx.x < 32) lk_psk[threadIdx.x >> 3][threadIdx.x & 7] = T.psk[threadIdx.x >> 3][threadIdx.x & 7];
-	if(threadIdx.x == 0) {
+	if(tid < HFDL_LK_RING) { lk_ring[tid] = make_float4(0.f, 0.f, 0.f, 0.f); lk_tags[tid] = HFDL_LK_TAG_INVALID; }
+	if(tid < 32) lk_psk[tid >> 3][tid & 7] = T.psk[tid >> 3][tid & 7];
+	if(tid == 0) {
 		for(int i = 0; i < HFDL_LK_INFLIGHT; i++) hfdl_mbar_init(&lk_mbar[i], 1);
 		hfdl_fence_mbar_init();
-		lk_loaded = 0; lk_tail = (int)(a.state[c].symsync_out_idx & 1u); lk_tail_k = -1; lk_end_seq = 0x7fffffff; lk_done = 0;
+		lk_loaded = 0; lk_tail = live ? (int)(a.state[c].symsync_out_idx & 1u) : 0; lk_tail_k = -1; lk_end_seq = 0x7fffffff; lk_done = 0;
 		lk_reset_gen = 0; lk_reset_k = 0; lk_reset_seq = 0; lk_ack_gen = 0;
 	}
 	__syncthreads();
+	if(!live) return;                               // the last CTA of a channel count that is not a multiple of HFDL_LK_NCH
 
 	if(warp == 2) {
 		// =========================== loader warp ===========================
@@ -568,33 +603,42 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		// levels, issued by lane 0, HFDL_LK_INFLIGHT chunks in flight, each completing on its own mbarrier.
 		const cf *bank = a.bank + (long long)c * a.bank_stride * 32;
 		const int nchunks = (N + HFDL_LK_CH - 1) / HFDL_LK_CH;
+		// Issue and completion are polled independently: a chunk waiting for ring space must not hold back the
+		// publication of the chunks that are already in flight (the demodulator warp only advances -- and frees ring
+		// space -- when the timing warp sees those samples).
 		if(lane == 0) {
-			for(int ch = 0; ch < nchunks + HFDL_LK_INFLIGHT - 1; ch++) {
-				if(ch < nchunks) {
-					const int n0 = ch * HFDL_LK_CH;
+			int issued = 0, completed = 0;
+			while(completed < nchunks) {
+				bool progress = false;
+				if(issued < nchunks && issued - completed < HFDL_LK_INFLIGHT) {
+					const int n0 = issued * HFDL_LK_CH;
 					// ring space: samples the demodulator warp has not passed yet must stay (the timing warp may be rolled back to them)
-					while(n0 + HFDL_LK_CH > lk_tail_k + 1 + HFDL_LK_BR - HFDL_LK_CH) {
-						if(lk_done) break;
-						HFDL_SPIN_PAUSE();
+					if(n0 + HFDL_LK_CH <= lk_tail_k + 1 + HFDL_LK_BR - HFDL_LK_CH) {
+						__threadfence_block();
+						hfdl_fence_proxy_async();                  // the consumers' reads of this ring slot come before the copy's writes
+						const int cnt = (N - n0 < HFDL_LK_CH) ? (N - n0) : HFDL_LK_CH;
+						const unsigned bank_bytes = (unsigned)cnt * 256u, lvl_bytes = (unsigned)((cnt + 3) & ~3) * 4u;
+						hfdl_mbar_t *mb = &lk_mbar[issued % HFDL_LK_INFLIGHT];      // chunk issued-INFLIGHT has completed: the barrier is free
+						hfdl_mbar_expect_tx(mb, bank_bytes + lvl_bytes);
+						hfdl_bulk_g2s(s_bank + (n0 & (HFDL_LK_BR - 1)) * 32, bank + (long long)n0 * 32, bank_bytes, mb);
+						hfdl_bulk_g2s(&lk_lvl[n0 & (HFDL_LK_BR - 1)], &lvl[n0], lvl_bytes, mb);
+						hfdl_mbar_arrive_emul(mb);
+						issued++; progress = true;
 					}
-					__threadfence_block();
-					hfdl_fence_proxy_async();                  // the consumers' reads of this ring slot come before the copy's writes
-					const int cnt = (N - n0 < HFDL_LK_CH) ? (N - n0) : HFDL_LK_CH;
-					const unsigned bank_bytes = (unsigned)cnt * 256u, lvl_bytes = (unsigned)((cnt + 3) & ~3) * 4u;
-					hfdl_mbar_t *mb = &lk_mbar[ch % HFDL_LK_INFLIGHT];
-					hfdl_mbar_expect_tx(mb, bank_bytes + lvl_bytes);
-					hfdl_bulk_g2s(s_bank + (n0 & (HFDL_LK_BR - 1)) * 32, bank + (long long)n0 * 32, bank_bytes, mb);
-					hfdl_bulk_g2s(&lk_lvl[n0 & (HFDL_LK_BR - 1)], &lvl[n0], lvl_bytes, mb);
-					hfdl_mbar_arrive_emul(mb);
 				}
-				if(ch >= HFDL_LK_INFLIGHT - 1) {             // chunk ch-(INFLIGHT-1) has to land before its barrier is armed again
-					const int done_ch = ch - (HFDL_LK_INFLIGHT - 1);
-					hfdl_mbar_t *mb = &lk_mbar[done_ch % HFDL_LK_INFLIGHT];
-					const unsigned parity = (unsigned)(done_ch / HFDL_LK_INFLIGHT) & 1u;
-					while(!hfdl_mbar_try_wait(mb, parity)) { }
-					__threadfence_block();
-					const int ready = (done_ch + 1) * HFDL_LK_CH;
-					lk_loaded = ready < N ? ready : N;
+				if(completed < issued) {
+					hfdl_mbar_t *mb = &lk_mbar[completed % HFDL_LK_INFLIGHT];
+					const unsigned parity = (unsigned)(completed / HFDL_LK_INFLIGHT) & 1u;
+					if(hfdl_mbar_try_wait(mb, parity)) {
+						__threadfence_block();
+						const int ready = (completed + 1) * HFDL_LK_CH;
+						lk_loaded = ready < N ? ready : N;
+						completed++; progress = true;
+					}
+				}
+				if(!progress) {
+					if(lk_done) break;
+					HFDL_SPIN_PAUSE();
 				}
 			}
 		}
@@ -684,7 +728,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 						const float level = lk_lvl[k & (HFDL_LK_BR - 1)];
 						tau += S.ss_del;
 						const int bi = hfdl_round_pos(tau * (float)HFDL_SS_NPFB);
-						lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_info(bi < HFDL_SS_NPFB, k), lk_tag_hi(my_gen, seq));
+						lk_ring_store(sh, seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_info(bi < HFDL_SS_NPFB, k), lk_tag_hi(my_gen, seq));
 						if(HFDL_UNLIKELY(bi < HFDL_SS_NPFB)) { seq++; odd = 1; b = bi; rare = 1; break; }     // del < 1: another output of the same sample
 						const int m = bi >> 4;
 						k += m; tau -= (float)m; b = bi & 15;
@@ -697,7 +741,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 						HFDL_SS_TED(mf, row, b);
 						tau += S.ss_del;
 						const int bi = hfdl_round_pos(tau * (float)HFDL_SS_NPFB);
-						lk_ring_store((seq + 1) & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_info(bi < HFDL_SS_NPFB, k), lk_tag_hi(my_gen, seq + 1));
+						lk_ring_store(sh, (seq + 1) & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, level, lk_info(bi < HFDL_SS_NPFB, k), lk_tag_hi(my_gen, seq + 1));
 						seq += 2;
 						if(HFDL_UNLIKELY(bi < HFDL_SS_NPFB)) { b = bi; rare = 1; break; }
 						const int m = bi >> 4;
@@ -732,7 +776,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				S.ss_decim_counter++;
 				S.ss_tau += S.ss_del;
 				S.ss_b = hfdl_round_pos(S.ss_tau * (float)HFDL_SS_NPFB);
-				if(lane == 0) lk_ring_store(seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, lk_lvl[kn & (HFDL_LK_BR - 1)], lk_info(S.ss_b < HFDL_SS_NPFB, kn), lk_tag_hi(my_gen, seq));
+				if(lane == 0) lk_ring_store(sh, seq & (HFDL_LK_RING - 1), mf.x * 0.33333334f, mf.y * 0.33333334f, lk_lvl[kn & (HFDL_LK_BR - 1)], lk_info(S.ss_b < HFDL_SS_NPFB, kn), lk_tag_hi(my_gen, seq));
 				seq++; n_gen_out++;
 			} else {
 				S.ss_tau -= 1.0f; S.ss_b -= HFDL_SS_NPFB;                   // ... then tau -= 1, b -= npfb
@@ -901,7 +945,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		};
 		for(;;) {
 			// fast path: a run of whole symbols up to AND including the symbol of the next framer event
-#define HFDL_RUN(MODE, AR) demod_run_timed<MODE, AR>(a.dbg_cycles, c, S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, &t_wait, cap, a.cap_eq, cap_n_eq, a.cap_max, lvl, A_bits, last_lvl, last_info)
+#define HFDL_RUN(MODE, AR) demod_run_timed<MODE, AR>(sh, a.dbg_cycles, c, S, E, seq, k_prev, gen, nsym, dsym, lane, symcnt, &t_wait, cap, a.cap_eq, cap_n_eq, a.cap_max, lvl, A_bits, last_lvl, last_info)
 			if(S.fr_state == HF_A1 && !(S.symsync_out_idx & 1u) && !reset_pending && a.debug_mode < 2
 					&& fabsf(S.c_dphi) <= 0.25f && symcnt + 1u < 13u * HFDL_SINGLE_SLOT_FRAME_LEN) {
 				const int nsym = (int)(13u * HFDL_SINGLE_SLOT_FRAME_LEN - 1u - symcnt);     // the symbol of the 13-frame timeout goes the generic way
@@ -934,13 +978,13 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			unsigned tagw;
 			bool have = false;
 			for(;;) {
-				tagw = (unsigned)HFDL_UNI(lk_ring_tag(seq & (HFDL_LK_RING - 1)));
+				tagw = (unsigned)HFDL_UNI(lk_ring_tag(sh, seq & (HFDL_LK_RING - 1)));
 				if(lk_tag_ok(tagw, gen, seq)) { have = true; break; }
 				if(HFDL_UNI(lk_ack_gen) == gen && seq >= HFDL_UNI(lk_end_seq)) break;
 				const long long t0 = hfdl_clock(); HFDL_SPIN_PAUSE(); t_wait += hfdl_clock() - t0;
 			}
 			if(!have) break;                                          // end of batch: every output consumed
-			const float4 ent = lk_ring_load(seq & (HFDL_LK_RING - 1), tagw >> 31);
+			const float4 ent = lk_ring_load(sh, seq & (HFDL_LK_RING - 1), tagw >> 31);
 			tagw = __float_as_uint(ent.w);
 			const int k = (int)(tagw & 0xFFFFFu);
 			const bool more = (tagw >> 20) & 1u;
@@ -972,7 +1016,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				}
 				if(HFDL_UNLIKELY(cap)) { if(lane == 0 && cap_n_eq < a.cap_max) a.cap_eq[cap_n_eq] = s; cap_n_eq++; }
 				cf x_hat;
-				unsigned bits = modem_demod(S.cur_arity, s, lk_psk, &x_hat);
+				unsigned bits = modem_demod(S.cur_arity, s, sh.psk, &x_hat);
 				// ---- costas adjust with the modem's phase error Im(r*conj(x_hat)) (hfdl.c:738,276-281)
 				float err = s.y * x_hat.x - s.x * x_hat.y;
 				err = 0.5f * (fabsf(err + 1.0f) - fabsf(err - 1.0f));     // branchless_limit, hfdl.c:269-274
