@@ -43,12 +43,16 @@ ESN0_DB = 20.0
 METRIC = "I/Q Msamples/s & CRC-good PDUs/s at 1/2/4/8 B200 vs fftw CPU ref"
 # blocks_per_slot * input_size / sample_rate >= one 2.344 s single-slot frame; seed = 635000 + cfg index;
 # loops = passes over the slab per step (so that K = 20 steps time more than a second of device work)
+# sfmt: BASELINE names CF32 for cfg2 only.  The wideband configurations take CS16, the native format of the SDRs that deliver
+# 20-60 Msps and the one dumphfdl's own SoapySDR input asks for first ("native sample format ... to avoid extra
+# conversion", input-soapysdr.c:52-61); --sample-format overrides.
 WORKLOADS = {
-    "cfg2": dict(sr=2000000, nch=8, blocks_per_slot=22, slots=4, seed=635002, loops=16, group=0),
-    "cfg3": dict(sr=20000000, nch=128, blocks_per_slot=14, slots=1, seed=635003, loops=32, group=0),
-    "cfg4": dict(sr=30000000, nch=256, blocks_per_slot=21, slots=1, seed=635004, loops=16, group=64),
-    "cfg5": dict(sr=60000000, nch=512, blocks_per_slot=21, slots=1, seed=635005, loops=16, group=64),
+    "cfg2": dict(sr=2000000, nch=8, blocks_per_slot=22, slots=4, seed=635002, loops=16, group=0, sfmt="cf32"),
+    "cfg3": dict(sr=20000000, nch=128, blocks_per_slot=14, slots=1, seed=635003, loops=32, group=0, sfmt="cs16"),
+    "cfg4": dict(sr=30000000, nch=256, blocks_per_slot=21, slots=1, seed=635004, loops=16, group=64, sfmt="cs16"),
+    "cfg5": dict(sr=60000000, nch=512, blocks_per_slot=21, slots=1, seed=635005, loops=16, group=64, sfmt="cs16"),
 }
+SFMT = {"cf32": dict(code=3, bps=8, np=np.float32, name="CF32"), "cs16": dict(code=2, bps=4, np=np.int16, name="CS16")}
 DEFAULT_BY_GPUS = {1: "cfg3", 2: "cfg3", 4: "cfg4", 8: "cfg5"}
 
 
@@ -109,6 +113,29 @@ def render_range(O, W, P, first, count, nthreads, noise_seed):
     sig = O.noise_sigma(P["amp"], sr, ESN0_DB)
     O.lib().orc_tx_add_noise(x, x.size, sig, noise_seed, nthreads)
     return x
+
+
+def to_raw(O, W, x):
+    """complex64 samples -> the workload's sample format (flat array of I/Q values)"""
+    if W["sfmt"] == "cf32":
+        return np.ascontiguousarray(x).view(np.float32)
+    raw = np.zeros(2 * x.size, np.int16)
+    O.lib().orc_quantize_cs16(np.ascontiguousarray(x), x.size, raw)
+    return raw
+
+
+def prepare_workload(name, a, world):
+    """The workload both arms run: BASELINE's configuration for the GPU count, the sample format, and -- when the
+    spectrum is sharded over `world` GPUs -- a slab whose block count divides by `world`."""
+    W = dict(WORKLOADS[name])
+    if a.loops > 0:
+        W["loops"] = a.loops
+    if a.sample_format:
+        W["sfmt"] = a.sample_format
+    W["multi"] = a.multi if world > 1 else "single"
+    if world > 1 and a.multi == "sharded":
+        W["blocks_per_slot"] = -(-W["blocks_per_slot"] // world) * world
+    return W
 
 
 class ClockSampler:
@@ -186,13 +213,18 @@ class ClockSampler:
 
 def config_of(name, W, P, world):
     """Identical for both arms: names the workload only (arm-specific step sizes are reported under "step")."""
-    if world > 1:
+    if world > 1 and W["multi"] == "sharded":
+        shard = ("%d GPUs, one capture: every GPU transforms 1/%d of each batch's overlap-save blocks for all channels (its share of the capture "
+                 "comes over its own PCIe link), the channels' pass-band spectrum slices change hands in an NCCL all-to-all over NVLink, channel k is "
+                 "demodulated on GPU k mod %d (%d channels per GPU)" % (world, world, world, W["nch"] // world))
+    elif world > 1:
         shard = "%d GPUs: one capture, channel k on GPU k mod %d (%d channels per GPU); value: NCCL broadcast from rank 0 every pass; e2e: host scatter (1/%d of every pass per PCIe link) + NCCL all-gather" % (world, world, W["nch"] // world, world)
     else:
         shard = "1 GPU: all %d channels" % W["nch"]
-    return {"workload": "%s: %.0f Msps CF32, %d HFDL channels, synthetic looped slab of %d overlap-save blocks (%.1f Msamples, %.0f MB > 126 MB L2, no explicit flush), "
-                        "Es/N0 %.0f dB, seed %d" % (name, W["sr"] / 1e6, W["nch"], P["nblocks"], P["nsamp"] / 1e6, P["nsamp"] * 8 / 1e6, ESN0_DB, W["seed"]),
-            "sample_rate": W["sr"], "channels": W["nch"], "blocks_per_slab": P["nblocks"], "esn0_db": ESN0_DB, "sharding": shard}
+    F = SFMT[W["sfmt"]]
+    return {"workload": "%s: %.0f Msps %s, %d HFDL channels, synthetic looped slab of %d overlap-save blocks (%.1f Msamples, %.0f MB > 126 MB L2, no explicit flush), "
+                        "Es/N0 %.0f dB, seed %d" % (name, W["sr"] / 1e6, F["name"], W["nch"], P["nblocks"], P["nsamp"] / 1e6, P["nsamp"] * F["bps"] / 1e6, ESN0_DB, W["seed"]),
+            "sample_rate": W["sr"], "sample_format": F["name"], "channels": W["nch"], "blocks_per_slab": P["nblocks"], "esn0_db": ESN0_DB, "sharding": shard}
 
 
 # ---------------------------------------------------------------------------------------------- CPU reference arm
@@ -202,7 +234,7 @@ def cpu_reference_setup(O, W, P):
     if fast is not None:
         kind = "reference"
         fft_threads = max(1, min(cores, 8))          # --fft-threads (main.c:438, fft.h:15 default 4); the channel threads are one per channel
-        p = O.RefPipeline(W["sr"], CF, P["freqs"], fft_threads=fft_threads, fast=True)
+        p = O.RefPipeline(W["sr"], CF, P["freqs"], sfmt=SFMT[W["sfmt"]]["code"], fft_threads=fft_threads, fast=True)
         backend = {0: "oracle FFT (persistent pool) as the fftw3f stand-in", 1: "fftw3f", 3: "fftw3f + fftw3f_threads"}[fast.ref_fft_backend()]
         desc = ("the reference's own block.c + fft.c + fastddc.c (all-bin fold) + hfdl.c + libfec/viterbi27_port.c compiled where they lie "
                 "(oracle/_ref/libref_fast.so, -O3 -ffast-math), wired as main.c does: 1 fft thread with %d FFT workers + %d channel threads on a %d-core host; "
@@ -212,7 +244,7 @@ def cpu_reference_setup(O, W, P):
     nt = min(cores, 32)
     p = O.Pipeline(W["sr"], CF, P["freqs"], fold_mode=O.FOLD_FULL, nthreads=nt, fast=True)
     desc = "restated CPU reference (oracle/liboracle_fast.so, -O3 -ffast-math, all-bin fold, %d threads on a %d-core host): oracle/_ref not built" % (nt, cores)
-    return dict(kind="port", p=p, cores=nt, desc=desc, feed=lambda seg: p.feed(seg), close=p.close, good=lambda: sum(1 for q in p.pdus() if q.crc_good))
+    return dict(kind="port", p=p, cores=nt, desc=desc, feed=lambda seg: p.feed(seg, SFMT[W["sfmt"]]["code"]), close=p.close, good=lambda: sum(1 for q in p.pdus() if q.crc_good))
 
 
 def fft_share(O, W, isz, per_block_s):
@@ -237,16 +269,17 @@ def cpu_reference(O, W, P, isz, x0, target_s=12.0):
     """cpu_baseline of the N = 1 line: a bounded sample (~target_s of CPU work) of the same workload: the looped slab
     (x0 = the whole slab) fed block by block, cyclically, the way the GPU arm loops over it."""
     R = cpu_reference_setup(O, W, P)
-    navail = x0.size // isz
-    R["feed"](x0[: isz])                     # warm up: page in, first block
+    v = 2 * isz                              # x0: the slab in the workload's sample format, two values per sample
+    navail = x0.size // v
+    R["feed"](x0[: v])                       # warm up: page in, first block
     t0 = time.perf_counter()
-    R["feed"](x0[isz: 2 * isz])
+    R["feed"](x0[v: 2 * v])
     per_block = time.perf_counter() - t0
     nb = int(max(2, min(20 * navail, target_s / max(per_block, 1e-6))))
     t0 = time.perf_counter()
     for i in range(nb):
         b = (2 + i) % navail
-        R["feed"](x0[b * isz:(b + 1) * isz])
+        R["feed"](x0[b * v:(b + 1) * v])
     dt = time.perf_counter() - t0
     share = fft_share(O, W, isz, dt / nb)
     good = R["good"]()
@@ -264,21 +297,22 @@ def run_reference_arm(a, O, name, W, world):
     R = cpu_reference_setup(O, W, P)
     # size a step: one warm-up block timed, then ~1.5 s of CPU work per step, at most the slab
     nb_total_max = P["nblocks"]
-    x = render_range(O, W, P, 0, min(nb_total_max, 3) * isz, ncpu, W["seed"])
-    R["feed"](x[: isz])
+    x = to_raw(O, W, render_range(O, W, P, 0, min(nb_total_max, 3) * isz, ncpu, W["seed"]))
+    v = 2 * isz
+    R["feed"](x[: v])
     t0 = time.perf_counter()
-    R["feed"](x[isz: 2 * isz])
+    R["feed"](x[v: 2 * v])
     per_block = time.perf_counter() - t0
     per = int(max(1, min(8, 1.5 / max(per_block, 1e-6))))
     need = (a.warmup + a.steps) * per
     have = min(need + 2, nb_total_max)
-    if have * isz > x.size:
-        x = np.concatenate([x, render_range(O, W, P, x.size, have * isz - x.size, ncpu, W["seed"] + 1)])
+    if have * v > x.size:
+        x = np.concatenate([x, to_raw(O, W, render_range(O, W, P, x.size // 2, have * isz - x.size // 2, ncpu, W["seed"] + 1))])
     pos = 2
     vals = []
     for s in range(a.warmup + a.steps):
         idx = [(pos + i) % have for i in range(per)]
-        seg = np.concatenate([x[i * isz:(i + 1) * isz] for i in idx])
+        seg = np.concatenate([x[i * v:(i + 1) * v] for i in idx])
         t0 = time.perf_counter()
         R["feed"](seg)
         dt = time.perf_counter() - t0
@@ -286,15 +320,15 @@ def run_reference_arm(a, O, name, W, world):
         if s >= a.warmup:
             vals.append(dt)
     tot = sum(vals)
-    v = a.steps * per * isz / tot / 1e6
+    val = a.steps * per * isz / tot / 1e6
     good = R["good"]()
     R["close"]()
-    line = {"metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+    line = {"metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * tot / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference", "config": config_of(name, W, P, world),
             "step": "%d consecutive overlap-save blocks (%.2f Msamples) of the slab per step (bounded sample of the workload)" % (per, per * isz / 1e6),
-            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": R["cores"], "kind": R["kind"], "sample": R["desc"]},
-            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": R["cores"], "kind": R["kind"], "sample": R["desc"]},
+            "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "pdus_crc_good": good}
     print(json.dumps(line))
 
@@ -308,6 +342,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--sample-format", default=None, choices=sorted(SFMT))
+    ap.add_argument("--multi", default="sharded", choices=["sharded", "broadcast"],
+                    help="N > 1: 'sharded' = every GPU transforms 1/N of the blocks, spectrum slices all-to-all; 'broadcast' = every GPU transforms the whole capture")
     ap.add_argument("--loops", type=int, default=0, help="passes over the slab per step (0 = the workload's default)")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: time the device-resident leg alone")
     a = ap.parse_args()
@@ -315,9 +352,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     name = a.workload or DEFAULT_BY_GPUS.get(max(world, a.gpus), "cfg3")
-    W = dict(WORKLOADS[name])
-    if a.loops > 0:
-        W["loops"] = a.loops
+    W = prepare_workload(name, a, max(world, a.gpus))
     if a.warmup < 3:
         a.warmup = 3                                   # timing rule: at least three warm-up steps
     import orclib as O
@@ -334,29 +369,48 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sharded = world > 1 and W["multi"] == "sharded"
+    F = SFMT[W["sfmt"]]
+    bps = F["bps"]
     ncpu = max(1, (os.cpu_count() or 1) // max(world, 1))
-    isz = O.geometry(W["sr"])[2].input_size
+    g0 = O.geometry(W["sr"])[2]
+    isz, ovl = g0.input_size, g0.overlap_length
     P = plan_frames(O, W, isz)
     nsamp, nblocks, loops = P["nsamp"], P["nblocks"], W["loops"]
     assert nsamp % world == 0
     part = nsamp // world
     # every rank renders its own 1/N of the slab (time slice); the whole slab is assembled over NCCL where needed
-    x_part = render_range(O, W, P, rank * part, part, ncpu, W["seed"] + 7919 * rank)
+    x_part = to_raw(O, W, render_range(O, W, P, rank * part, part, ncpu, W["seed"] + 7919 * rank))       # flat I/Q values
     my_idx = list(range(rank, W["nch"], world))
     freqs = [P["freqs"][i] for i in my_idx]
     truth_set = set(t for t in P["truth"] if t[0] in set(freqs))
     ntruth = len(truth_set)
-    h_part = torch.from_numpy(x_part.view(np.float32)).pin_memory()
+    h_part = torch.from_numpy(x_part.view(np.uint8)).pin_memory()      # raw bytes from here on (NCCL has no int16)
     d_part = torch.empty_like(h_part, device="cuda")
     d_part.copy_(h_part)
     nbuf = 3 if world > 1 else 1
-    bufs = [torch.empty(2 * nsamp, dtype=torch.float32, device="cuda") for _ in range(nbuf)]
-    if world > 1:
-        dist.all_gather_into_tensor(bufs[0], d_part)
-        d_slab = bufs[0].clone() if rank == 0 else None
+    if sharded:
+        # setup (untimed): the slab is assembled once so that every rank can cut out its share of each batch -- the blocks
+        # [rank * bl, (rank + 1) * bl) plus the overlap in front of them (cyclic: the slab loops)
+        bl = nblocks // world
+        full = torch.empty(nsamp * bps, dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(full, d_part)
+        lo = bps * (rank * bl * isz - ovl)
+        d_share = (torch.cat([full[lo:], full[: bps * bl * isz]]) if lo < 0 else full[lo: bps * (rank + 1) * bl * isz]).clone()
+        del full
+        h_share = torch.empty_like(d_share, device="cpu").pin_memory()
+        h_share.copy_(d_share)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        bufs, d_slab = [], None
     else:
-        bufs[0].copy_(d_part)
-        d_slab = bufs[0]
+        bufs = [torch.empty(nsamp * bps, dtype=torch.uint8, device="cuda") for _ in range(nbuf)]
+        if world > 1:
+            dist.all_gather_into_tensor(bufs[0], d_part)
+            d_slab = bufs[0].clone() if rank == 0 else None
+        else:
+            bufs[0].copy_(d_part)
+            d_slab = bufs[0]
     torch.cuda.synchronize()
 
     def barrier():
@@ -370,11 +424,54 @@ def main():
         exact = sum(1 for q in pdus if (q.freq, q.data()) in truth_set)
         return good, exact
 
-    # ---- value: capture resident in HBM (rank 0's HBM when N > 1)
-    fe = hb.Frontend(W["sr"], CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
+    def make_frontend():
+        fe_ = hb.Frontend(W["sr"], CF, freqs, sample_format=F["code"], device=local, max_blocks_per_batch=nblocks)
+        if sharded:
+            fe_.set_exchange(P["freqs"], world)
+        return fe_
+
+    class Exchange:
+        """Sharded spectrum, host side of one rank: FFT of this rank's blocks -> all-to-all of the slices -> this rank's
+        channels.  FFT + pack run on the main torch stream, the all-to-all and the hand-over to the demodulator on a side
+        stream, so the FFT of pass i + 1 runs beside the exchange of pass i."""
+
+        def __init__(self, fe_):
+            self.fe = fe_
+            n = world * bl * (W["nch"] // world) * int(fe_.L.hfdl_b200_slice_elems(fe_.h)) * 2
+            self.send = [torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(2)]
+            self.recv = [torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(nbuf)]
+            self.fs = torch.cuda.Stream()            # FFT + pack (a real stream: handle 0 would mean "the frontend's own stream" to the C ABI)
+            self.xs = torch.cuda.Stream()            # all-to-all + hand-over
+            self.ev_fft = [torch.cuda.Event() for _ in range(2)]
+            self.ev_sent = [torch.cuda.Event() for _ in range(2)]
+            self.i = 0
+
+        def run(self, d_in, ready=None):
+            i = self.i
+            if ready is not None:
+                self.fs.wait_event(ready)                           # the samples of this pass have landed
+            if i >= 2:
+                self.fs.wait_event(self.ev_sent[i % 2])             # the all-to-all of pass i-2 has read this send buffer
+            self.fe.spectrum_slices(d_in.data_ptr(), i * nblocks + rank * bl, bl, self.send[i % 2].data_ptr(), self.fs.cuda_stream)
+            self.ev_fft[i % 2].record(self.fs)
+            self.fe.wait_input(nbuf - 1)                            # the batch that read this receive buffer is through the channeliser
+            with torch.cuda.stream(self.xs):
+                self.xs.wait_event(self.ev_fft[i % 2])
+                dist.all_to_all_single(self.recv[i % nbuf], self.send[i % 2])     # NCCL over NVLink, equal splits: part q -> rank q
+                self.ev_sent[i % 2].record(self.xs)
+                self.fe.process_slices(self.recv[i % nbuf].data_ptr(), nblocks, self.xs.cuda_stream)
+            self.i += 1
+            return self.ev_fft[i % 2]
+
+    # ---- value: capture resident in HBM (sharded: every rank's share in its own HBM; broadcast: in rank 0's HBM)
+    fe = make_frontend()
     state = {"pos": 0, "i": 0}
+    xch = Exchange(fe) if sharded else None
 
     def pass_device():
+        if sharded:
+            xch.run(d_share)
+            return
         if world > 1:
             buf = bufs[state["i"] % nbuf]
             fe.wait_input(nbuf - 1)                     # the batch that read this buffer nbuf passes ago is through the channeliser stage
@@ -391,6 +488,7 @@ def main():
     for _ in range(a.warmup):
         for _ in range(loops):
             pass_device()
+    torch.cuda.synchronize()
     fe.sync()
     fe.pdus()
     clk = ClockSampler(local)
@@ -402,6 +500,7 @@ def main():
     for _ in range(a.steps):
         for _ in range(loops):
             pass_device()
+    torch.cuda.synchronize()
     ms_dev = fe.timer_stop()
     barrier()
     wall = time.perf_counter() - t0
@@ -415,6 +514,7 @@ def main():
     nprof = min(loops, 8)
     for _ in range(nprof):
         pass_device()
+    torch.cuda.synchronize()
     prof = fe.profile_read()
     fe.profile(False)
     fe.pdus()
@@ -423,26 +523,37 @@ def main():
         fe.L.hfdl_b200_print_summary(fe.h)
     geom = fe.geom
     fe.close()
+    del xch
 
     # ---- e2e: from pinned host memory
     e2e_ms, e_good, d2h_per_step, h2d_per_step = float("nan"), 0, 0, 0
     if not a.skip_e2e:
-        fe2 = hb.Frontend(W["sr"], CF, freqs, sample_format=hb.api.SFMT_CF32, device=local, max_blocks_per_batch=nblocks)
+        fe2 = make_frontend()
         st2 = {"pos": 0, "i": 0}
+        xch2 = Exchange(fe2) if sharded else None
 
         copy_stream = torch.cuda.Stream() if world > 1 else None
-        d_parts = [d_part, torch.empty_like(d_part)] if world > 1 else None
+        h_src = h_share if sharded else h_part
+        d_parts = [torch.empty_like(h_src, device="cuda") for _ in range(2)] if world > 1 else None
         h2d_ev = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
+        read_ev = [None, None]
 
         def start_h2d(i):
-            # this rank's 1/N of pass i over its own PCIe link, on its own stream (runs beside the all-gather of pass i-1)
+            # this rank's share of pass i over its own PCIe link, on its own stream (runs beside the FFT / all-gather of pass i-1)
             with torch.cuda.stream(copy_stream):
-                d_parts[i % 2].copy_(h_part, non_blocking=True)
+                if sharded and read_ev[i % 2] is not None:
+                    copy_stream.wait_event(read_ev[i % 2])             # the FFT of pass i-2 has read this device buffer
+                d_parts[i % 2].copy_(h_src, non_blocking=True)
                 h2d_ev[i % 2].record(copy_stream)
 
         def pass_host():
             i = st2["i"]
-            if world > 1:
+            if sharded:
+                if i == 0:
+                    start_h2d(0)
+                read_ev[i % 2] = xch2.run(d_parts[i % 2], h2d_ev[i % 2])
+                start_h2d(i + 1)
+            elif world > 1:
                 buf = bufs[i % nbuf]
                 if i == 0:
                     start_h2d(0)
@@ -459,6 +570,7 @@ def main():
 
         for _ in range(max(1, a.warmup * loops // 4)):
             pass_host()
+        torch.cuda.synchronize()
         fe2.flush()
         fe2.pdus()
         barrier()
@@ -467,13 +579,15 @@ def main():
             for _ in range(loops):
                 pass_host()
                 e_good += count(fe2.pdus())[0]           # PDU records of the batches that finished meanwhile (D2H)
+        torch.cuda.synchronize()
         fe2.flush()                                      # the timed region ends when every PDU is on the host
         e_good += count(fe2.pdus())[0]
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         d2h_per_step = fe2.result_bytes_per_batch() * loops
-        h2d_per_step = part * 8 * loops
+        h2d_per_step = h_src.numel() * loops
         fe2.close()
+        del xch2
 
     t = torch.tensor([ms, e2e_ms if e2e_ms == e2e_ms else 0.0, float(good), float(exact), float(e_good), float(ntruth), float(launches),
                       float(h2d_per_step), float(d2h_per_step)], dtype=torch.float64, device="cuda")
@@ -494,10 +608,12 @@ def main():
         N, M, out = geom.fft_size, geom.fft_inv_size, geom.out_per_block
         Cn = len(freqs)
         # algorithmic (compulsory) HBM bytes per overlap-save block ON ONE GPU, SURVEY 8(d): ingest read + spectrum write
-        # (both unsharded) + this GPU's channels' spectrum slice read + tap slice read + baseband write + demod read
-        b_blk = isz * 8 + N * 8 + Cn * M * 8 + Cn * M * 8 + Cn * out * 16
+        # (this GPU's share of the blocks: all of them unless the spectrum is sharded) + this GPU's channels' spectrum
+        # slice read + tap slice read + baseband write + demod read
+        fsh = 1.0 / world if sharded else 1.0
+        b_blk = int(fsh * (isz * bps + N * 8)) + Cn * M * 8 + Cn * M * 8 + Cn * out * 16
         nout = out * geom.resamp_rate
-        alg = {"fft_pass1": isz * 8, "fft_pass2": N * 8 if geom.fft_passes == 2 else 0, "fft_pass3": N * 8 if geom.fft_passes == 3 else 0,
+        alg = {"fft_pass1": isz * bps * fsh, "fft_pass2": N * 8 * fsh if geom.fft_passes == 2 else 0, "fft_pass3": N * 8 * fsh if geom.fft_passes == 3 else 0,
                "chan_extract": Cn * M * 16 + Cn * out * 8, "resamp": Cn * out * 8 * (1 + geom.resamp_rate),
                "agc": Cn * nout * (8 + 12), "bank": Cn * nout * (8 + 8 + 256), "loop": Cn * nout * (256 + 4), "fec": 0}
         peaks = {}
@@ -546,7 +662,7 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": config_of(name, W, P, world),
                 "step": "%d passes over the slab (%.1f Msamples, %d batches of %d blocks per GPU)" % (loops, loops * nsamp / 1e6, loops, nblocks),
                 "scaling_note": "the workload is BASELINE's configuration for the GPU count (cfg3 at 1-2, cfg4 at 4, cfg5 at 8 GPUs): capture rate and channel count grow with N; "
-                                "value counts capture samples once although every GPU transforms the whole capture",
+                                "value counts capture samples once" + ("" if sharded or world == 1 else " although every GPU transforms the whole capture"),
                 "pdus_per_s": good / (ms / 1e3), "pdus_crc_good": good, "pdus_exact": exact, "pdus_expected_per_pass": ntruth,
                 "e2e": {"value": e2e, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step),
                         "pdus_per_s": (e_good / (e2e_ms / 1e3)) if e2e_ms > 0 else None, "ms_per_step": e2e_ms / a.steps if e2e_ms > 0 else None},

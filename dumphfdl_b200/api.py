@@ -64,6 +64,11 @@ def bind(L):
     L.hfdl_b200_wait_input.argtypes = [vp, C.c_int32]
     L.hfdl_b200_push_peer.argtypes = [vp, vp]
     L.hfdl_b200_poll.argtypes = [vp]
+    L.hfdl_b200_set_exchange.argtypes = [vp, C.POINTER(C.c_int32), C.c_int32, C.c_int32]
+    L.hfdl_b200_spectrum_slices.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp]
+    L.hfdl_b200_process_slices.argtypes = [vp, vp, C.c_int32, vp]
+    L.hfdl_b200_slice_elems.argtypes = [vp]
+    L.hfdl_b200_slice_elems.restype = C.c_int64
     L.hfdl_b200_busy.argtypes = [vp]
     L.hfdl_b200_channel_counters.argtypes = [vp, C.c_int32, C.POINTER(Counters)]
     L.hfdl_b200_pdu_count.argtypes = [vp]
@@ -207,6 +212,23 @@ class Frontend:
         r = self.L.hfdl_b200_process_device(self.h, dptr, ring_samples, start_sample, nblocks)
         if r < 0:
             raise RuntimeError("hfdl_b200_process_device failed")
+        return r
+
+    def set_exchange(self, all_freqs_hz, nranks):
+        arr = (C.c_int32 * len(all_freqs_hz))(*all_freqs_hz)
+        if self.L.hfdl_b200_set_exchange(self.h, arr, len(all_freqs_hz), nranks) != 0:
+            raise RuntimeError("hfdl_b200_set_exchange failed")
+
+    def spectrum_slices(self, d_samples, first_block, nblocks, d_send, stream=None):
+        r = self.L.hfdl_b200_spectrum_slices(self.h, d_samples, first_block, nblocks, d_send, stream)
+        if r < 0:
+            raise RuntimeError("hfdl_b200_spectrum_slices failed")
+        return r
+
+    def process_slices(self, d_slices, nblocks, stream=None):
+        r = self.L.hfdl_b200_process_slices(self.h, d_slices, nblocks, stream)
+        if r < 0:
+            raise RuntimeError("hfdl_b200_process_slices failed")
         return r
 
     def sync(self):

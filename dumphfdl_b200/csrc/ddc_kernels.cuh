@@ -216,21 +216,32 @@ __device__ __forceinline__ WindowView window_view(const RawSource &src, int b) {
 	return v;
 }
 
+// one raw sample -> CF32.  The division by full_scale (input-helpers.c:10-78) is a multiplication by its reciprocal, as
+// in the reference's own build (-ffast-math implies -freciprocal-math, src/CMakeLists.txt:39-42).
+__device__ __forceinline__ cf load_raw(const void *base, int sfmt, long long r) {
+	if(sfmt == HFDL_SFMT_CF32) {
+		return reinterpret_cast<const cf *>(base)[r];                     // full_scale 1.0
+	} else if(sfmt == HFDL_SFMT_CS16) {
+		short2 q = reinterpret_cast<const short2 *>(base)[r];
+		const float rfs = 1.0f / 32767.5f;                                // SHRT_MAX + 0.5 (input-helpers.c:116)
+		return make_float2((float)q.x * rfs, (float)q.y * rfs);
+	} else {
+		uchar2 q = reinterpret_cast<const uchar2 *>(base)[r];
+		const float rfs = 1.0f / 127.0f, shift = 63.5f;                   // input-helpers.c:54,110
+		return make_float2(((float)q.x - shift) * rfs, ((float)q.y - shift) * rfs);
+	}
+}
+// all elements [n_lo, n_hi) of the window are real samples that lie in the ring without wrapping: they can be read
+// through one base index (no per-element zero-fill test, no wrap test, 32-bit offsets)
+__device__ __forceinline__ bool window_plain(const WindowView &v, long long n_lo, long long n_hi) {
+	return n_lo >= v.first_valid && v.start_ring + n_hi <= v.ring_len;
+}
+
 __device__ __forceinline__ cf load_window(const WindowView &v, long long n) {      // n in [0, N), N <= ring_len
 	if(n < v.first_valid) return make_float2(0.f, 0.f);
 	long long r = v.start_ring + n;
 	if(r >= v.ring_len) r -= v.ring_len;
-	if(v.sfmt == HFDL_SFMT_CF32) {
-		return reinterpret_cast<const cf *>(v.base)[r];                   // full_scale 1.0
-	} else if(v.sfmt == HFDL_SFMT_CS16) {
-		short2 q = reinterpret_cast<const short2 *>(v.base)[r];
-		const float fs = 32767.5f;                                        // SHRT_MAX + 0.5 (input-helpers.c:116)
-		return make_float2((float)q.x / fs, (float)q.y / fs);
-	} else {
-		uchar2 q = reinterpret_cast<const uchar2 *>(v.base)[r];
-		const float fs = 127.0f, shift = 63.5f;                           // input-helpers.c:54,110
-		return make_float2(((float)q.x - shift) / fs, ((float)q.y - shift) / fs);
-	}
+	return load_raw(v.base, v.sfmt, r);
 }
 
 // Column pass: FFT along an axis of stride 'inner' for T adjacent inner positions, then twiddle
@@ -396,8 +407,29 @@ __global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_col_pass_reg(ColPa
 		cf x[32];
 		if(a.first) {
 			const WindowView wv = window_view(a.src, blk);
+			if(window_plain(wv, base, base + (long long)(L - 1) * a.inner + T)) {      // CTA-uniform: all but the windows at the stream start / ring wrap
+				const long long r0 = wv.start_ring + base + (long long)b * a.inner + t;
+				const int step = B * a.inner;
+				if(wv.sfmt == HFDL_SFMT_CF32) {
+					const cf *q = reinterpret_cast<const cf *>(wv.base) + r0;
 #pragma unroll
-			for(int i = 0; i < 32; i++) x[i] = load_window(wv, base + (long long)(i * B + b) * a.inner + t);
+					for(int i = 0; i < 32; i++) x[i] = q[i * step];
+				} else if(wv.sfmt == HFDL_SFMT_CS16) {
+					const short2 *q = reinterpret_cast<const short2 *>(wv.base) + r0;
+					short2 raw[32];
+#pragma unroll
+					for(int i = 0; i < 32; i++) raw[i] = q[i * step];
+					const float rfs = 1.0f / 32767.5f;
+#pragma unroll
+					for(int i = 0; i < 32; i++) x[i] = make_float2((float)raw[i].x * rfs, (float)raw[i].y * rfs);
+				} else {
+#pragma unroll
+					for(int i = 0; i < 32; i++) x[i] = load_raw(wv.base, wv.sfmt, r0 + (long long)i * step);
+				}
+			} else {
+#pragma unroll
+				for(int i = 0; i < 32; i++) x[i] = load_window(wv, base + (long long)(i * B + b) * a.inner + t);
+			}
 		} else {
 #pragma unroll
 			for(int i = 0; i < 32; i++) x[i] = wk[(long long)(i * B + b) * a.inner + t];
@@ -413,32 +445,39 @@ __global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_col_pass_reg(ColPa
 		}
 	}
 	__syncthreads();
+	// inter-pass twiddle W^(k*c), W = exp(-2*pi*i / (L*inner)), k = ka + 32*kb, c = column (fixed per thread: T divides
+	// 256).  ka = ka0 + (256/T)*i walks with i, so W^(ka*c) = W^(ka0*c) * (W^((256/T)*c))^i: three sincospif per thread
+	// (exactly representable arguments), then one complex multiply per step (<= 15 steps)
 	const float inv_np = 1.0f / (float)((long long)L * a.inner);      // power of two: exact
-#pragma unroll
-	for(int i = 0; i < 32 / B; i++) {
-		const int p = tid + 256 * i;
-		const int t = p & (T - 1), ka = p >> LGT;
-		cf z[B];
-#pragma unroll
-		for(int b = 0; b < B; b++) z[b] = s[((ka << LGB) + b) * T + t];
-		fft_reg_dif<B>(z);
-		// inter-pass twiddle W^(k*c), k = ka + 32*kb, c = column: base W^(ka*c) times powers of W^(32*c)
-		const float c = (float)(n0 + t);
+	const int t = tid & (T - 1), ka0 = tid >> LGT;
+	const float c = (float)(n0 + t);
+	cf wka, wstep, pw[B];
+	{
 		float sn, cs;
-		sincospif(-2.0f * (float)ka * c * inv_np, &sn, &cs);
-		const cf wbase = make_float2(cs, sn);
+		sincospif(-2.0f * (float)ka0 * c * inv_np, &sn, &cs);
+		wka = make_float2(cs, sn);
+		sincospif(-2.0f * (float)(256 >> LGT) * c * inv_np, &sn, &cs);
+		wstep = make_float2(cs, sn);
 		sincospif(-2.0f * 32.0f * c * inv_np, &sn, &cs);
-		cf pw[B];
 		pw[0] = make_float2(1.f, 0.f);
 		if(B > 1) pw[1] = make_float2(cs, sn);
 #pragma unroll
 		for(int q = 2; q < B; q++) pw[q] = cmul(pw[q >> 1], pw[q - (q >> 1)]);
+	}
+#pragma unroll
+	for(int i = 0; i < 32 / B; i++) {
+		const int ka = ka0 + (256 >> LGT) * i;
+		cf z[B];
+#pragma unroll
+		for(int b = 0; b < B; b++) z[b] = s[((ka << LGB) + b) * T + t];
+		fft_reg_dif<B>(z);
 #pragma unroll
 		for(int j = 0; j < B; j++) {
 			const int kb = brev_ct(j, LGB);
-			const cf w = cmul(wbase, pw[kb]);
+			const cf w = cmul(wka, pw[kb]);
 			wk[(long long)(ka + 32 * kb) * a.inner + t] = cmul(z[j], w);
 		}
+		wka = cmul(wka, wstep);
 	}
 }
 
@@ -564,6 +603,7 @@ __global__ void tapslice_gather(const cf *work, FftPlan pl, int M, const int *of
 // K2+K3+K4.  grid = (C, B), block = HFDL_FFT_THREADS, smem = M*8.
 struct ChanArgs {
 	const cf *work;            // [B][N] scrambled spectra
+	const cf *slices;          // sharded spectrum: [B][C][M] pass-band slices in inverse-FFT input order (slice_pack); nullptr: read `work`
 	const cf *tapslice;        // [C][M]
 	const int *offsetbin;      // [C]
 	const float *dsa_rate;     // [C] phase increment per output sample / pi (libcsdr_gpl.c:26-39)
@@ -583,11 +623,16 @@ __global__ void __launch_bounds__(HFDL_FFT_THREADS) chan_extract(ChanArgs a) {
 	const int off = a.offsetbin[c];
 	const cf *W = a.work + (long long)b * a.pl.N;
 	const cf *H = a.tapslice + (long long)c * a.M;
-	for(int i = threadIdx.x; i < a.M; i += blockDim.x) {
-		int sg = i < a.M / 2 ? i : i - a.M;
-		int k = (off + sg) & (a.pl.N - 1);
-		cf v = cmul(__ldg(&H[i]), W[fft_bin_addr(a.pl, k)]);
-		s[brev_n(i, a.lgM)] = v;
+	if(a.slices) {
+		const cf *S = a.slices + ((long long)b * gridDim.x + c) * a.M;
+		for(int i = threadIdx.x; i < a.M; i += blockDim.x) s[brev_n(i, a.lgM)] = cmul(__ldg(&H[i]), S[i]);
+	} else {
+		for(int i = threadIdx.x; i < a.M; i += blockDim.x) {
+			int sg = i < a.M / 2 ? i : i - a.M;
+			int k = (off + sg) & (a.pl.N - 1);
+			cf v = cmul(__ldg(&H[i]), W[fft_bin_addr(a.pl, k)]);
+			s[brev_n(i, a.lgM)] = v;
+		}
 	}
 	__syncthreads();
 	smem_fft(s, a.lgM, 1, 1, a.tw, 1);
@@ -601,6 +646,23 @@ __global__ void __launch_bounds__(HFDL_FFT_THREADS) chan_extract(ChanArgs a) {
 		sincospif((float)(2.0 * fr), &sn, &cs);
 		cf v = cscale(s[a.scrap + j * a.post_dec], a.inv_norm);
 		out[j] = make_float2(cs * v.x - sn * v.y, sn * v.x + cs * v.y);
+	}
+}
+
+// Sharded spectrum (multi-GPU, one rank transforms a share of the blocks for every rank's channels): the pass-band slice
+// of channel j of the WHOLE job's channel list (M bins around offsetbin[j], inverse-FFT input order -- exactly what
+// chan_extract multiplies with the tap slice) goes to the send buffer of the rank that owns the channel:
+//   send[owner = j % R][block b][local channel j / R][M],   grid = (n_all, nb).
+// The exchange (all-to-all over NVLink) then leaves every rank with [all blocks of the batch][its channels][M].
+__global__ void slice_pack(const cf *spec, FftPlan pl, int M, const int *offsetbin, int nranks, int nb, cf *send) {
+	const int j = blockIdx.x, b = blockIdx.y;
+	const int owner = j % nranks, local = j / nranks, cper = gridDim.x / nranks;
+	const int off = offsetbin[j];
+	const cf *W = spec + (long long)b * pl.N;
+	cf *dst = send + (((long long)owner * nb + b) * cper + local) * M;
+	for(int i = threadIdx.x; i < M; i += blockDim.x) {
+		const int sg = i < M / 2 ? i : i - M;
+		dst[i] = W[fft_bin_addr(pl, (off + sg) & (pl.N - 1))];
 	}
 }
 

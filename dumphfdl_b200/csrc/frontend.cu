@@ -22,8 +22,8 @@
 
 namespace {
 
-enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_AGC, KC_BANK, KC_LOOP, KC_FEC, KC_COUNT };
-const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "agc", "bank", "loop", "fec" };
+enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_AGC, KC_BANK, KC_LOOP, KC_FEC, KC_PACK, KC_COUNT };
+const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "agc", "bank", "loop", "fec", "slice_pack" };
 
 struct ProfRec { int cls; cudaEvent_t e0, e1; };
 #ifndef HFDL_NSETS
@@ -38,6 +38,12 @@ FftPlan make_plan(int N) {
 	if(lg <= 12) { p.P = 1; p.lgL[0] = lg; }
 	else if(lg <= 18) { p.P = 2; p.lgL[0] = lg / 2; p.lgL[1] = lg - p.lgL[0]; }
 	else { p.P = 3; p.lgL[0] = lg / 3; p.lgL[1] = (lg - p.lgL[0]) / 2; p.lgL[2] = lg - p.lgL[0] - p.lgL[1]; }
+	if(p.P == 3) {
+		// experiments: HFDL_B200_FFT_PLAN="a,b" = log2 of the first two pass lengths of a three-pass plan
+		const char *e = getenv("HFDL_B200_FFT_PLAN");
+		int a = 0, b = 0;
+		if(e && sscanf(e, "%d,%d", &a, &b) == 2 && a >= 6 && a <= 9 && b >= 6 && b <= 9 && lg - a - b >= 6 && lg - a - b <= 9) { p.lgL[0] = a; p.lgL[1] = b; p.lgL[2] = lg - a - b; }
+	}
 	// natural-order, out-of-place last pass (fft_last_pass_nat): needs a register-resident last pass (L = 32*B,
 	// B = 2..16) and at least one tile of 256/B consecutive k1 rows
 	if(p.P >= 2 && !getenv("HFDL_B200_SMEM_FFT")) {
@@ -118,6 +124,9 @@ struct hfdl_b200_frontend {
 	// device memory
 	cf *d_work = nullptr, *d_spec = nullptr;       // FFT workspace (passes in place) / natural-order spectra (plan.natural)
 	unsigned *d_mask = nullptr; double spec_fill = 1.0;   // spectrum granules the channels read (bit set) / their share of the band
+	// sharded spectrum (hfdl_b200_set_exchange): the channel list of the whole job; channel j belongs to rank j % xr_ranks
+	int xr_ranks = 0, xr_nall = 0; int *d_all_offsetbin = nullptr;
+	cudaEvent_t ev_ext = nullptr;      // recorded on the caller's stream: the slices of the next batch have arrived
 	void *d_ring = nullptr; long long ring_len = 0;
 	cf *d_tapslice = nullptr; int *d_offsetbin = nullptr; float *d_dsa_rate = nullptr;
 	cf *d_bb = nullptr; long long bb_stride = 0;
@@ -199,7 +208,7 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 		int lgL = pl.lgL[p], L = 1 << lgL;
 		inner /= L;
 		ProfRec pr;
-		prof_begin(fe, KC_FFT1 + p, pr);
+		prof_begin2(fe, KC_FFT1 + p, pr, st);
 		if(p < pl.P - 1) {
 			ColPassArgs a;
 			a.src = src; a.work = work; a.tw = eng.d_tw; a.N = pl.N; a.lgL = lgL; a.inner = inner; a.lgInner = hfdl_ilog2(inner);
@@ -255,7 +264,7 @@ int run_fft(hfdl_b200_frontend *fe, const FftEngine &eng, const FftPlan &pl, con
 				HFDL_LAUNCH(fft_row_pass, grid, dim3(HFDL_FFT_THREADS), smem, st, a);
 			}
 		}
-		prof_end(fe, pr);
+		prof_end2(fe, pr, st);
 		if(fe) fe->launches++;
 		outer *= L;
 	}
@@ -345,7 +354,7 @@ int drain(hfdl_b200_frontend *fe) {
 // Consecutive batches use alternate sets (p = batch parity) of every buffer a later stage reads, so front + agc + bank
 // of batch i+1 run beside loop of batch i and fec of batch i-1; events order the reuse of a set two batches later.
 // The host collects the PDUs of batch i-1 after it has enqueued batch i.
-int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
+int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb, const cf *slices) {
 	const int p = (int)(fe->batch_seq % HFDL_NSETS), pp = (p + HFDL_NSETS - 1) % HFDL_NSETS, p2 = (p + HFDL_NSETS - 2) % HFDL_NSETS;
 	if(collect_batch(fe, p)) return -1;          // batch i-NSETS (normally collected long ago): every set-p buffer is free
 	cudaStream_t st = fe->stream, st2 = fe->stream2, stl = fe->st_loop, stf = fe->st_fec;
@@ -354,7 +363,9 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 	ProfRec pr;
 	// FFT passes over sub-batches of Bsub blocks (the in-place intermediate stays in L2 between the passes); the last pass
 	// writes the natural-order spectrum of block b at d_spec + b*N -- only the granules some channel's slice reads
-	for(int b0 = 0; b0 < nb; b0 += fe->Bsub) {
+	// (sharded spectrum: the pass-band slices of the batch arrive from the exchange instead, once ev_ext has fired)
+	if(slices) CK(cudaStreamWaitEvent(st, fe->ev_ext, 0));
+	for(int b0 = 0; b0 < nb && !slices; b0 += fe->Bsub) {
 		const int nsb = std::min(fe->Bsub, nb - b0);
 		RawSource src = src0;
 		src.pos0 = src0.pos0 + (long long)b0 * src0.block_stride;
@@ -364,7 +375,7 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 	}
 	{
 		ChanArgs a;
-		a.work = fe->plan.natural ? fe->d_spec : fe->d_work; a.tapslice = fe->d_tapslice; a.offsetbin = fe->d_offsetbin; a.dsa_rate = fe->d_dsa_rate;
+		a.work = fe->plan.natural ? fe->d_spec : fe->d_work; a.slices = slices; a.tapslice = fe->d_tapslice; a.offsetbin = fe->d_offsetbin; a.dsa_rate = fe->d_dsa_rate;
 		a.bb = fe->d_bb; a.tw = fe->fft.d_tw; a.pl = fe->plan;
 		a.M = g.fft_inv_size; a.lgM = hfdl_ilog2(g.fft_inv_size); a.scrap = g.scrap; a.post_dec = g.post_decimation;
 		a.out_per_block = fe->out_per_block; a.bb_stride = fe->bb_stride;
@@ -478,15 +489,39 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb) {
 
 // A failure in the middle of enqueueing leaves events unrecorded and counters half advanced: stop everything and
 // refuse further work instead of running on inconsistent pipeline state.
-int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb) {
+int run_batch(hfdl_b200_frontend *fe, const RawSource &src, int nb, const cf *slices = nullptr) {
 	if(fe->failed) return -1;
-	if(run_batch_impl(fe, src, nb) == 0) return 0;
+	if(run_batch_impl(fe, src, nb, slices) == 0) return 0;
 	fe->failed = true;
 	cudaStream_t sts[4] = { fe->stream, fe->stream2, fe->st_loop, fe->st_fec };
 	for(cudaStream_t q : sts) if(q) cudaStreamSynchronize(q);
 	for(int q = 0; q < HFDL_NSETS; q++) fe->flight[q].busy = false;
 	fprintf(stderr, "hfdl_b200: batch failed, frontend disabled\n");
 	return -1;
+}
+
+// granules of the spectrum some channel's pass-band slice reads (chan_extract / slice_pack: bins offsetbin - M/2 ..
+// offsetbin + M/2 - 1 mod N); the last FFT pass stores only those.  With a capture channel (parity / debug: the
+// CP_SPECTRUM checkpoint wants every bin) there is no mask and everything is stored.
+int build_spec_mask(hfdl_b200_frontend *fe, const std::vector<int> &offsetbin) {
+	const long long N = fe->g.fft_size, M = fe->g.fft_inv_size;
+	const long long ngran = N >> HFDL_SPEC_LG_GRAN;
+	std::vector<unsigned> m((size_t)((ngran + 31) / 32), 0u);
+	for(int ob : offsetbin) {
+		const long long off = ob;
+		for(long long k = off - M / 2; k < off + M / 2; k += HFDL_SPEC_GRAN) {
+			const long long gidx = (((k % N) + N) % N) >> HFDL_SPEC_LG_GRAN;
+			m[(size_t)(gidx >> 5)] |= 1u << (gidx & 31);
+		}
+		const long long last = ((((off + M / 2 - 1) % N) + N) % N) >> HFDL_SPEC_LG_GRAN;
+		m[(size_t)(last >> 5)] |= 1u << (last & 31);
+	}
+	if(!fe->d_mask) CK(cudaMalloc((void **)&fe->d_mask, sizeof(unsigned) * m.size()));
+	CK(cudaMemcpy(fe->d_mask, m.data(), sizeof(unsigned) * m.size(), cudaMemcpyHostToDevice));
+	long long set = 0;
+	for(unsigned w : m) set += __builtin_popcount(w);
+	fe->spec_fill = (double)set / (double)ngran;
+	return 0;
 }
 
 int compute_tapslices(hfdl_b200_frontend *fe) {
@@ -593,6 +628,7 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaStreamCreateWithFlags(&fe->st_stats, cudaStreamNonBlocking));
 	CKD(cudaStreamCreateWithFlags(&fe->st_h2d, cudaStreamNonBlocking));
 	CKD(cudaEventCreateWithFlags(&fe->ev_h2d, cudaEventDisableTiming));
+	CKD(cudaEventCreateWithFlags(&fe->ev_ext, cudaEventDisableTiming));
 	for(int q = 0; q < HFDL_NSETS; q++) {
 		CKD(cudaEventCreateWithFlags(&fe->ev_front[q], cudaEventDisableTiming));
 		CKD(cudaEventCreateWithFlags(&fe->ev_bank[q], cudaEventDisableTiming));
@@ -605,24 +641,9 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	CKD(cudaMalloc((void **)&fe->d_work, sizeof(cf) * (size_t)N * (fe->plan.natural ? std::max(fe->Bsub, 1) : B)));
 	if(fe->plan.natural) CKD(cudaMalloc((void **)&fe->d_spec, sizeof(cf) * (size_t)N * B));
 	if(fe->plan.natural && fe->cfg.capture_channel < 0 && !getenv("HFDL_B200_NO_SPEC_MASK")) {
-		// granules of the spectrum some channel's pass-band slice reads (chan_extract: bins offsetbin - M/2 .. offsetbin + M/2 - 1
-		// mod N); with a capture channel (parity / debug: the CP_SPECTRUM checkpoint wants every bin) everything is stored
-		const long long ngran = (long long)N >> HFDL_SPEC_LG_GRAN;
-		std::vector<unsigned> m((size_t)((ngran + 31) / 32), 0u);
-		for(int i = 0; i < C; i++) {
-			const long long off = fe->chg[(size_t)i].offsetbin;
-			for(long long k = off - M / 2; k < off + M / 2; k += HFDL_SPEC_GRAN) {
-				const long long gidx = (((k % N) + N) % N) >> HFDL_SPEC_LG_GRAN;
-				m[(size_t)(gidx >> 5)] |= 1u << (gidx & 31);
-			}
-			const long long last = ((((off + M / 2 - 1) % N) + N) % N) >> HFDL_SPEC_LG_GRAN;
-			m[(size_t)(last >> 5)] |= 1u << (last & 31);
-		}
-		CKD(cudaMalloc((void **)&fe->d_mask, sizeof(unsigned) * m.size()));
-		CKD(cudaMemcpy(fe->d_mask, m.data(), sizeof(unsigned) * m.size(), cudaMemcpyHostToDevice));
-		long long set = 0;
-		for(unsigned w : m) set += __builtin_popcount(w);
-		fe->spec_fill = (double)set / (double)ngran;
+		std::vector<int> ob((size_t)C);
+		for(int i = 0; i < C; i++) ob[(size_t)i] = fe->chg[(size_t)i].offsetbin;
+		if(build_spec_mask(fe, ob)) { hfdl_b200_destroy(fe); return -1; }
 	}
 	// host-fed ring: B + 1 blocks of capacity plus one batch that may still be read by the channeliser stage while the next
 	// samples arrive (the H2D copies run on their own stream, beside the FFT of the previous batch)
@@ -718,7 +739,7 @@ void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	cudaFree(fe->d_work); cudaFree(fe->d_spec); cudaFree(fe->d_mask); cudaFree(fe->d_ring); cudaFree(fe->d_tapslice); cudaFree(fe->d_offsetbin); cudaFree(fe->d_dsa_rate);
 	cudaFree(fe->d_bb); cudaFree(fe->d_rs_h); cudaFree(fe->d_tab); cudaFree(fe->d_state); cudaFree(fe->d_datasym);
 	cudaFree(fe->d_cap_agc); cudaFree(fe->d_cap_mf); cudaFree(fe->d_cap_eq); cudaFree(fe->d_cap_cnt); cudaFree(fe->d_tmp); cudaFree(fe->d_dbg);
-	cudaFree(fe->d_agc_state);
+	cudaFree(fe->d_agc_state); cudaFree(fe->d_all_offsetbin);
 	for(int q = 0; q < HFDL_NSETS; q++) {
 		cudaFree(fe->d_agc[q]); cudaFree(fe->d_mfo[q]); cudaFree(fe->d_lvl[q]); cudaFree(fe->d_bank[q]);
 		cudaFree(fe->d_rs[q]); cudaFree(fe->d_frames[q]); cudaFree(fe->d_nframes[q]); cudaFree(fe->d_pdus[q]);
@@ -733,6 +754,7 @@ void hfdl_b200_destroy(hfdl_b200_frontend_t *fe) {
 	if(fe->ev0) cudaEventDestroy(fe->ev0);
 	if(fe->ev1) cudaEventDestroy(fe->ev1);
 	if(fe->ev_h2d) cudaEventDestroy(fe->ev_h2d);
+	if(fe->ev_ext) cudaEventDestroy(fe->ev_ext);
 	fe->fft.destroy();
 	for(cudaStream_t q : sts) if(q) cudaStreamDestroy(q);
 	delete fe;
@@ -911,6 +933,72 @@ int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples
 	fe->fed = fe->blocks_done * (long long)g.input_size;
 	return done;
 }
+
+// ---- sharded spectrum (multi-GPU): every rank transforms a share of the overlap-save blocks for ALL channels of the job
+// and demodulates its own channels for ALL blocks; in between, the pass-band slices change hands (all-to-all over NVLink)
+int32_t hfdl_b200_set_exchange(hfdl_b200_frontend_t *fe, const int32_t *all_freqs_hz, int32_t n_all, int32_t nranks) {
+	if(!fe || !all_freqs_hz || nranks < 1 || n_all < nranks || n_all % nranks != 0) return -1;
+	HFDL_API(fe, -1);
+	if(n_all / nranks != fe->C) { fprintf(stderr, "hfdl_b200_set_exchange: this frontend has %d channels, the job gives every rank %d\n", fe->C, n_all / nranks); return -1; }
+	if(drain(fe)) return -1;
+	std::vector<int> ob((size_t)n_all);
+	for(int j = 0; j < n_all; j++) {
+		if(abs(fe->cfg.centerfreq_hz - all_freqs_hz[j]) >= fe->cfg.sample_rate / 2) return -1;
+		ob[(size_t)j] = hfdl_design::channel_geom(fe->g, fe->cfg.sample_rate, fe->cfg.centerfreq_hz, all_freqs_hz[j]).offsetbin;
+	}
+	if(fe->d_all_offsetbin) { cudaFree(fe->d_all_offsetbin); fe->d_all_offsetbin = nullptr; }
+	CK(cudaMalloc((void **)&fe->d_all_offsetbin, sizeof(int) * (size_t)n_all));
+	CK(cudaMemcpy(fe->d_all_offsetbin, ob.data(), sizeof(int) * (size_t)n_all, cudaMemcpyHostToDevice));
+	if(fe->d_mask && build_spec_mask(fe, ob)) return -1;          // the last FFT pass now stores what ANY rank's channels read
+	fe->xr_ranks = nranks; fe->xr_nall = n_all;
+	return 0;
+}
+
+int32_t hfdl_b200_spectrum_slices(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t first_block, int32_t nblocks, void *d_send, void *cuda_stream) {
+	if(!fe || !d_samples || !d_send || nblocks < 1 || first_block < 0) return -1;
+	HFDL_API(fe, -1);
+	if(fe->xr_ranks < 1 || nblocks > fe->Bmax) return -1;
+	const auto &g = fe->g;
+	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : fe->stream;
+	// the buffer holds stream positions [first_block * input_size - overlap, (first_block + nblocks) * input_size): as a "ring"
+	// that the windows never wrap in
+	RawSource src0;
+	src0.base = d_samples; src0.ring_len = (long long)g.overlap_length + (long long)nblocks * g.input_size;
+	src0.pos0 = first_block * (long long)g.input_size - g.overlap_length;
+	src0.ring_origin = ((-src0.pos0) % src0.ring_len + src0.ring_len) % src0.ring_len;
+	src0.block_stride = g.input_size; src0.sfmt = fe->sfmt;
+	ProfRec pr;
+	for(int b0 = 0; b0 < nblocks; b0 += fe->Bsub) {
+		const int nsb = std::min(fe->Bsub, nblocks - b0);
+		RawSource src = src0;
+		src.pos0 = src0.pos0 + (long long)b0 * src0.block_stride;
+		cf *spec = fe->plan.natural ? fe->d_spec + (long long)b0 * g.fft_size : nullptr;
+		cf *work = fe->plan.natural ? fe->d_work : fe->d_work + (long long)b0 * g.fft_size;
+		if(run_fft(fe, fe->fft, fe->plan, src, work, spec, nsb, st, fe->d_mask)) return -1;
+	}
+	prof_begin2(fe, KC_PACK, pr, st);
+	HFDL_LAUNCH(slice_pack, dim3((unsigned)fe->xr_nall, (unsigned)nblocks), dim3(256), 0, st,
+		fe->plan.natural ? fe->d_spec : fe->d_work, fe->plan, g.fft_inv_size, fe->d_all_offsetbin, fe->xr_ranks, nblocks, (cf *)d_send);
+	prof_end2(fe, pr, st);
+	fe->launches++;
+	CK(cudaGetLastError());
+	return nblocks;
+}
+
+int32_t hfdl_b200_process_slices(hfdl_b200_frontend_t *fe, const void *d_slices, int32_t nblocks, void *cuda_stream) {
+	if(!fe || !d_slices || nblocks < 1) return -1;
+	HFDL_API(fe, -1);
+	if(nblocks > fe->Bmax) return -1;
+	// whatever the caller's stream has queued so far (the exchange that fills d_slices) comes before the channeliser stage
+	CK(cudaEventRecord(fe->ev_ext, cuda_stream ? (cudaStream_t)cuda_stream : (cudaStream_t)0));
+	RawSource none;
+	memset(&none, 0, sizeof(none));
+	if(run_batch(fe, none, nblocks, (const cf *)d_slices)) return -1;
+	fe->fed = fe->blocks_done * (long long)fe->g.input_size;
+	return nblocks;
+}
+
+int64_t hfdl_b200_slice_elems(const hfdl_b200_frontend_t *fe) { return fe ? (int64_t)fe->g.fft_inv_size : -1; }
 
 int32_t hfdl_b200_sync(hfdl_b200_frontend_t *fe) {
 	HFDL_API(fe, -1);

@@ -146,6 +146,34 @@ int32_t hfdl_b200_push_peer(hfdl_b200_frontend_t *dst, hfdl_b200_frontend_t *src
 int32_t hfdl_b200_poll(hfdl_b200_frontend_t *fe);
 int32_t hfdl_b200_busy(hfdl_b200_frontend_t *fe);
 
+/* ---- Multi-GPU, sharded spectrum (one process per GPU or one process for all).  The reference hands every block's
+ * spectrum to every channel (fft.c:60-61, block.c:90-120: one producer, many consumers); across GPUs the cheap thing to
+ * hand over is not the capture but the M-bin pass-band slice each channel reads (fastddc.c:152-167 touches nothing
+ * else of the spectrum once the alias fold is restricted to the pass-band): C x M x 8 bytes per block instead of
+ * input_size x sample bytes.  So every rank runs the forward FFT of 1/R of a batch's blocks for ALL channels of the
+ * job, the slices change hands (all-to-all over NVLink: NCCL, or peer copies in one process), and every rank
+ * demodulates ITS channels for all blocks.  FFT work and PCIe ingest are then divided by R instead of replicated.
+ *
+ * hfdl_b200_set_exchange: declares the channel list of the whole job.  Channel j of the list belongs to rank j % nranks,
+ *   where it is local channel j / nranks (the frontend was created with exactly those n_all / nranks frequencies, in
+ *   that order).  From now on the last FFT pass stores the spectrum granules ANY listed channel reads.
+ * hfdl_b200_spectrum_slices: forward FFT of `nblocks` consecutive overlap-save windows, the first one being block
+ *   `first_block` of the stream; d_samples (device, configured sample format) holds the stream positions
+ *   [first_block * input_size - overlap_length, (first_block + nblocks) * input_size) (positions < 0 read as zero).
+ *   Writes d_send[nranks][nblocks][n_all / nranks][fft_inv_size] complex64: destination rank, block, that rank's local
+ *   channel, bins offsetbin - M/2 .. offsetbin + M/2 - 1 in inverse-FFT input order.  Runs on `cuda_stream` (a
+ *   cudaStream_t; NULL = the frontend's own front stream), so the caller's exchange can simply be queued behind it.
+ * hfdl_b200_process_slices: one batch of `nblocks` blocks from d_slices[nblocks][channels of this frontend][fft_inv_size]
+ *   (what the exchange delivers: the d_send parts addressed to this rank, in block order).  Everything queued on
+ *   `cuda_stream` so far (the exchange) is waited for on the device; the call itself does not block.  Consecutive
+ *   calls continue the stream, exactly like hfdl_b200_process_device; hfdl_b200_wait_input tells when d_slices may be
+ *   overwritten. */
+int32_t hfdl_b200_set_exchange(hfdl_b200_frontend_t *fe, const int32_t *all_freqs_hz, int32_t n_all, int32_t nranks);
+int32_t hfdl_b200_spectrum_slices(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t first_block, int32_t nblocks,
+		void *d_send, void *cuda_stream);
+int32_t hfdl_b200_process_slices(hfdl_b200_frontend_t *fe, const void *d_slices, int32_t nblocks, void *cuda_stream);
+int64_t hfdl_b200_slice_elems(const hfdl_b200_frontend_t *fe);
+
 int32_t hfdl_b200_pdu_count(hfdl_b200_frontend_t *fe);
 /* returns 1 and fills *pdu when one is available, 0 when the queue is empty */
 int32_t hfdl_b200_pop_pdu(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdu);

@@ -275,3 +275,110 @@ def case_frontend_stream(lib, sr, freqs, plan, dur, batch, esn0=20.0, seed=31, p
         assert a.size == b.size and rel(a, b) < TOL_DEMOD, name
     fe.close()
     return len(got)
+
+
+class HostMem:
+    """'Device' memory of the host-emulation build: plain numpy buffers."""
+
+    def upload(self, a):
+        return np.ascontiguousarray(a).copy()
+
+    def empty(self, nbytes):
+        return np.zeros(nbytes, np.uint8)
+
+    def ptr(self, h, byte_offset=0):
+        return h.ctypes.data + byte_offset
+
+    def copy(self, dst, dst_off, src, src_off, nbytes):
+        import ctypes
+        ctypes.memmove(dst.ctypes.data + dst_off, src.ctypes.data + src_off, nbytes)
+
+    def sync(self):
+        pass
+
+
+class CudaMem:
+    """Device memory through torch (GPU tests)."""
+
+    def __init__(self):
+        import torch
+        self.t = torch
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a)
+        return self.t.from_numpy(a.view(np.uint8).reshape(-1).copy()).cuda()
+
+    def empty(self, nbytes):
+        return self.t.zeros(nbytes, dtype=self.t.uint8, device="cuda")
+
+    def ptr(self, h, byte_offset=0):
+        return h.data_ptr() + byte_offset
+
+    def copy(self, dst, dst_off, src, src_off, nbytes):
+        dst[dst_off:dst_off + nbytes].copy_(src[src_off:src_off + nbytes])
+
+    def sync(self):
+        self.t.cuda.synchronize()
+
+
+def case_sharded_spectrum(lib, mem, sr, freqs, modes, dur, nranks, batch, sfmt=A.SFMT_CF32, seed=71, starts=None):
+    """Multi-GPU data path on ONE device: `nranks` frontends, rank r owning the channels freqs[r::nranks].  Per batch every
+    rank transforms its share of the blocks for all channels (hfdl_b200_spectrum_slices), the slices change hands (here:
+    plain copies standing in for the all-to-all) and every rank demodulates its channels (hfdl_b200_process_slices).
+    The PDUs must be those of one frontend that owns all channels (and the oracle's)."""
+    assert batch % nranks == 0 and len(freqs) % nranks == 0
+    x, truth = make_capture(sr, freqs, modes, dur, seed=seed, starts=starts)
+    raw = x
+    if sfmt == A.SFMT_CS16:
+        raw = np.zeros(2 * x.size, np.int16)
+        O.lib().orc_quantize_cs16(x, x.size, raw)
+    bps = {A.SFMT_CS16: 4, A.SFMT_CF32: 8}[sfmt]
+    fes = [A.Frontend(sr, CF, freqs[r::nranks], sample_format=sfmt, max_blocks_per_batch=batch, lib=lib) for r in range(nranks)]
+    for fe in fes:
+        fe.set_exchange(freqs, nranks)
+    g = fes[0].geom
+    isz, ovl, M = g.input_size, g.overlap_length, g.fft_inv_size
+    cper = len(freqs) // nranks
+    nb = x.size // isz
+    nb -= nb % nranks                                     # every batch (the last, shorter one too) splits evenly
+    rawb = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    padded = np.concatenate([np.zeros(ovl * bps, np.uint8), rawb[: nb * isz * bps]])
+    ref_fe = A.Frontend(sr, CF, freqs, sample_format=sfmt, max_blocks_per_batch=batch, lib=lib)
+    ref_fe.push(rawb[: nb * isz * bps])
+    ref_fe.flush()
+    want = sorted((q.freq, q.sample_cnt_a2, q.sample_cnt_end, q.M1, q.crc_good, q.data()) for q in ref_fe.pdus())
+    ref_fe.close()
+    slice_bytes = M * 8
+    done = 0
+    keep = []                                             # buffers stay alive until the pipelines have drained
+    while done < nb:
+        B = min(batch, nb - done)
+        bl = B // nranks
+        sends = []
+        for r, fe in enumerate(fes):
+            first = done + r * bl
+            buf = mem.upload(padded[first * isz * bps: (first * isz + ovl + bl * isz) * bps])
+            send = mem.empty(nranks * bl * cper * slice_bytes)
+            fe.spectrum_slices(mem.ptr(buf), first, bl, mem.ptr(send))
+            sends.append(send)
+            keep.append(buf)
+        mem.sync()                                        # spectrum_slices ran on each frontend's own stream: device-wide sync
+        part = bl * cper * slice_bytes
+        for q, fe in enumerate(fes):
+            recv = mem.empty(B * cper * slice_bytes)
+            for r in range(nranks):
+                mem.copy(recv, r * part, sends[r], q * part, part)
+            mem.sync()
+            fe.process_slices(mem.ptr(recv), B)
+            keep.append(recv)
+        keep += sends
+        done += B
+    got = []
+    for fe in fes:
+        fe.sync()
+        got += fe.pdus()
+        fe.close()
+    got = sorted((q.freq, q.sample_cnt_a2, q.sample_cnt_end, q.M1, q.crc_good, q.data()) for q in got)
+    assert got == want
+    assert sorted((f, d) for f, _, _, _, _, d in got) == sorted(truth)
+    return len(got)

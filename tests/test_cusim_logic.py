@@ -67,3 +67,8 @@ def test_tapslice_checkpoint(sim):
 
 def test_pruned_spectrum_equals_full(sim):
     assert K.case_pruned_spectrum(sim, 250000, [10063000, 9931000, 10110000], [1, 2, 0], 3.3, batch=5) == 3
+
+
+def test_sharded_spectrum_two_ranks(sim):
+    # multi-GPU data path (FFT blocks sharded, slices exchanged, channels sharded) on the host emulation: PDUs == one frontend's
+    assert K.case_sharded_spectrum(sim, K.HostMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4) == 4

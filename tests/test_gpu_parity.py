@@ -241,6 +241,19 @@ def test_device_resident_path_equals_host_path(lib):
     K.compare_pdus(b, [O_pdu(q) for q in a], truth)
 
 
+def test_sharded_spectrum_equals_single_frontend(lib):
+    # multi-GPU data path on one device: 2 and 4 "ranks", CF32 and CS16, batches that end ragged
+    assert K.case_sharded_spectrum(lib, K.CudaMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4) == 4
+    assert K.case_sharded_spectrum(lib, K.CudaMem(), 250000, [10063000, 9952000, 10101000, 9931000], [5, 2, 4, 3], 5.6, nranks=4, batch=8, sfmt=A.SFMT_CS16, seed=72) == 4
+
+
+def test_sharded_spectrum_cfg3_geometry(lib):
+    # three-pass natural-order plan (N = 2^22, M = 4096) with the pruned spectrum store, 2 ranks x 4 channels
+    sr = 20000000
+    freqs = [K.CF + int((k - 3.5) * 132000) // 1000 * 1000 for k in range(8)]
+    assert K.case_sharded_spectrum(lib, K.CudaMem(), sr, freqs, [1, 2, 0, 3, 1, 0, 2, 3], 2.8, nranks=2, batch=4, seed=73, starts=[0.05 + 0.005 * k for k in range(8)]) == 8
+
+
 class O_pdu:
     def __init__(self, q):
         self.freq, self.sample_cnt_end, self._d, self.M1, self.crc_good, self.sample_cnt_a2 = q.freq, q.sample_cnt_end, q.data(), q.M1, q.crc_good, q.sample_cnt_a2

@@ -134,3 +134,66 @@ def test_two_rank_scatter_allgather_gloo():
     ref = K.run_oracle(250000, FREQS, x, O.SFMT_CF32).pdus()
     want = sorted((int(r.sample_cnt_end), int(r.freq), r.data(), int(r.M1), int(r.crc_good)) for r in ref)
     assert merged == want and len(merged) == 3
+
+
+def _worker_sharded(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import dumphfdl_b200.api as A
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sim = A.bind(C.CDLL(os.path.join(HERE, "cusim", "libhfdl_cusim.so")))
+    sr, batch = 250000, 4
+    freqs = FREQS + [9931000]
+    x, _ = K.make_capture(sr, freqs, MODES + [3], 3.3, seed=43)          # every rank renders the same capture, uses its share only
+    fe = A.Frontend(sr, K.CF, freqs[rank::world], max_blocks_per_batch=batch, lib=sim)
+    fe.set_exchange(freqs, world)
+    g = fe.geom
+    isz, ovl, M = g.input_size, g.overlap_length, g.fft_inv_size
+    cper = len(freqs) // world
+    nb = x.size // isz
+    nb -= nb % world
+    padded = np.concatenate([np.zeros(ovl, np.complex64), x[: nb * isz]])
+    done, keep = 0, []
+    while done < nb:
+        B = min(batch, nb - done)
+        bl = B // world
+        first = done + rank * bl
+        mine = np.ascontiguousarray(padded[first * isz: first * isz + ovl + bl * isz])      # what this rank would upload over its own PCIe link
+        send = torch.zeros(world * bl * cper * M * 2, dtype=torch.float32)
+        recv = torch.zeros_like(send)
+        fe.spectrum_slices(mine.ctypes.data, first, bl, send.data_ptr())
+        dist.all_to_all_single(recv, send)            # NCCL over NVLink on GPUs (bench.py), gloo here
+        fe.process_slices(recv.data_ptr(), B)
+        keep += [mine, send, recv]
+        done += B
+    fe.sync()
+    from dumphfdl_b200 import sharding
+    merged = sharding.gather_pdus(fe.pdus())
+    if rank == 0:
+        q.put((merged, nb * isz))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_spectrum_gloo():
+    """bench.py's N > 1 data path: every rank transforms half of each batch's blocks for all channels, the pass-band
+    slices change hands in an all-to-all, every rank demodulates its own channels; merged PDUs == the oracle's."""
+    import torch.multiprocessing as mp
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "cusim"), "all"], check=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged, used = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    freqs = FREQS + [9931000]
+    x, truth = K.make_capture(250000, freqs, MODES + [3], 3.3, seed=43)
+    ref = K.run_oracle(250000, freqs, x[:used], O.SFMT_CF32).pdus()
+    want = sorted((int(r.sample_cnt_end), int(r.freq), r.data(), int(r.M1), int(r.crc_good)) for r in ref)
+    assert merged == want and len(merged) == 4
