@@ -44,6 +44,7 @@ void cbuffercf_release(cbuffercf q, unsigned int n) __attribute__((weak));
 }
 
 // ---- the block --------------------------------------------------------------------------------------------------
+#define HFDL_SHIM_NRECV 3
 struct gpu_frontend {
 	struct block block;            // must stay first: container_of idiom of fft.c:24 / hfdl.c:596
 	int ngpus;
@@ -53,6 +54,15 @@ struct gpu_frontend {
 	hfdl_gpu_pdu_callback cb; void *cb_user;
 	struct timeval t_start;
 	int64_t delivered;
+	// ngpus > 1, sharded spectrum (include/hfdl_b200.h): GPU d transforms its share of every batch's blocks for all
+	// channels, the pass-band slices change hands over NVLink (peer copies), GPU q demodulates channels q, q + ngpus, ...
+	bool sharded;
+	int device0, nfreq, bmax, recv_i;
+	int64_t blocks_done;
+	std::vector<void *> d_in, d_send;              // per GPU: its samples of a batch / the slices it computed
+	std::vector<void *> d_recv[HFDL_SHIM_NRECV];   // per GPU, rotated: the slices of all blocks for its channels
+	std::vector<cudaStream_t> st, xs;              // per GPU: upload + FFT + sends / hand-over to the demodulator
+	std::vector<cudaEvent_t> ev_up, ev_sent;
 };
 
 static void deliver(gpu_frontend *g) {
@@ -76,6 +86,50 @@ static void deliver(gpu_frontend *g) {
 			g->cb(&p, g->cb_user);
 		}
 	}
+}
+
+// One batch of nb blocks in sharded-spectrum mode.  staging = [overlap | nb * input_size] CF32 samples (pinned).
+static bool sharded_batch(gpu_frontend *g, int nb) {
+	const int G = g->ngpus, cper = g->nfreq / G;
+	const size_t isz = (size_t)g->geom.input_size, ovl = (size_t)g->geom.overlap_length;
+	const size_t slice = (size_t)g->geom.fft_inv_size * 2 * sizeof(float);
+	std::vector<int> n((size_t)G), first((size_t)G);
+	for(int d = 0, at = 0; d < G; d++) { n[(size_t)d] = nb / G + (d < nb % G ? 1 : 0); first[(size_t)d] = at; at += n[(size_t)d]; }
+	// every GPU uploads ITS blocks (plus the overlap in front of them) over its own PCIe link and transforms them
+	for(int d = 0; d < G; d++) {
+		if(n[(size_t)d] == 0) continue;
+		cudaSetDevice(g->device0 + d);
+		const float *src = g->staging + (size_t)first[(size_t)d] * isz * 2;
+		if(cudaMemcpyAsync(g->d_in[(size_t)d], src, (ovl + (size_t)n[(size_t)d] * isz) * 2 * sizeof(float), cudaMemcpyHostToDevice, g->st[(size_t)d]) != cudaSuccess) return false;
+		cudaEventRecord(g->ev_up[(size_t)d], g->st[(size_t)d]);
+		if(hfdl_b200_spectrum_slices(g->fe[(size_t)d], g->d_in[(size_t)d], g->blocks_done + first[(size_t)d], n[(size_t)d], g->d_send[(size_t)d], (void *)g->st[(size_t)d]) < 0) return false;
+	}
+	// the receive buffers rotate; the batch that read this one HFDL_SHIM_NRECV batches ago must be through the channeliser
+	const int slot = g->recv_i++ % HFDL_SHIM_NRECV;
+	for(int q = 0; q < G; q++) if(hfdl_b200_wait_input(g->fe[(size_t)q], HFDL_SHIM_NRECV - 1) < 0) return false;
+	// exchange: sender d's part for receiver q lands at the place of d's blocks in q's [nb][channels][M] array
+	for(int d = 0; d < G; d++) {
+		if(n[(size_t)d] == 0) continue;
+		cudaSetDevice(g->device0 + d);
+		const size_t part = (size_t)n[(size_t)d] * cper * slice;
+		for(int q = 0; q < G; q++) {
+			unsigned char *dst = (unsigned char *)g->d_recv[slot][(size_t)q] + (size_t)first[(size_t)d] * cper * slice;
+			const unsigned char *srcp = (const unsigned char *)g->d_send[(size_t)d] + (size_t)q * part;
+			if(cudaMemcpyPeerAsync(dst, g->device0 + q, srcp, g->device0 + d, part, g->st[(size_t)d]) != cudaSuccess) return false;
+		}
+		cudaEventRecord(g->ev_sent[(size_t)d], g->st[(size_t)d]);
+	}
+	for(int q = 0; q < G; q++) {
+		cudaSetDevice(g->device0 + q);
+		for(int d = 0; d < G; d++) if(n[(size_t)d] > 0) cudaStreamWaitEvent(g->xs[(size_t)q], g->ev_sent[(size_t)d], 0);
+		if(hfdl_b200_process_slices(g->fe[(size_t)q], g->d_recv[slot][(size_t)q], nb, (void *)g->xs[(size_t)q]) < 0) return false;
+	}
+	// the staging buffer is refilled next: the uploads must have left it
+	for(int d = 0; d < G; d++) if(n[(size_t)d] > 0 && cudaEventSynchronize(g->ev_up[(size_t)d]) != cudaSuccess) return false;
+	g->blocks_done += nb;
+	memmove(g->staging, g->staging + (size_t)nb * isz * 2, ovl * 2 * sizeof(float));      // overlap of the next batch
+	cudaSetDevice(g->device0);
+	return true;
 }
 
 // Consumer side of the one2one ring, as fft_thread runs it (fft.c:38-55) -- but nothing here waits for the GPU: the
@@ -110,11 +164,14 @@ static void *gpu_frontend_thread(void *ctx) {
 			if(take > g->staging_samples) take = (unsigned int)(g->staging_samples / isz) * isz;
 			void *rp;
 			cbuffercf_read(cb->buf, take, &rp, &nr);
-			memcpy(g->staging, rp, (size_t)nr * 2 * sizeof(float));
+			// (sharded mode keeps the previous batch's last overlap_length samples in front of the new ones)
+			memcpy(g->staging + (g->sharded ? (size_t)g->geom.overlap_length * 2 : 0), rp, (size_t)nr * 2 * sizeof(float));
 			cbuffercf_release(cb->buf, nr);
 		}
 		pthread_mutex_unlock(cb->mutex);
-		if(nr > 0) {
+		if(nr > 0 && g->sharded) {
+			if(!sharded_batch(g, (int)(nr / isz))) ok = false;
+		} else if(nr > 0) {
 			if(hfdl_b200_push_samples(g->fe[0], g->staging, nr) < 0) ok = false;
 			for(int d = 1; d < g->ngpus && ok; d++) if(hfdl_b200_push_peer(g->fe[(size_t)d], g->fe[0]) < 0) ok = false;
 			for(int d = 0; d < g->ngpus && ok; d++) if(hfdl_b200_submit(g->fe[(size_t)d]) < 0) ok = false;
@@ -123,7 +180,7 @@ static void *gpu_frontend_thread(void *ctx) {
 		if(!ok) { fprintf(stderr, "hfdl_gpu_frontend: GPU processing failed\n"); break; }
 		deliver(g);
 	}
-	for(int d = 0; d < g->ngpus; d++) hfdl_b200_flush(g->fe[(size_t)d]);
+	for(int d = 0; d < g->ngpus; d++) hfdl_b200_flush(g->fe[(size_t)d]);      // (sharded mode: nothing is buffered, this drains the pipelines)
 	deliver(g);
 	block->running = false;
 	return NULL;
@@ -145,6 +202,8 @@ struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_h
 	gpu_frontend *g = new gpu_frontend();
 	memset(&g->block, 0, sizeof(g->block));
 	g->ngpus = ngpus; g->staging = NULL; g->cb = NULL; g->cb_user = NULL; g->delivered = 0;
+	g->device0 = device; g->nfreq = nfreq; g->recv_i = 0; g->blocks_done = 0; g->bmax = 0;
+	g->sharded = ngpus > 1 && nfreq % ngpus == 0 && !getenv("HFDL_B200_SHIM_BROADCAST");
 	for(int d = 0; d < ngpus; d++) {
 		std::vector<int32_t> mine;
 		for(int k = d; k < nfreq; k += ngpus) mine.push_back(freqs_hz[k]);
@@ -164,11 +223,41 @@ struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_h
 	hfdl_b200_get_geometry(g->fe[0], &g->geom);
 	g->staging_samples = (size_t)g->geom.input_size * 8;
 	cudaSetDevice(device);
-	if(cudaMallocHost((void **)&g->staging, g->staging_samples * 2 * sizeof(float)) != cudaSuccess) {
-		for(auto q : g->fe) hfdl_b200_destroy(q);
-		delete g;
+	bool ok = true;
+	if(g->sharded) {
+		// a batch = what one ring read delivers, at most 8 blocks (and at least ngpus, so that every GPU can get one)
+		g->bmax = ngpus > 8 ? ngpus : 8;
+		g->staging_samples = (size_t)g->geom.input_size * (size_t)g->bmax;
+		const size_t isz = (size_t)g->geom.input_size, ovl = (size_t)g->geom.overlap_length, cper = (size_t)(nfreq / ngpus);
+		const size_t slice = (size_t)g->geom.fft_inv_size * 2 * sizeof(float);
+		const size_t share = (size_t)(g->bmax + ngpus - 1) / (size_t)ngpus;           // blocks one GPU transforms per batch
+		g->d_in.assign((size_t)ngpus, nullptr); g->d_send.assign((size_t)ngpus, nullptr);
+		for(int k = 0; k < HFDL_SHIM_NRECV; k++) g->d_recv[k].assign((size_t)ngpus, nullptr);
+		g->st.assign((size_t)ngpus, nullptr); g->xs.assign((size_t)ngpus, nullptr);
+		g->ev_up.assign((size_t)ngpus, nullptr); g->ev_sent.assign((size_t)ngpus, nullptr);
+		for(int d = 0; d < ngpus && ok; d++) {
+			cudaSetDevice(device + d);
+			for(int q = 0; q < ngpus; q++) if(q != d) {
+				int can = 0;
+				if(cudaDeviceCanAccessPeer(&can, device + d, device + q) == cudaSuccess && can && cudaDeviceEnablePeerAccess(device + q, 0) != cudaSuccess) cudaGetLastError();
+			}
+			ok = ok && hfdl_b200_set_exchange(g->fe[(size_t)d], freqs_hz, nfreq, ngpus) == 0;
+			ok = ok && cudaMalloc(&g->d_in[(size_t)d], (ovl + share * isz) * 2 * sizeof(float)) == cudaSuccess;
+			ok = ok && cudaMalloc(&g->d_send[(size_t)d], (size_t)ngpus * share * cper * slice) == cudaSuccess;
+			for(int k = 0; k < HFDL_SHIM_NRECV; k++) ok = ok && cudaMalloc(&g->d_recv[k][(size_t)d], (size_t)g->bmax * cper * slice) == cudaSuccess;
+			ok = ok && cudaStreamCreateWithFlags(&g->st[(size_t)d], cudaStreamNonBlocking) == cudaSuccess;
+			ok = ok && cudaStreamCreateWithFlags(&g->xs[(size_t)d], cudaStreamNonBlocking) == cudaSuccess;
+			ok = ok && cudaEventCreateWithFlags(&g->ev_up[(size_t)d], cudaEventDisableTiming) == cudaSuccess;
+			ok = ok && cudaEventCreateWithFlags(&g->ev_sent[(size_t)d], cudaEventDisableTiming) == cudaSuccess;
+		}
+		cudaSetDevice(device);
+	}
+	const size_t staging_total = g->staging_samples + (g->sharded ? (size_t)g->geom.overlap_length : 0);
+	if(!ok || cudaMallocHost((void **)&g->staging, staging_total * 2 * sizeof(float)) != cudaSuccess) {
+		hfdl_gpu_frontend_destroy(&g->block);
 		return NULL;
 	}
+	memset(g->staging, 0, staging_total * 2 * sizeof(float));
 	g->block.consumer.type = CONSUMER_SINGLE;
 	g->block.consumer.min_ru = (size_t)g->geom.fft_size;
 	g->block.producer.type = PRODUCER_NONE;
@@ -180,7 +269,16 @@ void hfdl_gpu_frontend_destroy(struct block *b) {
 	if(!b) return;
 	gpu_frontend *g = (gpu_frontend *)b;
 	for(auto q : g->fe) hfdl_b200_destroy(q);
-	cudaFreeHost(g->staging);
+	for(size_t d = 0; d < g->d_in.size(); d++) {
+		cudaSetDevice(g->device0 + (int)d);
+		cudaFree(g->d_in[d]); cudaFree(g->d_send[d]);
+		for(int k = 0; k < HFDL_SHIM_NRECV; k++) cudaFree(g->d_recv[k][d]);
+		if(g->st[d]) cudaStreamDestroy(g->st[d]);
+		if(g->xs[d]) cudaStreamDestroy(g->xs[d]);
+		if(g->ev_up[d]) cudaEventDestroy(g->ev_up[d]);
+		if(g->ev_sent[d]) cudaEventDestroy(g->ev_sent[d]);
+	}
+	if(g->staging) cudaFreeHost(g->staging);
 	delete g;
 }
 

@@ -115,6 +115,7 @@ struct hfdl_b200_frontend {
 	std::recursive_mutex mtx;       // every public entry point: the frontend may be driven and queried from different threads
 	bool peer_enabled = false, h2d_pending = false;
 	size_t loop_smem = HFDL_LK_SMEM;  // dynamic shared memory requested for loop_kernel (padding keeps other stages' CTAs off its SMs)
+	bool loop_smem_auto = true;
 	bool failed = false;            // a CUDA call failed mid-pipeline: every later call returns -1
 	int Bsub = 1;                   // blocks per FFT sub-batch (intermediate spectra stay in L2)
 	long long n_out_prev = 0;       // resampled samples of the previous batch (carry source)
@@ -610,8 +611,11 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	{ const char *dbg = getenv("HFDL_B200_DEBUG"); fe->debug_mode = dbg ? atoi(dbg) : 0; }
 	{
 		// loop_kernel's SMs: asking for more shared memory than the bank rings need keeps CTAs with a sizeable shared-memory
-		// footprint (FFT passes, chan_extract, fec) away from the latency-bound warps
+		// footprint (FFT passes, chan_extract, fec) away from the latency-bound warps.  HFDL_B200_LOOP_SMEM_KB sets it
+		// explicitly (0 = no padding); without it, padding is used when the spectrum is sharded over several GPUs (the
+		// other stages then have SMs to spare, hfdl_b200_set_exchange)
 		const char *e = getenv("HFDL_B200_LOOP_SMEM_KB");
+		fe->loop_smem_auto = (e == nullptr);
 		long kb = e ? atol(e) : 0;
 		if(kb > 216) kb = 216;
 		if((size_t)kb * 1024 > fe->loop_smem) fe->loop_smem = (size_t)kb * 1024;
@@ -951,6 +955,7 @@ int32_t hfdl_b200_set_exchange(hfdl_b200_frontend_t *fe, const int32_t *all_freq
 	CK(cudaMemcpy(fe->d_all_offsetbin, ob.data(), sizeof(int) * (size_t)n_all, cudaMemcpyHostToDevice));
 	if(fe->d_mask && build_spec_mask(fe, ob)) return -1;          // the last FFT pass now stores what ANY rank's channels read
 	fe->xr_ranks = nranks; fe->xr_nall = n_all;
+	if(fe->loop_smem_auto && nranks > 1) fe->loop_smem = (size_t)216 * 1024;
 	return 0;
 }
 

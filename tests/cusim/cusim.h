@@ -183,7 +183,7 @@ static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaDeviceSynchronize() { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return 0; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { const char *e = getenv("HFDL_CUSIM_DEVICES"); *n = e ? atoi(e) : 1; return 0; }      // several emulated "devices" share the host memory
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new cusim_event{0}; return 0; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.skipif(not os.path.exists(LIBREF) and not os.path.isdir
                                 reason="oracle/_ref/libref.so (reference block.c compiled in place) not available")
 
 
-def run_driver(libpath, sr, freqs, modes, dur, seed, ngpus=1):
+def run_driver(libpath, sr, freqs, modes, dur, seed, ngpus=1, env=None):
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "cusim"), "all"], check=True)
     O.reflib()
     x, truth = K.make_capture(sr, freqs, modes, dur, seed=seed)
@@ -33,7 +33,7 @@ def run_driver(libpath, sr, freqs, modes, dur, seed, ngpus=1):
         path = f.name
     try:
         out = subprocess.run([os.path.join(HERE, "block_driver"), LIBREF, libpath, path, str(sr), str(K.CF), str(ngpus)] + [str(f) for f in freqs],
-                             capture_output=True, text=True, timeout=900, check=True).stdout
+                             capture_output=True, text=True, timeout=900, check=True, env=dict(os.environ, **(env or {}))).stdout
     finally:
         os.unlink(path)
     rows = [l.split() for l in out.splitlines()]
@@ -69,6 +69,13 @@ def test_block_contract_host_emulation():
     assert run_driver(lib, 250000, [10063000, 9952000], [1, 2], 3.3, seed=31) == 2
 
 
+def test_block_contract_host_emulation_two_devices_sharded_spectrum():
+    # ngpus = 2 on the host emulation (two "devices" sharing the host memory): the sharded-spectrum mode of the wrapper --
+    # each GPU transforms its share of every batch's blocks, slices change hands by peer copies, channels are sharded
+    lib = os.path.join(HERE, "cusim", "libhfdl_cusim.so")
+    assert run_driver(lib, 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, seed=37, ngpus=2, env={"HFDL_CUSIM_DEVICES": "2"}) == 4
+
+
 @pytest.mark.gpu
 def test_block_contract_gpu():
     lib = os.path.join(ROOT, "dumphfdl_b200", "libhfdl_b200.so")
@@ -76,9 +83,13 @@ def test_block_contract_gpu():
 
 
 @pytest.mark.gpu
-def test_block_contract_two_gpus_peer_broadcast():
+def test_block_contract_two_gpus():
     import dumphfdl_b200 as hb
     if hb.load().hfdl_b200_device_count() < 2:
         pytest.skip("needs 2 GPUs")
     lib = os.path.join(ROOT, "dumphfdl_b200", "libhfdl_b200.so")
-    assert run_driver(lib, 2000000, [K.CF + 212000, K.CF - 424000, K.CF + 636000, K.CF - 100000], [3, 5, 0, 2], 5.8, seed=35, ngpus=2) == 4
+    freqs, modes = [K.CF + 212000, K.CF - 424000, K.CF + 636000, K.CF - 100000], [3, 5, 0, 2]
+    # sharded spectrum (4 channels on 2 GPUs: the default), then the capture broadcast (3 channels do not divide by 2; and forced)
+    assert run_driver(lib, 2000000, freqs, modes, 5.8, seed=35, ngpus=2) == 4
+    assert run_driver(lib, 2000000, freqs[:3], modes[:3], 5.8, seed=36, ngpus=2) == 3
+    assert run_driver(lib, 2000000, freqs, modes, 5.8, seed=35, ngpus=2, env={"HFDL_B200_SHIM_BROADCAST": "1"}) == 4
