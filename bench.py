@@ -124,6 +124,27 @@ def to_raw(O, W, x):
     return raw
 
 
+def bind_near_gpu(gpu):
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that the pinned host buffers it allocates (first
+    touch) sit on the GPU's NUMA node and N ranks uploading at once do not all pull from one socket's memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < ncpu:
+            os.sched_setaffinity(0, cpus)
+            return "%d CPUs local to GPU %d" % (len(cpus), idx)
+        return "no distinct CPU set for GPU %d" % idx
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+
+
 def prepare_workload(name, a, world):
     """The workload both arms run: BASELINE's configuration for the GPU count, the sample format, and -- when the
     spectrum is sharded over `world` GPUs -- a slab whose block count divides by `world`."""
@@ -366,6 +387,7 @@ def main():
     import dumphfdl_b200 as hb
     hb.load()
     torch.cuda.set_device(local)
+    numa = bind_near_gpu(local) if world > 1 else None     # before any pinned allocation: first touch decides the NUMA node
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -564,7 +586,9 @@ def main():
                 start_h2d(i + 1)                                       # d_parts[(i+1) % 2] was read by the all-gather of pass i-1, which has completed
                 fe2.process_device(buf.data_ptr(), nsamp, st2["pos"], nblocks)
             else:
-                fe2.push_ptr(h_part.data_ptr(), nsamp)                  # H2D inside the C-ABI call
+                # H2D inside the C-ABI call; the slab is never rewritten, so the call need not wait for its last copy (the PDU
+                # pick-up below then runs beside it); the final flush waits for everything
+                fe2.push_ptr(h_part.data_ptr(), nsamp, wait=False)
             st2["pos"] += nsamp
             st2["i"] += 1
 
@@ -669,6 +693,8 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "kernels": kern, "roofline": roof, "roofline_kernels": roofs,
                 "roofline_pipeline": {"bound": "hbm", "achieved": pipe_ach, "peak": peak, "unit": "GB/s", "frac": pipe_ach / peak, "algorithmic_bytes_per_block": b_blk},
                 "wall_ms_per_step": 1e3 * wall / a.steps}
+        if numa:
+            line["host_binding"] = numa
         if not a.no_cpu_baseline and world == 1:          # the CPU baseline is reported by the single-GPU run only
             line["cpu_baseline"] = cpu_reference(O, W, P, isz, x_part)
         print(json.dumps(line))

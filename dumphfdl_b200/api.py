@@ -57,6 +57,9 @@ def bind(L):
     L.hfdl_b200_destroy.restype = None
     L.hfdl_b200_get_geometry.argtypes = [vp, C.POINTER(Geometry)]
     L.hfdl_b200_push_samples.argtypes = [vp, vp, C.c_int64]
+    L.hfdl_b200_push_samples_nowait.argtypes = [vp, vp, C.c_int64]
+    L.hfdl_b200_wait_host_buffer.argtypes = [vp]
+    L.hfdl_b200_pop_pdus.argtypes = [vp, vp, C.c_int32]
     L.hfdl_b200_flush.argtypes = [vp]
     L.hfdl_b200_process_device.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_int32]
     L.hfdl_b200_sync.argtypes = [vp]
@@ -196,8 +199,8 @@ class Frontend:
             raise RuntimeError("hfdl_b200_push_samples failed")
         return r
 
-    def push_ptr(self, ptr, nsamples):
-        r = self.L.hfdl_b200_push_samples(self.h, ptr, nsamples)
+    def push_ptr(self, ptr, nsamples, wait=True):
+        r = (self.L.hfdl_b200_push_samples if wait else self.L.hfdl_b200_push_samples_nowait)(self.h, ptr, nsamples)
         if r < 0:
             raise RuntimeError("hfdl_b200_push_samples failed")
         return r
@@ -262,13 +265,21 @@ class Frontend:
             raise RuntimeError("hfdl_b200_channel_counters failed")
         return c
 
+    def wait_host_buffer(self):
+        if self.L.hfdl_b200_wait_host_buffer(self.h) != 0:
+            raise RuntimeError("hfdl_b200_wait_host_buffer failed")
+
     def pdus(self):
         out = []
         while True:
-            p = Pdu()
-            if self.L.hfdl_b200_pop_pdu(self.h, C.byref(p)) != 1:
+            n = self.L.hfdl_b200_pdu_count(self.h)
+            if n <= 0:
                 break
-            out.append(p)
+            arr = (Pdu * n)()
+            k = self.L.hfdl_b200_pop_pdus(self.h, arr, n)
+            out.extend(arr[i] for i in range(k))
+            if k < n:
+                break
         return out
 
     def stats(self, ch):

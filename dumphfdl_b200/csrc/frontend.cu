@@ -795,7 +795,7 @@ static int process_pending(hfdl_b200_frontend *fe, bool all) {
 	return done;
 }
 
-int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples) {
+static int32_t push_samples_impl(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples, bool wait_copy) {
 	if(!fe || (!samples && nsamples > 0) || nsamples < 0) return -1;
 	HFDL_API(fe, -1);
 	const auto &g = fe->g;
@@ -828,8 +828,16 @@ int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, in
 		blocks += r;
 	}
 	// the caller may reuse its buffer when this returns: wait for the last H2D copy (not for the processing)
-	if(fe->ev_h2d && blocks >= 0) CK(cudaEventSynchronize(fe->ev_h2d));
+	if(wait_copy && fe->ev_h2d && blocks >= 0) CK(cudaEventSynchronize(fe->ev_h2d));
 	return blocks;
+}
+
+int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples) { return push_samples_impl(fe, samples, nsamples, true); }
+int32_t hfdl_b200_push_samples_nowait(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples) { return push_samples_impl(fe, samples, nsamples, false); }
+int32_t hfdl_b200_wait_host_buffer(hfdl_b200_frontend_t *fe) {
+	HFDL_API(fe, -1);
+	if(fe->ev_h2d) CK(cudaEventSynchronize(fe->ev_h2d));
+	return 0;
 }
 
 // Multi-GPU: dst (another device) takes the samples src has received and dst has not, ring to ring over NVLink
@@ -1023,6 +1031,14 @@ int32_t hfdl_b200_pop_pdu(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdu) {
 	*pdu = fe->pduq.front();
 	fe->pduq.pop_front();
 	return 1;
+}
+
+int32_t hfdl_b200_pop_pdus(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdus, int32_t max) {
+	if(!fe || !pdus || max < 0) return -1;
+	std::lock_guard<std::recursive_mutex> lk(fe->mtx);
+	int32_t n = 0;
+	while(n < max && !fe->pduq.empty()) { pdus[n++] = fe->pduq.front(); fe->pduq.pop_front(); }
+	return n;
 }
 
 // Snapshot of one channel's demodulator state.  It does NOT drain the pipeline (the reference's stats thread reads

@@ -120,6 +120,12 @@ int32_t hfdl_b200_get_geometry(const hfdl_b200_frontend_t *fe, hfdl_b200_geometr
  * running and its PDUs appear in the queue with the next push / flush / sync (the reference's fft and channel
  * threads hand over through a barrier per block, block.c:90-120; the order of PDUs per channel is the same). */
 int32_t hfdl_b200_push_samples(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples);
+/* The same without waiting for the last host-to-device copy: the caller's buffer (pinned memory, or the copy is not
+ * asynchronous) must stay untouched until hfdl_b200_wait_host_buffer returns.  A producer with two staging buffers
+ * fills one while the other is still being copied (complex_samples_produce into a ring does the same for the
+ * reference's consumers, input-helpers.c:80-95). */
+int32_t hfdl_b200_push_samples_nowait(hfdl_b200_frontend_t *fe, const void *samples, int64_t nsamples);
+int32_t hfdl_b200_wait_host_buffer(hfdl_b200_frontend_t *fe);
 /* Process every whole block still buffered (a final partial block is dropped, as in fft.c:41-46) and wait
  * until all PDUs are in the queue. */
 int32_t hfdl_b200_flush(hfdl_b200_frontend_t *fe);
@@ -177,6 +183,8 @@ int64_t hfdl_b200_slice_elems(const hfdl_b200_frontend_t *fe);
 int32_t hfdl_b200_pdu_count(hfdl_b200_frontend_t *fe);
 /* returns 1 and fills *pdu when one is available, 0 when the queue is empty */
 int32_t hfdl_b200_pop_pdu(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdu);
+/* up to max PDUs at once (oldest first); returns how many were written */
+int32_t hfdl_b200_pop_pdus(hfdl_b200_frontend_t *fe, hfdl_b200_pdu_t *pdus, int32_t max);
 int32_t hfdl_b200_channel_noise_floor(hfdl_b200_frontend_t *fe, int32_t channel, float *level_linear);
 /* counters: A1 found, A2 found, M1 found, frames (hfdl.c:162-179) */
 int32_t hfdl_b200_channel_stats(hfdl_b200_frontend_t *fe, int32_t channel, int32_t out[4]);
