@@ -653,7 +653,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
                 tj = json.load(f)
-            if tj.get("workload") == name and tj.get("blocks_per_batch") == nblocks and tj.get("channels") == Cn:
+            if tj.get("workload") == "%s-%s" % (name, W["sfmt"]) and tj.get("blocks_per_batch") == nblocks and tj.get("channels") == Cn and world == 1:
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass

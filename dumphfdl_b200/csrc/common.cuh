@@ -111,8 +111,17 @@ static inline void hfdl_cusim_spin(int line) {      // test build only: yield + 
 	if((++n % 50000000ull) == 0 && getenv("HFDL_CUSIM_WATCHDOG")) fprintf(stderr, "cusim: thread %u block %u still spinning at line %d\n", threadIdx.x, blockIdx.x, line);
 }
 #define HFDL_SPIN_PAUSE() hfdl_cusim_spin(__LINE__)
+#define HFDL_SPIN_PAUSE_LONG() hfdl_cusim_spin(__LINE__)
 #else
 #define HFDL_SPIN_PAUSE() asm volatile("nanosleep.u32 20;" ::: "memory")
+// a waiter that is many symbols ahead of what it waits for (timing warp with a full output ring, loader with chunks in
+// flight): it shares a scheduler with another channel's demodulator warp, so it should not poll every few dozen cycles
+#ifndef HFDL_SPIN_LONG_NS
+#define HFDL_SPIN_LONG_NS 400
+#endif
+#define HFDL_SPIN_STR2(x) #x
+#define HFDL_SPIN_STR(x) HFDL_SPIN_STR2(x)
+#define HFDL_SPIN_PAUSE_LONG() asm volatile("nanosleep.u32 " HFDL_SPIN_STR(HFDL_SPIN_LONG_NS) ";" ::: "memory")
 #endif
 
 // sample formats (src/input-common.h sample_format)

@@ -542,6 +542,26 @@ __global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_last_pass_nat(RowP
 	const cf *wk = a.work + (long long)blk * a.N;
 	cf *out = a.out + (long long)blk * a.N;
 	const int tid = threadIdx.x;
+	const long long kstride = (long long)a.L1 * a.mid;          // natural-index stride of the last digit
+	// Which of this thread's 32 results are stored: result (i, j) is bin bin0 + kstride * (ka + 32 * kb).  The 32 lanes of
+	// a warp hold 32 adjacent bins (r = lane, T >= 32) or whole groups of T, so a granule of HFDL_SPEC_GRAN = 32 bins is
+	// decided by one mask bit; the 32 bits are fetched here, ahead of the row loads, instead of one dependent load in
+	// front of every store.
+	unsigned keep = 0xFFFFFFFFu;
+	if(a.mask) {
+		keep = 0u;
+		const int r2 = tid & (T - 1), kaq = tid >> LGT;
+		const long long bin0 = (k10 + r2) + (long long)a.L1 * kmid;
+#pragma unroll
+		for(int i = 0; i < 32 / B; i++) {
+#pragma unroll
+			for(int j = 0; j < B; j++) {
+				const int ka = kaq + (256 >> LGT) * i;
+				const unsigned g = (unsigned)((bin0 + kstride * (ka + 32 * brev_ct(j, LGB))) >> HFDL_SPEC_LG_GRAN);
+				keep |= ((__ldg(&a.mask[g >> 5]) >> (g & 31u)) & 1u) << (i * B + j);
+			}
+		}
+	}
 	{
 		const int b = tid & (B - 1), r = tid >> LGB;
 		const cf *row = wk + ((long long)(k10 + r) * a.mid + kmid) * L;
@@ -559,9 +579,9 @@ __global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_last_pass_nat(RowP
 		}
 	}
 	__syncthreads();
-	const long long kstride = (long long)a.L1 * a.mid;          // natural-index stride of the last digit
 #pragma unroll
 	for(int i = 0; i < 32 / B; i++) {
+		if(!((keep >> (i * B)) & ((1u << B) - 1u))) continue;      // none of the B results of this group is read by any channel
 		const int p = tid + 256 * i;
 		const int r = p & (T - 1), ka = p >> LGT;
 		cf z[B];
@@ -572,12 +592,7 @@ __global__ void __launch_bounds__(256, HFDL_FFT_REG_MINB) fft_last_pass_nat(RowP
 		cf *o = out + bin0;
 #pragma unroll
 		for(int j = 0; j < B; j++) {
-			const long long off = kstride * (ka + 32 * brev_ct(j, LGB));
-			if(a.mask) {          // channels cover a small part of the band: only the granules some slice reads are written
-				const unsigned g = (unsigned)((bin0 + off) >> HFDL_SPEC_LG_GRAN);
-				if(!((__ldg(&a.mask[g >> 5]) >> (g & 31u)) & 1u)) continue;
-			}
-			o[off] = z[j];
+			if((keep >> (i * B + j)) & 1u) o[kstride * (ka + 32 * brev_ct(j, LGB))] = z[j];
 		}
 	}
 }

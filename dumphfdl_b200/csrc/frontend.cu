@@ -22,6 +22,7 @@
 
 namespace {
 
+enum { LK_PACK4 = 0, LK_ROLE2 = 1, LK_PAIR2 = 2 };
 enum { KC_FFT1 = 0, KC_FFT2, KC_FFT3, KC_CHAN, KC_RESAMP, KC_AGC, KC_BANK, KC_LOOP, KC_FEC, KC_PACK, KC_COUNT };
 const char *kc_names[KC_COUNT] = { "fft_pass1", "fft_pass2", "fft_pass3", "chan_extract", "resamp", "agc", "bank", "loop", "fec", "slice_pack" };
 
@@ -90,7 +91,9 @@ struct FftEngine {
 		CK(cudaFuncSetAttribute(fft_row_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 		CK(cudaFuncSetAttribute(chan_extract, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 		CK(cudaFuncSetAttribute(fec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_FEC_SMEM));
-		CK(cudaFuncSetAttribute(loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+		CK(cudaFuncSetAttribute(loop_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+		CK(cudaFuncSetAttribute(loop_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+		CK(cudaFuncSetAttribute(loop_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
 		return 0;
 	}
 	void destroy() { if(d_tw) cudaFree(d_tw); d_tw = nullptr; }
@@ -114,8 +117,10 @@ struct hfdl_b200_frontend {
 	struct Flight { bool busy = false; } flight[HFDL_NSETS];
 	std::recursive_mutex mtx;       // every public entry point: the frontend may be driven and queried from different threads
 	bool peer_enabled = false, h2d_pending = false;
-	size_t loop_smem = HFDL_LK_SMEM;  // dynamic shared memory requested for loop_kernel (padding keeps other stages' CTAs off its SMs)
-	bool loop_smem_auto = true;
+	// loop_kernel: CTA layout (LK_PACK4 / LK_ROLE2 / LK_PAIR2, loop_kernel.cuh) and extra dynamic shared memory requested
+	// on top of the bank rings (padding keeps other stages' CTAs off its SMs)
+	int loop_layout = LK_PACK4; size_t loop_smem_pad_to = 0;
+	bool loop_auto = true;
 	bool failed = false;            // a CUDA call failed mid-pipeline: every later call returns -1
 	int Bsub = 1;                   // blocks per FFT sub-batch (intermediate spectra stay in L2)
 	long long n_out_prev = 0;       // resampled samples of the previous batch (carry source)
@@ -454,7 +459,12 @@ int run_batch_impl(hfdl_b200_frontend *fe, const RawSource &src0, int nb, const 
 		l.debug_mode = fe->debug_mode;
 		l.dbg_cycles = fe->d_dbg;
 		prof_begin2(fe, KC_LOOP, pr, stl);
-		HFDL_LAUNCH(loop_kernel, dim3((unsigned)((fe->C + HFDL_LK_NCH - 1) / HFDL_LK_NCH)), dim3(HFDL_LK_THREADS), fe->loop_smem, stl, l);
+		const int nch = fe->loop_layout == LK_PACK4 ? 4 : 2;
+		const size_t smem = std::max((size_t)nch * HFDL_LK_SMEM_CH, fe->loop_smem_pad_to);
+		const dim3 grid((unsigned)((fe->C + nch - 1) / nch));
+		if(fe->loop_layout == LK_PACK4) HFDL_LAUNCH((loop_kernel<4, false>), grid, dim3(lk_threads(4, false)), smem, stl, l);
+		else if(fe->loop_layout == LK_ROLE2) HFDL_LAUNCH((loop_kernel<2, true>), grid, dim3(lk_threads(2, true)), smem, stl, l);
+		else HFDL_LAUNCH((loop_kernel<2, false>), grid, dim3(lk_threads(2, false)), smem, stl, l);
 		prof_end2(fe, pr, stl);
 		fe->launches++;
 	}
@@ -610,15 +620,20 @@ int32_t hfdl_b200_create(hfdl_b200_frontend_t **out, const hfdl_b200_config_t *c
 	}
 	{ const char *dbg = getenv("HFDL_B200_DEBUG"); fe->debug_mode = dbg ? atoi(dbg) : 0; }
 	{
-		// loop_kernel's SMs: asking for more shared memory than the bank rings need keeps CTAs with a sizeable shared-memory
-		// footprint (FFT passes, chan_extract, fec) away from the latency-bound warps.  HFDL_B200_LOOP_SMEM_KB sets it
-		// explicitly (0 = no padding); without it, padding is used when the spectrum is sharded over several GPUs (the
-		// other stages then have SMs to spare, hfdl_b200_set_exchange)
-		const char *e = getenv("HFDL_B200_LOOP_SMEM_KB");
-		fe->loop_smem_auto = (e == nullptr);
+		// loop_kernel's CTA layout and SMs.  Asking for more shared memory than the bank rings need keeps CTAs with a sizeable
+		// shared-memory footprint (FFT passes, chan_extract, fec) away from the latency-bound warps.  Defaults: one GPU --
+		// four channels per CTA, no padding (the FFT stream needs the SMs); sharded spectrum over several GPUs
+		// (hfdl_b200_set_exchange) -- two channels per CTA, demodulator warps on schedulers of their own, padded.
+		// HFDL_B200_LOOP_LAYOUT = pack4 | role2 | pair2 and HFDL_B200_LOOP_SMEM_KB (0 = no padding) override.
+		const char *lay = getenv("HFDL_B200_LOOP_LAYOUT"), *e = getenv("HFDL_B200_LOOP_SMEM_KB");
+		fe->loop_auto = (lay == nullptr && e == nullptr);
+#ifdef HFDL_CUSIM
+		fe->loop_layout = LK_PAIR2;                    // host emulation: fewer host threads per CTA
+#endif
+		if(lay) fe->loop_layout = !strcmp(lay, "role2") ? LK_ROLE2 : (!strcmp(lay, "pair2") ? LK_PAIR2 : LK_PACK4);
 		long kb = e ? atol(e) : 0;
 		if(kb > 216) kb = 216;
-		if((size_t)kb * 1024 > fe->loop_smem) fe->loop_smem = (size_t)kb * 1024;
+		fe->loop_smem_pad_to = (size_t)(kb > 0 ? kb : 0) * 1024;
 	}
 	if(cfg->capture_channel >= fe->C) fe->cfg.capture_channel = -1;
 	if(fe->cfg.capture_max < 0) fe->cfg.capture_max = 0;
@@ -963,7 +978,12 @@ int32_t hfdl_b200_set_exchange(hfdl_b200_frontend_t *fe, const int32_t *all_freq
 	CK(cudaMemcpy(fe->d_all_offsetbin, ob.data(), sizeof(int) * (size_t)n_all, cudaMemcpyHostToDevice));
 	if(fe->d_mask && build_spec_mask(fe, ob)) return -1;          // the last FFT pass now stores what ANY rank's channels read
 	fe->xr_ranks = nranks; fe->xr_nall = n_all;
-	if(fe->loop_smem_auto && nranks > 1) fe->loop_smem = (size_t)216 * 1024;
+	if(fe->loop_auto && nranks > 1) {
+#ifndef HFDL_CUSIM
+		fe->loop_layout = LK_ROLE2;
+#endif
+		fe->loop_smem_pad_to = (size_t)216 * 1024;
+	}
 	return 0;
 }
 

@@ -24,18 +24,24 @@
 #include "common.cuh"
 
 #define HFDL_LK_WARPS 3                  // warps per channel: demodulator, timing, loader
-#ifndef HFDL_LK_NCH
-#define HFDL_LK_NCH 4                    // channels per CTA (see "channel packing" below)
-#endif
+#define HFDL_LK_NCH_MAX 4                // most channels a CTA serves (layouts below)
 #define HFDL_LK_CH_THREADS (32 * HFDL_LK_WARPS)
-#define HFDL_LK_THREADS (HFDL_LK_CH_THREADS * HFDL_LK_NCH)
+// CTA layouts (template parameters of loop_kernel; a warp sits on scheduler warp % 4):
+//   <4, false>  four channels, warps [d0 t0 l0 d1 t1 l1 ...]: every scheduler serves one demodulator, one timing and one
+//               loader warp of different channels.  Quarter of the SMs; the demodulator warp shares its scheduler and
+//               shared-memory pipeline with a timing warp (1.41 ms per cfg-3 batch alone on the GPU).
+//   <2, true>   two channels, role-major with two idle warps: [d0 d1 t0 t1 - - l0 l1] -- each demodulator warp has a
+//               scheduler of its own (1.14 ms alone, like one channel per CTA: 1.15 ms).  Half of the SMs; used with the
+//               padded shared-memory request when the other stages have SMs to spare (multi-GPU).
+//   <2, false>  two channels, warps [d0 t0 l0 d1 t1 l1] (host emulation: fewer host threads per CTA).
+__host__ __device__ constexpr int lk_threads(int nch, bool role_major) { return role_major ? 256 : HFDL_LK_CH_THREADS * nch; }
 #define HFDL_LK_RING 64                  // output entries the timing warp may run ahead of the demodulator warp
 #ifndef HFDL_LK_BR
 #define HFDL_LK_BR 128                   // bank ring, input samples (power of two, >= 4 loader chunks)
 #endif
 #define HFDL_LK_CH 32                    // input samples per loader chunk
 #define HFDL_LK_INFLIGHT 3               // loader chunks in flight
-#define HFDL_LK_SMEM (HFDL_LK_NCH * HFDL_LK_BR * 32 * 8)   // dynamic shared memory: one bank ring per channel
+#define HFDL_LK_SMEM_CH (HFDL_LK_BR * 32 * 8)             // dynamic shared memory per channel: its bank ring
 // Channel packing: the sequential warps of a channel are latency-bound and leave their SM's issue slots almost empty, but
 // they are slowed by ~40 % when the schedulers they sit on also serve the FFT / filter-bank CTAs of the other pipeline
 // stages (loop_kernel alone: 1.25 ms per cfg-3 batch; beside the other stages, one channel per SM: 1.75 ms).  Four
@@ -212,7 +218,7 @@ struct LkShared {
 	__align__(8) volatile int tailv[2];          // {sequence number, input-sample index} the demodulator warp has passed
 	volatile int reset_gen, reset_k, reset_seq, ack_gen;
 };
-__shared__ __align__(16) LkShared lk_sh[HFDL_LK_NCH];
+__shared__ __align__(16) LkShared lk_sh[HFDL_LK_NCH_MAX];
 #define lk_ring (sh.ring)
 #define lk_tags (sh.tags)
 #define lk_lvl (sh.lvl)
@@ -573,14 +579,25 @@ __device__ __forceinline__ int demod_run_timed(LkShared &sh, long long *dbg, int
 	return did;
 }
 
-// loop_kernel: grid = ceil(C / HFDL_LK_NCH), block = HFDL_LK_NCH x 96 threads (per channel: warp 0 demodulator, warp 1 timing,
-// warp 2 loader), dynamic smem = one bank ring per channel.
-__global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
-	HFDL_DYN_SMEM(cf, s_bank_all);                  // [HFDL_LK_NCH][HFDL_LK_BR][32]: arms 0..15 matched, 16..31 derivative
-	const int slot = threadIdx.x / HFDL_LK_CH_THREADS, tid = threadIdx.x - slot * HFDL_LK_CH_THREADS;
-	const int c = blockIdx.x * HFDL_LK_NCH + slot;
-	const bool live = c < a.n_channels;
-	const int lane = tid & 31, warp = tid >> 5;
+// loop_kernel<NCH, ROLE_MAJOR>: grid = ceil(C / NCH), block = lk_threads(NCH, ROLE_MAJOR) (per channel: a demodulator, a
+// timing and a loader warp; see "CTA layouts" above), dynamic smem = one bank ring per channel (+ padding).
+template <int NCH, bool ROLE_MAJOR>
+__global__ void __launch_bounds__(lk_threads(NCH, ROLE_MAJOR)) loop_kernel(LoopArgs a) {
+	HFDL_DYN_SMEM(cf, s_bank_all);                  // [NCH][HFDL_LK_BR][32]: arms 0..15 matched, 16..31 derivative
+	int slot, warp, lane;
+	bool idle_warp = false;
+	if(ROLE_MAJOR) {
+		const int wcta = threadIdx.x >> 5;
+		idle_warp = (wcta == 4 || wcta == 5);
+		warp = wcta < 2 ? 0 : (wcta < 4 ? 1 : 2); slot = wcta & 1; lane = threadIdx.x & 31;
+	} else {
+		slot = threadIdx.x / HFDL_LK_CH_THREADS;
+		const int t = threadIdx.x - slot * HFDL_LK_CH_THREADS;
+		warp = t >> 5; lane = t & 31;
+	}
+	const int tid = warp * 32 + lane;               // thread index within the channel's three warps
+	const int c = blockIdx.x * NCH + slot;
+	const bool live = c < a.n_channels && !idle_warp;
 	LkShared &sh = lk_sh[slot];
 	cf *s_bank = s_bank_all + slot * (HFDL_LK_BR * 32);
 	const DemodTables &T = *a.tab;
@@ -595,7 +612,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 		lk_reset_gen = 0; lk_reset_k = 0; lk_reset_seq = 0; lk_ack_gen = 0;
 	}
 	__syncthreads();
-	if(!live) return;                               // the last CTA of a channel count that is not a multiple of HFDL_LK_NCH
+	if(!live) return;                               // idle warps; the last CTA of a channel count that is not a multiple of NCH
 
 	if(warp == 2) {
 		// =========================== loader warp ===========================
@@ -638,7 +655,7 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				}
 				if(!progress) {
 					if(lk_done) break;
-					HFDL_SPIN_PAUSE();
+					HFDL_SPIN_PAUSE_LONG();
 				}
 			}
 		}
@@ -694,8 +711,8 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 			int k_lim = HFDL_UNI(lk_loaded);
 			if(seq >= seq_lim || (!mid && kn >= k_lim)) {
 				if(!t_blocked) t_blocked = hfdl_clock();
-				if(seq >= seq_lim) n_full++; else n_starved++;
-				HFDL_SPIN_PAUSE();
+				if(seq >= seq_lim) { n_full++; HFDL_SPIN_PAUSE_LONG(); }      // a full ring: dozens of symbols ahead of the demodulator
+				else { n_starved++; HFDL_SPIN_PAUSE(); }
 				continue;
 			}
 			if(t_blocked) { t_wait += hfdl_clock() - t_blocked; t_blocked = 0; }
@@ -756,7 +773,10 @@ __global__ void __launch_bounds__(HFDL_LK_THREADS) loop_kernel(LoopArgs a) {
 				if(seq != seq_in || rare) continue;
 				// no pair fitted: the ring is full or the loader is less than 4 samples ahead -> poll again; only the last
 				// samples of the batch (everything is loaded) go through the generic stepping below
-				if(seq + 2 > seq_lim2 || k_lim2 < N || kn >= N) { if(kn < N) HFDL_SPIN_PAUSE(); continue; }
+				if(seq + 2 > seq_lim2 || k_lim2 < N || kn >= N) {
+					if(kn < N) { if(seq + 2 > seq_lim2) HFDL_SPIN_PAUSE_LONG(); else HFDL_SPIN_PAUSE(); }
+					continue;
+				}
 			}
 			// ---------------- generic stepping (after a reset, odd alignment, rare cases) ----------------
 			if(!mid) {

@@ -24,6 +24,7 @@ lines = ["# ncu --set full --clock-control none captures, %s (B200, %s bench: %d
          "| kernel | grid x block | regs | duration ms | dram read MB | dram write MB | dram % of peak | L2 hit % | sm throughput % | warps active % | warp instr |",
          "|---|---|---|---|---|---|---|---|---|---|---|"]
 traffic, count = {}, {}
+col_seen = 0             # column passes seen since the last "last pass": the first is pass 1, the second pass 2
 for d in rows:
     kn = d['Kernel Name'].split('(')[0].replace('void ', '').strip()
     u = d['_units']
@@ -34,11 +35,18 @@ for d in rows:
         float(d['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed']), d.get('lts__t_sector_hit_rate.pct', '-'), float(d['sm__throughput.avg.pct_of_peak_sustained_elapsed']),
         float(d['sm__warps_active.avg.pct_of_peak_sustained_active']), float(d.get('smsp__inst_executed.sum', 0))))
     cls = name_map.get(kn.split('<')[0], kn)
+    if cls == 'fft_pass':
+        col_seen += 1
+        cls = 'fft_pass%d' % col_seen
+    elif cls == 'fft_last_pass':
+        cls = 'fft_pass%d' % (col_seen + 1)
+        col_seen = 0
     traffic[cls] = traffic.get(cls, 0) + int(rd + wr)
     count[cls] = count.get(cls, 0) + 1
 open(os.path.join(HERE, tag + '_ncu_summary.md'), 'w').write("\n".join(lines) + "\n")
 json.dump({"workload": workload, "blocks_per_batch": nblocks, "channels": nch,
            "source": "ncu --set full --clock-control none, the launches of one batch inside `python bench.py --steps 1 --warmup 3 --loops 1 --no-cpu-baseline --skip-e2e` "
                      "(profiles/%s_ncu_summary.md); dram__bytes_read.sum + dram__bytes_write.sum, summed over the launches of a class within the batch" % tag,
-           "launches_in_capture": count, "dram_bytes_per_batch": traffic}, open(os.path.join(HERE, tag + '_traffic.json'), 'w'), indent=1)
+           "launches_in_capture": count, "dram_bytes_per_batch": traffic,
+           "dram_bytes_per_launch": {k: int(v / count[k]) for k, v in traffic.items()}}, open(os.path.join(HERE, tag + '_traffic.json'), 'w'), indent=1)
 print("\n".join(lines[5:]))

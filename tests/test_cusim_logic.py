@@ -72,3 +72,10 @@ def test_pruned_spectrum_equals_full(sim):
 def test_sharded_spectrum_two_ranks(sim):
     # multi-GPU data path (FFT blocks sharded, slices exchanged, channels sharded) on the host emulation: PDUs == one frontend's
     assert K.case_sharded_spectrum(sim, K.HostMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4) == 4
+
+
+def test_loop_kernel_layouts_agree(sim, monkeypatch):
+    # the three CTA layouts of loop_kernel (pack4: four channels per CTA; role2: two, role-major with idle warps; pair2) give the same PDUs
+    for lay in ("role2", "pack4"):
+        monkeypatch.setenv("HFDL_B200_LOOP_LAYOUT", lay)
+        assert K.case_frontend(sim, 250000, [10063000, 9952000, 10101000], [3, 0, 2], 3.2, batch=3, seed=6) == 3
