@@ -154,8 +154,10 @@ def prepare_workload(name, a, world):
     if a.sample_format:
         W["sfmt"] = a.sample_format
     W["multi"] = a.multi if world > 1 else "single"
-    if world > 1 and a.multi == "sharded":
-        W["blocks_per_slot"] = -(-W["blocks_per_slot"] // world) * world
+    if world > 1 and W["nch"] % world:
+        W["multi"] = "broadcast"                       # the sharded spectrum wants the same number of channels on every GPU
+    if world > 1:
+        W["blocks_per_slot"] = -(-W["blocks_per_slot"] // world) * world      # every rank renders / uploads / transforms whole blocks
     return W
 
 

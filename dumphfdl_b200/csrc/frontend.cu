@@ -1214,21 +1214,49 @@ int64_t hfdl_b200_read_checkpoint(hfdl_b200_frontend_t *fe, int32_t what, int32_
 }
 
 // ---------------- stage entry points ----------------
+}  // extern "C"
+
+namespace {
+// Device allocations, stream, FFT engine and tables of a stage entry point: released on EVERY return path (the CK macro
+// returns early on a CUDA error).
+struct Scratch {
+	std::vector<void *> dev;
+	cudaStream_t st = nullptr;
+	FftEngine eng; bool eng_up = false;
+	DemodTables *T = nullptr;
+	template <typename P> cudaError_t alloc(P **p, size_t bytes) {
+		cudaError_t e = cudaMalloc((void **)p, bytes);
+		if(e == cudaSuccess) dev.push_back((void *)*p);
+		return e;
+	}
+	~Scratch() {
+		for(void *p : dev) cudaFree(p);
+		if(st) cudaStreamDestroy(st);
+		if(eng_up) eng.destroy();
+		delete T;
+	}
+};
+}  // namespace
+
+extern "C" {
+
 int32_t hfdl_b200_fft_forward(int32_t device, const void *in, void *outp, int32_t n, int32_t batch) {
 	if(!in || !outp || n < 2 || (n & (n - 1)) || batch < 1 || hfdl_b200_device_count() < 1) return -1;
 	CK(cudaSetDevice(device));
-	FftEngine eng;
+	Scratch S;
+	FftEngine &eng = S.eng;
+	S.eng_up = true;
 	if(eng.init()) return -1;
 	FftPlan pl = make_plan(n);
 	cf *d_in = nullptr, *d_work = nullptr, *d_spec = nullptr, *d_out = nullptr;
 	size_t bytes = sizeof(cf) * (size_t)n * (size_t)batch;
-	CK(cudaMalloc((void **)&d_in, bytes)); CK(cudaMalloc((void **)&d_work, bytes)); CK(cudaMalloc((void **)&d_out, sizeof(cf) * (size_t)n));
-	if(pl.natural) CK(cudaMalloc((void **)&d_spec, bytes));
+	CK(S.alloc(&d_in, bytes)); CK(S.alloc(&d_work, bytes)); CK(S.alloc(&d_out, sizeof(cf) * (size_t)n));
+	if(pl.natural) CK(S.alloc(&d_spec, bytes));
 	CK(cudaMemcpy(d_in, in, bytes, cudaMemcpyHostToDevice));
 	RawSource src;
 	src.base = d_in; src.ring_len = (long long)n * batch; src.pos0 = 0; src.ring_origin = 0; src.block_stride = n; src.sfmt = HFDL_SFMT_CF32;
-	cudaStream_t st = nullptr;
-	CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&S.st, cudaStreamNonBlocking));
+	cudaStream_t st = S.st;
 	int rc = run_fft(nullptr, eng, pl, src, d_work, d_spec, batch, st);
 	for(int b = 0; b < batch && rc == 0; b++) {
 		HFDL_LAUNCH(fft_gather_bins, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, pl.natural ? d_spec : d_work, pl, b, 0, n, d_out);
@@ -1236,9 +1264,6 @@ int32_t hfdl_b200_fft_forward(int32_t device, const void *in, void *outp, int32_
 		if(cudaMemcpy((cf *)outp + (size_t)b * n, d_out, sizeof(cf) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
 	}
 	if(cudaGetLastError() != cudaSuccess) rc = -1;
-	cudaStreamDestroy(st);
-	cudaFree(d_in); cudaFree(d_work); cudaFree(d_spec); cudaFree(d_out);
-	eng.destroy();
 	return rc;
 }
 
@@ -1247,33 +1272,34 @@ static int fec_run(int device, const void *symbols, const uint8_t *vin, int nfra
 	if(nframes < 1 || hfdl_b200_device_count() < 1) return -1;
 	CK(cudaSetDevice(device));
 	CK(cudaFuncSetAttribute(fec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HFDL_FEC_SMEM));
-	DemodTables *T = new DemodTables();
+	Scratch S;
+	DemodTables *T = S.T = new DemodTables();
 	hfdl_design::demod_tables(*T);
 	DemodTables *d_tab = nullptr; FrameRec *d_fr = nullptr; int *d_n = nullptr; PduRec *d_p = nullptr; cf *d_sym = nullptr;
 	unsigned char *d_soft = nullptr, *d_vin = nullptr;
-	CK(cudaMalloc((void **)&d_tab, sizeof(DemodTables)));
+	CK(S.alloc(&d_tab, sizeof(DemodTables)));
 	CK(cudaMemcpy(d_tab, T, sizeof(DemodTables), cudaMemcpyHostToDevice));
 	std::vector<FrameRec> fr((size_t)nframes);
 	for(int q = 0; q < nframes; q++) {
 		memset(&fr[(size_t)q], 0, sizeof(FrameRec));
 		fr[(size_t)q].channel = q / HFDL_FRAME_SLOTS_MIN; fr[(size_t)q].slot = q % HFDL_FRAME_SLOTS_MIN; fr[(size_t)q].M1 = M1; fr[(size_t)q].bitmask = bitmask;
 	}
-	CK(cudaMalloc((void **)&d_fr, sizeof(FrameRec) * (size_t)nframes));
+	CK(S.alloc(&d_fr, sizeof(FrameRec) * (size_t)nframes));
 	CK(cudaMemcpy(d_fr, fr.data(), sizeof(FrameRec) * (size_t)nframes, cudaMemcpyHostToDevice));
-	CK(cudaMalloc((void **)&d_n, sizeof(int)));
+	CK(S.alloc(&d_n, sizeof(int)));
 	CK(cudaMemcpy(d_n, &nframes, sizeof(int), cudaMemcpyHostToDevice));
-	CK(cudaMalloc((void **)&d_p, sizeof(PduRec) * (size_t)nframes));
+	CK(S.alloc(&d_p, sizeof(PduRec) * (size_t)nframes));
 	int nsym = T->mode_segments[M1] * 30;
 	if(symbols) {
-		CK(cudaMalloc((void **)&d_sym, sizeof(cf) * (size_t)nframes * HFDL_DATA_SYMS_MAX));
+		CK(S.alloc(&d_sym, sizeof(cf) * (size_t)nframes * HFDL_DATA_SYMS_MAX));
 		for(int q = 0; q < nframes; q++)
 			CK(cudaMemcpy(d_sym + (size_t)q * HFDL_DATA_SYMS_MAX, (const cf *)symbols + (size_t)q * nsym, sizeof(cf) * (size_t)nsym, cudaMemcpyHostToDevice));
 	}
 	if(vin) {
-		CK(cudaMalloc((void **)&d_vin, (size_t)nframes * 2 * nbits));
+		CK(S.alloc(&d_vin, (size_t)nframes * 2 * nbits));
 		CK(cudaMemcpy(d_vin, vin, (size_t)nframes * 2 * nbits, cudaMemcpyHostToDevice));
 	}
-	if(soft_out) CK(cudaMalloc((void **)&d_soft, (size_t)nframes * HFDL_FEC_VIN_MAX));
+	if(soft_out) CK(S.alloc(&d_soft, (size_t)nframes * HFDL_FEC_VIN_MAX));
 	FecArgs a;
 	a.frames = d_fr; a.nframes = d_n; a.max_frames = nframes; a.datasym = d_sym; a.nslots = HFDL_FRAME_SLOTS_MIN; a.tab = d_tab; a.pdus = d_p; a.soft_out = d_soft;
 	a.vin_direct = d_vin; a.vin_nbits = nbits;
@@ -1288,8 +1314,6 @@ static int fec_run(int device, const void *symbols, const uint8_t *vin, int nfra
 		if(crc_out) crc_out[q] = out[(size_t)q].crc_good;
 	}
 	if(soft_out) CK(cudaMemcpy(soft_out, d_soft, (size_t)nframes * HFDL_FEC_VIN_MAX, cudaMemcpyDeviceToHost));
-	cudaFree(d_tab); cudaFree(d_fr); cudaFree(d_n); cudaFree(d_p); cudaFree(d_sym); cudaFree(d_soft); cudaFree(d_vin);
-	delete T;
 	return 0;
 }
 
