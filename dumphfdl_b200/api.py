@@ -69,6 +69,7 @@ def bind(L):
     L.hfdl_b200_poll.argtypes = [vp]
     L.hfdl_b200_set_exchange.argtypes = [vp, C.POINTER(C.c_int32), C.c_int32, C.c_int32]
     L.hfdl_b200_spectrum_slices.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp]
+    L.hfdl_b200_spectrum_slices_to.argtypes = [vp, vp, C.c_int64, C.c_int32, C.POINTER(vp), C.c_int32, vp]
     L.hfdl_b200_process_slices.argtypes = [vp, vp, C.c_int32, vp]
     L.hfdl_b200_slice_elems.argtypes = [vp]
     L.hfdl_b200_slice_elems.restype = C.c_int64
@@ -226,6 +227,13 @@ class Frontend:
         r = self.L.hfdl_b200_spectrum_slices(self.h, d_samples, first_block, nblocks, d_send, stream)
         if r < 0:
             raise RuntimeError("hfdl_b200_spectrum_slices failed")
+        return r
+
+    def spectrum_slices_to(self, d_samples, first_block, nblocks, recv_ptrs, batch_block0, stream=None):
+        arr = (C.c_void_p * len(recv_ptrs))(*recv_ptrs)
+        r = self.L.hfdl_b200_spectrum_slices_to(self.h, d_samples, first_block, nblocks, arr, batch_block0, stream)
+        if r < 0:
+            raise RuntimeError("hfdl_b200_spectrum_slices_to failed")
         return r
 
     def process_slices(self, d_slices, nblocks, stream=None):

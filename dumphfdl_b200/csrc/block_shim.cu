@@ -57,6 +57,7 @@ struct gpu_frontend {
 	// ngpus > 1, sharded spectrum (include/hfdl_b200.h): GPU d transforms its share of every batch's blocks for all
 	// channels, the pass-band slices change hands over NVLink (peer copies), GPU q demodulates channels q, q + ngpus, ...
 	bool sharded;
+	bool direct;                                   // every GPU can store into every other GPU's memory: the pack kernel writes the receive buffers itself
 	int device0, nfreq, bmax, recv_i;
 	int64_t blocks_done;
 	std::vector<void *> d_in, d_send;              // per GPU: its samples of a batch / the slices it computed
@@ -95,27 +96,29 @@ static bool sharded_batch(gpu_frontend *g, int nb) {
 	const size_t slice = (size_t)g->geom.fft_inv_size * 2 * sizeof(float);
 	std::vector<int> n((size_t)G), first((size_t)G);
 	for(int d = 0, at = 0; d < G; d++) { n[(size_t)d] = nb / G + (d < nb % G ? 1 : 0); first[(size_t)d] = at; at += n[(size_t)d]; }
-	// every GPU uploads ITS blocks (plus the overlap in front of them) over its own PCIe link and transforms them
+	// the receive buffers rotate; the batch that read this one HFDL_SHIM_NRECV batches ago must be through the channeliser
+	const int slot = g->recv_i++ % HFDL_SHIM_NRECV;
+	for(int q = 0; q < G; q++) if(hfdl_b200_wait_input(g->fe[(size_t)q], HFDL_SHIM_NRECV - 1) < 0) return false;
+	// every GPU uploads ITS blocks (plus the overlap in front of them) over its own PCIe link and transforms them; the
+	// slices of GPU q's channels go to q's [nb][channels][M] array at the place of the sender's blocks -- stored there by
+	// the pack kernel itself over NVLink (peer access), or packed locally and copied device to device
 	for(int d = 0; d < G; d++) {
 		if(n[(size_t)d] == 0) continue;
 		cudaSetDevice(g->device0 + d);
 		const float *src = g->staging + (size_t)first[(size_t)d] * isz * 2;
 		if(cudaMemcpyAsync(g->d_in[(size_t)d], src, (ovl + (size_t)n[(size_t)d] * isz) * 2 * sizeof(float), cudaMemcpyHostToDevice, g->st[(size_t)d]) != cudaSuccess) return false;
 		cudaEventRecord(g->ev_up[(size_t)d], g->st[(size_t)d]);
-		if(hfdl_b200_spectrum_slices(g->fe[(size_t)d], g->d_in[(size_t)d], g->blocks_done + first[(size_t)d], n[(size_t)d], g->d_send[(size_t)d], (void *)g->st[(size_t)d]) < 0) return false;
-	}
-	// the receive buffers rotate; the batch that read this one HFDL_SHIM_NRECV batches ago must be through the channeliser
-	const int slot = g->recv_i++ % HFDL_SHIM_NRECV;
-	for(int q = 0; q < G; q++) if(hfdl_b200_wait_input(g->fe[(size_t)q], HFDL_SHIM_NRECV - 1) < 0) return false;
-	// exchange: sender d's part for receiver q lands at the place of d's blocks in q's [nb][channels][M] array
-	for(int d = 0; d < G; d++) {
-		if(n[(size_t)d] == 0) continue;
-		cudaSetDevice(g->device0 + d);
-		const size_t part = (size_t)n[(size_t)d] * cper * slice;
-		for(int q = 0; q < G; q++) {
-			unsigned char *dst = (unsigned char *)g->d_recv[slot][(size_t)q] + (size_t)first[(size_t)d] * cper * slice;
-			const unsigned char *srcp = (const unsigned char *)g->d_send[(size_t)d] + (size_t)q * part;
-			if(cudaMemcpyPeerAsync(dst, g->device0 + q, srcp, g->device0 + d, part, g->st[(size_t)d]) != cudaSuccess) return false;
+		if(g->direct) {
+			if(hfdl_b200_spectrum_slices_to(g->fe[(size_t)d], g->d_in[(size_t)d], g->blocks_done + first[(size_t)d], n[(size_t)d],
+					g->d_recv[slot].data(), first[(size_t)d], (void *)g->st[(size_t)d]) < 0) return false;
+		} else {
+			if(hfdl_b200_spectrum_slices(g->fe[(size_t)d], g->d_in[(size_t)d], g->blocks_done + first[(size_t)d], n[(size_t)d], g->d_send[(size_t)d], (void *)g->st[(size_t)d]) < 0) return false;
+			const size_t part = (size_t)n[(size_t)d] * cper * slice;
+			for(int q = 0; q < G; q++) {
+				unsigned char *dst = (unsigned char *)g->d_recv[slot][(size_t)q] + (size_t)first[(size_t)d] * cper * slice;
+				const unsigned char *srcp = (const unsigned char *)g->d_send[(size_t)d] + (size_t)q * part;
+				if(cudaMemcpyPeerAsync(dst, g->device0 + q, srcp, g->device0 + d, part, g->st[(size_t)d]) != cudaSuccess) return false;
+			}
 		}
 		cudaEventRecord(g->ev_sent[(size_t)d], g->st[(size_t)d]);
 	}
@@ -204,6 +207,7 @@ struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_h
 	g->ngpus = ngpus; g->staging = NULL; g->cb = NULL; g->cb_user = NULL; g->delivered = 0;
 	g->device0 = device; g->nfreq = nfreq; g->recv_i = 0; g->blocks_done = 0; g->bmax = 0;
 	g->sharded = ngpus > 1 && nfreq % ngpus == 0 && !getenv("HFDL_B200_SHIM_BROADCAST");
+	g->direct = g->sharded && !getenv("HFDL_B200_SHIM_COPY");
 	for(int d = 0; d < ngpus; d++) {
 		std::vector<int32_t> mine;
 		for(int k = d; k < nfreq; k += ngpus) mine.push_back(freqs_hz[k]);
@@ -239,7 +243,8 @@ struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_h
 			cudaSetDevice(device + d);
 			for(int q = 0; q < ngpus; q++) if(q != d) {
 				int can = 0;
-				if(cudaDeviceCanAccessPeer(&can, device + d, device + q) == cudaSuccess && can && cudaDeviceEnablePeerAccess(device + q, 0) != cudaSuccess) cudaGetLastError();
+				if(cudaDeviceCanAccessPeer(&can, device + d, device + q) != cudaSuccess || !can) { g->direct = false; continue; }
+				if(cudaDeviceEnablePeerAccess(device + q, 0) != cudaSuccess) cudaGetLastError();      // "already enabled" is fine
 			}
 			ok = ok && hfdl_b200_set_exchange(g->fe[(size_t)d], freqs_hz, nfreq, ngpus) == 0;
 			ok = ok && cudaMalloc(&g->d_in[(size_t)d], (ovl + share * isz) * 2 * sizeof(float)) == cudaSuccess;

@@ -666,18 +666,22 @@ __global__ void __launch_bounds__(HFDL_FFT_THREADS) chan_extract(ChanArgs a) {
 
 // Sharded spectrum (multi-GPU, one rank transforms a share of the blocks for every rank's channels): the pass-band slice
 // of channel j of the WHOLE job's channel list (M bins around offsetbin[j], inverse-FFT input order -- exactly what
-// chan_extract multiplies with the tap slice) goes to the send buffer of the rank that owns the channel:
-//   send[owner = j % R][block b][local channel j / R][M],   grid = (n_all, nb).
-// The exchange (all-to-all over NVLink) then leaves every rank with [all blocks of the batch][its channels][M].
-__global__ void slice_pack(const cf *spec, FftPlan pl, int M, const int *offsetbin, int nranks, int nb, cf *send) {
+// chan_extract multiplies with the tap slice) goes to the rank that owns the channel:
+//   dst.base[owner = j % R] + ((dst.blk0 + block b) * (C_all / R) + local channel j / R) * M,   grid = (n_all, nb).
+// dst.base[q] is either part q of a local send buffer (an all-to-all then delivers it) or rank q's receive buffer itself
+// (peer memory in a one-process multi-GPU setup: the stores cross NVLink straight from this kernel, no copy follows).
+// Either way every rank ends up with [all blocks of the batch][its channels][M].
+#define HFDL_MAX_RANKS 16
+struct SliceDst { cf *base[HFDL_MAX_RANKS]; long long blk0; };
+__global__ void slice_pack(const cf *spec, FftPlan pl, int M, const int *offsetbin, int nranks, SliceDst dst) {
 	const int j = blockIdx.x, b = blockIdx.y;
 	const int owner = j % nranks, local = j / nranks, cper = gridDim.x / nranks;
 	const int off = offsetbin[j];
 	const cf *W = spec + (long long)b * pl.N;
-	cf *dst = send + (((long long)owner * nb + b) * cper + local) * M;
+	cf *out = dst.base[owner] + ((dst.blk0 + b) * cper + local) * M;
 	for(int i = threadIdx.x; i < M; i += blockDim.x) {
 		const int sg = i < M / 2 ? i : i - M;
-		dst[i] = W[fft_bin_addr(pl, (off + sg) & (pl.N - 1))];
+		out[i] = W[fft_bin_addr(pl, (off + sg) & (pl.N - 1))];
 	}
 }
 

@@ -964,7 +964,7 @@ int32_t hfdl_b200_process_device(hfdl_b200_frontend_t *fe, const void *d_samples
 // ---- sharded spectrum (multi-GPU): every rank transforms a share of the overlap-save blocks for ALL channels of the job
 // and demodulates its own channels for ALL blocks; in between, the pass-band slices change hands (all-to-all over NVLink)
 int32_t hfdl_b200_set_exchange(hfdl_b200_frontend_t *fe, const int32_t *all_freqs_hz, int32_t n_all, int32_t nranks) {
-	if(!fe || !all_freqs_hz || nranks < 1 || n_all < nranks || n_all % nranks != 0) return -1;
+	if(!fe || !all_freqs_hz || nranks < 1 || nranks > HFDL_MAX_RANKS || n_all < nranks || n_all % nranks != 0) return -1;
 	HFDL_API(fe, -1);
 	if(n_all / nranks != fe->C) { fprintf(stderr, "hfdl_b200_set_exchange: this frontend has %d channels, the job gives every rank %d\n", fe->C, n_all / nranks); return -1; }
 	if(drain(fe)) return -1;
@@ -987,10 +987,7 @@ int32_t hfdl_b200_set_exchange(hfdl_b200_frontend_t *fe, const int32_t *all_freq
 	return 0;
 }
 
-int32_t hfdl_b200_spectrum_slices(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t first_block, int32_t nblocks, void *d_send, void *cuda_stream) {
-	if(!fe || !d_samples || !d_send || nblocks < 1 || first_block < 0) return -1;
-	HFDL_API(fe, -1);
-	if(fe->xr_ranks < 1 || nblocks > fe->Bmax) return -1;
+static int32_t spectrum_slices_impl(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t first_block, int32_t nblocks, const SliceDst &dst, void *cuda_stream) {
 	const auto &g = fe->g;
 	cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : fe->stream;
 	// the buffer holds stream positions [first_block * input_size - overlap, (first_block + nblocks) * input_size): as a "ring"
@@ -1011,11 +1008,35 @@ int32_t hfdl_b200_spectrum_slices(hfdl_b200_frontend_t *fe, const void *d_sample
 	}
 	prof_begin2(fe, KC_PACK, pr, st);
 	HFDL_LAUNCH(slice_pack, dim3((unsigned)fe->xr_nall, (unsigned)nblocks), dim3(256), 0, st,
-		fe->plan.natural ? fe->d_spec : fe->d_work, fe->plan, g.fft_inv_size, fe->d_all_offsetbin, fe->xr_ranks, nblocks, (cf *)d_send);
+		fe->plan.natural ? fe->d_spec : fe->d_work, fe->plan, g.fft_inv_size, fe->d_all_offsetbin, fe->xr_ranks, dst);
 	prof_end2(fe, pr, st);
 	fe->launches++;
 	CK(cudaGetLastError());
 	return nblocks;
+}
+
+int32_t hfdl_b200_spectrum_slices(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t first_block, int32_t nblocks, void *d_send, void *cuda_stream) {
+	if(!fe || !d_samples || !d_send || nblocks < 1 || first_block < 0) return -1;
+	HFDL_API(fe, -1);
+	if(fe->xr_ranks < 1 || nblocks > fe->Bmax) return -1;
+	SliceDst dst;
+	memset(&dst, 0, sizeof(dst));
+	const long long part = (long long)nblocks * (fe->xr_nall / fe->xr_ranks) * fe->g.fft_inv_size;
+	for(int q = 0; q < fe->xr_ranks; q++) dst.base[q] = (cf *)d_send + (long long)q * part;
+	dst.blk0 = 0;
+	return spectrum_slices_impl(fe, d_samples, first_block, nblocks, dst, cuda_stream);
+}
+
+int32_t hfdl_b200_spectrum_slices_to(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t first_block, int32_t nblocks,
+		void *const *d_recv_of_rank, int32_t batch_block0, void *cuda_stream) {
+	if(!fe || !d_samples || !d_recv_of_rank || nblocks < 1 || first_block < 0 || batch_block0 < 0) return -1;
+	HFDL_API(fe, -1);
+	if(fe->xr_ranks < 1 || nblocks > fe->Bmax) return -1;
+	SliceDst dst;
+	memset(&dst, 0, sizeof(dst));
+	for(int q = 0; q < fe->xr_ranks; q++) { if(!d_recv_of_rank[q]) return -1; dst.base[q] = (cf *)d_recv_of_rank[q]; }
+	dst.blk0 = batch_block0;
+	return spectrum_slices_impl(fe, d_samples, first_block, nblocks, dst, cuda_stream);
 }
 
 int32_t hfdl_b200_process_slices(hfdl_b200_frontend_t *fe, const void *d_slices, int32_t nblocks, void *cuda_stream) {

@@ -177,6 +177,12 @@ int32_t hfdl_b200_busy(hfdl_b200_frontend_t *fe);
 int32_t hfdl_b200_set_exchange(hfdl_b200_frontend_t *fe, const int32_t *all_freqs_hz, int32_t n_all, int32_t nranks);
 int32_t hfdl_b200_spectrum_slices(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t first_block, int32_t nblocks,
 		void *d_send, void *cuda_stream);
+/* The same with the exchange fused into the kernel (one process, peer access enabled between the GPUs): the slices of
+ * rank q's channels are stored straight into d_recv_of_rank[q] -- rank q's [batch blocks][channels][fft_inv_size] array,
+ * peer memory for q != this rank -- at block position batch_block0 + (0 .. nblocks-1).  The stores cross NVLink from
+ * inside the pack kernel; no copy follows, an event on cuda_stream tells the receivers when to go on. */
+int32_t hfdl_b200_spectrum_slices_to(hfdl_b200_frontend_t *fe, const void *d_samples, int64_t first_block, int32_t nblocks,
+		void *const *d_recv_of_rank, int32_t batch_block0, void *cuda_stream);
 int32_t hfdl_b200_process_slices(hfdl_b200_frontend_t *fe, const void *d_slices, int32_t nblocks, void *cuda_stream);
 int64_t hfdl_b200_slice_elems(const hfdl_b200_frontend_t *fe);
 

@@ -329,10 +329,11 @@ class CudaMem:
         self.t.cuda.synchronize()
 
 
-def case_sharded_spectrum(lib, mem, sr, freqs, modes, dur, nranks, batch, sfmt=A.SFMT_CF32, seed=71, starts=None):
+def case_sharded_spectrum(lib, mem, sr, freqs, modes, dur, nranks, batch, sfmt=A.SFMT_CF32, seed=71, starts=None, direct=False):
     """Multi-GPU data path on ONE device: `nranks` frontends, rank r owning the channels freqs[r::nranks].  Per batch every
     rank transforms its share of the blocks for all channels (hfdl_b200_spectrum_slices), the slices change hands (here:
     plain copies standing in for the all-to-all) and every rank demodulates its channels (hfdl_b200_process_slices).
+    direct = True: hfdl_b200_spectrum_slices_to -- the pack kernel stores into every rank's receive buffer itself.
     The PDUs must be those of one frontend that owns all channels (and the oracle's)."""
     assert batch % nranks == 0 and len(freqs) % nranks == 0
     x, truth = make_capture(sr, freqs, modes, dur, seed=seed, starts=starts)
@@ -363,22 +364,26 @@ def case_sharded_spectrum(lib, mem, sr, freqs, modes, dur, nranks, batch, sfmt=A
         B = min(batch, nb - done)
         bl = B // nranks
         sends = []
+        recvs = [mem.empty(B * cper * slice_bytes) for _ in fes]
         for r, fe in enumerate(fes):
             first = done + r * bl
             buf = mem.upload(padded[first * isz * bps: (first * isz + ovl + bl * isz) * bps])
+            keep.append(buf)
+            if direct:
+                fe.spectrum_slices_to(mem.ptr(buf), first, bl, [mem.ptr(h) for h in recvs], r * bl)
+                continue
             send = mem.empty(nranks * bl * cper * slice_bytes)
             fe.spectrum_slices(mem.ptr(buf), first, bl, mem.ptr(send))
             sends.append(send)
-            keep.append(buf)
         mem.sync()                                        # spectrum_slices ran on each frontend's own stream: device-wide sync
         part = bl * cper * slice_bytes
         for q, fe in enumerate(fes):
-            recv = mem.empty(B * cper * slice_bytes)
-            for r in range(nranks):
-                mem.copy(recv, r * part, sends[r], q * part, part)
-            mem.sync()
-            fe.process_slices(mem.ptr(recv), B)
-            keep.append(recv)
+            if not direct:
+                for r in range(nranks):
+                    mem.copy(recvs[q], r * part, sends[r], q * part, part)
+                mem.sync()
+            fe.process_slices(mem.ptr(recvs[q]), B)
+        keep += recvs
         keep += sends
         done += B
     got = []

@@ -74,6 +74,8 @@ def test_block_contract_host_emulation_two_devices_sharded_spectrum():
     # each GPU transforms its share of every batch's blocks, slices change hands by peer copies, channels are sharded
     lib = os.path.join(HERE, "cusim", "libhfdl_cusim.so")
     assert run_driver(lib, 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, seed=37, ngpus=2, env={"HFDL_CUSIM_DEVICES": "2"}) == 4
+    # ... with packed send buffers + device-to-device copies instead of the pack kernel storing into the peers' buffers
+    assert run_driver(lib, 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, seed=37, ngpus=2, env={"HFDL_CUSIM_DEVICES": "2", "HFDL_B200_SHIM_COPY": "1"}) == 4
 
 
 @pytest.mark.gpu
@@ -93,3 +95,4 @@ def test_block_contract_two_gpus():
     assert run_driver(lib, 2000000, freqs, modes, 5.8, seed=35, ngpus=2) == 4
     assert run_driver(lib, 2000000, freqs[:3], modes[:3], 5.8, seed=36, ngpus=2) == 3
     assert run_driver(lib, 2000000, freqs, modes, 5.8, seed=35, ngpus=2, env={"HFDL_B200_SHIM_BROADCAST": "1"}) == 4
+    assert run_driver(lib, 2000000, freqs, modes, 5.8, seed=35, ngpus=2, env={"HFDL_B200_SHIM_COPY": "1"}) == 4

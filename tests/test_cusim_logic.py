@@ -72,6 +72,8 @@ def test_pruned_spectrum_equals_full(sim):
 def test_sharded_spectrum_two_ranks(sim):
     # multi-GPU data path (FFT blocks sharded, slices exchanged, channels sharded) on the host emulation: PDUs == one frontend's
     assert K.case_sharded_spectrum(sim, K.HostMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4) == 4
+    # ... and with the exchange fused into the pack kernel (stores straight into every rank's receive buffer)
+    assert K.case_sharded_spectrum(sim, K.HostMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4, direct=True) == 4
 
 
 def test_loop_kernel_layouts_agree(sim, monkeypatch):
@@ -79,3 +81,28 @@ def test_loop_kernel_layouts_agree(sim, monkeypatch):
     for lay in ("role2", "pack4"):
         monkeypatch.setenv("HFDL_B200_LOOP_LAYOUT", lay)
         assert K.case_frontend(sim, 250000, [10063000, 9952000, 10101000], [3, 0, 2], 3.2, batch=3, seed=6) == 3
+
+
+def test_push_nowait_two_staging_buffers(sim):
+    # a producer with two staging buffers: hfdl_b200_push_samples_nowait + hfdl_b200_wait_host_buffer before a buffer is refilled
+    import numpy as np
+    sr, freqs = 250000, [10063000, 9952000]
+    x, truth = K.make_capture(sr, freqs, [1, 2], 3.3, seed=27)
+    ref = K.run_oracle(sr, freqs, x, A.SFMT_CF32).pdus()
+    fe = A.Frontend(sr, K.CF, freqs, max_blocks_per_batch=4, lib=sim)
+    chunk = 3 * fe.geom.input_size + 1234
+    stage = [np.zeros(chunk, np.complex64), np.zeros(chunk, np.complex64)]
+    got = []
+    for i, at in enumerate(range(0, x.size, chunk)):
+        seg = x[at:at + chunk]
+        buf = stage[i % 2]
+        if i >= 2:
+            fe.wait_host_buffer()                 # (one event for the newest copy: waiting for it covers the older ones)
+        buf[:seg.size] = seg
+        fe.push_ptr(buf.ctypes.data, seg.size, wait=False)
+        got += fe.pdus()
+    fe.wait_host_buffer()
+    fe.flush()
+    got += fe.pdus()
+    K.compare_pdus(got, ref, truth)
+    fe.close()

@@ -278,6 +278,8 @@ def test_sharded_spectrum_equals_single_frontend(lib):
     # multi-GPU data path on one device: 2 and 4 "ranks", CF32 and CS16, batches that end ragged
     assert K.case_sharded_spectrum(lib, K.CudaMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4) == 4
     assert K.case_sharded_spectrum(lib, K.CudaMem(), 250000, [10063000, 9952000, 10101000, 9931000], [5, 2, 4, 3], 5.6, nranks=4, batch=8, sfmt=A.SFMT_CS16, seed=72) == 4
+    # the exchange fused into the pack kernel (hfdl_b200_spectrum_slices_to)
+    assert K.case_sharded_spectrum(lib, K.CudaMem(), 250000, [10063000, 9952000, 10101000, 9931000], [5, 2, 4, 3], 5.6, nranks=4, batch=8, sfmt=A.SFMT_CS16, seed=72, direct=True) == 4
 
 
 def test_sharded_spectrum_cfg3_geometry(lib):
