@@ -238,7 +238,7 @@ def config_of(name, W, P, world):
     """Identical for both arms: names the workload only (arm-specific step sizes are reported under "step")."""
     if world > 1 and W["multi"] == "sharded":
         shard = ("%d GPUs, one capture: every GPU transforms 1/%d of each batch's overlap-save blocks for all channels (its share of the capture "
-                 "comes over its own PCIe link), the channels' pass-band spectrum slices change hands in an NCCL all-to-all over NVLink, channel k is "
+                 "comes over its own PCIe link, the overlap in front of it from the previous GPU over NVLink), the channels' pass-band spectrum slices change hands in an NCCL all-to-all over NVLink, channel k is "
                  "demodulated on GPU k mod %d (%d channels per GPU)" % (world, world, world, W["nch"] // world))
     elif world > 1:
         shard = "%d GPUs: one capture, channel k on GPU k mod %d (%d channels per GPU); value: NCCL broadcast from rank 0 every pass; e2e: host scatter (1/%d of every pass per PCIe link) + NCCL all-gather" % (world, world, W["nch"] // world, world)
@@ -470,10 +470,10 @@ def main():
             self.ev_sent = [torch.cuda.Event() for _ in range(2)]
             self.i = 0
 
-        def run(self, d_in, ready=None):
+        def run(self, d_in, ready=()):
             i = self.i
-            if ready is not None:
-                self.fs.wait_event(ready)                           # the samples of this pass have landed
+            for ev in ready:
+                self.fs.wait_event(ev)                              # the samples of this pass have landed
             if i >= 2:
                 self.fs.wait_event(self.ev_sent[i % 2])             # the all-to-all of pass i-2 has read this send buffer
             self.fe.spectrum_slices(d_in.data_ptr(), i * nblocks + rank * bl, bl, self.send[i % 2].data_ptr(), self.fs.cuda_stream)
@@ -561,21 +561,48 @@ def main():
         d_parts = [torch.empty_like(h_src, device="cuda") for _ in range(2)] if world > 1 else None
         h2d_ev = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
         read_ev = [None, None]
+        # sharded: a rank uploads exactly its own blocks; the overlap in front of them -- the last overlap_length samples of
+        # the previous rank's blocks -- comes from that rank over NVLink (a ring shift per pass), so the capture crosses
+        # PCIe exactly once in total.  Rank 0's overlap is the tail of the last rank's blocks of the PREVIOUS pass.
+        ovb = ovl * bps
+        h_blocks = h_share[ovb:] if sharded else None
+        ovl_stream = torch.cuda.Stream() if sharded else None
+        ovl_ev = [torch.cuda.Event(), torch.cuda.Event()] if sharded else None
 
         def start_h2d(i):
             # this rank's share of pass i over its own PCIe link, on its own stream (runs beside the FFT / all-gather of pass i-1)
             with torch.cuda.stream(copy_stream):
                 if sharded and read_ev[i % 2] is not None:
                     copy_stream.wait_event(read_ev[i % 2])             # the FFT of pass i-2 has read this device buffer
-                d_parts[i % 2].copy_(h_src, non_blocking=True)
+                    copy_stream.wait_event(ovl_ev[i % 2])              # ... and its tail has gone to the next rank
+                if sharded:
+                    d_parts[i % 2][ovb:].copy_(h_blocks, non_blocking=True)
+                else:
+                    d_parts[i % 2].copy_(h_src, non_blocking=True)
                 h2d_ev[i % 2].record(copy_stream)
+            if sharded:
+                with torch.cuda.stream(ovl_stream):
+                    ovl_stream.wait_event(h2d_ev[i % 2])
+                    tgt = d_parts[i % 2] if rank > 0 else d_parts[(i + 1) % 2]
+                    if rank == 0 and read_ev[(i + 1) % 2] is not None:
+                        ovl_stream.wait_event(read_ev[(i + 1) % 2])    # the FFT that last read the other buffer (its overlap part is written now)
+                    ops = [dist.P2POp(dist.isend, d_parts[i % 2][-ovb:], (rank + 1) % world),
+                           dist.P2POp(dist.irecv, tgt[:ovb], (rank - 1) % world)]
+                    for w in dist.batch_isend_irecv(ops):
+                        w.wait()
+                    ovl_ev[i % 2].record(ovl_stream)
 
         def pass_host():
             i = st2["i"]
             if sharded:
                 if i == 0:
                     start_h2d(0)
-                read_ev[i % 2] = xch2.run(d_parts[i % 2], h2d_ev[i % 2])
+                ready = [h2d_ev[i % 2]]
+                if rank > 0:
+                    ready.append(ovl_ev[i % 2])
+                elif i > 0:
+                    ready.append(ovl_ev[(i - 1) % 2])
+                read_ev[i % 2] = xch2.run(d_parts[i % 2], ready)
                 start_h2d(i + 1)
             elif world > 1:
                 buf = bufs[i % nbuf]
@@ -611,7 +638,7 @@ def main():
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         d2h_per_step = fe2.result_bytes_per_batch() * loops
-        h2d_per_step = h_src.numel() * loops
+        h2d_per_step = (h_blocks.numel() if sharded else h_src.numel()) * loops
         fe2.close()
         del xch2
 
