@@ -565,7 +565,8 @@ def main():
         # the previous rank's blocks -- comes from that rank over NVLink (a ring shift per pass), so the capture crosses
         # PCIe exactly once in total.  Rank 0's overlap is the tail of the last rank's blocks of the PREVIOUS pass.
         ovb = ovl * bps
-        h_blocks = h_share[ovb:] if sharded else None
+        shift = sharded and not os.environ.get("HFDL_BENCH_UPLOAD_OVERLAP")      # (A/B switch: every rank uploads its overlap itself)
+        h_blocks = h_share[ovb:] if shift else None
         ovl_stream = torch.cuda.Stream() if sharded else None
         ovl_ev = [torch.cuda.Event(), torch.cuda.Event()] if sharded else None
 
@@ -574,13 +575,14 @@ def main():
             with torch.cuda.stream(copy_stream):
                 if sharded and read_ev[i % 2] is not None:
                     copy_stream.wait_event(read_ev[i % 2])             # the FFT of pass i-2 has read this device buffer
-                    copy_stream.wait_event(ovl_ev[i % 2])              # ... and its tail has gone to the next rank
-                if sharded:
+                    if shift:
+                        copy_stream.wait_event(ovl_ev[i % 2])          # ... and its tail has gone to the next rank
+                if shift:
                     d_parts[i % 2][ovb:].copy_(h_blocks, non_blocking=True)
                 else:
                     d_parts[i % 2].copy_(h_src, non_blocking=True)
                 h2d_ev[i % 2].record(copy_stream)
-            if sharded:
+            if shift:
                 with torch.cuda.stream(ovl_stream):
                     ovl_stream.wait_event(h2d_ev[i % 2])
                     tgt = d_parts[i % 2] if rank > 0 else d_parts[(i + 1) % 2]
@@ -598,9 +600,9 @@ def main():
                 if i == 0:
                     start_h2d(0)
                 ready = [h2d_ev[i % 2]]
-                if rank > 0:
+                if shift and rank > 0:
                     ready.append(ovl_ev[i % 2])
-                elif i > 0:
+                elif shift and i > 0:
                     ready.append(ovl_ev[(i - 1) % 2])
                 read_ev[i % 2] = xch2.run(d_parts[i % 2], ready)
                 start_h2d(i + 1)
@@ -638,7 +640,7 @@ def main():
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         d2h_per_step = fe2.result_bytes_per_batch() * loops
-        h2d_per_step = (h_blocks.numel() if sharded else h_src.numel()) * loops
+        h2d_per_step = (h_blocks.numel() if shift else h_src.numel()) * loops
         fe2.close()
         del xch2
 
