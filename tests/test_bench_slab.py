@@ -44,3 +44,24 @@ def test_config_dict_is_the_same_for_both_arms():
     assert B.config_of("cfg3", W, P, 1) == B.config_of("cfg3", W, P, 1)
     assert "cfg3" in B.config_of("cfg3", W, P, 1)["workload"]
     assert B.DEFAULT_BY_GPUS == {1: "cfg3", 2: "cfg3", 4: "cfg4", 8: "cfg5"}
+
+
+def test_workload_per_gpu_count():
+    """prepare_workload: BASELINE's configuration for the GPU count, CS16 for the wideband ones, a slab whose block count
+    divides by the GPU count, the sharded spectrum unless the channels do not divide; both arms call it the same way."""
+    import argparse
+    B = _bench()
+    a = argparse.Namespace(loops=0, sample_format=None, multi="sharded")
+    for n in (1, 2, 4, 8):
+        name = B.DEFAULT_BY_GPUS[n]
+        W = B.prepare_workload(name, a, n)
+        assert W["blocks_per_slot"] % n == 0 and W["blocks_per_slot"] >= B.WORKLOADS[name]["blocks_per_slot"]
+        assert W["sfmt"] == "cs16" and W["multi"] == ("single" if n == 1 else "sharded")
+        isz = O.geometry(W["sr"])[2].input_size
+        P = dict(nblocks=W["blocks_per_slot"], nsamp=W["blocks_per_slot"] * isz)
+        c1, c2 = B.config_of(name, W, P, n), B.config_of(name, B.prepare_workload(name, a, n), P, n)
+        assert c1 == c2 and c1["sample_format"] == "CS16" and c1["channels"] == W["nch"]
+    assert B.prepare_workload("cfg3", a, 3)["multi"] == "broadcast"          # 128 channels do not divide by 3
+    assert B.prepare_workload("cfg2", a, 1)["sfmt"] == "cf32"                 # BASELINE names CF32 for config 2
+    a.sample_format = "cf32"
+    assert B.prepare_workload("cfg3", a, 1)["sfmt"] == "cf32"
