@@ -71,9 +71,10 @@ def test_pruned_spectrum_equals_full(sim):
 
 def test_sharded_spectrum_two_ranks(sim):
     # multi-GPU data path (FFT blocks sharded, slices exchanged, channels sharded) on the host emulation: PDUs == one frontend's
-    assert K.case_sharded_spectrum(sim, K.HostMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4) == 4
+    cache = {}
+    assert K.case_sharded_spectrum(sim, K.HostMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4, cache=cache) == 4
     # ... and with the exchange fused into the pack kernel (stores straight into every rank's receive buffer)
-    assert K.case_sharded_spectrum(sim, K.HostMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4, direct=True) == 4
+    assert K.case_sharded_spectrum(sim, K.HostMem(), 250000, [10063000, 9952000, 10101000, 9931000], [1, 2, 0, 3], 3.3, nranks=2, batch=4, direct=True, cache=cache) == 4
 
 
 def test_loop_kernel_layouts_agree(sim, monkeypatch):
