@@ -1,12 +1,12 @@
 // dumphfdl_b200/csrc/loop_kernel.cuh -- K8b-K11: the feedback part of the per-channel HFDL demodulator
 // (hfdl.c:707-891): symbol-timing recursion, Costas loop, T/2 LMS equaliser, M-PSK slicer, sampler and framer.
 //
-// One CTA per channel, three specialised warps that talk through shared-memory rings.  Every feedback loop of the
-// reference is a strictly sequential float recurrence, so the design goal is the SHORTEST DEPENDENT CHAIN and the
-// FEWEST INSTRUCTIONS on each sequential warp; everything that is not on a chain is moved to another warp or to
-// other lanes:
+// Three specialised warps per channel that talk through shared-memory rings; two or four channels per CTA (see "CTA
+// layouts" below).  Every feedback loop of the reference is a strictly sequential float recurrence, so the design goal
+// is the SHORTEST DEPENDENT CHAIN and the FEWEST INSTRUCTIONS on each sequential warp; everything that is not on a chain
+// is moved to another warp or to other lanes:
 //   warp 2 "loader"  streams the precomputed filter-bank rows (bank_kernel) and AGC levels of the channel from HBM
-//                    into a 256-sample shared-memory ring (one TMA bulk copy per 32-sample chunk, completion on mbarriers, 3 chunks in flight).
+//                    into a 128-sample shared-memory ring (one TMA bulk copy per 32-sample chunk, completion on mbarriers, 3 chunks in flight).
 //   warp 1 "timing"  symsync_crcf_step: iterates per OUTPUT (not per input sample): arm lookup in the ring, timing
 //                    error detector + loop filter on every second output, tau/arm update, skip to the input sample
 //                    of the next output.  Publishes {symbol, AGC level, tag} entries into a 64-entry output ring.
