@@ -167,6 +167,47 @@ def test_reference_cfg2_geometry_two_megasamples():
     p.close()
 
 
+def test_reference_cfg3_geometry_twenty_megasamples_cs16():
+    # BASELINE config 3 geometry as bench.py runs it (20 Msps CS16: N = 2^22, M = 4096, 1792 outputs per block, resampler
+    # 0.55296): the reference's input-helpers.c conversion + fft.c + fastddc.c + hfdl.c end to end vs the oracle
+    sr = 20000000
+    freqs = [CF - 8123000, CF + 4660000]
+    pd = [O.make_pdu(m, m % 2, 190 + m) for m in (1, 3)]
+    frames = [O.tx_frame(f, m, 0.05 + 0.01 * i, pd[i], cfo_hz=6.0 * i - 3, phase0=0.7 * i, amplitude=0.1) for i, (f, m) in enumerate(zip(freqs, (1, 3)))]
+    x = O.render(int(sr * 2.8), sr, CF, frames, noise_sigma=O.noise_sigma(0.1, sr, 20.0), seed=14)
+    raw = np.zeros(2 * x.size, np.int16)
+    O.lib().orc_quantize_cs16(x, x.size, raw)
+    del x
+    r, p = run_both(sr, freqs, raw, sfmt=O.SFMT_CS16, taps=True)
+    assert (p.ddc.fft_size, p.ddc.fft_inv_size, p.ddc.input_size, p.ddc.post_input_size // p.ddc.post_decimation) == (1 << 22, 4096, 3670016, 1792)
+    rp, _ = assert_same_pdus(r, p, freqs)
+    assert sorted(q.data() for q in rp) == sorted(pd)
+    assert_same_taps(r, p)
+    r.close()
+    p.close()
+
+
+@pytest.mark.parametrize("sr,N,sfmt", [(30000000, 1 << 22, O.SFMT_CF32), (60000000, 1 << 23, O.SFMT_CS16)])
+def test_reference_cfg4_cfg5_geometry(sr, N, sfmt):
+    # BASELINE config 4 / 5 geometries (30 Msps: N = 2^22, M = 2048; 60 Msps: N = 2^23, overlap 2^20): reference vs oracle
+    freqs = [CF - 9100000, CF + 3907000]
+    pd = [O.make_pdu(m, m % 2, 290 + m) for m in (2, 0)]
+    frames = [O.tx_frame(f, m, 0.04 + 0.01 * i, pd[i], cfo_hz=5.0 * i - 2, phase0=0.3 * i, amplitude=0.1) for i, (f, m) in enumerate(zip(freqs, (2, 0)))]
+    x = O.render(int(sr * 2.7), sr, CF, frames, noise_sigma=O.noise_sigma(0.1, sr, 20.0), seed=15)
+    raw = x
+    if sfmt == O.SFMT_CS16:
+        raw = np.zeros(2 * x.size, np.int16)
+        O.lib().orc_quantize_cs16(x, x.size, raw)
+        del x
+    r, p = run_both(sr, freqs, raw, sfmt=sfmt, taps=True)
+    assert (p.ddc.fft_size, p.ddc.fft_inv_size) == (N, 2048)
+    rp, _ = assert_same_pdus(r, p, freqs)
+    assert sorted(q.data() for q in rp) == sorted(pd)
+    assert_same_taps(r, p)
+    r.close()
+    p.close()
+
+
 def test_scrambler_same_under_both_liquid_msequence_conventions():
     # hfdl.c:333-345 picks (genpoly, init) by liquid version so that both conventions emit one sequence; the oracle's
     # orc_scrambler_bits must be that sequence (first 32 bits recorded in SURVEY appendix A)
