@@ -1,6 +1,7 @@
-"""Multi-GPU host logic: HFDL channels are independent after the shared forward FFT, so each
-GPU owns a disjoint channel set end to end.  The only exchange step is making the same wideband capture
-visible to every GPU: torch.distributed broadcast (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+"""Test helpers for the world_size-2 gloo tests (tests/test_multi_rank.py): the channel -> rank map the C ABI uses
+(hfdl_b200_set_exchange: channel k of the job belongs to rank k % nranks), a capture broadcast and a PDU gather.
+The multi-GPU data path itself is in the library (hfdl_b200_spectrum_slices / _slices_to / process_slices / push_peer,
+block_shim.cu for ngpus > 1); bench.py drives it with one process per GPU."""
 
 
 def shard_channels(freqs, rank, world):

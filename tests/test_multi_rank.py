@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     import torch
     import torch.distributed as dist
     import dumphfdl_b200.api as A
-    from dumphfdl_b200 import sharding
+    import rank_helpers as sharding
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -63,7 +63,7 @@ def test_two_rank_channel_sharding_gloo():
 
 
 def test_shard_map_is_a_partition():
-    from dumphfdl_b200 import sharding
+    import rank_helpers as sharding
     f = list(range(1000, 1013))
     for world in (1, 2, 4, 8):
         parts = [sharding.shard_channels(f, r, world) for r in range(world)]
@@ -89,7 +89,7 @@ def _worker_gather(rank, world, port, q):
     import torch
     import torch.distributed as dist
     import dumphfdl_b200.api as A
-    from dumphfdl_b200 import sharding
+    import rank_helpers as sharding
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -169,7 +169,7 @@ def _worker_sharded(rank, world, port, q):
         keep += [mine, send, recv]
         done += B
     fe.sync()
-    from dumphfdl_b200 import sharding
+    import rank_helpers as sharding
     merged = sharding.gather_pdus(fe.pdus())
     if rank == 0:
         q.put((merged, nb * isz))
