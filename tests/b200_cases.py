@@ -1,6 +1,8 @@
 """Parity cases shared by the GPU tests (real libhfdl_b200.so, -m gpu) and the CPU logic tests
 (same kernels compiled for host emulation, tests/cusim).  Every case drives the C ABI of
 include/hfdl_b200.h and compares with the CPU oracle on the same seeded input."""
+import ctypes as C
+
 import numpy as np
 
 import orclib as O
@@ -224,6 +226,52 @@ def case_frontend(lib, sr, freqs, modes, dur, sfmt=A.SFMT_CF32, batch=4, check_f
             assert (q.train_bits_bad, q.train_bits_total) == (r.train_bits_bad, r.train_bits_total)
     fe.close()
     return len(got)
+
+
+def case_errors_and_empty_inputs(lib):
+    """Error behaviour of the boundary and the degenerate inputs: what the reference rejects before it builds its blocks
+    (main.c:214-226 check_frequency_span, main.c:699-706 / fastddc.c:46-80 geometry, input-common.h sample formats) is
+    rejected by hfdl_b200_create; an empty push, a push shorter than one overlap-save block and a flush of an empty stream
+    are valid and give no PDU (fft.c:38-55 simply waits for input_size samples)."""
+    sr, f = 250000, 10063000
+    for kw, args in (
+            (dict(), (sr, CF, [])),                                    # no channel
+            (dict(), (sr, CF, [CF + sr // 2])),                        # |centre - channel| >= sample_rate / 2 (main.c:217)
+            (dict(), (sr, CF, [f, CF - sr // 2 - 1000])),              # ... any channel of the list
+            (dict(sample_format=0), (sr, CF, [f])),                    # SFMT_UNDEF
+            (dict(sample_format=4), (sr, CF, [f])),                    # beyond SFMT_CF32
+            (dict(), (5000, CF, [CF + 1000])),                         # rate below the 5400 Hz the demodulator runs at: decimation < 1
+    ):
+        try:
+            A.Frontend(*args, lib=lib, **kw)
+        except RuntimeError:
+            continue
+        raise AssertionError("hfdl_b200_create accepted %r %r" % (args, kw))
+    vp = C.c_void_p()
+    assert lib.hfdl_b200_create(None, None) == -1 and lib.hfdl_b200_create(C.byref(vp), None) == -1
+    fe = A.Frontend(sr, CF, [f, 9952000], max_blocks_per_batch=3, lib=lib)
+    g = fe.geom
+    assert fe.push(np.zeros(0, np.complex64)) == 0 and fe.flush() == 0 and fe.pdus() == []
+    assert lib.hfdl_b200_push_samples(fe.h, None, 5) == -1 and lib.hfdl_b200_push_samples(fe.h, None, -1) == -1
+    assert lib.hfdl_b200_push_samples(fe.h, None, 0) == 0
+    fe.push(np.zeros(g.input_size - 1, np.complex64))                 # one sample short of a block: nothing to transform yet
+    fe.flush()
+    assert fe.pdus() == [] and fe.launches() == 0
+    fe.push(np.zeros(1 + 2 * g.input_size, np.complex64))             # silence: blocks run, no preamble, no PDU
+    fe.flush()
+    assert fe.pdus() == [] and fe.launches() > 0
+    for c in range(2):
+        assert fe.stats(c) == (0, 0, 0, 0)
+        k = fe.counters(c)
+        assert k.freq == fe.freqs[c] and k.frames_processed == 0 and k.M1_not_found == 0 and k.A2_found == 0
+    st = (C.c_int32 * 4)()
+    assert lib.hfdl_b200_channel_stats(fe.h, 2, st) == -1 and lib.hfdl_b200_channel_stats(fe.h, -1, st) == -1
+    assert lib.hfdl_b200_channel_counters(fe.h, 2, C.byref(A.Counters())) == -1
+    lvl = C.c_float()
+    assert lib.hfdl_b200_channel_noise_floor(fe.h, 7, C.byref(lvl)) == -1
+    one = A.Pdu()
+    assert lib.hfdl_b200_pop_pdu(fe.h, C.byref(one)) == 0             # empty queue: 0, not an error
+    fe.close()
 
 
 def case_pruned_spectrum(lib, sr, freqs, modes, dur, batch, seed=61):

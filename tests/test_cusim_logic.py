@@ -57,6 +57,10 @@ def test_stream_submit_poll(sim):
     assert K.case_frontend_stream(sim, 250000, [10063000, 9952000], plan, 3.4, batch=4, push_blocks=1, seed=35, submit_poll=True) == 2
 
 
+def test_errors_and_empty_inputs(sim):
+    K.case_errors_and_empty_inputs(sim)
+
+
 def test_front_parser(sim):
     K.case_front_parser(sim)
 

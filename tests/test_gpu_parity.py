@@ -136,6 +136,10 @@ def test_pruned_spectrum_equals_full(lib):
     assert K.case_pruned_spectrum(lib, 8000000, [K.CF - 3100000, K.CF + 40000, K.CF + 3900000], [1, 3, 0], 2.9, batch=5, seed=62) == 3
 
 
+def test_errors_and_empty_inputs(lib):
+    K.case_errors_and_empty_inputs(lib)
+
+
 def test_front_parser_all_branches(lib):
     K.case_front_parser(lib)
 
