@@ -18,7 +18,9 @@
  *     WHOLE of hfdl.c (sample loop, Costas loop, sampler, framer FSM, descrambler, deinterleaver,
  *     decode_user_data, dispatch_pdu, statsd hook points) plus block.c / fft.c / input-helpers.c running as
  *     the reference's own threads: every DATADUMPS tap bit-identical, every PDU and its metadata identical --
- *     tests/test_oracle_hfdl_ref.py.
+ *     tests/test_oracle_hfdl_ref.py.  The PDU front (orc_pdu_front_parse, orc_fcs_check) is pinned against the
+ *     reference's own pdu.c / mpdu.c / spdu.c / lpdu.c / util.c / crc.c running their real pdu_decoder_thread
+ *     (oracle/_ref/libref_front.so) -- tests/test_oracle_front_ref.py.
  *   - NOT PINNED: the inside of the liquid-dsp objects (agc, firfilt, msresamp, symsync, eqlms, modem,
  *     bsequence, msequence; oracle/orc_liquid.c).  liquid-dsp is NOT in /root/reference (un-vendored
  *     dependency jgaeddert/liquid-dsp, any 1.3.0 <= v < 2.0 accepted by src/CMakeLists.txt:71-101), is not

@@ -6,6 +6,7 @@ import ctypes as C
 import numpy as np
 
 import orclib as O
+from pdu_forge import Forge
 import dumphfdl_b200.api as A
 
 # float tolerances (relative L2).  The reference itself is built -ffast-math, so float I/Q is
@@ -142,15 +143,19 @@ def check_front(got):
         assert q.crc_good == (w[0] == 0)
 
 
-def case_front_parser(lib):
+def case_front_parser(lib, nfuzz=300):
     pd = [O.make_pdu(m, k, 7 + m) for m in range(8) for k in range(5)] + [b"\x03", b"\x00" * 10, b"\x13\x05"]
+    # constructed MPDUs / SPDUs, one per branch of mpdu.c:56-159 / lpdu.c:129-150 / spdu.c:55-70, and mutated ones (the same
+    # generator is checked against the reference's own pdu_decoder_thread in tests/test_oracle_front_ref.py)
+    F = Forge(np.random.default_rng(77))
+    pd += F.branches() + F.fuzz(nfuzz)
     got = A.pdu_front_parse(pd, lib=lib)
     for p, g in zip(pd, got):
         w = O.pdu_front(p)
-        assert tuple(g[:7]) == w and g[7] == (w[0] == 0), (len(p), g, w)
+        assert tuple(g[:7]) == w and g[7] == (w[0] == 0), (len(p), bytes(p[:16]).hex(), g, w)
     # every branch is hit at least once: good / bad_fcs / too_short frames, both directions, bad and short LPDUs
     assert {g[0] for g in got} == {0, 1, 2} and {g[1] for g in got if g[0] == 0} == {0, 1}
-    assert any(g[4] for g in got) and any(g[5] for g in got)
+    assert any(g[4] for g in got) and any(g[5] for g in got) and max(g[2] for g in got) == 30
 
 
 def case_tapslice(lib, sr, freqs):

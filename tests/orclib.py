@@ -233,6 +233,40 @@ def reflib_fast():
     return R
 
 
+def reflib_front():
+    """The reference's own pdu.c / mpdu.c / spdu.c / lpdu.c / util.c / crc.c around its real pdu_decoder_thread
+    (oracle/ref_shim/front/ref_front_host.c); None if not built."""
+    if "ref_front" in _libs:
+        return _libs["ref_front"]
+    path = os.path.join(ODIR, "_ref", "libref_front.so")
+    if not os.path.exists(path) and os.path.isdir("/root/reference/src"):
+        build()
+    R = C.CDLL(path) if os.path.exists(path) else None
+    if R is not None:
+        u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+        R.ref_front_counter_name.restype = C.c_char_p
+        R.ref_front_run.argtypes = [u8p, np.ctypeslib.ndpointer(np.int32, flags="C"), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                    np.ctypeslib.ndpointer(np.int64, flags="C")]
+        R.ref_front_fcs_check.argtypes = [u8p, C.c_uint32]
+        R.crc16_ccitt.restype = C.c_uint16
+        R.crc16_ccitt.argtypes = [u8p, C.c_uint32, C.c_uint16]
+    _libs["ref_front"] = R
+    return R
+
+
+def ref_front_run(pdus, freq=10063000, output_mpdus=False, output_corrupted=False):
+    """Every PDU through the reference's pdu_decoder_thread, one at a time: list of {statsd counter / delivered-node name: count}."""
+    R = reflib_front()
+    K = R.ref_front_counter_count()
+    names = [R.ref_front_counter_name(i).decode() for i in range(K)]
+    buf = np.frombuffer(b"".join(bytes(p) for p in pdus) + b"\0", np.uint8).copy()
+    lens = np.array([len(p) for p in pdus], np.int32)
+    out = np.zeros((len(pdus), K), np.int64)
+    r = R.ref_front_run(buf, lens, len(pdus), freq, int(output_mpdus), int(output_corrupted), out)
+    assert r == 0, r
+    return [dict(zip(names, (int(v) for v in row))) for row in out]
+
+
 class RefPipeline:
     """The REFERENCE's own block.c + fft.c + fastddc.c + hfdl.c + viterbi27_port.c, wired as main.c does, fed as
     input-file.c does (oracle/ref_shim/ref_host.c).  One instance at a time (the PDU capture list is global)."""
