@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import b200_cases as K
+import golden_cases as GC
 import dumphfdl_b200 as hb
 import dumphfdl_b200.api as A
 import orclib as O
@@ -301,19 +302,13 @@ class O_pdu:
         return self._d
 
 
-def test_golden_fixture(lib):
-    """PDUs / frame positions recorded from the oracle in the development container (tests/golden/make_golden.py)."""
-    with open(os.path.join(HERE, "golden", "cfg1_pdus.json")) as f:
-        G = json.load(f)
-    x, _ = K.make_capture(G["sample_rate"], G["freqs"], G["modes"], G["dur"], seed=G["seed"])
-    raw = np.zeros(2 * x.size, np.int16)
-    O.lib().orc_quantize_cs16(x, x.size, raw)
-    fe = A.Frontend(G["sample_rate"], K.CF, G["freqs"], sample_format=A.SFMT_CS16, max_blocks_per_batch=7, lib=lib)
-    fe.push(raw)
-    fe.flush()
-    got = sorted((q.freq, q.sample_cnt_a2, q.sample_cnt_end, q.M1, q.data().hex()) for q in fe.pdus())
-    want = sorted((p["freq"], p["a2"], p["end"], p["M1"], p["octets"]) for p in G["pdus"])
-    assert got == want
+@pytest.mark.parametrize("name", GC.FIXTURES)
+def test_golden_fixture(lib, name):
+    """PDU octets, hfdl_pdu_metadata fields and statsd counters recorded from the reference's own code in the development
+    container (tests/golden/make_golden.py), frame positions from the oracle."""
+    G = GC.load(name)
+    pdus, counters = GC.run_frontend(G, lib)
+    GC.check_against(G, pdus, counters)
 
 
 def test_no_cpu_fallback_symbols(lib):
