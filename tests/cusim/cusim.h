@@ -49,6 +49,9 @@ static inline uint2 make_uint2(unsigned a, unsigned b) { uint2 r; r.x = a; r.y =
 #define __restrict__ __restrict
 #define __constant__ static
 
+#ifndef CUSIM_YIELDS
+#define CUSIM_YIELDS 200
+#endif
 namespace cusim {
 class Barrier {
 	std::atomic<unsigned> count{0}, gen{0}; unsigned n;
@@ -59,9 +62,14 @@ public:
 		if(count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
 			count.store(0, std::memory_order_relaxed);
 			gen.store(g + 1, std::memory_order_release);
+			gen.notify_all();
 		} else {
 			unsigned spins = 0;
-			while(gen.load(std::memory_order_acquire) == g) { if(++spins > 64) std::this_thread::yield(); }
+			while(gen.load(std::memory_order_acquire) == g) {
+				if(++spins <= 64) continue;
+				if(spins <= 64 + CUSIM_YIELDS) std::this_thread::yield();
+				else gen.wait(g, std::memory_order_acquire);            // a long wait (idle lanes, whole-CTA barriers): sleep on the futex
+			}
 		}
 	}
 };
