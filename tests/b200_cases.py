@@ -100,6 +100,81 @@ def make_capture(sr, freqs, modes, dur, esn0=20.0, seed=3, amp=None, starts=None
     return x, truth
 
 
+def hostile_capture(name, sr=250000, f=10063000):
+    """Captures the domain's edge cases are made of (one channel at f, centre CF): -> (complex64 capture, note).  What the
+    reference does with them is whatever its demodulator does; the oracle must do exactly the same (test_oracle_hfdl_ref.py)
+    and the kernels must follow the oracle (host emulation: test_cusim_logic.py)."""
+    pd = [O.make_pdu(1, 0, 501), O.make_pdu(2, 3, 502), O.make_pdu(3, 1, 503)]
+    amp, dur, esn0, seed = 0.1, 3.4, 20.0, 500
+    post = None
+    if name == "collision":            # two transmitters in one slot on one channel, 6 dB apart, different carrier offsets
+        frames = [O.tx_frame(f, 1, 0.25, pd[0], cfo_hz=6.0, phase0=0.3, amplitude=0.1),
+                  O.tx_frame(f, 2, 0.55, pd[1], cfo_hz=-9.0, phase0=2.0, amplitude=0.05)]
+    elif name == "equal_power_collision":
+        frames = [O.tx_frame(f, 1, 0.25, pd[0], cfo_hz=6.0, phase0=0.3, amplitude=0.07),
+                  O.tx_frame(f, 1, 0.40, pd[1][: len(pd[0])] if len(pd[1]) >= len(pd[0]) else pd[0], cfo_hz=-4.0, phase0=1.0, amplitude=0.07)]
+    elif name == "cfo_plus_70":        # carrier far off the dial frequency (Costas pull-in range)
+        frames = [O.tx_frame(f, 1, 0.25, pd[0], cfo_hz=70.0, phase0=0.3, amplitude=amp)]
+    elif name == "cfo_minus_45":
+        frames = [O.tx_frame(f, 3, 0.25, pd[2], cfo_hz=-45.0, phase0=1.3, amplitude=amp)]
+    elif name == "clipped":            # ADC overload: the capture is clipped at 60 % of the frame's peak before quantisation
+        frames = [O.tx_frame(f, 2, 0.25, pd[1], cfo_hz=5.0, phase0=0.3, amplitude=0.5)]
+        post = "clip"
+    elif name == "cut_at_end":         # the capture ends in the middle of the data part
+        frames = [O.tx_frame(f, 1, 0.25, pd[0], cfo_hz=5.0, phase0=0.3, amplitude=amp)]
+        dur = 1.6
+    elif name == "starts_mid_frame":   # the capture begins inside a frame's preamble; a complete frame follows
+        frames = [O.tx_frame(f, 1, -0.2, pd[0], cfo_hz=5.0, phase0=0.3, amplitude=amp),
+                  O.tx_frame(f, 3, 2.5, pd[2], cfo_hz=5.0, phase0=0.3, amplitude=amp)]
+        dur = 5.3
+    elif name == "adjacent_interferer":   # a 30 dB stronger carrier 1.5 kHz outside the channel's pass band
+        frames = [O.tx_frame(f, 2, 0.25, pd[1], cfo_hz=-3.0, phase0=0.3, amplitude=0.02)]
+        post = "interferer"
+        esn0 = 25.0
+        amp = 0.02
+    elif name == "dc_and_weak":        # a DC spur of the SDR at the centre frequency and a frame 40 dB below full scale
+        frames = [O.tx_frame(f, 1, 0.25, pd[0], cfo_hz=2.0, phase0=0.3, amplitude=0.01)]
+        post = "dc"
+        amp = 0.01
+    else:
+        raise KeyError(name)
+    x = O.render(int(sr * dur), sr, CF, frames, noise_sigma=O.noise_sigma(amp, sr, esn0), seed=seed)
+    if post == "clip":
+        lim = np.float32(0.3)
+        x = (np.clip(x.real, -lim, lim) + 1j * np.clip(x.imag, -lim, lim)).astype(np.complex64)
+    elif post == "interferer":
+        t = np.arange(x.size) / sr
+        x = (x + 0.6 * np.exp(2j * np.pi * (f - CF + 1440 + 2900.0) * t)).astype(np.complex64)
+    elif post == "dc":
+        x = (x + np.complex64(0.2 + 0.1j)).astype(np.complex64)
+    return x
+
+
+HOSTILE = ("collision", "equal_power_collision", "cfo_plus_70", "cfo_minus_45", "clipped", "cut_at_end", "starts_mid_frame",
+           "adjacent_interferer", "dc_and_weak")
+
+
+def case_hostile(lib, name, sr=250000, f=10063000, batch=4):
+    """the kernels on a hostile capture: PDUs (possibly none, possibly with bit errors), frame positions, demodulator and
+    frame counters and the continuous float checkpoints equal the oracle's"""
+    x = hostile_capture(name, sr, f)
+    p = run_oracle(sr, [f], x, A.SFMT_CF32, 0, ["agc", "mf", "eq"])
+    ref = p.pdus()
+    fe = A.Frontend(sr, CF, [f], max_blocks_per_batch=batch, capture_channel=0, capture_max=1 << 20, lib=lib)
+    fe.push(x)
+    fe.flush()
+    got = fe.pdus()
+    compare_pdus(got, ref)
+    assert fe.stats(0) == p.stats(0)
+    check_counters(fe, p, [f], ref)
+    check_front(got)
+    for tap in ("agc", "mf", "eq"):
+        a, b = fe.checkpoint(tap), p.capture(0, tap)
+        assert a.size == b.size and rel(a, b) < TOL_DEMOD, (name, tap, rel(a, b))
+    fe.close()
+    return len(got)
+
+
 def run_oracle(sr, freqs, raw, sfmt, capture_ch=None, taps=()):
     p = O.Pipeline(sr, CF, freqs, fold_mode=O.FOLD_SLICE, nthreads=8)
     if capture_ch is not None:

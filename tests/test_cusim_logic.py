@@ -61,6 +61,14 @@ def test_errors_and_empty_inputs(sim):
     K.case_errors_and_empty_inputs(sim)
 
 
+@pytest.mark.parametrize("name", K.HOSTILE)
+def test_hostile_captures_follow_the_oracle(sim, name):
+    # collisions (one gives a PDU with a bad FCS), carrier offsets up to no detection at all, clipping, frames cut by the end /
+    # the start of the capture, a strong adjacent carrier, a DC spur with a weak frame
+    # (the oracle equals the reference's own hfdl.c on these captures: test_oracle_hfdl_ref.py)
+    K.case_hostile(sim, name)
+
+
 def test_front_parser(sim):
     K.case_front_parser(sim)
 

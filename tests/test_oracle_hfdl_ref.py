@@ -14,6 +14,7 @@ prebuilt file; nothing here reads /root/reference at run time)."""
 import numpy as np
 import pytest
 
+import b200_cases as K
 import orclib as O
 
 pytestmark = pytest.mark.skipif(O.reflib() is None or not hasattr(O.reflib(), "ref_pipeline_create"),
@@ -116,6 +117,23 @@ def test_reference_hfdl_noise_only_resets_and_counters():
     a1, a2, m1, frames = p.stats(0)
     assert r.stat(F, "demod.preamble.A2_found") == a2 and r.stat(F, "demod.preamble.M1_found") == m1
     assert r.stat(F, "demod.preamble.errors.M1_not_found") == p.m1_not_found(0)
+    r.close()
+    p.close()
+
+
+@pytest.mark.parametrize("name", K.HOSTILE)
+def test_reference_hfdl_equals_oracle_on_hostile_captures(name):
+    """collisions, carrier offsets beyond the loop's comfort, clipping, frames cut by the capture's edges, a strong adjacent
+    carrier, a DC spur: whatever the reference's demodulator makes of them, the oracle makes the same -- every tap
+    bit-identical, the same PDUs (none, or with bit errors behind a good or bad FCS), the same counters"""
+    x = K.hostile_capture(name, SR, F)
+    r, p = run_both(SR, [F], x)
+    rp, _ = assert_same_pdus(r, p, [F])
+    assert_same_taps(r, p)
+    a1, a2, m1, frames = p.stats(0)
+    assert r.stat(F, "demod.preamble.A2_found") == a2 and r.stat(F, "demod.preamble.M1_found") == m1
+    assert r.stat(F, "demod.preamble.errors.M1_not_found") == p.m1_not_found(0)
+    assert len(rp) == frames
     r.close()
     p.close()
 
