@@ -150,6 +150,29 @@ def hostile_capture(name, sr=250000, f=10063000):
     return x
 
 
+def random_scenario(seed, sr=250000):
+    """A seeded random job: 1-3 channels, up to three frames per channel back to back or overlapping the next slot, modes,
+    PDU kinds, carrier offsets (+-30 Hz), amplitudes (26 dB range) and Es/N0 (3-25 dB) drawn at random -> (freqs, capture)"""
+    rng = np.random.default_rng(9000 + seed)
+    nch = int(rng.integers(1, 4))
+    freqs = sorted(rng.choice(np.arange(9890, 10111, 13), nch, replace=False) * 1000)
+    freqs = [int(f) for f in freqs]
+    frames, t_end = [], 0.0
+    amp0 = float(10 ** rng.uniform(-2.0, -0.7))
+    for f in freqs:
+        t = float(rng.uniform(0.05, 0.6))
+        for _ in range(int(rng.integers(1, 4))):
+            m = int(rng.integers(0, 8))
+            pdu = O.make_pdu(m, int(rng.integers(0, 5)), int(rng.integers(1, 1 << 30)))
+            frames.append(O.tx_frame(f, m, t, pdu, cfo_hz=float(rng.uniform(-30, 30)), phase0=float(rng.uniform(0, 6.28)),
+                                     amplitude=amp0 * float(10 ** rng.uniform(-0.3, 0.3))))
+            t += (2.4615 if m < 4 else 4.923) + float(rng.choice([0.0, 0.0, 0.35, -0.4]))      # next slot, a gap, or an overlap
+        t_end = max(t_end, t)
+    esn0 = float(rng.uniform(3, 25))
+    x = O.render(int(sr * (t_end + 0.4)), sr, CF, frames, noise_sigma=O.noise_sigma(amp0, sr, esn0), seed=seed)
+    return freqs, x
+
+
 HOSTILE = ("collision", "equal_power_collision", "cfo_plus_70", "cfo_minus_45", "clipped", "cut_at_end", "starts_mid_frame",
            "adjacent_interferer", "dc_and_weak")
 
@@ -409,6 +432,24 @@ def case_frontend_stream(lib, sr, freqs, plan, dur, batch, esn0=20.0, seed=31, p
     for name in ("agc", "mf", "eq"):
         a, b = fe.checkpoint(name), p.capture(0, name)
         assert a.size == b.size and rel(a, b) < TOL_DEMOD, name
+    fe.close()
+    return len(got)
+
+
+def case_random_job(lib, seed, sr=250000, batch=5):
+    """the kernels on a seeded random job (random_scenario): PDUs, positions, counters equal the oracle's"""
+    freqs, x = random_scenario(seed, sr)
+    p = run_oracle(sr, freqs, x, A.SFMT_CF32)
+    ref = p.pdus()
+    fe = A.Frontend(sr, CF, freqs, max_blocks_per_batch=batch, lib=lib)
+    fe.push(x)
+    fe.flush()
+    got = fe.pdus()
+    compare_pdus(got, ref)
+    for c in range(len(freqs)):
+        assert fe.stats(c) == p.stats(c)
+    check_counters(fe, p, freqs, ref)
+    check_front(got)
     fe.close()
     return len(got)
 

@@ -69,6 +69,12 @@ def test_hostile_captures_follow_the_oracle(sim, name):
     K.case_hostile(sim, name)
 
 
+@pytest.mark.parametrize("seed", [11, 15])
+def test_random_jobs_follow_the_oracle(sim, seed):
+    # two of the seeded random jobs of test_oracle_hfdl_ref.py::test_reference_hfdl_equals_oracle_on_random_jobs
+    assert K.case_random_job(sim, seed) >= 2
+
+
 def test_front_parser(sim):
     K.case_front_parser(sim)
 

@@ -138,6 +138,22 @@ def test_reference_hfdl_equals_oracle_on_hostile_captures(name):
     p.close()
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_reference_hfdl_equals_oracle_on_random_jobs(seed):
+    """differential test: seeded random jobs (channels, frames per channel, modes, PDU kinds, carrier offsets, amplitudes,
+    slot gaps / overlaps, Es/N0 3-25 dB) through the reference's own code and through the oracle"""
+    freqs, x = K.random_scenario(seed, SR)
+    r, p = run_both(SR, freqs, x)
+    rp, _ = assert_same_pdus(r, p, freqs)
+    assert_same_taps(r, p)
+    for c, f in enumerate(freqs):
+        a1, a2, m1, frames = p.stats(c)
+        assert r.stat(f, "demod.preamble.A2_found") == a2 and r.stat(f, "demod.preamble.M1_found") == m1
+        assert r.stat(f, "demod.preamble.errors.M1_not_found") == p.m1_not_found(c)
+    r.close()
+    p.close()
+
+
 def test_reference_multichannel_back_to_back_and_raw_formats():
     sr = 250000
     freqs = [10021000, 10063000, 10090000]
