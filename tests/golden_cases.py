@@ -23,8 +23,8 @@ def checksum(raw):
     return int(np.bitwise_xor.reduce(raw.view(np.uint16).astype(np.uint64) * np.arange(1, raw.size + 1, dtype=np.uint64) % 65521))
 
 
-def capture_of(G):
-    """-> CS16 capture (int16 I/Q pairs) of a fixture, regenerated from its plan"""
+def capture_of(G, verify=True):
+    """-> CS16 capture (int16 I/Q pairs) of a fixture, regenerated from its plan (verify: against the recorded checksum)"""
     if "plan" not in G:                 # cfg1_pdus.json: the capture of b200_cases.make_capture
         import b200_cases as K
         x, _ = K.make_capture(G["sample_rate"], G["freqs"], G["modes"], G["dur"], seed=G["seed"])
@@ -35,7 +35,7 @@ def capture_of(G):
                      noise_sigma=O.noise_sigma(G["amplitude"], G["sample_rate"], G["esn0_db"]), seed=G["seed"])
     raw = np.zeros(2 * x.size, np.int16)
     O.lib().orc_quantize_cs16(x, x.size, raw)
-    assert checksum(raw) == G["int16_checksum"], "the capture of the fixture could not be regenerated"
+    assert not verify or checksum(raw) == G["int16_checksum"], "the capture of the fixture could not be regenerated"
     return raw
 
 
