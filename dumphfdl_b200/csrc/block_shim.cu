@@ -196,6 +196,7 @@ struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_h
 		fprintf(stderr, "hfdl_gpu_frontend_create: the host program does not export liquid-dsp's cbuffercf_size/read/release\n");
 		return NULL;
 	}
+	if(!freqs_hz || nfreq < 1) { fprintf(stderr, "hfdl_gpu_frontend_create: no channel frequencies\n"); return NULL; }      // (main.c:687-695 refuses to start without one)
 	if(ngpus < 1) ngpus = 1;
 	if(ngpus > nfreq) ngpus = nfreq;
 	if(device < 0 || device + ngpus > hfdl_b200_device_count()) {

@@ -7,7 +7,7 @@
  *   input thread  = file_input_thread (input-file.c:35-74): read, wait for ring space, complex_samples_produce
  *   wiring        = block_connect_one2one(input, gpu) / block_start / block_connection_one2one_shutdown / block_is_running
  * Prints one line per PDU as the reference's decoder thread would receive it (struct hfdl_pdu_metadata, pdu.h:8-17).
- * usage: block_driver <libref.so> <lib.so> <capture.cf32> <sample_rate> <centerfreq_hz> <ngpus> <freq_hz>... */
+ * usage: block_driver <libref.so> <lib.so> <capture.cf32 | badargs> <sample_rate> <centerfreq_hz> <ngpus> <freq_hz>... */
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -83,6 +83,34 @@ int main(int argc, char **argv) {
 	int nf = argc - 7;
 	int32_t freqs[512];
 	for(int i = 0; i < nf; i++) freqs[i] = atoi(argv[7 + i]);
+	if(strcmp(argv[3], "badargs") == 0) {
+		/* what main.c refuses before it builds its blocks (no frequency: main.c:687-695; check_frequency_span: main.c:214-226)
+		 * and what cannot be served (devices that are not there) must come back as NULL, and the accessors must take a NULL block */
+		int32_t far_away[2] = { freqs[0], cf + sr / 2 };
+		hfdl_b200_counters_t c;
+		float db;
+		int bad = 0;
+		bad += A.create(sr, cf, NULL, 0, 0, 1) != NULL;
+		bad += A.create(sr, cf, freqs, 0, 0, 1) != NULL;
+		bad += A.create(sr, cf, NULL, nf, 0, 1) != NULL;
+		bad += A.create(sr, cf, far_away, 2, 0, 1) != NULL;
+		bad += A.create(sr, cf, freqs, nf, 99, 1) != NULL;
+		bad += A.create(sr, cf, freqs, nf, -1, 1) != NULL;
+		bad += A.create(5000, cf, freqs, nf, 0, 1) != NULL;
+		bad += A.counters(NULL, 0, &c) != -1;
+		bad += A.nf_db(NULL, 0, &db) != -1;
+		A.destroy(NULL);
+		struct block *ok = A.create(sr, cf, freqs, nf, 0, 0);      /* ngpus < 1 means one */
+		bad += ok == NULL;
+		if(ok) {
+			bad += ok->consumer.type != CONSUMER_SINGLE || ok->producer.type != PRODUCER_NONE || ok->thread_routine == NULL || ok->running;
+			bad += A.counters(ok, nf, &c) != -1 || A.counters(ok, -1, &c) != -1 || A.counters(ok, 0, NULL) != -1;
+			bad += A.counters(ok, 0, &c) != 0 || c.freq != freqs[0] || c.frames_processed != 0;
+			A.destroy(ok);                                         /* never connected, never started */
+		}
+		printf("BADARGS %d\n", bad);
+		return bad ? 1 : 0;
+	}
 	struct input in;
 	memset(&in, 0, sizeof(in));
 	in.fh = fopen(argv[3], "rb");

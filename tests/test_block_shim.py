@@ -64,6 +64,16 @@ def run_driver(libpath, sr, freqs, modes, dur, seed, ngpus=1, env=None):
     return len(got)
 
 
+def test_block_wrapper_error_behaviour_host_emulation():
+    """hfdl_gpu_frontend_create refuses what main.c refuses before it builds its blocks (no frequency, a channel outside the
+    capture's span, main.c:214-226,687-695) and devices that are not there; the accessors take a NULL block and bad indices"""
+    subprocess.run(["make", "-s", "-C", os.path.join(HERE, "cusim"), "all"], check=True)
+    O.reflib()
+    out = subprocess.run([os.path.join(HERE, "block_driver"), LIBREF, os.path.join(HERE, "cusim", "libhfdl_cusim.so"), "badargs",
+                          "250000", str(K.CF), "1", "10063000", "9952000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "BADARGS 0" in out.stdout, (out.stdout, out.stderr[-2000:])
+
+
 def test_block_contract_host_emulation():
     lib = os.path.join(HERE, "cusim", "libhfdl_cusim.so")
     assert run_driver(lib, 250000, [10063000, 9952000], [1, 2], 3.3, seed=31) == 2
