@@ -23,6 +23,13 @@ def test_fft_one_and_two_pass(sim):
     K.case_fft(sim, [64, 2048, 8192, 32768])
 
 
+def test_fft_every_power_of_two_plan(sim):
+    # every FFT size fastddc_init can ask for (2^15 at 250 ksps ... 2^23 at 60 Msps) and the smaller ones the stage entry
+    # accepts: one-, two- and three-pass plans with every pass length make_plan produces (frontend.cu)
+    K.case_fft(sim, [1 << k for k in range(6, 19)], batch=2, seed=11)
+    K.case_fft(sim, [1 << k for k in range(19, 24)], batch=1, seed=12)
+
+
 def test_viterbi_bitexact(sim):
     K.case_viterbi(sim, [540, 1080], frames=2)
 
