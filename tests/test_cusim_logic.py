@@ -43,6 +43,13 @@ def test_frontend_cfg1_cs16(sim):
     assert K.case_frontend(sim, 250000, [10063000], [1], 3.2, sfmt=A.SFMT_CS16, batch=4) == 1
 
 
+def test_frontend_other_sample_rates(sim):
+    # geometries between the BASELINE configurations: 1.024 Msps (N = 2^18 with M = 4096, resampler 0.675) and 768 ksps
+    # (N = 2^17, M = 2048, resampler 0.9), channels near the band edge
+    assert K.case_frontend(sim, 1024000, [K.CF + 401000], [2], 3.2, sfmt=A.SFMT_CS16, batch=3, seed=12, tol_ddc=2e-4) == 1
+    assert K.case_frontend(sim, 768000, [K.CF - 333000], [1], 3.2, batch=3, seed=13) == 1
+
+
 def test_frontend_two_channels_ragged_cf32(sim):
     assert K.case_frontend(sim, 250000, [10063000, 9952000], [3, 0], 3.2, batch=3, ragged=True, seed=5) == 2
 
