@@ -201,6 +201,22 @@ def test_reference_cfg2_geometry_two_megasamples():
     p.close()
 
 
+@pytest.mark.parametrize("sr", [768000, 1024000, 2400000, 5000000])
+def test_reference_other_sample_rates(sr):
+    """geometries between the BASELINE configurations (fastddc_init picks M = 2048 or 4096 and resampler rates from 0.55 to
+    0.9 depending on the rate): reference end to end == oracle, taps bit-identical"""
+    freqs = [CF - int(0.41 * sr) // 1000 * 1000, CF + 63000]
+    pd = [O.make_pdu(m, m % 2, 190 + m) for m in (2, 5)]
+    frames = [O.tx_frame(f, m, 0.1 + 0.05 * i, pd[i], cfo_hz=5.0 * i - 3, phase0=i, amplitude=0.08) for i, (f, m) in enumerate(zip(freqs, (2, 5)))]
+    x = O.render(int(sr * 5.4), sr, CF, frames, noise_sigma=O.noise_sigma(0.08, sr, 18.0), seed=14)
+    r, p = run_both(sr, freqs, x, taps=True)
+    rp, _ = assert_same_pdus(r, p, freqs)
+    assert sorted(q.data() for q in rp) == sorted(pd)
+    assert_same_taps(r, p)
+    r.close()
+    p.close()
+
+
 def test_reference_cfg3_geometry_twenty_megasamples_cs16():
     # BASELINE config 3 geometry as bench.py runs it (20 Msps CS16: N = 2^22, M = 4096, 1792 outputs per block, resampler
     # 0.55296): the reference's input-helpers.c conversion + fft.c + fastddc.c + hfdl.c end to end vs the oracle
