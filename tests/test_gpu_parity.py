@@ -316,3 +316,22 @@ def test_no_cpu_fallback_symbols(lib):
     import subprocess
     out = subprocess.run(["nm", "-D", hb.LIB_PATH], capture_output=True, text=True).stdout
     assert "orc_" not in out and "hfdl_b200_create" in out
+
+
+# Added after the GPU time of round 2 was spent: green under host emulation (test_cusim_logic.py), not yet run on a GPU, so
+# they do not gate the suite until they have been seen there once (HFDL_B200_EXTRA=1 pytest tests -m gpu).  DESIGN.md 4
+# describes the one kind of event (a timing-arm / slicer decision on a float boundary) that may need a tolerance here.
+extra = pytest.mark.skipif(not os.environ.get("HFDL_B200_EXTRA"), reason="opt-in: HFDL_B200_EXTRA=1 (not yet run on a GPU)")
+
+
+@extra
+@pytest.mark.parametrize("name", K.HOSTILE)
+def test_hostile_captures_follow_the_oracle(lib, name):
+    K.case_hostile(lib, name)
+
+
+@extra
+@pytest.mark.parametrize("seed", [0, 2, 5, 11, 15])
+def test_random_jobs_follow_the_oracle(lib, seed):
+    assert K.case_random_job(lib, seed) >= 2
+
