@@ -25,6 +25,7 @@ The synthetic capture and the list of transmitted PDUs come from the HFDL transm
 (oracle/orc_tx.c via tests/orclib.py): input generation and the exactness check of the decoded PDUs, outside every timed
 region and never on the product path.  The only oracle/ code that is TIMED is the cpu_baseline / --impl reference leg."""
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -258,7 +259,8 @@ def cpu_reference_setup(O, W, P):
         kind = "reference"
         fft_threads = max(1, min(cores, 8))          # --fft-threads (main.c:438, fft.h:15 default 4); the channel threads are one per channel
         p = O.RefPipeline(W["sr"], CF, P["freqs"], sfmt=SFMT[W["sfmt"]]["code"], fft_threads=fft_threads, fast=True)
-        backend = {0: "oracle FFT (persistent pool) as the fftw3f stand-in", 1: "fftw3f", 3: "fftw3f + fftw3f_threads"}[fast.ref_fft_backend()]
+        backend = {0: "oracle FFT (persistent pool) as the fftw3f stand-in", 1: "fftw3f", 3: "fftw3f + fftw3f_threads",
+                   4: "cache-blocked four-step FFT on a persistent worker pool (oracle/ref_shim/fft4step.c) as the fftw3f + fftw3f_threads stand-in"}[fast.ref_fft_backend()]
         desc = ("the reference's own block.c + fft.c + fastddc.c (all-bin fold) + hfdl.c + libfec/viterbi27_port.c compiled where they lie "
                 "(oracle/_ref/libref_fast.so, -O3 -ffast-math), wired as main.c does: 1 fft thread with %d FFT workers + %d channel threads on a %d-core host; "
                 "FFT backend: %s; liquid-dsp objects served by the oracle's restatement (liquid-dsp not installed)" % (fft_threads, W["nch"], cores, backend))
@@ -277,12 +279,20 @@ def fft_share(O, W, isz, per_block_s):
         n = g.fft_size
         x = (np.random.default_rng(1).standard_normal(n) + 0j).astype(np.complex64)
         o = np.zeros(n, np.complex64)
-        L = O.lib(True)
-        L.orc_fft_set_threads(max(1, min(os.cpu_count() or 1, 8)))
-        L.orc_fft(x, o, n, 1)
+        R = O.reflib_fast()
+        if R is not None and hasattr(R, "ref_fft_run"):          # the backend the reference arm really used (fftw3f or its stand-in)
+            cfp = np.ctypeslib.ndpointer(np.complex64, flags="C")
+            R.ref_fft_run.argtypes = [cfp, cfp, ctypes.c_int32, ctypes.c_int32]
+            R.csdr_fft_init(max(1, min(os.cpu_count() or 1, 8)))          # as cpu_reference_setup asked for (no effect once the pool runs)
+            run = lambda: R.ref_fft_run(x, o, n, 1)
+        else:
+            L = O.lib(True)
+            L.orc_fft_set_threads(max(1, min(os.cpu_count() or 1, 8)))
+            run = lambda: L.orc_fft(x, o, n, 1)
+        run()
         t0 = time.perf_counter()
         for _ in range(3):
-            L.orc_fft(x, o, n, 1)
+            run()
         return (time.perf_counter() - t0) / 3 / per_block_s
     except Exception:
         return None

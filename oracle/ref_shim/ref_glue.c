@@ -14,6 +14,11 @@
 
 void orc_fft(const float complex *in, float complex *out, int n, int dir);
 void orc_fft_set_threads(int nthreads);
+/* timing build only (REF_TIMING_BUILD, libref_fast.so): cache-blocked four-step FFT with a worker pool for the large
+ * transforms, ref_shim/fft4step.c; the parity build keeps orc_fft so that every tap stays bit-identical with the oracle */
+void fft4step(const float complex *in, float complex *out, int n, int dir);
+void fft4step_set_threads(int nthreads);
+int fft4step_usable(int n);
 
 typedef void *(*fftwf_plan_dft_1d_t)(int, void *, void *, int, unsigned);
 typedef void (*fftwf_execute_t)(void *);
@@ -44,13 +49,24 @@ static void probe_fftw(void) {
 		if(F.init_threads && F.with_nthreads) F.threads = 1;
 	}
 }
-/* 1: fftw3f (+2: with fftw3f_threads); 0: the oracle's FFT */
-int ref_fft_backend(void) { probe_fftw(); return F.ok ? (F.threads ? 3 : 1) : 0; }
+/* 1: fftw3f (+2: with fftw3f_threads); 0: the oracle's FFT; 4: the four-step FFT of the timing build */
+int ref_fft_backend(void) {
+	probe_fftw();
+	if(F.ok) return F.threads ? 3 : 1;
+#ifdef REF_TIMING_BUILD
+	return getenv("REF_NO_FFT4STEP") ? 0 : 4;           /* (A/B switch for the stand-in) */
+#else
+	return 0;
+#endif
+}
 
 void csdr_fft_init(int32_t thread_cnt) {                 /* fft_fftw.c:8-14 */
 	probe_fftw();
 	if(F.ok && F.threads) { F.init_threads(); F.with_nthreads(thread_cnt); }
 	orc_fft_set_threads(thread_cnt);
+#ifdef REF_TIMING_BUILD
+	fft4step_set_threads(thread_cnt);
+#endif
 }
 void csdr_fft_destroy() {}
 FFT_PLAN_T *csdr_make_fft_c2c(int32_t size, float complex *input, float complex *output, int32_t forward, int32_t benchmark) {
@@ -67,8 +83,18 @@ void csdr_destroy_fft_c2c(FFT_PLAN_T *plan) {
 	free(plan);
 }
 void csdr_fft_execute(FFT_PLAN_T *plan) {
+	const int dir = plan->plan == (void *)1 ? +1 : -1;
 	if(F.ok) F.exec(plan->plan);
-	else orc_fft(plan->input, plan->output, plan->size, plan->plan == (void *)1 ? +1 : -1);
+#ifdef REF_TIMING_BUILD
+	else if(fft4step_usable(plan->size) && ref_fft_backend() == 4) fft4step(plan->input, plan->output, plan->size, dir);
+#endif
+	else orc_fft(plan->input, plan->output, plan->size, dir);
+}
+/* direct entry for tests: one transform through whatever backend this build uses */
+void ref_fft_run(float complex *in, float complex *out, int32_t n, int32_t forward) {
+	FFT_PLAN_T *p = csdr_make_fft_c2c(n, in, out, forward, 0);
+	csdr_fft_execute(p);
+	csdr_destroy_fft_c2c(p);
 }
 /* fastddc.c declares is_integer as a C99 'inline' without an external definition */
 int32_t is_integer(float a) { return floorf(a) == a; }

@@ -176,3 +176,28 @@ def test_fcs_rules():
             assert L.orc_pdu_crc_good(p, p.size) == 1
             p[3] ^= 0x10
             assert L.orc_pdu_crc_good(p, p.size) == 0
+
+
+def test_timing_build_fft_standin_matches_numpy():
+    """oracle/_ref/libref_fast.so (the timed CPU baseline only): when fftw3f is not on the machine its large transforms run in
+    oracle/ref_shim/fft4step.c (cache-blocked four-step FFT on a worker pool) -- same unnormalised DFT, both signs, in place too"""
+    R = O.reflib_fast()
+    if R is None or not hasattr(R, "ref_fft_run"):
+        pytest.skip("oracle/_ref/libref_fast.so not built")
+    cfp = np.ctypeslib.ndpointer(np.complex64, flags="C")
+    R.ref_fft_run.argtypes = [cfp, cfp, C.c_int32, C.c_int32]
+    R.csdr_fft_init(4)
+    rng = np.random.default_rng(8)
+    for lg in (11, 12, 18, 19, 20, 22):
+        n = 1 << lg
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        y = np.zeros(n, np.complex64)
+        for fwd in (1, 0):
+            R.ref_fft_run(x, y, n, fwd)
+            ref = np.fft.fft(x.astype(np.complex128)) if fwd else np.fft.ifft(x.astype(np.complex128)) * n
+            assert np.linalg.norm(y - ref) / np.linalg.norm(ref) < 5e-7, (lg, fwd)
+        R.ref_fft_run(x, y, n, 1)
+        z = x.copy()
+        R.ref_fft_run(z, z, n, 1)                       # in place == out of place
+        assert np.array_equal(z.view(np.uint32), y.view(np.uint32))
+
