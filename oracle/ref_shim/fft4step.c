@@ -179,11 +179,13 @@ void fft4step_set_threads(int n) { if(!G.started) G.nth = n < 1 ? 1 : (n > MAXT 
 int fft4step_usable(int n) { return n >= (1 << 19) && n <= (1 << 24) && (n & (n - 1)) == 0; }
 
 /* (the reference has one fft thread; fft_channelizer_create runs before the threads start) */
-void fft4step(const cf32 *in, cf32 *out, int N, int dir) {
+/* returns 0 without doing anything when another transform is in flight (the channel blocks are created by several threads
+ * at once, each with its own tap-spectrum FFT: those callers run the streaming FFT on their own thread instead of queueing) */
+int fft4step(const cf32 *in, cf32 *out, int N, int dir) {
 	static pthread_mutex_t busy = PTHREAD_MUTEX_INITIALIZER;
 	int lg = 0;
 	while((1 << lg) < N) lg++;
-	pthread_mutex_lock(&busy);                          /* (a second caller simply waits its turn) */
+	if(pthread_mutex_trylock(&busy) != 0) return 0;
 	pthread_mutex_lock(&G.m);
 	if(!G.started) {                                    /* nth - 1 workers: the calling thread is the nth */
 		if(G.nth < 1) G.nth = 1;
@@ -205,4 +207,5 @@ void fft4step(const cf32 *in, cf32 *out, int N, int dir) {
 	while(G.pending > 0) pthread_cond_wait(&G.done, &G.m);
 	pthread_mutex_unlock(&G.m);
 	pthread_mutex_unlock(&busy);
+	return 1;
 }

@@ -16,7 +16,7 @@ void orc_fft(const float complex *in, float complex *out, int n, int dir);
 void orc_fft_set_threads(int nthreads);
 /* timing build only (REF_TIMING_BUILD, libref_fast.so): cache-blocked four-step FFT with a worker pool for the large
  * transforms, ref_shim/fft4step.c; the parity build keeps orc_fft so that every tap stays bit-identical with the oracle */
-void fft4step(const float complex *in, float complex *out, int n, int dir);
+int fft4step(const float complex *in, float complex *out, int n, int dir);      /* 0: busy, nothing done */
 void fft4step_set_threads(int nthreads);
 int fft4step_usable(int n);
 
@@ -86,7 +86,7 @@ void csdr_fft_execute(FFT_PLAN_T *plan) {
 	const int dir = plan->plan == (void *)1 ? +1 : -1;
 	if(F.ok) F.exec(plan->plan);
 #ifdef REF_TIMING_BUILD
-	else if(fft4step_usable(plan->size) && ref_fft_backend() == 4) fft4step(plan->input, plan->output, plan->size, dir);
+	else if(fft4step_usable(plan->size) && ref_fft_backend() == 4 && fft4step(plan->input, plan->output, plan->size, dir)) return;
 #endif
 	else orc_fft(plan->input, plan->output, plan->size, dir);
 }
