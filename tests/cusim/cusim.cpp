@@ -5,5 +5,5 @@ thread_local uint3_ t_threadIdx, t_blockIdx;
 thread_local dim3 t_blockDim, t_gridDim;
 thread_local BlockCtx *t_ctx;
 thread_local WarpCtx *t_warp;
-thread_local unsigned t_lane;
+thread_local unsigned t_lane, t_xpar;
 }

@@ -73,13 +73,13 @@ public:
 		}
 	}
 };
-struct WarpCtx { Barrier bar; uint64_t xch[32]; explicit WarpCtx(unsigned n) : bar(n) {} };
+struct WarpCtx { Barrier bar; uint64_t xch[2][32] = {}; explicit WarpCtx(unsigned n) : bar(n) {} };      // two exchange buffers, used alternately
 struct BlockCtx { Barrier *bar; std::vector<WarpCtx *> warps; unsigned char *dyn_smem; };
 extern thread_local uint3_ t_threadIdx, t_blockIdx;
 extern thread_local dim3 t_blockDim, t_gridDim;
 extern thread_local BlockCtx *t_ctx;
 extern thread_local WarpCtx *t_warp;
-extern thread_local unsigned t_lane;
+extern thread_local unsigned t_lane, t_xpar;
 
 template <typename F> void launch(dim3 grid, dim3 block, size_t smem, F body) {
 	unsigned nth = block.x * block.y * block.z;
@@ -93,7 +93,7 @@ template <typename F> void launch(dim3 grid, dim3 block, size_t smem, F body) {
 	}
 	ctx.dyn_smem = (unsigned char *)aligned_alloc(128, ((smem + 127) / 128 + 1) * 128);
 	auto worker = [&](unsigned tid) {
-		t_ctx = &ctx; t_warp = ctx.warps[tid / 32]; t_lane = tid % 32;
+		t_ctx = &ctx; t_warp = ctx.warps[tid / 32]; t_lane = tid % 32; t_xpar = 0;
 		t_blockDim = block; t_gridDim = grid;
 		t_threadIdx.x = tid % block.x; t_threadIdx.y = (tid / block.x) % block.y; t_threadIdx.z = tid / (block.x * block.y);
 		for(unsigned bz = 0; bz < grid.z; bz++)
@@ -113,13 +113,16 @@ template <typename F> void launch(dim3 grid, dim3 block, size_t smem, F body) {
 	for(auto w : ctx.warps) delete w;
 	free(ctx.dyn_smem);
 }
+// One barrier per exchange: every lane writes buffer p, all meet, every lane reads buffer p; the next exchange uses buffer
+// 1 - p, and buffer p is only written again two exchanges later -- after a barrier every lane reaches only once it has
+// finished reading here.  (All lanes of a warp take part in every exchange, so their parities stay in step.)
 template <typename T> static inline T shfl_any(T v, int src) {
 	static_assert(sizeof(T) <= 8, "shfl size");
 	uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
-	t_warp->xch[t_lane] = raw;
+	const unsigned p = t_xpar; t_xpar ^= 1u;
+	t_warp->xch[p][t_lane] = raw;
 	t_warp->bar.wait();
-	uint64_t got = t_warp->xch[src & 31];
-	t_warp->bar.wait();
+	uint64_t got = t_warp->xch[p][src & 31];
 	T r; memcpy(&r, &got, sizeof(T)); return r;
 }
 }  // namespace cusim
@@ -136,11 +139,11 @@ template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m, int 
 template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d, int w = 32) { int l = (int)cusim::t_lane, s = l + d; return cusim::shfl_any(v, (s & ~(w - 1)) != (l & ~(w - 1)) ? l : s); }
 template <typename T> static inline T __shfl_up_sync(unsigned, T v, int d, int = 32) { int s = (int)cusim::t_lane - d; return cusim::shfl_any(v, s < 0 ? (int)cusim::t_lane : s); }
 static inline unsigned __ballot_sync(unsigned, int pred) {
-	cusim::t_warp->xch[cusim::t_lane] = pred ? 1u : 0u;
+	const unsigned p = cusim::t_xpar; cusim::t_xpar ^= 1u;
+	cusim::t_warp->xch[p][cusim::t_lane] = pred ? 1u : 0u;
 	cusim::t_warp->bar.wait();
 	unsigned r = 0;
-	for(int i = 0; i < 32; i++) r |= (unsigned)(cusim::t_warp->xch[i] & 1u) << i;
-	cusim::t_warp->bar.wait();
+	for(int i = 0; i < 32; i++) r |= (unsigned)(cusim::t_warp->xch[p][i] & 1u) << i;
 	return r;
 }
 static inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
