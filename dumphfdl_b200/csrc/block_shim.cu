@@ -54,6 +54,8 @@ struct gpu_frontend {
 	hfdl_gpu_pdu_callback cb; void *cb_user;
 	struct timeval t_start;
 	int64_t delivered;
+	std::vector<int64_t> statsd_sent;              // per channel x 3: demod.preamble.* increments already forwarded to the host's statsd hook
+	struct timespec statsd_last;
 	// ngpus > 1, sharded spectrum (include/hfdl_b200.h): GPU d transforms its share of every batch's blocks for all
 	// channels, the pass-band slices change hands over NVLink (peer copies), GPU q demodulates channels q, q + ngpus, ...
 	bool sharded;
@@ -85,6 +87,31 @@ static void deliver(gpu_frontend *g) {
 			pdu_decoder_queue_push(m, octet_string_new(copy, (size_t)p.len), 0);
 		} else if(g->cb) {
 			g->cb(&p, g->cb_user);
+		}
+	}
+}
+
+// The reference fires statsd_increment_per_channel(freq, "demod.preamble.A2_found" / "M1_found" / "errors.M1_not_found") from its
+// channel threads (hfdl.c:818,828,840).  Here those events happen on the GPU; when the host program exports the hook (a
+// WITH_STATSD build of dumphfdl) the block thread forwards the increments about once a second and when it exits, so the
+// metrics of doc/STATSD_METRICS.md keep flowing.  The frame / LPDU counters are fired downstream by the host's own
+// pdu_decoder_thread, which is not replaced.
+static void forward_statsd(gpu_frontend *g, bool force) {
+	if(!statsd_counter_per_channel_increment) return;
+	struct timespec now;
+	clock_gettime(CLOCK_MONOTONIC, &now);
+	if(!force && (now.tv_sec - g->statsd_last.tv_sec) * 1000 + (now.tv_nsec - g->statsd_last.tv_nsec) / 1000000 < 1000) return;
+	g->statsd_last = now;
+	static char n_a2[] = "demod.preamble.A2_found", n_m1[] = "demod.preamble.M1_found", n_fail[] = "demod.preamble.errors.M1_not_found";
+	char *names[3] = { n_a2, n_m1, n_fail };      // (statsd.h:12-15: not const, the client may modify them)
+	if(g->statsd_sent.size() != (size_t)g->nfreq * 3) g->statsd_sent.assign((size_t)g->nfreq * 3, 0);
+	for(int k = 0; k < g->nfreq; k++) {
+		hfdl_b200_counters_t c;
+		if(hfdl_b200_channel_counters(g->fe[(size_t)(k % g->ngpus)], k / g->ngpus, &c) != 0) continue;
+		const int64_t cur[3] = { c.A2_found, c.M1_found, c.M1_not_found };
+		for(int i = 0; i < 3; i++) {
+			int64_t &sent = g->statsd_sent[(size_t)k * 3 + (size_t)i];
+			for(; sent < cur[i]; sent++) statsd_counter_per_channel_increment(c.freq, names[i]);
 		}
 	}
 }
@@ -182,9 +209,11 @@ static void *gpu_frontend_thread(void *ctx) {
 		for(int d = 0; d < g->ngpus && ok; d++) if(hfdl_b200_poll(g->fe[(size_t)d]) < 0) ok = false;
 		if(!ok) { fprintf(stderr, "hfdl_gpu_frontend: GPU processing failed\n"); break; }
 		deliver(g);
+		forward_statsd(g, false);
 	}
 	for(int d = 0; d < g->ngpus; d++) hfdl_b200_flush(g->fe[(size_t)d]);      // (sharded mode: nothing is buffered, this drains the pipelines)
 	deliver(g);
+	forward_statsd(g, true);
 	block->running = false;
 	return NULL;
 }
@@ -206,6 +235,7 @@ struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_h
 	gpu_frontend *g = new gpu_frontend();
 	memset(&g->block, 0, sizeof(g->block));
 	g->ngpus = ngpus; g->staging = NULL; g->cb = NULL; g->cb_user = NULL; g->delivered = 0;
+	g->statsd_last.tv_sec = 0; g->statsd_last.tv_nsec = 0;
 	g->device0 = device; g->nfreq = nfreq; g->recv_i = 0; g->blocks_done = 0; g->bmax = 0;
 	g->sharded = ngpus > 1 && nfreq % ngpus == 0 && !getenv("HFDL_B200_SHIM_BROADCAST");
 	g->direct = g->sharded && !getenv("HFDL_B200_SHIM_COPY");

@@ -33,6 +33,7 @@ static struct {
 	void (*produce)(struct circ_buffer *, float *, size_t);
 	unsigned int (*cb_space)(cbuffercf);
 	int (*pdu_count)(void);
+	long (*stat_count)(int32_t, const char *);
 	int (*pdu_get)(int, ref_pdu_t *);
 	struct block *(*create)(int32_t, int32_t, const int32_t *, int32_t, int32_t, int32_t);
 	void (*destroy)(struct block *);
@@ -76,7 +77,7 @@ int main(int argc, char **argv) {
 	SYM(hr, connect, "block_connect_one2one"); SYM(hr, disconnect, "block_disconnect_one2one"); SYM(hr, start, "block_start");
 	SYM(hr, shutdown, "block_connection_one2one_shutdown"); SYM(hr, is_running, "block_is_running");
 	SYM(hr, produce, "complex_samples_produce"); SYM(hr, cb_space, "cbuffercf_space_available");
-	SYM(hr, pdu_count, "ref_pdu_count"); SYM(hr, pdu_get, "ref_pdu_get");
+	SYM(hr, pdu_count, "ref_pdu_count"); SYM(hr, pdu_get, "ref_pdu_get"); SYM(hr, stat_count, "ref_stat_count");
 	SYM(h, create, "hfdl_gpu_frontend_create"); SYM(h, destroy, "hfdl_gpu_frontend_destroy");
 	SYM(h, counters, "hfdl_gpu_frontend_counters"); SYM(h, nf_db, "hfdl_gpu_frontend_noise_floor_db");
 	int32_t sr = atoi(argv[4]), cf = atoi(argv[5]), ngpus = atoi(argv[6]);
@@ -144,6 +145,10 @@ int main(int argc, char **argv) {
 				(long long)c.frames_processed, (long long)c.frames_good, (long long)c.frames_bad_fcs, (long long)c.frames_air2gnd, (long long)c.frames_gnd2air,
 				(long long)c.lpdus_processed, (long long)c.lpdus_good);
 	}
+	/* what the host program's statsd hook (statsd_counter_per_channel_increment, captured in libref.so) received from the block */
+	for(int i = 0; i < nf; i++)
+		printf("STATSD %d %lld %lld %lld\n", freqs[i], (long long)A.stat_count(freqs[i], "demod.preamble.A2_found"),
+			(long long)A.stat_count(freqs[i], "demod.preamble.M1_found"), (long long)A.stat_count(freqs[i], "demod.preamble.errors.M1_not_found"));
 	printf("POLLS %d\n", polls);
 	fflush(stdout);
 	A.disconnect(&in.block, fe);

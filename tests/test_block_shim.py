@@ -60,6 +60,10 @@ def run_driver(libpath, sr, freqs, modes, dur, seed, ngpus=1, env=None):
         assert cnt[f][3] == len(mine) and cnt[f][4] == sum(1 for v in fr if v[0] == 0) and cnt[f][5] == sum(1 for v in fr if v[0] == 1)
         assert cnt[f][6] == sum(1 for v in fr if v[0] == 0 and v[1] == 1) and cnt[f][7] == sum(1 for v in fr if v[0] == 0 and v[1] == 0)
         assert cnt[f][8] == sum(v[2] for v in fr) and cnt[f][9] == sum(v[3] for v in fr)
+    # ... and the demod.preamble.* increments the block forwarded to the host program's statsd hook (hfdl.c:818,828,840)
+    sd = {int(a[1]): [int(v) for v in a[2:]] for a in rows if a and a[0] == "STATSD"}
+    for f in freqs:
+        assert sd[f] == cnt[f][0:3], (f, sd[f], cnt[f][0:3])
     assert int([a for a in rows if a and a[0] == "POLLS"][0][1]) > 0
     return len(got)
 
