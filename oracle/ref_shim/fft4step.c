@@ -151,12 +151,20 @@ static void work(void) {
 static void *worker(void *arg) {
 	/* one core per worker: woken threads otherwise start on the waker's core and wait for the load balancer, which costs
 	 * more than the whole transform */
-	const long t = (long)arg, ncpu = sysconf(_SC_NPROCESSORS_ONLN);
-	if(ncpu > 1 && !getenv("REF_FFT_NO_PIN")) {
-		cpu_set_t cs;
-		CPU_ZERO(&cs);
-		CPU_SET((int)((t + 1) % ncpu), &cs);
-		pthread_setaffinity_np(pthread_self(), sizeof(cs), &cs);
+	const long t = (long)arg;
+	cpu_set_t allowed;
+	if(!getenv("REF_FFT_NO_PIN") && sched_getaffinity(0, sizeof(allowed), &allowed) == 0 && CPU_COUNT(&allowed) > 1) {
+		int want = (int)((t + 1) % CPU_COUNT(&allowed));           /* the (t+1)-th CPU this process may run on (cgroup cpusets) */
+		for(int c = 0; c < CPU_SETSIZE; c++) {
+			if(!CPU_ISSET(c, &allowed)) continue;
+			if(want-- == 0) {
+				cpu_set_t cs;
+				CPU_ZERO(&cs);
+				CPU_SET(c, &cs);
+				pthread_setaffinity_np(pthread_self(), sizeof(cs), &cs);
+				break;
+			}
+		}
 	}
 	unsigned long seen = 0;
 	for(;;) {
