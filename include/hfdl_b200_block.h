@@ -52,7 +52,10 @@ struct block {
 #endif
 
 /* Returns &obj->block with consumer = { CONSUMER_SINGLE, min_ru = fft_size }, producer = { PRODUCER_NONE } and
- * thread_routine set; NULL on error.  The ring carries CF32 (what complex_samples_produce writes).
+ * thread_routine set; NULL on error (no channel, a channel outside the capture's span as main.c:214-226 checks it, devices
+ * that are not there, a host program without liquid-dsp's cbuffercf).  The ring carries CF32 (what complex_samples_produce
+ * writes).  When the host program exports statsd_counter_per_channel_increment (statsd.h:15, WITH_STATSD builds) the block
+ * thread forwards the demod.preamble.A2_found / M1_found / errors.M1_not_found increments of hfdl.c:818,828,840 to it.
  * ngpus >= 1: CUDA devices device .. device+ngpus-1 share the work; channel k runs on GPU k mod ngpus end to end, the
  * samples cross PCIe once and reach the other GPUs over NVLink (the reference's one2many broadcast, block.c:90-120). */
 struct block *hfdl_gpu_frontend_create(int32_t sample_rate, int32_t centerfreq_hz, const int32_t *freqs_hz,
